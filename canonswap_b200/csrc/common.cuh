@@ -1,0 +1,194 @@
+// Internal definitions shared by the canonswap_b200 kernels and host code (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <map>
+#include <stdexcept>
+
+namespace cs {
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CS_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      throw cs::Error(-2, std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " +    \
+                              __FILE__ + ":" + std::to_string(__LINE__));                  \
+  } while (0)
+
+#define CS_REQUIRE(cond, code, msg)                                                        \
+  do {                                                                                     \
+    if (!(cond)) throw cs::Error((code), std::string(msg) + " [" #cond "]");               \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// activation tensors: fp32, channels-last, explicit strides (in elements). Channel stride is 1.
+// 2-D tensors use D = 1. C is the logical channel count; buffers may carry zero pad channels.
+// ------------------------------------------------------------------------------------------
+struct Act {
+  float* p = nullptr;
+  int B = 0, D = 1, H = 0, W = 0, C = 0;
+  long sb = 0, sd = 0, sh = 0, sw = 0;
+  long pixels() const { return (long)B * D * H * W; }
+};
+
+inline Act make_act(float* p, int B, int D, int H, int W, int C, int Cstride = -1) {
+  Act a;
+  if (Cstride < 0) Cstride = C;
+  a.p = p; a.B = B; a.D = D; a.H = H; a.W = W; a.C = C;
+  a.sw = Cstride; a.sh = (long)W * a.sw; a.sd = (long)H * a.sh; a.sb = (long)D * a.sd;
+  return a;
+}
+
+// The 32-channel x 16-depth feature volume lives as [B,H,W,16,32]: a 2-D tensor with 512
+// channels ordered ch' = d*32 + c (the reference's view order is ch = c*16 + d).
+inline Act vol_as_3d(float* p, int B, int H, int W) {
+  Act a; a.p = p; a.B = B; a.D = 16; a.H = H; a.W = W; a.C = 32;
+  a.sd = 32; a.sw = 512; a.sh = (long)W * 512; a.sb = (long)H * W * 512;
+  return a;
+}
+inline Act vol_as_2d(float* p, int B, int H, int W) { return make_act(p, B, 1, H, W, 512); }
+// channel slice [c0, c0+C) of a channels-last tensor (zero-copy concat)
+inline Act slice_c(Act a, int c0, int C) { a.p += c0; a.C = C; return a; }
+
+// split-bf16 operand planes for the tcgen05 conv: value ~= hi + lo, channels padded to Cp
+struct Opd {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int B = 0, D = 1, H = 0, W = 0, Cp = 0;
+  long sb = 0, sd = 0, sh = 0, sw = 0;
+};
+
+enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_SIGMOID = 3 };
+
+__host__ __device__ inline float apply_act(float v, int kind, float slope) {
+  switch (kind) {
+    case ACT_RELU: return v > 0.f ? v : 0.f;
+    case ACT_LRELU: return v > 0.f ? v : v * slope;
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// packed convolution weights (device)
+struct ConvW {
+  int Cin = 0, Cout = 0, KD = 1, KH = 1, KW = 1;
+  float* w32 = nullptr;    // [taps][Cin][Cout]   (SIMT path)
+  float* bias = nullptr;   // [Cout] or null
+  // tcgen05 path: B operand, K-major sub-blocks [taps * Cin_p/KC][Cout_p][KC], hi and lo planes
+  __nv_bfloat16* whi = nullptr;
+  __nv_bfloat16* wlo = nullptr;
+  int Cin_p = 0, Cout_p = 0, KC = 0;
+  int taps() const { return KD * KH * KW; }
+};
+
+// conv epilogue: v = acc + bias; v = act(v); v += residual; v *= mult[pixel]
+struct Epilogue {
+  int act = ACT_NONE;
+  float slope = 0.f;
+  const float* residual = nullptr;   // same geometry/strides as the output
+  long rs_b = 0, rs_d = 0, rs_h = 0, rs_w = 0;
+  const float* mult = nullptr;       // [B, Do*Ho*Wo] per-pixel multiplier
+};
+
+// conv geometry
+struct ConvGeom {
+  int PD = 0, PH = 0, PW = 0;
+  int Do = 1, Ho = 0, Wo = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// input transform (the "prep" kernel): gather + normalise + modulate + activate
+// ------------------------------------------------------------------------------------------
+enum NormKind { NORM_NONE = 0, NORM_AFFINE_C = 1, NORM_STATS_BC = 2 };
+
+struct Prep {
+  // sources (concat along C: src0 channels first, then src1)
+  Act src0, src1;            // src1.p == nullptr when unused
+  int upshift = 0;           // nearest upsample of (h,w) by 2^upshift (applies to src0 only)
+  int pool2 = 0;             // 2x2 average pool of (h,w) (src0 only)
+  int norm = NORM_NONE;
+  const float* scale = nullptr;   // AFFINE_C: per-channel scale / shift. STATS_BC: optional gamma/beta per channel
+  const float* shift = nullptr;
+  const float* mean = nullptr;    // STATS_BC: [B,C]
+  const float* rstd = nullptr;
+  const float* gb = nullptr;      // SPADE: [pixels, 2*C] (gamma | beta), applied after normalisation
+  Act add;                        // residual added before activation (add.p == nullptr when unused); geometry of the output
+  int act = ACT_NONE;
+  float slope = 0.f;
+};
+
+// ------------------------------------------------------------------------------------------
+// bump arena for per-call scratch
+// ------------------------------------------------------------------------------------------
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, high = 0;
+  bool measuring = false;    // dry run: no memory, just count
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    if (off > high) high = off;
+    if (measuring) return reinterpret_cast<void*>(uintptr_t(0x1000) + a);   // fake, never dereferenced
+    if (off > cap) throw Error(-5, "workspace arena exhausted");
+    return base + a;
+  }
+  float* f32(size_t n) { return static_cast<float*>(alloc(n * sizeof(float))); }
+  __nv_bfloat16* bf16(size_t n) { return static_cast<__nv_bfloat16*>(alloc(n * 2)); }
+  size_t mark() const { return off; }
+  void reset(size_t m = 0) { off = m; }
+};
+
+struct Launcher {            // everything a kernel launch helper needs
+  cudaStream_t stream = nullptr;
+  bool dry = false;          // measuring pass: skip launches
+  int64_t* counter = nullptr;
+  int conv_impl = 0;         // 0 auto, 1 SIMT, 2 TC
+  void count() const { if (counter) ++*counter; }
+};
+
+inline void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw Error(-2, std::string("launch ") + what + ": " + cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel launch helpers (implemented in the .cu files)
+// ------------------------------------------------------------------------------------------
+// kernels_elem.cu
+void prep_f32(const Launcher& L, const Prep& p, Act out);                    // out: fp32 (strides from Act)
+void prep_planes(const Launcher& L, const Prep& p, Opd out, float* out32);   // split-bf16 planes (+ optional fp32 copy, stride = logical C)
+void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch);
+void adaptive_blend(const Launcher& L, const float* o2 /*[P,1024]*/, const float* mask /*[P]*/,
+                    const float* residual /*[P,512] or null*/, int relu, float* y /*[P,512]*/, long P);
+void nchw_to_cl(const Launcher& L, const float* src, float* dst, int B, int C, long S, int vol_perm);
+void cl_to_nchw(const Launcher& L, const float* src, float* dst, int B, int C, long S, int vol_perm, int Cstride);
+void ingest_u8(const Launcher& L, const uint8_t* src, float* dst, long n);
+void emit_image(const Launcher& L, const float* y /*[B,H,W,Cs] conv_img out, 12 valid*/, int Cs,
+                float* img /*[B,3,2H,2W] or null*/, uint8_t* u8 /*[B,2H,2W,3] or null*/, int B, int H, int W);
+// kernels_conv_simt.cu
+void conv_simt(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y);
+void conv_cout1(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom& g, int act, float* y /*[B*Do*Ho*Wo]*/);
+// kernels_motion.cu
+void dm_input(const Launcher& L, const Act& c4, const float* kp_driving, const float* kp_source, int K,
+              Act out /*[B,D,H,W,(K+1)*5 (+pad)]*/);
+void softmax_flow_warp(const Launcher& L, const Act& logits /*[B,D,H,W,K+1]*/, const float* kp_driving,
+                       const float* kp_source, int K, const float* vol /*[B,H,W,16,32]*/,
+                       float* out /*[B,H,W,16,32]*/, float* deformation /*[B,D,H,W,3] or null*/);
+void grid_sample3d_cl(const Launcher& L, const float* vol, const float* grid, float* out, int B, int D, int H, int W);
+// conv_tc.cu
+bool conv_tc_eligible(const ConvW& w, const ConvGeom& g, const Opd& x);
+void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y);
+
+}  // namespace cs

@@ -1,0 +1,124 @@
+// Context, packed-weight inventory and per-call helpers of the canonswap_b200 library.
+#pragma once
+#include "common.cuh"
+#include "../../include/canonswap_b200.h"
+
+namespace cs {
+
+constexpr int NUM_KP = 21;
+constexpr int HG_IN = (NUM_KP + 1) * 5;   // 110
+constexpr int HG_OUT = 32 + HG_IN;        // 142
+
+struct Affine {              // per-channel scale / shift (folded eval-mode BN, or GN gamma/beta)
+  float* scale = nullptr;
+  float* shift = nullptr;
+};
+
+struct ResBlock3dW {         // reference util.py:80-102
+  Affine bn1;                // pre-activation BN on the block input
+  ConvW conv1;               // norm2 folded in (post-conv), ReLU epilogue
+  ConvW conv2;
+};
+
+struct GnResBlockW {         // reference util.py:515-544
+  ConvW conv1, conv2;
+  Affine gn1, gn2;
+};
+
+struct ResBlock2dW {         // reference util.py:105-128 at 512 channels (volume channel order)
+  Affine bn1;
+  ConvW conv1;               // norm2 folded, LeakyReLU(0.01) epilogue
+  ConvW conv2;
+};
+
+struct AdaptiveConvW {       // reference adaptive_modulate.py:73-193
+  float* w_base = nullptr;   // [9][512][512] fp32 master (internal channel order both sides)
+  float* bias_param = nullptr;   // [512]
+  float* fc0_w = nullptr; float* fc0_b = nullptr;   // style MLP (rows of fc2 permuted to internal order)
+  float* fc2_w = nullptr; float* fc2_b = nullptr;
+  ConvW mask_conv;           // 512 -> 1, sigmoid
+  ConvW combined;            // per identity: Cout = 1024 = [W | W * s * demod], bias = [0 | bias_param]
+  float* style = nullptr;    // [512] per identity
+  float* demod = nullptr;    // [512] per identity
+};
+
+struct SpadeNormW {          // reference util.py:282-302
+  ConvW shared;              // label_nc(256) -> 128, ReLU
+  ConvW gamma_beta;          // 128 -> 2*C : gamma | beta stacked along Cout
+  int C = 0;
+};
+
+struct SpadeBlockW {         // reference util.py:305-344
+  int fin = 0, fout = 0, fmid = 0;
+  bool learned_shortcut = false;
+  SpadeNormW norm_0, norm_1, norm_s;
+  ConvW conv_0, conv_1, conv_s;    // spectral-norm sigma folded
+};
+
+struct Weights {
+  // F
+  ConvW f_first, f_down[2], f_second;
+  ResBlock3dW f_res[6];
+  // W
+  ConvW dm_compress;
+  ConvW hg_enc[5], hg_dec[5], hg_final, dm_mask, dm_occlusion;
+  ConvW w_third, w_fourth;
+  // swap
+  AdaptiveConvW ad[14];
+  ResBlock3dW t_res[6];
+  // refine
+  GnResBlockW r_gn1[3], r_gn3[3];
+  ResBlock2dW r_res2[3];
+  // G
+  ConvW g_fc, g_img;
+  SpadeBlockW g_blocks[8];
+};
+
+}  // namespace cs
+
+struct cs_ctx {
+  int device = 0, max_batch = 1, net_h = 0, net_w = 0, h = 0, w = 0;
+  std::string err;
+  bool weights_loaded = false, identity_set = false;
+  int conv_impl = 0, use_graph = 0;
+  int64_t launches = 0;
+  std::vector<void*> owned;        // device allocations owned by the ctx
+  size_t owned_bytes = 0;
+  cs::Arena arena;
+  cs::Weights W;
+  double* stats_scratch = nullptr; // [max_batch*512*2] double
+  void* dmalloc(size_t bytes) {
+    void* p = nullptr;
+    CS_CUDA(cudaMalloc(&p, bytes ? bytes : 256));
+    owned.push_back(p); owned_bytes += bytes;
+    return p;
+  }
+};
+
+namespace cs {
+
+struct Net {                 // per-call view
+  cs_ctx* ctx;
+  Launcher L;
+  Arena* A;
+  const Weights& W() const { return ctx->W; }
+};
+
+// weights.cu
+void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n);
+void set_identity(cs_ctx* ctx, const float* id_dev, cudaStream_t stream);
+ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt /*[Cout][Cin][taps]*/, const std::vector<float>* bias,
+                     int Cout, int Cin, int KD, int KH, int KW);
+void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream);   // derive the split-bf16 B operand from w32 (conv_tc.cu)
+
+// net.cu : stages on the internal (channels-last) layout
+void run_F(Net& n, const float* img_cl, int B, float* vol_out);
+void run_warp(Net& n, const float* vol_in, const float* kp_source, const float* kp_driving, int B,
+              float* vol_out, float* occ, float* deformation);
+void run_warp_out(Net& n, const float* vol_in, const float* occ, int B, float* out256);
+void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks);
+void run_refine(Net& n, const float* vol_in, int B, float* vol_out);
+void run_spade(Net& n, const float* feat256, int B, float* img_nchw, uint8_t* img_u8);
+Act conv_layer(Net& n, const Prep* prep, const Act& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act* out);
+
+}  // namespace cs

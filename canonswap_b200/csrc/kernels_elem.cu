@@ -1,0 +1,316 @@
+// Element-wise / reduction / layout kernels of the generator hot path (HBM-bound, sm_100a).
+//   prep            gather (+nearest-up / 2x2 avg-pool / concat) -> normalise -> SPADE modulate -> (+add) -> act
+//                   -> fp32 channels-last and/or split-bf16 operand planes for the tcgen05 conv
+//   instance_stats  per-(b,c) mean / rstd (InstanceNorm2d, GroupNorm(32,32)), reference util.py:286,521
+//   adaptive_blend  mask*out_mod + (1-mask)*out_std, reference adaptive_modulate.py:186
+//   nchw<->cl       layout shims at the per-stage C-ABI boundary
+//   ingest / emit   u8 HWC -> fp32 (can_swap_e2e.py:147-163);  sigmoid + PixelShuffle(2) + u8 (spade_generator.py:56-57, can_swap_e2e.py:314-322)
+#include "common.cuh"
+
+namespace cs {
+
+// ------------------------------------------------------------------------------------------
+// prep
+// ------------------------------------------------------------------------------------------
+struct PrepK {
+  const float* s0; long s0b, s0d, s0h, s0w; int C0;
+  const float* s1; long s1b, s1d, s1h, s1w; int C1;
+  int upshift, pool2, norm, act; float slope;
+  const float *scale, *shift, *mean, *rstd, *gb, *add; long ab, ad, ah, aw;
+  int B, D, H, W;           // output geometry
+  int Cl;                   // logical channels C0 + C1
+  int Cout;                 // channels written (>= Cl, pad written as zero)
+  // outputs
+  float* o32; long ob, od, oh, ow;
+  __nv_bfloat16 *ohi, *olo; long pb, pd, ph, pw;
+};
+
+__global__ void __launch_bounds__(256) prep_kernel(PrepK k) {
+  long total = (long)k.B * k.D * k.H * k.W * k.Cout;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % k.Cout);
+    long pix = idx / k.Cout;
+    int w = (int)(pix % k.W); long t = pix / k.W;
+    int h = (int)(t % k.H); t /= k.H;
+    int d = (int)(t % k.D); int b = (int)(t / k.D);
+    float v = 0.f;
+    if (c < k.Cl) {
+      if (c < k.C0) {
+        if (k.pool2) {
+          const float* q = k.s0 + b * k.s0b + d * k.s0d + (2 * h) * k.s0h + (2 * w) * k.s0w + c;
+          v = 0.25f * ((q[0] + q[k.s0w]) + (q[k.s0h] + q[k.s0h + k.s0w]));
+        } else {
+          v = k.s0[b * k.s0b + d * k.s0d + (long)(h >> k.upshift) * k.s0h + (long)(w >> k.upshift) * k.s0w + c];
+        }
+        if (k.norm == NORM_AFFINE_C) {
+          v = v * k.scale[c] + k.shift[c];
+        } else if (k.norm == NORM_STATS_BC) {
+          v = (v - k.mean[b * k.C0 + c]) * k.rstd[b * k.C0 + c];
+          if (k.scale) v = v * k.scale[c] + k.shift[c];
+        }
+        if (k.gb) {
+          const float* g = k.gb + pix * (2L * k.C0);
+          v = v * (1.f + g[c]) + g[k.C0 + c];
+        }
+      } else {
+        v = k.s1[b * k.s1b + d * k.s1d + h * k.s1h + w * k.s1w + (c - k.C0)];
+      }
+      if (k.add) v += k.add[b * k.ab + d * k.ad + h * k.ah + w * k.aw + c];
+      v = apply_act(v, k.act, k.slope);
+    }
+    if (k.o32 && c < k.Cl) k.o32[b * k.ob + d * k.od + h * k.oh + w * k.ow + c] = v;
+    if (k.ohi) {
+      long o = b * k.pb + d * k.pd + h * k.ph + w * k.pw + c;
+      __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      k.ohi[o] = hi;
+      k.olo[o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  }
+}
+
+static PrepK make_prepk(const Prep& p) {
+  PrepK k{};
+  k.s0 = p.src0.p; k.s0b = p.src0.sb; k.s0d = p.src0.sd; k.s0h = p.src0.sh; k.s0w = p.src0.sw; k.C0 = p.src0.C;
+  k.s1 = p.src1.p; k.s1b = p.src1.sb; k.s1d = p.src1.sd; k.s1h = p.src1.sh; k.s1w = p.src1.sw;
+  k.C1 = p.src1.p ? p.src1.C : 0;
+  k.upshift = p.upshift; k.pool2 = p.pool2; k.norm = p.norm; k.act = p.act; k.slope = p.slope;
+  k.scale = p.scale; k.shift = p.shift; k.mean = p.mean; k.rstd = p.rstd; k.gb = p.gb;
+  k.add = p.add.p; k.ab = p.add.sb; k.ad = p.add.sd; k.ah = p.add.sh; k.aw = p.add.sw;
+  k.Cl = k.C0 + k.C1;
+  return k;
+}
+
+static void launch_prep(const Launcher& L, PrepK& k) {
+  L.count();
+  if (L.dry) return;
+  long total = (long)k.B * k.D * k.H * k.W * k.Cout;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 32) blocks = 148L * 32;
+  prep_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+  check_launch("prep");
+}
+
+void prep_f32(const Launcher& L, const Prep& p, Act out) {
+  PrepK k = make_prepk(p);
+  CS_REQUIRE(out.C == k.Cl, -1, "prep_f32: channel mismatch");
+  k.B = out.B; k.D = out.D; k.H = out.H; k.W = out.W; k.Cout = k.Cl;
+  k.o32 = out.p; k.ob = out.sb; k.od = out.sd; k.oh = out.sh; k.ow = out.sw;
+  launch_prep(L, k);
+}
+
+void prep_planes(const Launcher& L, const Prep& p, Opd out, float* out32) {
+  PrepK k = make_prepk(p);
+  CS_REQUIRE(out.Cp >= k.Cl, -1, "prep_planes: padded channels too small");
+  k.B = out.B; k.D = out.D; k.H = out.H; k.W = out.W; k.Cout = out.Cp;
+  k.ohi = out.hi; k.olo = out.lo; k.pb = out.sb; k.pd = out.sd; k.ph = out.sh; k.pw = out.sw;
+  if (out32) {
+    k.o32 = out32; k.ow = k.Cl; k.oh = (long)out.W * k.ow; k.od = (long)out.H * k.oh; k.ob = (long)out.D * k.od;
+  }
+  launch_prep(L, k);
+}
+
+// ------------------------------------------------------------------------------------------
+// instance statistics: scratch[b][c][2] double accumulators, then finalize
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restrict__ x, long sb, long sd, long sh, long sw,
+                                                           int D, int H, int W, int C, int CT, int chunk,
+                                                           double* __restrict__ acc) {
+  __shared__ float red[2][256];
+  int b = blockIdx.y;
+  long S = (long)D * H * W;
+  long p0 = (long)blockIdx.x * chunk;
+  long p1 = p0 + chunk < S ? p0 + chunk : S;
+  int rows = 256 / CT;
+  int r = threadIdx.x / CT, cl = threadIdx.x % CT;
+  for (int c = cl; c < C; c += CT) {       // uniform trip count across the block (CT divides into C rounds)
+    float s1 = 0.f, s2 = 0.f;
+    for (long p = p0 + r; p < p1; p += rows) {
+      int w = (int)(p % W); long t = p / W; int h = (int)(t % H); int d = (int)(t / H);
+      float v = x[b * sb + d * sd + h * sh + w * sw + c];
+      s1 += v; s2 += v * v;
+    }
+    red[0][threadIdx.x] = s1; red[1][threadIdx.x] = s2;
+    __syncthreads();
+    if (r == 0) {
+      double a1 = 0.0, a2 = 0.0;
+      for (int i = 0; i < rows; ++i) { a1 += red[0][i * CT + cl]; a2 += red[1][i * CT + cl]; }
+      atomicAdd(&acc[((long)b * C + c) * 2 + 0], a1);
+      atomicAdd(&acc[((long)b * C + c) * 2 + 1], a2);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void stats_finalize_kernel(const double* __restrict__ acc, float* __restrict__ mean, float* __restrict__ rstd,
+                                      int n, double inv_count, float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m = acc[2 * i] * inv_count;
+  double var = acc[2 * i + 1] * inv_count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch) {
+  L.count(); L.count();
+  if (L.dry) return;
+  int C = x.C;
+  int CT = 1;
+  while (CT * 2 <= C && CT * 2 <= 256) CT *= 2;
+  // when C is not a multiple of CT the strided loop `c = cl; c < C; c += CT` has a non-uniform trip
+  // count, which would break the __syncthreads above; require exact division.
+  CS_REQUIRE(C % CT == 0, -1, "instance_stats: C must be a power of two multiple");
+  long S = (long)x.D * x.H * x.W;
+  int chunk = 2048;
+  int nchunks = (int)((S + chunk - 1) / chunk);
+  CS_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * x.B * C, L.stream));
+  dim3 grid(nchunks, x.B);
+  stats_partial_kernel<<<grid, 256, 0, L.stream>>>(x.p, x.sb, x.sd, x.sh, x.sw, x.D, x.H, x.W, C, CT, chunk, scratch);
+  check_launch("stats_partial");
+  int n = x.B * C;
+  stats_finalize_kernel<<<(n + 127) / 128, 128, 0, L.stream>>>(scratch, mean, rstd, n, 1.0 / (double)S, eps);
+  check_launch("stats_finalize");
+}
+
+// ------------------------------------------------------------------------------------------
+// adaptive blend: o2 = [out_std(512) | out_mod(512)] per pixel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adaptive_blend_kernel(const float4* __restrict__ o2, const float* __restrict__ mask,
+                                                            const float4* __restrict__ residual, int relu,
+                                                            float4* __restrict__ y, long P) {
+  long total = P * 128;     // 512 channels / 4
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long pix = i >> 7; int q = (int)(i & 127);
+    float m = mask[pix];
+    float4 s = o2[pix * 256 + q], mo = o2[pix * 256 + 128 + q];
+    float4 v;
+    v.x = m * mo.x + (1.f - m) * s.x; v.y = m * mo.y + (1.f - m) * s.y;
+    v.z = m * mo.z + (1.f - m) * s.z; v.w = m * mo.w + (1.f - m) * s.w;
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (residual) { float4 r = residual[i]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+    y[i] = v;
+  }
+}
+
+void adaptive_blend(const Launcher& L, const float* o2, const float* mask, const float* residual, int relu, float* y, long P) {
+  L.count();
+  if (L.dry) return;
+  long blocks = (P * 128 + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  adaptive_blend_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(o2), mask,
+                                                               reinterpret_cast<const float4*>(residual), relu,
+                                                               reinterpret_cast<float4*>(y), P);
+  check_launch("adaptive_blend");
+}
+
+// ------------------------------------------------------------------------------------------
+// layout shims: [B,C,S] <-> [B,S,C'] with the optional volume permutation ch=c*16+d <-> ch'=d*32+c
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int vol_perm_fwd(int ch) { return (ch & 15) * 32 + (ch >> 4); }   // c*16+d -> d*32+c
+
+__global__ void __launch_bounds__(256) nchw_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                        int C, long S, int vol_perm, int Cstride) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.z;
+  long s0 = (long)blockIdx.x * 32; int c0 = blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    int c = c0 + i; long s = s0 + tx;
+    tile[i][tx] = (c < C && s < S) ? src[((long)b * C + c) * S + s] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    long s = s0 + i; int c = c0 + tx;
+    if (c < C && s < S) {
+      int cc = vol_perm ? vol_perm_fwd(c) : c;
+      dst[((long)b * S + s) * Cstride + cc] = tile[tx][i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cl_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                        int C, long S, int vol_perm, int Cstride) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.z;
+  long s0 = (long)blockIdx.x * 32; int c0 = blockIdx.y * 32;    // c0 indexes the channels-last (internal) channel
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    long s = s0 + i; int c = c0 + tx;
+    tile[i][tx] = (c < C && s < S) ? src[((long)b * S + s) * Cstride + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int ci = c0 + i; long s = s0 + tx;
+    if (ci < C && s < S) {
+      // internal channel ci = d*32+c  ->  reference channel c*16+d
+      int cr = vol_perm ? ((ci & 31) * 16 + (ci >> 5)) : ci;
+      dst[((long)b * C + cr) * S + s] = tile[tx][i];
+    }
+  }
+}
+
+void nchw_to_cl(const Launcher& L, const float* src, float* dst, int B, int C, long S, int vol_perm) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(!vol_perm || C == 512, -1, "vol_perm needs 512 channels");
+  dim3 grid((unsigned)((S + 31) / 32), (C + 31) / 32, B);
+  nchw_to_cl_kernel<<<grid, 256, 0, L.stream>>>(src, dst, C, S, vol_perm, C);
+  check_launch("nchw_to_cl");
+}
+
+void cl_to_nchw(const Launcher& L, const float* src, float* dst, int B, int C, long S, int vol_perm, int Cstride) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(!vol_perm || C == 512, -1, "vol_perm needs 512 channels");
+  dim3 grid((unsigned)((S + 31) / 32), (C + 31) / 32, B);
+  cl_to_nchw_kernel<<<grid, 256, 0, L.stream>>>(src, dst, C, S, vol_perm, Cstride);
+  check_launch("cl_to_nchw");
+}
+
+// ------------------------------------------------------------------------------------------
+// ingest / emit
+// ------------------------------------------------------------------------------------------
+__global__ void ingest_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i] / 255.f;      // astype(float32) / 255. ; clip is a no-op on u8 input
+}
+
+void ingest_u8(const Launcher& L, const uint8_t* src, float* dst, long n) {
+  L.count();
+  if (L.dry) return;
+  long blocks = (n + 255) / 256; if (blocks > 148L * 8) blocks = 148L * 8;
+  ingest_u8_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(src, dst, n);
+  check_launch("ingest_u8");
+}
+
+__global__ void __launch_bounds__(256) emit_image_kernel(const float* __restrict__ y, int Cs, float* __restrict__ img,
+                                                        uint8_t* __restrict__ u8, int B, int H, int W) {
+  int OH = 2 * H, OW = 2 * W;
+  long total = (long)B * OH * OW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int ow = (int)(i % OW); long t = i / OW; int oh = (int)(t % OH); int b = (int)(t / OH);
+    const float* q = y + (((long)b * H + (oh >> 1)) * W + (ow >> 1)) * Cs + (oh & 1) * 2 + (ow & 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = 1.f / (1.f + expf(-q[c * 4]));          // PixelShuffle(2): channel c*4 + i*2 + j
+      if (img) img[(((long)b * 3 + c) * OH + oh) * OW + ow] = v;
+      if (u8) {
+        float s = fminf(fmaxf(v, 0.f), 1.f) * 255.f;
+        s = fminf(fmaxf(s, 0.f), 255.f);
+        u8[i * 3 + c] = (uint8_t)s;                      // truncation, can_swap_e2e.py:320
+      }
+    }
+  }
+}
+
+void emit_image(const Launcher& L, const float* y, int Cs, float* img, uint8_t* u8, int B, int H, int W) {
+  L.count();
+  if (L.dry) return;
+  long total = (long)B * 4 * H * W;
+  long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+  emit_image_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(y, Cs, img, u8, B, H, W);
+  check_launch("emit_image");
+}
+
+}  // namespace cs

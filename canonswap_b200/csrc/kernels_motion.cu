@@ -1,0 +1,197 @@
+// Dense-motion sampling kernels (HBM-bound, sm_100a).
+//   dm_input           reference dense_motion.py:29-65,83-84: for every voxel and keypoint k build
+//                      [heatmap_k, trilinear sample of the 4-ch compressed feature at the k-th
+//                      pure-translation grid] -> hourglass input channel k*5 + {0..4}
+//   softmax_flow_warp  reference dense_motion.py:89-94 + warping_network.py:46-47,61: softmax over the
+//                      22 mask logits, flow = sum_k mask_k * motion_k, then the 5-D trilinear
+//                      grid_sample (zeros padding, align_corners=False) of the 32x16 feature volume
+//   grid_sample3d_cl   the bare 5-D grid_sample on the [B,H,W,16,32] volume (unit test entry)
+// Sampling semantics follow ATen grid_sampler_3d: ix = ((x+1)*W-1)/2, floor, 8 corners, zeros outside.
+#include "common.cuh"
+
+namespace cs {
+
+__device__ __forceinline__ float unnorm(float c, int size) { return ((c + 1.f) * size - 1.f) / 2.f; }
+
+struct Tri {           // trilinear footprint
+  int x0, y0, z0;
+  float w[8];          // order: tnw, tne, tsw, tse, bnw, bne, bsw, bse  (t = z0, n = y0, w = x0)
+};
+
+__device__ __forceinline__ Tri make_tri(float gx, float gy, float gz, int D, int H, int W) {
+  Tri t;
+  float ix = unnorm(gx, W), iy = unnorm(gy, H), iz = unnorm(gz, D);
+  float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  t.x0 = (int)fx; t.y0 = (int)fy; t.z0 = (int)fz;
+  float ex = fx + 1.f, ey = fy + 1.f, ez = fz + 1.f;     // east / south / bottom corner coordinates
+  float dxw = ex - ix, dxe = ix - fx;
+  float dyn = ey - iy, dys = iy - fy;
+  float dzt = ez - iz, dzb = iz - fz;
+  t.w[0] = dxw * dyn * dzt;  // tnw
+  t.w[1] = dxe * dyn * dzt;  // tne
+  t.w[2] = dxw * dys * dzt;  // tsw
+  t.w[3] = dxe * dys * dzt;  // tse
+  t.w[4] = dxw * dyn * dzb;  // bnw
+  t.w[5] = dxe * dyn * dzb;  // bne
+  t.w[6] = dxw * dys * dzb;  // bsw
+  t.w[7] = dxe * dys * dzb;  // bse
+  return t;
+}
+
+__device__ __forceinline__ void grid_xyz(int d, int h, int w, int D, int H, int W, float& gx, float& gy, float& gz) {
+  // make_coordinate_grid, reference util.py:41-50
+  gx = 2.f * ((float)w / (float)(W - 1)) - 1.f;
+  gy = 2.f * ((float)h / (float)(H - 1)) - 1.f;
+  gz = 2.f * ((float)d / (float)(D - 1)) - 1.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// dm_input: one thread per (voxel, k)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dm_input_kernel(const float4* __restrict__ c4, const float* __restrict__ kpd,
+                                                      const float* __restrict__ kps, int K, int B, int D, int H, int W,
+                                                      float* __restrict__ out, long ob, long od, long oh, long ow) {
+  long total = (long)B * D * H * W * (K + 1);
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int k = (int)(idx % (K + 1)); long pix = idx / (K + 1);
+    int w = (int)(pix % W); long t = pix / W; int h = (int)(t % H); t /= H; int d = (int)(t % D); int b = (int)(t / D);
+    float gx, gy, gz;
+    grid_xyz(d, h, w, D, H, W, gx, gy, gz);
+    float mx = gx, my = gy, mz = gz, heat = 0.f;
+    if (k > 0) {
+      const float* pd = kpd + ((long)b * K + (k - 1)) * 3;
+      const float* ps = kps + ((long)b * K + (k - 1)) * 3;
+      float dx = gx - pd[0], dy = gy - pd[1], dz = gz - pd[2];          // identity_grid - kp_driving
+      mx = dx + ps[0]; my = dy + ps[1]; mz = dz + ps[2];                 // + kp_source
+      float sx = gx - ps[0], sy = gy - ps[1], sz = gz - ps[2];
+      float qd = (dx * dx + dy * dy) + dz * dz, qs = (sx * sx + sy * sy) + sz * sz;
+      heat = expf(-0.5f * qd / 0.01f) - expf(-0.5f * qs / 0.01f);
+    }
+    Tri tr = make_tri(mx, my, mz, D, H, W);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+      for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+          int x = tr.x0 + cx, y = tr.y0 + cy, z = tr.z0 + cz;
+          if (x >= 0 && x < W && y >= 0 && y < H && z >= 0 && z < D) {
+            float wt = tr.w[cz * 4 + cy * 2 + cx];
+            float4 v = c4[(((long)b * D + z) * H + y) * W + x];
+            acc.x += v.x * wt; acc.y += v.y * wt; acc.z += v.z * wt; acc.w += v.w * wt;
+          }
+        }
+    float* o = out + b * ob + d * od + h * oh + w * ow + k * 5;
+    o[0] = heat; o[1] = acc.x; o[2] = acc.y; o[3] = acc.z; o[4] = acc.w;
+  }
+}
+
+void dm_input(const Launcher& L, const Act& c4, const float* kp_driving, const float* kp_source, int K, Act out) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(c4.C == 4 && c4.sw == 4, -1, "dm_input: compressed feature must be dense 4-channel");
+  long total = c4.pixels() * (K + 1);
+  long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
+  dm_input_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(c4.p), kp_driving, kp_source, K,
+                                                         c4.B, c4.D, c4.H, c4.W, out.p, out.sb, out.sd, out.sh, out.sw);
+  check_launch("dm_input");
+}
+
+// ------------------------------------------------------------------------------------------
+// sample the [B,H,W,16,32] volume: 8 threads per voxel, 4 channels (one float4) each
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 sample_vol(const float* __restrict__ vol, int b, const Tri& tr, int D, int H, int W, int c4) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+    for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+      for (int cx = 0; cx < 2; ++cx) {
+        int x = tr.x0 + cx, y = tr.y0 + cy, z = tr.z0 + cz;
+        if (x >= 0 && x < W && y >= 0 && y < H && z >= 0 && z < D) {
+          float wt = tr.w[cz * 4 + cy * 2 + cx];
+          float4 v = *reinterpret_cast<const float4*>(vol + (((long)b * H + y) * W + x) * 512 + z * 32 + c4 * 4);
+          acc.x += v.x * wt; acc.y += v.y * wt; acc.z += v.z * wt; acc.w += v.w * wt;
+        }
+      }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) softmax_flow_warp_kernel(const float* __restrict__ logits, long lb, long ld, long lh, long lw,
+                                                               const float* __restrict__ kpd, const float* __restrict__ kps,
+                                                               int K, int B, int D, int H, int W,
+                                                               const float* __restrict__ vol, float* __restrict__ out,
+                                                               float* __restrict__ deformation) {
+  long total = (long)B * D * H * W * 8;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int c4 = (int)(idx & 7); long pix = idx >> 3;
+    // voxel order (b, h, w, d): the 16 depths of a pixel are adjacent in the output volume
+    int d = (int)(pix % D); long t = pix / D; int w = (int)(t % W); t /= W; int h = (int)(t % H); int b = (int)(t / H);
+    const float* lg = logits + b * lb + d * ld + h * lh + w * lw;
+    float mxl = lg[0];
+    for (int k = 1; k <= K; ++k) mxl = fmaxf(mxl, lg[k]);
+    float gx, gy, gz;
+    grid_xyz(d, h, w, D, H, W, gx, gy, gz);
+    float den = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
+    for (int k = 0; k <= K; ++k) {
+      float e = expf(lg[k] - mxl);
+      den += e;
+      float mx = gx, my = gy, mz = gz;
+      if (k > 0) {
+        const float* pd = kpd + ((long)b * K + (k - 1)) * 3;
+        const float* ps = kps + ((long)b * K + (k - 1)) * 3;
+        mx = (gx - pd[0]) + ps[0]; my = (gy - pd[1]) + ps[1]; mz = (gz - pd[2]) + ps[2];
+      }
+      fx += mx * e; fy += my * e; fz += mz * e;
+    }
+    float inv = 1.f / den;
+    fx *= inv; fy *= inv; fz *= inv;
+    if (deformation && c4 == 0) {
+      float* df = deformation + ((((long)b * D + d) * H + h) * W + w) * 3;
+      df[0] = fx; df[1] = fy; df[2] = fz;
+    }
+    Tri tr = make_tri(fx, fy, fz, D, H, W);
+    float4 v = sample_vol(vol, b, tr, D, H, W, c4);
+    *reinterpret_cast<float4*>(out + (((long)b * H + h) * W + w) * 512 + d * 32 + c4 * 4) = v;
+  }
+}
+
+void softmax_flow_warp(const Launcher& L, const Act& logits, const float* kp_driving, const float* kp_source, int K,
+                       const float* vol, float* out, float* deformation) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(logits.D == 16 && logits.C >= K + 1, -1, "softmax_flow_warp: bad logits tensor");
+  long total = logits.pixels() * 8;
+  long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
+  softmax_flow_warp_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(logits.p, logits.sb, logits.sd, logits.sh, logits.sw,
+                                                                  kp_driving, kp_source, K, logits.B, logits.D, logits.H,
+                                                                  logits.W, vol, out, deformation);
+  check_launch("softmax_flow_warp");
+}
+
+__global__ void __launch_bounds__(256) grid_sample3d_cl_kernel(const float* __restrict__ vol, const float* __restrict__ grid,
+                                                              float* __restrict__ out, int B, int D, int H, int W) {
+  long total = (long)B * D * H * W * 8;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int c4 = (int)(idx & 7); long pix = idx >> 3;
+    int d = (int)(pix % D); long t = pix / D; int w = (int)(t % W); t /= W; int h = (int)(t % H); int b = (int)(t / H);
+    const float* g = grid + ((((long)b * D + d) * H + h) * W + w) * 3;
+    Tri tr = make_tri(g[0], g[1], g[2], D, H, W);
+    float4 v = sample_vol(vol, b, tr, D, H, W, c4);
+    *reinterpret_cast<float4*>(out + (((long)b * H + h) * W + w) * 512 + d * 32 + c4 * 4) = v;
+  }
+}
+
+void grid_sample3d_cl(const Launcher& L, const float* vol, const float* grid, float* out, int B, int D, int H, int W) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(D == 16, -1, "grid_sample3d_cl: depth must be 16");
+  long total = (long)B * D * H * W * 8;
+  long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
+  grid_sample3d_cl_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(vol, grid, out, B, D, H, W);
+  check_launch("grid_sample3d_cl");
+}
+
+}  // namespace cs
