@@ -1,0 +1,454 @@
+// extern "C" entry points of libcanonswap_b200.so (declared in include/canonswap_b200.h).
+// Every call validates its arguments, enqueues kernels on the caller's stream and returns a
+// cs_status; C++ exceptions never cross the ABI. There is no CPU or ATen/cuDNN fallback: a missing
+// device, unsupported shape or CUDA error is reported, not worked around.
+#include "ctx.cuh"
+#include <cstring>
+
+using namespace cs;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(cs_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CS_API_BEGIN(ctx)                                                              \
+  if (!(ctx)) return fail(nullptr, CS_ERR_INVALID, "null context");                    \
+  try {                                                                                \
+    CS_CUDA(cudaSetDevice((ctx)->device));
+#define CS_API_END(ctx)                                                                \
+    return CS_OK;                                                                      \
+  } catch (const cs::Error& e) {                                                       \
+    (ctx)->arena.reset(0);                                                             \
+    return fail((ctx), e.code, e.what());                                              \
+  } catch (const std::exception& e) {                                                  \
+    (ctx)->arena.reset(0);                                                             \
+    return fail((ctx), CS_ERR_INVALID, e.what());                                      \
+  }
+
+Net make_net(cs_ctx* ctx, void* stream, bool dry) {
+  Net n;
+  n.ctx = ctx;
+  n.A = &ctx->arena;
+  n.L.stream = static_cast<cudaStream_t>(stream);
+  n.L.dry = dry;
+  n.L.counter = dry ? nullptr : &ctx->launches;
+  n.L.conv_impl = ctx->conv_impl;
+  n.L.prof = dry ? nullptr : &ctx->prof;
+  return n;
+}
+
+void check_batch(cs_ctx* ctx, int B) {
+  CS_REQUIRE(ctx->weights_loaded, CS_ERR_STATE, "weights not loaded (call cs_load_weights first)");
+  CS_REQUIRE(B >= 1 && B <= ctx->max_batch, CS_ERR_INVALID, "batch size outside [1, max_batch]");
+}
+
+long vol_elems(const cs_ctx* ctx, int B) { return (long)B * ctx->h * ctx->w * 512; }
+
+// ---- stage bodies shared by the real calls and the workspace-measuring dry run ------------------
+void body_appearance(Net& n, const float* img, float* f3d, int B) {
+  cs_ctx* c = n.ctx;
+  float* img_cl = n.A->f32((size_t)B * c->net_h * c->net_w * 3);
+  float* vol = n.A->f32(vol_elems(c, B));
+  nchw_to_cl(n.L, img, img_cl, B, 3, (long)c->net_h * c->net_w, 0);
+  run_F(n, img_cl, B, vol);
+  cl_to_nchw(n.L, vol, f3d, B, 512, (long)c->h * c->w, 1, 512);
+}
+
+void body_warp(Net& n, const float* f3d, const float* kp_source, const float* kp_driving, float* out3d, float* occ,
+               float* deformation, int B) {
+  cs_ctx* c = n.ctx;
+  float* vin = n.A->f32(vol_elems(c, B));
+  float* vout = n.A->f32(vol_elems(c, B));
+  nchw_to_cl(n.L, f3d, vin, B, 512, (long)c->h * c->w, 1);
+  run_warp(n, vin, kp_source, kp_driving, B, vout, occ, deformation);
+  cl_to_nchw(n.L, vout, out3d, B, 512, (long)c->h * c->w, 1, 512);
+}
+
+void body_warp_out(Net& n, const float* f3d, const float* occ, float* out, int B) {
+  cs_ctx* c = n.ctx;
+  float* vin = n.A->f32(vol_elems(c, B));
+  float* o = n.A->f32((size_t)B * c->h * c->w * 256);
+  nchw_to_cl(n.L, f3d, vin, B, 512, (long)c->h * c->w, 1);
+  run_warp_out(n, vin, occ, B, o);
+  cl_to_nchw(n.L, o, out, B, 256, (long)c->h * c->w, 0, 256);
+}
+
+void body_warp_forward(Net& n, const float* f3d, const float* kp_driving, const float* kp_source, float* out, float* occ,
+                       float* deformation, int B) {
+  cs_ctx* c = n.ctx;
+  float* vin = n.A->f32(vol_elems(c, B));
+  float* vout = n.A->f32(vol_elems(c, B));
+  float* o = n.A->f32((size_t)B * c->h * c->w * 256);
+  float* occ_buf = occ ? occ : n.A->f32((size_t)B * c->h * c->w);
+  nchw_to_cl(n.L, f3d, vin, B, 512, (long)c->h * c->w, 1);
+  run_warp(n, vin, kp_source, kp_driving, B, vout, occ_buf, deformation);
+  run_warp_out(n, vout, occ_buf, B, o);
+  cl_to_nchw(n.L, o, out, B, 256, (long)c->h * c->w, 0, 256);
+}
+
+void body_swap(Net& n, const float* f3d, float* out3d, float* masks, int B) {
+  cs_ctx* c = n.ctx;
+  float* v = n.A->f32(vol_elems(c, B));
+  nchw_to_cl(n.L, f3d, v, B, 512, (long)c->h * c->w, 1);
+  run_swap(n, v, B, v, masks);
+  cl_to_nchw(n.L, v, out3d, B, 512, (long)c->h * c->w, 1, 512);
+}
+
+void body_refine(Net& n, const float* f3d, float* out3d, int B) {
+  cs_ctx* c = n.ctx;
+  float* v = n.A->f32(vol_elems(c, B));
+  nchw_to_cl(n.L, f3d, v, B, 512, (long)c->h * c->w, 1);
+  run_refine(n, v, B, v);
+  cl_to_nchw(n.L, v, out3d, B, 512, (long)c->h * c->w, 1, 512);
+}
+
+void body_spade(Net& n, const float* feat, float* img, uint8_t* img_u8, int B) {
+  cs_ctx* c = n.ctx;
+  float* f = n.A->f32((size_t)B * c->h * c->w * 256);
+  nchw_to_cl(n.L, feat, f, B, 256, (long)c->h * c->w, 0);
+  run_spade(n, f, B, img, img_u8);
+}
+
+// The per-frame loop body, reference can_swap_pipeline_e2e.py:242-267, entirely in the internal layout.
+void body_frame(Net& n, const void* frames, const float* kp_t, const float* kp_can, float* out_f32, uint8_t* out_u8, int B,
+                int flags) {
+  cs_ctx* c = n.ctx;
+  const long npix = (long)B * c->net_h * c->net_w;
+  float* img_cl = n.A->f32((size_t)npix * 3);
+  float* va = n.A->f32(vol_elems(c, B));
+  float* vb = n.A->f32(vol_elems(c, B));
+  float* occ = n.A->f32((size_t)B * c->h * c->w);
+  float* o256 = n.A->f32((size_t)B * c->h * c->w * 256);
+  if (flags & CS_FRAME_IN_U8_HWC) ingest_u8(n.L, static_cast<const uint8_t*>(frames), img_cl, npix * 3);   // prepare_videos
+  else nchw_to_cl(n.L, static_cast<const float*>(frames), img_cl, B, 3, (long)c->net_h * c->net_w, 0);
+  run_F(n, img_cl, B, va);                                        // :242 f_s = extract_feature_3d(I_s)
+  run_warp(n, va, /*kp_source=*/kp_t, /*kp_driving=*/kp_can, B, vb, occ, nullptr);   // :244 warp(f_s, x_t, x_can)
+  if (flags & CS_FRAME_DEBUG_DECODES) {                           // :248 rec_can = conv_decode(f_can, occ)
+    run_warp_out(n, vb, occ, B, o256);
+    run_spade(n, o256, B, nullptr, nullptr);
+  }
+  run_swap(n, vb, B, vb, nullptr);                                // :253 swap_module(f_can, source_id)
+  if (flags & CS_FRAME_DEBUG_DECODES) {                           // :257 swap_can = conv_decode(f_swap, occ)
+    run_warp_out(n, vb, occ, B, o256);
+    run_spade(n, o256, B, nullptr, nullptr);
+  }
+  run_refine(n, vb, B, vb);                                       // :262 refine_module(f_swap)
+  run_warp(n, vb, /*kp_source=*/kp_can, /*kp_driving=*/kp_t, B, va, occ, nullptr);   // :263 warp_decode(f_swap, x_can, x_t)
+  run_warp_out(n, va, occ, B, o256);
+  run_spade(n, o256, B, out_f32, out_u8);                         // :267 parse_output fused into the emit kernel
+}
+
+// size the arena: dry-run every entry point at max_batch and keep the high-water mark
+void size_workspace(cs_ctx* ctx) {
+  Arena& A = ctx->arena;
+  A.measuring = true; A.base = nullptr; A.cap = 0; A.off = 0; A.high = 0;
+  bool id = ctx->identity_set;
+  ctx->identity_set = true;
+  const int B = ctx->max_batch;
+  float* fake = reinterpret_cast<float*>(uintptr_t(0x1000));
+  {
+    Net n = make_net(ctx, nullptr, true);
+    // both conv implementations must fit (CS_OPT_CONV_IMPL may be flipped after loading)
+    for (int impl = 0; impl < 2; ++impl) {
+      n.L.conv_impl = impl;
+      A.reset(0); body_appearance(n, fake, fake, B);
+      A.reset(0); body_warp(n, fake, fake, fake, fake, fake, fake, B);
+      A.reset(0); body_warp_out(n, fake, fake, fake, B);
+      A.reset(0); body_warp_forward(n, fake, fake, fake, fake, nullptr, fake, B);
+      A.reset(0); body_swap(n, fake, fake, fake, B);
+      A.reset(0); body_refine(n, fake, fake, B);
+      A.reset(0); body_spade(n, fake, fake, reinterpret_cast<uint8_t*>(fake), B);
+      A.reset(0); body_frame(n, fake, fake, fake, fake, reinterpret_cast<uint8_t*>(fake), B,
+                             CS_FRAME_IN_U8_HWC | CS_FRAME_DEBUG_DECODES);
+    }
+  }
+  ctx->identity_set = id;
+  size_t need = A.high + (1 << 20);
+  A.measuring = false; A.off = 0; A.high = 0;
+  A.base = static_cast<char*>(ctx->dmalloc(need));
+  A.cap = need;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cs_create(cs_ctx** out, int device, int max_batch, int net_h, int net_w) {
+  if (!out) return fail(nullptr, CS_ERR_INVALID, "cs_create: null out pointer");
+  *out = nullptr;
+  if (max_batch < 1 || max_batch > 1024) return fail(nullptr, CS_ERR_INVALID, "cs_create: max_batch outside [1, 1024]");
+  if (net_h < 128 || net_w < 128 || net_h % 128 || net_w % 128 || net_h > 2048 || net_w > 2048)
+    return fail(nullptr, CS_ERR_INVALID, "cs_create: net_h / net_w must be multiples of 128 in [128, 2048]");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, CS_ERR_CUDA, std::string("cs_create: no CUDA device (") + cudaGetErrorString(e) +
+                                          "); this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, CS_ERR_INVALID, "cs_create: bad device index");
+  cs_ctx* ctx = nullptr;
+  try {
+    CS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      throw cs::Error(CS_ERR_CUDA, "cs_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                       ", this library is built for sm_100a (B200) only");
+    ctx = new cs_ctx();
+    ctx->device = device; ctx->max_batch = max_batch; ctx->net_h = net_h; ctx->net_w = net_w;
+    ctx->h = net_h / 4; ctx->w = net_w / 4;
+    size_t sb = sizeof(double) * 2 * (size_t)max_batch * 512;
+    if (sb < 4096) sb = 4096;
+    ctx->stats_scratch = static_cast<double*>(ctx->dmalloc(sb));
+  } catch (const std::exception& ex) {
+    if (ctx) cs_destroy(ctx);
+    return fail(nullptr, CS_ERR_CUDA, ex.what());
+  }
+  *out = ctx;
+  return CS_OK;
+}
+
+void cs_destroy(cs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (void* p : ctx->owned) cudaFree(p);
+  delete ctx;
+}
+
+const char* cs_last_error(const cs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int cs_set_option(cs_ctx* ctx, int option, int value) {
+  if (!ctx) return fail(nullptr, CS_ERR_INVALID, "null context");
+  switch (option) {
+    case CS_OPT_CONV_IMPL:
+      if (value < 0 || value > 1) return fail(ctx, CS_ERR_INVALID, "CS_OPT_CONV_IMPL: value must be 0 or 1");
+      ctx->conv_impl = value; return CS_OK;
+    case CS_OPT_USE_GRAPH:
+      ctx->use_graph = value ? 1 : 0; return CS_OK;
+    default: return fail(ctx, CS_ERR_INVALID, "unknown option");
+  }
+}
+
+int64_t cs_launch_count(const cs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+size_t cs_workspace_bytes(const cs_ctx* ctx) { return ctx ? ctx->owned_bytes : 0; }
+
+int cs_load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
+  CS_API_BEGIN(ctx)
+  load_weights(ctx, table, n);
+  size_workspace(ctx);
+  CS_API_END(ctx)
+}
+
+int cs_set_identity(cs_ctx* ctx, const float* id_dev, void* stream) {
+  CS_API_BEGIN(ctx)
+  set_identity(ctx, id_dev, static_cast<cudaStream_t>(stream));
+  CS_API_END(ctx)
+}
+
+int cs_appearance(cs_ctx* ctx, const float* img, float* f3d, int B, void* stream) {
+  CS_API_BEGIN(ctx)
+  check_batch(ctx, B);
+  CS_REQUIRE(img && f3d, CS_ERR_INVALID, "cs_appearance: null tensor");
+  Net n = make_net(ctx, stream, false);
+  ctx->arena.reset(0);
+  body_appearance(n, img, f3d, B);
+  CS_API_END(ctx)
+}
+
+int cs_warp(cs_ctx* ctx, const float* f3d, const float* kp_source, const float* kp_driving, float* out3d, float* occ,
+            float* deformation, int B, void* stream) {
+  CS_API_BEGIN(ctx)
+  check_batch(ctx, B);
+  CS_REQUIRE(f3d && kp_source && kp_driving && out3d && occ, CS_ERR_INVALID, "cs_warp: null tensor");
+  Net n = make_net(ctx, stream, false);
+  ctx->arena.reset(0);
+  body_warp(n, f3d, kp_source, kp_driving, out3d, occ, deformation, B);
+  CS_API_END(ctx)
+}
+
+int cs_warp_out(cs_ctx* ctx, const float* f3d, const float* occ, float* out, int B, void* stream) {
+  CS_API_BEGIN(ctx)
+  check_batch(ctx, B);
+  CS_REQUIRE(f3d && out, CS_ERR_INVALID, "cs_warp_out: null tensor");
+  Net n = make_net(ctx, stream, false);
+  ctx->arena.reset(0);
+  body_warp_out(n, f3d, occ, out, B);
+  CS_API_END(ctx)
+}
+
+int cs_warp_forward(cs_ctx* ctx, const float* f3d, const float* kp_driving, const float* kp_source, float* out, float* occ,
+                    float* deformation, int B, void* stream) {
+  CS_API_BEGIN(ctx)
+  check_batch(ctx, B);
+  CS_REQUIRE(f3d && kp_source && kp_driving && out, CS_ERR_INVALID, "cs_warp_forward: null tensor");
+  Net n = make_net(ctx, stream, false);
+  ctx->arena.reset(0);
+  body_warp_forward(n, f3d, kp_driving, kp_source, out, occ, deformation, B);
+  CS_API_END(ctx)
+}
+
+int cs_swap(cs_ctx* ctx, const float* f3d, float* out3d, float* masks, int B, void* stream) {
+  CS_API_BEGIN(ctx)
+  check_batch(ctx, B);
+  CS_REQUIRE(f3d && out3d, CS_ERR_INVALID, "cs_swap: null tensor");
+  CS_REQUIRE(ctx->identity_set, CS_ERR_STATE, "cs_swap before cs_set_identity");
+  Net n = make_net(ctx, stream, false);
+  ctx->arena.reset(0);
+  body_swap(n, f3d, out3d, masks, B);
+  CS_API_END(ctx)
+}
+
+int cs_refine(cs_ctx* ctx, const float* f3d, float* out3d, int B, void* stream) {
+  CS_API_BEGIN(ctx)
+  check_batch(ctx, B);
+  CS_REQUIRE(f3d && out3d, CS_ERR_INVALID, "cs_refine: null tensor");
+  Net n = make_net(ctx, stream, false);
+  ctx->arena.reset(0);
+  body_refine(n, f3d, out3d, B);
+  CS_API_END(ctx)
+}
+
+int cs_spade(cs_ctx* ctx, const float* feat, float* img, uint8_t* img_u8, int B, void* stream) {
+  CS_API_BEGIN(ctx)
+  check_batch(ctx, B);
+  CS_REQUIRE(feat && (img || img_u8), CS_ERR_INVALID, "cs_spade: null tensor");
+  Net n = make_net(ctx, stream, false);
+  ctx->arena.reset(0);
+  body_spade(n, feat, img, img_u8, B);
+  CS_API_END(ctx)
+}
+
+int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp_can, float* out_f32, uint8_t* out_u8, int B,
+             int flags, void* stream) {
+  CS_API_BEGIN(ctx)
+  check_batch(ctx, B);
+  CS_REQUIRE(frames && kp_t && kp_can && (out_f32 || out_u8), CS_ERR_INVALID, "cs_frame: null tensor");
+  CS_REQUIRE(ctx->identity_set, CS_ERR_STATE, "cs_frame before cs_set_identity");
+  Net n = make_net(ctx, stream, false);
+  ctx->arena.reset(0);
+  body_frame(n, frames, kp_t, kp_can, out_f32, out_u8, B, flags);
+  CS_API_END(ctx)
+}
+
+// ---- per-kernel-family timing (bench.py roofline leg) ---------------------------------------------
+int cs_profile(cs_ctx* ctx, int enable) {
+  CS_API_BEGIN(ctx)
+  CS_CUDA(cudaDeviceSynchronize());
+  for (auto& r : ctx->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  ctx->prof.recs.clear();
+  ctx->prof.on = enable != 0;
+  CS_API_END(ctx)
+}
+
+int cs_profile_read(cs_ctx* ctx, double* out) {
+  CS_API_BEGIN(ctx)
+  CS_REQUIRE(out != nullptr, CS_ERR_INVALID, "cs_profile_read: null output");
+  CS_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < PK_N * 4; ++i) out[i] = 0.0;
+  for (auto& r : ctx->prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      out[r.kind * 4 + 0] += ms; out[r.kind * 4 + 1] += r.flops; out[r.kind * 4 + 2] += r.bytes; out[r.kind * 4 + 3] += 1.0;
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  ctx->prof.recs.clear();
+  CS_API_END(ctx)
+}
+
+// ---- kernel-level entry points -------------------------------------------------------------------
+int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int D, int H, int W, int Cin,
+                 int Cout, int KD, int KH, int KW, int PD, int PH, int PW, int act, float slope, int impl, void* stream) {
+  CS_API_BEGIN(ctx)
+  CS_REQUIRE(x && w && y && B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, CS_ERR_INVALID, "cs_test_conv: bad argument");
+  CS_REQUIRE(KD > 0 && KH > 0 && KW > 0 && impl >= 0 && impl <= 2, CS_ERR_INVALID, "cs_test_conv: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CS_CUDA(cudaStreamSynchronize(st));
+  const size_t nw = (size_t)Cout * Cin * KD * KH * KW;
+  std::vector<float> hw(nw), hb;
+  CS_CUDA(cudaMemcpy(hw.data(), w, nw * sizeof(float), cudaMemcpyDeviceToHost));
+  if (bias) { hb.resize(Cout); CS_CUDA(cudaMemcpy(hb.data(), bias, Cout * sizeof(float), cudaMemcpyDeviceToHost)); }
+  const size_t owned0 = ctx->owned.size();
+  const size_t bytes0 = ctx->owned_bytes;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(st);
+    while (ctx->owned.size() > owned0) { cudaFree(ctx->owned.back()); ctx->owned.pop_back(); }
+    ctx->owned_bytes = bytes0;
+  };
+  try {
+    ConvW cw = pack_conv_host(ctx, hw, bias ? &hb : nullptr, Cout, Cin, KD, KH, KW);
+    const int Do = D + 2 * PD - KD + 1, Ho = H + 2 * PH - KH + 1, Wo = W + 2 * PW - KW + 1;
+    CS_REQUIRE(Do > 0 && Ho > 0 && Wo > 0, CS_ERR_INVALID, "cs_test_conv: empty output");
+    Act xa = make_act(const_cast<float*>(x), B, D, H, W, Cin);
+    Act ya = make_act(y, B, Do, Ho, Wo, Cout);
+    ConvGeom g; g.PD = PD; g.PH = PH; g.PW = PW; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
+    Epilogue e; e.act = act; e.slope = slope;
+    Launcher L; L.stream = st; L.counter = &ctx->launches;
+    const bool same = (Do == D && Ho == H && Wo == W && PD == KD / 2 && PH == KH / 2 && PW == KW / 2);
+    bool tc = same && conv_tc_supported(cw, ya);
+    if (impl == 2) CS_REQUIRE(tc, CS_ERR_INVALID, "cs_test_conv: shape not supported by the tcgen05 conv");
+    if (impl == 1) tc = false;
+    if (tc) {
+      // private scratch for the operand planes (the ctx arena may not exist before cs_load_weights)
+      Arena tmp; tmp.measuring = true;
+      conv_tc_alloc_operand(tmp, cw, ya);
+      Arena real; real.cap = tmp.high + 4096; real.base = static_cast<char*>(ctx->dmalloc(real.cap));
+      Opd opd = conv_tc_alloc_operand(real, cw, ya);
+      Prep p; p.src0 = xa;
+      prep_planes(L, p, opd, nullptr);
+      conv_tc(L, opd, cw, g, e, ya);
+    } else if (Cout == 1) {
+      conv_cout1(L, xa, cw, g, act, y);
+    } else {
+      conv_simt(L, xa, cw, g, e, ya, 0);
+    }
+  } catch (...) { cleanup(); throw; }
+  cleanup();
+  CS_API_END(ctx)
+}
+
+int cs_test_grid_sample3d(cs_ctx* ctx, const float* inp, const float* grid, float* out, int B, int C, int D, int H, int W,
+                          void* stream) {
+  CS_API_BEGIN(ctx)
+  CS_REQUIRE(inp && grid && out && B > 0, CS_ERR_INVALID, "cs_test_grid_sample3d: bad argument");
+  CS_REQUIRE(C == 32 && D == 16, CS_ERR_INVALID, "cs_test_grid_sample3d: only the 32x16 feature volume is supported");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Launcher L; L.stream = st; L.counter = &ctx->launches;
+  const size_t n = (size_t)B * 512 * H * W;
+  float *vin = nullptr, *vout = nullptr;
+  CS_CUDA(cudaMalloc(&vin, n * sizeof(float)));
+  if (cudaMalloc(&vout, n * sizeof(float)) != cudaSuccess) { cudaFree(vin); throw cs::Error(CS_ERR_NOMEM, "cudaMalloc failed"); }
+  try {
+    nchw_to_cl(L, inp, vin, B, 512, (long)H * W, 1);
+    grid_sample3d_cl(L, vin, grid, vout, B, D, H, W);
+    cl_to_nchw(L, vout, out, B, 512, (long)H * W, 1, 512);
+  } catch (...) { cudaStreamSynchronize(st); cudaFree(vin); cudaFree(vout); throw; }
+  cudaStreamSynchronize(st);
+  cudaFree(vin); cudaFree(vout);
+  CS_API_END(ctx)
+}
+
+int cs_test_instance_stats(cs_ctx* ctx, const float* x, float* mean, float* rstd, int B, int C, int S, float eps, void* stream) {
+  CS_API_BEGIN(ctx)
+  CS_REQUIRE(x && mean && rstd && B > 0 && C > 0 && S > 0, CS_ERR_INVALID, "cs_test_instance_stats: bad argument");
+  CS_REQUIRE(B <= ctx->max_batch && C <= 512, CS_ERR_INVALID, "cs_test_instance_stats: B*C exceeds the ctx scratch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Launcher L; L.stream = st; L.counter = &ctx->launches;
+  float* cl = nullptr;
+  CS_CUDA(cudaMalloc(&cl, (size_t)B * C * S * sizeof(float)));
+  try {
+    nchw_to_cl(L, x, cl, B, C, S, 0);
+    Act a = make_act(cl, B, 1, 1, S, C);
+    instance_stats(L, a, mean, rstd, eps, ctx->stats_scratch);
+  } catch (...) { cudaStreamSynchronize(st); cudaFree(cl); throw; }
+  cudaStreamSynchronize(st);
+  cudaFree(cl);
+  CS_API_END(ctx)
+}
+
+}  // extern "C"

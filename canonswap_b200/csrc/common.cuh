@@ -116,8 +116,8 @@ enum NormKind { NORM_NONE = 0, NORM_AFFINE_C = 1, NORM_STATS_BC = 2 };
 struct Prep {
   // sources (concat along C: src0 channels first, then src1)
   Act src0, src1;            // src1.p == nullptr when unused
-  int upshift = 0;           // nearest upsample of (h,w) by 2^upshift (applies to src0 only)
-  int pool2 = 0;             // 2x2 average pool of (h,w) (src0 only)
+  int upshift = 0;           // nearest upsample of (h,w) by 2^upshift (src0; src1 must be unused)
+  int pool2 = 0;             // 2x2 average pool of (h,w) (src0; src1 must be unused)
   int norm = NORM_NONE;
   const float* scale = nullptr;   // AFFINE_C: per-channel scale / shift. STATS_BC: optional gamma/beta per channel
   const float* shift = nullptr;
@@ -150,12 +150,36 @@ struct Arena {
   void reset(size_t m = 0) { off = m; }
 };
 
+// optional per-launch CUDA-event timing, aggregated per kernel family (bench.py's roofline leg)
+enum ProfKind { PK_CONV_TC = 0, PK_CONV_SIMT = 1, PK_PREP = 2, PK_STATS = 3, PK_SAMPLE = 4, PK_OTHER = 5, PK_N = 6 };
+struct Profiler {
+  struct Rec { cudaEvent_t a, b; int kind; double flops, bytes; };
+  std::vector<Rec> recs;
+  bool on = false;
+};
+
 struct Launcher {            // everything a kernel launch helper needs
   cudaStream_t stream = nullptr;
   bool dry = false;          // measuring pass: skip launches
   int64_t* counter = nullptr;
   int conv_impl = 0;         // 0 auto, 1 SIMT, 2 TC
+  Profiler* prof = nullptr;
   void count() const { if (counter) ++*counter; }
+};
+
+// brackets the launches issued in its scope with two events on the launching stream
+struct ProfScope {
+  const Launcher& L;
+  size_t idx = (size_t)-1;
+  ProfScope(const Launcher& l, int kind, double flops, double bytes) : L(l) {
+    if (!L.prof || !L.prof->on || L.dry) return;
+    Profiler::Rec r; r.kind = kind; r.flops = flops; r.bytes = bytes;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, L.stream);
+    idx = L.prof->recs.size();
+    L.prof->recs.push_back(r);
+  }
+  ~ProfScope() { if (idx != (size_t)-1) cudaEventRecord(L.prof->recs[idx].b, L.stream); }
 };
 
 inline void check_launch(const char* what) {
@@ -168,7 +192,8 @@ inline void check_launch(const char* what) {
 // ------------------------------------------------------------------------------------------
 // kernels_elem.cu
 void prep_f32(const Launcher& L, const Prep& p, Act out);                    // out: fp32 (strides from Act)
-void prep_planes(const Launcher& L, const Prep& p, Opd out, float* out32);   // split-bf16 planes (+ optional fp32 copy, stride = logical C)
+void prep_planes(const Launcher& L, const Prep& p, Opd out, const Act* out32);   // split-bf16 planes (+ optional fp32 copy)
+void avg2(const Launcher& L, const float* a, const float* b, float* y, long n);   // y = (a + b) / 2
 void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch);
 void adaptive_blend(const Launcher& L, const float* o2 /*[P,1024]*/, const float* mask /*[P]*/,
                     const float* residual /*[P,512] or null*/, int relu, float* y /*[P,512]*/, long P);
@@ -178,7 +203,8 @@ void ingest_u8(const Launcher& L, const uint8_t* src, float* dst, long n);
 void emit_image(const Launcher& L, const float* y /*[B,H,W,Cs] conv_img out, 12 valid*/, int Cs,
                 float* img /*[B,3,2H,2W] or null*/, uint8_t* u8 /*[B,2H,2W,3] or null*/, int B, int H, int W);
 // kernels_conv_simt.cu
-void conv_simt(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y);
+// xshift: the conv input is x nearest-upsampled by 2^xshift along (H, W) (read through index math)
+void conv_simt(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y, int xshift = 0);
 void conv_cout1(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom& g, int act, float* y /*[B*Do*Ho*Wo]*/);
 // kernels_motion.cu
 void dm_input(const Launcher& L, const Act& c4, const float* kp_driving, const float* kp_source, int K,
@@ -188,7 +214,9 @@ void softmax_flow_warp(const Launcher& L, const Act& logits /*[B,D,H,W,K+1]*/, c
                        float* out /*[B,H,W,16,32]*/, float* deformation /*[B,D,H,W,3] or null*/);
 void grid_sample3d_cl(const Launcher& L, const float* vol, const float* grid, float* out, int B, int D, int H, int W);
 // conv_tc.cu
-bool conv_tc_eligible(const ConvW& w, const ConvGeom& g, const Opd& x);
+// "same" convolution (stride 1, pad = k/2) of a dense channels-last tensor with the geometry of `out`
+bool conv_tc_supported(const ConvW& w, const Act& out);
+Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out);   // split-bf16 planes [B,D,H,W,Cin_p] x2
 void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y);
 
 }  // namespace cs

@@ -87,6 +87,7 @@ struct cs_ctx {
   cs::Arena arena;
   cs::Weights W;
   double* stats_scratch = nullptr; // [max_batch*512*2] double
+  cs::Profiler prof;
   void* dmalloc(size_t bytes) {
     void* p = nullptr;
     CS_CUDA(cudaMalloc(&p, bytes ? bytes : 256));
@@ -119,6 +120,5 @@ void run_warp_out(Net& n, const float* vol_in, const float* occ, int B, float* o
 void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks);
 void run_refine(Net& n, const float* vol_in, int B, float* vol_out);
 void run_spade(Net& n, const float* feat256, int B, float* img_nchw, uint8_t* img_u8);
-Act conv_layer(Net& n, const Prep* prep, const Act& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act* out);
 
 }  // namespace cs

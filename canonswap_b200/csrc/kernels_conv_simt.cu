@@ -19,6 +19,7 @@ struct ConvSimtK {
   float* y; long yb, yd, yh, yw;
   long M;                  // B*Do*Ho*Wo
   int vecA, vecB;          // 128-bit load eligibility
+  int xs;                  // input nearest-upsample shift on (H, W); k.H, k.W are the UPSAMPLED extents
 };
 
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvSimtK k) {
     int kw = tap % k.KW; int r = tap / k.KW; int kh = r % k.KH; int kd = r / k.KH;
     int id = od + kd - k.PD, ih = oh + kh - k.PH, iw = ow + kw - k.PW;
     bool inb = mvalid && id >= 0 && id < k.D && ih >= 0 && ih < k.H && iw >= 0 && iw < k.W;
-    const float* xp = k.x + ob * k.xb + id * k.xd + ih * k.xh + iw * k.xw;
+    const float* xp = k.x + ob * k.xb + id * k.xd + (long)(ih >> k.xs) * k.xh + (long)(iw >> k.xs) * k.xw;
     const float* wp = k.w + (long)tap * k.Cin * k.Cout;
     for (int c0 = 0; c0 < k.Cin; c0 += BK) {
       // ---- load A (transposed into As[k][m]) ----
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvSimtK k) {
   }
 }
 
-void conv_simt(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y) {
+void conv_simt(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y, int xshift) {
   L.count();
   if (L.dry) return;
   CS_REQUIRE(x.C == w.Cin, -1, "conv_simt: Cin mismatch");
@@ -133,7 +134,7 @@ void conv_simt(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom& 
   CS_REQUIRE(w.w32 != nullptr, -3, "conv_simt: weights not packed");
   ConvSimtK k{};
   k.x = x.p; k.xb = x.sb; k.xd = x.sd; k.xh = x.sh; k.xw = x.sw; k.Cin = x.C;
-  k.B = x.B; k.D = x.D; k.H = x.H; k.W = x.W;
+  k.B = x.B; k.D = x.D; k.H = x.H << xshift; k.W = x.W << xshift; k.xs = xshift;
   k.KD = w.KD; k.KH = w.KH; k.KW = w.KW; k.PD = g.PD; k.PH = g.PH; k.PW = g.PW;
   k.Do = g.Do; k.Ho = g.Ho; k.Wo = g.Wo;
   k.w = w.w32; k.bias = w.bias; k.Cout = w.Cout;
@@ -146,6 +147,7 @@ void conv_simt(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom& 
   k.vecA = (x.C % 4 == 0) && al4(x.sb) && al4(x.sd) && al4(x.sh) && al4(x.sw) && ((uintptr_t)x.p % 16 == 0);
   k.vecB = (w.Cout % 4 == 0) && ((uintptr_t)w.w32 % 16 == 0);
   dim3 grid((unsigned)((k.M + BM - 1) / BM), (w.Cout + BN - 1) / BN);
+  ProfScope ps(L, PK_CONV_SIMT, 2.0 * (double)k.M * w.Cout * w.Cin * w.taps(), 0.0);
   conv_simt_kernel<<<grid, 256, 0, L.stream>>>(k);
   check_launch("conv_simt");
 }
@@ -198,6 +200,7 @@ void conv_cout1(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom&
   k.PD = g.PD; k.PH = g.PH; k.PW = g.PW; k.Do = g.Do; k.Ho = g.Ho; k.Wo = g.Wo;
   k.w = w.w32; k.bias_p = w.bias; k.act = act; k.y = y;
   k.M = (long)x.B * g.Do * g.Ho * g.Wo;
+  ProfScope ps(L, PK_CONV_SIMT, 2.0 * (double)k.M * w.Cin * w.taps(), 0.0);
   conv_cout1_kernel<<<(unsigned)((k.M + 7) / 8), 256, 0, L.stream>>>(k);
   check_launch("conv_cout1");
 }

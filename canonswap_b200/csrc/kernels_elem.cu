@@ -86,6 +86,7 @@ static void launch_prep(const Launcher& L, PrepK& k) {
   long total = (long)k.B * k.D * k.H * k.W * k.Cout;
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 32) blocks = 148L * 32;
+  ProfScope ps(L, PK_PREP, 0.0, (double)total * 4.0 * 2.0);
   prep_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(k);
   check_launch("prep");
 }
@@ -98,13 +99,14 @@ void prep_f32(const Launcher& L, const Prep& p, Act out) {
   launch_prep(L, k);
 }
 
-void prep_planes(const Launcher& L, const Prep& p, Opd out, float* out32) {
+void prep_planes(const Launcher& L, const Prep& p, Opd out, const Act* out32) {
   PrepK k = make_prepk(p);
   CS_REQUIRE(out.Cp >= k.Cl, -1, "prep_planes: padded channels too small");
   k.B = out.B; k.D = out.D; k.H = out.H; k.W = out.W; k.Cout = out.Cp;
   k.ohi = out.hi; k.olo = out.lo; k.pb = out.sb; k.pd = out.sd; k.ph = out.sh; k.pw = out.sw;
   if (out32) {
-    k.o32 = out32; k.ow = k.Cl; k.oh = (long)out.W * k.ow; k.od = (long)out.H * k.oh; k.ob = (long)out.D * k.od;
+    CS_REQUIRE(out32->C == k.Cl, -1, "prep_planes: fp32 copy channel mismatch");
+    k.o32 = out32->p; k.ob = out32->sb; k.od = out32->sd; k.oh = out32->sh; k.ow = out32->sw;
   }
   launch_prep(L, k);
 }
@@ -164,6 +166,7 @@ void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, f
   long S = (long)x.D * x.H * x.W;
   int chunk = 2048;
   int nchunks = (int)((S + chunk - 1) / chunk);
+  ProfScope ps(L, PK_STATS, 0.0, (double)x.B * S * C * 4.0);
   CS_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * x.B * C, L.stream));
   dim3 grid(nchunks, x.B);
   stats_partial_kernel<<<grid, 256, 0, L.stream>>>(x.p, x.sb, x.sd, x.sh, x.sw, x.D, x.H, x.W, C, CT, chunk, scratch);
@@ -198,10 +201,24 @@ void adaptive_blend(const Launcher& L, const float* o2, const float* mask, const
   if (L.dry) return;
   long blocks = (P * 128 + 255) / 256;
   if (blocks > 148L * 16) blocks = 148L * 16;
+  ProfScope ps(L, PK_OTHER, 0.0, (double)P * (1024 + 512 + 512) * 4.0);
   adaptive_blend_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(o2), mask,
                                                                reinterpret_cast<const float4*>(residual), relu,
                                                                reinterpret_cast<float4*>(y), P);
   check_launch("adaptive_blend");
+}
+
+__global__ void avg2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = (a[i] + b[i]) / 2.f;
+}
+
+void avg2(const Launcher& L, const float* a, const float* b, float* y, long n) {
+  L.count();
+  if (L.dry) return;
+  long blocks = (n + 255) / 256; if (blocks > 148L * 8) blocks = 148L * 8;
+  avg2_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(a, b, y, n);
+  check_launch("avg2");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -309,6 +326,7 @@ void emit_image(const Launcher& L, const float* y, int Cs, float* img, uint8_t* 
   if (L.dry) return;
   long total = (long)B * 4 * H * W;
   long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+  ProfScope ps(L, PK_OTHER, 0.0, (double)total * 3 * (4.0 + (img ? 4.0 : 0.0) + (u8 ? 1.0 : 0.0)));
   emit_image_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(y, Cs, img, u8, B, H, W);
   check_launch("emit_image");
 }

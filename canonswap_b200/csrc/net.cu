@@ -1,0 +1,382 @@
+// The five hot-path networks expressed on the library's kernels (internal channels-last layout).
+// Every function cites the reference forward it implements; the arithmetic order inside each
+// fused step follows the reference (conv -> +bias -> BN -> act, IN -> (1+gamma) -> +beta -> act ...).
+//
+// Layout recap (DESIGN.md "Data layout"):
+//   2-D activations  [B,H,W,C] fp32
+//   feature volume   [B,H,W,16,32] fp32  == 2-D tensor with 512 channels ordered d*32+c
+//                                        == 3-D tensor (D=16, C=32) with strides sd=32, sw=512
+//   hourglass        [B,16,H,W,C] fp32 (NDHWC), skip concats are channel slices of one buffer
+#include "ctx.cuh"
+
+namespace cs {
+
+namespace {
+
+Act new_act(Net& n, int B, int D, int H, int W, int C, int Cstride = -1) {
+  if (Cstride < 0) Cstride = C;
+  float* p = n.A->f32((size_t)B * D * H * W * Cstride);
+  return make_act(p, B, D, H, W, C, Cstride);
+}
+
+struct ConvOpts {
+  int act = ACT_NONE;
+  float slope = 0.f;
+  const Act* residual = nullptr;
+  const float* mult = nullptr;
+  int xshift = 0;              // input is x nearest-upsampled by 2^xshift (no prep only)
+};
+
+Prep prep_of(const Act& src) {
+  Prep p;
+  p.src0 = src;
+  return p;
+}
+
+}  // namespace
+
+// One convolution layer: optional input transform (prep) -> conv -> fused epilogue.
+// With prep the conv input has the geometry of `out` and w.Cin channels; without, it is `x`.
+void conv_layer(Net& n, const Prep* prep, const Act& x, const ConvW& w, const ConvOpts& o, Act out) {
+  CS_REQUIRE(out.C == w.Cout, CS_ERR_INVALID, "conv_layer: Cout mismatch");
+  ConvGeom g;
+  g.PD = w.KD / 2; g.PH = w.KH / 2; g.PW = w.KW / 2;
+  g.Do = out.D; g.Ho = out.H; g.Wo = out.W;
+  Epilogue e;
+  e.act = o.act; e.slope = o.slope; e.mult = o.mult;
+  if (o.residual) {
+    e.residual = o.residual->p;
+    e.rs_b = o.residual->sb; e.rs_d = o.residual->sd; e.rs_h = o.residual->sh; e.rs_w = o.residual->sw;
+  }
+  size_t m = n.A->mark();
+  // ---- tcgen05 path: split-bf16 operand planes produced by the prep kernel ----
+  if (n.L.conv_impl != 1 && !o.xshift && conv_tc_supported(w, out)) {
+    Opd opd = conv_tc_alloc_operand(*n.A, w, out);
+    Prep ident;
+    if (!prep) { CS_REQUIRE(x.C == w.Cin, CS_ERR_INVALID, "conv_layer: Cin mismatch"); ident = prep_of(x); }
+    prep_planes(n.L, prep ? *prep : ident, opd, nullptr);
+    conv_tc(n.L, opd, w, g, e, out);
+    n.A->reset(m);
+    return;
+  }
+  // ---- fp32 SIMT path ----
+  if (prep) {
+    Act in = new_act(n, out.B, out.D, out.H, out.W, w.Cin);
+    prep_f32(n.L, *prep, in);
+    conv_simt(n.L, in, w, g, e, out, 0);
+  } else {
+    CS_REQUIRE(x.C == w.Cin, CS_ERR_INVALID, "conv_layer: Cin mismatch");
+    conv_simt(n.L, x, w, g, e, out, o.xshift);
+  }
+  n.A->reset(m);
+}
+
+// ------------------------------------------------------------------------------------------
+// blocks
+// ------------------------------------------------------------------------------------------
+// ResBlock3d, reference util.py:94-102, in place on the volume `vol` ([B,h,w,16,32]).
+static void resblock3d(Net& n, const ResBlock3dW& w, float* vol, int B, int h, int wd) {
+  size_t m = n.A->mark();
+  Act x = vol_as_3d(vol, B, h, wd);
+  Act t = vol_as_3d(n.A->f32((size_t)B * h * wd * 512), B, h, wd);
+  Prep p = prep_of(x);
+  p.norm = NORM_AFFINE_C; p.scale = w.bn1.scale; p.shift = w.bn1.shift; p.act = ACT_RELU;
+  ConvOpts o1; o1.act = ACT_RELU;                       // norm2 folded into conv1
+  conv_layer(n, &p, x, w.conv1, o1, t);
+  ConvOpts o2; o2.residual = &x;
+  conv_layer(n, nullptr, t, w.conv2, o2, x);            // out = conv2(.) + x, written over x
+  n.A->reset(m);
+}
+
+// ResBlock2d, reference util.py:120-128, in place on the volume seen as [B,h,w,512].
+static void resblock2d(Net& n, const ResBlock2dW& w, float* vol, int B, int h, int wd) {
+  size_t m = n.A->mark();
+  Act x = vol_as_2d(vol, B, h, wd);
+  Act t = new_act(n, B, 1, h, wd, 512);
+  Prep p = prep_of(x);
+  p.norm = NORM_AFFINE_C; p.scale = w.bn1.scale; p.shift = w.bn1.shift; p.act = ACT_LRELU; p.slope = 0.01f;
+  ConvOpts o1; o1.act = ACT_LRELU; o1.slope = 0.01f;
+  conv_layer(n, &p, x, w.conv1, o1, t);
+  ConvOpts o2; o2.residual = &x;
+  conv_layer(n, nullptr, t, w.conv2, o2, x);
+  n.A->reset(m);
+}
+
+// ResBlock3D_stage3_leak, reference util.py:528-544 (GroupNorm(32,32) == per-(b,c) instance norm), in place.
+static void gn_resblock3d(Net& n, const GnResBlockW& w, float* vol, int B, int h, int wd) {
+  size_t m = n.A->mark();
+  Act x = vol_as_3d(vol, B, h, wd);
+  Act t1 = vol_as_3d(n.A->f32((size_t)B * h * wd * 512), B, h, wd);
+  Act t2 = vol_as_3d(n.A->f32((size_t)B * h * wd * 512), B, h, wd);
+  float* mean = n.A->f32((size_t)B * 32);
+  float* rstd = n.A->f32((size_t)B * 32);
+  conv_layer(n, nullptr, x, w.conv1, ConvOpts(), t1);
+  instance_stats(n.L, t1, mean, rstd, 1e-5f, n.ctx->stats_scratch);
+  Prep p = prep_of(t1);
+  p.norm = NORM_STATS_BC; p.mean = mean; p.rstd = rstd; p.scale = w.gn1.scale; p.shift = w.gn1.shift;
+  p.act = ACT_LRELU; p.slope = 0.01f;
+  conv_layer(n, &p, t1, w.conv2, ConvOpts(), t2);
+  instance_stats(n.L, t2, mean, rstd, 1e-5f, n.ctx->stats_scratch);
+  Prep q = prep_of(t2);
+  q.norm = NORM_STATS_BC; q.mean = mean; q.rstd = rstd; q.scale = w.gn2.scale; q.shift = w.gn2.shift;
+  q.add = x; q.act = ACT_LRELU; q.slope = 0.01f;
+  prep_f32(n.L, q, x);                                   // lrelu(gn2(.) + x) -> x (element-wise, safe in place)
+  n.A->reset(m);
+}
+
+// ------------------------------------------------------------------------------------------
+// F : AppearanceFeatureExtractor.forward, reference appearance_feature_extractor.py:38-48
+// ------------------------------------------------------------------------------------------
+void run_F(Net& n, const float* img_cl, int B, float* vol_out) {
+  const Weights& W = n.W();
+  const int H = n.ctx->net_h, Wd = n.ctx->net_w, h = n.ctx->h, w = n.ctx->w;
+  size_t m = n.A->mark();
+  Act img = make_act(const_cast<float*>(img_cl), B, 1, H, Wd, 3);
+  ConvOpts relu; relu.act = ACT_RELU;
+  Act a0 = new_act(n, B, 1, H, Wd, 64);
+  conv_layer(n, nullptr, img, W.f_first, relu, a0);                       // SameBlock2d util.py:207-211
+  Act a1 = new_act(n, B, 1, H, Wd, 128);
+  conv_layer(n, nullptr, a0, W.f_down[0], relu, a1);                      // DownBlock2d util.py:161-166 (pool below)
+  Act a2 = new_act(n, B, 1, H / 2, Wd / 2, 256);
+  Prep p1 = prep_of(a1); p1.pool2 = 1;
+  conv_layer(n, &p1, a1, W.f_down[1], relu, a2);
+  Prep p2 = prep_of(a2); p2.pool2 = 1;
+  Act vol2d = vol_as_2d(vol_out, B, h, w);
+  conv_layer(n, &p2, a2, W.f_second, ConvOpts(), vol2d);                  // 1x1, Cout pre-permuted to d*32+c
+  n.A->reset(m);
+  for (int i = 0; i < 6; ++i) resblock3d(n, W.f_res[i], vol_out, B, h, w);
+}
+
+// ------------------------------------------------------------------------------------------
+// DenseMotionNetwork.forward, reference dense_motion.py:67-104.
+// Produces mask logits [B,16,h,w,24 (22 valid)], and the occlusion map [B,h,w].
+// ------------------------------------------------------------------------------------------
+static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, const float* kp_source, int B,
+                         Act* logits_out, float* occ) {
+  const Weights& W = n.W();
+  const int h = n.ctx->h, w = n.ctx->w, D = 16;
+  ConvOpts relu; relu.act = ACT_RELU;
+  // compress 1x1x1 32->4 + BN + ReLU (:70-72)
+  Act vol3 = vol_as_3d(const_cast<float*>(vol_in), B, h, w);
+  Act c4 = new_act(n, B, D, h, w, 4);
+  conv_layer(n, nullptr, vol3, W.dm_compress, relu, c4);
+  // concat buffers of the hourglass decoder (reference util.py:259-260: cat([out, skip]))
+  const int hs[6] = {h, h / 2, h / 4, h / 8, h / 16, h / 32};
+  const int ws[6] = {w, w / 2, w / 4, w / 8, w / 16, w / 32};
+  CS_REQUIRE(hs[5] >= 1 && ws[5] >= 1, CS_ERR_INVALID, "feature resolution too small for the 5-level hourglass");
+  Act cat5 = new_act(n, B, D, hs[0], ws[0], HG_OUT);     // [up4 32 | x 110]
+  Act cat4 = new_act(n, B, D, hs[1], ws[1], 128);        // [up3 64 | p0 64]
+  Act cat3 = new_act(n, B, D, hs[2], ws[2], 256);        // [up2 128 | p1 128]
+  Act cat2 = new_act(n, B, D, hs[3], ws[3], 512);        // [up1 256 | p2 256]
+  Act cat1 = new_act(n, B, D, hs[4], ws[4], 1024);       // [up0 512 | p3 512]
+  Act p4 = new_act(n, B, D, hs[5], ws[5], 1024);
+  // hourglass input: [heat_k, deformed_k(4)] per keypoint (:29-65, :83-84)
+  Act x = slice_c(cat5, 32, HG_IN);
+  dm_input(n.L, c4, kp_driving, kp_source, NUM_KP, x);
+  // encoder: conv-BN-ReLU at full res, then avg-pool (1,2,2) into the skip slice (util.py:185-190)
+  Act skips[5] = {slice_c(cat4, 64, 64), slice_c(cat3, 128, 128), slice_c(cat2, 256, 256), slice_c(cat1, 512, 512), p4};
+  Act cur = x;
+  for (int i = 0; i < 5; ++i) {
+    size_t m = n.A->mark();
+    Act e = new_act(n, B, D, hs[i], ws[i], W.hg_enc[i].Cout);
+    conv_layer(n, nullptr, cur, W.hg_enc[i], relu, e);
+    Prep pp = prep_of(e); pp.pool2 = 1;
+    prep_f32(n.L, pp, skips[i]);
+    n.A->reset(m);
+    cur = skips[i];
+  }
+  // decoder: nearest (1,2,2) upsample -> conv-BN-ReLU -> written next to its skip (util.py:142-147,255-262)
+  Act cats[5] = {cat1, cat2, cat3, cat4, cat5};
+  Act dcur = p4;
+  for (int i = 0; i < 5; ++i) {
+    Act dst = slice_c(cats[i], 0, W.hg_dec[i].Cout);
+    if (n.L.conv_impl == 1 || !conv_tc_supported(W.hg_dec[i], dst)) {
+      ConvOpts o = relu; o.xshift = 1;
+      conv_layer(n, nullptr, dcur, W.hg_dec[i], o, dst);
+    } else {
+      Prep up = prep_of(dcur); up.upshift = 1;
+      conv_layer(n, &up, dcur, W.hg_dec[i], relu, dst);
+    }
+    dcur = cats[i];
+  }
+  Act pred = new_act(n, B, D, h, w, HG_OUT);
+  conv_layer(n, nullptr, cat5, W.hg_final, relu, pred);
+  // mask logits 7x7x7 (:88); softmax is fused into the flow/warp kernel
+  Act logits = new_act(n, B, D, h, w, NUM_KP + 1, 24);
+  conv_layer(n, nullptr, pred, W.dm_mask, ConvOpts(), logits);
+  *logits_out = logits;
+  // occlusion 7x7 over (c*16+d) channels == conv3d kernel (16,7,7), pad (0,3,3) (:98-102)
+  ConvGeom g; g.PD = 0; g.PH = 3; g.PW = 3; g.Do = 1; g.Ho = h; g.Wo = w;
+  conv_cout1(n.L, pred, W.dm_occlusion, g, ACT_SIGMOID, occ);
+}
+
+// WarpingNetwork.warp, reference warping_network.py:49-62
+void run_warp(Net& n, const float* vol_in, const float* kp_source, const float* kp_driving, int B, float* vol_out,
+              float* occ, float* deformation) {
+  size_t m = n.A->mark();
+  Act logits;
+  float* occ_buf = occ ? occ : n.A->f32((size_t)B * n.ctx->h * n.ctx->w);
+  dense_motion(n, vol_in, kp_driving, kp_source, B, &logits, occ_buf);
+  softmax_flow_warp(n.L, logits, kp_driving, kp_source, NUM_KP, vol_in, vol_out, deformation);
+  n.A->reset(m);
+}
+
+// WarpingNetwork.warp_out, reference warping_network.py:64-71
+void run_warp_out(Net& n, const float* vol_in, const float* occ, int B, float* out256) {
+  const Weights& W = n.W();
+  const int h = n.ctx->h, w = n.ctx->w;
+  size_t m = n.A->mark();
+  Act x = vol_as_2d(const_cast<float*>(vol_in), B, h, w);
+  Act t = new_act(n, B, 1, h, w, 256);
+  ConvOpts o1; o1.act = ACT_LRELU; o1.slope = 0.01f;                      // SameBlock2d(lrelu=True), BN folded
+  conv_layer(n, nullptr, x, W.w_third, o1, t);
+  ConvOpts o2; o2.mult = occ;                                             // out * occlusion_map
+  conv_layer(n, nullptr, t, W.w_fourth, o2, make_act(out256, B, 1, h, w, 256));
+  n.A->reset(m);
+}
+
+// ------------------------------------------------------------------------------------------
+// swap : transfer_model2.forward, reference adaptive_modulate.py:522-554
+// ------------------------------------------------------------------------------------------
+// AdaptiveSharedWeightConv2d.forward (:128-193) as ONE conv with Cout = 1024 = [W | W*s*demod],
+// a 512->1 mask conv and the blend  mask*out_mod + (1-mask)*out_std (+ReLU / +residual).
+static void adaptive_conv(Net& n, const AdaptiveConvW& a, const Act& x, const float* residual, int relu, float* y,
+                          float* mask) {
+  size_t m = n.A->mark();
+  long P = x.pixels();
+  Act o2 = new_act(n, x.B, 1, x.H, x.W, 1024);
+  conv_layer(n, nullptr, x, a.combined, ConvOpts(), o2);
+  ConvGeom g; g.PD = 0; g.PH = 1; g.PW = 1; g.Do = 1; g.Ho = x.H; g.Wo = x.W;
+  conv_cout1(n.L, x, a.mask_conv, g, ACT_SIGMOID, mask);
+  adaptive_blend(n.L, o2.p, mask, residual, relu, y, P);
+  n.A->reset(m);
+}
+
+void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks) {
+  CS_REQUIRE(n.ctx->identity_set, CS_ERR_STATE, "cs_swap / cs_frame before cs_set_identity");
+  const Weights& W = n.W();
+  const int h = n.ctx->h, w = n.ctx->w;
+  const long P = (long)B * h * w;
+  size_t m = n.A->mark();
+  if (vol_out != vol_in && !n.L.dry)
+    CS_CUDA(cudaMemcpyAsync(vol_out, vol_in, (size_t)P * 512 * sizeof(float), cudaMemcpyDeviceToDevice, n.L.stream));
+  float* y1 = n.A->f32((size_t)P * 512);
+  float* m1 = n.A->f32((size_t)P);
+  float* m2 = n.A->f32((size_t)P);
+  Act x = vol_as_2d(vol_out, B, h, w);
+  Act t = vol_as_2d(y1, B, h, w);
+  for (int i = 0; i < 7; ++i) {                                           // ResnetBlock_Adaptive2D :337-349
+    adaptive_conv(n, W.ad[2 * i], x, nullptr, 1, y1, m1);
+    adaptive_conv(n, W.ad[2 * i + 1], t, vol_out, 0, vol_out, m2);        // x + y, in place
+    if (masks) avg2(n.L, m1, m2, masks + (long)i * P, P);
+  }
+  n.A->reset(m);
+  for (int i = 0; i < 6; ++i) resblock3d(n, W.t_res[i], vol_out, B, h, w);
+}
+
+// ------------------------------------------------------------------------------------------
+// refine : G3d.forward, reference adaptive_modulate.py:721-733
+// ------------------------------------------------------------------------------------------
+void run_refine(Net& n, const float* vol_in, int B, float* vol_out) {
+  const Weights& W = n.W();
+  const int h = n.ctx->h, w = n.ctx->w;
+  if (vol_out != vol_in && !n.L.dry)
+    CS_CUDA(cudaMemcpyAsync(vol_out, vol_in, (size_t)B * h * w * 512 * sizeof(float), cudaMemcpyDeviceToDevice, n.L.stream));
+  for (int i = 0; i < 3; ++i) gn_resblock3d(n, W.r_gn1[i], vol_out, B, h, w);
+  for (int i = 0; i < 3; ++i) resblock2d(n, W.r_res2[i], vol_out, B, h, w);
+  for (int i = 0; i < 3; ++i) gn_resblock3d(n, W.r_gn3[i], vol_out, B, h, w);
+}
+
+// ------------------------------------------------------------------------------------------
+// G : SPADEDecoder.forward, reference spade_generator.py:41-59
+// ------------------------------------------------------------------------------------------
+// SPADE (util.py:295-302): gamma|beta = conv(relu(conv(nearest(seg)))) as one Cout = 2C tensor [P, 2C]
+static float* spade_gamma_beta(Net& n, const SpadeNormW& s, const Act& seg, int segshift, int B, int H, int W) {
+  Act gb = new_act(n, B, 1, H, W, 2 * s.C);
+  size_t m = n.A->mark();
+  Act actv = new_act(n, B, 1, H, W, 128);
+  ConvOpts relu; relu.act = ACT_RELU;
+  if (segshift == 0) {
+    conv_layer(n, nullptr, seg, s.shared, relu, actv);
+  } else if (n.L.conv_impl == 1 || !conv_tc_supported(s.shared, actv)) {
+    relu.xshift = segshift;
+    conv_layer(n, nullptr, seg, s.shared, relu, actv);
+  } else {
+    Prep up = prep_of(seg); up.upshift = segshift;
+    conv_layer(n, &up, seg, s.shared, relu, actv);
+  }
+  conv_layer(n, nullptr, actv, s.gamma_beta, ConvOpts(), gb);
+  n.A->reset(m);
+  return gb.p;
+}
+
+// SPADEResnetBlock (util.py:329-344). x is read nearest-upsampled by 2^xup; returns [B,H,W,fout].
+static Act spade_block(Net& n, const SpadeBlockW& b, const Act& x, int xup, const Act& seg, int segshift, Act out) {
+  const int B = x.B, H = x.H << xup, W = x.W << xup;
+  size_t m = n.A->mark();
+  // InstanceNorm statistics of x (nearest upsampling leaves mean / biased variance unchanged)
+  float* mean = n.A->f32((size_t)B * b.fin);
+  float* rstd = n.A->f32((size_t)B * b.fin);
+  instance_stats(n.L, x, mean, rstd, 1e-5f, n.ctx->stats_scratch);
+  // shortcut
+  Act xs;
+  if (b.learned_shortcut) {
+    xs = new_act(n, B, 1, H, W, b.fout);
+    size_t m2 = n.A->mark();
+    float* gbs = spade_gamma_beta(n, b.norm_s, seg, segshift, B, H, W);
+    Prep ps = prep_of(x); ps.upshift = xup; ps.norm = NORM_STATS_BC; ps.mean = mean; ps.rstd = rstd; ps.gb = gbs;
+    conv_layer(n, &ps, x, b.conv_s, ConvOpts(), xs);
+    n.A->reset(m2);
+  } else {
+    CS_REQUIRE(xup == 0, CS_ERR_INVALID, "identity shortcut needs an un-upsampled input");
+    xs = x;
+  }
+  // dx = conv_0(lrelu(norm_0(x, seg), 0.2))
+  Act dx = new_act(n, B, 1, H, W, b.fmid);
+  {
+    size_t m2 = n.A->mark();
+    float* gb0 = spade_gamma_beta(n, b.norm_0, seg, segshift, B, H, W);
+    Prep p0 = prep_of(x); p0.upshift = xup; p0.norm = NORM_STATS_BC; p0.mean = mean; p0.rstd = rstd; p0.gb = gb0;
+    p0.act = ACT_LRELU; p0.slope = 0.2f;
+    conv_layer(n, &p0, x, b.conv_0, ConvOpts(), dx);
+    n.A->reset(m2);
+  }
+  // out = x_s + conv_1(lrelu(norm_1(dx, seg), 0.2))
+  {
+    float* mean1 = n.A->f32((size_t)B * b.fmid);
+    float* rstd1 = n.A->f32((size_t)B * b.fmid);
+    instance_stats(n.L, dx, mean1, rstd1, 1e-5f, n.ctx->stats_scratch);
+    float* gb1 = spade_gamma_beta(n, b.norm_1, seg, segshift, B, H, W);
+    Prep p1 = prep_of(dx); p1.norm = NORM_STATS_BC; p1.mean = mean1; p1.rstd = rstd1; p1.gb = gb1;
+    p1.act = ACT_LRELU; p1.slope = 0.2f;
+    ConvOpts o; o.residual = &xs;
+    conv_layer(n, &p1, dx, b.conv_1, o, out);
+  }
+  n.A->reset(m);
+  return out;
+}
+
+void run_spade(Net& n, const float* feat256, int B, float* img_nchw, uint8_t* img_u8) {
+  const Weights& W = n.W();
+  const int h = n.ctx->h, w = n.ctx->w;
+  size_t m = n.A->mark();
+  Act seg = make_act(const_cast<float*>(feat256), B, 1, h, w, 256);
+  Act xa = new_act(n, B, 1, h, w, 512);
+  Act xb = new_act(n, B, 1, h, w, 512);
+  conv_layer(n, nullptr, seg, W.g_fc, ConvOpts(), xa);
+  for (int i = 0; i < 6; ++i) {                                           // G_middle_0..5
+    spade_block(n, W.g_blocks[i], xa, 0, seg, 0, xb);
+    Act t = xa; xa = xb; xb = t;
+  }
+  Act u0 = new_act(n, B, 1, 2 * h, 2 * w, 256);
+  spade_block(n, W.g_blocks[6], xa, 1, seg, 1, u0);                       // up -> up_0
+  Act u1 = new_act(n, B, 1, 4 * h, 4 * w, 64);
+  spade_block(n, W.g_blocks[7], u0, 1, seg, 2, u1);                       // up -> up_1
+  Act y = new_act(n, B, 1, 4 * h, 4 * w, 12);
+  Prep pl = prep_of(u1); pl.act = ACT_LRELU; pl.slope = 0.2f;             // conv_img(leaky_relu(x, 0.2))
+  conv_layer(n, &pl, u1, W.g_img, ConvOpts(), y);
+  emit_image(n.L, y.p, 12, img_nchw, img_u8, B, 4 * h, 4 * w);            // PixelShuffle(2) + sigmoid (+ u8)
+  n.A->reset(m);
+}
+
+}  // namespace cs

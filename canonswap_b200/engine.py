@@ -1,0 +1,271 @@
+"""Engine: one `cs_ctx` of libcanonswap_b200.so bound to a CUDA device.
+
+Thin and explicit: torch is used only for device memory (`tensor.data_ptr()`), the current CUDA
+stream and lifetime; every computation is a C-ABI call into the hand-written sm_100a kernels.
+No call here ever falls back to PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional
+
+import torch
+
+from . import _lib, spec
+
+
+class CanonSwapError(RuntimeError):
+    """A negative cs_status from the C ABI (message = cs_last_error)."""
+
+
+def _flat_table(weights: Mapping[str, Mapping[str, torch.Tensor]]):
+    """`combined_weights.pth`-layout dict -> (cs_tensor_desc array, keep-alive list)."""
+    names, tensors = [], []
+    for net in spec.NETS:
+        if net not in weights:
+            raise KeyError(f"weights dict lacks the '{net}' state_dict (reference can_swap_e2e.py:93-98)")
+        for key, t in weights[net].items():
+            t = t.detach()
+            if t.dtype == torch.float32:
+                dt = _lib.CS_F32
+            elif t.dtype == torch.int64:
+                dt = _lib.CS_I64
+            else:
+                raise TypeError(f"{net}.{key}: unsupported dtype {t.dtype} (the reference checkpoint is fp32)")
+            names.append((f"{net}.{key}".encode(), dt))
+            tensors.append(t.to("cpu").contiguous())
+    arr = (_lib.TensorDesc * len(names))()
+    for i, ((name, dt), t) in enumerate(zip(names, tensors)):
+        arr[i].name = name
+        arr[i].data = t.data_ptr()
+        arr[i].dtype = dt
+        arr[i].ndim = t.dim()
+        for j, s in enumerate(t.shape):
+            arr[i].shape[j] = s
+    return arr, (names, tensors)
+
+
+class Engine:
+    """Owns a cs_ctx: packed weights + workspace for frames of `net_hw` up to `max_batch` per call."""
+
+    def __init__(self, weights: Mapping[str, Mapping[str, torch.Tensor]], net_hw=(256, 256), max_batch: int = 8,
+                 device: int = 0, conv_impl: int = 0):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        self.device = torch.device("cuda", device)
+        self.net_h, self.net_w = int(net_hw[0]), int(net_hw[1])
+        self.h, self.w = self.net_h // 4, self.net_w // 4
+        self.max_batch = int(max_batch)
+        rc = self._lib.cs_create(C.byref(self._ctx), device, self.max_batch, self.net_h, self.net_w)
+        if rc != 0:
+            msg = self._lib.cs_last_error(None).decode()
+            self._ctx = C.c_void_p()
+            raise CanonSwapError(f"cs_create failed ({rc}): {msg}")
+        if conv_impl:
+            self.set_option(_lib.CS_OPT_CONV_IMPL, conv_impl)
+        table, keep = _flat_table(weights)
+        self._check(self._lib.cs_load_weights(self._ctx, table, len(table)))
+        del keep
+        self._identity = None
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.cs_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CanonSwapError(f"canonswap_b200 error {rc}: {self._lib.cs_last_error(self._ctx).decode()}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _in(self, t: torch.Tensor, shape, dtype=torch.float32, name="tensor") -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+        if t.device != self.device:
+            raise ValueError(f"{name}: tensor is on {t.device}, engine is on {self.device} (no implicit copies)")
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: shape {tuple(t.shape)} != expected {tuple(shape)}")
+        if t.dtype != dtype:
+            raise TypeError(f"{name}: dtype {t.dtype} != expected {dtype}")
+        return t.detach().contiguous()
+
+    def _batch(self, t: torch.Tensor) -> int:
+        B = int(t.shape[0])
+        if not 1 <= B <= self.max_batch:
+            raise ValueError(f"batch {B} outside [1, max_batch={self.max_batch}]")
+        return B
+
+    def _new(self, *shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------------------------------
+    def set_option(self, option: int, value: int):
+        self._check(self._lib.cs_set_option(self._ctx, option, value))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.cs_launch_count(self._ctx))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self._lib.cs_workspace_bytes(self._ctx))
+
+    def set_identity(self, source_id: torch.Tensor):
+        """source_id [1,512] (or [512]) fp32 on the engine device: ArcFace identity, L2-normalised
+        (reference can_swap_e2e.py:102-107)."""
+        sid = source_id.reshape(-1)
+        sid = self._in(sid, (spec.LATENT,), name="source_id")
+        self._check(self._lib.cs_set_identity(self._ctx, sid.data_ptr(), self._stream()))
+        self._identity = sid
+
+    # ---- per-stage calls (reference module forwards) ------------------------------------------
+    def appearance(self, x: torch.Tensor) -> torch.Tensor:
+        B = self._batch(x)
+        x = self._in(x, (B, 3, self.net_h, self.net_w), name="x")
+        out = self._new(B, 32, 16, self.h, self.w)
+        self._check(self._lib.cs_appearance(self._ctx, x.data_ptr(), out.data_ptr(), B, self._stream()))
+        return out
+
+    def _kp(self, kp, B, name):
+        return self._in(kp, (B, spec.NUM_KP, 3), name=name)
+
+    def warp(self, feature_3d, kp_source, kp_driving, want_deformation=False):
+        B = self._batch(feature_3d)
+        f = self._in(feature_3d, (B, 32, 16, self.h, self.w), name="feature_3d")
+        ks, kd = self._kp(kp_source, B, "kp_source"), self._kp(kp_driving, B, "kp_driving")
+        out = self._new(B, 32, 16, self.h, self.w)
+        occ = self._new(B, 1, self.h, self.w)
+        deform = self._new(B, 16, self.h, self.w, 3) if want_deformation else None
+        self._check(self._lib.cs_warp(self._ctx, f.data_ptr(), ks.data_ptr(), kd.data_ptr(), out.data_ptr(),
+                                      occ.data_ptr(), deform.data_ptr() if deform is not None else None, B,
+                                      self._stream()))
+        return (out, occ, deform) if want_deformation else (out, occ)
+
+    def warp_out(self, out3d, occlusion_map=None):
+        B = self._batch(out3d)
+        f = self._in(out3d, (B, 32, 16, self.h, self.w), name="out")
+        occ = self._in(occlusion_map, (B, 1, self.h, self.w), name="occlusion_map") if occlusion_map is not None else None
+        out = self._new(B, 256, self.h, self.w)
+        self._check(self._lib.cs_warp_out(self._ctx, f.data_ptr(), occ.data_ptr() if occ is not None else None,
+                                          out.data_ptr(), B, self._stream()))
+        return out
+
+    def warp_forward(self, feature_3d, kp_driving, kp_source):
+        B = self._batch(feature_3d)
+        f = self._in(feature_3d, (B, 32, 16, self.h, self.w), name="feature_3d")
+        ks, kd = self._kp(kp_source, B, "kp_source"), self._kp(kp_driving, B, "kp_driving")
+        out = self._new(B, 256, self.h, self.w)
+        occ = self._new(B, 1, self.h, self.w)
+        deform = self._new(B, 16, self.h, self.w, 3)
+        self._check(self._lib.cs_warp_forward(self._ctx, f.data_ptr(), kd.data_ptr(), ks.data_ptr(), out.data_ptr(),
+                                              occ.data_ptr(), deform.data_ptr(), B, self._stream()))
+        return {"occlusion_map": occ, "deformation": deform, "out": out}
+
+    def swap(self, feature_3d, return_mask=False):
+        if self._identity is None:
+            raise CanonSwapError("swap: no identity set (call set_identity first)")
+        B = self._batch(feature_3d)
+        f = self._in(feature_3d, (B, 32, 16, self.h, self.w), name="x")
+        out = self._new(B, 32, 16, self.h, self.w)
+        masks = self._new(7, B, 1, self.h, self.w) if return_mask else None
+        self._check(self._lib.cs_swap(self._ctx, f.data_ptr(), out.data_ptr(),
+                                      masks.data_ptr() if masks is not None else None, B, self._stream()))
+        return (out, list(masks.unbind(0))) if return_mask else out
+
+    def refine(self, feature_3d):
+        B = self._batch(feature_3d)
+        f = self._in(feature_3d, (B, 32, 16, self.h, self.w), name="x")
+        out = self._new(B, 32, 16, self.h, self.w)
+        self._check(self._lib.cs_refine(self._ctx, f.data_ptr(), out.data_ptr(), B, self._stream()))
+        return out
+
+    def spade(self, feature, want_u8=False):
+        B = self._batch(feature)
+        f = self._in(feature, (B, 256, self.h, self.w), name="feature")
+        img = self._new(B, 3, 2 * self.net_h, 2 * self.net_w)
+        u8 = self._new(B, 2 * self.net_h, 2 * self.net_w, 3, dtype=torch.uint8) if want_u8 else None
+        self._check(self._lib.cs_spade(self._ctx, f.data_ptr(), img.data_ptr(),
+                                       u8.data_ptr() if u8 is not None else None, B, self._stream()))
+        return (img, u8) if want_u8 else img
+
+    # ---- the fused loop body --------------------------------------------------------------------
+    def frame(self, frames: torch.Tensor, kp_t: torch.Tensor, kp_can: torch.Tensor, out_u8: Optional[torch.Tensor] = None,
+              out_f32: Optional[torch.Tensor] = None, debug_decodes: bool = False):
+        """One batch of the per-frame loop body (reference can_swap_pipeline_e2e.py:242-267).
+
+        frames: [B,net_h,net_w,3] uint8 (HWC, as cropped) or [B,3,net_h,net_w] fp32 in [0,1];
+        kp_t = x_t_info['x_s'], kp_can = scale * kp  (both [B,21,3]).
+        Returns (out_u8 [B,2H,2W,3] uint8, out_f32 [B,3,2H,2W] or None).
+        """
+        if self._identity is None:
+            raise CanonSwapError("frame: no identity set (call set_identity first)")
+        B = self._batch(frames)
+        flags = _lib.CS_FRAME_DEBUG_DECODES if debug_decodes else 0
+        if frames.dtype == torch.uint8:
+            fr = self._in(frames, (B, self.net_h, self.net_w, 3), dtype=torch.uint8, name="frames")
+            flags |= _lib.CS_FRAME_IN_U8_HWC
+        else:
+            fr = self._in(frames, (B, 3, self.net_h, self.net_w), name="frames")
+        kt, kc = self._kp(kp_t, B, "kp_t"), self._kp(kp_can, B, "kp_can")
+        if out_u8 is None and out_f32 is None:
+            out_u8 = self._new(B, 2 * self.net_h, 2 * self.net_w, 3, dtype=torch.uint8)
+        if out_u8 is not None:
+            out_u8 = self._in(out_u8, (B, 2 * self.net_h, 2 * self.net_w, 3), dtype=torch.uint8, name="out_u8")
+        if out_f32 is not None:
+            out_f32 = self._in(out_f32, (B, 3, 2 * self.net_h, 2 * self.net_w), name="out_f32")
+        self._check(self._lib.cs_frame(self._ctx, fr.data_ptr(), kt.data_ptr(), kc.data_ptr(),
+                                       out_f32.data_ptr() if out_f32 is not None else None,
+                                       out_u8.data_ptr() if out_u8 is not None else None, B, flags, self._stream()))
+        return out_u8, out_f32
+
+    # ---- measurement -------------------------------------------------------------------------------
+    PROFILE_FAMILIES = ("conv_tcgen05", "conv_simt", "prep", "stats", "sampling", "other")
+
+    def profile(self, enable: bool):
+        self._check(self._lib.cs_profile(self._ctx, 1 if enable else 0))
+
+    def profile_read(self):
+        """{family: dict(ms, flops, bytes, launches)} accumulated since profile(True) / the last read."""
+        buf = (C.c_double * 24)()
+        self._check(self._lib.cs_profile_read(self._ctx, buf))
+        return {name: {"ms": buf[4 * i], "flops": buf[4 * i + 1], "bytes": buf[4 * i + 2], "launches": int(buf[4 * i + 3])}
+                for i, name in enumerate(self.PROFILE_FAMILIES)}
+
+    # ---- kernel-level test entry points ---------------------------------------------------------
+    def test_conv(self, x_cl, w, bias, pad, act=0, slope=0.0, impl=0):
+        """x_cl [B,D,H,W,Cin] channels-last, w [Cout,Cin,KD,KH,KW] -> y [B,Do,Ho,Wo,Cout]."""
+        B, D, H, W, Cin = x_cl.shape
+        Cout, _, KD, KH, KW = w.shape
+        PD, PH, PW = pad
+        Do, Ho, Wo = D + 2 * PD - KD + 1, H + 2 * PH - KH + 1, W + 2 * PW - KW + 1
+        y = self._new(B, Do, Ho, Wo, Cout)
+        x_cl, w = x_cl.contiguous(), w.contiguous()
+        b = bias.contiguous() if bias is not None else None
+        self._check(self._lib.cs_test_conv(self._ctx, x_cl.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None,
+                                           y.data_ptr(), B, D, H, W, Cin, Cout, KD, KH, KW, PD, PH, PW, act, float(slope),
+                                           impl, self._stream()))
+        return y
+
+    def test_grid_sample3d(self, inp, grid):
+        B, Cc, D, H, W = inp.shape
+        out = torch.empty_like(inp)
+        self._check(self._lib.cs_test_grid_sample3d(self._ctx, inp.contiguous().data_ptr(), grid.contiguous().data_ptr(),
+                                                    out.data_ptr(), B, Cc, D, H, W, self._stream()))
+        return out
+
+    def test_instance_stats(self, x, eps=1e-5):
+        B, Cc = x.shape[:2]
+        S = x[0, 0].numel()
+        mean, rstd = self._new(B, Cc), self._new(B, Cc)
+        self._check(self._lib.cs_test_instance_stats(self._ctx, x.contiguous().data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                     B, Cc, S, float(eps), self._stream()))
+        return mean, rstd

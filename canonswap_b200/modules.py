@@ -1,0 +1,324 @@
+"""Host-side mirror of the reference's operator surface for the generator hot path.
+
+The reference has no plugin registry: its "operator API" is the set of `nn.Module` attributes and
+wrapper methods on `can_swapper` that `CanSwapPipeline.execute` calls per frame
+(reference src/can_swap_e2e.py:39-348, src/can_swap_pipeline_e2e.py:223-283).  The classes below
+keep those names, argument orders, return types, `state_dict` keys and `.to()/.eval()` behaviour,
+but own no arithmetic: every `forward` is one C-ABI call into libcanonswap_b200.so via `Engine`.
+
+    AppearanceFeatureExtractor   reference src/modules/appearance_feature_extractor.py:14-48
+    WarpingNetwork               reference src/modules/warping_network.py:14-111
+    SPADEDecoder                 reference src/modules/spade_generator.py:13-59
+    transfer_model2 (= transfer_model_big)   reference src/modules/adaptive_modulate.py:485-554
+    G3d                          reference src/modules/adaptive_modulate.py:700-733
+    can_swapper                  reference src/can_swap_e2e.py:39-348 (hot-path members only)
+
+A module is bound to a shared `_EngineHub`; weights are (re)packed lazily on the first forward
+after `load_state_dict`.  Tensors must live on the hub's CUDA device: there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import spec
+from .engine import CanonSwapError, Engine
+
+_BUFFER_LEAVES = ("running_mean", "running_var", "num_batches_tracked", "weight_u", "weight_v")
+
+
+class _EngineHub:
+    """Shares one Engine per (net_h, net_w) among the five mirror modules."""
+
+    def __init__(self, device_id: int = 0, max_batch: int = 8, conv_impl: int = 0):
+        self.device_id, self.max_batch, self.conv_impl = device_id, max_batch, conv_impl
+        self.modules: Dict[str, "_SpecModule"] = {}
+        self.engines: Dict[Tuple[int, int], Engine] = {}
+        self.identity: Optional[torch.Tensor] = None
+        self.version = 0
+
+    def register(self, mod: "_SpecModule"):
+        self.modules[mod.NET] = mod
+        self.invalidate()
+
+    def invalidate(self):
+        for e in self.engines.values():
+            e.close()
+        self.engines.clear()
+        self.version += 1
+
+    def engine(self, net_hw: Tuple[int, int], batch: int = 1) -> Engine:
+        missing = [n for n in spec.NETS if n not in self.modules]
+        if missing:
+            raise CanonSwapError(f"engine needs all five hot-path networks; not bound: {missing}")
+        if batch > self.max_batch:
+            self.max_batch = batch
+            self.invalidate()
+        e = self.engines.get(net_hw)
+        if e is None:
+            weights = {n: m.state_dict() for n, m in self.modules.items()}
+            e = Engine(weights, net_hw=net_hw, max_batch=self.max_batch, device=self.device_id, conv_impl=self.conv_impl)
+            if self.identity is not None:
+                e.set_identity(self.identity)
+            self.engines[net_hw] = e
+        return e
+
+    def set_identity(self, source_id: torch.Tensor):
+        self.identity = source_id.detach().reshape(-1).clone()
+        for e in self.engines.values():
+            e.set_identity(self.identity)
+
+
+class _SpecModule(nn.Module):
+    """Parameters / buffers registered exactly as the reference module's state_dict lays them out."""
+    NET = ""
+
+    def __init__(self, hub: Optional[_EngineHub] = None):
+        super().__init__()
+        for key, shape in spec.net_spec(self.NET).items():
+            parts = key.split(".")
+            mod = self
+            for p in parts[:-1]:
+                if not hasattr(mod, p):
+                    mod.add_module(p, nn.Module())
+                mod = getattr(mod, p)
+            leaf = parts[-1]
+            if leaf == "num_batches_tracked":
+                mod.register_buffer(leaf, torch.zeros(shape, dtype=torch.int64))
+            elif leaf in _BUFFER_LEAVES:
+                mod.register_buffer(leaf, torch.zeros(shape, dtype=torch.float32))
+            else:
+                mod.register_parameter(leaf, nn.Parameter(torch.zeros(shape, dtype=torch.float32), requires_grad=False))
+        self._hub = hub if hub is not None else _EngineHub()
+        self._hub.register(self)
+        self.eval()
+
+    def bind(self, hub: _EngineHub):
+        self.__dict__["_hub"] = hub
+        hub.register(self)
+        return self
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        r = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self._hub.invalidate()
+        return r
+
+    def _apply(self, fn, recurse=True):
+        r = super()._apply(fn, recurse)
+        self._hub.invalidate()
+        return r
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise CanonSwapError("canonswap_b200 modules are inference-only (eval mode)")
+        return super().train(False)
+
+    def _engine(self, x: torch.Tensor, net_hw: Tuple[int, int]) -> Engine:
+        if not x.is_cuda:
+            raise CanonSwapError(f"{type(self).__name__}: input is on {x.device}; this implementation runs on "
+                                 "CUDA (B200) only and has no CPU fallback")
+        if x.device.index != self._hub.device_id:
+            raise CanonSwapError(f"input on cuda:{x.device.index}, engine bound to cuda:{self._hub.device_id}")
+        return self._hub.engine(net_hw, int(x.shape[0]))
+
+
+class AppearanceFeatureExtractor(_SpecModule):
+    NET = "appearance_feature_extractor"
+
+    def __init__(self, image_channel=3, block_expansion=64, num_down_blocks=2, max_features=512, reshape_channel=32,
+                 reshape_depth=16, num_resblocks=6, hub=None):
+        cfg = (image_channel, block_expansion, num_down_blocks, max_features, reshape_channel, reshape_depth, num_resblocks)
+        if cfg != (3, 64, 2, 512, 32, 16, 6):
+            raise CanonSwapError(f"unsupported AppearanceFeatureExtractor config {cfg} (reference models.yaml:2-9)")
+        super().__init__(hub)
+
+    def forward(self, source_image: torch.Tensor) -> torch.Tensor:
+        """[B,3,H,W] in [0,1] -> [B,32,16,H/4,W/4]"""
+        H, W = int(source_image.shape[2]), int(source_image.shape[3])
+        return self._engine(source_image, (H, W)).appearance(source_image.float())
+
+
+class WarpingNetwork(_SpecModule):
+    NET = "warping_module"
+
+    def __init__(self, num_kp=21, block_expansion=64, max_features=512, num_down_blocks=2, reshape_channel=32,
+                 estimate_occlusion_map=True, dense_motion_params=None, hub=None, **kwargs):
+        if num_kp != 21 or reshape_channel != 32 or not estimate_occlusion_map:
+            raise CanonSwapError("unsupported WarpingNetwork config (reference models.yaml:15-28)")
+        super().__init__(hub)
+        self.upscale = kwargs.get("upscale", 1)
+
+    def _eng(self, feature_3d):
+        return self._engine(feature_3d, (4 * int(feature_3d.shape[3]), 4 * int(feature_3d.shape[4])))
+
+    def warp(self, feature_3d, kp_source, kp_driving):
+        """reference warping_network.py:49-62 -> (out [B,32,16,h,w], occlusion_map [B,1,h,w])"""
+        return self._eng(feature_3d).warp(feature_3d.float(), kp_source.float(), kp_driving.float())
+
+    def warp_out(self, out, occlusion_map=None):
+        """reference warping_network.py:64-71 -> [B,256,h,w]"""
+        return self._eng(out).warp_out(out.float(), occlusion_map)
+
+    def forward(self, feature_3d, kp_driving, kp_source):
+        """reference warping_network.py:83-111 -> {'occlusion_map','deformation','out'}"""
+        return self._eng(feature_3d).warp_forward(feature_3d.float(), kp_driving.float(), kp_source.float())
+
+
+class SPADEDecoder(_SpecModule):
+    NET = "spade_generator"
+
+    def __init__(self, upscale=1, max_features=256, block_expansion=64, out_channels=64, num_down_blocks=2, hub=None):
+        if upscale != 2:
+            raise CanonSwapError("SPADEDecoder: only upscale=2 is supported (reference can_swap_e2e.py:62)")
+        super().__init__(hub)
+        self.upscale = upscale
+
+    def forward(self, feature: torch.Tensor) -> torch.Tensor:
+        """[B,256,h,w] -> [B,3,8h,8w] in [0,1]"""
+        return self._engine(feature, (4 * int(feature.shape[2]), 4 * int(feature.shape[3]))).spade(feature.float())
+
+
+class transfer_model2(_SpecModule):
+    NET = "transfer"
+
+    def forward(self, x: torch.Tensor, dlatents: torch.Tensor, return_mask: bool = False):
+        """reference adaptive_modulate.py:522-554. dlatents [1 or B,512]: one identity per call."""
+        d = dlatents.reshape(-1, spec.LATENT).float()
+        if d.shape[0] > 1 and not bool((d == d[:1]).all()):
+            raise CanonSwapError("transfer_model2: one source identity per call (the pipeline broadcasts a single source_id)")
+        hub = self._hub
+        if hub.identity is None or hub.identity.device != d.device or not torch.equal(hub.identity, d[0]):
+            hub.set_identity(d[0])
+        eng = self._engine(x, (4 * int(x.shape[3]), 4 * int(x.shape[4])))
+        return eng.swap(x.float(), return_mask=return_mask)
+
+
+transfer_model_big = transfer_model2        # reference adaptive_modulate.py alias used by can_swap_e2e.py:24
+
+
+class G3d(_SpecModule):
+    NET = "refine"
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self._engine(x, (4 * int(x.shape[3]), 4 * int(x.shape[4]))).refine(x.float())
+
+
+class can_swapper(object):
+    """Hot-path members of the reference wrapper (src/can_swap_e2e.py:39-348).
+
+    `inference_cfg` may be the reference's InferenceConfig (only `device_id`, `input_shape` and
+    `flag_use_half_precision` are read) or None.  `motion_extractor` / `netArc` are outside this
+    path; pass the reference's torch modules to keep `get_kp_info` / `getid`.
+    """
+
+    def __init__(self, inference_cfg=None, *, weights=None, device_id: Optional[int] = None, max_batch: int = 8,
+                 motion_extractor=None, netArc=None, conv_impl: int = 0):
+        self.inference_cfg = inference_cfg
+        if device_id is None:
+            device_id = getattr(inference_cfg, "device_id", 0) if inference_cfg is not None else 0
+        if getattr(inference_cfg, "flag_force_cpu", False):
+            raise CanonSwapError("flag_force_cpu: canonswap_b200 has no CPU path")
+        if getattr(inference_cfg, "flag_use_half_precision", False):
+            raise CanonSwapError("flag_use_half_precision: this path computes at fp32 parity only "
+                                 "(reference inference_canswap.py:58 forces it off)")
+        self.device_id = device_id
+        self.device = f"cuda:{device_id}"
+        self.input_shape = tuple(getattr(inference_cfg, "input_shape", (256, 256)))
+        self._hub = _EngineHub(device_id=device_id, max_batch=max_batch, conv_impl=conv_impl)
+        self.appearance_feature_extractor = AppearanceFeatureExtractor(hub=self._hub)
+        self.warping_module = WarpingNetwork(hub=self._hub)
+        self.spade_generator = SPADEDecoder(upscale=2, hub=self._hub)
+        self.swap_module = transfer_model_big(hub=self._hub)
+        self.refine_module = G3d(hub=self._hub)
+        self.motion_extractor = motion_extractor
+        self.netArc = netArc
+        if weights is not None:
+            self.load_cpk(weights)
+
+    # reference can_swap_e2e.py:87-100 (path or the already-loaded dict)
+    def load_cpk(self, combined_weights="pretrained_weights/combined_weights.pth"):
+        if isinstance(combined_weights, (str, bytes)):
+            combined_weights = torch.load(combined_weights, map_location=torch.device("cpu"))
+        self.appearance_feature_extractor.load_state_dict(combined_weights["appearance_feature_extractor"])
+        self.warping_module.load_state_dict(combined_weights["warping_module"])
+        self.spade_generator.load_state_dict(combined_weights["spade_generator"])
+        self.swap_module.load_state_dict(combined_weights["transfer"])
+        self.refine_module.load_state_dict(combined_weights["refine"])
+        if self.motion_extractor is not None and "motion_extractor" in combined_weights:
+            self.motion_extractor.load_state_dict(combined_weights["motion_extractor"])
+
+    def getid(self, img):
+        if self.netArc is None:
+            raise CanonSwapError("getid needs the ArcFace encoder (out of the hot path); pass netArc=")
+        img = torch.nn.functional.interpolate(img, size=(112, 112))
+        idv, _ = self.netArc(img)
+        return torch.nn.functional.normalize(idv, p=2, dim=1)
+
+    def swap(self, feature_3d, source_id):
+        return self.swap_module(feature_3d, source_id)
+
+    # reference can_swap_e2e.py:126-163
+    def prepare_source(self, img: np.ndarray) -> torch.Tensor:
+        if img.shape[0] != self.input_shape[0] or img.shape[1] != self.input_shape[1]:
+            raise CanonSwapError("prepare_source: resize the crop to input_shape first (cv2 is outside this path)")
+        x = img.copy()
+        if x.ndim == 3:
+            x = x[np.newaxis].astype(np.float32) / 255.
+        elif x.ndim == 4:
+            x = x.astype(np.float32) / 255.
+        else:
+            raise ValueError(f'img ndim should be 3 or 4: {x.ndim}')
+        x = np.clip(x, 0, 1)
+        return torch.from_numpy(x).permute(0, 3, 1, 2).to(self.device)
+
+    def prepare_videos(self, imgs) -> torch.Tensor:
+        if isinstance(imgs, list):
+            _imgs = np.array(imgs)[..., np.newaxis]
+        elif isinstance(imgs, np.ndarray):
+            _imgs = imgs
+        else:
+            raise ValueError(f'imgs type error: {type(imgs)}')
+        y = np.clip(_imgs.astype(np.float32) / 255., 0, 1)
+        return torch.from_numpy(y).permute(0, 4, 3, 1, 2).to(self.device)
+
+    def extract_feature_3d(self, x: torch.Tensor) -> torch.Tensor:
+        return self.appearance_feature_extractor(x).float()
+
+    def warp_decode(self, feature_3d, kp_source, kp_driving):
+        """reference can_swap_e2e.py:286-308"""
+        ret_dct = self.warping_module(feature_3d, kp_source=kp_source, kp_driving=kp_driving)
+        ret_dct['out'] = self.spade_generator(feature=ret_dct['out'])
+        return ret_dct
+
+    def conv_decode(self, out, occlusion_map=None):
+        """reference can_swap_e2e.py:309-312"""
+        return self.spade_generator(self.warping_module.warp_out(out, occlusion_map))
+
+    def parse_output(self, out: torch.Tensor) -> np.ndarray:
+        """reference can_swap_e2e.py:314-322"""
+        out = np.transpose(out.data.cpu().numpy(), [0, 2, 3, 1])
+        out = np.clip(out, 0, 1)
+        return np.clip(out * 255, 0, 255).astype(np.uint8)
+
+    # ---- the fused loop body (not in the reference: the whole of pipeline_e2e.py:242-267 in one call) ----
+    def set_source_identity(self, source_id: torch.Tensor):
+        self._hub.set_identity(source_id.to(self.device).float())
+
+    def swap_frames(self, frames: torch.Tensor, x_t: torch.Tensor, x_can: torch.Tensor, out_u8=None, out_f32=None,
+                    debug_decodes: bool = False):
+        """frames [B,H,W,3] u8 or [B,3,H,W] fp32 on device; x_t = x_t_info['x_s'], x_can = scale*kp.
+        Returns (u8 [B,2H,2W,3], fp32 [B,3,2H,2W] or None)."""
+        if frames.dtype == torch.uint8:
+            hw = (int(frames.shape[1]), int(frames.shape[2]))
+        else:
+            hw = (int(frames.shape[2]), int(frames.shape[3]))
+        if not frames.is_cuda:
+            raise CanonSwapError("swap_frames: frames must be on the CUDA device")
+        eng = self._hub.engine(hw, int(frames.shape[0]))
+        return eng.frame(frames, x_t, x_can, out_u8=out_u8, out_f32=out_f32, debug_decodes=debug_decodes)
+
+    def engine(self, net_hw=(256, 256), batch: int = 1) -> Engine:
+        return self._hub.engine(tuple(net_hw), batch)

@@ -1,0 +1,128 @@
+"""The per-frame loop of `CanSwapPipeline.execute` (reference src/can_swap_pipeline_e2e.py:223-283,
+generator part) as a batched, multi-GPU frame pipeline.
+
+Frames are independent given the source identity, so the clip is sharded
+round-robin -- frame i -> rank i mod world -- with NO data-path collective; the only message is one
+broadcast of the 512-float source identity from rank 0 (`broadcast_identity`).  Each rank streams
+its shard through `can_swapper.swap_frames` in batches: pinned host u8 frames -> H2D (copy stream)
+-> cs_frame (compute stream) -> D2H of the u8 result (copy stream), double-buffered so copies overlap
+the kernels.  Results land in a host array indexed by global frame id.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_frames: int, rank: int, world: int) -> List[int]:
+    """Global frame ids owned by `rank`: i with i % world == rank (BASELINE config 4)."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world {world}")
+    return list(range(rank, n_frames, world))
+
+
+def batches(indices: Sequence[int], batch: int) -> List[List[int]]:
+    if batch < 1:
+        raise ValueError("batch must be >= 1")
+    return [list(indices[i:i + batch]) for i in range(0, len(indices), batch)]
+
+
+def broadcast_identity(source_id: Optional[torch.Tensor], device=None, src: int = 0) -> torch.Tensor:
+    """One broadcast of the ArcFace identity [1,512] fp32 from `src` (the only collective of the path).
+    Without an initialised process group this is the identity function."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        if source_id is None:
+            raise ValueError("source_id is required on a single process")
+        return source_id if device is None else source_id.to(device)
+    if dist.get_rank() == src:
+        if source_id is None:
+            raise ValueError("source rank must provide source_id")
+        buf = source_id.detach().to(torch.float32).reshape(1, 512).clone()
+    else:
+        buf = torch.empty(1, 512, dtype=torch.float32)
+    if device is not None:
+        buf = buf.to(device)
+    dist.broadcast(buf, src=src)
+    return buf
+
+
+def run_sharded(process_batch: Callable[[List[int]], None], n_frames: int, batch: int, rank: int = 0, world: int = 1) -> int:
+    """Drive `process_batch(global_ids)` over this rank's shard; returns the number of frames done."""
+    mine = shard_indices(n_frames, rank, world)
+    for ids in batches(mine, batch):
+        process_batch(ids)
+    return len(mine)
+
+
+class FramePipeline:
+    """Host-buffer front end of the hot path: the call a user of the reference pipeline would make.
+
+    swapper: canonswap_b200.modules.can_swapper with weights loaded and the identity set.
+    """
+
+    def __init__(self, swapper, net_hw=(256, 256), batch: int = 8):
+        self.sw = swapper
+        self.batch = batch
+        self.net_h, self.net_w = net_hw
+        dev = torch.device(swapper.device)
+        self.dev = dev
+        self.compute = torch.cuda.current_stream(dev)
+        self.copy_in = torch.cuda.Stream(dev)
+        self.copy_out = torch.cuda.Stream(dev)
+        H, W = self.net_h, self.net_w
+        self.slots = []
+        for _ in range(2):
+            self.slots.append({
+                "frames": torch.empty(batch, H, W, 3, dtype=torch.uint8, device=dev),
+                "x_t": torch.empty(batch, 21, 3, device=dev),
+                "x_can": torch.empty(batch, 21, 3, device=dev),
+                "out": torch.empty(batch, 2 * H, 2 * W, 3, dtype=torch.uint8, device=dev),
+                "in_ready": torch.cuda.Event(), "done": torch.cuda.Event(), "drained": torch.cuda.Event(),
+            })
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def run(self, frames_u8: torch.Tensor, x_t: torch.Tensor, x_can: torch.Tensor, out_u8: torch.Tensor,
+            rank: int = 0, world: int = 1) -> int:
+        """frames_u8 [T,H,W,3] u8, x_t/x_can [T,21,3] fp32, out_u8 [T,2H,2W,3] u8 -- all PINNED host tensors.
+        Processes frames i % world == rank; returns how many. Synchronises before returning."""
+        T = frames_u8.shape[0]
+        mine = shard_indices(T, rank, world)
+        contiguous = world == 1
+        k = 0
+        for ids in batches(mine, self.batch):
+            s = self.slots[k % 2]
+            k += 1
+            b = len(ids)
+            with torch.cuda.stream(self.copy_in):
+                self.copy_in.wait_event(s["done"])            # previous use of this slot's inputs finished
+                if contiguous:
+                    lo, hi = ids[0], ids[-1] + 1
+                    s["frames"][:b].copy_(frames_u8[lo:hi], non_blocking=True)
+                    s["x_t"][:b].copy_(x_t[lo:hi], non_blocking=True)
+                    s["x_can"][:b].copy_(x_can[lo:hi], non_blocking=True)
+                else:
+                    for j, i in enumerate(ids):
+                        s["frames"][j].copy_(frames_u8[i], non_blocking=True)
+                        s["x_t"][j].copy_(x_t[i], non_blocking=True)
+                        s["x_can"][j].copy_(x_can[i], non_blocking=True)
+                s["in_ready"].record(self.copy_in)
+            self.h2d_bytes += b * (frames_u8[0].numel() + 2 * 21 * 3 * 4)
+            self.compute.wait_event(s["in_ready"])
+            self.compute.wait_event(s["drained"])             # previous D2H of this slot's output finished
+            self.sw.swap_frames(s["frames"][:b], s["x_t"][:b], s["x_can"][:b], out_u8=s["out"][:b])
+            s["done"].record(self.compute)
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(s["done"])
+                if contiguous:
+                    out_u8[ids[0]:ids[-1] + 1].copy_(s["out"][:b], non_blocking=True)
+                else:
+                    for j, i in enumerate(ids):
+                        out_u8[i].copy_(s["out"][j], non_blocking=True)
+                s["drained"].record(self.copy_out)
+            self.d2h_bytes += b * out_u8[0].numel()
+        self.copy_out.synchronize()
+        self.compute.synchronize()
+        return len(mine)

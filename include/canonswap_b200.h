@@ -26,6 +26,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define CS_API __attribute__((visibility("default")))
+#else
+#define CS_API
+#endif
+
 typedef struct cs_ctx cs_ctx;
 
 enum cs_status {
@@ -60,73 +66,80 @@ typedef struct cs_tensor_desc {
 /* ---- lifetime ------------------------------------------------------------------------------ */
 /* Replaces can_swapper.__init__ module construction (can_swap_e2e.py:60-68) for the five hot-path
  * networks. net_h, net_w: generator input size (multiple of 128; 256 for 512-px frames). */
-int cs_create(cs_ctx** out, int device, int max_batch, int net_h, int net_w);
-void cs_destroy(cs_ctx* ctx);
+CS_API int cs_create(cs_ctx** out, int device, int max_batch, int net_h, int net_w);
+CS_API void cs_destroy(cs_ctx* ctx);
 /* Text of the last error on this ctx (ctx may be NULL for cs_create failures). */
-const char* cs_last_error(const cs_ctx* ctx);
-int cs_set_option(cs_ctx* ctx, int option, int value);
+CS_API const char* cs_last_error(const cs_ctx* ctx);
+CS_API int cs_set_option(cs_ctx* ctx, int option, int value);
 /* Number of kernel launches issued by this ctx so far (for bench.py's gpu_launches). */
-int64_t cs_launch_count(const cs_ctx* ctx);
+CS_API int64_t cs_launch_count(const cs_ctx* ctx);
 /* Bytes of device workspace + packed weights owned by the ctx. */
-size_t cs_workspace_bytes(const cs_ctx* ctx);
+CS_API size_t cs_workspace_bytes(const cs_ctx* ctx);
 
 /* Replaces can_swapper.load_cpk (can_swap_e2e.py:87-100): ingests the raw reference state_dicts,
  * folds eval-mode BatchNorm and spectral-norm sigma, permutes and re-lays weights for the kernels. */
-int cs_load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n);
+CS_API int cs_load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n);
 
 /* Per-source state: derives the 14 style vectors and demodulated weight sets of transfer_model2
  * from the ArcFace identity (adaptive_modulate.py:148-155). id_dev: device [512] fp32. */
-int cs_set_identity(cs_ctx* ctx, const float* id_dev, void* stream);
+CS_API int cs_set_identity(cs_ctx* ctx, const float* id_dev, void* stream);
 
 /* ---- per-stage entry points (reference module forward()s) ---------------------------------- */
 /* AppearanceFeatureExtractor.forward (appearance_feature_extractor.py:38-48):
  * img [B,3,net_h,net_w] -> f3d [B,32,16,h,w] */
-int cs_appearance(cs_ctx* ctx, const float* img, float* f3d, int B, void* stream);
+CS_API int cs_appearance(cs_ctx* ctx, const float* img, float* f3d, int B, void* stream);
 
 /* WarpingNetwork.warp (warping_network.py:49-62): -> out3d [B,32,16,h,w], occ [B,1,h,w];
  * deformation [B,16,h,w,3] optional (may be NULL). kp_* are [B,21,3]. */
-int cs_warp(cs_ctx* ctx, const float* f3d, const float* kp_source, const float* kp_driving,
+CS_API int cs_warp(cs_ctx* ctx, const float* f3d, const float* kp_source, const float* kp_driving,
             float* out3d, float* occ, float* deformation, int B, void* stream);
 
 /* WarpingNetwork.warp_out (warping_network.py:64-71): f3d [B,32,16,h,w], occ [B,1,h,w] or NULL
  * -> out [B,256,h,w] */
-int cs_warp_out(cs_ctx* ctx, const float* f3d, const float* occ, float* out, int B, void* stream);
+CS_API int cs_warp_out(cs_ctx* ctx, const float* f3d, const float* occ, float* out, int B, void* stream);
 
 /* WarpingNetwork.forward (warping_network.py:83-111) -> out [B,256,h,w], occ [B,1,h,w],
  * deformation [B,16,h,w,3] (occ/deformation may be NULL). */
-int cs_warp_forward(cs_ctx* ctx, const float* f3d, const float* kp_driving, const float* kp_source,
+CS_API int cs_warp_forward(cs_ctx* ctx, const float* f3d, const float* kp_driving, const float* kp_source,
                     float* out, float* occ, float* deformation, int B, void* stream);
 
 /* transfer_model2.forward (adaptive_modulate.py:522-554) with the identity given to cs_set_identity.
  * masks: optional [7,B,1,h,w] (return_mask=True), may be NULL. */
-int cs_swap(cs_ctx* ctx, const float* f3d, float* out3d, float* masks, int B, void* stream);
+CS_API int cs_swap(cs_ctx* ctx, const float* f3d, float* out3d, float* masks, int B, void* stream);
 
 /* G3d.forward (adaptive_modulate.py:721-733) */
-int cs_refine(cs_ctx* ctx, const float* f3d, float* out3d, int B, void* stream);
+CS_API int cs_refine(cs_ctx* ctx, const float* f3d, float* out3d, int B, void* stream);
 
 /* SPADEDecoder.forward (spade_generator.py:41-59): feat [B,256,h,w] -> img [B,3,8h,8w] in [0,1];
  * img_u8 optional [B,8h,8w,3] u8 with can_swapper.parse_output semantics (can_swap_e2e.py:314-322). */
-int cs_spade(cs_ctx* ctx, const float* feat, float* img, uint8_t* img_u8, int B, void* stream);
+CS_API int cs_spade(cs_ctx* ctx, const float* feat, float* img, uint8_t* img_u8, int B, void* stream);
 
 /* ---- the fused per-frame loop body (pipeline_e2e.py:242-267) -------------------------------- */
 /* frames: see CS_FRAME_IN_U8_HWC; kp_t, kp_can [B,21,3] (x_t = x_t_info['x_s'], x_can = scale*kp);
  * out_f32 [B,3,2*net_h,2*net_w] and/or out_u8 [B,2*net_h,2*net_w,3] (either may be NULL). */
-int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp_can,
+CS_API int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp_can,
              float* out_f32, uint8_t* out_u8, int B, int flags, void* stream);
+
+/* ---- per-kernel-family timing (measurement only) -------------------------------------------- */
+/* enable != 0: bracket every kernel launch of this ctx with CUDA events on the launching stream. */
+CS_API int cs_profile(cs_ctx* ctx, int enable);
+/* Synchronises and writes out[6][4] = per family {tcgen05 conv, SIMT conv, prep, stats, sampling, other}:
+ * {total ms, algorithmic flops, algorithmic bytes, launches}; clears the records. */
+CS_API int cs_profile_read(cs_ctx* ctx, double* out);
 
 /* ---- kernel-level entry points (unit tests / profiling) ------------------------------------- */
 /* Generic "same"-style convolution on channels-last fp32 through the library's conv kernels.
  * x [B,D,H,W,Cin] -> y [B,Do,Ho,Wo,Cout]; w in PyTorch layout [Cout,Cin,KD,KH,KW] (device), bias
  * [Cout] or NULL. impl: 0 auto, 1 SIMT fp32, 2 tcgen05 split-bf16. act: 0 none 1 relu 2 lrelu 3 sigmoid */
-int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
+CS_API int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
                  int B, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW,
                  int PD, int PH, int PW, int act, float slope, int impl, void* stream);
 /* F.grid_sample(inp, grid, align_corners=False) 5-D trilinear zeros-padding on NCDHW fp32:
  * inp [B,C,D,H,W] (C multiple of 4), grid [B,D,H,W,3] -> out [B,C,D,H,W] */
-int cs_test_grid_sample3d(cs_ctx* ctx, const float* inp, const float* grid, float* out,
+CS_API int cs_test_grid_sample3d(cs_ctx* ctx, const float* inp, const float* grid, float* out,
                           int B, int C, int D, int H, int W, void* stream);
 /* per-(b,c) mean / rstd (biased variance, eps) of NCHW-style [B,C,S] fp32 */
-int cs_test_instance_stats(cs_ctx* ctx, const float* x, float* mean, float* rstd,
+CS_API int cs_test_instance_stats(cs_ctx* ctx, const float* x, float* mean, float* rstd,
                            int B, int C, int S, float eps, void* stream);
 
 #ifdef __cplusplus

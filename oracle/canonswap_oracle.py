@@ -89,11 +89,11 @@ def appearance_feature_extractor(sd, x):
 # ---------------------------------------------------------------------------------------------
 # W : dense motion + warp
 # ---------------------------------------------------------------------------------------------
-def make_coordinate_grid(d, h, w, dtype=torch.float32):
+def make_coordinate_grid(d, h, w, dtype=torch.float32, device=None):
     """reference util.py:41-58: identity grid in [-1,1], last dim ordered (x, y, z)."""
-    x = 2 * (torch.arange(w, dtype=dtype) / (w - 1)) - 1
-    y = 2 * (torch.arange(h, dtype=dtype) / (h - 1)) - 1
-    z = 2 * (torch.arange(d, dtype=dtype) / (d - 1)) - 1
+    x = 2 * (torch.arange(w, dtype=dtype, device=device) / (w - 1)) - 1
+    y = 2 * (torch.arange(h, dtype=dtype, device=device) / (h - 1)) - 1
+    z = 2 * (torch.arange(d, dtype=dtype, device=device) / (d - 1)) - 1
     zz, yy, xx = torch.meshgrid(z, y, x, indexing="ij")
     return torch.stack([xx, yy, zz], dim=-1)          # [d,h,w,3]
 
@@ -126,7 +126,7 @@ def dense_motion(sd, feature, kp_driving, kp_source, p="dense_motion_network"):
     bs, _, d, h, w = feature.shape
     K = kp_source.shape[1]
     f = F.relu(_bn(_conv3d(feature, sd, p + ".compress"), sd, p + ".norm"))        # :70-72  [B,4,d,h,w]
-    grid = make_coordinate_grid(d, h, w, kp_source.dtype)                          # :31
+    grid = make_coordinate_grid(d, h, w, kp_source.dtype, feature.device)          # :31
     # sparse motions :29-43
     d2s = grid[None, None] - kp_driving.view(bs, K, 1, 1, 1, 3) + kp_source.view(bs, K, 1, 1, 1, 3)
     motions = torch.cat([grid[None, None].expand(bs, 1, d, h, w, 3), d2s], dim=1)  # [B,K+1,d,h,w,3]
@@ -136,7 +136,7 @@ def dense_motion(sd, feature, kp_driving, kp_source, p="dense_motion_network"):
     deformed = deformed.view(bs, K + 1, 4, d, h, w)
     # heatmaps :55-65
     heat = kp2gaussian(kp_driving, grid) - kp2gaussian(kp_source, grid)
-    heat = torch.cat([torch.zeros(bs, 1, d, h, w, dtype=heat.dtype), heat], dim=1)[:, :, None]
+    heat = torch.cat([torch.zeros(bs, 1, d, h, w, dtype=heat.dtype, device=heat.device), heat], dim=1)[:, :, None]
     inp = torch.cat([heat, deformed], dim=2).view(bs, (K + 1) * 5, d, h, w)        # :83-84
     pred = hourglass(sd, p + ".hourglass", inp)                                    # :86
     logits = _conv3d(pred, sd, p + ".mask", 3)                                     # :88

@@ -1,0 +1,150 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol, fails loudly without a GPU,
+the host-side mirror keeps the reference state_dict layout, and the frame-sharding logic is exact
+(incl. a world_size-2 gloo run)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from canonswap_b200 import _build, _lib
+    _build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_header_symbol(lib):
+    from canonswap_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "canonswap_b200.h")).read()
+    declared = re.findall(r"^CS_API [^;(]*?\b(cs_[a-z0-9_]+)\(", hdr, flags=re.M)
+    assert sorted(declared) == sorted(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_no_gpu_means_loud_failure_not_fallback(lib):
+    import ctypes as C
+    ctx = C.c_void_p()
+    rc = lib.cs_create(C.byref(ctx), 0, 1, 256, 256)
+    assert rc < 0 and not ctx.value
+    assert b"no CPU fallback" in lib.cs_last_error(None)
+    from canonswap_b200.engine import CanonSwapError, Engine
+    with pytest.raises(CanonSwapError):
+        Engine({}, net_hw=(256, 256))
+
+
+def test_create_rejects_bad_arguments(lib):
+    import ctypes as C
+    ctx = C.c_void_p()
+    assert lib.cs_create(C.byref(ctx), 0, 0, 256, 256) == -1        # max_batch
+    assert lib.cs_create(C.byref(ctx), 0, 1, 200, 256) == -1        # not a multiple of 128
+    assert lib.cs_create(None, 0, 1, 256, 256) == -1
+    assert lib.cs_frame(None, None, None, None, None, None, 1, 0, None) == -1
+    assert lib.cs_launch_count(None) == 0
+
+
+def test_mirror_modules_keep_reference_state_dict_layout(synth_w):
+    from canonswap_b200 import modules, spec
+    from canonswap_b200.engine import CanonSwapError
+    sw = modules.can_swapper(weights=None, device_id=0)
+    mods = {"appearance_feature_extractor": sw.appearance_feature_extractor, "warping_module": sw.warping_module,
+            "spade_generator": sw.spade_generator, "transfer": sw.swap_module, "refine": sw.refine_module}
+    for name, m in mods.items():
+        assert set(m.state_dict().keys()) == set(spec.net_spec(name).keys())
+        r = m.load_state_dict(synth_w[name], strict=True)
+        assert not r.missing_keys and not r.unexpected_keys
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, synth_w[name][k])
+        assert not m.training
+    with pytest.raises(CanonSwapError):
+        sw.appearance_feature_extractor(torch.zeros(1, 3, 256, 256))          # CPU tensor -> no fallback
+    with pytest.raises(CanonSwapError):
+        sw.refine_module.train()
+    assert modules.transfer_model_big is modules.transfer_model2
+
+
+def test_wrapper_host_helpers_match_oracle():
+    from canonswap_b200 import modules
+    from oracle import canonswap_oracle as O
+    sw = modules.can_swapper.__new__(modules.can_swapper)
+    sw.device, sw.input_shape = "cpu", (16, 16)
+    u8 = np.random.RandomState(0).randint(0, 256, (3, 16, 16, 3)).astype(np.uint8)
+    y = sw.prepare_videos([f for f in u8])
+    assert torch.equal(y, O.prepare_videos(torch.from_numpy(u8)))
+    x = sw.prepare_source(u8[0])
+    assert x.shape == (1, 3, 16, 16)
+    img = torch.rand(2, 3, 8, 8) * 1.2 - 0.1
+    assert np.array_equal(sw.parse_output(img), O.parse_output(img).numpy())
+
+
+def test_shard_indices_partition():
+    from canonswap_b200.pipeline import batches, shard_indices
+    for T in (0, 1, 7, 64, 2048):
+        for world in (1, 2, 4, 8):
+            allv = sorted(i for r in range(world) for i in shard_indices(T, r, world))
+            assert allv == list(range(T))
+            for r in range(world):
+                assert all(i % world == r for i in shard_indices(T, r, world))
+    assert batches(list(range(5)), 2) == [[0, 1], [2, 3], [4]]
+    assert batches([], 8) == []
+    with pytest.raises(ValueError):
+        shard_indices(4, 2, 2)
+
+
+_GLOO_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["CS_ROOT"])
+from canonswap_b200.pipeline import broadcast_identity, run_sharded
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["CS_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+T, B = 37, 4
+g = torch.Generator().manual_seed(3)
+frames = torch.randint(0, 256, (T, 4, 4, 3), generator=g, dtype=torch.uint8)
+sid = torch.nn.functional.normalize(torch.randn(1, 512, generator=g)) if rank == 0 else None
+sid = broadcast_identity(sid)
+out = torch.zeros(T, 4, 4, 3, dtype=torch.int64)
+def proc(ids):            # stand-in for cs_frame: any per-frame function of (frame, identity)
+    for i in ids:
+        out[i] = frames[i].long() * 3 + int(sid[0, i % 512].item() * 1e6) % 7
+n = run_sharded(proc, T, B, rank, world)
+cnt = torch.tensor([n]); dist.all_reduce(cnt)
+dist.all_reduce(out)      # test-only reassembly (the product returns frames by per-rank D2H)
+if rank == 0:
+    np.save(os.environ["CS_OUT"], out.numpy())
+    np.save(os.environ["CS_OUT"] + ".sid.npy", sid.numpy())
+    assert cnt.item() == T
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_gloo_sharding_reassembles_exactly(tmp_path):
+    """N>1 path on CPU: round-robin shards + one identity broadcast == the single-process result."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    out = str(tmp_path / "out.npy")
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", CS_PORT=str(port), CS_OUT=out, CS_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        o, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, o.decode()
+    got = np.load(out)
+    sid = torch.from_numpy(np.load(out + ".sid.npy"))
+    g = torch.Generator().manual_seed(3)
+    frames = torch.randint(0, 256, (37, 4, 4, 3), generator=g, dtype=torch.uint8)
+    sid0 = torch.nn.functional.normalize(torch.randn(1, 512, generator=g))
+    assert torch.equal(sid, sid0)                                  # broadcast id equals the root's bit-for-bit
+    exp = torch.stack([frames[i].long() * 3 + int(sid0[0, i % 512].item() * 1e6) % 7 for i in range(37)])
+    assert np.array_equal(got, exp.numpy())

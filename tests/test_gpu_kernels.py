@@ -1,0 +1,129 @@
+"""GPU tests, kernel level: the C-ABI test entry points against the matching torch.nn.functional op
+(fp32, TF32 off) on random tensors including edge shapes."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(synth_w):
+    from canonswap_b200.engine import Engine
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    e = Engine(synth_w, net_hw=(128, 128), max_batch=2, device=0)
+    yield e
+    e.close()
+
+
+def _ref_conv(x_cl, w, b, pad):
+    x = x_cl.permute(0, 4, 1, 2, 3).contiguous().double()
+    y = F.conv3d(x, w.double(), None if b is None else b.double(), padding=pad)
+    return y.permute(0, 2, 3, 4, 1).float()
+
+
+CONV_CASES = [
+    # B, D, H, W, Cin, Cout, k(d,h,w), pad
+    (1, 1, 16, 16, 3, 64, (1, 3, 3), (0, 1, 1)),      # F.first
+    (2, 1, 8, 8, 64, 128, (1, 3, 3), (0, 1, 1)),
+    (1, 1, 8, 8, 256, 512, (1, 1, 1), (0, 0, 0)),     # 1x1
+    (1, 16, 8, 8, 32, 32, (3, 3, 3), (1, 1, 1)),      # ResBlock3d
+    (1, 16, 4, 4, 110, 64, (3, 3, 3), (1, 1, 1)),     # hourglass conv0, odd Cin
+    (1, 16, 8, 8, 142, 22, (7, 7, 7), (3, 3, 3)),     # mask conv, odd Cin / Cout
+    (1, 16, 2, 2, 64, 48, (3, 3, 3), (1, 1, 1)),      # tiny spatial
+    (1, 1, 8, 8, 512, 1, (1, 3, 3), (0, 1, 1)),       # mask_conv (Cout 1)
+    (1, 16, 8, 8, 142, 1, (16, 7, 7), (0, 3, 3)),     # occlusion as conv3d with full-depth kernel
+    (1, 1, 8, 8, 64, 12, (1, 3, 3), (0, 1, 1)),       # conv_img
+    (1, 1, 5, 7, 20, 33, (1, 3, 3), (0, 1, 1)),       # ragged everything
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("act", [0, 2])
+def test_conv_simt_matches_torch(eng, case, act):
+    B, D, H, W, Cin, Cout, k, pad = case
+    if Cout == 1 and act == 2:
+        pytest.skip("Cout=1 kernel supports none/sigmoid only")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(B, D, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, *k, device="cuda", generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    y = eng.test_conv(x, w, b, pad, act=act, slope=0.2, impl=1)
+    ref = _ref_conv(x, w, b, pad)
+    if act == 2:
+        ref = F.leaky_relu(ref, 0.2)
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_conv_sigmoid_cout1(eng):
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(2, 1, 8, 8, 512, device="cuda", generator=g)
+    w = torch.randn(1, 512, 1, 3, 3, device="cuda", generator=g) / 68.0
+    b = torch.randn(1, device="cuda", generator=g)
+    y = eng.test_conv(x, w, b, (0, 1, 1), act=3, impl=1)
+    ref = torch.sigmoid(_ref_conv(x, w, b, (0, 1, 1)))
+    assert (y - ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("hw", [(8, 8), (32, 32), (16, 24)])
+def test_grid_sample3d_matches_torch(eng, hw):
+    """5-D trilinear, zeros padding, align_corners=False (reference warping_network.py:46-47), including
+    out-of-range and exactly-on-border coordinates."""
+    H, W = hw
+    g = torch.Generator(device="cuda").manual_seed(9)
+    inp = torch.randn(2, 32, 16, H, W, device="cuda", generator=g)
+    grid = torch.rand(2, 16, H, W, 3, device="cuda", generator=g) * 2.6 - 1.3
+    grid[0, 0, 0, 0] = torch.tensor([-1.0, -1.0, -1.0], device="cuda")
+    grid[0, 0, 0, 1] = torch.tensor([1.0, 1.0, 1.0], device="cuda")
+    grid[0, 0, 0, 2] = torch.tensor([0.0, 0.0, 0.0], device="cuda")
+    grid[0, 0, 0, 3] = torch.tensor([5.0, -5.0, 0.3], device="cuda")
+    out = eng.test_grid_sample3d(inp, grid)
+    ref = F.grid_sample(inp, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    assert (out - ref).abs().max().item() <= 2e-5
+
+
+def test_grid_sample3d_identity_grid(eng):
+    """The reference's identity grid (align_corners=True style, util.py:41-58) sampled with
+    align_corners=False is NOT the identity map; both sides must agree on that."""
+    from oracle import canonswap_oracle as O
+    inp = torch.randn(1, 32, 16, 16, 16, device="cuda")
+    grid = O.make_coordinate_grid(16, 16, 16, device="cuda")[None].contiguous()
+    out = eng.test_grid_sample3d(inp, grid)
+    ref = F.grid_sample(inp, grid, align_corners=False)
+    assert (out - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 16 * 32 * 32), (2, 512, 32 * 32), (1, 64, 128 * 128), (2, 256, 1000)])
+def test_instance_stats(eng, shape):
+    B, C, S = shape
+    x = torch.randn(B, C, S, device="cuda") * 3 + 1.5
+    mean, rstd = eng.test_instance_stats(x, eps=1e-5)
+    xd = x.double()
+    rm = xd.mean(-1)
+    rv = xd.var(-1, unbiased=False)
+    assert (mean.double() - rm).abs().max().item() <= 1e-5
+    assert ((rstd.double() - 1 / torch.sqrt(rv + 1e-5)).abs() * torch.sqrt(rv + 1e-5)).max().item() <= 1e-5
+
+
+def test_bad_arguments_fail_loudly(eng):
+    from canonswap_b200.engine import CanonSwapError
+    with pytest.raises(ValueError):
+        eng.appearance(torch.zeros(1, 3, 64, 64, device="cuda"))          # wrong resolution for this ctx
+    with pytest.raises(ValueError):
+        eng.appearance(torch.zeros(3, 3, 128, 128, device="cuda"))        # batch > max_batch
+    with pytest.raises(ValueError):
+        eng.appearance(torch.zeros(1, 3, 128, 128))                       # CPU tensor: no fallback
+    with pytest.raises(CanonSwapError):
+        eng.test_conv(torch.zeros(1, 1, 4, 4, 8, device="cuda"), torch.zeros(8, 8, 1, 3, 3, device="cuda"), None,
+                      (0, 1, 1), impl=2 if not _tc_any(eng) else 7)
+
+
+def _tc_any(eng):
+    try:
+        eng.test_conv(torch.zeros(1, 1, 8, 16, 64, device="cuda"), torch.zeros(64, 64, 1, 3, 3, device="cuda"), None,
+                      (0, 1, 1), impl=2)
+        return True
+    except Exception:
+        return False

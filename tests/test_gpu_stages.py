@@ -1,0 +1,177 @@
+"""GPU parity tests proper: every stage of the hot path through the C ABI against the CPU oracle on
+the same seeded synthetic weights / inputs, and the end-to-end frame against the oracle and against
+the golden fixtures produced by the unmodified reference modules.
+
+Tolerance: BASELINE.json north_star -- max-abs 1e-3 fp32 vs the reference forward.  Stage tests feed
+each stage the ORACLE's input for that stage (so errors do not compound) and scale 1e-3 by the stage's
+dynamic range; the end-to-end image test uses the absolute 1e-3 on [0,1] pixels.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from canonswap_b200 import synth
+from oracle import canonswap_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3
+
+
+def _close(a, b, name, tol=TOL):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    scale = max(1.0, b.abs().max().item())
+    d = (a - b).abs().max().item()
+    assert d <= tol * scale, f"{name}: max|d| = {d:.3e} > {tol * scale:.3e}"
+    return d
+
+
+@pytest.fixture(scope="module")
+def case128(synth_w):
+    """B=2 at net 128x128 (config-2 resolution): oracle stages on CPU + a loaded engine."""
+    from canonswap_b200.engine import Engine
+    inp = synth.synth_inputs(2, 128)
+    ref = O.frame(synth_w, inp["frames"], inp["x_t"], inp["x_can"], inp["source_id"], debug_decodes=True)
+    eng = Engine(synth_w, net_hw=(128, 128), max_batch=2, device=0)
+    eng.set_identity(inp["source_id"].cuda())
+    cu = {k: v.cuda() for k, v in inp.items()}
+    yield eng, cu, ref
+    eng.close()
+
+
+def test_stage_appearance(case128):
+    eng, inp, ref = case128
+    _close(eng.appearance(inp["frames"]), ref["f_s"], "f_s")
+
+
+def test_stage_warp(case128):
+    eng, inp, ref = case128
+    out, occ, deform = eng.warp(ref["f_s"].cuda(), inp["x_t"], inp["x_can"], want_deformation=True)
+    _close(occ, ref["occ_can"], "occ_can")
+    _close(out, ref["f_can"], "f_can")
+    assert deform.shape == (2, 16, 32, 32, 3) and torch.isfinite(deform).all()
+
+
+def test_stage_swap_and_masks(case128, synth_w):
+    eng, inp, ref = case128
+    out, masks = eng.swap(ref["f_can"].cuda(), return_mask=True)
+    _close(out, ref["f_swap"], "f_swap")
+    _, omasks = O.swap_module(synth_w["transfer"], ref["f_can"], inp["source_id"].cpu().expand(2, -1), return_mask=True)
+    for i, (a, b) in enumerate(zip(masks, omasks)):
+        _close(a, b, f"mask{i}")
+
+
+def test_stage_refine(case128):
+    eng, inp, ref = case128
+    _close(eng.refine(ref["f_swap"].cuda()), ref["f_refine"], "f_refine")
+
+
+def test_stage_warp_forward(case128):
+    eng, inp, ref = case128
+    r = eng.warp_forward(ref["f_refine"].cuda(), kp_driving=inp["x_t"], kp_source=inp["x_can"])
+    _close(r["occlusion_map"], ref["occ"], "occ")
+    _close(r["deformation"], ref["deformation"], "deformation")
+    _close(r["out"], ref["warp_out"], "warp_out")
+
+
+def test_stage_warp_out_and_decode(case128):
+    eng, inp, ref = case128
+    w = eng.warp_out(ref["f_can"].cuda(), ref["occ_can"].cuda())
+    img = eng.spade(w)
+    _close(img, ref["rec_can"], "rec_can (conv_decode)")
+    w2 = eng.warp_out(ref["f_can"].cuda(), None)
+    assert torch.isfinite(w2).all() and w2.shape == w.shape
+
+
+def test_stage_spade_and_u8(case128):
+    eng, inp, ref = case128
+    img, u8 = eng.spade(ref["warp_out"].cuda(), want_u8=True)
+    _close(img, ref["out"], "out")
+    exp = O.parse_output(ref["out"])
+    diff = (u8.cpu().int() - exp.int()).abs()
+    assert diff.max().item() <= 1                      # truncation boundary crossings only
+    assert (diff > 0).float().mean().item() < 0.02
+
+
+def test_frame_end_to_end_vs_oracle(case128):
+    eng, inp, ref = case128
+    out_f32 = torch.empty(2, 3, 256, 256, device="cuda")
+    out_u8 = torch.empty(2, 256, 256, 3, dtype=torch.uint8, device="cuda")
+    eng.frame(inp["frames"], inp["x_t"], inp["x_can"], out_u8=out_u8, out_f32=out_f32)
+    d = _close(out_f32, ref["out"], "frame out")
+    print(f"end-to-end max|d| = {d:.3e}")
+    exp = O.parse_output(ref["out"])
+    assert (out_u8.cpu().int() - exp.int()).abs().max().item() <= 1
+    # u8 HWC ingest (prepare_videos) gives the same image bit-for-bit as the fp32 ingest
+    u8in = synth.synth_inputs(2, 128, u8=True)["frames"].cuda()
+    o2 = torch.empty_like(out_f32)
+    eng.frame(u8in, inp["x_t"], inp["x_can"], out_f32=o2)
+    assert torch.equal(o2, out_f32)
+    # debug decodes (pipeline_e2e.py:248,257) do not change the result
+    o3 = torch.empty_like(out_f32)
+    eng.frame(inp["frames"], inp["x_t"], inp["x_can"], out_f32=o3, debug_decodes=True)
+    assert torch.equal(o3, out_f32)
+    # determinism
+    o4 = torch.empty_like(out_f32)
+    eng.frame(inp["frames"], inp["x_t"], inp["x_can"], out_f32=o4)
+    assert torch.equal(o4, out_f32)
+
+
+@pytest.mark.parametrize("tag,T,hw", [("b1_128", 1, 128), ("b2_128", 2, 128), ("b1_256", 1, 256)])
+def test_frame_vs_golden_reference_fixtures(synth_w, tag, T, hw):
+    """tests/golden/*.npz come from the UNMODIFIED reference modules (make_golden.py)."""
+    from canonswap_b200.engine import Engine
+    g = np.load(os.path.join(GOLDEN, f"frame_{tag}.npz"))
+    inp = synth.synth_inputs(T, hw)
+    eng = Engine(synth_w, net_hw=(hw, hw), max_batch=T, device=0)
+    try:
+        eng.set_identity(inp["source_id"].cuda())
+        out = torch.empty(T, 3, 2 * hw, 2 * hw, device="cuda")
+        eng.frame(inp["frames"].cuda(), inp["x_t"].cuda(), inp["x_can"].cuda(), out_f32=out)
+        flat = out.cpu().reshape(-1)
+        step = max(1, flat.numel() // 4096)
+        d = np.abs(flat[::step][:4096].numpy() - g["out_sample"]).max()
+        assert d <= TOL, (tag, d)
+        assert abs(out.double().mean().item() - float(g["out_mean"])) <= 1e-4
+        if "out_full" in g:
+            assert np.abs(out.cpu().numpy() - g["out_full"]).max() <= TOL
+    finally:
+        eng.close()
+
+
+def test_batch_independence(case128):
+    """Frames are independent given the identity: a batch of 2 equals two batches of 1 bit-for-bit
+    (the property the multi-GPU frame sharding relies on)."""
+    eng, inp, ref = case128
+    both = torch.empty(2, 3, 256, 256, device="cuda")
+    eng.frame(inp["frames"], inp["x_t"], inp["x_can"], out_f32=both)
+    for i in range(2):
+        one = torch.empty(1, 3, 256, 256, device="cuda")
+        eng.frame(inp["frames"][i:i + 1], inp["x_t"][i:i + 1], inp["x_can"][i:i + 1], out_f32=one)
+        assert torch.equal(one[0], both[i])
+
+
+def test_reference_surface_mirror(synth_w):
+    """can_swapper mirror: same names / argument order / return types as reference can_swap_e2e.py,
+    composed exactly like pipeline_e2e.py:242-263."""
+    from canonswap_b200.modules import can_swapper
+    inp = synth.synth_inputs(1, 128, seed=5)
+    ref = O.frame(synth_w, inp["frames"], inp["x_t"], inp["x_can"], inp["source_id"])
+    sw = can_swapper(weights=synth_w, device_id=0, max_batch=1)
+    I_s, x_t, x_can, sid = (inp[k].cuda() for k in ("frames", "x_t", "x_can", "source_id"))
+    f_s = sw.extract_feature_3d(I_s)
+    f_can, occ_map = sw.warping_module.warp(f_s, x_t, x_can)
+    rec_can = sw.conv_decode(f_can, occ_map)
+    f_swap = sw.swap_module(f_can, sid)
+    f_swap = sw.refine_module(f_swap)
+    out = sw.warp_decode(f_swap, x_can, x_t)
+    assert set(out.keys()) == {"occlusion_map", "deformation", "out"}
+    _close(out["out"], ref["out"], "mirror out")
+    img = sw.parse_output(out["out"])
+    assert img.dtype == np.uint8 and img.shape == (1, 256, 256, 3)
+    assert rec_can.shape == (1, 3, 256, 256)
+    u8, _ = sw.swap_frames(I_s, x_t, x_can)
+    assert np.abs(u8.cpu().numpy().astype(int) - img.astype(int)).max() <= 1
