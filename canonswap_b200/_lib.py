@@ -15,6 +15,7 @@ CS_FRAME_IN_U8_HWC = 1
 CS_FRAME_DEBUG_DECODES = 2
 CS_OPT_CONV_IMPL = 1
 CS_OPT_USE_GRAPH = 2
+CS_OPT_TC_PASSES = 3
 
 # every symbol include/canonswap_b200.h declares
 SYMBOLS = [
@@ -65,7 +66,7 @@ def load() -> C.CDLL:
     lib.cs_frame.argtypes = [vp, p, p, p, p, p, i, i, vp]
     lib.cs_profile.argtypes = [vp, i]
     lib.cs_profile_read.argtypes = [vp, C.POINTER(C.c_double)]
-    lib.cs_test_conv.argtypes = [vp, p, p, p, p] + [i] * 14 + [f, i, vp]
+    lib.cs_test_conv.argtypes = [vp, p, p, p, p] + [i] * 13 + [f, i, vp]
     lib.cs_test_grid_sample3d.argtypes = [vp, p, p, p, i, i, i, i, i, vp]
     lib.cs_test_instance_stats.argtypes = [vp, p, p, p, i, i, i, f, vp]
     for name in SYMBOLS:

@@ -38,6 +38,7 @@ Net make_net(cs_ctx* ctx, void* stream, bool dry) {
   n.L.dry = dry;
   n.L.counter = dry ? nullptr : &ctx->launches;
   n.L.conv_impl = ctx->conv_impl;
+  n.L.npass = ctx->tc_passes;
   n.L.prof = dry ? nullptr : &ctx->prof;
   return n;
 }
@@ -228,6 +229,9 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
     case CS_OPT_CONV_IMPL:
       if (value < 0 || value > 1) return fail(ctx, CS_ERR_INVALID, "CS_OPT_CONV_IMPL: value must be 0 or 1");
       ctx->conv_impl = value; return CS_OK;
+    case CS_OPT_TC_PASSES:
+      if (value < 1 || value > 3) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_PASSES: value must be 1, 2 or 3");
+      ctx->tc_passes = value; return CS_OK;
     case CS_OPT_USE_GRAPH:
       ctx->use_graph = value ? 1 : 0; return CS_OK;
     default: return fail(ctx, CS_ERR_INVALID, "unknown option");
@@ -382,13 +386,14 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
   };
   try {
     ConvW cw = pack_conv_host(ctx, hw, bias ? &hb : nullptr, Cout, Cin, KD, KH, KW);
+    CS_CUDA(cudaDeviceSynchronize());          // the packing kernels ran on the null stream
     const int Do = D + 2 * PD - KD + 1, Ho = H + 2 * PH - KH + 1, Wo = W + 2 * PW - KW + 1;
     CS_REQUIRE(Do > 0 && Ho > 0 && Wo > 0, CS_ERR_INVALID, "cs_test_conv: empty output");
     Act xa = make_act(const_cast<float*>(x), B, D, H, W, Cin);
     Act ya = make_act(y, B, Do, Ho, Wo, Cout);
     ConvGeom g; g.PD = PD; g.PH = PH; g.PW = PW; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
     Epilogue e; e.act = act; e.slope = slope;
-    Launcher L; L.stream = st; L.counter = &ctx->launches;
+    Launcher L; L.stream = st; L.counter = &ctx->launches; L.npass = ctx->tc_passes; L.prof = &ctx->prof;
     const bool same = (Do == D && Ho == H && Wo == W && PD == KD / 2 && PH == KH / 2 && PW == KW / 2);
     bool tc = same && conv_tc_supported(cw, ya);
     if (impl == 2) CS_REQUIRE(tc, CS_ERR_INVALID, "cs_test_conv: shape not supported by the tcgen05 conv");

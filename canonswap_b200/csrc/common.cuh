@@ -62,12 +62,11 @@ inline Act vol_as_2d(float* p, int B, int H, int W) { return make_act(p, B, 1, H
 // channel slice [c0, c0+C) of a channels-last tensor (zero-copy concat)
 inline Act slice_c(Act a, int c0, int C) { a.p += c0; a.C = C; return a; }
 
-// split-bf16 operand planes for the tcgen05 conv: value ~= hi + lo, channels padded to Cp
+// split-bf16 operand of the tcgen05 conv: dense channels-last [B,D,H,W,nblk,64] bf16 where every
+// 32-channel block is the 128-byte row [hi x32 | lo x32], value ~= hi + lo (pad channels are zero)
 struct Opd {
-  __nv_bfloat16* hi = nullptr;
-  __nv_bfloat16* lo = nullptr;
-  int B = 0, D = 1, H = 0, W = 0, Cp = 0;
-  long sb = 0, sd = 0, sh = 0, sw = 0;
+  __nv_bfloat16* p = nullptr;
+  int B = 0, D = 1, H = 0, W = 0, nblk = 0;
 };
 
 enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_SIGMOID = 3 };
@@ -86,10 +85,9 @@ struct ConvW {
   int Cin = 0, Cout = 0, KD = 1, KH = 1, KW = 1;
   float* w32 = nullptr;    // [taps][Cin][Cout]   (SIMT path)
   float* bias = nullptr;   // [Cout] or null
-  // tcgen05 path: B operand, K-major sub-blocks [taps * Cin_p/KC][Cout_p][KC], hi and lo planes
-  __nv_bfloat16* whi = nullptr;
-  __nv_bfloat16* wlo = nullptr;
-  int Cin_p = 0, Cout_p = 0, KC = 0;
+  // tcgen05 path: B operand [Cout_p][tap][nblk][hi 32 | lo 32] bf16 (K-major rows), N tile BN
+  __nv_bfloat16* wtc = nullptr;
+  int nblk = 0, Cout_p = 0, BN = 0;
   int taps() const { return KD * KH * KW; }
 };
 
@@ -163,6 +161,7 @@ struct Launcher {            // everything a kernel launch helper needs
   bool dry = false;          // measuring pass: skip launches
   int64_t* counter = nullptr;
   int conv_impl = 0;         // 0 auto, 1 SIMT, 2 TC
+  int npass = 3;             // split-bf16 MMA passes of the tcgen05 conv (3 = hi*hi + lo*hi + hi*lo)
   Profiler* prof = nullptr;
   void count() const { if (counter) ++*counter; }
 };
@@ -216,7 +215,7 @@ void grid_sample3d_cl(const Launcher& L, const float* vol, const float* grid, fl
 // conv_tc.cu
 // "same" convolution (stride 1, pad = k/2) of a dense channels-last tensor with the geometry of `out`
 bool conv_tc_supported(const ConvW& w, const Act& out);
-Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out);   // split-bf16 planes [B,D,H,W,Cin_p] x2
+Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out);   // split-bf16 operand with the geometry of `out`
 void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y);
 
 }  // namespace cs

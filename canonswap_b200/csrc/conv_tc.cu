@@ -1,17 +1,456 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the kernel lands: nothing is eligible yet,
-// so every conv takes the fp32 SIMT path).
+// tcgen05 implicit-GEMM convolution for sm_100a (the dense-contraction hot path: every conv2d / conv3d
+// of the five networks with Cin >= 16 and Cout >= 8).
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * W[cout, tap, cin]
+//
+//   M tile  = 128 output pixels = one 4-D spatial box (bb x bd x bh x bw) of the channels-last input,
+//             so the A tile of filter tap (kd,kh,kw) is the SAME box shifted by the tap: one TMA tiled
+//             load per stage, the zero padding of the convolution is TMA out-of-bounds zero fill.
+//   N tile  = BN <= 256 output channels, K = taps x Cin walked in 32-channel blocks.
+//   operand = split bf16: every fp32 value v is stored as hi = bf16(v), lo = bf16(v - hi); a 32-channel
+//             block is the 128-byte row [hi x32 | lo x32], which is exactly one SWIZZLE_128B row, so a
+//             stage is ONE A box (128 rows) and ONE B box (BN rows) and the MMA descriptors of the
+//             hi / lo halves are 64-byte K-advances inside the swizzle atom.
+//   math    = 3 x tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32 in TMEM) per 16-channel K step:
+//             hi*hi + hi*lo + lo*hi  (~2^-16 relative, the 1e-3 fp32 parity bar of BASELINE.json);
+//             `npass` 2 / 1 drop the correction terms (measurement only).
+//   roles   = warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
+//             (tcgen05.ld -> bias / activation / residual / per-pixel multiplier -> fp32 channels-last).
 #include "ctx.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
 
 namespace cs {
 
-bool conv_tc_supported(const ConvW&, const Act&) { return false; }
+namespace {
 
-Opd conv_tc_alloc_operand(Arena&, const ConvW&, const Act&) { throw Error(CS_ERR_INVALID, "tcgen05 conv not built"); }
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-void conv_tc(const Launcher&, const Opd&, const ConvW&, const ConvGeom&, const Epilogue&, Act) {
-  throw Error(CS_ERR_INVALID, "tcgen05 conv not built");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 1023u) == 1023u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();       // 4 s
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 at bits 46-47,
+// layout type 2 at bits 61-63, stride byte offset = 1024 B between 8-row groups).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
 }
 
-void pack_tc(cs_ctx*, ConvW&, cudaStream_t) {}
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+struct ConvTcK {
+  int B, D, H, W;                  // output (= input) geometry
+  int lbw, lbh, lbd, lbb;          // log2 of the box extents (product 128)
+  int ntw, nth, ntd;               // tiles per dimension (batch tiles = gridDim.x / (ntw*nth*ntd))
+  int KD, KH, KW, PD, PH, PW;
+  int nblk;                        // 32-channel blocks of the (padded) input
+  int last_ksteps;                 // 16-channel K steps in the last block (1 or 2)
+  int rowA;                        // bf16 elements per pixel of the operand planes = nblk * 64
+  int BN, Cout, stages, npass;
+  const float* bias; int act; float slope;
+  const float* res; long rb, rd, rh, rw;
+  const float* mult;
+  float* y; long yb, yd, yh, yw;
+  int vec4;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int A_TILE_BYTES = 128 * 128;
+
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, ConvTcK k) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)k.BN * 128u;
+  const uint32_t bars = base + (uint32_t)k.stages * stage_bytes;      // full[stages], empty[stages], tmem_full, tmem slot
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (k.stages + s); };
+  const uint32_t tmem_full = bars + 16u * k.stages;
+  const uint32_t tmem_slot = tmem_full + 8u;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < k.BN) tmem_cols <<= 1;
+
+  // tile origin
+  int t = blockIdx.x;
+  const int tw = t % k.ntw; t /= k.ntw;
+  const int th = t % k.nth; t /= k.nth;
+  const int td = t % k.ntd; const int tb = t / k.ntd;
+  const int w0 = tw << k.lbw, h0 = th << k.lbh, d0 = td << k.lbd, b0 = tb << k.lbb;
+  const int n0 = blockIdx.y * k.BN;
+  const int taps = k.KD * k.KH * k.KW;
+  const int niter = taps * k.nblk;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < k.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int kw = tap % k.KW; const int r = tap / k.KW; const int kh = r % k.KH; const int kd = r / k.KH;
+        const int cw = w0 + kw - k.PW, ch = h0 + kh - k.PH, cd = d0 + kd - k.PD;
+        for (int blk = 0; blk < k.nblk; ++blk, ++it) {
+          const int s = it % k.stages;
+          const uint32_t ph = (uint32_t)(it / k.stages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), stage_bytes);
+          const uint32_t sa = base + (uint32_t)s * stage_bytes;
+          tma_load_5d(sa, &tmA, full_bar(s), blk * 64, cw, ch, cd, b0);
+          tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), tap * k.rowA + blk * 64, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(k.BN >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t acc = 0;
+      int it = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        for (int blk = 0; blk < k.nblk; ++blk, ++it) {
+          const int s = it % k.stages;
+          const uint32_t ph = (uint32_t)(it / k.stages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)s * stage_bytes;
+          const uint32_t sb = sa + A_TILE_BYTES;
+          const int ksteps = (blk == k.nblk - 1) ? k.last_ksteps : 2;
+          for (int pass = 0; pass < k.npass; ++pass) {
+            // pass 0: hi*hi, pass 1: lo*hi, pass 2: hi*lo   (lo half = +64 B inside the swizzled row)
+            const uint32_t aoff = (pass == 1) ? 64u : 0u;
+            const uint32_t boff = (pass == 2) ? 64u : 0u;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              tc_mma_bf16(tmem_base, umma_desc(sa + aoff + 32u * ks), umma_desc(sb + boff + 32u * ks), idesc, acc);
+              acc = 1;
+            }
+          }
+          tc_commit(empty_bar(s));
+        }
+      }
+      tc_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int r = row;
+    const int ow = w0 + (r & ((1 << k.lbw) - 1)); r >>= k.lbw;
+    const int oh = h0 + (r & ((1 << k.lbh) - 1)); r >>= k.lbh;
+    const int od = d0 + (r & ((1 << k.lbd) - 1)); r >>= k.lbd;
+    const int ob = b0 + r;
+    const bool valid = ow < k.W && oh < k.H && od < k.D && ob < k.B;
+    float* yp = k.y + ob * k.yb + od * k.yd + oh * k.yh + ow * k.yw;
+    const float* rp = k.res ? k.res + ob * k.rb + od * k.rd + oh * k.rh + ow * k.rw : nullptr;
+    float mu = 1.f;
+    if (k.mult && valid) mu = k.mult[(((long)ob * k.D + od) * k.H + oh) * k.W + ow];
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < k.BN; c0 += 16) {
+      if (n0 + c0 >= k.Cout) break;                         // warp-uniform
+      uint32_t v[16];
+      tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tc_ld_wait();
+      if (!valid) continue;
+      const int n = n0 + c0;
+      if (k.vec4 && n + 15 < k.Cout) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float x = __uint_as_float(v[j + i]);
+            if (k.bias) x += __ldg(k.bias + n + j + i);
+            o[i] = apply_act(x, k.act, k.slope);
+          }
+          if (rp) {
+            float4 rr = *reinterpret_cast<const float4*>(rp + n + j);
+            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+          }
+          if (k.mult) { o[0] *= mu; o[1] *= mu; o[2] *= mu; o[3] *= mu; }
+          *reinterpret_cast<float4*>(yp + n + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (n + j < k.Cout) {
+            float x = __uint_as_float(v[j]);
+            if (k.bias) x += __ldg(k.bias + n + j);
+            x = apply_act(x, k.act, k.slope);
+            if (rp) x += rp[n + j];
+            if (k.mult) x *= mu;
+            yp[n + j] = x;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: w32 [tap][Cin][Cout] fp32 -> [Cout_p][tap][nblk][hi 32 | lo 32] bf16
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ out, int taps,
+                                                      int Cin, int Cout, int Cout_p, int nblk) {
+  const long rowlen = (long)taps * nblk * 64;
+  const long total = (long)Cout_p * taps * nblk * 32;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int j = (int)(i & 31); long r = i >> 5;
+    int blk = (int)(r % nblk); r /= nblk;
+    int tap = (int)(r % taps); int co = (int)(r / taps);
+    int ci = blk * 32 + j;
+    float v = (co < Cout && ci < Cin) ? w32[((long)tap * Cin + ci) * Cout + co] : 0.f;
+    __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    long o = (long)co * rowlen + ((long)tap * nblk + blk) * 64 + j;
+    out[o] = hi;
+    out[o + 32] = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  if (!fn) throw Error(CS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  return fn;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int pick_bn(int Cout) {
+  int c16 = round_up(Cout, 16);
+  if (c16 <= 256) return c16;
+  // split into equal tiles of <= 256 columns
+  int nt = (c16 + 255) / 256;
+  return round_up((c16 + nt - 1) / nt, 16);
+}
+
+// power-of-two box extent p <= cap covering `dim` with the fewest padded elements (ties: larger p)
+int pick_box(int dim, int cap, int* log2out) {
+  int best = 1, bestl = 0;
+  long best_pad = dim;
+  for (int l = 1, p = 2; p <= cap; ++l, p <<= 1) {
+    long pad = (long)((dim + p - 1) / p) * p;
+    if (pad <= best_pad) { best = p; bestl = l; best_pad = pad; }
+    if (p >= dim) break;
+  }
+  *log2out = bestl;
+  return best;
+}
+
+bool g_attr_set[64] = {};
+constexpr int MAX_DYN_SMEM = 200 * 1024;
+
+}  // namespace
+
+bool conv_tc_supported(const ConvW& w, const Act& out) {
+  (void)out;
+  return w.wtc != nullptr;
+}
+
+bool conv_tc_shape_ok(int Cin, int Cout) { return Cin >= 16 && Cout >= 8; }
+
+Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out) {
+  Opd o;
+  o.B = out.B; o.D = out.D; o.H = out.H; o.W = out.W;
+  o.nblk = (w.Cin + 31) / 32;
+  o.p = A.bf16((size_t)out.B * out.D * out.H * out.W * o.nblk * 64);
+  return o;
+}
+
+void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream) {
+  if (!conv_tc_shape_ok(w.Cin, w.Cout) || !w.w32) return;
+  const int nblk = (w.Cin + 31) / 32;
+  const int BN = pick_bn(w.Cout);
+  const int Cout_p = round_up(w.Cout, BN);
+  const size_t n = (size_t)Cout_p * w.taps() * nblk * 64;
+  if (!w.wtc) w.wtc = static_cast<__nv_bfloat16*>(ctx->dmalloc(n * sizeof(__nv_bfloat16)));
+  w.nblk = nblk; w.BN = BN; w.Cout_p = Cout_p;
+  long total = (long)Cout_p * w.taps() * nblk * 32;
+  long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+  pack_tc_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w.w32, w.wtc, w.taps(), w.Cin, w.Cout, Cout_p, nblk);
+  check_launch("pack_tc");
+}
+
+void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(w.wtc != nullptr, CS_ERR_WEIGHTS, "conv_tc: tcgen05 operand not packed");
+  CS_REQUIRE(g.Do == x.D && g.Ho == x.H && g.Wo == x.W && g.PD == w.KD / 2 && g.PH == w.KH / 2 && g.PW == w.KW / 2,
+             CS_ERR_INVALID, "conv_tc: only stride-1 'same' convolutions");
+  CS_REQUIRE(y.C == w.Cout && x.nblk == w.nblk, CS_ERR_INVALID, "conv_tc: channel mismatch");
+
+  ConvTcK k{};
+  k.B = x.B; k.D = x.D; k.H = x.H; k.W = x.W;
+  int cap = 128;
+  int bw = pick_box(x.W, cap, &k.lbw); cap /= bw;
+  int bh = pick_box(x.H, cap, &k.lbh); cap /= bh;
+  int bd = pick_box(x.D, cap, &k.lbd); cap /= bd;
+  int bb = cap; k.lbb = 0; while ((1 << k.lbb) < bb) ++k.lbb;
+  k.ntw = (x.W + bw - 1) / bw; k.nth = (x.H + bh - 1) / bh; k.ntd = (x.D + bd - 1) / bd;
+  const int ntb = (x.B + bb - 1) / bb;
+  k.KD = w.KD; k.KH = w.KH; k.KW = w.KW; k.PD = g.PD; k.PH = g.PH; k.PW = g.PW;
+  k.nblk = w.nblk;
+  k.last_ksteps = ((w.Cin - (w.nblk - 1) * 32) + 15) / 16;
+  k.rowA = w.nblk * 64;
+  k.BN = w.BN; k.Cout = w.Cout;
+  k.npass = L.npass >= 1 && L.npass <= 3 ? L.npass : 3;
+  k.bias = w.bias; k.act = e.act; k.slope = e.slope;
+  k.res = e.residual; k.rb = e.rs_b; k.rd = e.rs_d; k.rh = e.rs_h; k.rw = e.rs_w;
+  k.mult = e.mult;
+  k.y = y.p; k.yb = y.sb; k.yd = y.sd; k.yh = y.sh; k.yw = y.sw;
+  auto al4 = [](long v) { return (v & 3) == 0; };
+  k.vec4 = al4(y.sb) && al4(y.sd) && al4(y.sh) && al4(y.sw) && ((uintptr_t)y.p % 16 == 0) &&
+           (!e.residual || (al4(e.rs_b) && al4(e.rs_d) && al4(e.rs_h) && al4(e.rs_w) && ((uintptr_t)e.residual % 16 == 0)));
+
+  const int stage_bytes = A_TILE_BYTES + k.BN * 128;
+  const int niter = w.taps() * w.nblk;
+  // thin-N tiles keep the footprint under ~100 KB so two CTAs share an SM (prologue / epilogue overlap)
+  const int budget = (k.BN <= 64) ? 100 * 1024 : MAX_DYN_SMEM;
+  int stages = (budget - 2048) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > niter) stages = niter;
+  if (stages < 1) stages = 1;
+  k.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 16 * stages + 32;
+
+  // tensor maps
+  auto enc = encode_fn();
+  CUtensorMap tmA, tmB;
+  {
+    const cuuint64_t pix = (cuuint64_t)k.rowA * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)k.rowA, (cuuint64_t)x.W, (cuuint64_t)x.H, (cuuint64_t)x.D, (cuuint64_t)x.B};
+    cuuint64_t strides[4] = {pix, pix * x.W, pix * x.W * x.H, pix * x.W * x.H * x.D};
+    cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, (cuuint32_t)bb};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CS_REQUIRE(r == CUDA_SUCCESS, CS_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled(A) failed");
+  }
+  {
+    const cuuint64_t rowlen = (cuuint64_t)w.taps() * k.rowA;
+    cuuint64_t dims[2] = {rowlen, (cuuint64_t)w.Cout_p};
+    cuuint64_t strides[1] = {rowlen * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)k.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.wtc, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CS_REQUIRE(r == CUDA_SUCCESS, CS_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled(B) failed");
+  }
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (!g_attr_set[dev & 63]) {
+    CS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
+    g_attr_set[dev & 63] = true;
+  }
+  dim3 grid((unsigned)(k.ntw * k.nth * k.ntd * ntb), (unsigned)(w.Cout_p / k.BN));
+  const long M = (long)x.B * x.D * x.H * x.W;
+  ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * w.Cout * w.Cin * w.taps(), 0.0);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, L.stream>>>(tmA, tmB, k);
+  check_launch("conv_tc");
+}
 
 }  // namespace cs

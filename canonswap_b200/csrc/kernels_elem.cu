@@ -22,7 +22,7 @@ struct PrepK {
   int Cout;                 // channels written (>= Cl, pad written as zero)
   // outputs
   float* o32; long ob, od, oh, ow;
-  __nv_bfloat16 *ohi, *olo; long pb, pd, ph, pw;
+  __nv_bfloat16* opl; long prow;   // split-bf16 operand: dense pixels, prow = nblk*64 elements per pixel
 };
 
 __global__ void __launch_bounds__(256) prep_kernel(PrepK k) {
@@ -59,11 +59,11 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepK k) {
       v = apply_act(v, k.act, k.slope);
     }
     if (k.o32 && c < k.Cl) k.o32[b * k.ob + d * k.od + h * k.oh + w * k.ow + c] = v;
-    if (k.ohi) {
-      long o = b * k.pb + d * k.pd + h * k.ph + w * k.pw + c;
+    if (k.opl) {
+      long o = pix * k.prow + (c >> 5) * 64 + (c & 31);
       __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      k.ohi[o] = hi;
-      k.olo[o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      k.opl[o] = hi;
+      k.opl[o + 32] = __float2bfloat16_rn(v - __bfloat162float(hi));
     }
   }
 }
@@ -101,9 +101,9 @@ void prep_f32(const Launcher& L, const Prep& p, Act out) {
 
 void prep_planes(const Launcher& L, const Prep& p, Opd out, const Act* out32) {
   PrepK k = make_prepk(p);
-  CS_REQUIRE(out.Cp >= k.Cl, -1, "prep_planes: padded channels too small");
-  k.B = out.B; k.D = out.D; k.H = out.H; k.W = out.W; k.Cout = out.Cp;
-  k.ohi = out.hi; k.olo = out.lo; k.pb = out.sb; k.pd = out.sd; k.ph = out.sh; k.pw = out.sw;
+  CS_REQUIRE(out.nblk * 32 >= k.Cl, -1, "prep_planes: padded channels too small");
+  k.B = out.B; k.D = out.D; k.H = out.H; k.W = out.W; k.Cout = out.nblk * 32;
+  k.opl = out.p; k.prow = (long)out.nblk * 64;
   if (out32) {
     CS_REQUIRE(out32->C == k.Cl, -1, "prep_planes: fp32 copy channel mismatch");
     k.o32 = out32->p; k.ob = out32->sb; k.od = out32->sd; k.oh = out32->sh; k.ow = out32->sw;

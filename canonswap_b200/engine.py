@@ -63,9 +63,10 @@ class Engine:
             raise CanonSwapError(f"cs_create failed ({rc}): {msg}")
         if conv_impl:
             self.set_option(_lib.CS_OPT_CONV_IMPL, conv_impl)
-        table, keep = _flat_table(weights)
-        self._check(self._lib.cs_load_weights(self._ctx, table, len(table)))
-        del keep
+        if weights is not None:          # None: kernel-level test entry points only (no networks)
+            table, keep = _flat_table(weights)
+            self._check(self._lib.cs_load_weights(self._ctx, table, len(table)))
+            del keep
         self._identity = None
 
     # ------------------------------------------------------------------------------------------

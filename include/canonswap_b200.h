@@ -61,6 +61,7 @@ typedef struct cs_tensor_desc {
 
 /* options of cs_set_option */
 #define CS_OPT_CONV_IMPL 1       /* 0 = auto (tcgen05 where eligible), 1 = force SIMT fp32 convs (debug) */
+#define CS_OPT_TC_PASSES 3       /* split-bf16 MMA passes of the tcgen05 conv: 3 (default, fp32-grade) | 2 | 1 (measurement only) */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

@@ -57,6 +57,31 @@ def test_conv_simt_matches_torch(eng, case, act):
     assert (y - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
 
 
+TC_CASES = [c for c in CONV_CASES if c[4] >= 16 and c[5] >= 8] + [
+    (3, 16, 1, 1, 512, 1024, (3, 3, 3), (1, 1, 1)),   # deepest hourglass level at net 128: 1x1 spatial, batch-tiled box
+    (1, 1, 24, 40, 48, 272, (1, 3, 3), (0, 1, 1)),    # non-power-of-two extents, two N tiles of 144
+    (2, 1, 64, 64, 512, 512, (1, 3, 3), (0, 1, 1)),   # the most-used shape
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("act", [0, 2])
+def test_conv_tcgen05_matches_torch(eng, case, act):
+    """The tcgen05 split-bf16 implicit GEMM (3 MMA passes, fp32 accumulate in TMEM) against fp64 torch:
+    fp32-grade agreement, far inside the 1e-3 parity bar."""
+    B, D, H, W, Cin, Cout, k, pad = case
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(B, D, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, *k, device="cuda", generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    y = eng.test_conv(x, w, b, pad, act=act, slope=0.2, impl=2)
+    ref = _ref_conv(x, w, b, pad)
+    if act == 2:
+        ref = F.leaky_relu(ref, 0.2)
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
+
+
 def test_conv_sigmoid_cout1(eng):
     g = torch.Generator(device="cuda").manual_seed(8)
     x = torch.randn(2, 1, 8, 8, 512, device="cuda", generator=g)

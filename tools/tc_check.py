@@ -1,0 +1,79 @@
+"""Development probe (GPU box): tcgen05 conv vs torch on many shapes, errors + per-launch timing.
+Prints one line per case; never asserts, so one run shows every shape."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+from canonswap_b200 import synth, _lib
+from canonswap_b200.engine import Engine
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+CASES = [
+    # B, D, H, W, Cin, Cout, k, pad, time?
+    (1, 1, 8, 16, 64, 64, (1, 1, 1), (0, 0, 0), 0),
+    (1, 1, 8, 16, 64, 64, (1, 3, 3), (0, 1, 1), 0),
+    (2, 1, 8, 8, 64, 128, (1, 3, 3), (0, 1, 1), 0),
+    (1, 1, 8, 8, 256, 512, (1, 1, 1), (0, 0, 0), 0),
+    (1, 16, 8, 8, 32, 32, (3, 3, 3), (1, 1, 1), 0),
+    (1, 16, 4, 4, 110, 64, (3, 3, 3), (1, 1, 1), 0),
+    (1, 16, 8, 8, 142, 22, (7, 7, 7), (3, 3, 3), 0),
+    (1, 16, 2, 2, 64, 48, (3, 3, 3), (1, 1, 1), 0),
+    (3, 16, 1, 1, 512, 1024, (3, 3, 3), (1, 1, 1), 0),
+    (1, 1, 8, 8, 64, 12, (1, 3, 3), (0, 1, 1), 0),
+    (1, 1, 5, 7, 20, 33, (1, 3, 3), (0, 1, 1), 0),
+    (1, 1, 24, 40, 48, 272, (1, 3, 3), (0, 1, 1), 0),
+    # real shapes, timed
+    (8, 1, 64, 64, 512, 512, (1, 3, 3), (0, 1, 1), 1),
+    (8, 1, 64, 64, 512, 1024, (1, 3, 3), (0, 1, 1), 1),
+    (8, 1, 64, 64, 256, 128, (1, 3, 3), (0, 1, 1), 1),
+    (8, 1, 64, 64, 128, 1024, (1, 3, 3), (0, 1, 1), 1),
+    (8, 16, 64, 64, 32, 32, (3, 3, 3), (1, 1, 1), 1),
+    (2, 16, 64, 64, 142, 142, (3, 3, 3), (1, 1, 1), 1),
+    (2, 16, 64, 64, 142, 22, (7, 7, 7), (3, 3, 3), 1),
+    (8, 1, 256, 256, 64, 64, (1, 3, 3), (0, 1, 1), 1),
+    (8, 1, 256, 256, 128, 64, (1, 3, 3), (0, 1, 1), 1),
+    (8, 1, 128, 128, 256, 256, (1, 3, 3), (0, 1, 1), 1),
+]
+
+
+def main():
+    passes = [int(a) for a in sys.argv[1:]] or [3]
+    eng = Engine(None, net_hw=(128, 128), max_batch=1, device=0)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for np_ in passes:
+        eng.set_option(_lib.CS_OPT_TC_PASSES, np_)
+        for (B, D, H, Wd, Cin, Cout, k, pad, timed) in CASES:
+            x = torch.randn(B, D, H, Wd, Cin, device="cuda", generator=g)
+            w = torch.randn(Cout, Cin, *k, device="cuda", generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5
+            b = torch.randn(Cout, device="cuda", generator=g)
+            tag = f"np={np_} B{B} D{D} {H}x{Wd} {Cin}->{Cout} k{k}"
+            try:
+                eng.profile(True)
+                y = eng.test_conv(x, w, b, pad, act=2, slope=0.2, impl=2)
+                if timed:
+                    for _ in range(3):
+                        y = eng.test_conv(x, w, b, pad, act=2, slope=0.2, impl=2)
+                torch.cuda.synchronize()
+                fam = eng.profile_read()["conv_tcgen05"]
+                eng.profile(False)
+                xr = x.permute(0, 4, 1, 2, 3).contiguous()
+                if timed:
+                    ref = F.leaky_relu(F.conv3d(xr, w, b, padding=pad), 0.2).permute(0, 2, 3, 4, 1)
+                else:
+                    ref = F.leaky_relu(F.conv3d(xr.double(), w.double(), b.double(), padding=pad), 0.2).permute(0, 2, 3, 4, 1).float()
+                err = (y - ref).abs().max().item()
+                scale = ref.abs().max().item()
+                ms = fam["ms"] / max(1, fam["launches"])
+                tf = fam["flops"] / max(1, fam["launches"]) / (ms * 1e9) if ms > 0 else 0
+                print(f"{tag}: max|d|={err:.3e} (ref max {scale:.2f}) {ms:.3f} ms {tf:.1f} TF/s-equiv", flush=True)
+            except Exception as e:
+                print(f"{tag}: FAILED {type(e).__name__}: {e}", flush=True)
+                if "CUDA" in str(e) or "launch" in str(e) or "illegal" in str(e) or "unspecified" in str(e):
+                    raise
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
