@@ -115,6 +115,7 @@ struct ConvTcK {
   int last_ksteps;                 // 16-channel K steps in the last block (1 or 2)
   int rowA;                        // bf16 elements per pixel of the operand planes = nblk * 64
   int BN, Cout, stages, npass;
+  int tcols, nsets;                // TMEM columns allocated, accumulator sets of BN columns (see kernel)
   const float* bias; int act; float slope;
   const float* res; long rb, rd, rh, rw;
   const float* mult;
@@ -139,8 +140,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < k.BN) tmem_cols <<= 1;
+  const uint32_t tmem_cols = (uint32_t)k.tcols;
+  // Accumulator sets.  The tensor core adds every MMA into the fp32 TMEM accumulator with truncation, so
+  // the error of one accumulator grows linearly with its chain length (~2^-24 |acc| per MMA, measured).
+  // The chain is therefore split over `nsets` accumulators of BN columns that the epilogue sums in
+  // fp32 registers: set 0 takes the small correction products (lo*hi, hi*lo), sets 1.. take hi*hi of
+  // consecutive K ranges.
+  const int corr = (k.npass > 1 && k.nsets > 1) ? 1 : 0;
+  const int nmain = k.nsets - corr;
 
   // tile origin
   int t = blockIdx.x;
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(k.BN >> 3) << 17) | ((128u >> 4) << 24);
-      uint32_t acc = 0;
+      uint32_t used = 0;
       int it = 0;
       for (int tap = 0; tap < taps; ++tap) {
         for (int blk = 0; blk < k.nblk; ++blk, ++it) {
@@ -202,13 +209,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           const uint32_t sb = sa + A_TILE_BYTES;
           const int ksteps = (blk == k.nblk - 1) ? k.last_ksteps : 2;
+          const int main_set = corr + (int)(((long)it * nmain) / niter);
           for (int pass = 0; pass < k.npass; ++pass) {
             // pass 0: hi*hi, pass 1: lo*hi, pass 2: hi*lo   (lo half = +64 B inside the swizzled row)
             const uint32_t aoff = (pass == 1) ? 64u : 0u;
             const uint32_t boff = (pass == 2) ? 64u : 0u;
+            const int set = (pass == 0 || !corr) ? main_set : 0;
+            const uint32_t d = tmem_base + (uint32_t)(set * k.BN);
             for (int ks = 0; ks < ksteps; ++ks) {
-              tc_mma_bf16(tmem_base, umma_desc(sa + aoff + 32u * ks), umma_desc(sb + boff + 32u * ks), idesc, acc);
-              acc = 1;
+              tc_mma_bf16(d, umma_desc(sa + aoff + 32u * ks), umma_desc(sb + boff + 32u * ks), idesc, (used >> set) & 1u);
+              used |= 1u << set;
             }
           }
           tc_commit(empty_bar(s));
@@ -235,8 +245,23 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     for (int c0 = 0; c0 < k.BN; c0 += 16) {
       if (n0 + c0 >= k.Cout) break;                         // warp-uniform
       uint32_t v[16];
-      tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      tc_ld16(trow + (uint32_t)(corr * k.BN), v);
       tc_ld_wait();
+      for (int st = corr + 1; st < k.nsets; ++st) {          // main sets in K order ...
+        uint32_t u[16];
+        tc_ld16(trow + (uint32_t)(st * k.BN), u);
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+      }
+      if (corr) {                                            // ... then the small correction terms
+        uint32_t u[16];
+        tc_ld16(trow, u);
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+      }
       if (!valid) continue;
       const int n = n0 + c0;
       if (k.vec4 && n + 15 < k.Cout) {
@@ -364,7 +389,8 @@ Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out) {
 void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream) {
   if (!conv_tc_shape_ok(w.Cin, w.Cout) || !w.w32) return;
   const int nblk = (w.Cin + 31) / 32;
-  const int BN = pick_bn(w.Cout);
+  int BN = pick_bn(w.Cout);
+  if (w.taps() * nblk * 2 > 1024 && BN > 128) BN = 128;      // deep K: 4 accumulator sets instead of 2
   const int Cout_p = round_up(w.Cout, BN);
   const size_t n = (size_t)Cout_p * w.taps() * nblk * 64;
   if (!w.wtc) w.wtc = static_cast<__nv_bfloat16*>(ctx->dmalloc(n * sizeof(__nv_bfloat16)));
@@ -408,8 +434,25 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
 
   const int stage_bytes = A_TILE_BYTES + k.BN * 128;
   const int niter = w.taps() * w.nblk;
+  // accumulator sets: one for the correction products + enough hi*hi sets for chains of <= ~256 MMAs
+  {
+    const int steps_main = niter * 2;
+    int want = 1 + (steps_main + 255) / 256;
+    if (k.npass == 1) want -= 1;
+    if (want < 1) want = 1;
+    int cols = k.BN * want;
+    if (cols > 512) cols = 512;
+    int tcols = 32;
+    while (tcols < cols) tcols <<= 1;
+    int nsets = tcols / k.BN;
+    if (nsets > 16) nsets = 16;
+    const int maxsets = niter + (k.npass > 1 ? 1 : 0);
+    if (nsets > maxsets) nsets = maxsets;
+    if (nsets < 1) nsets = 1;
+    k.tcols = tcols; k.nsets = nsets;
+  }
   // thin-N tiles keep the footprint under ~100 KB so two CTAs share an SM (prologue / epilogue overlap)
-  const int budget = (k.BN <= 64) ? 100 * 1024 : MAX_DYN_SMEM;
+  const int budget = (k.BN <= 64 && k.tcols <= 256) ? 100 * 1024 : MAX_DYN_SMEM;
   int stages = (budget - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > niter) stages = niter;
