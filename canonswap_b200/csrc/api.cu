@@ -394,16 +394,17 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
     ConvGeom g; g.PD = PD; g.PH = PH; g.PW = PW; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
     Epilogue e; e.act = act; e.slope = slope;
     Launcher L; L.stream = st; L.counter = &ctx->launches; L.npass = ctx->tc_passes; L.prof = &ctx->prof;
-    const bool same = (Do == D && Ho == H && Wo == W && PD == KD / 2 && PH == KH / 2 && PW == KW / 2);
+    const bool same = (Ho == H && Wo == W && PH == KH / 2 && PW == KW / 2) &&
+                      ((Do == D && PD == KD / 2) || (Do == 1 && KD == D && PD == 0));
     bool tc = same && conv_tc_supported(cw, ya);
     if (impl == 2) CS_REQUIRE(tc, CS_ERR_INVALID, "cs_test_conv: shape not supported by the tcgen05 conv");
     if (impl == 1) tc = false;
     if (tc) {
       // private scratch for the operand planes (the ctx arena may not exist before cs_load_weights)
       Arena tmp; tmp.measuring = true;
-      conv_tc_alloc_operand(tmp, cw, ya);
+      conv_tc_alloc_operand(tmp, cw, xa);
       Arena real; real.cap = tmp.high + 4096; real.base = static_cast<char*>(ctx->dmalloc(real.cap));
-      Opd opd = conv_tc_alloc_operand(real, cw, ya);
+      Opd opd = conv_tc_alloc_operand(real, cw, xa);
       Prep p; p.src0 = xa;
       prep_planes(L, p, opd, nullptr);
       conv_tc(L, opd, cw, g, e, ya);

@@ -93,29 +93,79 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 at bits 46-47,
-// layout type 2 at bits 61-63, stride byte offset = 1024 B between 8-row groups).
+// layout type 2 at bits 61-63, stride byte offset = 1024 B between 8-row groups). The low word is the
+// 16-byte-granular start address, so a K advance of 32 B (one 16-element bf16 K step) is +2 and the
+// lo half of a [hi x32 | lo x32] row (+64 B) is +4.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(1024u >> 4) << 32;
-  d |= 1ull << 46;
-  d |= 2ull << 61;
-  return d;
+  constexpr uint64_t HI = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;
+  return HI | (uint64_t)((saddr & 0x3FFFFu) >> 4);
+}
+
+// All the MMAs of one pipeline stage (one 32-channel K block) + the commit that frees the stage, issued
+// by one elected lane of a converged warp in a single asm block (the issue thread is the critical path
+// of the kernel: no divergence bookkeeping, no per-MMA descriptor rebuild).
+//   hi*hi -> [d_main] (first MMA accumulates iff acc_main), lo*hi and hi*lo -> [d_corr] (iff acc_corr)
+#define CS_MMA_HEAD                                   \
+  "{\n\t"                                             \
+  ".reg .pred pe, pm, pc, pt;\n\t"                    \
+  ".reg .b64 a2, a4, a6, b2, b4, b6;\n\t"             \
+  "elect.sync _|pe, 0xffffffff;\n\t"                  \
+  "setp.ne.b32 pm, %5, 0;\n\t"                        \
+  "setp.ne.b32 pc, %6, 0;\n\t"                        \
+  "setp.eq.b32 pt, %4, %4;\n\t"                       \
+  "add.s64 a2, %2, 2;\n\t"                            \
+  "add.s64 a4, %2, 4;\n\t"                            \
+  "add.s64 a6, %2, 6;\n\t"                            \
+  "add.s64 b2, %3, 2;\n\t"                            \
+  "add.s64 b4, %3, 4;\n\t"                            \
+  "add.s64 b6, %3, 6;\n\t"
+#define CS_MMA(D, A, B, P) "@pe tcgen05.mma.cta_group::1.kind::f16 [" D "], " A ", " B ", %4, " P ";\n\t"
+#define CS_MMA_TAIL "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
+#define CS_MMA_OPS                                                                                                     \
+  ::"r"(d_main), "r"(d_corr), "l"(ad), "l"(bd), "r"(idesc), "r"(acc_main), "r"(acc_corr), "r"(bar) : "memory"
+
+template <int NPASS, int KSTEPS>
+__device__ __forceinline__ void mma_stage(uint32_t d_main, uint32_t d_corr, uint64_t ad, uint64_t bd, uint32_t idesc,
+                                          uint32_t acc_main, uint32_t acc_corr, uint32_t bar) {
+  if constexpr (NPASS == 3 && KSTEPS == 2) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%0", "a2", "b2", "pt")      // hi*hi
+                 CS_MMA("%1", "a4", "%3", "pc") CS_MMA("%1", "a6", "b2", "pt")                  // lo*hi
+                 CS_MMA("%1", "%2", "b4", "pt") CS_MMA("%1", "a2", "b6", "pt") CS_MMA_TAIL CS_MMA_OPS);
+  } else if constexpr (NPASS == 3 && KSTEPS == 1) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%1", "a4", "%3", "pc") CS_MMA("%1", "%2", "b4", "pt")
+                     CS_MMA_TAIL CS_MMA_OPS);
+  } else if constexpr (NPASS == 2 && KSTEPS == 2) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%0", "a2", "b2", "pt") CS_MMA("%1", "a4", "%3", "pc")
+                     CS_MMA("%1", "a6", "b2", "pt") CS_MMA_TAIL CS_MMA_OPS);
+  } else if constexpr (NPASS == 2 && KSTEPS == 1) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%1", "a4", "%3", "pc") CS_MMA_TAIL CS_MMA_OPS);
+  } else if constexpr (NPASS == 1 && KSTEPS == 2) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%0", "a2", "b2", "pt") CS_MMA_TAIL CS_MMA_OPS);
+  } else {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA_TAIL CS_MMA_OPS);
+  }
+}
+
+template <int NPASS>
+__device__ __forceinline__ void mma_stage_k(int ksteps, uint32_t d_main, uint32_t d_corr, uint64_t ad, uint64_t bd,
+                                            uint32_t idesc, uint32_t acc_main, uint32_t acc_corr, uint32_t bar) {
+  if (ksteps == 2) mma_stage<NPASS, 2>(d_main, d_corr, ad, bd, idesc, acc_main, acc_corr, bar);
+  else mma_stage<NPASS, 1>(d_main, d_corr, ad, bd, idesc, acc_main, acc_corr, bar);
 }
 
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
 struct ConvTcK {
-  int B, D, H, W;                  // output (= input) geometry
+  int B, D, H, W;                  // output geometry (the tensor map carries the input extents)
   int lbw, lbh, lbd, lbb;          // log2 of the box extents (product 128)
   int ntw, nth, ntd;               // tiles per dimension (batch tiles = gridDim.x / (ntw*nth*ntd))
   int KD, KH, KW, PD, PH, PW;
   int nblk;                        // 32-channel blocks of the (padded) input
   int last_ksteps;                 // 16-channel K steps in the last block (1 or 2)
-  int rowA;                        // bf16 elements per pixel of the operand planes = nblk * 64
+  int rowA;                        // bf16 elements per pixel of the operand = nblk * 64
   int BN, Cout, stages, npass;
-  int tcols, nsets;                // TMEM columns allocated, accumulator sets of BN columns (see kernel)
+  int tcols, nsets, chunk;         // TMEM columns, accumulator sets of BN columns, K iterations per hi*hi set
   const float* bias; int act; float slope;
   const float* res; long rb, rd, rh, rw;
   const float* mult;
@@ -125,19 +175,19 @@ struct ConvTcK {
 
 constexpr int TC_THREADS = 192;
 constexpr int A_TILE_BYTES = 128 * 128;
+constexpr int STG_LD = 36;                                  // floats per staged row (32 + pad, 16-B aligned)
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;              // one 32x32 fp32 staging tile per epilogue warp
 
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, ConvTcK k) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)k.BN * 128u;
-  const uint32_t bars = base + (uint32_t)k.stages * stage_bytes;      // full[stages], empty[stages], tmem_full, tmem slot
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (k.stages + s); };
+  const uint32_t stg = base + (uint32_t)k.stages * stage_bytes;       // epilogue staging
+  const uint32_t bars = stg + STG_BYTES;                              // full[stages], empty[stages], tmem_full, tmem slot
   const uint32_t tmem_full = bars + 16u * k.stages;
   const uint32_t tmem_slot = tmem_full + 8u;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (uint32_t)k.tcols;
@@ -145,9 +195,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   // the error of one accumulator grows linearly with its chain length (~2^-24 |acc| per MMA, measured).
   // The chain is therefore split over `nsets` accumulators of BN columns that the epilogue sums in
   // fp32 registers: set 0 takes the small correction products (lo*hi, hi*lo), sets 1.. take hi*hi of
-  // consecutive K ranges.
+  // consecutive K ranges of `chunk` iterations.
   const int corr = (k.npass > 1 && k.nsets > 1) ? 1 : 0;
-  const int nmain = k.nsets - corr;
 
   // tile origin
   int t = blockIdx.x;
@@ -157,12 +206,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const int w0 = tw << k.lbw, h0 = th << k.lbh, d0 = td << k.lbd, b0 = tb << k.lbb;
   const int n0 = blockIdx.y * k.BN;
   const int taps = k.KD * k.KH * k.KW;
-  const int niter = taps * k.nblk;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < k.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < k.stages; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (k.stages + s), 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -173,127 +221,157 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (one lane) =====
     if (lane == 0) {
-      int it = 0;
+      int s = 0; uint32_t ph = 0;
       for (int tap = 0; tap < taps; ++tap) {
         const int kw = tap % k.KW; const int r = tap / k.KW; const int kh = r % k.KH; const int kd = r / k.KH;
         const int cw = w0 + kw - k.PW, ch = h0 + kh - k.PH, cd = d0 + kd - k.PD;
-        for (int blk = 0; blk < k.nblk; ++blk, ++it) {
-          const int s = it % k.stages;
-          const uint32_t ph = (uint32_t)(it / k.stages) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), stage_bytes);
+        const int kcol = tap * k.rowA;
+        for (int blk = 0; blk < k.nblk; ++blk) {
+          const uint32_t fb = bars + 8u * s;
+          mbar_wait(fb + 8u * k.stages, ph ^ 1u);
+          mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
-          tma_load_5d(sa, &tmA, full_bar(s), blk * 64, cw, ch, cd, b0);
-          tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), tap * k.rowA + blk * 64, n0);
+          tma_load_5d(sa, &tmA, fb, blk * 64, cw, ch, cd, b0);
+          tma_load_2d(sa + A_TILE_BYTES, &tmB, fb, kcol + blk * 64, n0);
+          if (++s == k.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(k.BN >> 3) << 17) | ((128u >> 4) << 24);
-      uint32_t used = 0;
-      int it = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        for (int blk = 0; blk < k.nblk; ++blk, ++it) {
-          const int s = it % k.stages;
-          const uint32_t ph = (uint32_t)(it / k.stages) & 1u;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t sa = base + (uint32_t)s * stage_bytes;
-          const uint32_t sb = sa + A_TILE_BYTES;
-          const int ksteps = (blk == k.nblk - 1) ? k.last_ksteps : 2;
-          const int main_set = corr + (int)(((long)it * nmain) / niter);
-          for (int pass = 0; pass < k.npass; ++pass) {
-            // pass 0: hi*hi, pass 1: lo*hi, pass 2: hi*lo   (lo half = +64 B inside the swizzled row)
-            const uint32_t aoff = (pass == 1) ? 64u : 0u;
-            const uint32_t boff = (pass == 2) ? 64u : 0u;
-            const int set = (pass == 0 || !corr) ? main_set : 0;
-            const uint32_t d = tmem_base + (uint32_t)(set * k.BN);
-            for (int ks = 0; ks < ksteps; ++ks) {
-              tc_mma_bf16(d, umma_desc(sa + aoff + 32u * ks), umma_desc(sb + boff + 32u * ks), idesc, (used >> set) & 1u);
-              used |= 1u << set;
-            }
-          }
-          tc_commit(empty_bar(s));
+    // ===== MMA issuer: the whole warp walks the loop converged, one elected lane issues =====
+    // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(k.BN >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t d_corr0 = tmem_base;
+    uint32_t d_main = tmem_base + (uint32_t)(corr * k.BN);
+    int s = 0; uint32_t ph = 0;
+    int in_set = 0;
+    uint32_t acc_corr = 0;
+    for (int tap = 0; tap < taps; ++tap) {
+      for (int blk = 0; blk < k.nblk; ++blk) {
+        const uint32_t fb = bars + 8u * s;
+        mbar_wait(fb, ph);
+        tc_fence_after();
+        const uint32_t sa = base + (uint32_t)s * stage_bytes;
+        const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + A_TILE_BYTES);
+        const int ksteps = (blk == k.nblk - 1) ? k.last_ksteps : 2;
+        const uint32_t acc_main = in_set > 0 ? 1u : 0u;
+        const uint32_t eb = fb + 8u * k.stages;
+        if (corr) {
+          mma_stage_k<3>(ksteps, d_main, d_corr0, ad, bd, idesc, acc_main, acc_corr, eb);
+        } else if (k.npass == 3) {                       // single accumulator: corrections follow hi*hi in place
+          mma_stage_k<3>(ksteps, d_main, d_main, ad, bd, idesc, acc_main, 1u, eb);
+        } else if (k.npass == 2) {
+          mma_stage_k<2>(ksteps, d_main, d_main, ad, bd, idesc, acc_main, 1u, eb);
+        } else {
+          mma_stage_k<1>(ksteps, d_main, d_main, ad, bd, idesc, acc_main, 1u, eb);
         }
+        acc_corr = 1u;
+        if (++in_set == k.chunk) { in_set = 0; d_main += (uint32_t)k.BN; }
+        if (++s == k.stages) { s = 0; ph ^= 1u; }
       }
-      tc_commit(tmem_full);
     }
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(tmem_full) : "memory");
   } else {
     // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 =====
+    // phase 1: each lane pulls its pixel row (32 columns, all accumulator sets summed) into a padded smem tile;
+    // phase 2: the warp walks the tile 4 rows x 128 B at a time so global stores / residual loads are coalesced.
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    int r = row;
-    const int ow = w0 + (r & ((1 << k.lbw) - 1)); r >>= k.lbw;
-    const int oh = h0 + (r & ((1 << k.lbh) - 1)); r >>= k.lbh;
-    const int od = d0 + (r & ((1 << k.lbd) - 1)); r >>= k.lbd;
-    const int ob = b0 + r;
-    const bool valid = ow < k.W && oh < k.H && od < k.D && ob < k.B;
-    float* yp = k.y + ob * k.yb + od * k.yd + oh * k.yh + ow * k.yw;
-    const float* rp = k.res ? k.res + ob * k.rb + od * k.rd + oh * k.rh + ow * k.rw : nullptr;
-    float mu = 1.f;
-    if (k.mult && valid) mu = k.mult[(((long)ob * k.D + od) * k.H + oh) * k.W + ow];
+    float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + q * 32 * STG_LD;
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    long yoff[8], roff[8];
+    float mu[8];
+    uint32_t vmask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int r = q * 32 + sub + 4 * i;
+      const int ow = w0 + (r & ((1 << k.lbw) - 1)); r >>= k.lbw;
+      const int oh = h0 + (r & ((1 << k.lbh) - 1)); r >>= k.lbh;
+      const int od = d0 + (r & ((1 << k.lbd) - 1)); r >>= k.lbd;
+      const int ob = b0 + r;
+      const bool valid = ow < k.W && oh < k.H && od < k.D && ob < k.B;
+      if (valid) vmask |= 1u << i;
+      yoff[i] = ob * k.yb + od * k.yd + oh * k.yh + ow * k.yw;
+      roff[i] = ob * k.rb + od * k.rd + oh * k.rh + ow * k.rw;
+      mu[i] = (k.mult && valid) ? k.mult[(((long)ob * k.D + od) * k.H + oh) * k.W + ow] : 1.f;
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    for (int c0 = 0; c0 < k.BN; c0 += 16) {
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < k.BN; c0 += 32) {
       if (n0 + c0 >= k.Cout) break;                         // warp-uniform
-      uint32_t v[16];
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      tc_ld16(trow + (uint32_t)(corr * k.BN), v);
-      tc_ld_wait();
-      for (int st = corr + 1; st < k.nsets; ++st) {          // main sets in K order ...
-        uint32_t u[16];
-        tc_ld16(trow + (uint32_t)(st * k.BN), u);
-        tc_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-      }
-      if (corr) {                                            // ... then the small correction terms
-        uint32_t u[16];
-        tc_ld16(trow, u);
-        tc_ld_wait();
+      for (int half = 0; half < 2; ++half) {
+        if (c0 + 16 * half < k.BN) {                        // warp-uniform (BN is a multiple of 16)
+          uint32_t v[16];
+          const uint32_t tcol = trow + (uint32_t)(c0 + 16 * half);
+          tc_ld16(tcol + (uint32_t)(corr * k.BN), v);
+          tc_ld_wait();
+          for (int st = corr + 1; st < k.nsets; ++st) {     // hi*hi sets in K order ...
+            uint32_t u[16];
+            tc_ld16(tcol + (uint32_t)(st * k.BN), u);
+            tc_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-      }
-      if (!valid) continue;
-      const int n = n0 + c0;
-      if (k.vec4 && n + 15 < k.Cout) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float x = __uint_as_float(v[j + i]);
-            if (k.bias) x += __ldg(k.bias + n + j + i);
-            o[i] = apply_act(x, k.act, k.slope);
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
           }
-          if (rp) {
-            float4 rr = *reinterpret_cast<const float4*>(rp + n + j);
-            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-          }
-          if (k.mult) { o[0] *= mu; o[1] *= mu; o[2] *= mu; o[3] *= mu; }
-          *reinterpret_cast<float4*>(yp + n + j) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-      } else {
+          if (corr) {                                       // ... then the small correction terms
+            uint32_t u[16];
+            tc_ld16(tcol, u);
+            tc_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (n + j < k.Cout) {
-            float x = __uint_as_float(v[j]);
-            if (k.bias) x += __ldg(k.bias + n + j);
-            x = apply_act(x, k.act, k.slope);
-            if (rp) x += rp[n + j];
-            if (k.mult) x *= mu;
-            yp[n + j] = x;
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
           }
+          float4* dst = reinterpret_cast<float4*>(tile + lane * STG_LD + 16 * half);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
         }
       }
+      __syncwarp();
+      const int n = n0 + c0 + c4;
+      if (c0 + c4 < k.BN && n < k.Cout) {
+        float bz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (k.bias) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (n + j < k.Cout) bz[j] = __ldg(k.bias + n + j);
+        }
+        const bool full4 = k.vec4 && (n + 3 < k.Cout);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!((vmask >> i) & 1u)) continue;
+          const float4 a = *reinterpret_cast<const float4*>(tile + (sub + 4 * i) * STG_LD + c4);
+          float o[4] = {a.x + bz[0], a.y + bz[1], a.z + bz[2], a.w + bz[3]};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], k.act, k.slope);
+          float* yp = k.y + yoff[i] + n;
+          if (full4) {
+            if (k.res) {
+              const float4 rr = *reinterpret_cast<const float4*>(k.res + roff[i] + n);
+              o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+            }
+            *reinterpret_cast<float4*>(yp) = make_float4(o[0] * mu[i], o[1] * mu[i], o[2] * mu[i], o[3] * mu[i]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (n + j < k.Cout) {
+                float x = o[j];
+                if (k.res) x += k.res[roff[i] + n + j];
+                yp[j] = x * mu[i];
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
     }
   }
 
@@ -376,7 +454,7 @@ bool conv_tc_supported(const ConvW& w, const Act& out) {
   return w.wtc != nullptr;
 }
 
-bool conv_tc_shape_ok(int Cin, int Cout) { return Cin >= 16 && Cout >= 8; }
+bool conv_tc_shape_ok(int Cin, int Cout) { return Cin >= 16 && Cout >= 1; }
 
 Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out) {
   Opd o;
@@ -405,18 +483,21 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   L.count();
   if (L.dry) return;
   CS_REQUIRE(w.wtc != nullptr, CS_ERR_WEIGHTS, "conv_tc: tcgen05 operand not packed");
-  CS_REQUIRE(g.Do == x.D && g.Ho == x.H && g.Wo == x.W && g.PD == w.KD / 2 && g.PH == w.KH / 2 && g.PW == w.KW / 2,
-             CS_ERR_INVALID, "conv_tc: only stride-1 'same' convolutions");
+  // stride-1 'same' convolutions, or a kernel spanning the full depth without depth padding (Do = 1)
+  const bool same_d = g.Do == x.D && g.PD == w.KD / 2;
+  const bool full_d = g.Do == 1 && w.KD == x.D && g.PD == 0;
+  CS_REQUIRE((same_d || full_d) && g.Ho == x.H && g.Wo == x.W && g.PH == w.KH / 2 && g.PW == w.KW / 2, CS_ERR_INVALID,
+             "conv_tc: unsupported geometry");
   CS_REQUIRE(y.C == w.Cout && x.nblk == w.nblk, CS_ERR_INVALID, "conv_tc: channel mismatch");
 
   ConvTcK k{};
-  k.B = x.B; k.D = x.D; k.H = x.H; k.W = x.W;
+  k.B = x.B; k.D = g.Do; k.H = x.H; k.W = x.W;
   int cap = 128;
   int bw = pick_box(x.W, cap, &k.lbw); cap /= bw;
   int bh = pick_box(x.H, cap, &k.lbh); cap /= bh;
-  int bd = pick_box(x.D, cap, &k.lbd); cap /= bd;
+  int bd = pick_box(g.Do, cap, &k.lbd); cap /= bd;
   int bb = cap; k.lbb = 0; while ((1 << k.lbb) < bb) ++k.lbb;
-  k.ntw = (x.W + bw - 1) / bw; k.nth = (x.H + bh - 1) / bh; k.ntd = (x.D + bd - 1) / bd;
+  k.ntw = (x.W + bw - 1) / bw; k.nth = (x.H + bh - 1) / bh; k.ntd = (g.Do + bd - 1) / bd;
   const int ntb = (x.B + bb - 1) / bb;
   k.KD = w.KD; k.KH = w.KH; k.KW = w.KW; k.PD = g.PD; k.PH = g.PH; k.PW = g.PW;
   k.nblk = w.nblk;
@@ -446,19 +527,22 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     while (tcols < cols) tcols <<= 1;
     int nsets = tcols / k.BN;
     if (nsets > 16) nsets = 16;
-    const int maxsets = niter + (k.npass > 1 ? 1 : 0);
-    if (nsets > maxsets) nsets = maxsets;
     if (nsets < 1) nsets = 1;
-    k.tcols = tcols; k.nsets = nsets;
+    const int corr = (k.npass > 1 && nsets > 1) ? 1 : 0;
+    int nmain = nsets - corr;
+    if (nmain > niter) nmain = niter;
+    const int chunk = (niter + nmain - 1) / nmain;          // K iterations per hi*hi set
+    nmain = (niter + chunk - 1) / chunk;                    // sets actually written
+    k.tcols = tcols; k.nsets = corr + nmain; k.chunk = chunk;
   }
   // thin-N tiles keep the footprint under ~100 KB so two CTAs share an SM (prologue / epilogue overlap)
   const int budget = (k.BN <= 64 && k.tcols <= 256) ? 100 * 1024 : MAX_DYN_SMEM;
-  int stages = (budget - 2048) / stage_bytes;
+  int stages = (budget - 2048 - STG_BYTES) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > niter) stages = niter;
   if (stages < 1) stages = 1;
   k.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 16 * stages + 32;
+  const size_t smem = (size_t)stages * stage_bytes + STG_BYTES + 1024 + 16 * stages + 32;
 
   // tensor maps
   auto enc = encode_fn();
@@ -490,7 +574,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     g_attr_set[dev & 63] = true;
   }
   dim3 grid((unsigned)(k.ntw * k.nth * k.ntd * ntb), (unsigned)(w.Cout_p / k.BN));
-  const long M = (long)x.B * x.D * x.H * x.W;
+  const long M = (long)x.B * g.Do * x.H * x.W;
   ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * w.Cout * w.Cin * w.taps(), 0.0);
   conv_tc_kernel<<<grid, TC_THREADS, smem, L.stream>>>(tmA, tmB, k);
   check_launch("conv_tc");

@@ -80,14 +80,101 @@ static PrepK make_prepk(const Prep& p) {
   return k;
 }
 
+// 4 channels per thread: float4 loads, float4 / 8-byte bf16x4 stores. Requires every channel count,
+// stride and base pointer involved to be a multiple of 4 elements (checked by prep_vec_ok).
+__global__ void __launch_bounds__(256) prep_kernel_v4(PrepK k) {
+  const int C4 = k.Cout >> 2;
+  const long total = (long)k.B * k.D * k.H * k.W * C4;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C4) * 4;
+    const long pix = idx / C4;
+    const int w = (int)(pix % k.W); long t = pix / k.W;
+    const int h = (int)(t % k.H); t /= k.H;
+    const int d = (int)(t % k.D); const int b = (int)(t / k.D);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < k.Cl) {
+      if (c < k.C0) {
+        if (k.pool2) {
+          const float* q = k.s0 + b * k.s0b + d * k.s0d + (2 * h) * k.s0h + (2 * w) * k.s0w + c;
+          const float4 a0 = *reinterpret_cast<const float4*>(q), a1 = *reinterpret_cast<const float4*>(q + k.s0w);
+          const float4 a2 = *reinterpret_cast<const float4*>(q + k.s0h), a3 = *reinterpret_cast<const float4*>(q + k.s0h + k.s0w);
+          v.x = 0.25f * ((a0.x + a1.x) + (a2.x + a3.x)); v.y = 0.25f * ((a0.y + a1.y) + (a2.y + a3.y));
+          v.z = 0.25f * ((a0.z + a1.z) + (a2.z + a3.z)); v.w = 0.25f * ((a0.w + a1.w) + (a2.w + a3.w));
+        } else {
+          v = *reinterpret_cast<const float4*>(k.s0 + b * k.s0b + d * k.s0d + (long)(h >> k.upshift) * k.s0h +
+                                               (long)(w >> k.upshift) * k.s0w + c);
+        }
+        if (k.norm == NORM_AFFINE_C) {
+          const float4 sc = *reinterpret_cast<const float4*>(k.scale + c), sh = *reinterpret_cast<const float4*>(k.shift + c);
+          v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+        } else if (k.norm == NORM_STATS_BC) {
+          const float4 m = *reinterpret_cast<const float4*>(k.mean + b * k.C0 + c);
+          const float4 r = *reinterpret_cast<const float4*>(k.rstd + b * k.C0 + c);
+          v.x = (v.x - m.x) * r.x; v.y = (v.y - m.y) * r.y; v.z = (v.z - m.z) * r.z; v.w = (v.w - m.w) * r.w;
+          if (k.scale) {
+            const float4 sc = *reinterpret_cast<const float4*>(k.scale + c), sh = *reinterpret_cast<const float4*>(k.shift + c);
+            v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+          }
+        }
+        if (k.gb) {
+          const float* g = k.gb + pix * (2L * k.C0) + c;
+          const float4 ga = *reinterpret_cast<const float4*>(g), be = *reinterpret_cast<const float4*>(g + k.C0);
+          v.x = v.x * (1.f + ga.x) + be.x; v.y = v.y * (1.f + ga.y) + be.y;
+          v.z = v.z * (1.f + ga.z) + be.z; v.w = v.w * (1.f + ga.w) + be.w;
+        }
+      } else {
+        v = *reinterpret_cast<const float4*>(k.s1 + b * k.s1b + d * k.s1d + h * k.s1h + w * k.s1w + (c - k.C0));
+      }
+      if (k.add) {
+        const float4 a = *reinterpret_cast<const float4*>(k.add + b * k.ab + d * k.ad + h * k.ah + w * k.aw + c);
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      }
+      v.x = apply_act(v.x, k.act, k.slope); v.y = apply_act(v.y, k.act, k.slope);
+      v.z = apply_act(v.z, k.act, k.slope); v.w = apply_act(v.w, k.act, k.slope);
+    }
+    if (k.o32 && c < k.Cl) *reinterpret_cast<float4*>(k.o32 + b * k.ob + d * k.od + h * k.oh + w * k.ow + c) = v;
+    if (k.opl) {
+      const long o = pix * k.prow + (c >> 5) * 64 + (c & 31);
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+      const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+      uint2 hv, lv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+      lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(k.opl + o) = hv;
+      *reinterpret_cast<uint2*>(k.opl + o + 32) = lv;
+    }
+  }
+}
+
+static bool prep_vec_ok(const PrepK& k) {
+  auto a4 = [](long v) { return (v & 3) == 0; };
+  auto p16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (!(a4(k.C0) && a4(k.C1) && a4(k.Cl) && a4(k.Cout))) return false;
+  if (!(a4(k.s0b) && a4(k.s0d) && a4(k.s0h) && a4(k.s0w) && p16(k.s0))) return false;
+  if (k.s1 && !(a4(k.s1b) && a4(k.s1d) && a4(k.s1h) && a4(k.s1w) && p16(k.s1))) return false;
+  if (k.add && !(a4(k.ab) && a4(k.ad) && a4(k.ah) && a4(k.aw) && p16(k.add))) return false;
+  if (k.o32 && !(a4(k.ob) && a4(k.od) && a4(k.oh) && a4(k.ow) && p16(k.o32))) return false;
+  if (!(p16(k.scale) && p16(k.shift) && p16(k.mean) && p16(k.rstd) && p16(k.gb) && p16(k.opl))) return false;
+  return true;
+}
+
 static void launch_prep(const Launcher& L, PrepK& k) {
   L.count();
   if (L.dry) return;
-  long total = (long)k.B * k.D * k.H * k.W * k.Cout;
-  long blocks = (total + 255) / 256;
-  if (blocks > 148L * 32) blocks = 148L * 32;
-  ProfScope ps(L, PK_PREP, 0.0, (double)total * 4.0 * 2.0);
-  prep_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+  const long total = (long)k.B * k.D * k.H * k.W * k.Cout;
+  // algorithmic bytes: every logical element read once (fp32) and written once (fp32 or hi+lo bf16)
+  ProfScope ps(L, PK_PREP, 0.0, (double)k.B * k.D * k.H * k.W * k.Cl * 4.0 * 2.0);
+  if (prep_vec_ok(k)) {
+    long blocks = (total / 4 + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    prep_kernel_v4<<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+  } else {
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 32) blocks = 148L * 32;
+    prep_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+  }
   check_launch("prep");
 }
 
@@ -154,23 +241,69 @@ __global__ void stats_finalize_kernel(const double* __restrict__ acc, float* __r
   rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// dense [B,S,C] fp32 (C a multiple of 4, C <= 1024): a block takes `rows` consecutive positions, thread = (row group,
+// float4 of channels); fp32 partials over <= rows/groups positions, smem reduce over row groups, fp64 atomics.
+__global__ void __launch_bounds__(256) stats_dense_kernel(const float* __restrict__ x, long S, int C, int rows,
+                                                          double* __restrict__ acc) {
+  __shared__ float4 red1[256], red2[256];
+  const int b = blockIdx.y;
+  const int C4 = C >> 2;
+  const int groups = 256 / C4;                   // C4 is a power of two <= 256
+  const int g = threadIdx.x / C4, c4 = threadIdx.x % C4;
+  const long p0 = (long)blockIdx.x * rows;
+  const long p1 = p0 + rows < S ? p0 + rows : S;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const float4* xp = reinterpret_cast<const float4*>(x + (long)b * S * C) + c4;
+  for (long p = p0 + g; p < p1; p += groups) {
+    const float4 v = __ldg(xp + p * C4);
+    s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+    s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+  }
+  red1[threadIdx.x] = s1; red2[threadIdx.x] = s2;
+  __syncthreads();
+  if (g == 0) {
+    double a[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    for (int i = 0; i < groups; ++i) {
+      const float4 u = red1[i * C4 + c4], w = red2[i * C4 + c4];
+      a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+      q[0] += w.x; q[1] += w.y; q[2] += w.z; q[3] += w.w;
+    }
+    double* o = acc + ((long)b * C + c4 * 4) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { atomicAdd(o + 2 * j, a[j]); atomicAdd(o + 2 * j + 1, q[j]); }
+  }
+}
+
 void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch) {
   L.count(); L.count();
   if (L.dry) return;
   int C = x.C;
-  int CT = 1;
-  while (CT * 2 <= C && CT * 2 <= 256) CT *= 2;
-  // when C is not a multiple of CT the strided loop `c = cl; c < C; c += CT` has a non-uniform trip
-  // count, which would break the __syncthreads above; require exact division.
-  CS_REQUIRE(C % CT == 0, -1, "instance_stats: C must be a power of two multiple");
   long S = (long)x.D * x.H * x.W;
-  int chunk = 2048;
-  int nchunks = (int)((S + chunk - 1) / chunk);
   ProfScope ps(L, PK_STATS, 0.0, (double)x.B * S * C * 4.0);
   CS_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * x.B * C, L.stream));
-  dim3 grid(nchunks, x.B);
-  stats_partial_kernel<<<grid, 256, 0, L.stream>>>(x.p, x.sb, x.sd, x.sh, x.sw, x.D, x.H, x.W, C, CT, chunk, scratch);
-  check_launch("stats_partial");
+  const int C4 = C >> 2;
+  const bool pow2 = C4 > 0 && (C4 & (C4 - 1)) == 0;
+  if ((C & 3) == 0 && pow2 && C4 <= 256 && x.sb == S * C && ((uintptr_t)x.p & 15) == 0) {
+    // the tensor is dense per sample with the channel fastest (2-D activations and the [h,w,16,32] volume alike)
+    const int groups = 256 / C4;
+    long rows = (x.B * S + 2047) / 2048;          // ~2048 blocks in flight
+    if (rows < groups) rows = groups;
+    if (rows > 64L * groups) rows = 64L * groups; // <= 64 fp32 additions per partial
+    dim3 grid((unsigned)((S + rows - 1) / rows), x.B);
+    stats_dense_kernel<<<grid, 256, 0, L.stream>>>(x.p, S, C, (int)rows, scratch);
+    check_launch("stats_dense");
+  } else {
+    int CT = 1;
+    while (CT * 2 <= C && CT * 2 <= 256) CT *= 2;
+    // when C is not a multiple of CT the strided loop `c = cl; c < C; c += CT` has a non-uniform trip
+    // count, which would break the __syncthreads above; require exact division.
+    CS_REQUIRE(C % CT == 0, -1, "instance_stats: C must be a power of two multiple");
+    int chunk = 2048;
+    int nchunks = (int)((S + chunk - 1) / chunk);
+    dim3 grid(nchunks, x.B);
+    stats_partial_kernel<<<grid, 256, 0, L.stream>>>(x.p, x.sb, x.sd, x.sh, x.sw, x.D, x.H, x.W, C, CT, chunk, scratch);
+    check_launch("stats_partial");
+  }
   int n = x.B * C;
   stats_finalize_kernel<<<(n + 127) / 128, 128, 0, L.stream>>>(scratch, mean, rstd, n, 1.0 / (double)S, eps);
   check_launch("stats_finalize");

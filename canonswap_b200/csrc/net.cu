@@ -71,6 +71,22 @@ void conv_layer(Net& n, const Prep* prep, const Act& x, const ConvW& w, const Co
   n.A->reset(m);
 }
 
+// tcgen05 conv on an operand that is already in split-bf16 form (several convs can share one operand)
+static void conv_from_operand(Net& n, const Opd& opd, const ConvW& w, const ConvOpts& o, Act out) {
+  ConvGeom g;
+  g.PD = (out.D == opd.D) ? w.KD / 2 : 0; g.PH = w.KH / 2; g.PW = w.KW / 2;
+  g.Do = out.D; g.Ho = out.H; g.Wo = out.W;
+  Epilogue e;
+  e.act = o.act; e.slope = o.slope; e.mult = o.mult;
+  if (o.residual) {
+    e.residual = o.residual->p;
+    e.rs_b = o.residual->sb; e.rs_d = o.residual->sd; e.rs_h = o.residual->sh; e.rs_w = o.residual->sw;
+  }
+  conv_tc(n.L, opd, w, g, e, out);
+}
+
+static bool use_tc(const Net& n, const ConvW& w, const Act& out) { return n.L.conv_impl != 1 && conv_tc_supported(w, out); }
+
 // ------------------------------------------------------------------------------------------
 // blocks
 // ------------------------------------------------------------------------------------------
@@ -202,12 +218,23 @@ static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, c
   Act pred = new_act(n, B, D, h, w, HG_OUT);
   conv_layer(n, nullptr, cat5, W.hg_final, relu, pred);
   // mask logits 7x7x7 (:88); softmax is fused into the flow/warp kernel
+  // occlusion 7x7 over (c*16+d) channels == conv3d kernel (16,7,7), pad (0,3,3), then sigmoid (:98-102)
   Act logits = new_act(n, B, D, h, w, NUM_KP + 1, 24);
-  conv_layer(n, nullptr, pred, W.dm_mask, ConvOpts(), logits);
   *logits_out = logits;
-  // occlusion 7x7 over (c*16+d) channels == conv3d kernel (16,7,7), pad (0,3,3) (:98-102)
-  ConvGeom g; g.PD = 0; g.PH = 3; g.PW = 3; g.Do = 1; g.Ho = h; g.Wo = w;
-  conv_cout1(n.L, pred, W.dm_occlusion, g, ACT_SIGMOID, occ);
+  Act occ_act = make_act(occ, B, 1, h, w, 1);
+  if (use_tc(n, W.dm_mask, logits) && use_tc(n, W.dm_occlusion, occ_act)) {
+    size_t m = n.A->mark();
+    Opd opd = conv_tc_alloc_operand(*n.A, W.dm_mask, pred);             // both convs read the same operand
+    prep_planes(n.L, prep_of(pred), opd, nullptr);
+    conv_from_operand(n, opd, W.dm_mask, ConvOpts(), logits);
+    ConvOpts sg; sg.act = ACT_SIGMOID;
+    conv_from_operand(n, opd, W.dm_occlusion, sg, occ_act);
+    n.A->reset(m);
+  } else {
+    conv_layer(n, nullptr, pred, W.dm_mask, ConvOpts(), logits);
+    ConvGeom g; g.PD = 0; g.PH = 3; g.PW = 3; g.Do = 1; g.Ho = h; g.Wo = w;
+    conv_cout1(n.L, pred, W.dm_occlusion, g, ACT_SIGMOID, occ);
+  }
 }
 
 // WarpingNetwork.warp, reference warping_network.py:49-62
@@ -245,9 +272,18 @@ static void adaptive_conv(Net& n, const AdaptiveConvW& a, const Act& x, const fl
   size_t m = n.A->mark();
   long P = x.pixels();
   Act o2 = new_act(n, x.B, 1, x.H, x.W, 1024);
-  conv_layer(n, nullptr, x, a.combined, ConvOpts(), o2);
-  ConvGeom g; g.PD = 0; g.PH = 1; g.PW = 1; g.Do = 1; g.Ho = x.H; g.Wo = x.W;
-  conv_cout1(n.L, x, a.mask_conv, g, ACT_SIGMOID, mask);
+  Act mask_act = make_act(mask, x.B, 1, x.H, x.W, 1);
+  if (use_tc(n, a.combined, o2) && use_tc(n, a.mask_conv, mask_act)) {
+    Opd opd = conv_tc_alloc_operand(*n.A, a.combined, o2);
+    prep_planes(n.L, prep_of(x), opd, nullptr);
+    conv_from_operand(n, opd, a.combined, ConvOpts(), o2);
+    ConvOpts sg; sg.act = ACT_SIGMOID;
+    conv_from_operand(n, opd, a.mask_conv, sg, mask_act);
+  } else {
+    conv_layer(n, nullptr, x, a.combined, ConvOpts(), o2);
+    ConvGeom g; g.PD = 0; g.PH = 1; g.PW = 1; g.Do = 1; g.Ho = x.H; g.Wo = x.W;
+    conv_cout1(n.L, x, a.mask_conv, g, ACT_SIGMOID, mask);
+  }
   adaptive_blend(n.L, o2.p, mask, residual, relu, y, P);
   n.A->reset(m);
 }

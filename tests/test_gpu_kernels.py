@@ -57,7 +57,7 @@ def test_conv_simt_matches_torch(eng, case, act):
     assert (y - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
 
 
-TC_CASES = [c for c in CONV_CASES if c[4] >= 16 and c[5] >= 8] + [
+TC_CASES = [c for c in CONV_CASES if c[4] >= 16] + [
     (3, 16, 1, 1, 512, 1024, (3, 3, 3), (1, 1, 1)),   # deepest hourglass level at net 128: 1x1 spatial, batch-tiled box
     (1, 1, 24, 40, 48, 272, (1, 3, 3), (0, 1, 1)),    # non-power-of-two extents, two N tiles of 144
     (2, 1, 64, 64, 512, 512, (1, 3, 3), (0, 1, 1)),   # the most-used shape
@@ -80,6 +80,18 @@ def test_conv_tcgen05_matches_torch(eng, case, act):
         ref = F.leaky_relu(ref, 0.2)
     assert y.shape == ref.shape
     assert (y - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_conv_tcgen05_epilogue_residual_mult_strided(eng):
+    """Engine-level check of the fused epilogue is in test_gpu_stages (warp_out: x occlusion, resblocks:
+    + residual); here: the same conv through both implementations must agree to fp32 round-off."""
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.randn(2, 1, 32, 32, 256, device="cuda", generator=g)
+    w = torch.randn(256, 256, 1, 3, 3, device="cuda", generator=g) / 48.0
+    b = torch.randn(256, device="cuda", generator=g)
+    y_tc = eng.test_conv(x, w, b, (0, 1, 1), act=1, impl=2)
+    y_simt = eng.test_conv(x, w, b, (0, 1, 1), act=1, impl=1)
+    assert (y_tc - y_simt).abs().max().item() <= 5e-5 * max(1.0, y_simt.abs().max().item())
 
 
 def test_conv_sigmoid_cout1(eng):
