@@ -370,7 +370,7 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
                  int Cout, int KD, int KH, int KW, int PD, int PH, int PW, int act, float slope, int impl, void* stream) {
   CS_API_BEGIN(ctx)
   CS_REQUIRE(x && w && y && B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, CS_ERR_INVALID, "cs_test_conv: bad argument");
-  CS_REQUIRE(KD > 0 && KH > 0 && KW > 0 && impl >= 0 && impl <= 2, CS_ERR_INVALID, "cs_test_conv: bad argument");
+  CS_REQUIRE(KD > 0 && KH > 0 && KW > 0 && impl >= 0 && impl <= 3, CS_ERR_INVALID, "cs_test_conv: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CS_CUDA(cudaStreamSynchronize(st));
   const size_t nw = (size_t)Cout * Cin * KD * KH * KW;
@@ -399,7 +399,25 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
     bool tc = same && conv_tc_supported(cw, ya);
     if (impl == 2) CS_REQUIRE(tc, CS_ERR_INVALID, "cs_test_conv: shape not supported by the tcgen05 conv");
     if (impl == 1) tc = false;
-    if (tc) {
+    if (impl == 3) {
+      // the depth-stacked 7x7x7 kernel: output rows padded to a multiple of 4 channels, then compacted
+      pack_conv7(ctx, cw);
+      CS_CUDA(cudaDeviceSynchronize());
+      const int ldo = (Cout + 3) / 4 * 4;
+      float* tmp_out = static_cast<float*>(ctx->dmalloc((size_t)B * D * H * W * ldo * sizeof(float)));
+      Act oa = make_act(tmp_out, B, D, H, W, Cout, ldo);
+      CS_REQUIRE(same && conv7_supported(cw, oa), CS_ERR_INVALID, "cs_test_conv: shape not supported by the 7x7x7 kernel");
+      Arena tmp; tmp.measuring = true;
+      conv_tc_alloc_operand(tmp, cw, xa);
+      Arena real; real.cap = tmp.high + 4096; real.base = static_cast<char*>(ctx->dmalloc(real.cap));
+      Opd opd = conv_tc_alloc_operand(real, cw, xa);
+      float* parts = static_cast<float*>(ctx->dmalloc(conv7_scratch_floats(oa) * sizeof(float)));
+      Prep p; p.src0 = xa;
+      prep_planes(L, p, opd, nullptr);
+      conv7_tc(L, opd, cw, oa, parts);
+      CS_CUDA(cudaMemcpy2DAsync(y, (size_t)Cout * 4, tmp_out, (size_t)ldo * 4, (size_t)Cout * 4, (size_t)B * D * H * W,
+                                cudaMemcpyDeviceToDevice, st));
+    } else if (tc) {
       // private scratch for the operand planes (the ctx arena may not exist before cs_load_weights)
       Arena tmp; tmp.measuring = true;
       conv_tc_alloc_operand(tmp, cw, xa);

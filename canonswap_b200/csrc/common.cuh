@@ -87,6 +87,7 @@ struct ConvW {
   float* bias = nullptr;   // [Cout] or null
   // tcgen05 path: B operand [Cout_p][tap][nblk][hi 32 | lo 32] bf16 (K-major rows), N tile BN
   __nv_bfloat16* wtc = nullptr;
+  __nv_bfloat16* w7 = nullptr;     // 7x7x7 depth-stacked packing (conv7_tc.cu), mask conv only
   int nblk = 0, Cout_p = 0, BN = 0;
   int taps() const { return KD * KH * KW; }
 };
@@ -217,5 +218,9 @@ void grid_sample3d_cl(const Launcher& L, const float* vol, const float* grid, fl
 bool conv_tc_supported(const ConvW& w, const Act& out);
 Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out);   // split-bf16 operand with the geometry of `out`
 void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y);
+// conv7_tc.cu : the 7x7x7 mask conv (depth-stacked, kh-split); scratch holds the 7 partial logit tensors
+bool conv7_supported(const ConvW& w, const Act& out);
+size_t conv7_scratch_floats(const Act& out);
+void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* scratch);
 
 }  // namespace cs

@@ -1,0 +1,316 @@
+// The 7x7x7 mask convolution of DenseMotionNetwork (reference dense_motion.py:18,88: Conv3d(142 -> 22, k=7, p=3)
+// on the [B,142,16,h,w] hourglass output) -- the largest single op of the path (140.5 GFLOP per pass) and the
+// worst shaped one for an implicit GEMM (N = 22).  Dedicated tcgen05 kernel, "depth-stacked, kh-split":
+//
+//   * one CTA = 128 (h,w) pixels x 8 output depths x 22 channels, for ONE filter row kh.
+//     For an input slice z and a filter tap (kh,kw) the A tile (128 pixels x 32 channels of slice z, shifted by
+//     the tap; TMA zero-fills the h/w padding) contributes to every output depth d = z-3 .. z+3 at once:
+//     the B tile stacks the 7 depth taps kd = z-d+3 along N (7 x 32 = 224 columns, clipped to the CTA's 8 depths),
+//     so N is 32..224 instead of 22, every A tile is loaded once for 7 depth taps, and TMEM holds the
+//     8 x 32 accumulator columns of the CTA (+ the same again for the split-bf16 correction products).
+//   * the 7 filter rows kh go to 7 different CTAs that write 7 partial logit tensors, summed (+ bias) by a small
+//     fp32 kernel.  That keeps every TMEM accumulation chain at 7 z x 7 kw x 9 K-steps = 441 MMAs (the tensor
+//     core accumulates with truncation: error grows with the chain length, see conv_tc.cu) and gives the
+//     grid 7x more CTAs (3584 at B = 8) for 148 SMs.
+//
+// Operand format, pipeline roles and MMA issue are those of conv_tc.cu.
+#include "tc_ptx.cuh"
+
+namespace cs {
+
+using namespace tc;
+
+namespace {
+
+constexpr int C7_COUT_P = 32;                    // 22 -> 32 columns per output depth
+constexpr int C7_GROUP = 8;                      // output depths per CTA
+constexpr int C7_BROWS = 7 * C7_COUT_P;          // 224 B rows per stage
+constexpr int C7_STAGE_BYTES = A_TILE_BYTES + C7_BROWS * 128;
+constexpr int C7_STAGES = 4;
+constexpr int C7_SMEM = C7_STAGES * C7_STAGE_BYTES + STG_BYTES + 1024 + 16 * C7_STAGES + 32;
+
+struct Conv7K {
+  int B, H, W;                     // D = 16
+  int lbw, lbh, ntw, nth;
+  int nblk, last_ksteps, Cout;
+  float* parts;                    // [7][B,16,H,W,ldo]
+  long part_stride;                // elements between partial tensors
+  int ldo;                         // channel stride of a partial (24)
+};
+
+__global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB, Conv7K k) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t stg = base + (uint32_t)C7_STAGES * C7_STAGE_BYTES;
+  const uint32_t bars = stg + STG_BYTES;
+  const uint32_t tmem_full = bars + 16u * C7_STAGES;
+  const uint32_t tmem_slot = tmem_full + 8u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int tw = t % k.ntw; t /= k.ntw;
+  const int th = t % k.nth; const int b = t / k.nth;
+  const int w0 = tw << k.lbw, h0 = th << k.lbh;
+  const int g = blockIdx.y;                      // output depths [8g, 8g+8)
+  const int kh = blockIdx.z;
+  const int zlo = max(0, C7_GROUP * g - 3), zhi = min(15, C7_GROUP * g + C7_GROUP - 1 + 3);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < C7_STAGES; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (C7_STAGES + s), 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  // zero the accumulators: every MMA below accumulates (a slice touches a sliding window of depth columns)
+  if (warp >= 2) {
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c = 0; c < 512; c += 16) tc_st16_zero(trow + (uint32_t)c);
+    tc_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int z = zlo; z <= zhi; ++z) {
+        const int jlo = max(0, C7_GROUP * g - z + 3);          // first depth tap slot whose output is in the group
+        for (int kw = 0; kw < 7; ++kw) {
+          const int brow = ((kh * 7 + kw) * 7 + jlo) * C7_COUT_P;
+          for (int blk = 0; blk < k.nblk; ++blk) {
+            const uint32_t fb = bars + 8u * s;
+            mbar_wait(fb + 8u * C7_STAGES, ph ^ 1u);
+            mbar_expect_tx(fb, C7_STAGE_BYTES);
+            const uint32_t sa = base + (uint32_t)s * C7_STAGE_BYTES;
+            tma_load_5d(sa, &tmA, fb, blk * 64, w0 + kw - 3, h0 + kh - 3, z, b);
+            tma_load_2d(sa + A_TILE_BYTES, &tmB, fb, blk * 64, brow);
+            if (++s == C7_STAGES) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (converged warp, elected lane inside the asm block) =====
+    int s = 0; uint32_t ph = 0;
+    for (int z = zlo; z <= zhi; ++z) {
+      const int dlo = max(z - 3, C7_GROUP * g), dhi = min(z + 3, C7_GROUP * g + C7_GROUP - 1);
+      const uint32_t N = (uint32_t)(dhi - dlo + 1) * C7_COUT_P;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t d_main = tmem_base + (uint32_t)((dlo - C7_GROUP * g) * C7_COUT_P);
+      const uint32_t d_corr = d_main + 256u;
+      for (int kw = 0; kw < 7; ++kw) {
+        for (int blk = 0; blk < k.nblk; ++blk) {
+          const uint32_t fb = bars + 8u * s;
+          mbar_wait(fb, ph);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)s * C7_STAGE_BYTES;
+          const int ksteps = (blk == k.nblk - 1) ? k.last_ksteps : 2;
+          mma_stage_k<3>(ksteps, d_main, d_corr, umma_desc(sa), umma_desc(sa + A_TILE_BYTES), idesc, 1u, 1u,
+                         fb + 8u * C7_STAGES);
+          if (++s == C7_STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(tmem_full) : "memory");
+  } else {
+    // ===== epilogue: per output depth, 32 columns (main + corr) -> smem tile -> coalesced partial rows =====
+    const int q = warp & 3;
+    float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + q * 32 * STG_LD;
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    long poff[8];
+    uint32_t vmask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int r = q * 32 + sub + 4 * i;
+      const int ow = w0 + (r & ((1 << k.lbw) - 1)); r >>= k.lbw;
+      const int oh = h0 + r;
+      if (ow < k.W && oh < k.H) vmask |= 1u << i;
+      poff[i] = ((long)oh * k.W + ow) * k.ldo;
+    }
+    float* pbase = k.parts + (long)kh * k.part_stride + (long)b * 16 * k.H * k.W * k.ldo;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int dl = 0; dl < C7_GROUP; ++dl) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[16], u[16];
+        tc_ld16(trow + (uint32_t)(dl * C7_COUT_P + 16 * half), v);
+        tc_ld16(trow + (uint32_t)(256 + dl * C7_COUT_P + 16 * half), u);
+        tc_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(tile + lane * STG_LD + 16 * half);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
+                               __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
+                               __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
+      }
+      __syncwarp();
+      if (c4 < k.ldo) {
+        float* pd = pbase + (long)(C7_GROUP * g + dl) * k.H * k.W * k.ldo + c4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!((vmask >> i) & 1u)) continue;
+          *reinterpret_cast<float4*>(pd + poff[i]) = *reinterpret_cast<const float4*>(tile + (sub + 4 * i) * STG_LD + c4);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// w32 [tap = (kd*7+kh)*7+kw][Cin][Cout] fp32 -> rows ((kh*7+kw)*7 + j)*32 + co, j <-> kd = 6 - j (ascending output
+// depth d = z - 3 + j), columns [blk][hi 32 | lo 32]
+__global__ void __launch_bounds__(256) pack_conv7_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ out, int Cin,
+                                                         int Cout, int nblk) {
+  const long total = 49L * 7 * C7_COUT_P * nblk * 32;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int e = (int)(i & 31); long r = i >> 5;
+    const int blk = (int)(r % nblk); r /= nblk;
+    const int co = (int)(r % C7_COUT_P); r /= C7_COUT_P;
+    const int j = (int)(r % 7); const int khw = (int)(r / 7);       // khw = kh*7 + kw
+    const int kd = 6 - j, ci = blk * 32 + e;
+    const int tap = kd * 49 + khw;
+    const float v = (co < Cout && ci < Cin) ? w32[((long)tap * Cin + ci) * Cout + co] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const long row = ((long)khw * 7 + j) * C7_COUT_P + co;
+    const long o = row * (nblk * 64L) + blk * 64 + e;
+    out[o] = hi;
+    out[o + 32] = lo;
+  }
+}
+
+// logits[i] = sum_p parts[p][i] + bias[channel]
+__global__ void __launch_bounds__(256) sum_parts_kernel(const float4* __restrict__ parts, long stride4, int nparts,
+                                                        const float* __restrict__ bias, int Cout, int ldo4,
+                                                        float4* __restrict__ out, long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 a = __ldg(parts + i);
+    for (int p = 1; p < nparts; ++p) {
+      const float4 v = __ldg(parts + p * stride4 + i);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const int c = (int)(i % ldo4) * 4;
+    if (bias) {
+      if (c < Cout) a.x += bias[c];
+      if (c + 1 < Cout) a.y += bias[c + 1];
+      if (c + 2 < Cout) a.z += bias[c + 2];
+      if (c + 3 < Cout) a.w += bias[c + 3];
+    }
+    out[i] = a;
+  }
+}
+
+bool g_attr7[64] = {};
+
+}  // namespace
+
+bool conv7_supported(const ConvW& w, const Act& out) {
+  return w.w7 != nullptr && out.D == 16 && (long)out.H * out.W >= 128 && out.sw % 4 == 0 && out.sw >= w.Cout &&
+         out.sh == (long)out.W * out.sw && out.sd == (long)out.H * out.sh && out.sb == 16 * out.sd;
+}
+
+size_t conv7_scratch_floats(const Act& out) { return (size_t)7 * out.B * 16 * out.H * out.W * out.sw; }
+
+void pack_conv7(cs_ctx* ctx, ConvW& w) {
+  if (!(w.KD == 7 && w.KH == 7 && w.KW == 7 && w.Cout <= C7_COUT_P && w.Cin >= 16 && w.w32)) return;
+  const int nblk = (w.Cin + 31) / 32;
+  const size_t n = (size_t)49 * 7 * C7_COUT_P * nblk * 64;
+  if (!w.w7) w.w7 = static_cast<__nv_bfloat16*>(ctx->dmalloc(n * sizeof(__nv_bfloat16)));
+  pack_conv7_kernel<<<148 * 8, 256>>>(w.w32, w.w7, w.Cin, w.Cout, nblk);
+  check_launch("pack_conv7");
+}
+
+// x: split-bf16 operand [B,16,H,W,nblk*64]; out: logits [B,16,H,W,ldo] (dense, ldo = out.sw >= Cout);
+// scratch: conv7_scratch_floats(out) floats
+void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* scratch) {
+  L.count(); L.count();
+  if (L.dry) return;
+  CS_REQUIRE(conv7_supported(w, out) && x.D == 16 && x.nblk == (w.Cin + 31) / 32 && x.B == out.B && x.H == out.H &&
+                 x.W == out.W, CS_ERR_INVALID, "conv7_tc: unsupported geometry");
+  Conv7K k{};
+  k.B = x.B; k.H = x.H; k.W = x.W;
+  int cap = 128;
+  const int bw = pick_box(x.W, cap, &k.lbw); cap /= bw;
+  const int bh = cap; k.lbh = 0; while ((1 << k.lbh) < bh) ++k.lbh;
+  k.ntw = (x.W + bw - 1) / bw; k.nth = (x.H + bh - 1) / bh;
+  k.nblk = x.nblk;
+  k.last_ksteps = ((w.Cin - (x.nblk - 1) * 32) + 15) / 16;
+  k.Cout = w.Cout;
+  k.ldo = (int)out.sw;
+  k.parts = scratch;
+  k.part_stride = (long)x.B * 16 * x.H * x.W * k.ldo;
+
+  auto enc = encode_fn();
+  CUtensorMap tmA, tmB;
+  const int rowA = x.nblk * 64;
+  {
+    const cuuint64_t pix = (cuuint64_t)rowA * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)rowA, (cuuint64_t)x.W, (cuuint64_t)x.H, 16, (cuuint64_t)x.B};
+    cuuint64_t strides[4] = {pix, pix * x.W, pix * x.W * x.H, pix * x.W * x.H * 16};
+    cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CS_REQUIRE(r == CUDA_SUCCESS, CS_ERR_CUDA, "conv7_tc: cuTensorMapEncodeTiled(A) failed");
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)rowA, (cuuint64_t)(49 * C7_BROWS)};
+    cuuint64_t strides[1] = {(cuuint64_t)rowA * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)C7_BROWS};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w7, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CS_REQUIRE(r == CUDA_SUCCESS, CS_ERR_CUDA, "conv7_tc: cuTensorMapEncodeTiled(B) failed");
+  }
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (!g_attr7[dev & 63]) {
+    CS_CUDA(cudaFuncSetAttribute(conv7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C7_SMEM));
+    g_attr7[dev & 63] = true;
+  }
+  const long M = (long)x.B * 16 * x.H * x.W;
+  {
+    ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * w.Cout * w.Cin * 343.0, 0.0);
+    dim3 grid((unsigned)(k.ntw * k.nth * x.B), 16 / C7_GROUP, 7);
+    conv7_tc_kernel<<<grid, TC_THREADS, C7_SMEM, L.stream>>>(tmA, tmB, k);
+    check_launch("conv7_tc");
+  }
+  {
+    const long n4 = M * k.ldo / 4;
+    ProfScope ps(L, PK_OTHER, 0.0, (double)n4 * 16.0 * 8.0);
+    long blocks = (n4 + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+    sum_parts_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(scratch), k.part_stride / 4, 7, w.bias,
+                                                           w.Cout, k.ldo / 4, reinterpret_cast<float4*>(out.p), n4);
+    check_launch("sum_parts");
+  }
+}
+
+}  // namespace cs

@@ -110,7 +110,8 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n);
 void set_identity(cs_ctx* ctx, const float* id_dev, cudaStream_t stream);
 ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt /*[Cout][Cin][taps]*/, const std::vector<float>* bias,
                      int Cout, int Cin, int KD, int KH, int KW);
-void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream);   // derive the split-bf16 B operand from w32 (conv_tc.cu)
+void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream);
+void pack_conv7(cs_ctx* ctx, ConvW& w);                      // conv7_tc.cu   // derive the split-bf16 B operand from w32 (conv_tc.cu)
 
 // net.cu : stages on the internal (channels-last) layout
 void run_F(Net& n, const float* img_cl, int B, float* vol_out);

@@ -226,7 +226,12 @@ static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, c
     size_t m = n.A->mark();
     Opd opd = conv_tc_alloc_operand(*n.A, W.dm_mask, pred);             // both convs read the same operand
     prep_planes(n.L, prep_of(pred), opd, nullptr);
-    conv_from_operand(n, opd, W.dm_mask, ConvOpts(), logits);
+    if (conv7_supported(W.dm_mask, logits)) {
+      float* parts = n.A->f32(conv7_scratch_floats(logits));
+      conv7_tc(n.L, opd, W.dm_mask, logits, parts);
+    } else {
+      conv_from_operand(n, opd, W.dm_mask, ConvOpts(), logits);
+    }
     ConvOpts sg; sg.act = ACT_SIGMOID;
     conv_from_operand(n, opd, W.dm_occlusion, sg, occ_act);
     n.A->reset(m);

@@ -1,0 +1,157 @@
+// PTX building blocks shared by the tcgen05 convolution kernels (sm_100a): mbarrier, TMA tiled loads,
+// tcgen05 fences / commit / ld / st, the K-major SWIZZLE_128B UMMA descriptor and the per-stage MMA issue block.
+#pragma once
+#include "ctx.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace cs {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 1023u) == 1023u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();       // 4 s
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 at bits 46-47,
+// layout type 2 at bits 61-63, stride byte offset = 1024 B between 8-row groups). The low word is the
+// 16-byte-granular start address, so a K advance of 32 B (one 16-element bf16 K step) is +2 and the
+// lo half of a [hi x32 | lo x32] row (+64 B) is +4.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  constexpr uint64_t HI = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;
+  return HI | (uint64_t)((saddr & 0x3FFFFu) >> 4);
+}
+
+// All the MMAs of one pipeline stage (one 32-channel K block) + the commit that frees the stage, issued
+// by one elected lane of a converged warp in a single asm block (the issue thread is the critical path
+// of the kernel: no divergence bookkeeping, no per-MMA descriptor rebuild).
+//   hi*hi -> [d_main] (first MMA accumulates iff acc_main), lo*hi and hi*lo -> [d_corr] (iff acc_corr)
+#define CS_MMA_HEAD                                   \
+  "{\n\t"                                             \
+  ".reg .pred pe, pm, pc, pt;\n\t"                    \
+  ".reg .b64 a2, a4, a6, b2, b4, b6;\n\t"             \
+  "elect.sync _|pe, 0xffffffff;\n\t"                  \
+  "setp.ne.b32 pm, %5, 0;\n\t"                        \
+  "setp.ne.b32 pc, %6, 0;\n\t"                        \
+  "setp.eq.b32 pt, %4, %4;\n\t"                       \
+  "add.s64 a2, %2, 2;\n\t"                            \
+  "add.s64 a4, %2, 4;\n\t"                            \
+  "add.s64 a6, %2, 6;\n\t"                            \
+  "add.s64 b2, %3, 2;\n\t"                            \
+  "add.s64 b4, %3, 4;\n\t"                            \
+  "add.s64 b6, %3, 6;\n\t"
+#define CS_MMA(D, A, B, P) "@pe tcgen05.mma.cta_group::1.kind::f16 [" D "], " A ", " B ", %4, " P ";\n\t"
+#define CS_MMA_TAIL "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
+#define CS_MMA_OPS                                                                                                     \
+  ::"r"(d_main), "r"(d_corr), "l"(ad), "l"(bd), "r"(idesc), "r"(acc_main), "r"(acc_corr), "r"(bar) : "memory"
+
+template <int NPASS, int KSTEPS>
+__device__ __forceinline__ void mma_stage(uint32_t d_main, uint32_t d_corr, uint64_t ad, uint64_t bd, uint32_t idesc,
+                                          uint32_t acc_main, uint32_t acc_corr, uint32_t bar) {
+  if constexpr (NPASS == 3 && KSTEPS == 2) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%0", "a2", "b2", "pt")      // hi*hi
+                 CS_MMA("%1", "a4", "%3", "pc") CS_MMA("%1", "a6", "b2", "pt")                  // lo*hi
+                 CS_MMA("%1", "%2", "b4", "pt") CS_MMA("%1", "a2", "b6", "pt") CS_MMA_TAIL CS_MMA_OPS);
+  } else if constexpr (NPASS == 3 && KSTEPS == 1) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%1", "a4", "%3", "pc") CS_MMA("%1", "%2", "b4", "pt")
+                     CS_MMA_TAIL CS_MMA_OPS);
+  } else if constexpr (NPASS == 2 && KSTEPS == 2) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%0", "a2", "b2", "pt") CS_MMA("%1", "a4", "%3", "pc")
+                     CS_MMA("%1", "a6", "b2", "pt") CS_MMA_TAIL CS_MMA_OPS);
+  } else if constexpr (NPASS == 2 && KSTEPS == 1) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%1", "a4", "%3", "pc") CS_MMA_TAIL CS_MMA_OPS);
+  } else if constexpr (NPASS == 1 && KSTEPS == 2) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%0", "a2", "b2", "pt") CS_MMA_TAIL CS_MMA_OPS);
+  } else {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA_TAIL CS_MMA_OPS);
+  }
+}
+
+template <int NPASS>
+__device__ __forceinline__ void mma_stage_k(int ksteps, uint32_t d_main, uint32_t d_corr, uint64_t ad, uint64_t bd,
+                                            uint32_t idesc, uint32_t acc_main, uint32_t acc_corr, uint32_t bar) {
+  if (ksteps == 2) mma_stage<NPASS, 2>(d_main, d_corr, ad, bd, idesc, acc_main, acc_corr, bar);
+  else mma_stage<NPASS, 1>(d_main, d_corr, ad, bd, idesc, acc_main, acc_corr, bar);
+}
+
+
+__device__ __forceinline__ void tc_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int TC_THREADS = 192;
+constexpr int A_TILE_BYTES = 128 * 128;
+constexpr int STG_LD = 36;                                  // floats per staged row (32 + pad, 16-B aligned)
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;              // one 32x32 fp32 staging tile per epilogue warp
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn();             // conv_tc.cu
+int pick_box(int dim, int cap, int* log2out);               // conv_tc.cu
+
+}  // namespace tc
+}  // namespace cs

@@ -275,6 +275,7 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
     fold_bn_post(fin, read_bn(t, p + ".hourglass.decoder.norm", HG_OUT));
     W.hg_final = pack(ctx, fin);
     W.dm_mask = pack(ctx, read_conv(t, p + ".mask", NUM_KP + 1, HG_OUT, 7, 7, 7));
+    pack_conv7(ctx, W.dm_mask);
     HostConv cmp = read_conv(t, p + ".compress", 4, 32, 1, 1, 1);
     fold_bn_post(cmp, read_bn(t, p + ".norm", 4));
     W.dm_compress = pack(ctx, cmp);

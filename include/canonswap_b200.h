@@ -131,7 +131,7 @@ CS_API int cs_profile_read(cs_ctx* ctx, double* out);
 /* ---- kernel-level entry points (unit tests / profiling) ------------------------------------- */
 /* Generic "same"-style convolution on channels-last fp32 through the library's conv kernels.
  * x [B,D,H,W,Cin] -> y [B,Do,Ho,Wo,Cout]; w in PyTorch layout [Cout,Cin,KD,KH,KW] (device), bias
- * [Cout] or NULL. impl: 0 auto, 1 SIMT fp32, 2 tcgen05 split-bf16. act: 0 none 1 relu 2 lrelu 3 sigmoid */
+ * [Cout] or NULL. impl: 0 auto, 1 SIMT fp32, 2 tcgen05 split-bf16, 3 tcgen05 depth-stacked 7x7x7 kernel. act: 0 none 1 relu 2 lrelu 3 sigmoid */
 CS_API int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
                  int B, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW,
                  int PD, int PH, int PW, int act, float slope, int impl, void* stream);

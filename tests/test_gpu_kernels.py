@@ -82,6 +82,20 @@ def test_conv_tcgen05_matches_torch(eng, case, act):
     assert (y - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("case", [(1, 16, 16, 8, 142, 22), (2, 16, 32, 32, 142, 22), (1, 16, 24, 40, 70, 24)])
+def test_conv7_depth_stacked_matches_torch(eng, case):
+    """The dedicated 7x7x7 mask-conv kernel (depth-stacked N, kh-split partial sums) against fp64 torch."""
+    B, D, H, W, Cin, Cout = case
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(B, D, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 7, 7, 7, device="cuda", generator=g) / (Cin * 343) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    y = eng.test_conv(x, w, b, (3, 3, 3), impl=3)
+    ref = _ref_conv(x, w, b, (3, 3, 3))
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
+
+
 def test_conv_tcgen05_epilogue_residual_mult_strided(eng):
     """Engine-level check of the fused epilogue is in test_gpu_stages (warp_out: x occlusion, resblocks:
     + residual); here: the same conv through both implementations must agree to fp32 round-off."""
