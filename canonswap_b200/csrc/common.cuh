@@ -89,6 +89,7 @@ struct ConvW {
   __nv_bfloat16* wtc = nullptr;
   __nv_bfloat16* w7 = nullptr;     // 7x7x7 depth-stacked packing (conv7_tc.cu), mask conv only
   int nblk = 0, Cout_p = 0, BN = 0;
+  int zrows = 0;                   // > 0: depth-dependent weights (rows d*zrows .. of wtc belong to depth slice d)
   int taps() const { return KD * KH * KW; }
 };
 
@@ -99,6 +100,14 @@ struct Epilogue {
   const float* residual = nullptr;   // same geometry/strides as the output
   long rs_b = 0, rs_d = 0, rs_h = 0, rs_w = 0;
   const float* mult = nullptr;       // [B, Do*Ho*Wo] per-pixel multiplier
+  // tcgen05 path only: additionally emit act2(v * emit_scale[c] + emit_shift[c]) as the split-bf16 operand
+  // [pixels, emit_nblk, 64] of the next conv (scale/shift null = identity); the fp32 output pointer may then be null
+  __nv_bfloat16* emit = nullptr;
+  int emit_nblk = 0;
+  const float* emit_scale = nullptr;
+  const float* emit_shift = nullptr;
+  int emit_act = ACT_NONE;
+  float emit_slope = 0.f;
 };
 
 // conv geometry
@@ -196,7 +205,8 @@ void prep_planes(const Launcher& L, const Prep& p, Opd out, const Act* out32);  
 void avg2(const Launcher& L, const float* a, const float* b, float* y, long n);   // y = (a + b) / 2
 void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch);
 void adaptive_blend(const Launcher& L, const float* o2 /*[P,1024]*/, const float* mask /*[P]*/,
-                    const float* residual /*[P,512] or null*/, int relu, float* y /*[P,512]*/, long P);
+                    const float* residual /*[P,512] or null*/, int relu, float* y /*[P,512] or null*/,
+                    __nv_bfloat16* opl /*next conv operand [P,16,64] or null*/, long P);
 void nchw_to_cl(const Launcher& L, const float* src, float* dst, int B, int C, long S, int vol_perm);
 void cl_to_nchw(const Launcher& L, const float* src, float* dst, int B, int C, long S, int vol_perm, int Cstride);
 void ingest_u8(const Launcher& L, const uint8_t* src, float* dst, long n);
@@ -222,5 +232,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
 bool conv7_supported(const ConvW& w, const Act& out);
 size_t conv7_scratch_floats(const Act& out);
 void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* scratch);
+// occlusion map = sigmoid(bias + sum_{z,kh,kw} Y[b,z,h+kh-3,w+kw-3,kh*7+kw]) from the per-tap projections Y [B,16,H,W,64]
+void occlusion_gather(const Launcher& L, const Act& Y, const float* bias, float* occ);
 
 }  // namespace cs

@@ -38,11 +38,14 @@ struct ConvTcK {
   int rowA;                        // bf16 elements per pixel of the operand = nblk * 64
   int BN, Cout, stages, npass;
   int tcols, nsets, chunk;         // TMEM columns, accumulator sets of BN columns, K iterations per hi*hi set
+  int zrows;                       // > 0: depth-dependent weights, B rows of depth slice d start at d * zrows
   const float* bias; int act; float slope;
   const float* res; long rb, rd, rh, rw;
   const float* mult;
-  float* y; long yb, yd, yh, yw;
+  float* y; long yb, yd, yh, yw;               // may be null when only the operand is emitted
   int vec4;
+  // optional: also write act(v * escale[n] + eshift[n]) as the split-bf16 operand of the next conv (dense, output geometry)
+  __nv_bfloat16* emit; int erow; const float* escale; const float* eshift; int eact; float eslope;
 };
 
 
@@ -73,6 +76,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const int td = t % k.ntd; const int tb = t / k.ntd;
   const int w0 = tw << k.lbw, h0 = th << k.lbh, d0 = td << k.lbd, b0 = tb << k.lbb;
   const int n0 = blockIdx.y * k.BN;
+  const int nrow0 = n0 + d0 * k.zrows;            // first B row of this tile
   const int taps = k.KD * k.KH * k.KW;
 
   if (warp == 0 && lane == 0) {
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
           tma_load_5d(sa, &tmA, fb, blk * 64, cw, ch, cd, b0);
-          tma_load_2d(sa + A_TILE_BYTES, &tmB, fb, kcol + blk * 64, n0);
+          tma_load_2d(sa + A_TILE_BYTES, &tmB, fb, kcol + blk * 64, nrow0);
           if (++s == k.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int q = warp & 3;
     float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + q * 32 * STG_LD;
     const int sub = lane >> 3, c4 = (lane & 7) * 4;
-    long yoff[8], roff[8];
+    long yoff[8], roff[8], epix[8];
     float mu[8];
     uint32_t vmask = 0;
 #pragma unroll
@@ -169,7 +173,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       if (valid) vmask |= 1u << i;
       yoff[i] = ob * k.yb + od * k.yd + oh * k.yh + ow * k.yw;
       roff[i] = ob * k.rb + od * k.rd + oh * k.rh + ow * k.rw;
+      epix[i] = (((long)ob * k.D + od) * k.H + oh) * k.W + ow;
       mu[i] = (k.mult && valid) ? k.mult[(((long)ob * k.D + od) * k.H + oh) * k.W + ow] : 1.f;
+    }
+    if (k.res) {                                            // pull the residual tile towards L2 while the MMAs run
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!((vmask >> i) & 1u)) continue;
+        for (int c = c4 * 8; c < k.BN && n0 + c < k.Cout; c += 256)       // one 128-B line per lane, 8 lanes per row
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(k.res + roff[i] + n0 + c));
+      }
     }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
@@ -213,6 +226,19 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           for (int j = 0; j < 4; ++j) if (n + j < k.Cout) bz[j] = __ldg(k.bias + n + j);
         }
         const bool full4 = k.vec4 && (n + 3 < k.Cout);
+        float4 rr4[8];
+        if (full4 && k.res) {                               // all residual loads in flight before the first use
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            rr4[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float4*>(k.res + roff[i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float es[4] = {1.f, 1.f, 1.f, 1.f}, eb[4] = {0.f, 0.f, 0.f, 0.f};
+        if (k.emit && k.escale) {                           // emission needs Cout % 32 == 0: n .. n+3 are valid
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(k.escale + n));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(k.eshift + n));
+          es[0] = s4.x; es[1] = s4.y; es[2] = s4.z; es[3] = s4.w;
+          eb[0] = b4.x; eb[1] = b4.y; eb[2] = b4.z; eb[3] = b4.w;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (!((vmask >> i) & 1u)) continue;
@@ -220,22 +246,39 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           float o[4] = {a.x + bz[0], a.y + bz[1], a.z + bz[2], a.w + bz[3]};
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], k.act, k.slope);
-          float* yp = k.y + yoff[i] + n;
-          if (full4) {
-            if (k.res) {
-              const float4 rr = *reinterpret_cast<const float4*>(k.res + roff[i] + n);
-              o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-            }
-            *reinterpret_cast<float4*>(yp) = make_float4(o[0] * mu[i], o[1] * mu[i], o[2] * mu[i], o[3] * mu[i]);
-          } else {
+          if (k.res) {
+            if (full4) {
+              o[0] += rr4[i].x; o[1] += rr4[i].y; o[2] += rr4[i].z; o[3] += rr4[i].w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (n + j < k.Cout) {
-                float x = o[j];
-                if (k.res) x += k.res[roff[i] + n + j];
-                yp[j] = x * mu[i];
-              }
+              for (int j = 0; j < 4; ++j) if (n + j < k.Cout) o[j] += k.res[roff[i] + n + j];
             }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] *= mu[i];
+          if (k.y) {
+            float* yp = k.y + yoff[i] + n;
+            if (full4) {
+              *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) if (n + j < k.Cout) yp[j] = o[j];
+            }
+          }
+          if (k.emit) {                                     // the next conv's split-bf16 operand, transform fused
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope);
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(e[0], e[1]), h23 = __floats2bfloat162_rn(e[2], e[3]);
+            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(e[0] - f01.x, e[1] - f01.y);
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(e[2] - f23.x, e[3] - f23.y);
+            uint2 hv, lv;
+            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+            __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (n >> 5) * 64 + (n & 31);
+            *reinterpret_cast<uint2*>(ep) = hv;
+            *reinterpret_cast<uint2*>(ep + 32) = lv;
           }
         }
       }
@@ -374,12 +417,17 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   k.nblk = w.nblk;
   k.last_ksteps = ((w.Cin - (w.nblk - 1) * 32) + 15) / 16;
   k.rowA = w.nblk * 64;
-  k.BN = w.BN; k.Cout = w.Cout;
+  k.BN = w.BN; k.Cout = w.Cout; k.zrows = w.zrows;
   k.npass = L.npass >= 1 && L.npass <= 3 ? L.npass : 3;
   k.bias = w.bias; k.act = e.act; k.slope = e.slope;
   k.res = e.residual; k.rb = e.rs_b; k.rd = e.rs_d; k.rh = e.rs_h; k.rw = e.rs_w;
   k.mult = e.mult;
   k.y = y.p; k.yb = y.sb; k.yd = y.sd; k.yh = y.sh; k.yw = y.sw;
+  if (e.emit) {
+    CS_REQUIRE(w.Cout % 32 == 0 && e.emit_nblk * 32 == w.Cout, CS_ERR_INVALID, "conv_tc: operand emission needs Cout % 32 == 0");
+    k.emit = e.emit; k.erow = e.emit_nblk * 64; k.escale = e.emit_scale; k.eshift = e.emit_shift; k.eact = e.emit_act;
+    k.eslope = e.emit_slope;
+  }
   auto al4 = [](long v) { return (v & 3) == 0; };
   k.vec4 = al4(y.sb) && al4(y.sd) && al4(y.sh) && al4(y.sw) && ((uintptr_t)y.p % 16 == 0) &&
            (!e.residual || (al4(e.rs_b) && al4(e.rs_d) && al4(e.rs_h) && al4(e.rs_w) && ((uintptr_t)e.residual % 16 == 0)));
@@ -444,7 +492,8 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     CS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
     g_attr_set[dev & 63] = true;
   }
-  dim3 grid((unsigned)(k.ntw * k.nth * k.ntd * ntb), (unsigned)(w.Cout_p / k.BN));
+  if (w.zrows > 0) CS_REQUIRE(bd == 1 && w.zrows % k.BN == 0, CS_ERR_INVALID, "conv_tc: depth-dependent weights need one depth per tile");
+  dim3 grid((unsigned)(k.ntw * k.nth * k.ntd * ntb), (unsigned)((w.zrows > 0 ? w.zrows : w.Cout_p) / k.BN));
   const long M = (long)x.B * g.Do * x.H * x.W;
   ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * w.Cout * w.Cin * w.taps(), 0.0);
   conv_tc_kernel<<<grid, TC_THREADS, smem, L.stream>>>(tmA, tmB, k);

@@ -131,6 +131,11 @@ __global__ void __launch_bounds__(256) prep_kernel_v4(PrepK k) {
       }
       v.x = apply_act(v.x, k.act, k.slope); v.y = apply_act(v.y, k.act, k.slope);
       v.z = apply_act(v.z, k.act, k.slope); v.w = apply_act(v.w, k.act, k.slope);
+      if (c + 3 >= k.Cl) {                       // ragged tail (plain conversions only): the over-read lanes are pad
+        if (c + 1 >= k.Cl) v.y = 0.f;
+        if (c + 2 >= k.Cl) v.z = 0.f;
+        v.w = 0.f;
+      }
     }
     if (k.o32 && c < k.Cl) *reinterpret_cast<float4*>(k.o32 + b * k.ob + d * k.od + h * k.oh + w * k.ow + c) = v;
     if (k.opl) {
@@ -151,7 +156,13 @@ __global__ void __launch_bounds__(256) prep_kernel_v4(PrepK k) {
 static bool prep_vec_ok(const PrepK& k) {
   auto a4 = [](long v) { return (v & 3) == 0; };
   auto p16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-  if (!(a4(k.C0) && a4(k.C1) && a4(k.Cl) && a4(k.Cout))) return false;
+  if (!a4(k.Cout)) return false;
+  if (!(a4(k.C0) && a4(k.C1))) {
+    // ragged channel count: only a plain single-source conversion into operand planes, reading the (finite or not)
+    // pad floats of a row whose stride covers the rounded-up channel count
+    const bool plain = !k.s1 && k.norm == NORM_NONE && !k.gb && !k.add && !k.pool2 && !k.o32;
+    if (!(plain && k.s0w >= ((k.C0 + 3) & ~3))) return false;
+  }
   if (!(a4(k.s0b) && a4(k.s0d) && a4(k.s0h) && a4(k.s0w) && p16(k.s0))) return false;
   if (k.s1 && !(a4(k.s1b) && a4(k.s1d) && a4(k.s1h) && a4(k.s1w) && p16(k.s1))) return false;
   if (k.add && !(a4(k.ab) && a4(k.ad) && a4(k.ah) && a4(k.aw) && p16(k.add))) return false;
@@ -313,8 +324,8 @@ void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, f
 // adaptive blend: o2 = [out_std(512) | out_mod(512)] per pixel
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adaptive_blend_kernel(const float4* __restrict__ o2, const float* __restrict__ mask,
-                                                            const float4* __restrict__ residual, int relu,
-                                                            float4* __restrict__ y, long P) {
+                                                            const float4* residual, int relu, float4* y,
+                                                            __nv_bfloat16* __restrict__ opl, long P) {
   long total = P * 128;     // 512 channels / 4
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long pix = i >> 7; int q = (int)(i & 127);
@@ -325,11 +336,25 @@ __global__ void __launch_bounds__(256) adaptive_blend_kernel(const float4* __res
     v.z = m * mo.z + (1.f - m) * s.z; v.w = m * mo.w + (1.f - m) * s.w;
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     if (residual) { float4 r = residual[i]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
-    y[i] = v;
+    if (y) y[i] = v;
+    if (opl) {                // split-bf16 operand of the next conv: [pix][16 blocks][hi 32 | lo 32]
+      const int c = q * 4;
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+      const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+      uint2 hv, lv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+      lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+      __nv_bfloat16* o = opl + pix * 1024 + (c >> 5) * 64 + (c & 31);
+      *reinterpret_cast<uint2*>(o) = hv;
+      *reinterpret_cast<uint2*>(o + 32) = lv;
+    }
   }
 }
 
-void adaptive_blend(const Launcher& L, const float* o2, const float* mask, const float* residual, int relu, float* y, long P) {
+void adaptive_blend(const Launcher& L, const float* o2, const float* mask, const float* residual, int relu, float* y,
+                    __nv_bfloat16* opl, long P) {
   L.count();
   if (L.dry) return;
   long blocks = (P * 128 + 255) / 256;
@@ -337,7 +362,7 @@ void adaptive_blend(const Launcher& L, const float* o2, const float* mask, const
   ProfScope ps(L, PK_OTHER, 0.0, (double)P * (1024 + 512 + 512) * 4.0);
   adaptive_blend_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(o2), mask,
                                                                reinterpret_cast<const float4*>(residual), relu,
-                                                               reinterpret_cast<float4*>(y), P);
+                                                               reinterpret_cast<float4*>(y), opl, P);
   check_launch("adaptive_blend");
 }
 

@@ -187,6 +187,63 @@ __global__ void __launch_bounds__(256) grid_sample3d_cl_kernel(const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// occlusion map from per-tap projections (reference dense_motion.py:98-102).
+// The 7x7 conv over 142*16 channels is split into (1) a 1x1x1 tcgen05 GEMM with depth-dependent weights,
+// Y[b,z,h,w,kh*7+kw] = sum_c pred[b,z,h,w,c] * Wocc[c*16+z, kh, kw], and (2) this gather:
+// occ[b,h,w] = sigmoid(bias + sum_{z,kh,kw} Y[b,z,h+kh-3,w+kw-3,kh*7+kw]).  One warp = 32 consecutive w of one
+// (b,h); per (z,kh) lane l loads the 7 kw-columns of row w0+l-3 (28 contiguous bytes), lanes 0..5 also rows
+// w0+29..w0+34, and the diagonal sum is formed with shuffles: every Y element is read once.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) occlusion_gather_kernel(const float* __restrict__ Y, const float* __restrict__ bias,
+                                                               float* __restrict__ occ, int B, int D, int H, int W, int ldy) {
+  const int lane = threadIdx.x & 31;
+  const int wtiles = (W + 31) / 32;
+  const long warp_id = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (warp_id >= (long)B * H * wtiles) return;
+  const int wt = (int)(warp_id % wtiles); const long r = warp_id / wtiles;
+  const int h = (int)(r % H); const int b = (int)(r / H);
+  const int w0 = wt * 32;
+  const int xa = w0 + lane - 3;                 // row held in v[]
+  const int xb = w0 + 32 + lane - 3;            // row held in e[] (lanes 0..5)
+  const bool va = xa >= 0 && xa < W, vb = lane < 6 && xb < W;
+  float acc = 0.f;
+  for (int z = 0; z < D; ++z) {
+    for (int kh = 0; kh < 7; ++kh) {
+      const int y = h + kh - 3;
+      if (y < 0 || y >= H) continue;            // warp-uniform
+      const float* row = Y + ((((long)b * D + z) * H + y) * W) * ldy + kh * 7;
+      float v[7], e[7];
+#pragma unroll
+      for (int kw = 0; kw < 7; ++kw) {
+        v[kw] = va ? __ldg(row + (long)xa * ldy + kw) : 0.f;
+        e[kw] = vb ? __ldg(row + (long)xb * ldy + kw) : 0.f;
+      }
+#pragma unroll
+      for (int kw = 0; kw < 7; ++kw) {
+        // output w0+l needs row index (l + kw) of the 38-row window
+        const int src = (lane + kw) & 31;
+        const float fv = __shfl_sync(0xffffffffu, v[kw], src);
+        const float fe = __shfl_sync(0xffffffffu, e[kw], src);
+        acc += (lane + kw < 32) ? fv : fe;
+      }
+    }
+  }
+  const int w = w0 + lane;
+  if (w < W) occ[((long)b * H + h) * W + w] = 1.f / (1.f + expf(-(acc + (bias ? bias[0] : 0.f))));
+}
+
+void occlusion_gather(const Launcher& L, const Act& Y, const float* bias, float* occ) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(Y.C >= 49 && Y.sh == (long)Y.W * Y.sw && Y.sd == (long)Y.H * Y.sh && Y.sb == (long)Y.D * Y.sd, -1,
+             "occlusion_gather: Y must be dense [B,D,H,W,>=49]");
+  const long warps = (long)Y.B * Y.H * ((Y.W + 31) / 32);
+  ProfScope ps(L, PK_SAMPLE, 0.0, (double)Y.pixels() * 49 * 4.0);
+  occlusion_gather_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, L.stream>>>(Y.p, bias, occ, Y.B, Y.D, Y.H, Y.W, (int)Y.sw);
+  check_launch("occlusion_gather");
+}
+
 void grid_sample3d_cl(const Launcher& L, const float* vol, const float* grid, float* out, int B, int D, int H, int W) {
   L.count();
   if (L.dry) return;

@@ -25,6 +25,11 @@ struct ConvOpts {
   const Act* residual = nullptr;
   const float* mult = nullptr;
   int xshift = 0;              // input is x nearest-upsampled by 2^xshift (no prep only)
+  // tcgen05 path: also emit the next conv's operand from the epilogue (see Epilogue in common.cuh)
+  const Opd* emit = nullptr;
+  const Affine* emit_affine = nullptr;
+  int emit_act = ACT_NONE;
+  float emit_slope = 0.f;
 };
 
 Prep prep_of(const Act& src) {
@@ -82,6 +87,11 @@ static void conv_from_operand(Net& n, const Opd& opd, const ConvW& w, const Conv
     e.residual = o.residual->p;
     e.rs_b = o.residual->sb; e.rs_d = o.residual->sd; e.rs_h = o.residual->sh; e.rs_w = o.residual->sw;
   }
+  if (o.emit) {
+    e.emit = o.emit->p; e.emit_nblk = o.emit->nblk;
+    if (o.emit_affine) { e.emit_scale = o.emit_affine->scale; e.emit_shift = o.emit_affine->shift; }
+    e.emit_act = o.emit_act; e.emit_slope = o.emit_slope;
+  }
   conv_tc(n.L, opd, w, g, e, out);
 }
 
@@ -102,6 +112,44 @@ static void resblock3d(Net& n, const ResBlock3dW& w, float* vol, int B, int h, i
   ConvOpts o2; o2.residual = &x;
   conv_layer(n, nullptr, t, w.conv2, o2, x);            // out = conv2(.) + x, written over x
   n.A->reset(m);
+}
+
+// A run of pre-activation residual blocks (ResBlock3d util.py:94-102 on the 3-D view, ResBlock2d util.py:120-128 on the
+// 2-D view) on the tcgen05 path: only the first block's input goes through a prep kernel; every conv epilogue emits
+// the next conv's split-bf16 operand (conv1: act(.) as is, conv2: act(bn1_next(x + conv2(.)))), so the intermediate
+// `t` never exists in fp32 and the volume is read once per block (as the residual).
+struct PreActBlock { const Affine* bn1; const ConvW* conv1; const ConvW* conv2; };
+
+static void preact_chain_tc(Net& n, const PreActBlock* blk, int nb, Act x, int act, float slope) {
+  size_t m = n.A->mark();
+  Opd a = conv_tc_alloc_operand(*n.A, *blk[0].conv1, x);
+  Opd t = conv_tc_alloc_operand(*n.A, *blk[0].conv2, x);
+  Opd b = conv_tc_alloc_operand(*n.A, *blk[0].conv1, x);
+  Prep p = prep_of(x);
+  p.norm = NORM_AFFINE_C; p.scale = blk[0].bn1->scale; p.shift = blk[0].bn1->shift; p.act = act; p.slope = slope;
+  prep_planes(n.L, p, a, nullptr);
+  Act none = x; none.p = nullptr;                        // geometry only: conv1 writes no fp32 output
+  for (int i = 0; i < nb; ++i) {
+    ConvOpts o1; o1.act = act; o1.slope = slope;         // norm2 folded into conv1
+    o1.emit = &t;
+    conv_from_operand(n, a, *blk[i].conv1, o1, none);
+    ConvOpts o2; o2.residual = &x;
+    if (i + 1 < nb) { o2.emit = &b; o2.emit_affine = blk[i + 1].bn1; o2.emit_act = act; o2.emit_slope = slope; }
+    conv_from_operand(n, t, *blk[i].conv2, o2, x);       // x = conv2(.) + x, in place
+    Opd tmp = a; a = b; b = tmp;
+  }
+  n.A->reset(m);
+}
+
+static void resblock3d_run(Net& n, const ResBlock3dW* w, int nb, float* vol, int B, int h, int wd) {
+  Act x = vol_as_3d(vol, B, h, wd);
+  if (use_tc(n, w[0].conv1, x)) {
+    PreActBlock blk[8];
+    for (int i = 0; i < nb; ++i) blk[i] = PreActBlock{&w[i].bn1, &w[i].conv1, &w[i].conv2};
+    preact_chain_tc(n, blk, nb, x, ACT_RELU, 0.f);
+  } else {
+    for (int i = 0; i < nb; ++i) resblock3d(n, w[i], vol, B, h, wd);
+  }
 }
 
 // ResBlock2d, reference util.py:120-128, in place on the volume seen as [B,h,w,512].
@@ -160,7 +208,7 @@ void run_F(Net& n, const float* img_cl, int B, float* vol_out) {
   Act vol2d = vol_as_2d(vol_out, B, h, w);
   conv_layer(n, &p2, a2, W.f_second, ConvOpts(), vol2d);                  // 1x1, Cout pre-permuted to d*32+c
   n.A->reset(m);
-  for (int i = 0; i < 6; ++i) resblock3d(n, W.f_res[i], vol_out, B, h, w);
+  resblock3d_run(n, W.f_res, 6, vol_out, B, h, w);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -180,7 +228,7 @@ static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, c
   const int hs[6] = {h, h / 2, h / 4, h / 8, h / 16, h / 32};
   const int ws[6] = {w, w / 2, w / 4, w / 8, w / 16, w / 32};
   CS_REQUIRE(hs[5] >= 1 && ws[5] >= 1, CS_ERR_INVALID, "feature resolution too small for the 5-level hourglass");
-  Act cat5 = new_act(n, B, D, hs[0], ws[0], HG_OUT);     // [up4 32 | x 110]
+  Act cat5 = new_act(n, B, D, hs[0], ws[0], HG_OUT, 144); // [up4 32 | x 110] (+2 pad floats: 16-byte rows)
   Act cat4 = new_act(n, B, D, hs[1], ws[1], 128);        // [up3 64 | p0 64]
   Act cat3 = new_act(n, B, D, hs[2], ws[2], 256);        // [up2 128 | p1 128]
   Act cat2 = new_act(n, B, D, hs[3], ws[3], 512);        // [up1 256 | p2 256]
@@ -215,7 +263,7 @@ static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, c
     }
     dcur = cats[i];
   }
-  Act pred = new_act(n, B, D, h, w, HG_OUT);
+  Act pred = new_act(n, B, D, h, w, HG_OUT, 144);
   conv_layer(n, nullptr, cat5, W.hg_final, relu, pred);
   // mask logits 7x7x7 (:88); softmax is fused into the flow/warp kernel
   // occlusion 7x7 over (c*16+d) channels == conv3d kernel (16,7,7), pad (0,3,3), then sigmoid (:98-102)
@@ -232,8 +280,14 @@ static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, c
     } else {
       conv_from_operand(n, opd, W.dm_mask, ConvOpts(), logits);
     }
-    ConvOpts sg; sg.act = ACT_SIGMOID;
-    conv_from_operand(n, opd, W.dm_occlusion, sg, occ_act);
+    if (opd.H * opd.W >= 128) {                                         // one depth slice per tile
+      Act Y = new_act(n, B, D, h, w, 64);
+      conv_from_operand(n, opd, W.dm_occ_y, ConvOpts(), Y);
+      occlusion_gather(n.L, Y, W.dm_occlusion.bias, occ);
+    } else {
+      ConvOpts sg; sg.act = ACT_SIGMOID;
+      conv_from_operand(n, opd, W.dm_occlusion, sg, occ_act);
+    }
     n.A->reset(m);
   } else {
     conv_layer(n, nullptr, pred, W.dm_mask, ConvOpts(), logits);
@@ -277,19 +331,23 @@ static void adaptive_conv(Net& n, const AdaptiveConvW& a, const Act& x, const fl
   size_t m = n.A->mark();
   long P = x.pixels();
   Act o2 = new_act(n, x.B, 1, x.H, x.W, 1024);
-  Act mask_act = make_act(mask, x.B, 1, x.H, x.W, 1);
-  if (use_tc(n, a.combined, o2) && use_tc(n, a.mask_conv, mask_act)) {
-    Opd opd = conv_tc_alloc_operand(*n.A, a.combined, o2);
-    prep_planes(n.L, prep_of(x), opd, nullptr);
-    conv_from_operand(n, opd, a.combined, ConvOpts(), o2);
-    ConvOpts sg; sg.act = ACT_SIGMOID;
-    conv_from_operand(n, opd, a.mask_conv, sg, mask_act);
-  } else {
-    conv_layer(n, nullptr, x, a.combined, ConvOpts(), o2);
-    ConvGeom g; g.PD = 0; g.PH = 1; g.PW = 1; g.Do = 1; g.Ho = x.H; g.Wo = x.W;
-    conv_cout1(n.L, x, a.mask_conv, g, ACT_SIGMOID, mask);
-  }
-  adaptive_blend(n.L, o2.p, mask, residual, relu, y, P);
+  conv_layer(n, nullptr, x, a.combined, ConvOpts(), o2);
+  ConvGeom g; g.PD = 0; g.PH = 1; g.PW = 1; g.Do = 1; g.Ho = x.H; g.Wo = x.W;
+  conv_cout1(n.L, x, a.mask_conv, g, ACT_SIGMOID, mask);
+  adaptive_blend(n.L, o2.p, mask, residual, relu, y, nullptr, P);
+  n.A->reset(m);
+}
+
+// tcgen05 variant: input already in operand form (shared by the combined conv and the mask conv); the blend
+// writes the fp32 result (if wanted) and / or the next adaptive conv's operand.
+static void adaptive_conv_tc(Net& n, const AdaptiveConvW& a, const Act& geom, const Opd& in, const float* residual, int relu,
+                             float* y, const Opd* out, float* mask) {
+  size_t m = n.A->mark();
+  Act o2 = new_act(n, geom.B, 1, geom.H, geom.W, 1024);
+  conv_from_operand(n, in, a.combined, ConvOpts(), o2);
+  ConvOpts sg; sg.act = ACT_SIGMOID;
+  conv_from_operand(n, in, a.mask_conv, sg, make_act(mask, geom.B, 1, geom.H, geom.W, 1));
+  adaptive_blend(n.L, o2.p, mask, residual, relu, y, out ? out->p : nullptr, geom.pixels());
   n.A->reset(m);
 }
 
@@ -301,18 +359,30 @@ void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks) 
   size_t m = n.A->mark();
   if (vol_out != vol_in && !n.L.dry)
     CS_CUDA(cudaMemcpyAsync(vol_out, vol_in, (size_t)P * 512 * sizeof(float), cudaMemcpyDeviceToDevice, n.L.stream));
-  float* y1 = n.A->f32((size_t)P * 512);
   float* m1 = n.A->f32((size_t)P);
   float* m2 = n.A->f32((size_t)P);
   Act x = vol_as_2d(vol_out, B, h, w);
-  Act t = vol_as_2d(y1, B, h, w);
-  for (int i = 0; i < 7; ++i) {                                           // ResnetBlock_Adaptive2D :337-349
-    adaptive_conv(n, W.ad[2 * i], x, nullptr, 1, y1, m1);
-    adaptive_conv(n, W.ad[2 * i + 1], t, vol_out, 0, vol_out, m2);        // x + y, in place
-    if (masks) avg2(n.L, m1, m2, masks + (long)i * P, P);
+  Act mk = make_act(m1, B, 1, h, w, 1);
+  if (use_tc(n, W.ad[0].combined, make_act(nullptr, B, 1, h, w, 1024)) && use_tc(n, W.ad[0].mask_conv, mk)) {
+    Opd oa = conv_tc_alloc_operand(*n.A, W.ad[0].combined, x);
+    Opd ob = conv_tc_alloc_operand(*n.A, W.ad[0].combined, x);
+    prep_planes(n.L, prep_of(x), oa, nullptr);
+    for (int i = 0; i < 7; ++i) {                                           // ResnetBlock_Adaptive2D :337-349
+      adaptive_conv_tc(n, W.ad[2 * i], x, oa, nullptr, 1, nullptr, &ob, m1);              // y = relu(conv1(x)): operand only
+      adaptive_conv_tc(n, W.ad[2 * i + 1], x, ob, vol_out, 0, vol_out, i < 6 ? &oa : nullptr, m2);   // x + conv2(y), in place
+      if (masks) avg2(n.L, m1, m2, masks + (long)i * P, P);
+    }
+  } else {
+    float* y1 = n.A->f32((size_t)P * 512);
+    Act t = vol_as_2d(y1, B, h, w);
+    for (int i = 0; i < 7; ++i) {
+      adaptive_conv(n, W.ad[2 * i], x, nullptr, 1, y1, m1);
+      adaptive_conv(n, W.ad[2 * i + 1], t, vol_out, 0, vol_out, m2);        // x + y, in place
+      if (masks) avg2(n.L, m1, m2, masks + (long)i * P, P);
+    }
   }
   n.A->reset(m);
-  for (int i = 0; i < 6; ++i) resblock3d(n, W.t_res[i], vol_out, B, h, w);
+  resblock3d_run(n, W.t_res, 6, vol_out, B, h, w);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -324,7 +394,16 @@ void run_refine(Net& n, const float* vol_in, int B, float* vol_out) {
   if (vol_out != vol_in && !n.L.dry)
     CS_CUDA(cudaMemcpyAsync(vol_out, vol_in, (size_t)B * h * w * 512 * sizeof(float), cudaMemcpyDeviceToDevice, n.L.stream));
   for (int i = 0; i < 3; ++i) gn_resblock3d(n, W.r_gn1[i], vol_out, B, h, w);
-  for (int i = 0; i < 3; ++i) resblock2d(n, W.r_res2[i], vol_out, B, h, w);
+  {
+    Act x2 = vol_as_2d(vol_out, B, h, w);
+    if (use_tc(n, W.r_res2[0].conv1, x2)) {
+      PreActBlock blk[3];
+      for (int i = 0; i < 3; ++i) blk[i] = PreActBlock{&W.r_res2[i].bn1, &W.r_res2[i].conv1, &W.r_res2[i].conv2};
+      preact_chain_tc(n, blk, 3, x2, ACT_LRELU, 0.01f);
+    } else {
+      for (int i = 0; i < 3; ++i) resblock2d(n, W.r_res2[i], vol_out, B, h, w);
+    }
+  }
   for (int i = 0; i < 3; ++i) gn_resblock3d(n, W.r_gn3[i], vol_out, B, h, w);
 }
 

@@ -282,6 +282,25 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
     // occlusion: Conv2d(142*16 -> 1, 7x7) on prediction.view(B, 142*16, h, w), channel = c*16 + d
     // == Conv3d(142 -> 1, kernel (16,7,7), padding (0,3,3)) on the [B,142,16,h,w] prediction
     W.dm_occlusion = pack(ctx, read_conv(t, p + ".occlusion", 1, HG_OUT, 16, 7, 7));
+    {  // per-tap projection weights of the occlusion conv: rows z*64 + (kh*7+kw), a 1x1x1 conv with depth-dependent weights
+      HostConv oc = read_conv(t, p + ".occlusion", 1, HG_OUT, 16, 7, 7);      // [1][142][16*49]
+      ConvW& y = W.dm_occ_y;
+      y.Cin = HG_OUT; y.Cout = 64; y.KD = y.KH = y.KW = 1;
+      y.nblk = (HG_OUT + 31) / 32; y.BN = 64; y.zrows = 64; y.Cout_p = 64 * 16;
+      const long rowlen = (long)y.nblk * 64;
+      std::vector<__nv_bfloat16> hw((size_t)y.Cout_p * rowlen, __float2bfloat16(0.f));
+      for (int z = 0; z < 16; ++z)
+        for (int tp = 0; tp < 49; ++tp)
+          for (int ci = 0; ci < HG_OUT; ++ci) {
+            const float v = oc.w[(long)ci * (16 * 49) + z * 49 + tp];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            const long o = ((long)z * 64 + tp) * rowlen + (ci >> 5) * 64 + (ci & 31);
+            hw[o] = hi; hw[o + 32] = lo;
+          }
+      y.wtc = static_cast<__nv_bfloat16*>(ctx->dmalloc(hw.size() * sizeof(__nv_bfloat16)));
+      CS_CUDA(cudaMemcpy(y.wtc, hw.data(), hw.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    }
     HostConv third = read_conv(t, "third.conv", 256, 512, 1, 3, 3);
     fold_bn_post(third, read_bn(t, "third.norm", 256));
     permute_in_vol(third);
