@@ -16,6 +16,10 @@ CS_FRAME_DEBUG_DECODES = 2
 CS_OPT_CONV_IMPL = 1
 CS_OPT_USE_GRAPH = 2
 CS_OPT_TC_PASSES = 3
+CS_OPT_TC_SETS = 4
+CS_OPT_TC_COMP = 5
+CS_OPT_TC_PAIR = 6
+CS_OPT_TC_STACKED3 = 7
 
 # every symbol include/canonswap_b200.h declares
 SYMBOLS = [

@@ -39,6 +39,10 @@ Net make_net(cs_ctx* ctx, void* stream, bool dry) {
   n.L.counter = dry ? nullptr : &ctx->launches;
   n.L.conv_impl = ctx->conv_impl;
   n.L.npass = ctx->tc_passes;
+  n.L.max_sets = ctx->tc_sets;
+  n.L.acc_comp = (float)ctx->tc_comp;
+  n.L.pair = ctx->tc_pair != 0;
+  n.L.stacked3 = ctx->tc_stacked3 != 0;
   n.L.prof = dry ? nullptr : &ctx->prof;
   return n;
 }
@@ -232,6 +236,16 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
     case CS_OPT_TC_PASSES:
       if (value < 1 || value > 3) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_PASSES: value must be 1, 2 or 3");
       ctx->tc_passes = value; return CS_OK;
+    case CS_OPT_TC_SETS:
+      if (value < 0 || value > 16) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_SETS: value must be in [0, 16]");
+      ctx->tc_sets = value; return CS_OK;
+    case CS_OPT_TC_COMP:
+      if (value < 0 || value > 1000) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_COMP: value must be in [0, 1000]");
+      ctx->tc_comp = value; return CS_OK;
+    case CS_OPT_TC_STACKED3:
+      ctx->tc_stacked3 = value ? 1 : 0; return CS_OK;
+    case CS_OPT_TC_PAIR:
+      ctx->tc_pair = value ? 1 : 0; return CS_OK;
     case CS_OPT_USE_GRAPH:
       ctx->use_graph = value ? 1 : 0; return CS_OK;
     default: return fail(ctx, CS_ERR_INVALID, "unknown option");
@@ -370,7 +384,7 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
                  int Cout, int KD, int KH, int KW, int PD, int PH, int PW, int act, float slope, int impl, void* stream) {
   CS_API_BEGIN(ctx)
   CS_REQUIRE(x && w && y && B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, CS_ERR_INVALID, "cs_test_conv: bad argument");
-  CS_REQUIRE(KD > 0 && KH > 0 && KW > 0 && impl >= 0 && impl <= 3, CS_ERR_INVALID, "cs_test_conv: bad argument");
+  CS_REQUIRE(KD > 0 && KH > 0 && KW > 0 && impl >= 0 && impl <= 4, CS_ERR_INVALID, "cs_test_conv: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CS_CUDA(cudaStreamSynchronize(st));
   const size_t nw = (size_t)Cout * Cin * KD * KH * KW;
@@ -393,13 +407,25 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
     Act ya = make_act(y, B, Do, Ho, Wo, Cout);
     ConvGeom g; g.PD = PD; g.PH = PH; g.PW = PW; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
     Epilogue e; e.act = act; e.slope = slope;
-    Launcher L; L.stream = st; L.counter = &ctx->launches; L.npass = ctx->tc_passes; L.prof = &ctx->prof;
+    Launcher L; L.stream = st; L.counter = &ctx->launches; L.npass = ctx->tc_passes; L.prof = &ctx->prof; L.max_sets = ctx->tc_sets; L.acc_comp = (float)ctx->tc_comp; L.pair = ctx->tc_pair != 0;
     const bool same = (Ho == H && Wo == W && PH == KH / 2 && PW == KW / 2) &&
                       ((Do == D && PD == KD / 2) || (Do == 1 && KD == D && PD == 0));
     bool tc = same && conv_tc_supported(cw, ya);
     if (impl == 2) CS_REQUIRE(tc, CS_ERR_INVALID, "cs_test_conv: shape not supported by the tcgen05 conv");
     if (impl == 1) tc = false;
-    if (impl == 3) {
+    if (impl == 4) {
+      // the depth-stacked 32 -> 32 3x3x3 kernel
+      pack_conv3s(ctx, cw);
+      CS_CUDA(cudaDeviceSynchronize());
+      CS_REQUIRE(same && D == 16 && conv3s_supported(cw, H, W), CS_ERR_INVALID, "cs_test_conv: shape not supported by the stacked 3x3x3 kernel");
+      Arena tmp; tmp.measuring = true;
+      conv_tc_alloc_operand(tmp, cw, xa);
+      Arena real; real.cap = tmp.high + 4096; real.base = static_cast<char*>(ctx->dmalloc(real.cap));
+      Opd opd = conv_tc_alloc_operand(real, cw, xa);
+      Prep p; p.src0 = xa;
+      prep_planes(L, p, opd, nullptr);
+      conv3s_tc(L, opd, cw, e, ya);
+    } else if (impl == 3) {
       // the depth-stacked 7x7x7 kernel: output rows padded to a multiple of 4 channels, then compacted
       pack_conv7(ctx, cw);
       CS_CUDA(cudaDeviceSynchronize());

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -69,6 +70,28 @@ struct Opd {
   int B = 0, D = 1, H = 0, W = 0, nblk = 0;
 };
 
+// The split itself: hi = bf16(v), lo = bf16(v - hi), v ~= hi + lo to ~2^-17 relative.
+// (A scaled-fp16 remainder would add 3 more bits, but tcgen05.mma kind::f16 rejects mixed f16 x bf16 operand
+// formats -- "illegal instruction" on B200 -- so both halves stay bf16.)
+constexpr float LO_UNSCALE = 1.f;
+
+__host__ __device__ inline void split_operand(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+#ifdef __CUDACC__
+// 4 values -> {hi01, hi23} and {lo01, lo23} packed as two 32-bit words each
+__device__ __forceinline__ void split_operand4(float a, float b, float c, float d, uint2& hv, uint2& lv) {
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(a, b), h23 = __floats2bfloat162_rn(c, d);
+  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+  const __nv_bfloat162 l01 = __floats2bfloat162_rn(a - f01.x, b - f01.y);
+  const __nv_bfloat162 l23 = __floats2bfloat162_rn(c - f23.x, d - f23.y);
+  hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+  lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+}
+#endif
+
 enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_SIGMOID = 3 };
 
 __host__ __device__ inline float apply_act(float v, int kind, float slope) {
@@ -87,6 +110,7 @@ struct ConvW {
   float* bias = nullptr;   // [Cout] or null
   // tcgen05 path: B operand [Cout_p][tap][nblk][hi 32 | lo 32] bf16 (K-major rows), N tile BN
   __nv_bfloat16* wtc = nullptr;
+  __nv_bfloat16* w3s = nullptr;    // 3x3x3 32->32 depth-stacked packing (conv3s_tc.cu)
   __nv_bfloat16* w7 = nullptr;     // 7x7x7 depth-stacked packing (conv7_tc.cu), mask conv only
   int nblk = 0, Cout_p = 0, BN = 0;
   int zrows = 0;                   // > 0: depth-dependent weights (rows d*zrows .. of wtc belong to depth slice d)
@@ -172,6 +196,10 @@ struct Launcher {            // everything a kernel launch helper needs
   int64_t* counter = nullptr;
   int conv_impl = 0;         // 0 auto, 1 SIMT, 2 TC
   int npass = 3;             // split-bf16 MMA passes of the tcgen05 conv (3 = hi*hi + lo*hi + hi*lo)
+  int max_sets = 0;          // cap on the accumulator sets (0 = automatic)
+  bool stacked3 = true;      // depth-stacked kernel for the 32 -> 32 3x3x3 volume convs
+  bool pair = true;          // tcgen05 pair mode (cta_group::2, 2-CTA clusters) for wide N tiles
+  float acc_comp = 72.f;     // accumulate-truncation compensation per chained MMA, in units of 1e-10 (0 = off)
   Profiler* prof = nullptr;
   void count() const { if (counter) ++*counter; }
 };
@@ -228,6 +256,9 @@ void grid_sample3d_cl(const Launcher& L, const float* vol, const float* grid, fl
 bool conv_tc_supported(const ConvW& w, const Act& out);
 Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out);   // split-bf16 operand with the geometry of `out`
 void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y);
+// conv3s_tc.cu : the 32 -> 32 3x3x3 volume convs (depth-stacked, weights resident in shared memory)
+bool conv3s_supported(const ConvW& w, int H, int W);
+void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& e, Act y);
 // conv7_tc.cu : the 7x7x7 mask conv (depth-stacked, kh-split); scratch holds the 7 partial logit tensors
 bool conv7_supported(const ConvW& w, const Act& out);
 size_t conv7_scratch_floats(const Act& out);

@@ -1,0 +1,313 @@
+// The 32 -> 32 channel 3x3x3 convolutions of the 32x16 feature volume (ResBlock3d / ResBlock3D_stage3_leak, reference
+// util.py:80-102,515-544: 36 of them per frame).  As a plain implicit GEMM they have N = 32 and re-read every input tile
+// from L2 once per filter tap (27x): the generic kernel runs them at the L2 bandwidth limit.  Dedicated tcgen05 kernel,
+// "depth-stacked, weights resident":
+//
+//   * one CTA = 128 (h,w) pixels x ALL 16 depths x 32 channels: 16 x 32 = 512 fp32 accumulator columns = the whole TMEM.
+//   * for an input slice z and an in-plane tap (kh,kw) the A tile (128 pixels x 32 channels, shifted by the tap, TMA
+//     zero-fills the h/w padding) feeds the three output depths d = z-1, z, z+1 at once: the B tile stacks the depth taps
+//     kd = z-d+1 along N (3 x 32 = 96 columns landing at TMEM column 32*(z-1)), so every input tile is loaded 9 times
+//     instead of 27 and the MMAs are 3x wider.
+//   * the complete weight set (9 in-plane taps x 96 rows x 128 B = 108 KB) is loaded into shared memory once per CTA;
+//     the pipeline only streams A tiles.
+//   * accumulation chain per output column: 3 slices x 9 taps x 2 K-steps x 3 passes = 162 MMAs (one accumulator).
+//
+// Operand format, MMA issue and the fused epilogue (bias, activation, residual, fp32 store and / or emission of the next
+// conv's operand) are those of conv_tc.cu.
+#include "tc_ptx.cuh"
+
+namespace cs {
+
+using namespace tc;
+
+namespace {
+
+constexpr int C3_BTAP_BYTES = 96 * 128;                   // one in-plane tap: 3 depth taps x 32 couts x [hi 32 | lo 32]
+constexpr int C3_B_BYTES = 9 * C3_BTAP_BYTES;             // 108 KB resident weights
+constexpr int C3_STAGES = 5;
+constexpr int C3_SMEM = C3_B_BYTES + C3_STAGES * A_TILE_BYTES + STG_BYTES + 1024 + 16 * C3_STAGES + 64;
+
+struct Conv3sK {
+  int B, H, W;                     // D = 16, C = 32
+  int lbw, lbh, ntw, nth;
+  const float* bias; int act; float slope;
+  const float* res; long rb, rd, rh, rw;
+  float* y; long yb, yd, yh, yw;
+  __nv_bfloat16* emit; const float* escale; const float* eshift; int eact; float eslope;
+  float acc_scale;
+};
+
+template <bool RES, bool EMIT>
+__global__ void __launch_bounds__(TC_THREADS) conv3s_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB, Conv3sK k) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bres = base;                                        // resident weights
+  const uint32_t abase = base + C3_B_BYTES;                          // A stages
+  const uint32_t stg = abase + (uint32_t)C3_STAGES * A_TILE_BYTES;
+  const uint32_t bars = stg + STG_BYTES;                             // full[S], empty[S], tmem_full, wready, tmem slot
+  const uint32_t tmem_full = bars + 16u * C3_STAGES;
+  const uint32_t wready = tmem_full + 8u;
+  const uint32_t tmem_slot = wready + 8u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int tw = t % k.ntw; t /= k.ntw;
+  const int th = t % k.nth; const int b = t / k.nth;
+  const int w0 = tw << k.lbw, h0 = th << k.lbh;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < C3_STAGES; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (C3_STAGES + s), 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(wready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  // zero the accumulators: every MMA accumulates (a slice touches a sliding window of depth columns)
+  if (warp >= 2) {
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c = 0; c < 512; c += 16) tc_st16_zero(trow + (uint32_t)c);
+    tc_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ===== TMA producer: the weights once, then the A tiles =====
+    if (lane == 0) {
+      mbar_expect_tx(wready, C3_B_BYTES);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(bres + (uint32_t)tap * C3_BTAP_BYTES, &tmB, wready, 0, tap * 96);
+      int s = 0; uint32_t ph = 0;
+      for (int z = 0; z < 16; ++z) {
+        for (int tap = 0; tap < 9; ++tap) {
+          const int kh = tap / 3, kw = tap % 3;
+          const uint32_t fb = bars + 8u * s;
+          mbar_wait(fb + 8u * C3_STAGES, ph ^ 1u);
+          mbar_expect_tx(fb, A_TILE_BYTES);
+          tma_load_5d(abase + (uint32_t)s * A_TILE_BYTES, &tmA, fb, 0, w0 + kw - 1, h0 + kh - 1, z, b);
+          if (++s == C3_STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (converged warp, elected lane inside the asm block) =====
+    mbar_wait(wready, 0);
+    int s = 0; uint32_t ph = 0;
+    for (int z = 0; z < 16; ++z) {
+      const int dlo = max(z - 1, 0), dhi = min(z + 1, 15);
+      const uint32_t N = (uint32_t)(dhi - dlo + 1) * 32u;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t d_acc = tmem_base + (uint32_t)(dlo * 32);
+      const uint32_t brow = (uint32_t)(dlo - (z - 1)) * 32u * 128u;  // skip the depth-tap slot of d = -1
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t fb = bars + 8u * s;
+        mbar_wait(fb, ph);
+        tc_fence_after();
+        mma_stage<3, 2>(d_acc, d_acc, umma_desc(abase + (uint32_t)s * A_TILE_BYTES),
+                        umma_desc(bres + (uint32_t)tap * C3_BTAP_BYTES + brow), idesc, 1u, 1u, fb + 8u * C3_STAGES);
+        if (++s == C3_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(tmem_full) : "memory");
+  } else {
+    // ===== epilogue: per output depth 32 columns -> smem tile -> coalesced rows =====
+    const int q = warp & 3;
+    float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + q * 32 * STG_LD;
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    long yoff[8], roff[RES ? 8 : 1], epix[EMIT ? 8 : 1];
+    uint32_t vmask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int r = q * 32 + sub + 4 * i;
+      const int ow = w0 + (r & ((1 << k.lbw) - 1)); r >>= k.lbw;
+      const int oh = h0 + r;
+      if (ow < k.W && oh < k.H) vmask |= 1u << i;
+      yoff[i] = b * k.yb + oh * k.yh + ow * k.yw + c4;
+      if constexpr (RES) roff[i] = b * k.rb + oh * k.rh + ow * k.rw + c4;
+      if constexpr (EMIT) epix[i] = (((long)b * 16) * k.H + oh) * k.W + ow;
+    }
+    float bz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k.bias) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(k.bias + c4));
+      bz[0] = t4.x; bz[1] = t4.y; bz[2] = t4.z; bz[3] = t4.w;
+    }
+    float es[4] = {1.f, 1.f, 1.f, 1.f}, eb[4] = {0.f, 0.f, 0.f, 0.f};
+    if (EMIT && k.escale) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(k.escale + c4));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(k.eshift + c4));
+      es[0] = s4.x; es[1] = s4.y; es[2] = s4.z; es[3] = s4.w;
+      eb[0] = b4.x; eb[1] = b4.y; eb[2] = b4.z; eb[3] = b4.w;
+    }
+    const long dstride_e = (long)k.H * k.W;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int d = 0; d < 16; ++d) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[16];
+        tc_ld16(trow + (uint32_t)(d * 32 + 16 * half), v);
+        tc_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(tile + lane * STG_LD + 16 * half);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+      }
+      __syncwarp();
+      float4 rr4[RES ? 8 : 1];
+      if constexpr (RES) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rr4[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float4*>(k.res + roff[i] + d * k.rd) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!((vmask >> i) & 1u)) continue;
+        const float4 a = *reinterpret_cast<const float4*>(tile + (sub + 4 * i) * STG_LD + c4);
+        float o[4] = {fmaf(a.x, k.acc_scale, bz[0]), fmaf(a.y, k.acc_scale, bz[1]), fmaf(a.z, k.acc_scale, bz[2]),
+                      fmaf(a.w, k.acc_scale, bz[3])};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], k.act, k.slope);
+        if constexpr (RES) { o[0] += rr4[i].x; o[1] += rr4[i].y; o[2] += rr4[i].z; o[3] += rr4[i].w; }
+        if (k.y) *reinterpret_cast<float4*>(k.y + yoff[i] + d * k.yd) = make_float4(o[0], o[1], o[2], o[3]);
+        if constexpr (EMIT) {
+          float e[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope);
+          uint2 hv, lv;
+          split_operand4(e[0], e[1], e[2], e[3], hv, lv);
+          __nv_bfloat16* ep = k.emit + (epix[i] + d * dstride_e) * 64 + c4;
+          *reinterpret_cast<uint2*>(ep) = hv;
+          *reinterpret_cast<uint2*>(ep + 32) = lv;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// w32 [tap = (kd*3+kh)*3+kw][32][32] fp32 -> rows ((kh*3+kw)*3 + j)*32 + co with kd = 2 - j (ascending output depth
+// d = z - 1 + j), 64 columns [hi 32 | lo 32]
+__global__ void __launch_bounds__(256) pack_conv3s_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ out) {
+  const int total = 9 * 3 * 32 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i & 31; int r = i >> 5;
+    const int co = r & 31; r >>= 5;
+    const int j = r % 3; const int khw = r / 3;
+    const int tap = (2 - j) * 9 + khw;
+    const float v = w32[((long)tap * 32 + ci) * 32 + co];
+    __nv_bfloat16 hi, lo;
+    split_operand(v, hi, lo);
+    const long o = (((long)khw * 3 + j) * 32 + co) * 64 + ci;
+    out[o] = hi;
+    out[o + 32] = lo;
+  }
+}
+
+bool g_attr3[64] = {};
+
+}  // namespace
+
+bool conv3s_supported(const ConvW& w, int H, int W) {
+  return w.w3s != nullptr && (long)H * W >= 128;
+}
+
+void pack_conv3s(cs_ctx* ctx, ConvW& w) {
+  if (!(w.KD == 3 && w.KH == 3 && w.KW == 3 && w.Cin == 32 && w.Cout == 32 && w.w32)) return;
+  if (!w.w3s) w.w3s = static_cast<__nv_bfloat16*>(ctx->dmalloc((size_t)9 * 96 * 64 * sizeof(__nv_bfloat16)));
+  pack_conv3s_kernel<<<108, 256>>>(w.w32, w.w3s);
+  check_launch("pack_conv3s");
+}
+
+// x: split-bf16 operand [B,16,H,W,64] of a 32-channel volume; y (fp32, may have a null pointer when only the operand is
+// emitted) / residual: channels-last with generic strides and channel stride 1 (the [B,h,w,16,32] volume view).
+void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& e, Act y) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(conv3s_supported(w, x.H, x.W) && x.D == 16 && x.nblk == 1 && y.D == 16 && y.C == 32 && y.H == x.H && y.W == x.W &&
+                 y.B == x.B, CS_ERR_INVALID, "conv3s_tc: unsupported geometry");
+  auto al4 = [](long v) { return (v & 3) == 0; };
+  CS_REQUIRE(al4(y.sb) && al4(y.sd) && al4(y.sh) && al4(y.sw) && ((uintptr_t)y.p % 16 == 0), CS_ERR_INVALID,
+             "conv3s_tc: output must be 16-byte aligned");
+  CS_REQUIRE(!e.mult, CS_ERR_INVALID, "conv3s_tc: per-pixel multiplier not supported");
+  Conv3sK k{};
+  k.B = x.B; k.H = x.H; k.W = x.W;
+  int cap = 128;
+  const int bw = pick_box(x.W, cap, &k.lbw); cap /= bw;
+  const int bh = cap; k.lbh = 0; while ((1 << k.lbh) < bh) ++k.lbh;
+  k.ntw = (x.W + bw - 1) / bw; k.nth = (x.H + bh - 1) / bh;
+  k.bias = w.bias; k.act = e.act; k.slope = e.slope;
+  k.res = e.residual; k.rb = e.rs_b; k.rd = e.rs_d; k.rh = e.rs_h; k.rw = e.rs_w;
+  if (e.residual)
+    CS_REQUIRE(al4(e.rs_b) && al4(e.rs_d) && al4(e.rs_h) && al4(e.rs_w) && ((uintptr_t)e.residual % 16 == 0), CS_ERR_INVALID,
+               "conv3s_tc: residual must be 16-byte aligned");
+  k.y = y.p; k.yb = y.sb; k.yd = y.sd; k.yh = y.sh; k.yw = y.sw;
+  if (e.emit) {
+    CS_REQUIRE(e.emit_nblk == 1, CS_ERR_INVALID, "conv3s_tc: emitted operand must have 32 channels");
+    k.emit = e.emit; k.escale = e.emit_scale; k.eshift = e.emit_shift; k.eact = e.emit_act; k.eslope = e.emit_slope;
+  }
+  k.acc_scale = 1.0f + L.acc_comp * 1e-10f * 162.f;
+
+  auto enc = encode_fn();
+  CUtensorMap tmA, tmB;
+  {
+    const cuuint64_t pix = 64 * 2;
+    cuuint64_t dims[5] = {64, (cuuint64_t)x.W, (cuuint64_t)x.H, 16, (cuuint64_t)x.B};
+    cuuint64_t strides[4] = {pix, pix * x.W, pix * x.W * x.H, pix * x.W * x.H * 16};
+    cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CS_REQUIRE(r == CUDA_SUCCESS, CS_ERR_CUDA, "conv3s_tc: cuTensorMapEncodeTiled(A) failed");
+  }
+  {
+    cuuint64_t dims[2] = {64, 9 * 96};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 96};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w3s, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CS_REQUIRE(r == CUDA_SUCCESS, CS_ERR_CUDA, "conv3s_tc: cuTensorMapEncodeTiled(B) failed");
+  }
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, Conv3sK);
+  static const KernelFn fns[2][2] = {{conv3s_tc_kernel<false, false>, conv3s_tc_kernel<false, true>},
+                                     {conv3s_tc_kernel<true, false>, conv3s_tc_kernel<true, true>}};
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (!g_attr3[dev & 63]) {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) CS_CUDA(cudaFuncSetAttribute(fns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
+    g_attr3[dev & 63] = true;
+  }
+  const long M = (long)x.B * 16 * x.H * x.W;
+  ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * 32 * 32 * 27, 0.0);
+  dim3 grid((unsigned)(k.ntw * k.nth * x.B));
+  fns[k.res != nullptr][k.emit != nullptr]<<<grid, TC_THREADS, C3_SMEM, L.stream>>>(tmA, tmB, k);
+  check_launch("conv3s_tc");
+}
+
+}  // namespace cs

@@ -36,6 +36,7 @@ struct Conv7K {
   float* parts;                    // [7][B,16,H,W,ldo]
   long part_stride;                // elements between partial tensors
   int ldo;                         // channel stride of a partial (24)
+  float acc_scale;                 // round-toward-zero compensation of the hi*hi chain (see conv_tc.cu)
 };
 
 __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -159,10 +160,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
         float4* dst = reinterpret_cast<float4*>(tile + lane * STG_LD + 16 * half);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          dst[j] = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(u[4 * j]),
-                               __uint_as_float(v[4 * j + 1]) + __uint_as_float(u[4 * j + 1]),
-                               __uint_as_float(v[4 * j + 2]) + __uint_as_float(u[4 * j + 2]),
-                               __uint_as_float(v[4 * j + 3]) + __uint_as_float(u[4 * j + 3]));
+          dst[j] = make_float4(fmaf(__uint_as_float(v[4 * j]), k.acc_scale, __uint_as_float(u[4 * j]) * LO_UNSCALE),
+                               fmaf(__uint_as_float(v[4 * j + 1]), k.acc_scale, __uint_as_float(u[4 * j + 1]) * LO_UNSCALE),
+                               fmaf(__uint_as_float(v[4 * j + 2]), k.acc_scale, __uint_as_float(u[4 * j + 2]) * LO_UNSCALE),
+                               fmaf(__uint_as_float(v[4 * j + 3]), k.acc_scale, __uint_as_float(u[4 * j + 3]) * LO_UNSCALE));
       }
       __syncwarp();
       if (c4 < k.ldo) {
@@ -198,8 +199,8 @@ __global__ void __launch_bounds__(256) pack_conv7_kernel(const float* __restrict
     const int kd = 6 - j, ci = blk * 32 + e;
     const int tap = kd * 49 + khw;
     const float v = (co < Cout && ci < Cin) ? w32[((long)tap * Cin + ci) * Cout + co] : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16 hi, lo;
+    split_operand(v, hi, lo);
     const long row = ((long)khw * 7 + j) * C7_COUT_P + co;
     const long o = row * (nblk * 64L) + blk * 64 + e;
     out[o] = hi;
@@ -267,6 +268,7 @@ void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* s
   k.ldo = (int)out.sw;
   k.parts = scratch;
   k.part_stride = (long)x.B * 16 * x.H * x.W * k.ldo;
+  k.acc_scale = 1.0f + L.acc_comp * 1e-10f * (float)(7 * 7 * (2 * (x.nblk - 1) + k.last_ksteps));   // chain: 7 z x 7 kw x K steps
 
   auto enc = encode_fn();
   CUtensorMap tmA, tmB;

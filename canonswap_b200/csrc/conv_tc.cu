@@ -38,6 +38,7 @@ struct ConvTcK {
   int rowA;                        // bf16 elements per pixel of the operand = nblk * 64
   int BN, Cout, stages, npass;
   int tcols, nsets, chunk;         // TMEM columns, accumulator sets of BN columns, K iterations per hi*hi set
+  float acc_scale;                 // compensation of the tensor core's round-toward-zero accumulation (see host code)
   int zrows;                       // > 0: depth-dependent weights, B rows of depth slice d start at d * zrows
   const float* bias; int act; float slope;
   const float* res; long rb, rd, rh, rw;
@@ -49,12 +50,22 @@ struct ConvTcK {
 };
 
 
+// RES / EMIT: compile-time epilogue variants (residual add, operand emission) -- the epilogue is not overlapped
+// with the main loop, so the plain variant must not carry the registers of the fused ones.
+// CTAS = 2: the CTAs of a 2-CTA cluster (two consecutive M tiles, same N tile) run as a tcgen05 pair: each loads its own
+// A tile and HALF of the B tile, the leader issues cta_group::2 MMAs (M = 256) that read A / B from both CTAs' shared
+// memory and accumulate into both CTAs' TMEM.  Halving the B bytes written and read per CTA takes the kernel off the
+// shared-memory bandwidth limit that bounds the 1-CTA form at N = 256 (3 MMAs per operand load).
+template <bool RES, bool EMIT, int CTAS>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, ConvTcK k) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)k.BN * 128u;
+  uint32_t cta_rank = 0;
+  if constexpr (CTAS == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const uint32_t brows = (uint32_t)k.BN / CTAS;                       // B rows held by this CTA
+  const uint32_t stage_bytes = A_TILE_BYTES + brows * 128u;
   const uint32_t stg = base + (uint32_t)k.stages * stage_bytes;       // epilogue staging
   const uint32_t bars = stg + STG_BYTES;                              // full[stages], empty[stages], tmem_full, tmem slot
   const uint32_t tmem_full = bars + 16u * k.stages;
@@ -87,11 +98,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
@@ -106,18 +122,24 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         for (int blk = 0; blk < k.nblk; ++blk) {
           const uint32_t fb = bars + 8u * s;
           mbar_wait(fb + 8u * k.stages, ph ^ 1u);
-          mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = base + (uint32_t)s * stage_bytes;
-          tma_load_5d(sa, &tmA, fb, blk * 64, cw, ch, cd, b0);
-          tma_load_2d(sa + A_TILE_BYTES, &tmB, fb, kcol + blk * 64, nrow0);
+          if constexpr (CTAS == 2) {
+            if (cta_rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);          // both CTAs' bytes land on the leader's barrier
+            tma_load_5d_2sm(sa, &tmA, fb, blk * 64, cw, ch, cd, b0);
+            tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, fb, kcol + blk * 64, nrow0 + (int)(cta_rank * brows));
+          } else {
+            mbar_expect_tx(fb, stage_bytes);
+            tma_load_5d(sa, &tmA, fb, blk * 64, cw, ch, cd, b0);
+            tma_load_2d(sa + A_TILE_BYTES, &tmB, fb, kcol + blk * 64, nrow0);
+          }
           if (++s == k.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (CTAS == 1 || cta_rank == 0)) {
     // ===== MMA issuer: the whole warp walks the loop converged, one elected lane issues =====
-    // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(k.BN >> 3) << 17) | ((128u >> 4) << 24);
+    // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128 per CTA
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(k.BN >> 3) << 17) | (((128u * CTAS) >> 4) << 24);
     const uint32_t d_corr0 = tmem_base;
     uint32_t d_main = tmem_base + (uint32_t)(corr * k.BN);
     int s = 0; uint32_t ph = 0;
@@ -133,8 +155,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         const int ksteps = (blk == k.nblk - 1) ? k.last_ksteps : 2;
         const uint32_t acc_main = in_set > 0 ? 1u : 0u;
         const uint32_t eb = fb + 8u * k.stages;
-        if (corr) {
+        if constexpr (CTAS == 2) {
+          mma_stage_k<3, 2>(ksteps, d_main, corr ? d_corr0 : d_main, ad, bd, idesc, acc_main, corr ? acc_corr : 1u, eb);
+        } else if (corr && k.npass == 3) {
           mma_stage_k<3>(ksteps, d_main, d_corr0, ad, bd, idesc, acc_main, acc_corr, eb);
+        } else if (corr) {
+          mma_stage_k<2>(ksteps, d_main, d_corr0, ad, bd, idesc, acc_main, acc_corr, eb);
         } else if (k.npass == 3) {                       // single accumulator: corrections follow hi*hi in place
           mma_stage_k<3>(ksteps, d_main, d_main, ad, bd, idesc, acc_main, 1u, eb);
         } else if (k.npass == 2) {
@@ -147,19 +173,27 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         if (++s == k.stages) { s = 0; ph ^= 1u; }
       }
     }
-    asm volatile(
-        "{\n\t.reg .pred pe;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-        ::"r"(tmem_full) : "memory");
-  } else {
+    if constexpr (CTAS == 2) {
+      asm volatile(
+          "{\n\t.reg .pred pe;\n\t.reg .b16 mk;\n\tmov.b16 mk, 3;\n\t"
+          "elect.sync _|pe, 0xffffffff;\n\t"
+          "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], mk;\n\t}"
+          ::"r"(tmem_full) : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred pe;\n\t"
+          "elect.sync _|pe, 0xffffffff;\n\t"
+          "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+          ::"r"(tmem_full) : "memory");
+    }
+  } else if (warp >= 2) {
     // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 =====
     // phase 1: each lane pulls its pixel row (32 columns, all accumulator sets summed) into a padded smem tile;
     // phase 2: the warp walks the tile 4 rows x 128 B at a time so global stores / residual loads are coalesced.
     const int q = warp & 3;
     float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + q * 32 * STG_LD;
     const int sub = lane >> 3, c4 = (lane & 7) * 4;
-    long yoff[8], roff[8], epix[8];
+    long yoff[8], roff[RES ? 8 : 1], epix[EMIT ? 8 : 1];
     float mu[8];
     uint32_t vmask = 0;
 #pragma unroll
@@ -172,11 +206,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       const bool valid = ow < k.W && oh < k.H && od < k.D && ob < k.B;
       if (valid) vmask |= 1u << i;
       yoff[i] = ob * k.yb + od * k.yd + oh * k.yh + ow * k.yw;
-      roff[i] = ob * k.rb + od * k.rd + oh * k.rh + ow * k.rw;
-      epix[i] = (((long)ob * k.D + od) * k.H + oh) * k.W + ow;
+      if constexpr (RES) roff[i] = ob * k.rb + od * k.rd + oh * k.rh + ow * k.rw;
+      if constexpr (EMIT) epix[i] = (((long)ob * k.D + od) * k.H + oh) * k.W + ow;
       mu[i] = (k.mult && valid) ? k.mult[(((long)ob * k.D + od) * k.H + oh) * k.W + ow] : 1.f;
     }
-    if (k.res) {                                            // pull the residual tile towards L2 while the MMAs run
+    if constexpr (RES) {                                    // pull the residual tile towards L2 while the MMAs run
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (!((vmask >> i) & 1u)) continue;
@@ -208,7 +242,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             tc_ld16(tcol, u);
             tc_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            for (int j = 0; j < 16; ++j)
+              v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), k.acc_scale, __uint_as_float(u[j]) * LO_UNSCALE));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * k.acc_scale);
           }
           float4* dst = reinterpret_cast<float4*>(tile + lane * STG_LD + 16 * half);
 #pragma unroll
@@ -226,14 +264,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           for (int j = 0; j < 4; ++j) if (n + j < k.Cout) bz[j] = __ldg(k.bias + n + j);
         }
         const bool full4 = k.vec4 && (n + 3 < k.Cout);
-        float4 rr4[8];
-        if (full4 && k.res) {                               // all residual loads in flight before the first use
+        float4 rr4[RES ? 8 : 1];
+        if constexpr (RES) {
+          if (full4) {                                      // all residual loads in flight before the first use
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            rr4[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float4*>(k.res + roff[i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 8; ++i)
+              rr4[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float4*>(k.res + roff[i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         float es[4] = {1.f, 1.f, 1.f, 1.f}, eb[4] = {0.f, 0.f, 0.f, 0.f};
-        if (k.emit && k.escale) {                           // emission needs Cout % 32 == 0: n .. n+3 are valid
+        if (EMIT && k.escale) {                             // emission needs Cout % 32 == 0: n .. n+3 are valid
           const float4 s4 = __ldg(reinterpret_cast<const float4*>(k.escale + n));
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(k.eshift + n));
           es[0] = s4.x; es[1] = s4.y; es[2] = s4.z; es[3] = s4.w;
@@ -246,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           float o[4] = {a.x + bz[0], a.y + bz[1], a.z + bz[2], a.w + bz[3]};
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], k.act, k.slope);
-          if (k.res) {
+          if constexpr (RES) {
             if (full4) {
               o[0] += rr4[i].x; o[1] += rr4[i].y; o[2] += rr4[i].z; o[3] += rr4[i].w;
             } else {
@@ -265,17 +305,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
               for (int j = 0; j < 4; ++j) if (n + j < k.Cout) yp[j] = o[j];
             }
           }
-          if (k.emit) {                                     // the next conv's split-bf16 operand, transform fused
+          if constexpr (EMIT) {                             // the next conv's split-bf16 operand, transform fused
             float e[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope);
-            const __nv_bfloat162 h01 = __floats2bfloat162_rn(e[0], e[1]), h23 = __floats2bfloat162_rn(e[2], e[3]);
-            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-            const __nv_bfloat162 l01 = __floats2bfloat162_rn(e[0] - f01.x, e[1] - f01.y);
-            const __nv_bfloat162 l23 = __floats2bfloat162_rn(e[2] - f23.x, e[3] - f23.y);
             uint2 hv, lv;
-            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+            split_operand4(e[0], e[1], e[2], e[3], hv, lv);
             __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (n >> 5) * 64 + (n & 31);
             *reinterpret_cast<uint2*>(ep) = hv;
             *reinterpret_cast<uint2*>(ep + 32) = lv;
@@ -287,10 +322,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();   // the peer may still read this CTA's smem / TMEM
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    if constexpr (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -307,8 +345,8 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
     int tap = (int)(r % taps); int co = (int)(r / taps);
     int ci = blk * 32 + j;
     float v = (co < Cout && ci < Cin) ? w32[((long)tap * Cin + ci) * Cout + co] : 0.f;
-    __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16 hi, lo;
+    split_operand(v, hi, lo);
     long o = (long)co * rowlen + ((long)tap * nblk + blk) * 64 + j;
     out[o] = hi;
     out[o + 32] = lo;
@@ -432,8 +470,12 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   k.vec4 = al4(y.sb) && al4(y.sd) && al4(y.sh) && al4(y.sw) && ((uintptr_t)y.p % 16 == 0) &&
            (!e.residual || (al4(e.rs_b) && al4(e.rs_d) && al4(e.rs_h) && al4(e.rs_w) && ((uintptr_t)e.residual % 16 == 0)));
 
-  const int stage_bytes = A_TILE_BYTES + k.BN * 128;
+  const unsigned m_tiles = (unsigned)(k.ntw * k.nth * k.ntd * ntb);
+  // tcgen05 pair mode (cta_group::2): wide N tiles, an even number of M tiles, weights shared by the pair
   const int niter = w.taps() * w.nblk;
+  // (measured: +12% at K = 2304 .. 3834, +2% at K = 4608, a loss for K <= 1152 where the cluster sync is not amortised)
+  const bool pair = L.pair && k.BN >= 128 && (m_tiles % 2 == 0) && w.zrows == 0 && k.npass == 3 && niter >= 64;
+  const int stage_bytes = A_TILE_BYTES + (pair ? k.BN / 2 : k.BN) * 128;
   // accumulator sets: one for the correction products + enough hi*hi sets for chains of <= ~256 MMAs
   {
     const int steps_main = niter * 2;
@@ -446,6 +488,8 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     while (tcols < cols) tcols <<= 1;
     int nsets = tcols / k.BN;
     if (nsets > 16) nsets = 16;
+    if (L.max_sets > 0 && nsets > L.max_sets) nsets = L.max_sets;
+    if (nsets < 2 && k.npass > 1) nsets = 2;               // the scaled correction products need their own accumulator
     if (nsets < 1) nsets = 1;
     const int corr = (k.npass > 1 && nsets > 1) ? 1 : 0;
     int nmain = nsets - corr;
@@ -453,6 +497,11 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     const int chunk = (niter + nmain - 1) / nmain;          // K iterations per hi*hi set
     nmain = (niter + chunk - 1) / chunk;                    // sets actually written
     k.tcols = tcols; k.nsets = corr + nmain; k.chunk = chunk;
+    // The tensor core truncates (rounds toward zero) when it adds an MMA into the fp32 accumulator: measured on B200, a
+    // chain of L MMAs loses ~7e-9 * L of the accumulated magnitude, systematically (mean signed error, tools/tc_check.py).
+    // Errors of that sign add linearly over the ~75 stacked convs, so the epilogue scales the hi*hi sum back.
+    const int chain = chunk * 2 * (corr ? 1 : k.npass);
+    k.acc_scale = 1.0f + L.acc_comp * 1e-10f * (float)chain;
   }
   // thin-N tiles keep the footprint under ~100 KB so two CTAs share an SM (prologue / epilogue overlap)
   const int budget = (k.BN <= 64 && k.tcols <= 256) ? 100 * 1024 : MAX_DYN_SMEM;
@@ -480,7 +529,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     const cuuint64_t rowlen = (cuuint64_t)w.taps() * k.rowA;
     cuuint64_t dims[2] = {rowlen, (cuuint64_t)w.Cout_p};
     cuuint64_t strides[1] = {rowlen * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)k.BN};
+    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? k.BN / 2 : k.BN)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.wtc, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -488,15 +537,31 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   }
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, ConvTcK);
+  static const KernelFn fns[2][2][2] = {
+      {{conv_tc_kernel<false, false, 1>, conv_tc_kernel<false, false, 2>}, {conv_tc_kernel<false, true, 1>, conv_tc_kernel<false, true, 2>}},
+      {{conv_tc_kernel<true, false, 1>, conv_tc_kernel<true, false, 2>}, {conv_tc_kernel<true, true, 1>, conv_tc_kernel<true, true, 2>}}};
   if (!g_attr_set[dev & 63]) {
-    CS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c)
+          CS_CUDA(cudaFuncSetAttribute(fns[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
     g_attr_set[dev & 63] = true;
   }
   if (w.zrows > 0) CS_REQUIRE(bd == 1 && w.zrows % k.BN == 0, CS_ERR_INVALID, "conv_tc: depth-dependent weights need one depth per tile");
-  dim3 grid((unsigned)(k.ntw * k.nth * k.ntd * ntb), (unsigned)((w.zrows > 0 ? w.zrows : w.Cout_p) / k.BN));
+  dim3 grid(m_tiles, (unsigned)((w.zrows > 0 ? w.zrows : w.Cout_p) / k.BN));
   const long M = (long)x.B * g.Do * x.H * x.W;
   ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * w.Cout * w.Cin * w.taps(), 0.0);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, L.stream>>>(tmA, tmB, k);
+  const bool has_res = k.res != nullptr, has_emit = k.emit != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
+  cudaLaunchAttribute attr[1];
+  if (pair) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  CS_CUDA(cudaLaunchKernelEx(&cfg, fns[has_res][has_emit][pair ? 1 : 0], tmA, tmB, k));
   check_launch("conv_tc");
 }
 

@@ -81,7 +81,7 @@ struct cs_ctx {
   int device = 0, max_batch = 1, net_h = 0, net_w = 0, h = 0, w = 0;
   std::string err;
   bool weights_loaded = false, identity_set = false;
-  int conv_impl = 0, use_graph = 0, tc_passes = 3;
+  int conv_impl = 0, use_graph = 0, tc_passes = 3, tc_sets = 0, tc_comp = 72, tc_pair = 1, tc_stacked3 = 1;
   int64_t launches = 0;
   std::vector<void*> owned;        // device allocations owned by the ctx
   size_t owned_bytes = 0;
@@ -112,6 +112,7 @@ void set_identity(cs_ctx* ctx, const float* id_dev, cudaStream_t stream);
 ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt /*[Cout][Cin][taps]*/, const std::vector<float>* bias,
                      int Cout, int Cin, int KD, int KH, int KW);
 void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream);
+void pack_conv3s(cs_ctx* ctx, ConvW& w);                     // conv3s_tc.cu
 void pack_conv7(cs_ctx* ctx, ConvW& w);                      // conv7_tc.cu   // derive the split-bf16 B operand from w32 (conv_tc.cu)
 
 // net.cu : stages on the internal (channels-last) layout

@@ -61,9 +61,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepK k) {
     if (k.o32 && c < k.Cl) k.o32[b * k.ob + d * k.od + h * k.oh + w * k.ow + c] = v;
     if (k.opl) {
       long o = pix * k.prow + (c >> 5) * 64 + (c & 31);
-      __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      k.opl[o] = hi;
-      k.opl[o + 32] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      split_operand(v, k.opl[o], k.opl[o + 32]);
     }
   }
 }
@@ -140,13 +138,8 @@ __global__ void __launch_bounds__(256) prep_kernel_v4(PrepK k) {
     if (k.o32 && c < k.Cl) *reinterpret_cast<float4*>(k.o32 + b * k.ob + d * k.od + h * k.oh + w * k.ow + c) = v;
     if (k.opl) {
       const long o = pix * k.prow + (c >> 5) * 64 + (c & 31);
-      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
-      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
-      const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
       uint2 hv, lv;
-      hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-      lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+      split_operand4(v.x, v.y, v.z, v.w, hv, lv);
       *reinterpret_cast<uint2*>(k.opl + o) = hv;
       *reinterpret_cast<uint2*>(k.opl + o + 32) = lv;
     }
@@ -339,13 +332,8 @@ __global__ void __launch_bounds__(256) adaptive_blend_kernel(const float4* __res
     if (y) y[i] = v;
     if (opl) {                // split-bf16 operand of the next conv: [pix][16 blocks][hi 32 | lo 32]
       const int c = q * 4;
-      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
-      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
-      const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
       uint2 hv, lv;
-      hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-      lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+      split_operand4(v.x, v.y, v.z, v.w, hv, lv);
       __nv_bfloat16* o = opl + pix * 1024 + (c >> 5) * 64 + (c & 31);
       *reinterpret_cast<uint2*>(o) = hv;
       *reinterpret_cast<uint2*>(o + 32) = lv;

@@ -60,7 +60,8 @@ void conv_layer(Net& n, const Prep* prep, const Act& x, const ConvW& w, const Co
     Prep ident;
     if (!prep) { CS_REQUIRE(x.C == w.Cin, CS_ERR_INVALID, "conv_layer: Cin mismatch"); ident = prep_of(x); }
     prep_planes(n.L, prep ? *prep : ident, opd, nullptr);
-    conv_tc(n.L, opd, w, g, e, out);
+    if (n.L.stacked3 && !o.mult && out.D == 16 && conv3s_supported(w, out.H, out.W)) conv3s_tc(n.L, opd, w, e, out);
+    else conv_tc(n.L, opd, w, g, e, out);
     n.A->reset(m);
     return;
   }
@@ -92,6 +93,10 @@ static void conv_from_operand(Net& n, const Opd& opd, const ConvW& w, const Conv
     if (o.emit_affine) { e.emit_scale = o.emit_affine->scale; e.emit_shift = o.emit_affine->shift; }
     e.emit_act = o.emit_act; e.emit_slope = o.emit_slope;
   }
+  if (n.L.stacked3 && !o.mult && out.D == 16 && opd.D == 16 && conv3s_supported(w, opd.H, opd.W)) {
+    conv3s_tc(n.L, opd, w, e, out);                      // 32 -> 32 3x3x3 volume conv: depth-stacked kernel
+    return;
+  }
   conv_tc(n.L, opd, w, g, e, out);
 }
 
@@ -120,7 +125,7 @@ static void resblock3d(Net& n, const ResBlock3dW& w, float* vol, int B, int h, i
 // `t` never exists in fp32 and the volume is read once per block (as the residual).
 struct PreActBlock { const Affine* bn1; const ConvW* conv1; const ConvW* conv2; };
 
-static void preact_chain_tc(Net& n, const PreActBlock* blk, int nb, Act x, int act, float slope) {
+static void preact_chain_tc(Net& n, const PreActBlock* blk, int nb, Act x, int act, float slope, bool emit_from_conv2) {
   size_t m = n.A->mark();
   Opd a = conv_tc_alloc_operand(*n.A, *blk[0].conv1, x);
   Opd t = conv_tc_alloc_operand(*n.A, *blk[0].conv2, x);
@@ -134,9 +139,17 @@ static void preact_chain_tc(Net& n, const PreActBlock* blk, int nb, Act x, int a
     o1.emit = &t;
     conv_from_operand(n, a, *blk[i].conv1, o1, none);
     ConvOpts o2; o2.residual = &x;
-    if (i + 1 < nb) { o2.emit = &b; o2.emit_affine = blk[i + 1].bn1; o2.emit_act = act; o2.emit_slope = slope; }
+    const bool fuse = emit_from_conv2 && i + 1 < nb;
+    if (fuse) { o2.emit = &b; o2.emit_affine = blk[i + 1].bn1; o2.emit_act = act; o2.emit_slope = slope; }
     conv_from_operand(n, t, *blk[i].conv2, o2, x);       // x = conv2(.) + x, in place
-    Opd tmp = a; a = b; b = tmp;
+    if (fuse) {
+      Opd tmp = a; a = b; b = tmp;
+    } else if (i + 1 < nb) {
+      // wide tiles: residual + fp32 + operand in one (non-overlapped) epilogue costs more than a bandwidth-bound prep
+      Prep pn = prep_of(x);
+      pn.norm = NORM_AFFINE_C; pn.scale = blk[i + 1].bn1->scale; pn.shift = blk[i + 1].bn1->shift; pn.act = act; pn.slope = slope;
+      prep_planes(n.L, pn, a, nullptr);
+    }
   }
   n.A->reset(m);
 }
@@ -146,7 +159,7 @@ static void resblock3d_run(Net& n, const ResBlock3dW* w, int nb, float* vol, int
   if (use_tc(n, w[0].conv1, x)) {
     PreActBlock blk[8];
     for (int i = 0; i < nb; ++i) blk[i] = PreActBlock{&w[i].bn1, &w[i].conv1, &w[i].conv2};
-    preact_chain_tc(n, blk, nb, x, ACT_RELU, 0.f);
+    preact_chain_tc(n, blk, nb, x, ACT_RELU, 0.f, true);
   } else {
     for (int i = 0; i < nb; ++i) resblock3d(n, w[i], vol, B, h, wd);
   }
@@ -399,7 +412,7 @@ void run_refine(Net& n, const float* vol_in, int B, float* vol_out) {
     if (use_tc(n, W.r_res2[0].conv1, x2)) {
       PreActBlock blk[3];
       for (int i = 0; i < 3; ++i) blk[i] = PreActBlock{&W.r_res2[i].bn1, &W.r_res2[i].conv1, &W.r_res2[i].conv2};
-      preact_chain_tc(n, blk, 3, x2, ACT_LRELU, 0.01f);
+      preact_chain_tc(n, blk, 3, x2, ACT_LRELU, 0.01f, false);
     } else {
       for (int i = 0; i < 3; ++i) resblock2d(n, W.r_res2[i], vol_out, B, h, w);
     }

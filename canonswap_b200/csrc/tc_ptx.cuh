@@ -52,6 +52,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
                ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+// cta_group::2 variants: issued by both CTAs of a pair, the transaction bytes land on the LEADER CTA's barrier
+// (shared::cluster address with the peer bit cleared, as CUTLASS' SM100_TMA_2SM_LOAD does).
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
+                                                int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -87,11 +107,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // All the MMAs of one pipeline stage (one 32-channel K block) + the commit that frees the stage, issued
 // by one elected lane of a converged warp in a single asm block (the issue thread is the critical path
 // of the kernel: no divergence bookkeeping, no per-MMA descriptor rebuild).
-//   hi*hi -> [d_main] (first MMA accumulates iff acc_main), lo*hi and hi*lo -> [d_corr] (iff acc_corr)
+//   hi*hi -> [d_main] (first MMA accumulates iff acc_main), lo*hi and hi*lo -> [d_corr] (iff acc_corr).
+// (ilh / ihl are the instruction descriptors of the lo*hi / hi*lo MMAs: same as hi*hi, both halves are bf16.)
 #define CS_MMA_HEAD                                   \
   "{\n\t"                                             \
   ".reg .pred pe, pm, pc, pt;\n\t"                    \
   ".reg .b64 a2, a4, a6, b2, b4, b6;\n\t"             \
+  ".reg .b32 ilh, ihl;\n\t"                           \
+  "mov.b32 ilh, %4;\n\t"                              \
+  "mov.b32 ihl, %4;\n\t"                              \
   "elect.sync _|pe, 0xffffffff;\n\t"                  \
   "setp.ne.b32 pm, %5, 0;\n\t"                        \
   "setp.ne.b32 pc, %6, 0;\n\t"                        \
@@ -102,38 +126,53 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   "add.s64 b2, %3, 2;\n\t"                            \
   "add.s64 b4, %3, 4;\n\t"                            \
   "add.s64 b6, %3, 6;\n\t"
-#define CS_MMA(D, A, B, P) "@pe tcgen05.mma.cta_group::1.kind::f16 [" D "], " A ", " B ", %4, " P ";\n\t"
+#define CS_MMA(D, A, B, I, P) "@pe tcgen05.mma.cta_group::1.kind::f16 [" D "], " A ", " B ", " I ", " P ";\n\t"
 #define CS_MMA_TAIL "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
+// pair variants: one MMA spans both CTAs (M = 256), the commit arrives on the barrier of BOTH CTAs
+#define CS_MMA2(D, A, B, I, P) "@pe tcgen05.mma.cta_group::2.kind::f16 [" D "], " A ", " B ", " I ", " P ";\n\t"
+#define CS_MMA2_TAIL                                                                                         \
+  "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], mk;\n\t}"
+#define CS_MMA2_HEAD CS_MMA_HEAD ".reg .b16 mk;\n\tmov.b16 mk, 3;\n\t"
 #define CS_MMA_OPS                                                                                                     \
   ::"r"(d_main), "r"(d_corr), "l"(ad), "l"(bd), "r"(idesc), "r"(acc_main), "r"(acc_corr), "r"(bar) : "memory"
 
-template <int NPASS, int KSTEPS>
+template <int NPASS, int KSTEPS, int CTAS = 1>
 __device__ __forceinline__ void mma_stage(uint32_t d_main, uint32_t d_corr, uint64_t ad, uint64_t bd, uint32_t idesc,
                                           uint32_t acc_main, uint32_t acc_corr, uint32_t bar) {
-  if constexpr (NPASS == 3 && KSTEPS == 2) {
-    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%0", "a2", "b2", "pt")      // hi*hi
-                 CS_MMA("%1", "a4", "%3", "pc") CS_MMA("%1", "a6", "b2", "pt")                  // lo*hi
-                 CS_MMA("%1", "%2", "b4", "pt") CS_MMA("%1", "a2", "b6", "pt") CS_MMA_TAIL CS_MMA_OPS);
+  if constexpr (CTAS == 2) {
+    static_assert(NPASS == 3, "pair MMAs are built for the 3-pass path only");
+    if constexpr (KSTEPS == 2) {
+      asm volatile(CS_MMA2_HEAD CS_MMA2("%0", "%2", "%3", "%4", "pm") CS_MMA2("%0", "a2", "b2", "%4", "pt")
+                   CS_MMA2("%1", "a4", "%3", "ilh", "pc") CS_MMA2("%1", "a6", "b2", "ilh", "pt")
+                   CS_MMA2("%1", "%2", "b4", "ihl", "pt") CS_MMA2("%1", "a2", "b6", "ihl", "pt") CS_MMA2_TAIL CS_MMA_OPS);
+    } else {
+      asm volatile(CS_MMA2_HEAD CS_MMA2("%0", "%2", "%3", "%4", "pm") CS_MMA2("%1", "a4", "%3", "ilh", "pc") CS_MMA2("%1", "%2", "b4", "ihl", "pt")
+                       CS_MMA2_TAIL CS_MMA_OPS);
+    }
+  } else if constexpr (NPASS == 3 && KSTEPS == 2) {
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "%4", "pm") CS_MMA("%0", "a2", "b2", "%4", "pt")      // hi*hi
+                 CS_MMA("%1", "a4", "%3", "ilh", "pc") CS_MMA("%1", "a6", "b2", "ilh", "pt")                  // lo*hi
+                 CS_MMA("%1", "%2", "b4", "ihl", "pt") CS_MMA("%1", "a2", "b6", "ihl", "pt") CS_MMA_TAIL CS_MMA_OPS);
   } else if constexpr (NPASS == 3 && KSTEPS == 1) {
-    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%1", "a4", "%3", "pc") CS_MMA("%1", "%2", "b4", "pt")
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "%4", "pm") CS_MMA("%1", "a4", "%3", "ilh", "pc") CS_MMA("%1", "%2", "b4", "ihl", "pt")
                      CS_MMA_TAIL CS_MMA_OPS);
   } else if constexpr (NPASS == 2 && KSTEPS == 2) {
-    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%0", "a2", "b2", "pt") CS_MMA("%1", "a4", "%3", "pc")
-                     CS_MMA("%1", "a6", "b2", "pt") CS_MMA_TAIL CS_MMA_OPS);
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "%4", "pm") CS_MMA("%0", "a2", "b2", "%4", "pt") CS_MMA("%1", "a4", "%3", "ilh", "pc")
+                     CS_MMA("%1", "a6", "b2", "ilh", "pt") CS_MMA_TAIL CS_MMA_OPS);
   } else if constexpr (NPASS == 2 && KSTEPS == 1) {
-    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%1", "a4", "%3", "pc") CS_MMA_TAIL CS_MMA_OPS);
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "%4", "pm") CS_MMA("%1", "a4", "%3", "ilh", "pc") CS_MMA_TAIL CS_MMA_OPS);
   } else if constexpr (NPASS == 1 && KSTEPS == 2) {
-    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA("%0", "a2", "b2", "pt") CS_MMA_TAIL CS_MMA_OPS);
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "%4", "pm") CS_MMA("%0", "a2", "b2", "%4", "pt") CS_MMA_TAIL CS_MMA_OPS);
   } else {
-    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "pm") CS_MMA_TAIL CS_MMA_OPS);
+    asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "%4", "pm") CS_MMA_TAIL CS_MMA_OPS);
   }
 }
 
-template <int NPASS>
+template <int NPASS, int CTAS = 1>
 __device__ __forceinline__ void mma_stage_k(int ksteps, uint32_t d_main, uint32_t d_corr, uint64_t ad, uint64_t bd,
                                             uint32_t idesc, uint32_t acc_main, uint32_t acc_corr, uint32_t bar) {
-  if (ksteps == 2) mma_stage<NPASS, 2>(d_main, d_corr, ad, bd, idesc, acc_main, acc_corr, bar);
-  else mma_stage<NPASS, 1>(d_main, d_corr, ad, bd, idesc, acc_main, acc_corr, bar);
+  if (ksteps == 2) mma_stage<NPASS, 2, CTAS>(d_main, d_corr, ad, bd, idesc, acc_main, acc_corr, bar);
+  else mma_stage<NPASS, 1, CTAS>(d_main, d_corr, ad, bd, idesc, acc_main, acc_corr, bar);
 }
 
 

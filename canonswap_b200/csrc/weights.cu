@@ -151,6 +151,8 @@ ResBlock3dW read_resblock3d(cs_ctx* ctx, const Table& t, const std::string& p) {
   fold_bn_post(c1, read_bn(t, p + ".norm2", 32));
   r.conv1 = pack(ctx, c1);
   r.conv2 = pack(ctx, read_conv(t, p + ".conv2", 32, 32, 3, 3, 3));
+  pack_conv3s(ctx, r.conv1);
+  pack_conv3s(ctx, r.conv2);
   return r;
 }
 
@@ -158,6 +160,8 @@ GnResBlockW read_gn_resblock(cs_ctx* ctx, const Table& t, const std::string& p) 
   GnResBlockW r;                                                 // reference util.py:515-544
   r.conv1 = pack(ctx, read_conv(t, p + ".conv1", 32, 32, 3, 3, 3));
   r.conv2 = pack(ctx, read_conv(t, p + ".conv2", 32, 32, 3, 3, 3));
+  pack_conv3s(ctx, r.conv1);
+  pack_conv3s(ctx, r.conv2);
   r.gn1.scale = upload(ctx, t.f32(p + ".gn1.weight", 32), 32);
   r.gn1.shift = upload(ctx, t.f32(p + ".gn1.bias", 32), 32);
   r.gn2.scale = upload(ctx, t.f32(p + ".gn2.weight", 32), 32);
@@ -293,8 +297,8 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
         for (int tp = 0; tp < 49; ++tp)
           for (int ci = 0; ci < HG_OUT; ++ci) {
             const float v = oc.w[(long)ci * (16 * 49) + z * 49 + tp];
-            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            __nv_bfloat16 hi, lo;
+            split_operand(v, hi, lo);
             const long o = ((long)z * 64 + tp) * rowlen + (ci >> 5) * 64 + (ci & 31);
             hw[o] = hi; hw[o + 32] = lo;
           }

@@ -96,6 +96,23 @@ def test_conv7_depth_stacked_matches_torch(eng, case):
     assert (y - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("case", [(1, 16, 8), (2, 24, 40), (2, 32, 32)])
+@pytest.mark.parametrize("act", [0, 2])
+def test_conv3_depth_stacked_matches_torch(eng, case, act):
+    """The dedicated 32->32 3x3x3 volume-conv kernel (depth-stacked N, weights resident in smem) against fp64 torch."""
+    B, H, W = case
+    g = torch.Generator(device="cuda").manual_seed(14)
+    x = torch.randn(B, 16, H, W, 32, device="cuda", generator=g)
+    w = torch.randn(32, 32, 3, 3, 3, device="cuda", generator=g) / (32 * 27) ** 0.5
+    b = torch.randn(32, device="cuda", generator=g)
+    y = eng.test_conv(x, w, b, (1, 1, 1), act=act, slope=0.2, impl=4)
+    ref = _ref_conv(x, w, b, (1, 1, 1))
+    if act == 2:
+        ref = F.leaky_relu(ref, 0.2)
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
+
+
 def test_conv_tcgen05_epilogue_residual_mult_strided(eng):
     """Engine-level check of the fused epilogue is in test_gpu_stages (warp_out: x occlusion, resblocks:
     + residual); here: the same conv through both implementations must agree to fp32 round-off."""

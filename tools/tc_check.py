@@ -35,6 +35,10 @@ CASES = [
     (8, 1, 256, 256, 64, 64, (1, 3, 3), (0, 1, 1), 1),
     (8, 1, 256, 256, 128, 64, (1, 3, 3), (0, 1, 1), 1),
     (8, 1, 128, 128, 256, 256, (1, 3, 3), (0, 1, 1), 1),
+    # the depth-stacked 32->32 3x3x3 kernel (impl 4)
+    (1, 16, 16, 8, 32, 32, (3, 3, 3), (1, 1, 1), 5),
+    (2, 16, 24, 40, 32, 32, (3, 3, 3), (1, 1, 1), 5),
+    (8, 16, 64, 64, 32, 32, (3, 3, 3), (1, 1, 1), 6),
     # the depth-stacked 7x7x7 kernel (impl 3)
     (1, 16, 16, 8, 142, 22, (7, 7, 7), (3, 3, 3), 3),
     (2, 16, 32, 32, 142, 22, (7, 7, 7), (3, 3, 3), 3),
@@ -45,18 +49,22 @@ CASES = [
 
 
 def main():
-    passes = [int(a) for a in sys.argv[1:]] or [3]
+    passes = [3]
+    comps = [int(a) for a in sys.argv[1:] if not a.startswith("nopair")] or [72]
+    pair = 0 if "nopair" in sys.argv[1:] else 1
     eng = Engine(None, net_hw=(128, 128), max_batch=1, device=0)
     g = torch.Generator(device="cuda").manual_seed(7)
-    for np_ in passes:
-        eng.set_option(_lib.CS_OPT_TC_PASSES, np_)
+    for comp in comps:
+      for np_ in passes:
+        eng.set_option(_lib.CS_OPT_TC_COMP, comp)
+        eng.set_option(_lib.CS_OPT_TC_PAIR, pair)
         for (B, D, H, Wd, Cin, Cout, k, pad, timed) in CASES:
             x = torch.randn(B, D, H, Wd, Cin, device="cuda", generator=g)
             w = torch.randn(Cout, Cin, *k, device="cuda", generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5
             b = torch.randn(Cout, device="cuda", generator=g)
-            tag = f"np={np_} B{B} D{D} {H}x{Wd} {Cin}->{Cout} k{k}"
-            impl, act = (3, 0) if timed >= 3 else (2, 2)
-            timed = timed in (1, 4)
+            tag = f"comp={comp} pair={pair} B{B} D{D} {H}x{Wd} {Cin}->{Cout} k{k}"
+            impl, act = (4, 2) if timed >= 5 else ((3, 0) if timed >= 3 else (2, 2))
+            timed = timed in (1, 4, 6)
             try:
                 eng.profile(True)
                 y = eng.test_conv(x, w, b, pad, act=act, slope=0.2, impl=impl)
@@ -73,6 +81,10 @@ def main():
                     ref = F.conv3d(xr.double(), w.double(), b.double(), padding=pad).permute(0, 2, 3, 4, 1).float()
                 if act == 2:
                     ref = F.leaky_relu(ref, 0.2)
+                big = ref.abs() > 1.0
+                bias = (((y - ref) * ref.sign())[big].double().mean() / ref[big].abs().double().mean()).item() if big.any() else 0.0
+                rms = ((y - ref)[big].double().pow(2).mean().sqrt() / ref[big].abs().double().mean()).item() if big.any() else 0.0
+                tag += f" bias={bias:+.2e} rms={rms:.2e}"
                 err = (y - ref).abs().max().item()
                 scale = ref.abs().max().item()
                 ms = fam["ms"] / max(1, fam["launches"])
