@@ -221,6 +221,7 @@ void cs_destroy(cs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  ctx->drop_graphs();
   for (void* p : ctx->owned) cudaFree(p);
   delete ctx;
 }
@@ -229,6 +230,9 @@ const char* cs_last_error(const cs_ctx* ctx) { return ctx ? ctx->err.c_str() : g
 
 int cs_set_option(cs_ctx* ctx, int option, int value) {
   if (!ctx) return fail(nullptr, CS_ERR_INVALID, "null context");
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->drop_graphs();                                       // captured graphs bake the kernel selection in
   switch (option) {
     case CS_OPT_CONV_IMPL:
       if (value < 0 || value > 1) return fail(ctx, CS_ERR_INVALID, "CS_OPT_CONV_IMPL: value must be 0 or 1");
@@ -349,7 +353,63 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
   CS_REQUIRE(ctx->identity_set, CS_ERR_STATE, "cs_frame before cs_set_identity");
   Net n = make_net(ctx, stream, false);
   ctx->arena.reset(0);
-  body_frame(n, frames, kp_t, kp_can, out_f32, out_u8, B, flags);
+  if (!ctx->use_graph || ctx->prof.on) {
+    body_frame(n, frames, kp_t, kp_can, out_f32, out_u8, B, flags);
+  } else {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t npix = (size_t)B * ctx->net_h * ctx->net_w;
+    const size_t in_bytes = (flags & CS_FRAME_IN_U8_HWC) ? npix * 3 : npix * 3 * sizeof(float);
+    const size_t kp_bytes = (size_t)B * NUM_KP * 3 * sizeof(float);
+    const size_t o32_bytes = npix * 4 * 3 * sizeof(float), ou8_bytes = npix * 4 * 3;
+    if (!ctx->g_frames) {                                   // staging buffers sized for max_batch
+      const size_t mp = (size_t)ctx->max_batch * ctx->net_h * ctx->net_w;
+      ctx->g_frames = ctx->dmalloc(mp * 3 * sizeof(float));
+      ctx->g_kpt = static_cast<float*>(ctx->dmalloc((size_t)ctx->max_batch * NUM_KP * 3 * sizeof(float)));
+      ctx->g_kpc = static_cast<float*>(ctx->dmalloc((size_t)ctx->max_batch * NUM_KP * 3 * sizeof(float)));
+      ctx->g_out32 = static_cast<float*>(ctx->dmalloc(mp * 4 * 3 * sizeof(float)));
+      ctx->g_outu8 = static_cast<uint8_t*>(ctx->dmalloc(mp * 4 * 3));
+    }
+    cs_ctx::FrameGraph* fg = nullptr;
+    for (auto& g : ctx->graphs)
+      if (g.B == B && g.flags == flags && g.f32 == (out_f32 != nullptr) && g.u8 == (out_u8 != nullptr)) fg = &g;
+    if (!fg) {
+      ctx->graphs.emplace_back();
+      fg = &ctx->graphs.back();
+      fg->B = B; fg->flags = flags; fg->f32 = out_f32 != nullptr; fg->u8 = out_u8 != nullptr;
+    }
+    if (fg->seen == 0) {
+      // first call of this shape runs eagerly (lazy one-time initialisation must not happen under capture)
+      fg->seen = 1;
+      body_frame(n, frames, kp_t, kp_can, out_f32, out_u8, B, flags);
+    } else {
+      if (!fg->exec) {
+        const int64_t l0 = ctx->launches;
+        cudaGraph_t graph = nullptr;
+        CS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+          body_frame(n, ctx->g_frames, ctx->g_kpt, ctx->g_kpc, out_f32 ? ctx->g_out32 : nullptr, out_u8 ? ctx->g_outu8 : nullptr, B,
+                     flags);
+        } catch (...) {
+          cudaStreamEndCapture(st, &graph);
+          if (graph) cudaGraphDestroy(graph);
+          throw;
+        }
+        CS_CUDA(cudaStreamEndCapture(st, &graph));
+        cudaError_t ie = cudaGraphInstantiate(&fg->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { fg->exec = nullptr; throw cs::Error(CS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+        fg->launches = ctx->launches - l0;
+        ctx->launches = l0;
+      }
+      CS_CUDA(cudaMemcpyAsync(ctx->g_frames, frames, in_bytes, cudaMemcpyDeviceToDevice, st));
+      CS_CUDA(cudaMemcpyAsync(ctx->g_kpt, kp_t, kp_bytes, cudaMemcpyDeviceToDevice, st));
+      CS_CUDA(cudaMemcpyAsync(ctx->g_kpc, kp_can, kp_bytes, cudaMemcpyDeviceToDevice, st));
+      CS_CUDA(cudaGraphLaunch(fg->exec, st));
+      if (out_f32) CS_CUDA(cudaMemcpyAsync(out_f32, ctx->g_out32, o32_bytes, cudaMemcpyDeviceToDevice, st));
+      if (out_u8) CS_CUDA(cudaMemcpyAsync(out_u8, ctx->g_outu8, ou8_bytes, cudaMemcpyDeviceToDevice, st));
+      ctx->launches += fg->launches;
+    }
+  }
   CS_API_END(ctx)
 }
 

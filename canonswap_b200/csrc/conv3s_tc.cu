@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3s_tc_kernel(const __grid_cons
     for (int z = 0; z < 16; ++z) {
       const int dlo = max(z - 1, 0), dhi = min(z + 1, 15);
       const uint32_t N = (uint32_t)(dhi - dlo + 1) * 32u;
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | IDESC_AB_FMT | ((N >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t d_acc = tmem_base + (uint32_t)(dlo * 32);
       const uint32_t brow = (uint32_t)(dlo - (z - 1)) * 32u * 128u;  // skip the depth-tap slot of d = -1
       for (int tap = 0; tap < 9; ++tap) {
@@ -212,14 +212,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv3s_tc_kernel(const __grid_cons
 
 // w32 [tap = (kd*3+kh)*3+kw][32][32] fp32 -> rows ((kh*3+kw)*3 + j)*32 + co with kd = 2 - j (ascending output depth
 // d = z - 1 + j), 64 columns [hi 32 | lo 32]
-__global__ void __launch_bounds__(256) pack_conv3s_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(256) pack_conv3s_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ out, float wmul) {
   const int total = 9 * 3 * 32 * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ci = i & 31; int r = i >> 5;
     const int co = r & 31; r >>= 5;
     const int j = r % 3; const int khw = r / 3;
     const int tap = (2 - j) * 9 + khw;
-    const float v = w32[((long)tap * 32 + ci) * 32 + co];
+    const float v = w32[((long)tap * 32 + ci) * 32 + co] * wmul;
     __nv_bfloat16 hi, lo;
     split_operand(v, hi, lo);
     const long o = (((long)khw * 3 + j) * 32 + co) * 64 + ci;
@@ -239,7 +239,7 @@ bool conv3s_supported(const ConvW& w, int H, int W) {
 void pack_conv3s(cs_ctx* ctx, ConvW& w) {
   if (!(w.KD == 3 && w.KH == 3 && w.KW == 3 && w.Cin == 32 && w.Cout == 32 && w.w32)) return;
   if (!w.w3s) w.w3s = static_cast<__nv_bfloat16*>(ctx->dmalloc((size_t)9 * 96 * 64 * sizeof(__nv_bfloat16)));
-  pack_conv3s_kernel<<<108, 256>>>(w.w32, w.w3s);
+  pack_conv3s_kernel<<<108, 256>>>(w.w32, w.w3s, w.wmul);
   check_launch("pack_conv3s");
 }
 
@@ -270,7 +270,7 @@ void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& 
     CS_REQUIRE(e.emit_nblk == 1, CS_ERR_INVALID, "conv3s_tc: emitted operand must have 32 channels");
     k.emit = e.emit; k.escale = e.emit_scale; k.eshift = e.emit_shift; k.eact = e.emit_act; k.eslope = e.emit_slope;
   }
-  k.acc_scale = 1.0f + L.acc_comp * 1e-10f * 162.f;
+  k.acc_scale = (1.0f + L.acc_comp * 1e-10f * 162.f) / w.wmul;     // truncation compensation and the weight pre-scale
 
   auto enc = encode_fn();
   CUtensorMap tmA, tmB;

@@ -25,9 +25,14 @@ namespace {
 constexpr int C7_COUT_P = 32;                    // 22 -> 32 columns per output depth
 constexpr int C7_GROUP = 8;                      // output depths per CTA
 constexpr int C7_BROWS = 7 * C7_COUT_P;          // 224 B rows per stage
-constexpr int C7_STAGE_BYTES = A_TILE_BYTES + C7_BROWS * 128;
-constexpr int C7_STAGES = 4;
-constexpr int C7_SMEM = C7_STAGES * C7_STAGE_BYTES + STG_BYTES + 1024 + 16 * C7_STAGES + 32;
+// CTAS = 1: 4 stages of A (16 KB) + B (28 KB).  CTAS = 2 (tcgen05 pair, two pixel tiles share the weights): each CTA holds
+// half of the B rows, 6 stages of 16 + 14 KB.
+template <int CTAS> struct C7Cfg {
+  static constexpr int BROWS = C7_BROWS / CTAS;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + BROWS * 128;
+  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 16 * STAGES + 32;
+};
 
 struct Conv7K {
   int B, H, W;                     // D = 16
@@ -37,10 +42,16 @@ struct Conv7K {
   long part_stride;                // elements between partial tensors
   int ldo;                         // channel stride of a partial (24)
   float acc_scale;                 // round-toward-zero compensation of the hi*hi chain (see conv_tc.cu)
+  float out_scale;                 // 1 / ConvW::wmul
 };
 
+template <int CTAS>
 __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, Conv7K k) {
+  constexpr int C7_STAGES = C7Cfg<CTAS>::STAGES;
+  constexpr int C7_STAGE_BYTES = C7Cfg<CTAS>::STAGE_BYTES;
+  uint32_t cta_rank = 0;
+  if constexpr (CTAS == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -66,8 +77,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -81,7 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
     tc_st_wait();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();    // barriers + zeroed accumulators of BOTH CTAs
   tc_fence_after();
 
   if (warp == 0) {
@@ -90,27 +106,35 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
       int s = 0; uint32_t ph = 0;
       for (int z = zlo; z <= zhi; ++z) {
         const int jlo = max(0, C7_GROUP * g - z + 3);          // first depth tap slot whose output is in the group
+        const int nd = min(z + 3, C7_GROUP * g + C7_GROUP - 1) - max(z - 3, C7_GROUP * g) + 1;   // output depths of this slice
         for (int kw = 0; kw < 7; ++kw) {
-          const int brow = ((kh * 7 + kw) * 7 + jlo) * C7_COUT_P;
+          // pair mode: this CTA supplies rows [rank * N/2, (rank+1) * N/2) of the N = 32 * nd row B operand
+          const int brow = ((kh * 7 + kw) * 7 + jlo) * C7_COUT_P + (CTAS == 2 ? (int)cta_rank * nd * (C7_COUT_P / 2) : 0);
           for (int blk = 0; blk < k.nblk; ++blk) {
             const uint32_t fb = bars + 8u * s;
             mbar_wait(fb + 8u * C7_STAGES, ph ^ 1u);
-            mbar_expect_tx(fb, C7_STAGE_BYTES);
             const uint32_t sa = base + (uint32_t)s * C7_STAGE_BYTES;
-            tma_load_5d(sa, &tmA, fb, blk * 64, w0 + kw - 3, h0 + kh - 3, z, b);
-            tma_load_2d(sa + A_TILE_BYTES, &tmB, fb, blk * 64, brow);
+            if constexpr (CTAS == 2) {
+              if (cta_rank == 0) mbar_expect_tx(fb, 2u * C7_STAGE_BYTES);
+              tma_load_5d_2sm(sa, &tmA, fb, blk * 64, w0 + kw - 3, h0 + kh - 3, z, b);
+              tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, fb, blk * 64, brow);
+            } else {
+              mbar_expect_tx(fb, C7_STAGE_BYTES);
+              tma_load_5d(sa, &tmA, fb, blk * 64, w0 + kw - 3, h0 + kh - 3, z, b);
+              tma_load_2d(sa + A_TILE_BYTES, &tmB, fb, blk * 64, brow);
+            }
             if (++s == C7_STAGES) { s = 0; ph ^= 1u; }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (converged warp, elected lane inside the asm block) =====
+  } else if (warp == 1 && (CTAS == 1 || cta_rank == 0)) {
+    // ===== MMA issuer (converged warp, elected lane inside the asm block; the pair's leader only) =====
     int s = 0; uint32_t ph = 0;
     for (int z = zlo; z <= zhi; ++z) {
       const int dlo = max(z - 3, C7_GROUP * g), dhi = min(z + 3, C7_GROUP * g + C7_GROUP - 1);
       const uint32_t N = (uint32_t)(dhi - dlo + 1) * C7_COUT_P;
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | IDESC_AB_FMT | ((N >> 3) << 17) | (((128u * CTAS) >> 4) << 24);
       const uint32_t d_main = tmem_base + (uint32_t)((dlo - C7_GROUP * g) * C7_COUT_P);
       const uint32_t d_corr = d_main + 256u;
       for (int kw = 0; kw < 7; ++kw) {
@@ -120,18 +144,26 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)s * C7_STAGE_BYTES;
           const int ksteps = (blk == k.nblk - 1) ? k.last_ksteps : 2;
-          mma_stage_k<3>(ksteps, d_main, d_corr, umma_desc(sa), umma_desc(sa + A_TILE_BYTES), idesc, 1u, 1u,
-                         fb + 8u * C7_STAGES);
+          mma_stage_k<3, CTAS>(ksteps, d_main, d_corr, umma_desc(sa), umma_desc(sa + A_TILE_BYTES), idesc, 1u, 1u,
+                               fb + 8u * C7_STAGES);
           if (++s == C7_STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
-    asm volatile(
-        "{\n\t.reg .pred pe;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-        ::"r"(tmem_full) : "memory");
-  } else {
+    if constexpr (CTAS == 2) {
+      asm volatile(
+          "{\n\t.reg .pred pe;\n\t.reg .b16 mk;\n\tmov.b16 mk, 3;\n\t"
+          "elect.sync _|pe, 0xffffffff;\n\t"
+          "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], mk;\n\t}"
+          ::"r"(tmem_full) : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred pe;\n\t"
+          "elect.sync _|pe, 0xffffffff;\n\t"
+          "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+          ::"r"(tmem_full) : "memory");
+    }
+  } else if (warp >= 2) {
     // ===== epilogue: per output depth, 32 columns (main + corr) -> smem tile -> coalesced partial rows =====
     const int q = warp & 3;
     float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + q * 32 * STG_LD;
@@ -160,10 +192,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
         float4* dst = reinterpret_cast<float4*>(tile + lane * STG_LD + 16 * half);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          dst[j] = make_float4(fmaf(__uint_as_float(v[4 * j]), k.acc_scale, __uint_as_float(u[4 * j]) * LO_UNSCALE),
-                               fmaf(__uint_as_float(v[4 * j + 1]), k.acc_scale, __uint_as_float(u[4 * j + 1]) * LO_UNSCALE),
-                               fmaf(__uint_as_float(v[4 * j + 2]), k.acc_scale, __uint_as_float(u[4 * j + 2]) * LO_UNSCALE),
-                               fmaf(__uint_as_float(v[4 * j + 3]), k.acc_scale, __uint_as_float(u[4 * j + 3]) * LO_UNSCALE));
+          dst[j] = make_float4(fmaf(__uint_as_float(v[4 * j]), k.acc_scale, __uint_as_float(u[4 * j])) * k.out_scale,
+                               fmaf(__uint_as_float(v[4 * j + 1]), k.acc_scale, __uint_as_float(u[4 * j + 1])) * k.out_scale,
+                               fmaf(__uint_as_float(v[4 * j + 2]), k.acc_scale, __uint_as_float(u[4 * j + 2])) * k.out_scale,
+                               fmaf(__uint_as_float(v[4 * j + 3]), k.acc_scale, __uint_as_float(u[4 * j + 3])) * k.out_scale);
       }
       __syncwarp();
       if (c4 < k.ldo) {
@@ -179,17 +211,20 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if constexpr (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
 // w32 [tap = (kd*7+kh)*7+kw][Cin][Cout] fp32 -> rows ((kh*7+kw)*7 + j)*32 + co, j <-> kd = 6 - j (ascending output
 // depth d = z - 3 + j), columns [blk][hi 32 | lo 32]
 __global__ void __launch_bounds__(256) pack_conv7_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ out, int Cin,
-                                                         int Cout, int nblk) {
+                                                         int Cout, int nblk, float wmul) {
   const long total = 49L * 7 * C7_COUT_P * nblk * 32;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int e = (int)(i & 31); long r = i >> 5;
@@ -198,7 +233,7 @@ __global__ void __launch_bounds__(256) pack_conv7_kernel(const float* __restrict
     const int j = (int)(r % 7); const int khw = (int)(r / 7);       // khw = kh*7 + kw
     const int kd = 6 - j, ci = blk * 32 + e;
     const int tap = kd * 49 + khw;
-    const float v = (co < Cout && ci < Cin) ? w32[((long)tap * Cin + ci) * Cout + co] : 0.f;
+    const float v = (co < Cout && ci < Cin) ? w32[((long)tap * Cin + ci) * Cout + co] * wmul : 0.f;
     __nv_bfloat16 hi, lo;
     split_operand(v, hi, lo);
     const long row = ((long)khw * 7 + j) * C7_COUT_P + co;
@@ -245,7 +280,7 @@ void pack_conv7(cs_ctx* ctx, ConvW& w) {
   const int nblk = (w.Cin + 31) / 32;
   const size_t n = (size_t)49 * 7 * C7_COUT_P * nblk * 64;
   if (!w.w7) w.w7 = static_cast<__nv_bfloat16*>(ctx->dmalloc(n * sizeof(__nv_bfloat16)));
-  pack_conv7_kernel<<<148 * 8, 256>>>(w.w32, w.w7, w.Cin, w.Cout, nblk);
+  pack_conv7_kernel<<<148 * 8, 256>>>(w.w32, w.w7, w.Cin, w.Cout, nblk, w.wmul);
   check_launch("pack_conv7");
 }
 
@@ -268,8 +303,11 @@ void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* s
   k.ldo = (int)out.sw;
   k.parts = scratch;
   k.part_stride = (long)x.B * 16 * x.H * x.W * k.ldo;
+  k.out_scale = 1.0f / w.wmul;
   k.acc_scale = 1.0f + L.acc_comp * 1e-10f * (float)(7 * 7 * (2 * (x.nblk - 1) + k.last_ksteps));   // chain: 7 z x 7 kw x K steps
 
+  const unsigned gx = (unsigned)(k.ntw * k.nth * x.B);
+  const bool pair = L.pair && (gx % 2 == 0);
   auto enc = encode_fn();
   CUtensorMap tmA, tmB;
   const int rowA = x.nblk * 64;
@@ -286,7 +324,7 @@ void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* s
   {
     cuuint64_t dims[2] = {(cuuint64_t)rowA, (cuuint64_t)(49 * C7_BROWS)};
     cuuint64_t strides[1] = {(cuuint64_t)rowA * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)C7_BROWS};
+    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? C7_BROWS / 2 : C7_BROWS)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w7, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -295,15 +333,25 @@ void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* s
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
   if (!g_attr7[dev & 63]) {
-    CS_CUDA(cudaFuncSetAttribute(conv7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C7_SMEM));
+    CS_CUDA(cudaFuncSetAttribute(conv7_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C7Cfg<1>::SMEM));
+    CS_CUDA(cudaFuncSetAttribute(conv7_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C7Cfg<2>::SMEM));
     g_attr7[dev & 63] = true;
   }
   const long M = (long)x.B * 16 * x.H * x.W;
   {
     ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * w.Cout * w.Cin * 343.0, 0.0);
-    dim3 grid((unsigned)(k.ntw * k.nth * x.B), 16 / C7_GROUP, 7);
-    conv7_tc_kernel<<<grid, TC_THREADS, C7_SMEM, L.stream>>>(tmA, tmB, k);
-    check_launch("conv7_tc");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, 16 / C7_GROUP, 7); cfg.blockDim = dim3(TC_THREADS); cfg.stream = L.stream;
+    cfg.dynamicSmemBytes = pair ? C7Cfg<2>::SMEM : C7Cfg<1>::SMEM;
+    cudaLaunchAttribute attr[1];
+    if (pair) {
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CS_CUDA(cudaLaunchKernelEx(&cfg, conv7_tc_kernel<2>, tmA, tmB, k));
+    } else {
+      CS_CUDA(cudaLaunchKernelEx(&cfg, conv7_tc_kernel<1>, tmA, tmB, k));
+    }
   }
   {
     const long n4 = M * k.ldo / 4;

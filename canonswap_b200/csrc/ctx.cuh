@@ -81,7 +81,7 @@ struct cs_ctx {
   int device = 0, max_batch = 1, net_h = 0, net_w = 0, h = 0, w = 0;
   std::string err;
   bool weights_loaded = false, identity_set = false;
-  int conv_impl = 0, use_graph = 0, tc_passes = 3, tc_sets = 0, tc_comp = 72, tc_pair = 1, tc_stacked3 = 1;
+  int conv_impl = 0, use_graph = 0, tc_passes = 3, tc_sets = 0, tc_comp = 120, tc_pair = 1, tc_stacked3 = 1;
   int64_t launches = 0;
   std::vector<void*> owned;        // device allocations owned by the ctx
   size_t owned_bytes = 0;
@@ -89,6 +89,15 @@ struct cs_ctx {
   cs::Weights W;
   double* stats_scratch = nullptr; // [max_batch*512*2] double
   cs::Profiler prof;
+  // CUDA-graph replay of cs_frame (CS_OPT_USE_GRAPH): the whole loop body is captured once per (B, flags, outputs)
+  // on fixed staging buffers; a call then is copy-in -> graph launch -> copy-out on the caller's stream.
+  struct FrameGraph { cudaGraphExec_t exec = nullptr; int B = 0, flags = 0; bool f32 = false, u8 = false; int seen = 0; int64_t launches = 0; };
+  std::vector<FrameGraph> graphs;
+  void* g_frames = nullptr; float* g_kpt = nullptr; float* g_kpc = nullptr; float* g_out32 = nullptr; uint8_t* g_outu8 = nullptr;
+  void drop_graphs() {
+    for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
   void* dmalloc(size_t bytes) {
     void* p = nullptr;
     CS_CUDA(cudaMalloc(&p, bytes ? bytes : 256));
@@ -111,6 +120,7 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n);
 void set_identity(cs_ctx* ctx, const float* id_dev, cudaStream_t stream);
 ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt /*[Cout][Cin][taps]*/, const std::vector<float>* bias,
                      int Cout, int Cin, int KD, int KH, int KW);
+float weight_prescale(const float* w, size_t n);             // weights.cu
 void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream);
 void pack_conv3s(cs_ctx* ctx, ConvW& w);                     // conv3s_tc.cu
 void pack_conv7(cs_ctx* ctx, ConvW& w);                      // conv7_tc.cu   // derive the split-bf16 B operand from w32 (conv_tc.cu)

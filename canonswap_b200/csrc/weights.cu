@@ -204,6 +204,17 @@ SpadeNormW read_spade(cs_ctx* ctx, const Table& t, const std::string& p, int C) 
 
 }  // namespace
 
+// power of two that brings max|w| to ~2^10: the fp16 remainders of the packed tcgen05 weights stay in the normal range
+float weight_prescale(const float* w, size_t n) {
+  float mx = 0.f;
+  for (size_t i = 0; i < n; ++i) { float a = std::fabs(w[i]); if (a > mx && std::isfinite(a)) mx = a; }
+  if (!(mx > 0.f)) return 1.f;
+  int k = (int)std::floor(std::log2(1024.0 / (double)mx));
+  if (k < -8) k = -8;
+  if (k > 24) k = 24;
+  return std::ldexp(1.f, k);
+}
+
 // ------------------------------------------------------------------------------------------
 // [Cout][Cin][taps] (PyTorch) -> device [taps][Cin][Cout] (+ bias) (+ tcgen05 operand)
 // ------------------------------------------------------------------------------------------
@@ -221,6 +232,7 @@ ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt, const std::vec
     }
   c.w32 = upload(ctx, w);
   if (bias) c.bias = upload(ctx, *bias);
+  c.wmul = weight_prescale(w_pt.data(), w_pt.size());
   pack_tc(ctx, c, nullptr);
   return c;
 }
@@ -292,11 +304,12 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
       y.Cin = HG_OUT; y.Cout = 64; y.KD = y.KH = y.KW = 1;
       y.nblk = (HG_OUT + 31) / 32; y.BN = 64; y.zrows = 64; y.Cout_p = 64 * 16;
       const long rowlen = (long)y.nblk * 64;
+      y.wmul = weight_prescale(oc.w.data(), oc.w.size());
       std::vector<__nv_bfloat16> hw((size_t)y.Cout_p * rowlen, __float2bfloat16(0.f));
       for (int z = 0; z < 16; ++z)
         for (int tp = 0; tp < 49; ++tp)
           for (int ci = 0; ci < HG_OUT; ++ci) {
-            const float v = oc.w[(long)ci * (16 * 49) + z * 49 + tp];
+            const float v = oc.w[(long)ci * (16 * 49) + z * 49 + tp] * y.wmul;
             __nv_bfloat16 hi, lo;
             split_operand(v, hi, lo);
             const long o = ((long)z * 64 + tp) * rowlen + (ci >> 5) * 64 + (ci & 31);
@@ -342,6 +355,8 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
     a.mask_conv = pack(ctx, mc);
     // per-identity combined conv: filled by set_identity
     a.combined.Cin = 512; a.combined.Cout = 1024; a.combined.KD = 1; a.combined.KH = 3; a.combined.KW = 3;
+    // [W | W*s*demod]: the demodulated half has filters of norm <= 1, so 2^14 keeps it far from fp16 saturation
+    a.combined.wmul = std::fmin(weight_prescale(base.w.data(), base.w.size()), 16384.f);
     a.combined.w32 = static_cast<float*>(ctx->dmalloc((size_t)9 * 512 * 1024 * sizeof(float)));
     a.combined.bias = static_cast<float*>(ctx->dmalloc(1024 * sizeof(float)));
     a.style = static_cast<float*>(ctx->dmalloc(512 * sizeof(float)));

@@ -63,7 +63,7 @@ typedef struct cs_tensor_desc {
 #define CS_OPT_CONV_IMPL 1       /* 0 = auto (tcgen05 where eligible), 1 = force SIMT fp32 convs (debug) */
 #define CS_OPT_TC_PASSES 3       /* split-bf16 MMA passes of the tcgen05 conv: 3 (default, fp32-grade) | 2 | 1 (measurement only) */
 #define CS_OPT_TC_SETS 4         /* cap on TMEM accumulator sets per tile (0 = automatic; 1 = single accumulator, measurement only) */
-#define CS_OPT_TC_COMP 5         /* tensor-core accumulate-truncation compensation per chained MMA, units of 1e-10 (default 72, 0 = off) */
+#define CS_OPT_TC_COMP 5         /* tensor-core accumulate-truncation compensation per chained MMA, units of 1e-10 (default 120, 0 = off) */
 #define CS_OPT_TC_PAIR 6         /* 1 = tcgen05 pair mode (cta_group::2 over 2-CTA clusters) for wide N tiles */
 #define CS_OPT_TC_STACKED3 7     /* 1 (default) = depth-stacked kernel for the 32->32 3x3x3 volume convs, 0 = generic implicit GEMM */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */

@@ -142,6 +142,31 @@ def test_frame_vs_golden_reference_fixtures(synth_w, tag, T, hw):
         eng.close()
 
 
+def test_cuda_graph_replay_is_bit_identical(case128):
+    """CS_OPT_USE_GRAPH: cs_frame replayed from a captured CUDA graph (fixed staging buffers) must reproduce the
+    eager result bit for bit, call after call, for changing inputs."""
+    from canonswap_b200 import _lib
+    eng, inp, ref = case128
+    xs = [inp["frames"], inp["frames"].flip(0).contiguous(), (inp["frames"] * 0.5).contiguous()]
+    eager = []
+    for x in xs:
+        o = torch.empty(2, 3, 256, 256, device="cuda")
+        eng.frame(x, inp["x_t"], inp["x_can"], out_f32=o)
+        eager.append(o)
+    eng.set_option(_lib.CS_OPT_USE_GRAPH, 1)
+    try:
+        l0 = eng.launch_count
+        for rep in range(2):
+            for x, e in zip(xs, eager):
+                o = torch.empty(2, 3, 256, 256, device="cuda")
+                u = torch.empty(2, 256, 256, 3, dtype=torch.uint8, device="cuda")
+                eng.frame(x, inp["x_t"], inp["x_can"], out_f32=o, out_u8=u)
+                assert torch.equal(o, e)
+        assert eng.launch_count > l0
+    finally:
+        eng.set_option(_lib.CS_OPT_USE_GRAPH, 0)
+
+
 def test_batch_independence(case128):
     """Frames are independent given the identity: a batch of 2 equals two batches of 1 bit-for-bit
     (the property the multi-GPU frame sharding relies on)."""

@@ -40,8 +40,8 @@ def run(tag):
 
 eng.set_option(_lib.CS_OPT_CONV_IMPL, 1); run("simt     ")
 eng.set_option(_lib.CS_OPT_CONV_IMPL, 0)
-for comp in (0, 72, 140):
+for comp in (100, 120, 140, 170):
     eng.set_option(_lib.CS_OPT_TC_COMP, comp); run(f"tc comp={comp}")
-eng.set_option(_lib.CS_OPT_TC_COMP, 72)
+eng.set_option(_lib.CS_OPT_TC_COMP, 120)
 if "pair" in sys.argv:
     eng.set_option(_lib.CS_OPT_TC_PAIR, 1); run("tc pair  ")

@@ -50,7 +50,7 @@ CASES = [
 
 def main():
     passes = [3]
-    comps = [int(a) for a in sys.argv[1:] if not a.startswith("nopair")] or [72]
+    comps = [int(a) for a in sys.argv[1:] if not a.startswith("nopair")] or [120]
     pair = 0 if "nopair" in sys.argv[1:] else 1
     eng = Engine(None, net_hw=(128, 128), max_batch=1, device=0)
     g = torch.Generator(device="cuda").manual_seed(7)
