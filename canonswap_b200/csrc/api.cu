@@ -222,6 +222,7 @@ void cs_destroy(cs_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   ctx->drop_graphs();
+  if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
   for (void* p : ctx->owned) cudaFree(p);
   delete ctx;
 }
@@ -385,16 +386,19 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
       if (!fg->exec) {
         const int64_t l0 = ctx->launches;
         cudaGraph_t graph = nullptr;
-        CS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        if (!ctx->cap_stream) CS_CUDA(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+        cudaStream_t cst = ctx->cap_stream;
+        n.L.stream = cst;
+        CS_CUDA(cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal));
         try {
           body_frame(n, ctx->g_frames, ctx->g_kpt, ctx->g_kpc, out_f32 ? ctx->g_out32 : nullptr, out_u8 ? ctx->g_outu8 : nullptr, B,
                      flags);
         } catch (...) {
-          cudaStreamEndCapture(st, &graph);
+          cudaStreamEndCapture(cst, &graph);
           if (graph) cudaGraphDestroy(graph);
           throw;
         }
-        CS_CUDA(cudaStreamEndCapture(st, &graph));
+        CS_CUDA(cudaStreamEndCapture(cst, &graph));
         cudaError_t ie = cudaGraphInstantiate(&fg->exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) { fg->exec = nullptr; throw cs::Error(CS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }

@@ -98,6 +98,15 @@ __device__ __forceinline__ void split_operand4(float a, float b, float c, float 
   hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
   lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
 }
+__device__ __forceinline__ void split_operand2(float a, float b, uint32_t& hv, uint32_t& lv) {
+  const float lim = 65504.f;
+  a = a > lim ? lim : (a < -lim ? -lim : a); b = b > lim ? lim : (b < -lim ? -lim : b);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hv = *reinterpret_cast<const uint32_t*>(&h);
+  lv = *reinterpret_cast<const uint32_t*>(&l);
+}
 #endif
 
 enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_SIGMOID = 3 };
@@ -141,6 +150,13 @@ struct Epilogue {
   const float* emit_shift = nullptr;
   int emit_act = ACT_NONE;
   float emit_slope = 0.f;
+  // SPADE mode (tcgen05 path, with `emit`): the conv is a gamma|beta conv whose columns are interleaved in chunks of
+  // [gamma x16 | beta x16]; the epilogue emits act(((x - mean) * rstd) * (1 + gamma) + beta) of the tensor x being
+  // normalised (dense [B,Hx,Wx,C], read nearest-upsampled by 2^sp_xshift) instead of gamma / beta themselves.
+  const float* sp_x = nullptr;
+  const float* sp_mean = nullptr;   // [B,C]
+  const float* sp_rstd = nullptr;
+  int sp_C = 0, sp_xshift = 0, sp_Hx = 0, sp_Wx = 0;
 };
 
 // conv geometry
@@ -164,7 +180,7 @@ struct Prep {
   const float* shift = nullptr;
   const float* mean = nullptr;    // STATS_BC: [B,C]
   const float* rstd = nullptr;
-  const float* gb = nullptr;      // SPADE: [pixels, 2*C] (gamma | beta), applied after normalisation
+  const float* gb = nullptr;      // SPADE: [pixels, 2*C] in chunks of [gamma x16 | beta x16], applied after normalisation
   Act add;                        // residual added before activation (add.p == nullptr when unused); geometry of the output
   int act = ACT_NONE;
   float slope = 0.f;
@@ -206,6 +222,7 @@ struct Launcher {            // everything a kernel launch helper needs
   int conv_impl = 0;         // 0 auto, 1 SIMT, 2 TC
   int npass = 3;             // split-bf16 MMA passes of the tcgen05 conv (3 = hi*hi + lo*hi + hi*lo)
   int max_sets = 0;          // cap on the accumulator sets (0 = automatic)
+  bool spade_fused = true;   // SPADE normalise + modulate + activate inside the gamma|beta conv's epilogue
   bool stacked3 = true;      // depth-stacked kernel for the 32 -> 32 3x3x3 volume convs
   bool pair = true;          // tcgen05 pair mode (cta_group::2, 2-CTA clusters) for wide N tiles
   float acc_comp = 120.f;     // accumulate-truncation compensation per chained MMA, in units of 1e-10 (0 = off)

@@ -48,6 +48,8 @@ struct ConvTcK {
   int vec4;
   // optional: also write act(v * escale[n] + eshift[n]) as the split-bf16 operand of the next conv (dense, output geometry)
   __nv_bfloat16* emit; int erow; const float* escale; const float* eshift; int eact; float eslope;
+  // SPADE epilogue (see Epilogue::sp_x)
+  const float* sp_x; const float* sp_mean; const float* sp_rstd; int sp_C, sp_xs, sp_Hx, sp_Wx;
 };
 
 
@@ -57,7 +59,7 @@ struct ConvTcK {
 // A tile and HALF of the B tile, the leader issues cta_group::2 MMAs (M = 256) that read A / B from both CTAs' shared
 // memory and accumulate into both CTAs' TMEM.  Halving the B bytes written and read per CTA takes the kernel off the
 // shared-memory bandwidth limit that bounds the 1-CTA form at N = 256 (3 MMAs per operand load).
-template <bool RES, bool EMIT, int CTAS>
+template <bool RES, bool EMIT, int CTAS, bool SPADE = false>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, ConvTcK k) {
   extern __shared__ uint8_t smem_raw[];
@@ -194,7 +196,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int q = warp & 3;
     float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + q * 32 * STG_LD;
     const int sub = lane >> 3, c4 = (lane & 7) * 4;
-    long yoff[8], roff[RES ? 8 : 1], epix[EMIT ? 8 : 1];
+    long yoff[8], roff[RES ? 8 : 1], epix[EMIT ? 8 : 1], xoff[SPADE ? 8 : 1];
+    int sbase[SPADE ? 8 : 1];
     float mu[8];
     uint32_t vmask = 0;
 #pragma unroll
@@ -209,6 +212,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       yoff[i] = ob * k.yb + od * k.yd + oh * k.yh + ow * k.yw;
       if constexpr (RES) roff[i] = ob * k.rb + od * k.rd + oh * k.rh + ow * k.rw;
       if constexpr (EMIT) epix[i] = (((long)ob * k.D + od) * k.H + oh) * k.W + ow;
+      if constexpr (SPADE) {
+        xoff[i] = (((long)ob * k.sp_Hx + (oh >> k.sp_xs)) * k.sp_Wx + (ow >> k.sp_xs)) * k.sp_C;
+        sbase[i] = ob * k.sp_C;
+      }
       mu[i] = (k.mult && valid) ? k.mult[(((long)ob * k.D + od) * k.H + oh) * k.W + ow] : 1.f;
     }
     if constexpr (RES) {                                    // pull the residual tile towards L2 while the MMAs run
@@ -257,6 +264,40 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         }
       }
       __syncwarp();
+      if constexpr (SPADE) {
+        // chunk = [gamma of 16 channels | beta of the same 16 channels]; lane -> (row group, channel pair)
+        const int cc = (lane & 7) * 2;
+        const int ncol = n0 + c0;
+        const int ch = (ncol >> 1) + cc;
+        float bg[2] = {0.f, 0.f}, bb[2] = {0.f, 0.f};
+        if (k.bias) {
+          bg[0] = __ldg(k.bias + ncol + cc); bg[1] = __ldg(k.bias + ncol + cc + 1);
+          bb[0] = __ldg(k.bias + ncol + 16 + cc); bb[1] = __ldg(k.bias + ncol + 16 + cc + 1);
+        }
+        float2 xv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          xv[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float2*>(k.sp_x + xoff[i] + ch) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!((vmask >> i) & 1u)) continue;
+          const float* trp = tile + (sub + 4 * i) * STG_LD;
+          const float2 g = *reinterpret_cast<const float2*>(trp + cc);
+          const float2 bt = *reinterpret_cast<const float2*>(trp + 16 + cc);
+          const float2 mn = __ldg(reinterpret_cast<const float2*>(k.sp_mean + sbase[i] + ch));
+          const float2 rs = __ldg(reinterpret_cast<const float2*>(k.sp_rstd + sbase[i] + ch));
+          float v0 = ((xv[i].x - mn.x) * rs.x) * (1.f + (g.x + bg[0])) + (bt.x + bb[0]);
+          float v1 = ((xv[i].y - mn.y) * rs.y) * (1.f + (g.y + bg[1])) + (bt.y + bb[1]);
+          v0 = apply_act(v0, k.eact, k.eslope); v1 = apply_act(v1, k.eact, k.eslope);
+          uint32_t hv, lv;
+          split_operand2(v0, v1, hv, lv);
+          __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (ch >> 5) * 64 + (ch & 31);
+          *reinterpret_cast<uint32_t*>(ep) = hv;
+          *reinterpret_cast<uint32_t*>(ep + 32) = lv;
+        }
+        __syncwarp();
+        continue;
+      }
       const int n = n0 + c0 + c4;
       if (c0 + c4 < k.BN && n < k.Cout) {
         float bz[4] = {0.f, 0.f, 0.f, 0.f};
@@ -462,7 +503,13 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   k.res = e.residual; k.rb = e.rs_b; k.rd = e.rs_d; k.rh = e.rs_h; k.rw = e.rs_w;
   k.mult = e.mult;
   k.y = y.p; k.yb = y.sb; k.yd = y.sd; k.yh = y.sh; k.yw = y.sw;
-  if (e.emit) {
+  if (e.sp_x) {
+    CS_REQUIRE(e.emit && !e.residual && !e.mult && y.p == nullptr && w.Cout == 2 * e.sp_C && e.sp_C % 16 == 0 &&
+                   e.emit_nblk * 32 >= e.sp_C && e.sp_C % 32 == 0 && g.Do == 1, CS_ERR_INVALID, "conv_tc: bad SPADE epilogue");
+    k.emit = e.emit; k.erow = e.emit_nblk * 64; k.eact = e.emit_act; k.eslope = e.emit_slope;
+    k.sp_x = e.sp_x; k.sp_mean = e.sp_mean; k.sp_rstd = e.sp_rstd; k.sp_C = e.sp_C; k.sp_xs = e.sp_xshift;
+    k.sp_Hx = e.sp_Hx; k.sp_Wx = e.sp_Wx;
+  } else if (e.emit) {
     CS_REQUIRE(w.Cout % 32 == 0 && e.emit_nblk * 32 == w.Cout, CS_ERR_INVALID, "conv_tc: operand emission needs Cout % 32 == 0");
     k.emit = e.emit; k.erow = e.emit_nblk * 64; k.escale = e.emit_scale; k.eshift = e.emit_shift; k.eact = e.emit_act;
     k.eslope = e.emit_slope;
@@ -548,6 +595,8 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
       for (int b = 0; b < 2; ++b)
         for (int c = 0; c < 2; ++c)
           CS_CUDA(cudaFuncSetAttribute(fns[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
+    CS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
+    CS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
     g_attr_set[dev & 63] = true;
   }
   if (w.zrows > 0) CS_REQUIRE(bd == 1 && w.zrows % k.BN == 0, CS_ERR_INVALID, "conv_tc: depth-dependent weights need one depth per tile");
@@ -563,7 +612,9 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
   }
-  CS_CUDA(cudaLaunchKernelEx(&cfg, fns[has_res][has_emit][pair ? 1 : 0], tmA, tmB, k));
+  KernelFn fn = fns[has_res][has_emit][pair ? 1 : 0];
+  if (k.sp_x) fn = pair ? conv_tc_kernel<false, true, 2, true> : conv_tc_kernel<false, true, 1, true>;
+  CS_CUDA(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, k));
   check_launch("conv_tc");
 }
 

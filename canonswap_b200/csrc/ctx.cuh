@@ -93,6 +93,7 @@ struct cs_ctx {
   // on fixed staging buffers; a call then is copy-in -> graph launch -> copy-out on the caller's stream.
   struct FrameGraph { cudaGraphExec_t exec = nullptr; int B = 0, flags = 0; bool f32 = false, u8 = false; int seen = 0; int64_t launches = 0; };
   std::vector<FrameGraph> graphs;
+  cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the legacy default stream cannot be captured)
   void* g_frames = nullptr; float* g_kpt = nullptr; float* g_kpc = nullptr; float* g_out32 = nullptr; uint8_t* g_outu8 = nullptr;
   void drop_graphs() {
     for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);

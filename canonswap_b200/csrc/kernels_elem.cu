@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepK k) {
           if (k.scale) v = v * k.scale[c] + k.shift[c];
         }
         if (k.gb) {
-          const float* g = k.gb + pix * (2L * k.C0);
-          v = v * (1.f + g[c]) + g[k.C0 + c];
+          const float* g = k.gb + pix * (2L * k.C0) + (c >> 4) * 32 + (c & 15);   // [gamma x16 | beta x16] chunks
+          v = v * (1.f + g[0]) + g[16];
         }
       } else {
         v = k.s1[b * k.s1b + d * k.s1d + h * k.s1h + w * k.s1w + (c - k.C0)];
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(256) prep_kernel_v4(PrepK k) {
           }
         }
         if (k.gb) {
-          const float* g = k.gb + pix * (2L * k.C0) + c;
-          const float4 ga = *reinterpret_cast<const float4*>(g), be = *reinterpret_cast<const float4*>(g + k.C0);
+          const float* g = k.gb + pix * (2L * k.C0) + (c >> 4) * 32 + (c & 15);   // [gamma x16 | beta x16] chunks
+          const float4 ga = *reinterpret_cast<const float4*>(g), be = *reinterpret_cast<const float4*>(g + 16);
           v.x = v.x * (1.f + ga.x) + be.x; v.y = v.y * (1.f + ga.y) + be.y;
           v.z = v.z * (1.f + ga.z) + be.z; v.w = v.w * (1.f + ga.w) + be.w;
         }

@@ -30,6 +30,11 @@ struct ConvOpts {
   const Affine* emit_affine = nullptr;
   int emit_act = ACT_NONE;
   float emit_slope = 0.f;
+  // SPADE-fused epilogue of a gamma|beta conv (see Epilogue::sp_x): the tensor being normalised and its statistics
+  const Act* sp_x = nullptr;
+  int sp_xshift = 0;
+  const float* sp_mean = nullptr;
+  const float* sp_rstd = nullptr;
 };
 
 Prep prep_of(const Act& src) {
@@ -92,6 +97,10 @@ static void conv_from_operand(Net& n, const Opd& opd, const ConvW& w, const Conv
     e.emit = o.emit->p; e.emit_nblk = o.emit->nblk;
     if (o.emit_affine) { e.emit_scale = o.emit_affine->scale; e.emit_shift = o.emit_affine->shift; }
     e.emit_act = o.emit_act; e.emit_slope = o.emit_slope;
+  }
+  if (o.sp_x) {
+    e.sp_x = o.sp_x->p; e.sp_mean = o.sp_mean; e.sp_rstd = o.sp_rstd; e.sp_C = o.sp_x->C; e.sp_xshift = o.sp_xshift;
+    e.sp_Hx = o.sp_x->H; e.sp_Wx = o.sp_x->W;
   }
   if (n.L.stacked3 && !o.mult && out.D == 16 && opd.D == 16 && conv3s_supported(w, opd.H, opd.W)) {
     conv3s_tc(n.L, opd, w, e, out);                      // 32 -> 32 3x3x3 volume conv: depth-stacked kernel
@@ -443,9 +452,84 @@ static float* spade_gamma_beta(Net& n, const SpadeNormW& s, const Act& seg, int 
   return gb.p;
 }
 
+// tcgen05 form of one SPADE normalisation + activation (util.py:295-302) feeding `consumer`: two kernels, no fp32
+// intermediates.  mlp_shared runs on the (shared) seg operand and emits relu(.) as the operand of the gamma|beta conv,
+// whose SPADE epilogue reads x and its instance statistics and emits act(x_hat * (1 + gamma) + beta) directly as the
+// consumer conv's operand.
+static Opd spade_norm_tc(Net& n, const SpadeNormW& s, const Opd& seg_op, const Act& x, int xup, const float* mean, const float* rstd,
+                         int act, float slope, const ConvW& consumer, int B, int H, int W) {
+  Act geom128 = make_act(nullptr, B, 1, H, W, 128);
+  Act geom2c = make_act(nullptr, B, 1, H, W, 2 * s.C);
+  Opd mod = conv_tc_alloc_operand(*n.A, consumer, geom2c);            // survives this call (caller resets the arena)
+  size_t m = n.A->mark();
+  Opd actv = conv_tc_alloc_operand(*n.A, s.gamma_beta, geom128);
+  ConvOpts o1; o1.act = ACT_RELU; o1.emit = &actv;
+  conv_from_operand(n, seg_op, s.shared, o1, geom128);
+  ConvOpts o2; o2.emit = &mod; o2.emit_act = act; o2.emit_slope = slope;
+  o2.sp_x = &x; o2.sp_xshift = xup; o2.sp_mean = mean; o2.sp_rstd = rstd;
+  conv_from_operand(n, actv, s.gamma_beta, o2, geom2c);
+  n.A->reset(m);
+  return mod;
+}
+
+static bool spade_block_tc_ok(const Net& n, const SpadeBlockW& b) {
+  if (n.L.conv_impl == 1 || !n.L.spade_fused) return false;
+  const ConvW* ws[] = {&b.norm_0.shared, &b.norm_0.gamma_beta, &b.norm_1.shared, &b.norm_1.gamma_beta, &b.conv_0, &b.conv_1};
+  for (const ConvW* w : ws) if (!w->wtc) return false;
+  if (b.learned_shortcut && !(b.norm_s.shared.wtc && b.norm_s.gamma_beta.wtc && b.conv_s.wtc)) return false;
+  return b.fin % 32 == 0 && b.fmid % 32 == 0;
+}
+
+// SPADEResnetBlock (util.py:329-344) on the tcgen05 path. seg_op: split operand of the (upsampled) seg map at this
+// block's resolution, shared by the block's mlp_shared convs.
+static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, const Opd& seg_op, Act out) {
+  const int B = x.B, H = x.H << xup, W = x.W << xup;
+  size_t m = n.A->mark();
+  float* mean = n.A->f32((size_t)B * b.fin);
+  float* rstd = n.A->f32((size_t)B * b.fin);
+  instance_stats(n.L, x, mean, rstd, 1e-5f, n.ctx->stats_scratch);
+  Act xs;
+  if (b.learned_shortcut) {
+    xs = new_act(n, B, 1, H, W, b.fout);
+    size_t m2 = n.A->mark();
+    Opd ms = spade_norm_tc(n, b.norm_s, seg_op, x, xup, mean, rstd, ACT_NONE, 0.f, b.conv_s, B, H, W);
+    conv_from_operand(n, ms, b.conv_s, ConvOpts(), xs);
+    n.A->reset(m2);
+  } else {
+    CS_REQUIRE(xup == 0, CS_ERR_INVALID, "identity shortcut needs an un-upsampled input");
+    xs = x;
+  }
+  Act dx = new_act(n, B, 1, H, W, b.fmid);
+  {
+    size_t m2 = n.A->mark();
+    Opd m0 = spade_norm_tc(n, b.norm_0, seg_op, x, xup, mean, rstd, ACT_LRELU, 0.2f, b.conv_0, B, H, W);
+    conv_from_operand(n, m0, b.conv_0, ConvOpts(), dx);
+    n.A->reset(m2);
+  }
+  {
+    float* mean1 = n.A->f32((size_t)B * b.fmid);
+    float* rstd1 = n.A->f32((size_t)B * b.fmid);
+    instance_stats(n.L, dx, mean1, rstd1, 1e-5f, n.ctx->stats_scratch);
+    Opd m1 = spade_norm_tc(n, b.norm_1, seg_op, dx, 0, mean1, rstd1, ACT_LRELU, 0.2f, b.conv_1, B, H, W);
+    ConvOpts o; o.residual = &xs;
+    conv_from_operand(n, m1, b.conv_1, o, out);
+  }
+  n.A->reset(m);
+  return out;
+}
+
 // SPADEResnetBlock (util.py:329-344). x is read nearest-upsampled by 2^xup; returns [B,H,W,fout].
 static Act spade_block(Net& n, const SpadeBlockW& b, const Act& x, int xup, const Act& seg, int segshift, Act out) {
   const int B = x.B, H = x.H << xup, W = x.W << xup;
+  if (spade_block_tc_ok(n, b)) {
+    size_t m0 = n.A->mark();
+    Opd seg_op = conv_tc_alloc_operand(*n.A, b.norm_0.shared, make_act(nullptr, B, 1, H, W, 128));
+    Prep up = prep_of(seg); up.upshift = segshift;
+    prep_planes(n.L, up, seg_op, nullptr);
+    spade_block_tc(n, b, x, xup, seg_op, out);
+    n.A->reset(m0);
+    return out;
+  }
   size_t m = n.A->mark();
   // InstanceNorm statistics of x (nearest upsampling leaves mean / biased variance unchanged)
   float* mean = n.A->f32((size_t)B * b.fin);

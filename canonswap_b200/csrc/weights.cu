@@ -194,10 +194,21 @@ SpadeNormW read_spade(cs_ctx* ctx, const Table& t, const std::string& p, int C) 
   s.shared = pack(ctx, read_conv(t, p + ".mlp_shared.0", 128, 256, 1, 3, 3));
   HostConv g = read_conv(t, p + ".mlp_gamma", C, 128, 1, 3, 3);
   HostConv b = read_conv(t, p + ".mlp_beta", C, 128, 1, 3, 3);
+  // gamma | beta as ONE conv whose output channels are interleaved in chunks of [gamma x16 | beta x16]: a 32-column
+  // chunk of the tcgen05 epilogue then holds both modulation terms of 16 channels (SPADE-fused epilogue, conv_tc.cu);
+  // channel c: gamma at (c/16)*32 + c%16, beta 16 further.
   HostConv gb;
   gb.Cout = 2 * C; gb.Cin = 128; gb.KD = 1; gb.KH = 3; gb.KW = 3;
-  gb.w = g.w; gb.w.insert(gb.w.end(), b.w.begin(), b.w.end());
-  gb.b = g.b; gb.b.insert(gb.b.end(), b.b.begin(), b.b.end());
+  const long per = 128L * 9;
+  gb.w.resize((size_t)2 * C * per);
+  gb.b.resize((size_t)2 * C);
+  for (int c = 0; c < C; ++c) {
+    const long ng = (long)(c / 16) * 32 + (c % 16), nb = ng + 16;
+    std::memcpy(gb.w.data() + ng * per, g.w.data() + (long)c * per, per * sizeof(float));
+    std::memcpy(gb.w.data() + nb * per, b.w.data() + (long)c * per, per * sizeof(float));
+    gb.b[ng] = g.b[c];
+    gb.b[nb] = b.b[c];
+  }
   s.gamma_beta = pack(ctx, gb);
   return s;
 }
