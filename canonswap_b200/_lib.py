@@ -20,6 +20,7 @@ CS_OPT_TC_SETS = 4
 CS_OPT_TC_COMP = 5
 CS_OPT_TC_PAIR = 6
 CS_OPT_TC_STACKED3 = 7
+CS_OPT_TC_CORESIDENT = 8
 
 # every symbol include/canonswap_b200.h declares
 SYMBOLS = [

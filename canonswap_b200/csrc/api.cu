@@ -43,6 +43,7 @@ Net make_net(cs_ctx* ctx, void* stream, bool dry) {
   n.L.acc_comp = (float)ctx->tc_comp;
   n.L.pair = ctx->tc_pair != 0;
   n.L.stacked3 = ctx->tc_stacked3 != 0;
+  n.L.coresident = ctx->tc_cores != 0;
   n.L.prof = dry ? nullptr : &ctx->prof;
   return n;
 }
@@ -247,6 +248,8 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
     case CS_OPT_TC_COMP:
       if (value < 0 || value > 1000) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_COMP: value must be in [0, 1000]");
       ctx->tc_comp = value; return CS_OK;
+    case CS_OPT_TC_CORESIDENT:
+      ctx->tc_cores = value ? 1 : 0; return CS_OK;
     case CS_OPT_TC_STACKED3:
       ctx->tc_stacked3 = value ? 1 : 0; return CS_OK;
     case CS_OPT_TC_PAIR:
@@ -471,7 +474,7 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
     Act ya = make_act(y, B, Do, Ho, Wo, Cout);
     ConvGeom g; g.PD = PD; g.PH = PH; g.PW = PW; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
     Epilogue e; e.act = act; e.slope = slope;
-    Launcher L; L.stream = st; L.counter = &ctx->launches; L.npass = ctx->tc_passes; L.prof = &ctx->prof; L.max_sets = ctx->tc_sets; L.acc_comp = (float)ctx->tc_comp; L.pair = ctx->tc_pair != 0;
+    Launcher L; L.stream = st; L.counter = &ctx->launches; L.npass = ctx->tc_passes; L.prof = &ctx->prof; L.max_sets = ctx->tc_sets; L.acc_comp = (float)ctx->tc_comp; L.pair = ctx->tc_pair != 0; L.coresident = ctx->tc_cores != 0;
     const bool same = (Ho == H && Wo == W && PH == KH / 2 && PW == KW / 2) &&
                       ((Do == D && PD == KD / 2) || (Do == 1 && KD == D && PD == 0));
     bool tc = same && conv_tc_supported(cw, ya);

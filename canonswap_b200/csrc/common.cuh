@@ -157,6 +157,11 @@ struct Epilogue {
   const float* sp_mean = nullptr;   // [B,C]
   const float* sp_rstd = nullptr;
   int sp_C = 0, sp_xshift = 0, sp_Hx = 0, sp_Wx = 0;
+  // phase mode (tcgen05 path): the conv input is the operand nearest-upsampled by 2^phase_shift.  Instead of
+  // materialising it, the conv runs on the low-resolution operand once per output phase (a, b) with the taps that fall on
+  // the same source pixel pre-summed (ConvW packed by pack_phase_conv: Cout = 4^phase_shift * BN rows): 2.25 (x2) or
+  // 4 (x4) times fewer MACs and no upsampled operand.
+  int phase_shift = 0;
 };
 
 // conv geometry
@@ -222,8 +227,10 @@ struct Launcher {            // everything a kernel launch helper needs
   int conv_impl = 0;         // 0 auto, 1 SIMT, 2 TC
   int npass = 3;             // split-bf16 MMA passes of the tcgen05 conv (3 = hi*hi + lo*hi + hi*lo)
   int max_sets = 0;          // cap on the accumulator sets (0 = automatic)
+  bool phase_conv = true;    // convs of a nearest-upsampled seg map in phase form on the low-resolution operand
   bool spade_fused = true;   // SPADE normalise + modulate + activate inside the gamma|beta conv's epilogue
   bool stacked3 = true;      // depth-stacked kernel for the 32 -> 32 3x3x3 volume convs
+  bool coresident = false;   // short-K wide tiles as 2 co-resident CTAs per SM (see conv_tc.cu)
   bool pair = true;          // tcgen05 pair mode (cta_group::2, 2-CTA clusters) for wide N tiles
   float acc_comp = 120.f;     // accumulate-truncation compensation per chained MMA, in units of 1e-10 (0 = off)
   Profiler* prof = nullptr;

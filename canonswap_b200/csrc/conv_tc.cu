@@ -50,6 +50,10 @@ struct ConvTcK {
   __nv_bfloat16* emit; int erow; const float* escale; const float* eshift; int eact; float eslope;
   // SPADE epilogue (see Epilogue::sp_x)
   const float* sp_x; const float* sp_mean; const float* sp_rstd; int sp_C, sp_xs, sp_Hx, sp_Wx;
+  // phase mode (conv of a nearest-upsampled input computed on the low-resolution operand, see Epilogue::phase_shift):
+  // N tile p = output phase (a, b) = (p >> ph_s, p & (2^ph_s - 1)); only the taps in tapmask[p] are walked; the tile's
+  // pixels land at (oh * 2^ph_s + a, ow * 2^ph_s + b) of the output.
+  int ph_s; unsigned short tapmask[16];
 };
 
 
@@ -60,7 +64,7 @@ struct ConvTcK {
 // memory and accumulate into both CTAs' TMEM.  Halving the B bytes written and read per CTA takes the kernel off the
 // shared-memory bandwidth limit that bounds the 1-CTA form at N = 256 (3 MMAs per operand load).
 template <bool RES, bool EMIT, int CTAS, bool SPADE = false>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, ConvTcK k) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -70,7 +74,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const uint32_t brows = (uint32_t)k.BN / CTAS;                       // B rows held by this CTA
   const uint32_t stage_bytes = A_TILE_BYTES + brows * 128u;
   const uint32_t stg = base + (uint32_t)k.stages * stage_bytes;       // epilogue staging
-  const uint32_t bars = stg + STG_BYTES;                              // full[stages], empty[stages], tmem_full, tmem slot
+  const int egroups = ((int)(blockDim.x >> 5) - 2) >> 2;              // epilogue warp groups (4 warps each): 1 or 2
+  const uint32_t bars = stg + (uint32_t)egroups * STG_BYTES;          // full[stages], empty[stages], tmem_full, tmem slot
   const uint32_t tmem_full = bars + 16u * k.stages;
   const uint32_t tmem_slot = tmem_full + 8u;
 
@@ -91,6 +96,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const int w0 = tw << k.lbw, h0 = th << k.lbh, d0 = td << k.lbd, b0 = tb << k.lbb;
   const int n0 = blockIdx.y * k.BN;
   const int nrow0 = n0 + d0 * k.zrows;            // first B row of this tile
+  const uint32_t tmask = k.ph_s ? k.tapmask[blockIdx.y] : 0xFFFFFFFFu;
+  const int ph_a = k.ph_s ? (int)(blockIdx.y >> k.ph_s) : 0, ph_b = k.ph_s ? (int)(blockIdx.y & ((1u << k.ph_s) - 1)) : 0;
+  const int chan0 = k.ph_s ? n0 : 0;              // phase tiles all produce output channels 0 .. BN-1
   const int taps = k.KD * k.KH * k.KW;
 
   if (warp == 0 && lane == 0) {
@@ -119,6 +127,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tap = 0; tap < taps; ++tap) {
+        if (!((tmask >> (tap & 31)) & 1u)) continue;
         const int kw = tap % k.KW; const int r = tap / k.KW; const int kh = r % k.KH; const int kd = r / k.KH;
         const int cw = w0 + kw - k.PW, ch = h0 + kh - k.PH, cd = d0 + kd - k.PD;
         const int kcol = tap * k.rowA;
@@ -149,6 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     int in_set = 0;
     uint32_t acc_corr = 0;
     for (int tap = 0; tap < taps; ++tap) {
+      if (!((tmask >> (tap & 31)) & 1u)) continue;
       for (int blk = 0; blk < k.nblk; ++blk) {
         const uint32_t fb = bars + 8u * s;
         mbar_wait(fb, ph);
@@ -193,8 +203,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 =====
     // phase 1: each lane pulls its pixel row (32 columns, all accumulator sets summed) into a padded smem tile;
     // phase 2: the warp walks the tile 4 rows x 128 B at a time so global stores / residual loads are coalesced.
+    // with 2 groups (wide tiles) the groups take alternate 32-column chunks: the epilogue is not overlapped with the main
+    // loop, so its throughput is on the critical path of every tile
     const int q = warp & 3;
-    float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + q * 32 * STG_LD;
+    const int eg = (warp - 2) >> 2;
+    float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + (eg * 4 + q) * 32 * STG_LD;
     const int sub = lane >> 3, c4 = (lane & 7) * 4;
     long yoff[8], roff[RES ? 8 : 1], epix[EMIT ? 8 : 1], xoff[SPADE ? 8 : 1];
     int sbase[SPADE ? 8 : 1];
@@ -209,16 +222,17 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       const int ob = b0 + r;
       const bool valid = ow < k.W && oh < k.H && od < k.D && ob < k.B;
       if (valid) vmask |= 1u << i;
-      yoff[i] = ob * k.yb + od * k.yd + oh * k.yh + ow * k.yw;
-      if constexpr (RES) roff[i] = ob * k.rb + od * k.rd + oh * k.rh + ow * k.rw;
-      if constexpr (EMIT) epix[i] = (((long)ob * k.D + od) * k.H + oh) * k.W + ow;
+      const int oh2 = (oh << k.ph_s) + ph_a, ow2 = (ow << k.ph_s) + ph_b;        // output position (phase mode: upsampled grid)
+      yoff[i] = ob * k.yb + od * k.yd + oh2 * k.yh + ow2 * k.yw;
+      if constexpr (RES) roff[i] = ob * k.rb + od * k.rd + oh2 * k.rh + ow2 * k.rw;
+      if constexpr (EMIT) epix[i] = (((long)ob * k.D + od) * (k.H << k.ph_s) + oh2) * (k.W << k.ph_s) + ow2;
       if constexpr (SPADE) {
         xoff[i] = (((long)ob * k.sp_Hx + (oh >> k.sp_xs)) * k.sp_Wx + (ow >> k.sp_xs)) * k.sp_C;
         sbase[i] = ob * k.sp_C;
       }
       mu[i] = (k.mult && valid) ? k.mult[(((long)ob * k.D + od) * k.H + oh) * k.W + ow] : 1.f;
     }
-    if constexpr (RES) {                                    // pull the residual tile towards L2 while the MMAs run
+    if (RES && eg == 0) {                                   // pull the residual tile towards L2 while the MMAs run
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (!((vmask >> i) & 1u)) continue;
@@ -229,7 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < k.BN; c0 += 32) {
+    for (int c0 = eg * 32; c0 < k.BN; c0 += 32 * egroups) {
       if (n0 + c0 >= k.Cout) break;                         // warp-uniform
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -305,19 +319,20 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 4; ++j) if (n + j < k.Cout) bz[j] = __ldg(k.bias + n + j);
         }
+        const int nc = n - chan0;                           // output channel (phase mode: every N tile is channels 0 .. BN-1)
         const bool full4 = k.vec4 && (n + 3 < k.Cout);
         float4 rr4[RES ? 8 : 1];
         if constexpr (RES) {
           if (full4) {                                      // all residual loads in flight before the first use
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              rr4[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float4*>(k.res + roff[i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              rr4[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float4*>(k.res + roff[i] + nc) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         float es[4] = {1.f, 1.f, 1.f, 1.f}, eb[4] = {0.f, 0.f, 0.f, 0.f};
         if (EMIT && k.escale) {                             // emission needs Cout % 32 == 0: n .. n+3 are valid
-          const float4 s4 = __ldg(reinterpret_cast<const float4*>(k.escale + n));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(k.eshift + n));
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(k.escale + nc));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(k.eshift + nc));
           es[0] = s4.x; es[1] = s4.y; es[2] = s4.z; es[3] = s4.w;
           eb[0] = b4.x; eb[1] = b4.y; eb[2] = b4.z; eb[3] = b4.w;
         }
@@ -333,13 +348,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
               o[0] += rr4[i].x; o[1] += rr4[i].y; o[2] += rr4[i].z; o[3] += rr4[i].w;
             } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) if (n + j < k.Cout) o[j] += k.res[roff[i] + n + j];
+              for (int j = 0; j < 4; ++j) if (n + j < k.Cout) o[j] += k.res[roff[i] + nc + j];
             }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] *= mu[i];
           if (k.y) {
-            float* yp = k.y + yoff[i] + n;
+            float* yp = k.y + yoff[i] + nc;
             if (full4) {
               *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
@@ -353,7 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope);
             uint2 hv, lv;
             split_operand4(e[0], e[1], e[2], e[3], hv, lv);
-            __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (n >> 5) * 64 + (n & 31);
+            __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (nc >> 5) * 64 + (nc & 31);
             *reinterpret_cast<uint2*>(ep) = hv;
             *reinterpret_cast<uint2*>(ep + 32) = lv;
           }
@@ -480,9 +495,16 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   // stride-1 'same' convolutions, or a kernel spanning the full depth without depth padding (Do = 1)
   const bool same_d = g.Do == x.D && g.PD == w.KD / 2;
   const bool full_d = g.Do == 1 && w.KD == x.D && g.PD == 0;
-  CS_REQUIRE((same_d || full_d) && g.Ho == x.H && g.Wo == x.W && g.PH == w.KH / 2 && g.PW == w.KW / 2, CS_ERR_INVALID,
-             "conv_tc: unsupported geometry");
-  CS_REQUIRE(y.C == w.Cout && x.nblk == w.nblk, CS_ERR_INVALID, "conv_tc: channel mismatch");
+  const int ps = e.phase_shift;
+  CS_REQUIRE((same_d || full_d) && g.Ho == (x.H << ps) && g.Wo == (x.W << ps) && g.PH == w.KH / 2 && g.PW == w.KW / 2,
+             CS_ERR_INVALID, "conv_tc: unsupported geometry");
+  if (ps) {
+    CS_REQUIRE(ps <= 2 && w.KD == 1 && w.KH == 3 && w.KW == 3 && w.Cout == (w.BN << (2 * ps)) && y.C == w.BN && w.zrows == 0 &&
+                   !e.residual && !e.mult && !e.sp_x, CS_ERR_INVALID, "conv_tc: bad phase-mode conv");
+  } else {
+    CS_REQUIRE(y.C == w.Cout, CS_ERR_INVALID, "conv_tc: channel mismatch");
+  }
+  CS_REQUIRE(x.nblk == w.nblk, CS_ERR_INVALID, "conv_tc: channel mismatch");
 
   ConvTcK k{};
   k.B = x.B; k.D = g.Do; k.H = x.H; k.W = x.W;
@@ -498,6 +520,20 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   k.last_ksteps = ((w.Cin - (w.nblk - 1) * 32) + 15) / 16;
   k.rowA = w.nblk * 64;
   k.BN = w.BN; k.Cout = w.Cout; k.zrows = w.zrows;
+  k.ph_s = ps;
+  if (ps) {
+    // output row Y = y*f + a reads input rows floor((Y + dy) / f): a = 0 -> {y-1: dy=-1, y: dy=0,+1}; a = f-1 -> {y: dy=-1,0, y+1: dy=+1};
+    // else only row y.  The packed weights hold the per-phase tap sums; taps outside the mask are zero and skipped.
+    const int f = 1 << ps;
+    for (int a = 0; a < f; ++a)
+      for (int b = 0; b < f; ++b) {
+        unsigned rows = 2u | (a == 0 ? 1u : 0u) | (a == f - 1 ? 4u : 0u), cols = 2u | (b == 0 ? 1u : 0u) | (b == f - 1 ? 4u : 0u);
+        unsigned m = 0;
+        for (int ty = 0; ty < 3; ++ty)
+          for (int tx = 0; tx < 3; ++tx) if (((rows >> ty) & 1u) && ((cols >> tx) & 1u)) m |= 1u << (ty * 3 + tx);
+        k.tapmask[a * f + b] = (unsigned short)m;
+      }
+  }
   k.npass = L.npass >= 1 && L.npass <= 3 ? L.npass : 3;
   k.bias = w.bias; k.act = e.act; k.slope = e.slope;
   k.res = e.residual; k.rb = e.rs_b; k.rd = e.rs_d; k.rh = e.rs_h; k.rw = e.rs_w;
@@ -510,7 +546,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     k.sp_x = e.sp_x; k.sp_mean = e.sp_mean; k.sp_rstd = e.sp_rstd; k.sp_C = e.sp_C; k.sp_xs = e.sp_xshift;
     k.sp_Hx = e.sp_Hx; k.sp_Wx = e.sp_Wx;
   } else if (e.emit) {
-    CS_REQUIRE(w.Cout % 32 == 0 && e.emit_nblk * 32 == w.Cout, CS_ERR_INVALID, "conv_tc: operand emission needs Cout % 32 == 0");
+    CS_REQUIRE(y.C % 32 == 0 && e.emit_nblk * 32 == y.C, CS_ERR_INVALID, "conv_tc: operand emission needs Cout % 32 == 0");
     k.emit = e.emit; k.erow = e.emit_nblk * 64; k.escale = e.emit_scale; k.eshift = e.emit_shift; k.eact = e.emit_act;
     k.eslope = e.emit_slope;
   }
@@ -522,7 +558,12 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   // tcgen05 pair mode (cta_group::2): wide N tiles, an even number of M tiles, weights shared by the pair
   const int niter = w.taps() * w.nblk;
   // (measured: +12% at K = 2304 .. 3834, +2% at K = 4608, a loss for K <= 1152 where the cluster sync is not amortised)
-  const bool pair = L.pair && k.BN >= 128 && (m_tiles % 2 == 0) && w.zrows == 0 && k.npass == 3 && niter >= 64;
+  // short-K wide tiles: the (non-overlapped) epilogue is 35-50% of a tile.  Co-resident mode runs them as tcgen05 pairs with
+  // ONE accumulator set (256 columns) and two pipeline stages, so two CTAs fit on an SM and one's epilogue overlaps the
+  // other's main loop.
+  const bool cores = L.coresident && k.BN > 64 && niter <= 72 && (m_tiles % 2 == 0) && w.zrows == 0 && k.npass == 3 && ps == 0 &&
+                     !e.sp_x;
+  const bool pair = (L.pair && k.BN >= 128 && (m_tiles % 2 == 0) && w.zrows == 0 && k.npass == 3 && niter >= 64 && ps == 0) || cores;
   const int stage_bytes = A_TILE_BYTES + (pair ? k.BN / 2 : k.BN) * 128;
   // accumulator sets: one for the correction products + enough hi*hi sets for chains of <= ~256 MMAs
   {
@@ -532,19 +573,21 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     if (want < 1) want = 1;
     int cols = k.BN * want;
     if (cols > 512) cols = 512;
+    if (cores) cols = k.BN;
     int tcols = 32;
     while (tcols < cols) tcols <<= 1;
     int nsets = tcols / k.BN;
     if (nsets > 16) nsets = 16;
     if (L.max_sets > 0 && nsets > L.max_sets) nsets = L.max_sets;
-    if (nsets < 2 && k.npass > 1) nsets = 2;               // the scaled correction products need their own accumulator
+    if (cores) nsets = 1;
     if (nsets < 1) nsets = 1;
     const int corr = (k.npass > 1 && nsets > 1) ? 1 : 0;
     int nmain = nsets - corr;
     if (nmain > niter) nmain = niter;
     const int chunk = (niter + nmain - 1) / nmain;          // K iterations per hi*hi set
     nmain = (niter + chunk - 1) / chunk;                    // sets actually written
-    k.tcols = tcols; k.nsets = corr + nmain; k.chunk = chunk;
+    if (ps) { nmain = 1; }
+    k.tcols = tcols; k.nsets = corr + nmain; k.chunk = ps ? (1 << 30) : chunk;
     // The tensor core truncates (rounds toward zero) when it adds an MMA into the fp32 accumulator: measured on B200, a
     // chain of L MMAs loses ~1.2e-8 * L of the accumulated magnitude, systematically (mean signed error, tools/tc_check.py).
     // Errors of that sign add linearly over the ~75 stacked convs, so the epilogue scales the hi*hi sum back.
@@ -553,13 +596,15 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     k.out_scale = 1.0f / w.wmul;
   }
   // thin-N tiles keep the footprint under ~100 KB so two CTAs share an SM (prologue / epilogue overlap)
-  const int budget = (k.BN <= 64 && k.tcols <= 256) ? 100 * 1024 : MAX_DYN_SMEM;
-  int stages = (budget - 2048 - STG_BYTES) / stage_bytes;
+  const int budget = ((k.BN <= 64 && k.tcols <= 256) || cores) ? 100 * 1024 : MAX_DYN_SMEM;
+  const int egroups = (k.BN > 64 && !cores) ? 2 : 1;       // 8 epilogue warps on wide tiles (1 CTA per SM)
+  const int stg_bytes = egroups * STG_BYTES;
+  int stages = (budget - 2048 - stg_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > niter) stages = niter;
   if (stages < 1) stages = 1;
   k.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + STG_BYTES + 1024 + 16 * stages + 32;
+  const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 1024 + 16 * stages + 32;
 
   // tensor maps
   auto enc = encode_fn();
@@ -601,11 +646,11 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   }
   if (w.zrows > 0) CS_REQUIRE(bd == 1 && w.zrows % k.BN == 0, CS_ERR_INVALID, "conv_tc: depth-dependent weights need one depth per tile");
   dim3 grid(m_tiles, (unsigned)((w.zrows > 0 ? w.zrows : w.Cout_p) / k.BN));
-  const long M = (long)x.B * g.Do * x.H * x.W;
-  ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * w.Cout * w.Cin * w.taps(), 0.0);
+  const long M = (long)x.B * g.Do * g.Ho * g.Wo;          // phase mode: the algorithmic conv runs on the upsampled grid
+  ProfScope pscope(L, PK_CONV_TC, 2.0 * (double)M * y.C * w.Cin * w.taps(), 0.0);
   const bool has_res = k.res != nullptr, has_emit = k.emit != nullptr;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
+  cfg.gridDim = grid; cfg.blockDim = dim3(64 + 128 * egroups); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
   cudaLaunchAttribute attr[1];
   if (pair) {
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -35,6 +35,7 @@ struct ConvOpts {
   int sp_xshift = 0;
   const float* sp_mean = nullptr;
   const float* sp_rstd = nullptr;
+  int phase_shift = 0;         // tcgen05 phase-mode conv of a nearest-upsampled operand (see Epilogue::phase_shift)
 };
 
 Prep prep_of(const Act& src) {
@@ -88,7 +89,7 @@ static void conv_from_operand(Net& n, const Opd& opd, const ConvW& w, const Conv
   g.PD = (out.D == opd.D) ? w.KD / 2 : 0; g.PH = w.KH / 2; g.PW = w.KW / 2;
   g.Do = out.D; g.Ho = out.H; g.Wo = out.W;
   Epilogue e;
-  e.act = o.act; e.slope = o.slope; e.mult = o.mult;
+  e.act = o.act; e.slope = o.slope; e.mult = o.mult; e.phase_shift = o.phase_shift;
   if (o.residual) {
     e.residual = o.residual->p;
     e.rs_b = o.residual->sb; e.rs_d = o.residual->sd; e.rs_h = o.residual->sh; e.rs_w = o.residual->sw;
@@ -456,15 +457,20 @@ static float* spade_gamma_beta(Net& n, const SpadeNormW& s, const Act& seg, int 
 // intermediates.  mlp_shared runs on the (shared) seg operand and emits relu(.) as the operand of the gamma|beta conv,
 // whose SPADE epilogue reads x and its instance statistics and emits act(x_hat * (1 + gamma) + beta) directly as the
 // consumer conv's operand.
-static Opd spade_norm_tc(Net& n, const SpadeNormW& s, const Opd& seg_op, const Act& x, int xup, const float* mean, const float* rstd,
-                         int act, float slope, const ConvW& consumer, int B, int H, int W) {
+static Opd spade_norm_tc(Net& n, const SpadeNormW& s, const Opd& seg_op, int seg_phase, const Act& x, int xup, const float* mean,
+                         const float* rstd, int act, float slope, const ConvW& consumer, int B, int H, int W) {
   Act geom128 = make_act(nullptr, B, 1, H, W, 128);
   Act geom2c = make_act(nullptr, B, 1, H, W, 2 * s.C);
   Opd mod = conv_tc_alloc_operand(*n.A, consumer, geom2c);            // survives this call (caller resets the arena)
   size_t m = n.A->mark();
   Opd actv = conv_tc_alloc_operand(*n.A, s.gamma_beta, geom128);
   ConvOpts o1; o1.act = ACT_RELU; o1.emit = &actv;
-  conv_from_operand(n, seg_op, s.shared, o1, geom128);
+  if (seg_phase > 0) {                                   // seg_op is the LOW-resolution seg: phase-form conv, upsampled output
+    o1.phase_shift = seg_phase;
+    conv_from_operand(n, seg_op, s.shared_ph, o1, geom128);
+  } else {
+    conv_from_operand(n, seg_op, s.shared, o1, geom128);
+  }
   ConvOpts o2; o2.emit = &mod; o2.emit_act = act; o2.emit_slope = slope;
   o2.sp_x = &x; o2.sp_xshift = xup; o2.sp_mean = mean; o2.sp_rstd = rstd;
   conv_from_operand(n, actv, s.gamma_beta, o2, geom2c);
@@ -482,7 +488,7 @@ static bool spade_block_tc_ok(const Net& n, const SpadeBlockW& b) {
 
 // SPADEResnetBlock (util.py:329-344) on the tcgen05 path. seg_op: split operand of the (upsampled) seg map at this
 // block's resolution, shared by the block's mlp_shared convs.
-static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, const Opd& seg_op, Act out) {
+static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, const Opd& seg_op, int seg_phase, Act out) {
   const int B = x.B, H = x.H << xup, W = x.W << xup;
   size_t m = n.A->mark();
   float* mean = n.A->f32((size_t)B * b.fin);
@@ -492,7 +498,7 @@ static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, c
   if (b.learned_shortcut) {
     xs = new_act(n, B, 1, H, W, b.fout);
     size_t m2 = n.A->mark();
-    Opd ms = spade_norm_tc(n, b.norm_s, seg_op, x, xup, mean, rstd, ACT_NONE, 0.f, b.conv_s, B, H, W);
+    Opd ms = spade_norm_tc(n, b.norm_s, seg_op, seg_phase, x, xup, mean, rstd, ACT_NONE, 0.f, b.conv_s, B, H, W);
     conv_from_operand(n, ms, b.conv_s, ConvOpts(), xs);
     n.A->reset(m2);
   } else {
@@ -502,7 +508,7 @@ static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, c
   Act dx = new_act(n, B, 1, H, W, b.fmid);
   {
     size_t m2 = n.A->mark();
-    Opd m0 = spade_norm_tc(n, b.norm_0, seg_op, x, xup, mean, rstd, ACT_LRELU, 0.2f, b.conv_0, B, H, W);
+    Opd m0 = spade_norm_tc(n, b.norm_0, seg_op, seg_phase, x, xup, mean, rstd, ACT_LRELU, 0.2f, b.conv_0, B, H, W);
     conv_from_operand(n, m0, b.conv_0, ConvOpts(), dx);
     n.A->reset(m2);
   }
@@ -510,7 +516,7 @@ static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, c
     float* mean1 = n.A->f32((size_t)B * b.fmid);
     float* rstd1 = n.A->f32((size_t)B * b.fmid);
     instance_stats(n.L, dx, mean1, rstd1, 1e-5f, n.ctx->stats_scratch);
-    Opd m1 = spade_norm_tc(n, b.norm_1, seg_op, dx, 0, mean1, rstd1, ACT_LRELU, 0.2f, b.conv_1, B, H, W);
+    Opd m1 = spade_norm_tc(n, b.norm_1, seg_op, seg_phase, dx, 0, mean1, rstd1, ACT_LRELU, 0.2f, b.conv_1, B, H, W);
     ConvOpts o; o.residual = &xs;
     conv_from_operand(n, m1, b.conv_1, o, out);
   }
@@ -523,10 +529,14 @@ static Act spade_block(Net& n, const SpadeBlockW& b, const Act& x, int xup, cons
   const int B = x.B, H = x.H << xup, W = x.W << xup;
   if (spade_block_tc_ok(n, b)) {
     size_t m0 = n.A->mark();
-    Opd seg_op = conv_tc_alloc_operand(*n.A, b.norm_0.shared, make_act(nullptr, B, 1, H, W, 128));
-    Prep up = prep_of(seg); up.upshift = segshift;
+    // the seg map's operand at its own resolution; up blocks convolve it in phase form instead of upsampling it
+    const bool phase = segshift > 0 && n.L.phase_conv && b.norm_0.shared_ph.wtc && b.norm_1.shared_ph.wtc &&
+                       (!b.learned_shortcut || b.norm_s.shared_ph.wtc) && b.norm_0.phase_shift == segshift;
+    const int sh = phase ? 0 : segshift;
+    Opd seg_op = conv_tc_alloc_operand(*n.A, b.norm_0.shared, make_act(nullptr, B, 1, seg.H << sh, seg.W << sh, 128));
+    Prep up = prep_of(seg); up.upshift = sh;
     prep_planes(n.L, up, seg_op, nullptr);
-    spade_block_tc(n, b, x, xup, seg_op, out);
+    spade_block_tc(n, b, x, xup, seg_op, phase ? segshift : 0, out);
     n.A->reset(m0);
     return out;
   }

@@ -184,7 +184,8 @@ __device__ __forceinline__ void tc_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;                             // 2 role warps + 4 epilogue warps
+constexpr int TC_THREADS_MAX = 320;                         // ... or 8 epilogue warps (conv_tc.cu, wide tiles)
 constexpr int A_TILE_BYTES = 128 * 128;
 constexpr int STG_LD = 36;                                  // floats per staged row (32 + pad, 16-B aligned)
 constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;              // one 32x32 fp32 staging tile per epilogue warp

@@ -188,10 +188,42 @@ HostConv read_sn_conv(const Table& t, const std::string& p, int Cout, int Cin, i
   return c;
 }
 
-SpadeNormW read_spade(cs_ctx* ctx, const Table& t, const std::string& p, int C) {
+// 3x3 conv applied to an input nearest-upsampled by f = 2^shift, rewritten on the low-resolution input: output phase
+// (a, b) sees the source rows {y-1, y} (a = 0), {y} (0 < a < f-1) or {y, y+1} (a = f-1), so the taps that hit the same
+// source pixel are summed.  Result: a 3x3 conv with f*f*Cout output rows (phase-major), zero where a phase has no tap.
+HostConv phase_conv(const HostConv& c, int shift) {
+  const int f = 1 << shift;
+  HostConv r;
+  r.Cout = c.Cout * f * f; r.Cin = c.Cin; r.KD = 1; r.KH = 3; r.KW = 3;
+  r.w.assign((size_t)r.Cout * c.Cin * 9, 0.f);
+  auto src_tap = [&](int a, int d) { return a == 0 ? (d == 0 ? 0 : 1) : (a == f - 1 ? (d == 2 ? 2 : 1) : 1); };
+  for (int a = 0; a < f; ++a)
+    for (int b = 0; b < f; ++b)
+      for (int co = 0; co < c.Cout; ++co)
+        for (int ci = 0; ci < c.Cin; ++ci) {
+          const float* w = c.w.data() + ((long)co * c.Cin + ci) * 9;
+          float* o = r.w.data() + (((long)(a * f + b) * c.Cout + co) * c.Cin + ci) * 9;
+          for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) o[src_tap(a, dy) * 3 + src_tap(b, dx)] += w[dy * 3 + dx];
+        }
+  if (!c.b.empty()) {
+    r.b.resize(r.Cout);
+    for (int p = 0; p < f * f; ++p) std::memcpy(r.b.data() + (long)p * c.Cout, c.b.data(), c.Cout * sizeof(float));
+  }
+  return r;
+}
+
+SpadeNormW read_spade(cs_ctx* ctx, const Table& t, const std::string& p, int C, int phase_shift = 0) {
   SpadeNormW s;                                                  // reference util.py:282-302
   s.C = C;
-  s.shared = pack(ctx, read_conv(t, p + ".mlp_shared.0", 128, 256, 1, 3, 3));
+  HostConv sh = read_conv(t, p + ".mlp_shared.0", 128, 256, 1, 3, 3);
+  s.shared = pack(ctx, sh);
+  if (phase_shift > 0) {
+    s.phase_shift = phase_shift;
+    s.shared_ph = pack(ctx, phase_conv(sh, phase_shift));
+    s.shared_ph.BN = 128;                       // one N tile per phase (the packed rows do not depend on the tile width)
+    s.shared_ph.Cout_p = s.shared_ph.Cout;
+  }
   HostConv g = read_conv(t, p + ".mlp_gamma", C, 128, 1, 3, 3);
   HostConv b = read_conv(t, p + ".mlp_beta", C, 128, 1, 3, 3);
   // gamma | beta as ONE conv whose output channels are interleaved in chunks of [gamma x16 | beta x16]: a 32-column
@@ -410,11 +442,12 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
       b.learned_shortcut = b.fin != b.fout;
       b.conv_0 = pack(ctx, read_sn_conv(t, p + ".conv_0", b.fmid, b.fin, 3, true));
       b.conv_1 = pack(ctx, read_sn_conv(t, p + ".conv_1", b.fout, b.fmid, 3, true));
-      b.norm_0 = read_spade(ctx, t, p + ".norm_0", b.fin);
-      b.norm_1 = read_spade(ctx, t, p + ".norm_1", b.fmid);
+      const int pshift = i == 6 ? 1 : (i == 7 ? 2 : 0);          // up_0 / up_1 read seg nearest-upsampled x2 / x4 (util.py:297)
+      b.norm_0 = read_spade(ctx, t, p + ".norm_0", b.fin, pshift);
+      b.norm_1 = read_spade(ctx, t, p + ".norm_1", b.fmid, pshift);
       if (b.learned_shortcut) {
         b.conv_s = pack(ctx, read_sn_conv(t, p + ".conv_s", b.fout, b.fin, 1, false));
-        b.norm_s = read_spade(ctx, t, p + ".norm_s", b.fin);
+        b.norm_s = read_spade(ctx, t, p + ".norm_s", b.fin, pshift);
       }
     }
   }

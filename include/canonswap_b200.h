@@ -66,6 +66,7 @@ typedef struct cs_tensor_desc {
 #define CS_OPT_TC_COMP 5         /* tensor-core accumulate-truncation compensation per chained MMA, units of 1e-10 (default 120, 0 = off) */
 #define CS_OPT_TC_PAIR 6         /* 1 = tcgen05 pair mode (cta_group::2 over 2-CTA clusters) for wide N tiles */
 #define CS_OPT_TC_STACKED3 7     /* 1 (default) = depth-stacked kernel for the 32->32 3x3x3 volume convs, 0 = generic implicit GEMM */
+#define CS_OPT_TC_CORESIDENT 8   /* 1 = short-K wide tiles as two co-resident single-accumulator pair CTAs per SM (default 0) */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

@@ -35,6 +35,8 @@ CASES = [
     (8, 1, 256, 256, 64, 64, (1, 3, 3), (0, 1, 1), 1),
     (8, 1, 256, 256, 128, 64, (1, 3, 3), (0, 1, 1), 1),
     (8, 1, 128, 128, 256, 256, (1, 3, 3), (0, 1, 1), 1),
+    (8, 1, 256, 256, 128, 512, (1, 3, 3), (0, 1, 1), 1),
+    (8, 1, 64, 64, 256, 512, (1, 3, 3), (0, 1, 1), 1),
     # the depth-stacked 32->32 3x3x3 kernel (impl 4)
     (1, 16, 16, 8, 32, 32, (3, 3, 3), (1, 1, 1), 5),
     (2, 16, 24, 40, 32, 32, (3, 3, 3), (1, 1, 1), 5),
@@ -50,19 +52,21 @@ CASES = [
 
 def main():
     passes = [3]
-    comps = [int(a) for a in sys.argv[1:] if not a.startswith("nopair")] or [120]
+    comps = [int(a) for a in sys.argv[1:] if a[0].isdigit()] or [120]
     pair = 0 if "nopair" in sys.argv[1:] else 1
+    cores = 1 if "cores" in sys.argv[1:] else 0
     eng = Engine(None, net_hw=(128, 128), max_batch=1, device=0)
     g = torch.Generator(device="cuda").manual_seed(7)
     for comp in comps:
       for np_ in passes:
         eng.set_option(_lib.CS_OPT_TC_COMP, comp)
         eng.set_option(_lib.CS_OPT_TC_PAIR, pair)
+        eng.set_option(_lib.CS_OPT_TC_CORESIDENT, cores)
         for (B, D, H, Wd, Cin, Cout, k, pad, timed) in CASES:
             x = torch.randn(B, D, H, Wd, Cin, device="cuda", generator=g)
             w = torch.randn(Cout, Cin, *k, device="cuda", generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5
             b = torch.randn(Cout, device="cuda", generator=g)
-            tag = f"comp={comp} pair={pair} B{B} D{D} {H}x{Wd} {Cin}->{Cout} k{k}"
+            tag = f"comp={comp} pair={pair} cores={cores} B{B} D{D} {H}x{Wd} {Cin}->{Cout} k{k}"
             impl, act = (4, 2) if timed >= 5 else ((3, 0) if timed >= 3 else (2, 2))
             timed = timed in (1, 4, 6)
             try:
