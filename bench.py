@@ -257,13 +257,19 @@ def main():
         d = fam[dom]
         if d["ms"] > 0:
             ach = d["flops"] / (d["ms"] * 1e9)
+            traffic = None                                # dram bytes per launch of the same kernels, from the committed ncu pass
+            tp = os.path.join(ROOT, "profiles", "conv_family_traffic.json")
+            if dom == "conv_tcgen05" and os.path.exists(tp):
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                        "frac": ach / tf_peak, "traffic": None, "peak_source": f"{src} bf16 sustained (MEASURED_PEAKS.json)",
+                        "frac": ach / tf_peak, "traffic": traffic, "peak_source": f"{src} bf16 sustained (MEASURED_PEAKS.json)",
                         "avg_launch_ms": d["ms"] / max(1, d["launches"]),
                         "algorithmic_flops_per_launch": d["flops"] / max(1, d["launches"]),
                         "note": "achieved = algorithmic fp32-equivalent FLOPs (2*MAC) of all launches of the family / "
-                                "summed CUDA-event durations; the tcgen05 path spends 3 bf16 MMAs per algorithmic MAC "
-                                "(split-bf16 for the 1e-3 fp32 parity bar), so its ceiling is 1/3 of peak"}
+                                "summed CUDA-event durations (conv_tc / conv7_tc / conv3s_tc kernels); the tcgen05 path spends "
+                                "3 fp16 MMAs per algorithmic MAC (split-fp16 operands for the 1e-3 fp32 parity bar), so its "
+                                "ceiling is 1/3 of the 16-bit peak; traffic = dram bytes per launch from the committed ncu "
+                                "pass (profiles/conv_family_traffic.json)"}
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only) -----------------
     cpu = None
@@ -278,7 +284,7 @@ def main():
         print(json.dumps({
             "metric": "face-swap frames/sec @512px", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (split-bf16 x3 tcgen05 MMA, fp32 accumulate)" if args.conv_impl == 0 else "f32",
+            "vs_baseline": None, "dtype": "f32 (split-fp16 x3 tcgen05 MMA, fp32 accumulate)" if args.conv_impl == 0 else "f32",
             "data": "synthetic",
             "config": {"workload": "512x512 frames (net 256x256), 256-frame synthetic clip, batch 8 per step per GPU, "
                                    "core path pipeline_e2e.py:242-267 (configs[2])",

@@ -208,19 +208,21 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
     const int q = warp & 3;
     const int eg = (warp - 2) >> 2;
     float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + (eg * 4 + q) * 32 * STG_LD;
-    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    // row mapping of the coalesced phase: 4 rows x 8 lanes (x 8 passes); SPADE: 8 rows x 4 lanes (x 4 passes)
+    constexpr int RSTEP = SPADE ? 8 : 4;
+    const int sub = SPADE ? (lane >> 2) : (lane >> 3), c4 = (lane & 7) * 4;
     long yoff[8], roff[RES ? 8 : 1], epix[EMIT ? 8 : 1], xoff[SPADE ? 8 : 1];
     int sbase[SPADE ? 8 : 1];
     float mu[8];
     uint32_t vmask = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      int r = q * 32 + sub + 4 * i;
+      int r = q * 32 + sub + RSTEP * i;
       const int ow = w0 + (r & ((1 << k.lbw) - 1)); r >>= k.lbw;
       const int oh = h0 + (r & ((1 << k.lbh) - 1)); r >>= k.lbh;
       const int od = d0 + (r & ((1 << k.lbd) - 1)); r >>= k.lbd;
       const int ob = b0 + r;
-      const bool valid = ow < k.W && oh < k.H && od < k.D && ob < k.B;
+      const bool valid = (SPADE ? i < 4 : true) && ow < k.W && oh < k.H && od < k.D && ob < k.B;
       if (valid) vmask |= 1u << i;
       const int oh2 = (oh << k.ph_s) + ph_a, ow2 = (ow << k.ph_s) + ph_b;        // output position (phase mode: upsampled grid)
       yoff[i] = ob * k.yb + od * k.yd + oh2 * k.yh + ow2 * k.yw;
@@ -279,35 +281,38 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
       }
       __syncwarp();
       if constexpr (SPADE) {
-        // chunk = [gamma of 16 channels | beta of the same 16 channels]; lane -> (row group, channel pair)
-        const int cc = (lane & 7) * 2;
+        // chunk = [gamma of 16 channels | beta of the same 16 channels]; lane -> (row of 8, 4 of the 16 channels)
+        const int cc = (lane & 3) * 4;
         const int ncol = n0 + c0;
         const int ch = (ncol >> 1) + cc;
-        float bg[2] = {0.f, 0.f}, bb[2] = {0.f, 0.f};
+        float4 bg = make_float4(0.f, 0.f, 0.f, 0.f), bb = bg;
         if (k.bias) {
-          bg[0] = __ldg(k.bias + ncol + cc); bg[1] = __ldg(k.bias + ncol + cc + 1);
-          bb[0] = __ldg(k.bias + ncol + 16 + cc); bb[1] = __ldg(k.bias + ncol + 16 + cc + 1);
+          bg = __ldg(reinterpret_cast<const float4*>(k.bias + ncol + cc));
+          bb = __ldg(reinterpret_cast<const float4*>(k.bias + ncol + 16 + cc));
         }
-        float2 xv[8];
+        float4 xv[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          xv[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float2*>(k.sp_x + xoff[i] + ch) : make_float2(0.f, 0.f);
+        for (int i = 0; i < 4; ++i)
+          xv[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float4*>(k.sp_x + xoff[i] + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           if (!((vmask >> i) & 1u)) continue;
-          const float* trp = tile + (sub + 4 * i) * STG_LD;
-          const float2 g = *reinterpret_cast<const float2*>(trp + cc);
-          const float2 bt = *reinterpret_cast<const float2*>(trp + 16 + cc);
-          const float2 mn = __ldg(reinterpret_cast<const float2*>(k.sp_mean + sbase[i] + ch));
-          const float2 rs = __ldg(reinterpret_cast<const float2*>(k.sp_rstd + sbase[i] + ch));
-          float v0 = ((xv[i].x - mn.x) * rs.x) * (1.f + (g.x + bg[0])) + (bt.x + bb[0]);
-          float v1 = ((xv[i].y - mn.y) * rs.y) * (1.f + (g.y + bg[1])) + (bt.y + bb[1]);
+          const float* trp = tile + (sub + 8 * i) * STG_LD;
+          const float4 g = *reinterpret_cast<const float4*>(trp + cc);
+          const float4 bt = *reinterpret_cast<const float4*>(trp + 16 + cc);
+          const float4 mn = __ldg(reinterpret_cast<const float4*>(k.sp_mean + sbase[i] + ch));
+          const float4 rs = __ldg(reinterpret_cast<const float4*>(k.sp_rstd + sbase[i] + ch));
+          float v0 = ((xv[i].x - mn.x) * rs.x) * (1.f + (g.x + bg.x)) + (bt.x + bb.x);
+          float v1 = ((xv[i].y - mn.y) * rs.y) * (1.f + (g.y + bg.y)) + (bt.y + bb.y);
+          float v2 = ((xv[i].z - mn.z) * rs.z) * (1.f + (g.z + bg.z)) + (bt.z + bb.z);
+          float v3 = ((xv[i].w - mn.w) * rs.w) * (1.f + (g.w + bg.w)) + (bt.w + bb.w);
           v0 = apply_act(v0, k.eact, k.eslope); v1 = apply_act(v1, k.eact, k.eslope);
-          uint32_t hv, lv;
-          split_operand2(v0, v1, hv, lv);
+          v2 = apply_act(v2, k.eact, k.eslope); v3 = apply_act(v3, k.eact, k.eslope);
+          uint2 hv, lv;
+          split_operand4(v0, v1, v2, v3, hv, lv);
           __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (ch >> 5) * 64 + (ch & 31);
-          *reinterpret_cast<uint32_t*>(ep) = hv;
-          *reinterpret_cast<uint32_t*>(ep + 32) = lv;
+          *reinterpret_cast<uint2*>(ep) = hv;
+          *reinterpret_cast<uint2*>(ep + 32) = lv;
         }
         __syncwarp();
         continue;
