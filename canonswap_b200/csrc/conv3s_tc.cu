@@ -24,7 +24,7 @@ namespace {
 
 constexpr int C3_BTAP_BYTES = 96 * 128;                   // one in-plane tap: 3 depth taps x 32 couts x [hi 32 | lo 32]
 constexpr int C3_B_BYTES = 9 * C3_BTAP_BYTES;             // 108 KB resident weights
-constexpr int C3_STAGES = 5;
+constexpr int C3_STAGES = 6;                              // 6 x 16 KB in flight: the A stream is TMA-latency bound
 constexpr int C3_SMEM = C3_B_BYTES + C3_STAGES * A_TILE_BYTES + STG_BYTES + 1024 + 16 * C3_STAGES + 64;
 
 struct Conv3sK {
