@@ -13,6 +13,7 @@ from ._build import LIB
 CS_F32, CS_I64, CS_U8 = 0, 1, 2
 CS_FRAME_IN_U8_HWC = 1
 CS_FRAME_DEBUG_DECODES = 2
+CS_FRAME_V2I = 4
 CS_OPT_CONV_IMPL = 1
 CS_OPT_USE_GRAPH = 2
 CS_OPT_TC_PASSES = 3
@@ -21,6 +22,7 @@ CS_OPT_TC_COMP = 5
 CS_OPT_TC_PAIR = 6
 CS_OPT_TC_STACKED3 = 7
 CS_OPT_TC_CORESIDENT = 8
+CS_OPT_TC_BN_MAX = 9
 
 # every symbol include/canonswap_b200.h declares
 SYMBOLS = [

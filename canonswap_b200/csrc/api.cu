@@ -133,6 +133,12 @@ void body_frame(Net& n, const void* frames, const float* kp_t, const float* kp_c
   if (flags & CS_FRAME_IN_U8_HWC) ingest_u8(n.L, static_cast<const uint8_t*>(frames), img_cl, npix * 3);   // prepare_videos
   else nchw_to_cl(n.L, static_cast<const float*>(frames), img_cl, B, 3, (long)c->net_h * c->net_w, 0);
   run_F(n, img_cl, B, va);                                        // :242 f_s = extract_feature_3d(I_s)
+  if (flags & CS_FRAME_V2I) {                                     // can_swap_pipeline_v2i.py:308-309
+    run_warp(n, va, /*kp_source=*/kp_t, /*kp_driving=*/kp_can, B, vb, occ, nullptr);
+    run_warp_out(n, vb, occ, B, o256);
+    run_spade(n, o256, B, out_f32, out_u8);
+    return;
+  }
   run_warp(n, va, /*kp_source=*/kp_t, /*kp_driving=*/kp_can, B, vb, occ, nullptr);   // :244 warp(f_s, x_t, x_can)
   if (flags & CS_FRAME_DEBUG_DECODES) {                           // :248 rec_can = conv_decode(f_can, occ)
     run_warp_out(n, vb, occ, B, o256);
@@ -248,6 +254,9 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
     case CS_OPT_TC_COMP:
       if (value < 0 || value > 1000) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_COMP: value must be in [0, 1000]");
       ctx->tc_comp = value; return CS_OK;
+    case CS_OPT_TC_BN_MAX:
+      if (value != 0 && (value < 16 || value > 256 || value % 16)) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_BN_MAX: 0 or a multiple of 16 in [16, 256]");
+      ctx->tc_bn_max = value; return CS_OK;
     case CS_OPT_TC_CORESIDENT:
       ctx->tc_cores = value ? 1 : 0; return CS_OK;
     case CS_OPT_TC_STACKED3:
@@ -354,7 +363,7 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
   CS_API_BEGIN(ctx)
   check_batch(ctx, B);
   CS_REQUIRE(frames && kp_t && kp_can && (out_f32 || out_u8), CS_ERR_INVALID, "cs_frame: null tensor");
-  CS_REQUIRE(ctx->identity_set, CS_ERR_STATE, "cs_frame before cs_set_identity");
+  CS_REQUIRE(ctx->identity_set || (flags & CS_FRAME_V2I), CS_ERR_STATE, "cs_frame before cs_set_identity");
   Net n = make_net(ctx, stream, false);
   ctx->arena.reset(0);
   if (!ctx->use_graph || ctx->prof.on) {

@@ -483,6 +483,7 @@ void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream) {
   const int nblk = (w.Cin + 31) / 32;
   int BN = pick_bn(w.Cout);
   if (w.taps() * nblk * 2 > 1024 && BN > 128) BN = 128;      // deep K: 4 accumulator sets instead of 2
+  if (ctx->tc_bn_max > 0 && BN > ctx->tc_bn_max) BN = ctx->tc_bn_max;
   const int Cout_p = round_up(w.Cout, BN);
   const size_t n = (size_t)Cout_p * w.taps() * nblk * 64;
   if (!w.wtc) w.wtc = static_cast<__nv_bfloat16*>(ctx->dmalloc(n * sizeof(__nv_bfloat16)));

@@ -200,17 +200,19 @@ class Engine:
 
     # ---- the fused loop body --------------------------------------------------------------------
     def frame(self, frames: torch.Tensor, kp_t: torch.Tensor, kp_can: torch.Tensor, out_u8: Optional[torch.Tensor] = None,
-              out_f32: Optional[torch.Tensor] = None, debug_decodes: bool = False):
+              out_f32: Optional[torch.Tensor] = None, debug_decodes: bool = False, v2i: bool = False):
         """One batch of the per-frame loop body (reference can_swap_pipeline_e2e.py:242-267).
 
         frames: [B,net_h,net_w,3] uint8 (HWC, as cropped) or [B,3,net_h,net_w] fp32 in [0,1];
         kp_t = x_t_info['x_s'], kp_can = scale * kp  (both [B,21,3]).
         Returns (out_u8 [B,2H,2W,3] uint8, out_f32 [B,3,2H,2W] or None).
         """
-        if self._identity is None:
+        if self._identity is None and not v2i:
             raise CanonSwapError("frame: no identity set (call set_identity first)")
         B = self._batch(frames)
         flags = _lib.CS_FRAME_DEBUG_DECODES if debug_decodes else 0
+        if v2i:      # reference can_swap_pipeline_v2i.py:308-309: kp_t = kp_source, kp_can = kp_driving, no swap / refine
+            flags |= _lib.CS_FRAME_V2I
         if frames.dtype == torch.uint8:
             fr = self._in(frames, (B, self.net_h, self.net_w, 3), dtype=torch.uint8, name="frames")
             flags |= _lib.CS_FRAME_IN_U8_HWC

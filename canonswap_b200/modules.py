@@ -320,5 +320,14 @@ class can_swapper(object):
         eng = self._hub.engine(hw, int(frames.shape[0]))
         return eng.frame(frames, x_t, x_can, out_u8=out_u8, out_f32=out_f32, debug_decodes=debug_decodes)
 
+    def animate_frames(self, frames: torch.Tensor, kp_source: torch.Tensor, kp_driving: torch.Tensor, out_u8=None, out_f32=None):
+        """The per-frame body of the video-to-image pipeline (reference can_swap_pipeline_v2i.py:308-309) in one call:
+        warp_decode(extract_feature_3d(frames), kp_source, kp_driving). Returns (u8 [B,2H,2W,3], fp32 or None)."""
+        if not frames.is_cuda:
+            raise CanonSwapError("animate_frames: frames must be on the CUDA device")
+        hw = (int(frames.shape[1]), int(frames.shape[2])) if frames.dtype == torch.uint8 else (int(frames.shape[2]), int(frames.shape[3]))
+        eng = self._hub.engine(hw, int(frames.shape[0]))
+        return eng.frame(frames, kp_source, kp_driving, out_u8=out_u8, out_f32=out_f32, v2i=True)
+
     def engine(self, net_hw=(256, 256), batch: int = 1) -> Engine:
         return self._hub.engine(tuple(net_hw), batch)

@@ -58,6 +58,9 @@ typedef struct cs_tensor_desc {
 /* flags of cs_frame */
 #define CS_FRAME_IN_U8_HWC   1   /* frames are [B,net_h,net_w,3] u8 (else [B,3,net_h,net_w] fp32)   */
 #define CS_FRAME_DEBUG_DECODES 2 /* also run the two debug decodes of pipeline_e2e.py:248,257 (results discarded) */
+#define CS_FRAME_V2I         4   /* video-to-image per-frame body (can_swap_pipeline_v2i.py:308-309) instead of the e2e one:
+                                    out = warp_decode(extract_feature_3d(frames), kp_source = kp_t, kp_driving = kp_can);
+                                    no identity needed (the swap ran once per source, outside the loop) */
 
 /* options of cs_set_option */
 #define CS_OPT_CONV_IMPL 1       /* 0 = auto (tcgen05 where eligible), 1 = force SIMT fp32 convs (debug) */
@@ -67,6 +70,7 @@ typedef struct cs_tensor_desc {
 #define CS_OPT_TC_PAIR 6         /* 1 = tcgen05 pair mode (cta_group::2 over 2-CTA clusters) for wide N tiles */
 #define CS_OPT_TC_STACKED3 7     /* 1 (default) = depth-stacked kernel for the 32->32 3x3x3 volume convs, 0 = generic implicit GEMM */
 #define CS_OPT_TC_CORESIDENT 8   /* 1 = short-K wide tiles as two co-resident single-accumulator pair CTAs per SM (default 0) */
+#define CS_OPT_TC_BN_MAX 9       /* cap on the N tile of convs packed AFTER the call (0 = automatic; experiments) */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

@@ -318,3 +318,13 @@ def frame(weights, I_s, x_t, x_can, source_id, debug_decodes=False):
         r["occ"], r["deformation"], r["warp_out"] = wf["occlusion_map"], wf["deformation"], wf["out"]
         r["out"], r["logits"] = spade_decoder(sdG, wf["out"], return_logits=True)
     return r
+
+
+def frame_v2i(weights, I, kp_source, kp_driving):
+    """The per-frame body of the video-to-image pipeline, reference can_swap_pipeline_v2i.py:308-309:
+    out = warp_decode(extract_feature_3d(I), kp_source, kp_driving)  (can_swap_e2e.py:286-308)."""
+    sdF, sdW, sdG = (weights["appearance_feature_extractor"], weights["warping_module"], weights["spade_generator"])
+    with torch.no_grad():
+        f = appearance_feature_extractor(sdF, I)
+        wf = warping_forward(sdW, f, kp_driving=kp_driving, kp_source=kp_source)
+        return spade_decoder(sdG, wf["out"])

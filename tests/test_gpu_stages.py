@@ -167,6 +167,54 @@ def test_cuda_graph_replay_is_bit_identical(case128):
         eng.set_option(_lib.CS_OPT_USE_GRAPH, 0)
 
 
+def test_frame_1024px_stress_config(synth_w):
+    """BASELINE config 5 resolution (1024-px frames = net 512x512, volume 32x16x128x128): one frame against the oracle."""
+    from canonswap_b200.engine import Engine
+    inp = synth.synth_inputs(1, 512, seed=11)
+    ref = O.frame(synth_w, inp["frames"], inp["x_t"], inp["x_can"], inp["source_id"])["out"]
+    eng = Engine(synth_w, net_hw=(512, 512), max_batch=1, device=0)
+    try:
+        eng.set_identity(inp["source_id"].cuda())
+        out = torch.empty(1, 3, 1024, 1024, device="cuda")
+        eng.frame(inp["frames"].cuda(), inp["x_t"].cuda(), inp["x_can"].cuda(), out_f32=out)
+        d = (out.cpu() - ref).abs().max().item()
+        assert d <= TOL, d
+    finally:
+        eng.close()
+
+
+def test_frame_rectangular_and_ragged_batch(synth_w):
+    """Non-square network input (128 x 256) and a batch that is not a multiple of anything (B = 3 of max_batch 4)."""
+    from canonswap_b200.engine import Engine
+    g = torch.Generator().manual_seed(21)
+    frames = torch.rand(3, 3, 128, 256, generator=g)
+    x_can = (0.3 * torch.randn(3, 21, 3, generator=g)).clamp(-0.9, 0.9)
+    x_t = x_can + 0.05 * torch.randn(3, 21, 3, generator=g)
+    sid = torch.nn.functional.normalize(torch.randn(1, 512, generator=g))
+    ref = O.frame(synth_w, frames, x_t, x_can, sid)["out"]
+    eng = Engine(synth_w, net_hw=(128, 256), max_batch=4, device=0)
+    try:
+        eng.set_identity(sid.cuda())
+        out = torch.empty(3, 3, 256, 512, device="cuda")
+        eng.frame(frames.cuda(), x_t.cuda(), x_can.cuda(), out_f32=out)
+        assert (out.cpu() - ref).abs().max().item() <= TOL
+    finally:
+        eng.close()
+
+
+def test_v2i_frame_body(case128, synth_w):
+    """the video-to-image per-frame body (can_swap_pipeline_v2i.py:308-309) on the same kernels,
+    fused (CS_FRAME_V2I) and through the mirror's extract_feature_3d + warp_decode."""
+    eng, inp, ref = case128
+    exp = O.frame_v2i(synth_w, inp["frames"].cpu(), inp["x_can"].cpu(), inp["x_t"].cpu())
+    out = torch.empty(2, 3, 256, 256, device="cuda")
+    eng.frame(inp["frames"], inp["x_can"], inp["x_t"], out_f32=out, v2i=True)
+    _close(out, exp, "v2i frame")
+    f = eng.appearance(inp["frames"])
+    wf = eng.warp_forward(f, kp_driving=inp["x_t"], kp_source=inp["x_can"])
+    _close(eng.spade(wf["out"]), exp, "v2i staged")
+
+
 def test_batch_independence(case128):
     """Frames are independent given the identity: a batch of 2 equals two batches of 1 bit-for-bit
     (the property the multi-GPU frame sharding relies on)."""
