@@ -139,6 +139,8 @@ def main():
     ap.add_argument("--conv-impl", type=int, default=0, help="0 auto (tcgen05 where eligible), 1 force fp32 SIMT convs")
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the CPU baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lanes", type=int, default=None, help="CS_OPT_LANES: concurrent sub-batches of a graph-replayed step (1 | 2)")
+    ap.add_argument("--opt", action="append", default=[], help="experiment: library option id=value (cs_set_option), repeatable")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of a step individually (default: CUDA-graph replay)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -172,6 +174,11 @@ def main():
     if not args.no_graph:
         from canonswap_b200 import _lib
         eng.set_option(_lib.CS_OPT_USE_GRAPH, 1)          # cs_frame replays a captured CUDA graph (same kernels, fewer launch gaps)
+        if args.lanes:
+            eng.set_option(_lib.CS_OPT_LANES, args.lanes)
+    for kv in args.opt:
+        oid, val = kv.split("=")
+        eng.set_option(int(oid), int(val))
     # this rank's frames: i % world == rank (round-robin, BASELINE config 4)
     mine = list(range(rank, CLIP, world))
     n_batches = len(mine) // B
@@ -290,7 +297,7 @@ def main():
                                    "core path pipeline_e2e.py:242-267 (configs[2])",
                        "frames_per_step_per_gpu": B, "sharding": "frame i -> rank i % N, identity NCCL broadcast",
                        "l2": "per-step working set (activations > 1 GB, weights 0.6 GB) exceeds the 126 MB L2; "
-                             "32 distinct input batches rotate", "conv_impl": args.conv_impl, "cuda_graph": not args.no_graph,
+                             "32 distinct input batches rotate", "conv_impl": args.conv_impl, "cuda_graph": not args.no_graph, "lanes": args.lanes,
                        "gflop_per_frame": GFLOP_PER_FRAME},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "families": families, "achieved_tflops_whole_step": value * GFLOP_PER_FRAME / 1000.0,

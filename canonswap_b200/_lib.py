@@ -23,12 +23,13 @@ CS_OPT_TC_PAIR = 6
 CS_OPT_TC_STACKED3 = 7
 CS_OPT_TC_CORESIDENT = 8
 CS_OPT_TC_BN_MAX = 9
+CS_OPT_LANES = 10
 
 # every symbol include/canonswap_b200.h declares
 SYMBOLS = [
     "cs_create", "cs_destroy", "cs_last_error", "cs_set_option", "cs_launch_count", "cs_workspace_bytes",
     "cs_load_weights", "cs_set_identity", "cs_appearance", "cs_warp", "cs_warp_out", "cs_warp_forward",
-    "cs_swap", "cs_refine", "cs_spade", "cs_frame", "cs_profile", "cs_profile_read", "cs_test_conv", "cs_test_grid_sample3d",
+    "cs_swap", "cs_refine", "cs_spade", "cs_frame", "cs_profile", "cs_profile_read", "cs_profile_dump", "cs_test_conv", "cs_test_grid_sample3d",
     "cs_test_instance_stats",
 ]
 
@@ -73,6 +74,7 @@ def load() -> C.CDLL:
     lib.cs_frame.argtypes = [vp, p, p, p, p, p, i, i, vp]
     lib.cs_profile.argtypes = [vp, i]
     lib.cs_profile_read.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.cs_profile_dump.argtypes = [vp, C.c_char_p, i]
     lib.cs_test_conv.argtypes = [vp, p, p, p, p] + [i] * 13 + [f, i, vp]
     lib.cs_test_grid_sample3d.argtypes = [vp, p, p, p, i, i, i, i, i, vp]
     lib.cs_test_instance_stats.argtypes = [vp, p, p, p, i, i, i, f, vp]

@@ -34,6 +34,7 @@ Net make_net(cs_ctx* ctx, void* stream, bool dry) {
   Net n;
   n.ctx = ctx;
   n.A = &ctx->arena;
+  n.stats = ctx->stats_scratch;
   n.L.stream = static_cast<cudaStream_t>(stream);
   n.L.dry = dry;
   n.L.counter = dry ? nullptr : &ctx->launches;
@@ -179,6 +180,19 @@ void size_workspace(cs_ctx* ctx) {
                              CS_FRAME_IN_U8_HWC | CS_FRAME_DEBUG_DECODES);
     }
   }
+  // two-lane replay (CS_OPT_LANES): each half of the arena must hold cs_frame at ceil(max_batch / 2)
+  size_t full_high = A.high;
+  {
+    Net n = make_net(ctx, nullptr, true);
+    A.high = 0;
+    for (int impl = 0; impl < 2; ++impl) {
+      n.L.conv_impl = impl;
+      A.reset(0); body_frame(n, fake, fake, fake, fake, reinterpret_cast<uint8_t*>(fake), (B + 1) / 2,
+                             CS_FRAME_IN_U8_HWC | CS_FRAME_DEBUG_DECODES);
+    }
+    ctx->arena_half_need = A.high + 4096;
+    A.high = full_high > 2 * ctx->arena_half_need ? full_high : 2 * ctx->arena_half_need;
+  }
   ctx->identity_set = id;
   size_t need = A.high + (1 << 20);
   A.measuring = false; A.off = 0; A.high = 0;
@@ -216,6 +230,7 @@ int cs_create(cs_ctx** out, int device, int max_batch, int net_h, int net_w) {
     size_t sb = sizeof(double) * 2 * (size_t)max_batch * 512;
     if (sb < 4096) sb = 4096;
     ctx->stats_scratch = static_cast<double*>(ctx->dmalloc(sb));
+    ctx->stats_scratch2 = static_cast<double*>(ctx->dmalloc(sb));
   } catch (const std::exception& ex) {
     if (ctx) cs_destroy(ctx);
     return fail(nullptr, CS_ERR_CUDA, ex.what());
@@ -230,6 +245,9 @@ void cs_destroy(cs_ctx* ctx) {
   cudaDeviceSynchronize();
   ctx->drop_graphs();
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
+  if (ctx->cap_stream2) cudaStreamDestroy(ctx->cap_stream2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (void* p : ctx->owned) cudaFree(p);
   delete ctx;
 }
@@ -265,6 +283,9 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
       ctx->tc_pair = value ? 1 : 0; return CS_OK;
     case CS_OPT_USE_GRAPH:
       ctx->use_graph = value ? 1 : 0; return CS_OK;
+    case CS_OPT_LANES:
+      if (value < 1 || value > 2) return fail(ctx, CS_ERR_INVALID, "CS_OPT_LANES: value must be 1 or 2");
+      ctx->lanes = value; return CS_OK;
     default: return fail(ctx, CS_ERR_INVALID, "unknown option");
   }
 }
@@ -403,8 +424,34 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
         n.L.stream = cst;
         CS_CUDA(cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal));
         try {
-          body_frame(n, ctx->g_frames, ctx->g_kpt, ctx->g_kpc, out_f32 ? ctx->g_out32 : nullptr, out_u8 ? ctx->g_outu8 : nullptr, B,
-                     flags);
+          if (ctx->lanes == 2 && B >= 2) {
+            // two concurrent sub-batches on forked capture streams: frames are independent, so the tail wave of one lane's
+            // kernel is filled by CTAs of the other lane's (each lane owns half of the arena and its own statistics scratch)
+            const int B0 = (B + 1) / 2, B1 = B - B0;
+            if (!ctx->cap_stream2) CS_CUDA(cudaStreamCreateWithFlags(&ctx->cap_stream2, cudaStreamNonBlocking));
+            if (!ctx->ev_fork) CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            if (!ctx->ev_join) CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+            Arena a0 = ctx->arena, a1 = ctx->arena;
+            const size_t half = (ctx->arena.cap / 2) & ~size_t(255);
+            a0.cap = half; a0.off = 0; a0.high = 0;
+            a1.base = ctx->arena.base + half; a1.cap = ctx->arena.cap - half; a1.off = 0; a1.high = 0;
+            CS_CUDA(cudaEventRecord(ctx->ev_fork, cst));
+            CS_CUDA(cudaStreamWaitEvent(ctx->cap_stream2, ctx->ev_fork, 0));
+            const size_t px0 = (size_t)B0 * ctx->net_h * ctx->net_w;
+            const size_t in_off = (flags & CS_FRAME_IN_U8_HWC) ? px0 * 3 : px0 * 3 * sizeof(float);
+            Net n0 = n; n0.A = &a0;
+            Net n1 = n; n1.A = &a1; n1.L.stream = ctx->cap_stream2; n1.stats = ctx->stats_scratch2;
+            body_frame(n0, ctx->g_frames, ctx->g_kpt, ctx->g_kpc, out_f32 ? ctx->g_out32 : nullptr, out_u8 ? ctx->g_outu8 : nullptr,
+                       B0, flags);
+            body_frame(n1, static_cast<char*>(ctx->g_frames) + in_off, ctx->g_kpt + (size_t)B0 * NUM_KP * 3,
+                       ctx->g_kpc + (size_t)B0 * NUM_KP * 3, out_f32 ? ctx->g_out32 + px0 * 4 * 3 : nullptr,
+                       out_u8 ? ctx->g_outu8 + px0 * 4 * 3 : nullptr, B1, flags);
+            CS_CUDA(cudaEventRecord(ctx->ev_join, ctx->cap_stream2));
+            CS_CUDA(cudaStreamWaitEvent(cst, ctx->ev_join, 0));
+          } else {
+            body_frame(n, ctx->g_frames, ctx->g_kpt, ctx->g_kpc, out_f32 ? ctx->g_out32 : nullptr, out_u8 ? ctx->g_outu8 : nullptr, B,
+                       flags);
+          }
         } catch (...) {
           cudaStreamEndCapture(cst, &graph);
           if (graph) cudaGraphDestroy(graph);
@@ -452,6 +499,23 @@ int cs_profile_read(cs_ctx* ctx, double* out) {
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   ctx->prof.recs.clear();
+  CS_API_END(ctx)
+}
+
+int cs_profile_dump(cs_ctx* ctx, char* buf, int cap) {
+  CS_API_BEGIN(ctx)
+  CS_REQUIRE(buf != nullptr && cap > 0, CS_ERR_INVALID, "cs_profile_dump: bad buffer");
+  CS_CUDA(cudaDeviceSynchronize());
+  int off = 0;
+  buf[0] = 0;
+  int idx = 0;
+  for (auto& r : ctx->prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = -1.f;
+    int nw = snprintf(buf + off, (size_t)(cap - off), "%d,%d,%.6f,%.6e,%.6e,%s\n", idx++, r.kind, ms, r.flops, r.bytes, r.desc);
+    if (nw < 0 || nw >= cap - off) { buf[off] = 0; break; }
+    off += nw;
+  }
   CS_API_END(ctx)
 }
 

@@ -215,7 +215,7 @@ struct Arena {
 // optional per-launch CUDA-event timing, aggregated per kernel family (bench.py's roofline leg)
 enum ProfKind { PK_CONV_TC = 0, PK_CONV_SIMT = 1, PK_PREP = 2, PK_STATS = 3, PK_SAMPLE = 4, PK_OTHER = 5, PK_N = 6 };
 struct Profiler {
-  struct Rec { cudaEvent_t a, b; int kind; double flops, bytes; };
+  struct Rec { cudaEvent_t a, b; int kind; double flops, bytes; char desc[88]; };
   std::vector<Rec> recs;
   bool on = false;
 };
@@ -234,6 +234,7 @@ struct Launcher {            // everything a kernel launch helper needs
   bool pair = true;          // tcgen05 pair mode (cta_group::2, 2-CTA clusters) for wide N tiles
   float acc_comp = 120.f;     // accumulate-truncation compensation per chained MMA, in units of 1e-10 (0 = off)
   Profiler* prof = nullptr;
+  const char* tag = nullptr;  // stage label attached to profiler records
   void count() const { if (counter) ++*counter; }
 };
 
@@ -241,9 +242,10 @@ struct Launcher {            // everything a kernel launch helper needs
 struct ProfScope {
   const Launcher& L;
   size_t idx = (size_t)-1;
-  ProfScope(const Launcher& l, int kind, double flops, double bytes) : L(l) {
+  ProfScope(const Launcher& l, int kind, double flops, double bytes, const char* desc = nullptr) : L(l) {
     if (!L.prof || !L.prof->on || L.dry) return;
     Profiler::Rec r; r.kind = kind; r.flops = flops; r.bytes = bytes;
+    snprintf(r.desc, sizeof(r.desc), "%s%s%s", L.tag ? L.tag : "", L.tag ? " " : "", desc ? desc : "");
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
     cudaEventRecord(r.a, L.stream);
     idx = L.prof->recs.size();

@@ -304,7 +304,7 @@ void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& 
     g_attr3[dev & 63] = true;
   }
   const long M = (long)x.B * 16 * x.H * x.W;
-  ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * 32 * 32 * 27, 0.0);
+  ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * 32 * 32 * 27, 0.0, "conv3s");
   dim3 grid((unsigned)(k.ntw * k.nth * x.B));
   fns[k.res != nullptr][k.emit != nullptr]<<<grid, TC_THREADS, C3_SMEM, L.stream>>>(tmA, tmB, k);
   check_launch("conv3s_tc");

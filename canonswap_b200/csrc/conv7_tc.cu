@@ -339,7 +339,7 @@ void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* s
   }
   const long M = (long)x.B * 16 * x.H * x.W;
   {
-    ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * w.Cout * w.Cin * 343.0, 0.0);
+    ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * w.Cout * w.Cin * 343.0, 0.0, "conv7");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(gx, 16 / C7_GROUP, 7); cfg.blockDim = dim3(TC_THREADS); cfg.stream = L.stream;
     cfg.dynamicSmemBytes = pair ? C7Cfg<2>::SMEM : C7Cfg<1>::SMEM;
@@ -355,7 +355,7 @@ void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* s
   }
   {
     const long n4 = M * k.ldo / 4;
-    ProfScope ps(L, PK_OTHER, 0.0, (double)n4 * 16.0 * 8.0);
+    ProfScope ps(L, PK_OTHER, 0.0, (double)n4 * 16.0 * 8.0, "sum_parts");
     long blocks = (n4 + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
     sum_parts_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(scratch), k.part_stride / 4, 7, w.bias,
                                                            w.Cout, k.ldo / 4, reinterpret_cast<float4*>(out.p), n4);

@@ -242,10 +242,35 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
           asm volatile("prefetch.global.L2 [%0];" ::"l"(k.res + roff[i] + n0 + c));
       }
     }
+    // SPADE: the normalised input x_hat = (x - mean) * rstd of every chunk this warp will emit does not depend on the
+    // accumulators: it is gathered into registers here, i.e. while the MMAs of the tile are still running
+    // (<= 4 chunks per warp: 2 epilogue groups for BN > 64, checked by the host)
+    float4 xh[SPADE ? 4 : 1][SPADE ? 4 : 1];
+    if constexpr (SPADE) {
+      const int cc = (lane & 3) * 4;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c0 = (eg + ci * egroups) * 32;
+        const bool live = c0 < k.BN && n0 + c0 < k.Cout;
+        const int ch = ((n0 + c0) >> 1) + cc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xh[ci][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live && ((vmask >> i) & 1u)) {
+            const float4 xv = *reinterpret_cast<const float4*>(k.sp_x + xoff[i] + ch);
+            const float4 mn = __ldg(reinterpret_cast<const float4*>(k.sp_mean + sbase[i] + ch));
+            const float4 rs = __ldg(reinterpret_cast<const float4*>(k.sp_rstd + sbase[i] + ch));
+            xh[ci][i] = make_float4((xv.x - mn.x) * rs.x, (xv.y - mn.y) * rs.y, (xv.z - mn.z) * rs.z, (xv.w - mn.w) * rs.w);
+          }
+        }
+      }
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    int cidx = -1;
     for (int c0 = eg * 32; c0 < k.BN; c0 += 32 * egroups) {
+      ++cidx;
       if (n0 + c0 >= k.Cout) break;                         // warp-uniform
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -292,20 +317,21 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
         }
         float4 xv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          xv[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float4*>(k.sp_x + xoff[i] + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) {
+          xv[i] = xh[0][i];
+#pragma unroll
+          for (int ci = 1; ci < 4; ++ci) if (ci == cidx) xv[i] = xh[ci][i];
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (!((vmask >> i) & 1u)) continue;
           const float* trp = tile + (sub + 8 * i) * STG_LD;
           const float4 g = *reinterpret_cast<const float4*>(trp + cc);
           const float4 bt = *reinterpret_cast<const float4*>(trp + 16 + cc);
-          const float4 mn = __ldg(reinterpret_cast<const float4*>(k.sp_mean + sbase[i] + ch));
-          const float4 rs = __ldg(reinterpret_cast<const float4*>(k.sp_rstd + sbase[i] + ch));
-          float v0 = ((xv[i].x - mn.x) * rs.x) * (1.f + (g.x + bg.x)) + (bt.x + bb.x);
-          float v1 = ((xv[i].y - mn.y) * rs.y) * (1.f + (g.y + bg.y)) + (bt.y + bb.y);
-          float v2 = ((xv[i].z - mn.z) * rs.z) * (1.f + (g.z + bg.z)) + (bt.z + bb.z);
-          float v3 = ((xv[i].w - mn.w) * rs.w) * (1.f + (g.w + bg.w)) + (bt.w + bb.w);
+          float v0 = xv[i].x * (1.f + (g.x + bg.x)) + (bt.x + bb.x);
+          float v1 = xv[i].y * (1.f + (g.y + bg.y)) + (bt.y + bb.y);
+          float v2 = xv[i].z * (1.f + (g.z + bg.z)) + (bt.z + bb.z);
+          float v3 = xv[i].w * (1.f + (g.w + bg.w)) + (bt.w + bb.w);
           v0 = apply_act(v0, k.eact, k.eslope); v1 = apply_act(v1, k.eact, k.eslope);
           v2 = apply_act(v2, k.eact, k.eslope); v3 = apply_act(v3, k.eact, k.eslope);
           uint2 hv, lv;
@@ -604,6 +630,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   // thin-N tiles keep the footprint under ~100 KB so two CTAs share an SM (prologue / epilogue overlap)
   const int budget = ((k.BN <= 64 && k.tcols <= 256) || cores) ? 100 * 1024 : MAX_DYN_SMEM;
   const int egroups = (k.BN > 64 && !cores) ? 2 : 1;       // 8 epilogue warps on wide tiles (1 CTA per SM)
+  CS_REQUIRE(!k.sp_x || (k.BN + 32 * egroups - 1) / (32 * egroups) <= 4, CS_ERR_INVALID, "conv_tc: SPADE epilogue holds <= 4 chunks per warp");
   const int stg_bytes = egroups * STG_BYTES;
   int stages = (budget - 2048 - stg_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -653,7 +680,11 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   if (w.zrows > 0) CS_REQUIRE(bd == 1 && w.zrows % k.BN == 0, CS_ERR_INVALID, "conv_tc: depth-dependent weights need one depth per tile");
   dim3 grid(m_tiles, (unsigned)((w.zrows > 0 ? w.zrows : w.Cout_p) / k.BN));
   const long M = (long)x.B * g.Do * g.Ho * g.Wo;          // phase mode: the algorithmic conv runs on the upsampled grid
-  ProfScope pscope(L, PK_CONV_TC, 2.0 * (double)M * y.C * w.Cin * w.taps(), 0.0);
+  char desc[80];
+  snprintf(desc, sizeof(desc), "tc M=%ld Cin=%d Cout=%d k=%dx%dx%d BN=%d st=%d sets=%d %s%s%s%s%s grid=%ux%u", M, w.Cin, y.C, w.KD, w.KH, w.KW,
+           k.BN, stages, k.nsets, pair ? "pair " : "", k.res ? "res " : "", k.emit ? "emit " : "", k.sp_x ? "spade " : "", ps ? "phase " : "",
+           grid.x, grid.y);
+  ProfScope pscope(L, PK_CONV_TC, 2.0 * (double)M * y.C * w.Cin * w.taps(), 0.0, desc);
   const bool has_res = k.res != nullptr, has_emit = k.emit != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(64 + 128 * egroups); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;

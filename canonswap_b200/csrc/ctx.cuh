@@ -90,6 +90,11 @@ struct cs_ctx {
   cs::Arena arena;
   cs::Weights W;
   double* stats_scratch = nullptr; // [max_batch*512*2] double
+  double* stats_scratch2 = nullptr; // the second lane's (CS_OPT_LANES)
+  int lanes = 1;                   // CS_OPT_LANES: a graph-captured cs_frame runs as this many concurrent sub-batches
+  cudaStream_t cap_stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  size_t arena_half_need = 0;      // high-water mark of cs_frame at ceil(max_batch / 2)
   cs::Profiler prof;
   // CUDA-graph replay of cs_frame (CS_OPT_USE_GRAPH): the whole loop body is captured once per (B, flags, outputs)
   // on fixed staging buffers; a call then is copy-in -> graph launch -> copy-out on the caller's stream.
@@ -115,6 +120,7 @@ struct Net {                 // per-call view
   cs_ctx* ctx;
   Launcher L;
   Arena* A;
+  double* stats = nullptr;   // instance-statistics scratch of this lane
   const Weights& W() const { return ctx->W; }
 };
 

@@ -147,7 +147,7 @@ void conv_simt(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom& 
   k.vecA = (x.C % 4 == 0) && al4(x.sb) && al4(x.sd) && al4(x.sh) && al4(x.sw) && ((uintptr_t)x.p % 16 == 0);
   k.vecB = (w.Cout % 4 == 0) && ((uintptr_t)w.w32 % 16 == 0);
   dim3 grid((unsigned)((k.M + BM - 1) / BM), (w.Cout + BN - 1) / BN);
-  ProfScope ps(L, PK_CONV_SIMT, 2.0 * (double)k.M * w.Cout * w.Cin * w.taps(), 0.0);
+  ProfScope ps(L, PK_CONV_SIMT, 2.0 * (double)k.M * w.Cout * w.Cin * w.taps(), 0.0, "simt");
   conv_simt_kernel<<<grid, 256, 0, L.stream>>>(k);
   check_launch("conv_simt");
 }
@@ -200,7 +200,7 @@ void conv_cout1(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom&
   k.PD = g.PD; k.PH = g.PH; k.PW = g.PW; k.Do = g.Do; k.Ho = g.Ho; k.Wo = g.Wo;
   k.w = w.w32; k.bias_p = w.bias; k.act = act; k.y = y;
   k.M = (long)x.B * g.Do * g.Ho * g.Wo;
-  ProfScope ps(L, PK_CONV_SIMT, 2.0 * (double)k.M * w.Cin * w.taps(), 0.0);
+  ProfScope ps(L, PK_CONV_SIMT, 2.0 * (double)k.M * w.Cin * w.taps(), 0.0, "cout1");
   conv_cout1_kernel<<<(unsigned)((k.M + 7) / 8), 256, 0, L.stream>>>(k);
   check_launch("conv_cout1");
 }

@@ -169,7 +169,7 @@ static void launch_prep(const Launcher& L, PrepK& k) {
   if (L.dry) return;
   const long total = (long)k.B * k.D * k.H * k.W * k.Cout;
   // algorithmic bytes: every logical element read once (fp32) and written once (fp32 or hi+lo bf16)
-  ProfScope ps(L, PK_PREP, 0.0, (double)k.B * k.D * k.H * k.W * k.Cl * 4.0 * 2.0);
+  ProfScope ps(L, PK_PREP, 0.0, (double)k.B * k.D * k.H * k.W * k.Cl * 4.0 * 2.0, "prep");
   if (prep_vec_ok(k)) {
     long blocks = (total / 4 + 255) / 256;
     if (blocks > 148L * 16) blocks = 148L * 16;
@@ -283,7 +283,7 @@ void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, f
   if (L.dry) return;
   int C = x.C;
   long S = (long)x.D * x.H * x.W;
-  ProfScope ps(L, PK_STATS, 0.0, (double)x.B * S * C * 4.0);
+  ProfScope ps(L, PK_STATS, 0.0, (double)x.B * S * C * 4.0, "stats");
   CS_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * x.B * C, L.stream));
   const int C4 = C >> 2;
   const bool pow2 = C4 > 0 && (C4 & (C4 - 1)) == 0;
@@ -347,7 +347,7 @@ void adaptive_blend(const Launcher& L, const float* o2, const float* mask, const
   if (L.dry) return;
   long blocks = (P * 128 + 255) / 256;
   if (blocks > 148L * 16) blocks = 148L * 16;
-  ProfScope ps(L, PK_OTHER, 0.0, (double)P * (1024 + 512 + 512) * 4.0);
+  ProfScope ps(L, PK_OTHER, 0.0, (double)P * (1024 + 512 + 512) * 4.0, "blend");
   adaptive_blend_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(o2), mask,
                                                                reinterpret_cast<const float4*>(residual), relu,
                                                                reinterpret_cast<float4*>(y), opl, P);
@@ -472,7 +472,7 @@ void emit_image(const Launcher& L, const float* y, int Cs, float* img, uint8_t* 
   if (L.dry) return;
   long total = (long)B * 4 * H * W;
   long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
-  ProfScope ps(L, PK_OTHER, 0.0, (double)total * 3 * (4.0 + (img ? 4.0 : 0.0) + (u8 ? 1.0 : 0.0)));
+  ProfScope ps(L, PK_OTHER, 0.0, (double)total * 3 * (4.0 + (img ? 4.0 : 0.0) + (u8 ? 1.0 : 0.0)), "emit_image");
   emit_image_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(y, Cs, img, u8, B, H, W);
   check_launch("emit_image");
 }

@@ -93,7 +93,7 @@ void dm_input(const Launcher& L, const Act& c4, const float* kp_driving, const f
   CS_REQUIRE(c4.C == 4 && c4.sw == 4, -1, "dm_input: compressed feature must be dense 4-channel");
   long total = c4.pixels() * (K + 1);
   long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
-  ProfScope ps(L, PK_SAMPLE, 0.0, (double)c4.pixels() * (4 + 110) * 4.0);
+  ProfScope ps(L, PK_SAMPLE, 0.0, (double)c4.pixels() * (4 + 110) * 4.0, "dm_input");
   dm_input_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(c4.p), kp_driving, kp_source, K,
                                                          c4.B, c4.D, c4.H, c4.W, out.p, out.sb, out.sd, out.sh, out.sw);
   check_launch("dm_input");
@@ -167,7 +167,7 @@ void softmax_flow_warp(const Launcher& L, const Act& logits, const float* kp_dri
   long total = logits.pixels() * 8;
   long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
   // algorithmic bytes / voxel: 32 ch in + 32 ch out + 22 logits (22.5 MB / sample)
-  ProfScope ps(L, PK_SAMPLE, 0.0, (double)logits.pixels() * (32 + 32 + (K + 1)) * 4.0);
+  ProfScope ps(L, PK_SAMPLE, 0.0, (double)logits.pixels() * (32 + 32 + (K + 1)) * 4.0, "flow_warp");
   softmax_flow_warp_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(logits.p, logits.sb, logits.sd, logits.sh, logits.sw,
                                                                   kp_driving, kp_source, K, logits.B, logits.D, logits.H,
                                                                   logits.W, vol, out, deformation);
@@ -239,7 +239,7 @@ void occlusion_gather(const Launcher& L, const Act& Y, const float* bias, float*
   CS_REQUIRE(Y.C >= 49 && Y.sh == (long)Y.W * Y.sw && Y.sd == (long)Y.H * Y.sh && Y.sb == (long)Y.D * Y.sd, -1,
              "occlusion_gather: Y must be dense [B,D,H,W,>=49]");
   const long warps = (long)Y.B * Y.H * ((Y.W + 31) / 32);
-  ProfScope ps(L, PK_SAMPLE, 0.0, (double)Y.pixels() * 49 * 4.0);
+  ProfScope ps(L, PK_SAMPLE, 0.0, (double)Y.pixels() * 49 * 4.0, "occ_gather");
   occlusion_gather_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, L.stream>>>(Y.p, bias, occ, Y.B, Y.D, Y.H, Y.W, (int)Y.sw);
   check_launch("occlusion_gather");
 }

@@ -198,12 +198,12 @@ static void gn_resblock3d(Net& n, const GnResBlockW& w, float* vol, int B, int h
   float* mean = n.A->f32((size_t)B * 32);
   float* rstd = n.A->f32((size_t)B * 32);
   conv_layer(n, nullptr, x, w.conv1, ConvOpts(), t1);
-  instance_stats(n.L, t1, mean, rstd, 1e-5f, n.ctx->stats_scratch);
+  instance_stats(n.L, t1, mean, rstd, 1e-5f, n.stats);
   Prep p = prep_of(t1);
   p.norm = NORM_STATS_BC; p.mean = mean; p.rstd = rstd; p.scale = w.gn1.scale; p.shift = w.gn1.shift;
   p.act = ACT_LRELU; p.slope = 0.01f;
   conv_layer(n, &p, t1, w.conv2, ConvOpts(), t2);
-  instance_stats(n.L, t2, mean, rstd, 1e-5f, n.ctx->stats_scratch);
+  instance_stats(n.L, t2, mean, rstd, 1e-5f, n.stats);
   Prep q = prep_of(t2);
   q.norm = NORM_STATS_BC; q.mean = mean; q.rstd = rstd; q.scale = w.gn2.scale; q.shift = w.gn2.shift;
   q.add = x; q.act = ACT_LRELU; q.slope = 0.01f;
@@ -215,6 +215,7 @@ static void gn_resblock3d(Net& n, const GnResBlockW& w, float* vol, int B, int h
 // F : AppearanceFeatureExtractor.forward, reference appearance_feature_extractor.py:38-48
 // ------------------------------------------------------------------------------------------
 void run_F(Net& n, const float* img_cl, int B, float* vol_out) {
+  n.L.tag = "F";
   const Weights& W = n.W();
   const int H = n.ctx->net_h, Wd = n.ctx->net_w, h = n.ctx->h, w = n.ctx->w;
   size_t m = n.A->mark();
@@ -322,6 +323,7 @@ static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, c
 // WarpingNetwork.warp, reference warping_network.py:49-62
 void run_warp(Net& n, const float* vol_in, const float* kp_source, const float* kp_driving, int B, float* vol_out,
               float* occ, float* deformation) {
+  n.L.tag = "warp";
   size_t m = n.A->mark();
   Act logits;
   float* occ_buf = occ ? occ : n.A->f32((size_t)B * n.ctx->h * n.ctx->w);
@@ -332,6 +334,7 @@ void run_warp(Net& n, const float* vol_in, const float* kp_source, const float* 
 
 // WarpingNetwork.warp_out, reference warping_network.py:64-71
 void run_warp_out(Net& n, const float* vol_in, const float* occ, int B, float* out256) {
+  n.L.tag = "warp_out";
   const Weights& W = n.W();
   const int h = n.ctx->h, w = n.ctx->w;
   size_t m = n.A->mark();
@@ -375,6 +378,7 @@ static void adaptive_conv_tc(Net& n, const AdaptiveConvW& a, const Act& geom, co
 }
 
 void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks) {
+  n.L.tag = "swap";
   CS_REQUIRE(n.ctx->identity_set, CS_ERR_STATE, "cs_swap / cs_frame before cs_set_identity");
   const Weights& W = n.W();
   const int h = n.ctx->h, w = n.ctx->w;
@@ -412,6 +416,7 @@ void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks) 
 // refine : G3d.forward, reference adaptive_modulate.py:721-733
 // ------------------------------------------------------------------------------------------
 void run_refine(Net& n, const float* vol_in, int B, float* vol_out) {
+  n.L.tag = "refine";
   const Weights& W = n.W();
   const int h = n.ctx->h, w = n.ctx->w;
   if (vol_out != vol_in && !n.L.dry)
@@ -493,7 +498,7 @@ static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, c
   size_t m = n.A->mark();
   float* mean = n.A->f32((size_t)B * b.fin);
   float* rstd = n.A->f32((size_t)B * b.fin);
-  instance_stats(n.L, x, mean, rstd, 1e-5f, n.ctx->stats_scratch);
+  instance_stats(n.L, x, mean, rstd, 1e-5f, n.stats);
   Act xs;
   if (b.learned_shortcut) {
     xs = new_act(n, B, 1, H, W, b.fout);
@@ -515,7 +520,7 @@ static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, c
   {
     float* mean1 = n.A->f32((size_t)B * b.fmid);
     float* rstd1 = n.A->f32((size_t)B * b.fmid);
-    instance_stats(n.L, dx, mean1, rstd1, 1e-5f, n.ctx->stats_scratch);
+    instance_stats(n.L, dx, mean1, rstd1, 1e-5f, n.stats);
     Opd m1 = spade_norm_tc(n, b.norm_1, seg_op, seg_phase, dx, 0, mean1, rstd1, ACT_LRELU, 0.2f, b.conv_1, B, H, W);
     ConvOpts o; o.residual = &xs;
     conv_from_operand(n, m1, b.conv_1, o, out);
@@ -544,7 +549,7 @@ static Act spade_block(Net& n, const SpadeBlockW& b, const Act& x, int xup, cons
   // InstanceNorm statistics of x (nearest upsampling leaves mean / biased variance unchanged)
   float* mean = n.A->f32((size_t)B * b.fin);
   float* rstd = n.A->f32((size_t)B * b.fin);
-  instance_stats(n.L, x, mean, rstd, 1e-5f, n.ctx->stats_scratch);
+  instance_stats(n.L, x, mean, rstd, 1e-5f, n.stats);
   // shortcut
   Act xs;
   if (b.learned_shortcut) {
@@ -572,7 +577,7 @@ static Act spade_block(Net& n, const SpadeBlockW& b, const Act& x, int xup, cons
   {
     float* mean1 = n.A->f32((size_t)B * b.fmid);
     float* rstd1 = n.A->f32((size_t)B * b.fmid);
-    instance_stats(n.L, dx, mean1, rstd1, 1e-5f, n.ctx->stats_scratch);
+    instance_stats(n.L, dx, mean1, rstd1, 1e-5f, n.stats);
     float* gb1 = spade_gamma_beta(n, b.norm_1, seg, segshift, B, H, W);
     Prep p1 = prep_of(dx); p1.norm = NORM_STATS_BC; p1.mean = mean1; p1.rstd = rstd1; p1.gb = gb1;
     p1.act = ACT_LRELU; p1.slope = 0.2f;
@@ -584,6 +589,7 @@ static Act spade_block(Net& n, const SpadeBlockW& b, const Act& x, int xup, cons
 }
 
 void run_spade(Net& n, const float* feat256, int B, float* img_nchw, uint8_t* img_u8) {
+  n.L.tag = "spade";
   const Weights& W = n.W();
   const int h = n.ctx->h, w = n.ctx->w;
   size_t m = n.A->mark();

@@ -243,6 +243,17 @@ class Engine:
         return {name: {"ms": buf[4 * i], "flops": buf[4 * i + 1], "bytes": buf[4 * i + 2], "launches": int(buf[4 * i + 3])}
                 for i, name in enumerate(self.PROFILE_FAMILIES)}
 
+    def profile_dump(self):
+        """Per-launch records since profile(True): list of dict(idx, family, ms, flops, bytes, desc)."""
+        buf = C.create_string_buffer(1 << 20)
+        self._check(self._lib.cs_profile_dump(self._ctx, buf, len(buf)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            idx, kind, ms, fl, by, desc = line.split(",", 5)
+            rows.append({"idx": int(idx), "family": self.PROFILE_FAMILIES[int(kind)], "ms": float(ms), "flops": float(fl),
+                         "bytes": float(by), "desc": desc})
+        return rows
+
     # ---- kernel-level test entry points ---------------------------------------------------------
     def test_conv(self, x_cl, w, bias, pad, act=0, slope=0.0, impl=0):
         """x_cl [B,D,H,W,Cin] channels-last, w [Cout,Cin,KD,KH,KW] -> y [B,Do,Ho,Wo,Cout]."""

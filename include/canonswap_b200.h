@@ -71,6 +71,7 @@ typedef struct cs_tensor_desc {
 #define CS_OPT_TC_STACKED3 7     /* 1 (default) = depth-stacked kernel for the 32->32 3x3x3 volume convs, 0 = generic implicit GEMM */
 #define CS_OPT_TC_CORESIDENT 8   /* 1 = short-K wide tiles as two co-resident single-accumulator pair CTAs per SM (default 0) */
 #define CS_OPT_TC_BN_MAX 9       /* cap on the N tile of convs packed AFTER the call (0 = automatic; experiments) */
+#define CS_OPT_LANES 10         /* 1 | 2: a graph-captured cs_frame runs as this many concurrent sub-batches (forked streams) */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -136,6 +137,9 @@ CS_API int cs_profile(cs_ctx* ctx, int enable);
 /* Synchronises and writes out[6][4] = per family {tcgen05 conv, SIMT conv, prep, stats, sampling, other}:
  * {total ms, algorithmic flops, algorithmic bytes, launches}; clears the records. */
 CS_API int cs_profile_read(cs_ctx* ctx, double* out);
+/* Synchronises and writes one CSV line per recorded launch ("index,family,ms,flops,bytes,description") into buf
+ * (NUL-terminated, truncated at cap); does not clear the records. */
+CS_API int cs_profile_dump(cs_ctx* ctx, char* buf, int cap);
 
 /* ---- kernel-level entry points (unit tests / profiling) ------------------------------------- */
 /* Generic "same"-style convolution on channels-last fp32 through the library's conv kernels.
