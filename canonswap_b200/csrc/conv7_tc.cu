@@ -5,9 +5,13 @@
 //   * one CTA = 128 (h,w) pixels x 8 output depths x 22 channels, for ONE filter row kh.
 //     For an input slice z and a filter tap (kh,kw) the A tile (128 pixels x 32 channels of slice z, shifted by
 //     the tap; TMA zero-fills the h/w padding) contributes to every output depth d = z-3 .. z+3 at once:
-//     the B tile stacks the 7 depth taps kd = z-d+3 along N (7 x 32 = 224 columns, clipped to the CTA's 8 depths),
-//     so N is 32..224 instead of 22, every A tile is loaded once for 7 depth taps, and TMEM holds the
-//     8 x 32 accumulator columns of the CTA (+ the same again for the split-bf16 correction products).
+//     the B tile stacks the 7 depth taps kd = z-d+3 along N (7 x 24 = 168 columns, clipped to the CTA's 8 depths),
+//     so N is 32..176 instead of 22, every A tile is loaded once for 7 depth taps, and TMEM holds the
+//     8 x 24 accumulator columns of the CTA (+ the same again for the split-fp16 correction products).
+//     A depth slot is 24 columns (22 channels + 2 pad), not 32: 25 % fewer MMA columns.  UMMA needs N % 16 == 0, so
+//     an odd number of slots is rounded up by 8 columns; those 8 extra B rows / D columns are harmless by
+//     construction: the used slots end either at the last slot of the filter position (followed by 8 zero rows
+//     in the packed weights) or at the last depth of the CTA's group (the extra columns are scratch TMEM).
 //   * the 7 filter rows kh go to 7 different CTAs that write 7 partial logit tensors, summed (+ bias) by a small
 //     fp32 kernel.  That keeps every TMEM accumulation chain at 7 z x 7 kw x 9 K-steps = 441 MMAs (the tensor
 //     core accumulates with truncation: error grows with the chain length, see conv_tc.cu) and gives the
@@ -22,15 +26,15 @@ using namespace tc;
 
 namespace {
 
-constexpr int C7_COUT_P = 32;                    // 22 -> 32 columns per output depth
+constexpr int C7_COUT_P = 24;                    // 22 -> 24 columns per output depth
 constexpr int C7_GROUP = 8;                      // output depths per CTA
-constexpr int C7_BROWS = 7 * C7_COUT_P;          // 224 B rows per stage
-// CTAS = 1: 4 stages of A (16 KB) + B (28 KB).  CTAS = 2 (tcgen05 pair, two pixel tiles share the weights): each CTA holds
-// half of the B rows, 6 stages of 16 + 14 KB.
+constexpr int C7_BROWS = 7 * C7_COUT_P + 8;      // 176 B rows per filter position (kh,kw): 7 depth slots + 8 zero rows
+// CTAS = 1: 5 stages of A (16 KB) + B (22 KB).  CTAS = 2 (tcgen05 pair, two pixel tiles share the weights): each CTA holds
+// half of the B rows, 7 stages of 16 + 11 KB.
 template <int CTAS> struct C7Cfg {
   static constexpr int BROWS = C7_BROWS / CTAS;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + BROWS * 128;
-  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
+  static constexpr int STAGES = CTAS == 2 ? 7 : 5;
   static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 16 * STAGES + 32;
 };
 
@@ -108,8 +112,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
         const int jlo = max(0, C7_GROUP * g - z + 3);          // first depth tap slot whose output is in the group
         const int nd = min(z + 3, C7_GROUP * g + C7_GROUP - 1) - max(z - 3, C7_GROUP * g) + 1;   // output depths of this slice
         for (int kw = 0; kw < 7; ++kw) {
-          // pair mode: this CTA supplies rows [rank * N/2, (rank+1) * N/2) of the N = 32 * nd row B operand
-          const int brow = ((kh * 7 + kw) * 7 + jlo) * C7_COUT_P + (CTAS == 2 ? (int)cta_rank * nd * (C7_COUT_P / 2) : 0);
+          // pair mode: this CTA supplies rows [rank * N/2, (rank+1) * N/2) of the N = round16(24 * nd) row B operand
+          const int npad = (nd * C7_COUT_P + 15) & ~15;
+          const int brow = (kh * 7 + kw) * C7_BROWS + jlo * C7_COUT_P + (CTAS == 2 ? (int)cta_rank * (npad / 2) : 0);
           for (int blk = 0; blk < k.nblk; ++blk) {
             const uint32_t fb = bars + 8u * s;
             mbar_wait(fb + 8u * C7_STAGES, ph ^ 1u);
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
     int s = 0; uint32_t ph = 0;
     for (int z = zlo; z <= zhi; ++z) {
       const int dlo = max(z - 3, C7_GROUP * g), dhi = min(z + 3, C7_GROUP * g + C7_GROUP - 1);
-      const uint32_t N = (uint32_t)(dhi - dlo + 1) * C7_COUT_P;
+      const uint32_t N = ((uint32_t)(dhi - dlo + 1) * C7_COUT_P + 15u) & ~15u;
       const uint32_t idesc = (1u << 4) | IDESC_AB_FMT | ((N >> 3) << 17) | (((128u * CTAS) >> 4) << 24);
       const uint32_t d_main = tmem_base + (uint32_t)((dlo - C7_GROUP * g) * C7_COUT_P);
       const uint32_t d_corr = d_main + 256u;
@@ -186,6 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[16], u[16];
+        // (the second half reads 8 valid columns + 8 of the next depth slot, which are not stored: c4 < ldo below)
         tc_ld16(trow + (uint32_t)(dl * C7_COUT_P + 16 * half), v);
         tc_ld16(trow + (uint32_t)(256 + dl * C7_COUT_P + 16 * half), u);
         tc_ld_wait();
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
 // depth d = z - 3 + j), columns [blk][hi 32 | lo 32]
 __global__ void __launch_bounds__(256) pack_conv7_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ out, int Cin,
                                                          int Cout, int nblk, float wmul) {
-  const long total = 49L * 7 * C7_COUT_P * nblk * 32;
+  const long total = 49L * 7 * C7_COUT_P * nblk * 32;         // the 8 pad rows per filter position stay zero (memset)
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int e = (int)(i & 31); long r = i >> 5;
     const int blk = (int)(r % nblk); r /= nblk;
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(256) pack_conv7_kernel(const float* __restrict
     const float v = (co < Cout && ci < Cin) ? w32[((long)tap * Cin + ci) * Cout + co] * wmul : 0.f;
     __nv_bfloat16 hi, lo;
     split_operand(v, hi, lo);
-    const long row = ((long)khw * 7 + j) * C7_COUT_P + co;
+    const long row = (long)khw * C7_BROWS + j * C7_COUT_P + co;
     const long o = row * (nblk * 64L) + blk * 64 + e;
     out[o] = hi;
     out[o + 32] = lo;
@@ -269,7 +275,7 @@ bool g_attr7[64] = {};
 }  // namespace
 
 bool conv7_supported(const ConvW& w, const Act& out) {
-  return w.w7 != nullptr && out.D == 16 && (long)out.H * out.W >= 128 && out.sw % 4 == 0 && out.sw >= w.Cout &&
+  return w.w7 != nullptr && out.D == 16 && (long)out.H * out.W >= 128 && out.sw % 4 == 0 && out.sw >= w.Cout && out.sw <= C7_COUT_P &&
          out.sh == (long)out.W * out.sw && out.sd == (long)out.H * out.sh && out.sb == 16 * out.sd;
 }
 
@@ -278,8 +284,9 @@ size_t conv7_scratch_floats(const Act& out) { return (size_t)7 * out.B * 16 * ou
 void pack_conv7(cs_ctx* ctx, ConvW& w) {
   if (!(w.KD == 7 && w.KH == 7 && w.KW == 7 && w.Cout <= C7_COUT_P && w.Cin >= 16 && w.w32)) return;
   const int nblk = (w.Cin + 31) / 32;
-  const size_t n = (size_t)49 * 7 * C7_COUT_P * nblk * 64;
+  const size_t n = (size_t)49 * C7_BROWS * nblk * 64;
   if (!w.w7) w.w7 = static_cast<__nv_bfloat16*>(ctx->dmalloc(n * sizeof(__nv_bfloat16)));
+  CS_CUDA(cudaMemset(w.w7, 0, n * sizeof(__nv_bfloat16)));
   pack_conv7_kernel<<<148 * 8, 256>>>(w.w32, w.w7, w.Cin, w.Cout, nblk, w.wmul);
   check_launch("pack_conv7");
 }
