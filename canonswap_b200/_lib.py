@@ -21,9 +21,11 @@ CS_OPT_TC_SETS = 4
 CS_OPT_TC_COMP = 5
 CS_OPT_TC_PAIR = 6
 CS_OPT_TC_STACKED3 = 7
-CS_OPT_TC_CORESIDENT = 8
+CS_OPT_TC_DOUBLE_BUFFER = 8
 CS_OPT_TC_BN_MAX = 9
 CS_OPT_LANES = 10
+CS_OPT_TC_CHAIN_MAX = 12
+CS_OPT_TC_SINGLE_CHAIN = 11
 
 # every symbol include/canonswap_b200.h declares
 SYMBOLS = [

@@ -43,8 +43,10 @@ Net make_net(cs_ctx* ctx, void* stream, bool dry) {
   n.L.max_sets = ctx->tc_sets;
   n.L.acc_comp = (float)ctx->tc_comp;
   n.L.pair = ctx->tc_pair != 0;
+  n.L.pair_min_iter = ctx->tc_pair > 1 ? ctx->tc_pair : 16;
   n.L.stacked3 = ctx->tc_stacked3 != 0;
-  n.L.coresident = ctx->tc_cores != 0;
+  n.L.double_buffer = ctx->tc_dbuf != 0;
+  n.L.single_chain = ctx->tc_single_chain;
   n.L.prof = dry ? nullptr : &ctx->prof;
   return n;
 }
@@ -275,12 +277,19 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
     case CS_OPT_TC_BN_MAX:
       if (value != 0 && (value < 16 || value > 256 || value % 16)) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_BN_MAX: 0 or a multiple of 16 in [16, 256]");
       ctx->tc_bn_max = value; return CS_OK;
-    case CS_OPT_TC_CORESIDENT:
-      ctx->tc_cores = value ? 1 : 0; return CS_OK;
+    case CS_OPT_TC_SINGLE_CHAIN:
+      if (value < 0 || value > 4096) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_SINGLE_CHAIN: value must be in [0, 4096]");
+      ctx->tc_single_chain = value; return CS_OK;
+    case CS_OPT_TC_CHAIN_MAX:
+      if (value < 0 || value > 100000) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_CHAIN_MAX: value must be in [0, 100000]");
+      ctx->tc_chain_max = value; return CS_OK;
+    case CS_OPT_TC_DOUBLE_BUFFER:
+      ctx->tc_dbuf = value ? 1 : 0; return CS_OK;
     case CS_OPT_TC_STACKED3:
       ctx->tc_stacked3 = value ? 1 : 0; return CS_OK;
     case CS_OPT_TC_PAIR:
-      ctx->tc_pair = value ? 1 : 0; return CS_OK;
+      if (value < 0 || value > 100000) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_PAIR: value must be in [0, 100000]");
+      ctx->tc_pair = value; return CS_OK;
     case CS_OPT_USE_GRAPH:
       ctx->use_graph = value ? 1 : 0; return CS_OK;
     case CS_OPT_LANES:
@@ -547,7 +556,7 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
     Act ya = make_act(y, B, Do, Ho, Wo, Cout);
     ConvGeom g; g.PD = PD; g.PH = PH; g.PW = PW; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
     Epilogue e; e.act = act; e.slope = slope;
-    Launcher L; L.stream = st; L.counter = &ctx->launches; L.npass = ctx->tc_passes; L.prof = &ctx->prof; L.max_sets = ctx->tc_sets; L.acc_comp = (float)ctx->tc_comp; L.pair = ctx->tc_pair != 0; L.coresident = ctx->tc_cores != 0;
+    Launcher L; L.stream = st; L.counter = &ctx->launches; L.npass = ctx->tc_passes; L.prof = &ctx->prof; L.max_sets = ctx->tc_sets; L.acc_comp = (float)ctx->tc_comp; L.pair = ctx->tc_pair != 0; L.pair_min_iter = ctx->tc_pair > 1 ? ctx->tc_pair : 16; L.double_buffer = ctx->tc_dbuf != 0; L.single_chain = ctx->tc_single_chain;
     const bool same = (Ho == H && Wo == W && PH == KH / 2 && PW == KW / 2) &&
                       ((Do == D && PD == KD / 2) || (Do == 1 && KD == D && PD == 0));
     bool tc = same && conv_tc_supported(cw, ya);

@@ -215,7 +215,7 @@ struct Arena {
 // optional per-launch CUDA-event timing, aggregated per kernel family (bench.py's roofline leg)
 enum ProfKind { PK_CONV_TC = 0, PK_CONV_SIMT = 1, PK_PREP = 2, PK_STATS = 3, PK_SAMPLE = 4, PK_OTHER = 5, PK_N = 6 };
 struct Profiler {
-  struct Rec { cudaEvent_t a, b; int kind; double flops, bytes; char desc[88]; };
+  struct Rec { cudaEvent_t a, b; int kind; double flops, bytes; char desc[120]; };
   std::vector<Rec> recs;
   bool on = false;
 };
@@ -230,9 +230,11 @@ struct Launcher {            // everything a kernel launch helper needs
   bool phase_conv = true;    // convs of a nearest-upsampled seg map in phase form on the low-resolution operand
   bool spade_fused = true;   // SPADE normalise + modulate + activate inside the gamma|beta conv's epilogue
   bool stacked3 = true;      // depth-stacked kernel for the 32 -> 32 3x3x3 volume convs
-  bool coresident = false;   // short-K wide tiles as 2 co-resident CTAs per SM (see conv_tc.cu)
   bool pair = true;          // tcgen05 pair mode (cta_group::2, 2-CTA clusters) for wide N tiles
-  float acc_comp = 120.f;     // accumulate-truncation compensation per chained MMA, in units of 1e-10 (0 = off)
+  int pair_min_iter = 16;    // ... with at least this many K iterations
+  int single_chain = 256;    // convs whose whole MMA chain (hi*hi + corrections) is at most this long use ONE accumulator
+  bool double_buffer = true; // two TMEM accumulator buffers where they fit (epilogue overlaps the next tile's MMAs)
+  float acc_comp = 170.f;     // accumulate-truncation compensation per chained MMA, in units of 1e-10 (0 = off)
   Profiler* prof = nullptr;
   const char* tag = nullptr;  // stage label attached to profiler records
   void count() const { if (counter) ++*counter; }

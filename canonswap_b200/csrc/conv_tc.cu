@@ -38,6 +38,8 @@ struct ConvTcK {
   int rowA;                        // bf16 elements per pixel of the operand = nblk * 64
   int BN, Cout, stages, npass;
   int tcols, nsets, chunk;         // TMEM columns, accumulator sets of BN columns, K iterations per hi*hi set
+  int nacc;                        // accumulator buffers (of nsets * BN columns): 2 = the epilogue of tile i overlaps the MMAs of tile i+1
+  int m_units, n_tiles;            // persistent tile loop: units of CTAS consecutive M tiles x N tiles (unit u -> m = u % m_units, n = u / m_units)
   float acc_scale;                 // compensation of the tensor core's round-toward-zero accumulation (see host code)
   float out_scale;                 // 1 / ConvW::wmul
   int zrows;                       // > 0: depth-dependent weights, B rows of depth slice d start at d * zrows
@@ -57,6 +59,24 @@ struct ConvTcK {
 };
 
 
+struct TileOrg { int w0, h0, d0, b0, n0, nrow0, ph_a, ph_b, chan0; uint32_t tmask; };
+// origin of M tile `m_tile` (a 4-D spatial box) and N tile `n_idx`
+__device__ __forceinline__ TileOrg tile_origin(const ConvTcK& k, int m_tile, int n_idx) {
+  TileOrg o;
+  int t = m_tile;
+  const int tw = t % k.ntw; t /= k.ntw;
+  const int th = t % k.nth; t /= k.nth;
+  const int td = t % k.ntd; const int tb = t / k.ntd;
+  o.w0 = tw << k.lbw; o.h0 = th << k.lbh; o.d0 = td << k.lbd; o.b0 = tb << k.lbb;
+  o.n0 = n_idx * k.BN;
+  o.nrow0 = o.n0 + o.d0 * k.zrows;               // first B row of this tile
+  o.tmask = k.ph_s ? k.tapmask[n_idx] : 0xFFFFFFFFu;
+  o.ph_a = k.ph_s ? (n_idx >> k.ph_s) : 0;
+  o.ph_b = k.ph_s ? (n_idx & ((1 << k.ph_s) - 1)) : 0;
+  o.chan0 = k.ph_s ? o.n0 : 0;                   // phase tiles all produce output channels 0 .. BN-1
+  return o;
+}
+
 // RES / EMIT: compile-time epilogue variants (residual add, operand emission) -- the epilogue is not overlapped
 // with the main loop, so the plain variant must not carry the registers of the fused ones.
 // CTAS = 2: the CTAs of a 2-CTA cluster (two consecutive M tiles, same N tile) run as a tcgen05 pair: each loads its own
@@ -75,9 +95,10 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
   const uint32_t stage_bytes = A_TILE_BYTES + brows * 128u;
   const uint32_t stg = base + (uint32_t)k.stages * stage_bytes;       // epilogue staging
   const int egroups = ((int)(blockDim.x >> 5) - 2) >> 2;              // epilogue warp groups (4 warps each): 1 or 2
-  const uint32_t bars = stg + (uint32_t)egroups * STG_BYTES;          // full[stages], empty[stages], tmem_full, tmem slot
+  const uint32_t bars = stg + (uint32_t)egroups * STG_BYTES;          // full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem slot
   const uint32_t tmem_full = bars + 16u * k.stages;
-  const uint32_t tmem_slot = tmem_full + 8u;
+  const uint32_t tmem_empty = tmem_full + 16u;
+  const uint32_t tmem_slot = tmem_empty + 16u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (uint32_t)k.tcols;
@@ -87,25 +108,19 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
   // fp32 registers: set 0 takes the small correction products (lo*hi, hi*lo), sets 1.. take hi*hi of
   // consecutive K ranges of `chunk` iterations.
   const int corr = (k.npass > 1 && k.nsets > 1) ? 1 : 0;
-
-  // tile origin
-  int t = blockIdx.x;
-  const int tw = t % k.ntw; t /= k.ntw;
-  const int th = t % k.nth; t /= k.nth;
-  const int td = t % k.ntd; const int tb = t / k.ntd;
-  const int w0 = tw << k.lbw, h0 = th << k.lbh, d0 = td << k.lbd, b0 = tb << k.lbb;
-  const int n0 = blockIdx.y * k.BN;
-  const int nrow0 = n0 + d0 * k.zrows;            // first B row of this tile
-  const uint32_t tmask = k.ph_s ? k.tapmask[blockIdx.y] : 0xFFFFFFFFu;
-  const int ph_a = k.ph_s ? (int)(blockIdx.y >> k.ph_s) : 0, ph_b = k.ph_s ? (int)(blockIdx.y & ((1u << k.ph_s) - 1)) : 0;
-  const int chan0 = k.ph_s ? n0 : 0;              // phase tiles all produce output channels 0 .. BN-1
+  const uint32_t acc_cols = (uint32_t)(k.nsets * k.BN);
   const int taps = k.KD * k.KH * k.KW;
+  // persistent tile loop: cluster c (one CTA, or a tcgen05 pair) walks units c, c + #clusters, ...
+  const int unit0 = (int)(blockIdx.x / CTAS), unit_step = (int)(gridDim.x / CTAS), units = k.m_units * k.n_tiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < k.stages; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (k.stages + s), 1); }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full + 8u * b, 1);
+      mbar_init(tmem_empty + 8u * b, (uint32_t)(CTAS * ((int)(blockDim.x >> 5) - 2)));   // every epilogue warp of the cluster
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -123,28 +138,31 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   if (warp == 0) {
-    // ===== TMA producer (one lane) =====
+    // ===== TMA producer (one lane): runs ahead across tiles, bounded only by the free pipeline stages =====
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        if (!((tmask >> (tap & 31)) & 1u)) continue;
-        const int kw = tap % k.KW; const int r = tap / k.KW; const int kh = r % k.KH; const int kd = r / k.KH;
-        const int cw = w0 + kw - k.PW, ch = h0 + kh - k.PH, cd = d0 + kd - k.PD;
-        const int kcol = tap * k.rowA;
-        for (int blk = 0; blk < k.nblk; ++blk) {
-          const uint32_t fb = bars + 8u * s;
-          mbar_wait(fb + 8u * k.stages, ph ^ 1u);
-          const uint32_t sa = base + (uint32_t)s * stage_bytes;
-          if constexpr (CTAS == 2) {
-            if (cta_rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);          // both CTAs' bytes land on the leader's barrier
-            tma_load_5d_2sm(sa, &tmA, fb, blk * 64, cw, ch, cd, b0);
-            tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, fb, kcol + blk * 64, nrow0 + (int)(cta_rank * brows));
-          } else {
-            mbar_expect_tx(fb, stage_bytes);
-            tma_load_5d(sa, &tmA, fb, blk * 64, cw, ch, cd, b0);
-            tma_load_2d(sa + A_TILE_BYTES, &tmB, fb, kcol + blk * 64, nrow0);
+      for (int u = unit0; u < units; u += unit_step) {
+        const TileOrg o = tile_origin(k, (u % k.m_units) * CTAS + (int)cta_rank, u / k.m_units);
+        for (int tap = 0; tap < taps; ++tap) {
+          if (!((o.tmask >> (tap & 31)) & 1u)) continue;
+          const int kw = tap % k.KW; const int r = tap / k.KW; const int kh = r % k.KH; const int kd = r / k.KH;
+          const int cw = o.w0 + kw - k.PW, ch = o.h0 + kh - k.PH, cd = o.d0 + kd - k.PD;
+          const int kcol = tap * k.rowA;
+          for (int blk = 0; blk < k.nblk; ++blk) {
+            const uint32_t fb = bars + 8u * s;
+            mbar_wait(fb + 8u * k.stages, ph ^ 1u);
+            const uint32_t sa = base + (uint32_t)s * stage_bytes;
+            if constexpr (CTAS == 2) {
+              if (cta_rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);          // both CTAs' bytes land on the leader's barrier
+              tma_load_5d_2sm(sa, &tmA, fb, blk * 64, cw, ch, cd, o.b0);
+              tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, fb, kcol + blk * 64, o.nrow0 + (int)(cta_rank * brows));
+            } else {
+              mbar_expect_tx(fb, stage_bytes);
+              tma_load_5d(sa, &tmA, fb, blk * 64, cw, ch, cd, o.b0);
+              tma_load_2d(sa + A_TILE_BYTES, &tmB, fb, kcol + blk * 64, o.nrow0);
+            }
+            if (++s == k.stages) { s = 0; ph ^= 1u; }
           }
-          if (++s == k.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -152,52 +170,62 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
     // ===== MMA issuer: the whole warp walks the loop converged, one elected lane issues =====
     // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128 per CTA
     const uint32_t idesc = (1u << 4) | IDESC_AB_FMT | ((uint32_t)(k.BN >> 3) << 17) | (((128u * CTAS) >> 4) << 24);
-    const uint32_t d_corr0 = tmem_base;
-    uint32_t d_main = tmem_base + (uint32_t)(corr * k.BN);
     int s = 0; uint32_t ph = 0;
-    int in_set = 0;
-    uint32_t acc_corr = 0;
-    for (int tap = 0; tap < taps; ++tap) {
-      if (!((tmask >> (tap & 31)) & 1u)) continue;
-      for (int blk = 0; blk < k.nblk; ++blk) {
-        const uint32_t fb = bars + 8u * s;
-        mbar_wait(fb, ph);
+    int it = 0;
+    for (int u = unit0; u < units; u += unit_step, ++it) {
+      const uint32_t tmask = k.ph_s ? k.tapmask[u / k.m_units] : 0xFFFFFFFFu;
+      const int buf = k.nacc == 2 ? (it & 1) : 0, use = k.nacc == 2 ? (it >> 1) : it;
+      if (use > 0) {                                       // the epilogue warps (of both CTAs) have drained this buffer
+        mbar_wait(tmem_empty + 8u * buf, (uint32_t)((use - 1) & 1));
         tc_fence_after();
-        const uint32_t sa = base + (uint32_t)s * stage_bytes;
-        const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + A_TILE_BYTES);
-        const int ksteps = (blk == k.nblk - 1) ? k.last_ksteps : 2;
-        const uint32_t acc_main = in_set > 0 ? 1u : 0u;
-        const uint32_t eb = fb + 8u * k.stages;
-        if constexpr (CTAS == 2) {
-          mma_stage_k<3, 2>(ksteps, d_main, corr ? d_corr0 : d_main, ad, bd, idesc, acc_main, corr ? acc_corr : 1u, eb);
-        } else if (corr && k.npass == 3) {
-          mma_stage_k<3>(ksteps, d_main, d_corr0, ad, bd, idesc, acc_main, acc_corr, eb);
-        } else if (corr) {
-          mma_stage_k<2>(ksteps, d_main, d_corr0, ad, bd, idesc, acc_main, acc_corr, eb);
-        } else if (k.npass == 3) {                       // single accumulator: corrections follow hi*hi in place
-          mma_stage_k<3>(ksteps, d_main, d_main, ad, bd, idesc, acc_main, 1u, eb);
-        } else if (k.npass == 2) {
-          mma_stage_k<2>(ksteps, d_main, d_main, ad, bd, idesc, acc_main, 1u, eb);
-        } else {
-          mma_stage_k<1>(ksteps, d_main, d_main, ad, bd, idesc, acc_main, 1u, eb);
-        }
-        acc_corr = 1u;
-        if (++in_set == k.chunk) { in_set = 0; d_main += (uint32_t)k.BN; }
-        if (++s == k.stages) { s = 0; ph ^= 1u; }
       }
-    }
-    if constexpr (CTAS == 2) {
-      asm volatile(
-          "{\n\t.reg .pred pe;\n\t.reg .b16 mk;\n\tmov.b16 mk, 3;\n\t"
-          "elect.sync _|pe, 0xffffffff;\n\t"
-          "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], mk;\n\t}"
-          ::"r"(tmem_full) : "memory");
-    } else {
-      asm volatile(
-          "{\n\t.reg .pred pe;\n\t"
-          "elect.sync _|pe, 0xffffffff;\n\t"
-          "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-          ::"r"(tmem_full) : "memory");
+      const uint32_t d_corr0 = tmem_base + (uint32_t)buf * acc_cols;
+      uint32_t d_main = d_corr0 + (uint32_t)(corr * k.BN);
+      int in_set = 0;
+      uint32_t acc_corr = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        if (!((tmask >> (tap & 31)) & 1u)) continue;
+        for (int blk = 0; blk < k.nblk; ++blk) {
+          const uint32_t fb = bars + 8u * s;
+          mbar_wait(fb, ph);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)s * stage_bytes;
+          const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + A_TILE_BYTES);
+          const int ksteps = (blk == k.nblk - 1) ? k.last_ksteps : 2;
+          const uint32_t acc_main = in_set > 0 ? 1u : 0u;
+          const uint32_t eb = fb + 8u * k.stages;
+          if constexpr (CTAS == 2) {
+            mma_stage_k<3, 2>(ksteps, d_main, corr ? d_corr0 : d_main, ad, bd, idesc, acc_main, corr ? acc_corr : 1u, eb);
+          } else if (corr && k.npass == 3) {
+            mma_stage_k<3>(ksteps, d_main, d_corr0, ad, bd, idesc, acc_main, acc_corr, eb);
+          } else if (corr) {
+            mma_stage_k<2>(ksteps, d_main, d_corr0, ad, bd, idesc, acc_main, acc_corr, eb);
+          } else if (k.npass == 3) {                       // single accumulator: corrections follow hi*hi in place
+            mma_stage_k<3>(ksteps, d_main, d_main, ad, bd, idesc, acc_main, 1u, eb);
+          } else if (k.npass == 2) {
+            mma_stage_k<2>(ksteps, d_main, d_main, ad, bd, idesc, acc_main, 1u, eb);
+          } else {
+            mma_stage_k<1>(ksteps, d_main, d_main, ad, bd, idesc, acc_main, 1u, eb);
+          }
+          acc_corr = 1u;
+          if (++in_set == k.chunk) { in_set = 0; d_main += (uint32_t)k.BN; }
+          if (++s == k.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+      const uint32_t tf = tmem_full + 8u * buf;
+      if constexpr (CTAS == 2) {
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\t.reg .b16 mk;\n\tmov.b16 mk, 3;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], mk;\n\t}"
+            ::"r"(tf) : "memory");
+      } else {
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+            ::"r"(tf) : "memory");
+      }
     }
   } else if (warp >= 2) {
     // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 =====
@@ -211,6 +239,10 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
     // row mapping of the coalesced phase: 4 rows x 8 lanes (x 8 passes); SPADE: 8 rows x 4 lanes (x 4 passes)
     constexpr int RSTEP = SPADE ? 8 : 4;
     const int sub = SPADE ? (lane >> 2) : (lane >> 3), c4 = (lane & 7) * 4;
+    int it = 0;
+    for (int u = unit0; u < units; u += unit_step, ++it) {
+    const TileOrg o = tile_origin(k, (u % k.m_units) * CTAS + (int)cta_rank, u / k.m_units);
+    const int w0 = o.w0, h0 = o.h0, d0 = o.d0, b0 = o.b0, n0 = o.n0, ph_a = o.ph_a, ph_b = o.ph_b, chan0 = o.chan0;
     long yoff[8], roff[RES ? 8 : 1], epix[EMIT ? 8 : 1], xoff[SPADE ? 8 : 1];
     int sbase[SPADE ? 8 : 1];
     float mu[8];
@@ -265,9 +297,10 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
         }
       }
     }
-    mbar_wait(tmem_full, 0);
+    const int buf = k.nacc == 2 ? (it & 1) : 0, use = k.nacc == 2 ? (it >> 1) : it;
+    mbar_wait(tmem_full + 8u * buf, (uint32_t)(use & 1));
     tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t trow = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(q * 32) << 16);
     int cidx = -1;
     for (int c0 = eg * 32; c0 < k.BN; c0 += 32 * egroups) {
       ++cidx;
@@ -407,6 +440,17 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
       }
       __syncwarp();
     }
+    // this warp's TMEM reads of the tile are complete (every tcgen05.ld above was waited for): hand the accumulator
+    // buffer back to the MMA issuer -- the leader CTA's, which also writes the peer's TMEM in pair mode
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (CTAS == 2)
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((tmem_empty + 8u * buf) & PEER_BIT_MASK) : "memory");
+      else
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty + 8u * buf) : "memory");
+    }
+    }  // tile loop
   }
 
   tc_fence_before();
@@ -455,7 +499,7 @@ int pick_bn(int Cout) {
 }
 
 bool g_attr_set[64] = {};
-constexpr int MAX_DYN_SMEM = 200 * 1024;
+constexpr int MAX_DYN_SMEM = 220 * 1024;
 
 }  // namespace
 
@@ -508,7 +552,17 @@ void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream) {
   if (!conv_tc_shape_ok(w.Cin, w.Cout) || !w.w32) return;
   const int nblk = (w.Cin + 31) / 32;
   int BN = pick_bn(w.Cout);
-  if (w.taps() * nblk * 2 > 1024 && BN > 128) BN = 128;      // deep K: 4 accumulator sets instead of 2
+  // Accumulator-set policy.  The hi*hi products of a tile accumulate in 512 / BN - 1 TMEM sets (one more holds the small
+  // correction products); every MMA added into a set truncates it (round toward zero), so the error grows with the chain
+  // length per set.  Halve the N tile (down to 128) until a chain is at most `chain_max` MMAs: BN = 256 leaves one hi*hi set
+  // (a 3x3 conv over 512 channels would chain 288 MMAs), BN = 128 three (96 each).  Measured end to end (max|d| vs the
+  // oracle, 1e-3 bar; fp32-vs-fp32 reordering noise alone is 1.2e-4 / 4.9e-4 .. 6.9e-4 at 512 / 1024 px): 320 -> 256 takes
+  // 5.0e-4 -> 3.3e-4 at 512 px and 1.0e-3 -> 8.6e-4 at 1024 px at the same step time (BN = 128 pairs tile the SMs better).
+  {
+    const int chain_max = ctx->tc_chain_max > 0 ? ctx->tc_chain_max : 256;
+    const int steps_main = w.taps() * nblk * 2;
+    while (BN > 128 && (steps_main + (512 / BN - 1) - 1) / (512 / BN - 1) > chain_max) BN = round_up(BN / 2, 16);
+  }
   if (ctx->tc_bn_max > 0 && BN > ctx->tc_bn_max) BN = ctx->tc_bn_max;
   const int Cout_p = round_up(w.Cout, BN);
   const size_t n = (size_t)Cout_p * w.taps() * nblk * 64;
@@ -587,31 +641,29 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
            (!e.residual || (al4(e.rs_b) && al4(e.rs_d) && al4(e.rs_h) && al4(e.rs_w) && ((uintptr_t)e.residual % 16 == 0)));
 
   const unsigned m_tiles = (unsigned)(k.ntw * k.nth * k.ntd * ntb);
-  // tcgen05 pair mode (cta_group::2): wide N tiles, an even number of M tiles, weights shared by the pair
+  // tcgen05 pair mode (cta_group::2): wide N tiles, an even number of M tiles, weights shared by the pair.  The kernel is
+  // persistent, so the cluster set-up is paid once per launch and short-K convs profit too (halved B traffic per CTA).
   const int niter = w.taps() * w.nblk;
-  // (measured: +12% at K = 2304 .. 3834, +2% at K = 4608, a loss for K <= 1152 where the cluster sync is not amortised)
-  // short-K wide tiles: the (non-overlapped) epilogue is 35-50% of a tile.  Co-resident mode runs them as tcgen05 pairs with
-  // ONE accumulator set (256 columns) and two pipeline stages, so two CTAs fit on an SM and one's epilogue overlaps the
-  // other's main loop.
-  const bool cores = L.coresident && k.BN > 64 && niter <= 72 && (m_tiles % 2 == 0) && w.zrows == 0 && k.npass == 3 && ps == 0 &&
-                     !e.sp_x;
-  const bool pair = (L.pair && k.BN >= 128 && (m_tiles % 2 == 0) && w.zrows == 0 && k.npass == 3 && niter >= 64 && ps == 0) || cores;
+  const bool pair = L.pair && k.BN >= 128 && (m_tiles % 2 == 0) && w.zrows == 0 && k.npass == 3 && niter >= L.pair_min_iter && ps == 0;
   const int stage_bytes = A_TILE_BYTES + (pair ? k.BN / 2 : k.BN) * 128;
-  // accumulator sets: one for the correction products + enough hi*hi sets for chains of <= ~256 MMAs
+  // thin N tiles (short MMAs: the per-stage issue overhead dominates) run as TWO co-resident CTAs per SM, each with half of the
+  // shared memory and of the TMEM columns
+  const bool thin = k.BN <= 64;
+  // accumulator sets: chains of <= ~256 MMAs per TMEM accumulator.  A short K (whole chain <= 256 MMAs) runs in ONE
+  // accumulator; otherwise one set for the correction products + hi*hi sets of <= ~256 MMAs.  If two such buffers fit
+  // into the 512 TMEM columns the accumulators are double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1.
   {
     const int steps_main = niter * 2;
-    int want = 1 + (steps_main + 255) / 256;
-    if (k.npass == 1) want -= 1;
-    if (want < 1) want = 1;
-    int cols = k.BN * want;
-    if (cols > 512) cols = 512;
-    if (cores) cols = k.BN;
-    int tcols = 32;
-    while (tcols < cols) tcols <<= 1;
-    int nsets = tcols / k.BN;
+    int want = (steps_main * k.npass <= L.single_chain) ? 1 : 1 + (steps_main + 255) / 256;
+    if (k.npass == 1 && want > 1) want -= 1;
+    if (L.max_sets > 0 && want > L.max_sets) want = L.max_sets;
+    const int tmem_budget = thin ? 256 : 512;
+    while (want > 1 && k.BN * want > tmem_budget) --want;
+    k.nacc = (L.double_buffer && 2 * k.BN * want <= tmem_budget) ? 2 : 1;
+    const int per_buf = tmem_budget / k.nacc;
+    int nsets = want == 1 ? 1 : per_buf / k.BN;               // spare columns shorten the chains further
     if (nsets > 16) nsets = 16;
     if (L.max_sets > 0 && nsets > L.max_sets) nsets = L.max_sets;
-    if (cores) nsets = 1;
     if (nsets < 1) nsets = 1;
     const int corr = (k.npass > 1 && nsets > 1) ? 1 : 0;
     int nmain = nsets - corr;
@@ -619,7 +671,10 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     const int chunk = (niter + nmain - 1) / nmain;          // K iterations per hi*hi set
     nmain = (niter + chunk - 1) / chunk;                    // sets actually written
     if (ps) { nmain = 1; }
-    k.tcols = tcols; k.nsets = corr + nmain; k.chunk = ps ? (1 << 30) : chunk;
+    k.nsets = corr + nmain; k.chunk = ps ? (1 << 30) : chunk;
+    int tcols = 32;
+    while (tcols < k.nacc * k.nsets * k.BN) tcols <<= 1;
+    k.tcols = tcols;
     // The tensor core truncates (rounds toward zero) when it adds an MMA into the fp32 accumulator: measured on B200, a
     // chain of L MMAs loses ~1.2e-8 * L of the accumulated magnitude, systematically (mean signed error, tools/tc_check.py).
     // Errors of that sign add linearly over the ~75 stacked convs, so the epilogue scales the hi*hi sum back.
@@ -627,17 +682,21 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     k.acc_scale = 1.0f + L.acc_comp * 1e-10f * (float)chain;
     k.out_scale = 1.0f / w.wmul;
   }
-  // thin-N tiles keep the footprint under ~100 KB so two CTAs share an SM (prologue / epilogue overlap)
-  const int budget = ((k.BN <= 64 && k.tcols <= 256) || cores) ? 100 * 1024 : MAX_DYN_SMEM;
-  const int egroups = (k.BN > 64 && !cores) ? 2 : 1;       // 8 epilogue warps on wide tiles (1 CTA per SM)
+  const int egroups = k.BN > 64 ? 2 : 1;                   // 8 epilogue warps on wide tiles
   CS_REQUIRE(!k.sp_x || (k.BN + 32 * egroups - 1) / (32 * egroups) <= 4, CS_ERR_INVALID, "conv_tc: SPADE epilogue holds <= 4 chunks per warp");
   const int stg_bytes = egroups * STG_BYTES;
-  int stages = (budget - 2048 - stg_bytes) / stage_bytes;
+  int stages = ((thin ? 100 * 1024 : MAX_DYN_SMEM) - 2048 - stg_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
-  if (stages > niter) stages = niter;
   if (stages < 1) stages = 1;
   k.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 1024 + 16 * stages + 32;
+  const size_t smem = (size_t)stages * stage_bytes + stg_bytes + 1024 + 16 * stages + 64;
+  // persistent grid: one CTA (or pair) per SM walks the tiles round-robin, N tile-major so concurrent CTAs share the weights
+  const int ctas = pair ? 2 : 1;
+  k.m_units = (int)m_tiles / ctas;
+  k.n_tiles = (w.zrows > 0 ? w.zrows : w.Cout_p) / k.BN;
+  const int units = k.m_units * k.n_tiles;
+  static int n_sm = 0;
+  if (!n_sm) { int dev0 = 0; CS_CUDA(cudaGetDevice(&dev0)); CS_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev0)); }
 
   // tensor maps
   auto enc = encode_fn();
@@ -678,16 +737,15 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     g_attr_set[dev & 63] = true;
   }
   if (w.zrows > 0) CS_REQUIRE(bd == 1 && w.zrows % k.BN == 0, CS_ERR_INVALID, "conv_tc: depth-dependent weights need one depth per tile");
-  dim3 grid(m_tiles, (unsigned)((w.zrows > 0 ? w.zrows : w.Cout_p) / k.BN));
   const long M = (long)x.B * g.Do * g.Ho * g.Wo;          // phase mode: the algorithmic conv runs on the upsampled grid
-  char desc[80];
-  snprintf(desc, sizeof(desc), "tc M=%ld Cin=%d Cout=%d k=%dx%dx%d BN=%d st=%d sets=%d %s%s%s%s%s grid=%ux%u", M, w.Cin, y.C, w.KD, w.KH, w.KW,
-           k.BN, stages, k.nsets, pair ? "pair " : "", k.res ? "res " : "", k.emit ? "emit " : "", k.sp_x ? "spade " : "", ps ? "phase " : "",
-           grid.x, grid.y);
+  char desc[120];
+  snprintf(desc, sizeof(desc), "tc M=%ld Cin=%d Cout=%d k=%dx%dx%d BN=%d st=%d sets=%d acc=%d %s%s%s%s%s tiles=%dx%d", M, w.Cin, y.C, w.KD,
+           w.KH, w.KW, k.BN, stages, k.nsets, k.nacc, pair ? "pair " : "", k.res ? "res " : "", k.emit ? "emit " : "", k.sp_x ? "spade " : "",
+           ps ? "phase " : "", (int)m_tiles, k.n_tiles);
   ProfScope pscope(L, PK_CONV_TC, 2.0 * (double)M * y.C * w.Cin * w.taps(), 0.0, desc);
   const bool has_res = k.res != nullptr, has_emit = k.emit != nullptr;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(64 + 128 * egroups); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
+  cfg.blockDim = dim3(64 + 128 * egroups); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
   cudaLaunchAttribute attr[1];
   if (pair) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -696,6 +754,26 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   }
   KernelFn fn = fns[has_res][has_emit][pair ? 1 : 0];
   if (k.sp_x) fn = pair ? conv_tc_kernel<false, true, 2, true> : conv_tc_kernel<false, true, 1, true>;
+  int clusters = thin ? 2 * n_sm : n_sm;
+  if (pair) {
+    // co-resident 2-CTA clusters (GPC boundaries can strand an SM): a persistent grid must not exceed one wave
+    static std::map<std::pair<const void*, size_t>, int> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(reinterpret_cast<const void*>(fn), smem);
+    auto itc = cache.find(key);
+    if (itc == cache.end()) {
+      cfg.gridDim = dim3((unsigned)n_sm / 2 * 2);
+      int nc = 0;
+      CS_CUDA(cudaOccupancyMaxActiveClusters(&nc, fn, &cfg));
+      if (nc < 1) nc = 1;
+      if (nc > n_sm / 2) nc = n_sm / 2;
+      itc = cache.emplace(key, nc).first;
+    }
+    clusters = itc->second;
+  }
+  if (clusters > units) clusters = units;
+  cfg.gridDim = dim3((unsigned)(clusters * ctas));
   CS_CUDA(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, k));
   check_launch("conv_tc");
 }

@@ -49,7 +49,7 @@ class Engine:
     """Owns a cs_ctx: packed weights + workspace for frames of `net_hw` up to `max_batch` per call."""
 
     def __init__(self, weights: Mapping[str, Mapping[str, torch.Tensor]], net_hw=(256, 256), max_batch: int = 8,
-                 device: int = 0, conv_impl: int = 0):
+                 device: int = 0, conv_impl: int = 0, options: Mapping[int, int] | None = None):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         self.device = torch.device("cuda", device)
@@ -63,6 +63,8 @@ class Engine:
             raise CanonSwapError(f"cs_create failed ({rc}): {msg}")
         if conv_impl:
             self.set_option(_lib.CS_OPT_CONV_IMPL, conv_impl)
+        for k, v in (options or {}).items():      # options that shape the weight packing must precede cs_load_weights
+            self.set_option(int(k), int(v))
         if weights is not None:          # None: kernel-level test entry points only (no networks)
             table, keep = _flat_table(weights)
             self._check(self._lib.cs_load_weights(self._ctx, table, len(table)))

@@ -66,11 +66,15 @@ typedef struct cs_tensor_desc {
 #define CS_OPT_CONV_IMPL 1       /* 0 = auto (tcgen05 where eligible), 1 = force SIMT fp32 convs (debug) */
 #define CS_OPT_TC_PASSES 3       /* split-bf16 MMA passes of the tcgen05 conv: 3 (default, fp32-grade) | 2 | 1 (measurement only) */
 #define CS_OPT_TC_SETS 4         /* cap on TMEM accumulator sets per tile (0 = automatic; 1 = single accumulator, measurement only) */
-#define CS_OPT_TC_COMP 5         /* tensor-core accumulate-truncation compensation per chained MMA, units of 1e-10 (default 120, 0 = off) */
-#define CS_OPT_TC_PAIR 6         /* 1 = tcgen05 pair mode (cta_group::2 over 2-CTA clusters) for wide N tiles */
+#define CS_OPT_TC_COMP 5         /* tensor-core accumulate-truncation compensation per chained MMA, units of 1e-10 (default 170, 0 = off) */
+#define CS_OPT_TC_PAIR 6         /* tcgen05 pair mode (cta_group::2 over 2-CTA clusters) for wide N tiles: 0 = off, 1 = on (default),
+                                    n > 1 = only for convs with at least n K iterations */
 #define CS_OPT_TC_STACKED3 7     /* 1 (default) = depth-stacked kernel for the 32->32 3x3x3 volume convs, 0 = generic implicit GEMM */
-#define CS_OPT_TC_CORESIDENT 8   /* 1 = short-K wide tiles as two co-resident single-accumulator pair CTAs per SM (default 0) */
+#define CS_OPT_TC_DOUBLE_BUFFER 8 /* 1 (default) = two TMEM accumulator buffers where they fit: a tile's epilogue overlaps the next tile's MMAs */
 #define CS_OPT_TC_BN_MAX 9       /* cap on the N tile of convs packed AFTER the call (0 = automatic; experiments) */
+#define CS_OPT_TC_SINGLE_CHAIN 11 /* convs whose whole MMA chain is at most this long accumulate in ONE TMEM set (0 = never) */
+#define CS_OPT_TC_CHAIN_MAX 12   /* longest hi*hi MMA chain per TMEM accumulator set for convs packed AFTER the call: the N tile is halved
+                                    until it holds (0 = default 256) */
 #define CS_OPT_LANES 10         /* 1 | 2: a graph-captured cs_frame runs as this many concurrent sub-batches (forked streams) */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */
 

@@ -10,10 +10,20 @@ from oracle import canonswap_oracle as O
 net = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 B = 2 if net <= 128 else 1
 W = synth.synth_weights()
-inp = synth.synth_inputs(B, net)
+inp = synth.synth_inputs(B, net, seed=int([a[5:] for a in sys.argv[2:] if a.startswith('seed=')][0]) if any(a.startswith('seed=') for a in sys.argv[2:]) else 1234)
 ref = O.frame(W, inp["frames"], inp["x_t"], inp["x_can"], inp["source_id"], debug_decodes=False)
 cu = {k: v.cuda() for k, v in inp.items()}
-eng = Engine(W, net_hw=(net, net), max_batch=B, device=0)
+pre = {}
+for a in sys.argv[2:]:
+    if a.startswith("pre="):
+        for kv in a[4:].split(","):
+            kk, vv = kv.split(":")
+            pre[int(kk)] = int(vv)
+seed = 1234
+for a in sys.argv[2:]:
+    if a.startswith("seed="):
+        seed = int(a[5:])
+eng = Engine(W, net_hw=(net, net), max_batch=B, device=0, options=pre)
 eng.set_identity(cu["source_id"])
 
 
@@ -38,10 +48,15 @@ def run(tag):
     print(tag, " ".join(f"{k}={v[0]:.2e}/{v[1]:.1f}" for k, v in r.items()), flush=True)
 
 
-eng.set_option(_lib.CS_OPT_CONV_IMPL, 1); run("simt     ")
+if "nosimt" not in sys.argv:
+    eng.set_option(_lib.CS_OPT_CONV_IMPL, 1); run("simt     ")
 eng.set_option(_lib.CS_OPT_CONV_IMPL, 0)
-for comp in (100, 120, 140, 170):
+comps = (100, 120, 140, 170)
+for a in sys.argv[2:]:
+    if a.startswith("comps="):
+        comps = tuple(int(x) for x in a[6:].split(","))
+for comp in comps:
     eng.set_option(_lib.CS_OPT_TC_COMP, comp); run(f"tc comp={comp}")
-eng.set_option(_lib.CS_OPT_TC_COMP, 120)
+eng.set_option(_lib.CS_OPT_TC_COMP, 170)
 if "pair" in sys.argv:
     eng.set_option(_lib.CS_OPT_TC_PAIR, 1); run("tc pair  ")

@@ -54,7 +54,7 @@ def main():
     passes = [3]
     comps = [int(a) for a in sys.argv[1:] if a[0].isdigit()] or [120]
     pair = 0 if "nopair" in sys.argv[1:] else 1
-    cores = 1 if "cores" in sys.argv[1:] else 0
+    dbuf = 0 if "nodbuf" in sys.argv[1:] else 1
     bnmax = 128 if "bn128" in sys.argv[1:] else 0
     eng = Engine(None, net_hw=(128, 128), max_batch=1, device=0)
     g = torch.Generator(device="cuda").manual_seed(7)
@@ -62,13 +62,13 @@ def main():
       for np_ in passes:
         eng.set_option(_lib.CS_OPT_TC_COMP, comp)
         eng.set_option(_lib.CS_OPT_TC_PAIR, pair)
-        eng.set_option(_lib.CS_OPT_TC_CORESIDENT, cores)
+        eng.set_option(_lib.CS_OPT_TC_DOUBLE_BUFFER, dbuf)
         eng.set_option(_lib.CS_OPT_TC_BN_MAX, bnmax)
         for (B, D, H, Wd, Cin, Cout, k, pad, timed) in CASES:
             x = torch.randn(B, D, H, Wd, Cin, device="cuda", generator=g)
             w = torch.randn(Cout, Cin, *k, device="cuda", generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5
             b = torch.randn(Cout, device="cuda", generator=g)
-            tag = f"comp={comp} pair={pair} cores={cores} bn={bnmax} B{B} D{D} {H}x{Wd} {Cin}->{Cout} k{k}"
+            tag = f"comp={comp} pair={pair} dbuf={dbuf} bn={bnmax} B{B} D{D} {H}x{Wd} {Cin}->{Cout} k{k}"
             impl, act = (4, 2) if timed >= 5 else ((3, 0) if timed >= 3 else (2, 2))
             timed = timed in (1, 4, 6)
             try:
