@@ -6,8 +6,11 @@
 //   * one CTA = 128 (h,w) pixels x ALL 16 depths x 32 channels: 16 x 32 = 512 fp32 accumulator columns = the whole TMEM.
 //   * for an input slice z and an in-plane tap (kh,kw) the A tile (128 pixels x 32 channels, shifted by the tap, TMA
 //     zero-fills the h/w padding) feeds the three output depths d = z-1, z, z+1 at once: the B tile stacks the depth taps
-//     kd = z-d+1 along N (3 x 32 = 96 columns landing at TMEM column 32*(z-1)), so every input tile is loaded 9 times
-//     instead of 27 and the MMAs are 3x wider.
+//     kd = z-d+1 along N (3 x 32 = 96 columns landing at TMEM column 32*(z-1)), so the MMAs are 3x wider.
+//   * halo tiles: the pixel tile is 8 (w) x 16 (h), so a shift by one image row is a shift by 8 operand rows = exactly one
+//     1024-byte SWIZZLE_128B atom.  One TMA box of 8 x 18 pixels (18 KB) therefore serves the three kh taps of a (z, kw):
+//     their A descriptors start 0 / 1024 / 2048 bytes into the stage.  Every input slice is loaded 3 times instead of
+//     27 (the first version of this kernel, 9 loads of 16 KB per slice, was bound by the L2 -> SM stream).
 //   * the complete weight set (9 in-plane taps x 96 rows x 128 B = 108 KB) is loaded into shared memory once per CTA;
 //     the pipeline only streams A tiles.
 //   * accumulation chain per output column: 3 slices x 9 taps x 2 K-steps x 3 passes = 162 MMAs (one accumulator).
@@ -24,12 +27,15 @@ namespace {
 
 constexpr int C3_BTAP_BYTES = 96 * 128;                   // one in-plane tap: 3 depth taps x 32 couts x [hi 32 | lo 32]
 constexpr int C3_B_BYTES = 9 * C3_BTAP_BYTES;             // 108 KB resident weights
-constexpr int C3_STAGES = 6;                              // 6 x 16 KB in flight: the A stream is TMA-latency bound
-constexpr int C3_SMEM = C3_B_BYTES + C3_STAGES * A_TILE_BYTES + STG_BYTES + 1024 + 16 * C3_STAGES + 64;
+constexpr int C3_HALO_BYTES = 18 * 8 * 128;               // 8 (w) x 18 (h) pixels x [hi 32 | lo 32]
+constexpr int C3_STAGES = 4;                              // 4 x 18 KB in flight (18 MMAs per stage)
+constexpr int C3_EGROUPS = 2;                             // 8 epilogue warps: the groups take alternate output depths
+constexpr int C3_SMEM = C3_B_BYTES + C3_STAGES * C3_HALO_BYTES + C3_EGROUPS * STG_BYTES + 1024 + 16 * C3_STAGES + 64;
+constexpr int C3_THREADS = 64 + 128 * C3_EGROUPS;
 
 struct Conv3sK {
   int B, H, W;                     // D = 16, C = 32
-  int lbw, lbh, ntw, nth;
+  int ntw, nth;                    // tiles of 8 (w) x 16 (h) pixels
   const float* bias; int act; float slope;
   const float* res; long rb, rd, rh, rw;
   float* y; long yb, yd, yh, yw;
@@ -38,15 +44,15 @@ struct Conv3sK {
 };
 
 template <bool RES, bool EMIT>
-__global__ void __launch_bounds__(TC_THREADS) conv3s_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(C3_THREADS) conv3s_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, Conv3sK k) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t bres = base;                                        // resident weights
   const uint32_t abase = base + C3_B_BYTES;                          // A stages
-  const uint32_t stg = abase + (uint32_t)C3_STAGES * A_TILE_BYTES;
-  const uint32_t bars = stg + STG_BYTES;                             // full[S], empty[S], tmem_full, wready, tmem slot
+  const uint32_t stg = abase + (uint32_t)C3_STAGES * C3_HALO_BYTES;
+  const uint32_t bars = stg + C3_EGROUPS * STG_BYTES;                // full[S], empty[S], tmem_full, wready, tmem slot
   const uint32_t tmem_full = bars + 16u * C3_STAGES;
   const uint32_t wready = tmem_full + 8u;
   const uint32_t tmem_slot = wready + 8u;
@@ -55,7 +61,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3s_tc_kernel(const __grid_cons
   int t = blockIdx.x;
   const int tw = t % k.ntw; t /= k.ntw;
   const int th = t % k.nth; const int b = t / k.nth;
-  const int w0 = tw << k.lbw, h0 = th << k.lbh;
+  const int w0 = tw << 3, h0 = th << 4;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -77,7 +83,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3s_tc_kernel(const __grid_cons
   // zero the accumulators: every MMA accumulates (a slice touches a sliding window of depth columns)
   if (warp >= 2) {
     const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int c = 0; c < 512; c += 16) tc_st16_zero(trow + (uint32_t)c);
+    for (int c = ((warp - 2) >> 2) * 16; c < 512; c += 16 * C3_EGROUPS) tc_st16_zero(trow + (uint32_t)c);
     tc_st_wait();
   }
   tc_fence_before();
@@ -91,12 +97,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv3s_tc_kernel(const __grid_cons
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(bres + (uint32_t)tap * C3_BTAP_BYTES, &tmB, wready, 0, tap * 96);
       int s = 0; uint32_t ph = 0;
       for (int z = 0; z < 16; ++z) {
-        for (int tap = 0; tap < 9; ++tap) {
-          const int kh = tap / 3, kw = tap % 3;
+        for (int kw = 0; kw < 3; ++kw) {
           const uint32_t fb = bars + 8u * s;
           mbar_wait(fb + 8u * C3_STAGES, ph ^ 1u);
-          mbar_expect_tx(fb, A_TILE_BYTES);
-          tma_load_5d(abase + (uint32_t)s * A_TILE_BYTES, &tmA, fb, 0, w0 + kw - 1, h0 + kh - 1, z, b);
+          mbar_expect_tx(fb, C3_HALO_BYTES);
+          tma_load_5d(abase + (uint32_t)s * C3_HALO_BYTES, &tmA, fb, 0, w0 + kw - 1, h0 - 1, z, b);
           if (++s == C3_STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -111,12 +116,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv3s_tc_kernel(const __grid_cons
       const uint32_t idesc = (1u << 4) | IDESC_AB_FMT | ((N >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t d_acc = tmem_base + (uint32_t)(dlo * 32);
       const uint32_t brow = (uint32_t)(dlo - (z - 1)) * 32u * 128u;  // skip the depth-tap slot of d = -1
-      for (int tap = 0; tap < 9; ++tap) {
+      for (int kw = 0; kw < 3; ++kw) {
         const uint32_t fb = bars + 8u * s;
         mbar_wait(fb, ph);
         tc_fence_after();
-        mma_stage<3, 2>(d_acc, d_acc, umma_desc(abase + (uint32_t)s * A_TILE_BYTES),
-                        umma_desc(bres + (uint32_t)tap * C3_BTAP_BYTES + brow), idesc, 1u, 1u, fb + 8u * C3_STAGES);
+        const uint32_t sa = abase + (uint32_t)s * C3_HALO_BYTES;
+        // kh = 0, 1, 2: the 128-row window of the halo tile starting kh image rows (= kh swizzle atoms) down
+        mma_stage32_nocommit(d_acc, d_acc, umma_desc(sa), umma_desc(bres + (uint32_t)kw * C3_BTAP_BYTES + brow), idesc, 1u, 1u);
+        mma_stage32_nocommit(d_acc, d_acc, umma_desc(sa + 1024u), umma_desc(bres + (uint32_t)(3 + kw) * C3_BTAP_BYTES + brow), idesc, 1u, 1u);
+        mma_stage<3, 2>(d_acc, d_acc, umma_desc(sa + 2048u), umma_desc(bres + (uint32_t)(6 + kw) * C3_BTAP_BYTES + brow), idesc, 1u, 1u,
+                        fb + 8u * C3_STAGES);
         if (++s == C3_STAGES) { s = 0; ph ^= 1u; }
       }
     }
@@ -127,15 +136,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv3s_tc_kernel(const __grid_cons
         ::"r"(tmem_full) : "memory");
   } else {
     // ===== epilogue: per output depth 32 columns -> smem tile -> coalesced rows =====
-    const int q = warp & 3;
-    float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + q * 32 * STG_LD;
+    const int q = warp & 3, eg = (warp - 2) >> 2;
+    float* tile = reinterpret_cast<float*>(smem_raw + (stg - raw)) + (eg * 4 + q) * 32 * STG_LD;
     const int sub = lane >> 3, c4 = (lane & 7) * 4;
     long yoff[8], roff[RES ? 8 : 1], epix[EMIT ? 8 : 1];
     uint32_t vmask = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       int r = q * 32 + sub + 4 * i;
-      const int ow = w0 + (r & ((1 << k.lbw) - 1)); r >>= k.lbw;
+      const int ow = w0 + (r & 7); r >>= 3;
       const int oh = h0 + r;
       if (ow < k.W && oh < k.H) vmask |= 1u << i;
       yoff[i] = b * k.yb + oh * k.yh + ow * k.yw + c4;
@@ -155,10 +164,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv3s_tc_kernel(const __grid_cons
       eb[0] = b4.x; eb[1] = b4.y; eb[2] = b4.z; eb[3] = b4.w;
     }
     const long dstride_e = (long)k.H * k.W;
+    if constexpr (RES) {                                    // pull this warp's residual rows towards L2 while the MMAs run
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!((vmask >> i) & 1u)) continue;
+        for (int d = eg; d < 16; d += C3_EGROUPS)
+          if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(k.res + roff[i] + d * k.rd));
+      }
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int d = 0; d < 16; ++d) {
+    for (int d = eg; d < 16; d += C3_EGROUPS) {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[16];
@@ -256,10 +273,7 @@ void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& 
   CS_REQUIRE(!e.mult, CS_ERR_INVALID, "conv3s_tc: per-pixel multiplier not supported");
   Conv3sK k{};
   k.B = x.B; k.H = x.H; k.W = x.W;
-  int cap = 128;
-  const int bw = pick_box(x.W, cap, &k.lbw); cap /= bw;
-  const int bh = cap; k.lbh = 0; while ((1 << k.lbh) < bh) ++k.lbh;
-  k.ntw = (x.W + bw - 1) / bw; k.nth = (x.H + bh - 1) / bh;
+  k.ntw = (x.W + 7) / 8; k.nth = (x.H + 15) / 16;
   k.bias = w.bias; k.act = e.act; k.slope = e.slope;
   k.res = e.residual; k.rb = e.rs_b; k.rd = e.rs_d; k.rh = e.rs_h; k.rw = e.rs_w;
   if (e.residual)
@@ -278,7 +292,7 @@ void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& 
     const cuuint64_t pix = 64 * 2;
     cuuint64_t dims[5] = {64, (cuuint64_t)x.W, (cuuint64_t)x.H, 16, (cuuint64_t)x.B};
     cuuint64_t strides[4] = {pix, pix * x.W, pix * x.W * x.H, pix * x.W * x.H * 16};
-    cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+    cuuint32_t box[5] = {64, 8, 18, 1, 1};                 // halo tile: 8 (w) x 18 (h) pixels
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -306,7 +320,7 @@ void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& 
   const long M = (long)x.B * 16 * x.H * x.W;
   ProfScope ps(L, PK_CONV_TC, 2.0 * (double)M * 32 * 32 * 27, 0.0, "conv3s");
   dim3 grid((unsigned)(k.ntw * k.nth * x.B));
-  fns[k.res != nullptr][k.emit != nullptr]<<<grid, TC_THREADS, C3_SMEM, L.stream>>>(tmA, tmB, k);
+  fns[k.res != nullptr][k.emit != nullptr]<<<grid, C3_THREADS, C3_SMEM, L.stream>>>(tmA, tmB, k);
   check_launch("conv3s_tc");
 }
 

@@ -168,6 +168,16 @@ __device__ __forceinline__ void mma_stage(uint32_t d_main, uint32_t d_corr, uint
   }
 }
 
+// the same 6 MMAs (3 passes x 2 K-steps, one CTA) without the commit: several operand windows of one pipeline stage
+// (conv3s_tc.cu: the three kh taps of a halo tile) are issued back to back and the last one frees the stage
+__device__ __forceinline__ void mma_stage32_nocommit(uint32_t d_main, uint32_t d_corr, uint64_t ad, uint64_t bd, uint32_t idesc,
+                                                     uint32_t acc_main, uint32_t acc_corr) {
+  const uint32_t bar = 0;
+  asm volatile(CS_MMA_HEAD CS_MMA("%0", "%2", "%3", "%4", "pm") CS_MMA("%0", "a2", "b2", "%4", "pt")
+               CS_MMA("%1", "a4", "%3", "ilh", "pc") CS_MMA("%1", "a6", "b2", "ilh", "pt")
+               CS_MMA("%1", "%2", "b4", "ihl", "pt") CS_MMA("%1", "a2", "b6", "ihl", "pt") "}" CS_MMA_OPS);
+}
+
 template <int NPASS, int CTAS = 1>
 __device__ __forceinline__ void mma_stage_k(int ksteps, uint32_t d_main, uint32_t d_corr, uint64_t ad, uint64_t bd,
                                             uint32_t idesc, uint32_t acc_main, uint32_t acc_corr, uint32_t bar) {
