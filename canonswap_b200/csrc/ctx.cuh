@@ -91,7 +91,7 @@ struct cs_ctx {
   cs::Weights W;
   double* stats_scratch = nullptr; // [max_batch*512*2] double
   double* stats_scratch2 = nullptr; // the second lane's (CS_OPT_LANES)
-  int lanes = 1;                   // CS_OPT_LANES: a graph-captured cs_frame runs as this many concurrent sub-batches
+  int lanes = 2;                   // CS_OPT_LANES: a graph-captured cs_frame runs as this many concurrent sub-batches
   cudaStream_t cap_stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t arena_half_need = 0;      // high-water mark of cs_frame at ceil(max_batch / 2)
