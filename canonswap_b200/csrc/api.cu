@@ -35,6 +35,7 @@ Net make_net(cs_ctx* ctx, void* stream, bool dry) {
   n.ctx = ctx;
   n.A = &ctx->arena;
   n.stats = ctx->stats_scratch;
+  n.grn = ctx->M.sumsq;
   n.L.stream = static_cast<cudaStream_t>(stream);
   n.L.dry = dry;
   n.L.counter = dry ? nullptr : &ctx->launches;
@@ -135,6 +136,14 @@ void body_frame(Net& n, const void* frames, const float* kp_t, const float* kp_c
   float* o256 = n.A->f32((size_t)B * c->h * c->w * 256);
   if (flags & CS_FRAME_IN_U8_HWC) ingest_u8(n.L, static_cast<const uint8_t*>(frames), img_cl, npix * 3);   // prepare_videos
   else nchw_to_cl(n.L, static_cast<const float*>(frames), img_cl, B, 3, (long)c->net_h * c->net_w, 0);
+  if (flags & CS_FRAME_MOTION) {                                  // x_t / x_can of the frames from M (:112-125, :231-243)
+    float* heads = n.A->f32((size_t)B * CS_MOTION_HEADS);
+    float* kt = n.A->f32((size_t)B * NUM_KP * 3);
+    float* kc = n.A->f32((size_t)B * NUM_KP * 3);
+    run_motion(n, img_cl, B, heads);
+    run_keypoints(n, heads, B, kt, kc, nullptr, nullptr);
+    kp_t = kt; kp_can = kc;
+  }
   run_F(n, img_cl, B, va);                                        // :242 f_s = extract_feature_3d(I_s)
   if (flags & CS_FRAME_V2I) {                                     // can_swap_pipeline_v2i.py:308-309
     run_warp(n, va, /*kp_source=*/kp_t, /*kp_driving=*/kp_can, B, vb, occ, nullptr);
@@ -158,6 +167,13 @@ void body_frame(Net& n, const void* frames, const float* kp_t, const float* kp_c
   run_spade(n, o256, B, out_f32, out_u8);                         // :267 parse_output fused into the emit kernel
 }
 
+void body_motion(Net& n, const float* img, float* heads, int B) {
+  cs_ctx* c = n.ctx;
+  float* img_cl = n.A->f32((size_t)B * c->net_h * c->net_w * 3);
+  nchw_to_cl(n.L, img, img_cl, B, 3, (long)c->net_h * c->net_w, 0);
+  run_motion(n, img_cl, B, heads);
+}
+
 // size the arena: dry-run every entry point at max_batch and keep the high-water mark
 void size_workspace(cs_ctx* ctx) {
   Arena& A = ctx->arena;
@@ -179,7 +195,8 @@ void size_workspace(cs_ctx* ctx) {
       A.reset(0); body_refine(n, fake, fake, B);
       A.reset(0); body_spade(n, fake, fake, reinterpret_cast<uint8_t*>(fake), B);
       A.reset(0); body_frame(n, fake, fake, fake, fake, reinterpret_cast<uint8_t*>(fake), B,
-                             CS_FRAME_IN_U8_HWC | CS_FRAME_DEBUG_DECODES);
+                             CS_FRAME_IN_U8_HWC | CS_FRAME_DEBUG_DECODES | (ctx->M.loaded ? CS_FRAME_MOTION : 0));
+      if (ctx->M.loaded) { A.reset(0); body_motion(n, fake, fake, B); }
     }
   }
   // two-lane replay (CS_OPT_LANES): each half of the arena must hold cs_frame at ceil(max_batch / 2)
@@ -190,7 +207,7 @@ void size_workspace(cs_ctx* ctx) {
     for (int impl = 0; impl < 2; ++impl) {
       n.L.conv_impl = impl;
       A.reset(0); body_frame(n, fake, fake, fake, fake, reinterpret_cast<uint8_t*>(fake), (B + 1) / 2,
-                             CS_FRAME_IN_U8_HWC | CS_FRAME_DEBUG_DECODES);
+                             CS_FRAME_IN_U8_HWC | CS_FRAME_DEBUG_DECODES | (ctx->M.loaded ? CS_FRAME_MOTION : 0));
     }
     ctx->arena_half_need = A.high + 4096;
     A.high = full_high > 2 * ctx->arena_half_need ? full_high : 2 * ctx->arena_half_need;
@@ -305,6 +322,7 @@ size_t cs_workspace_bytes(const cs_ctx* ctx) { return ctx ? ctx->owned_bytes : 0
 int cs_load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
   CS_API_BEGIN(ctx)
   load_weights(ctx, table, n);
+  if (motion_weights_present(table, n)) load_motion_weights(ctx, table, n);   // optional: combined_weights['motion_extractor']
   size_workspace(ctx);
   CS_API_END(ctx)
 }
@@ -392,7 +410,9 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
              int flags, void* stream) {
   CS_API_BEGIN(ctx)
   check_batch(ctx, B);
-  CS_REQUIRE(frames && kp_t && kp_can && (out_f32 || out_u8), CS_ERR_INVALID, "cs_frame: null tensor");
+  CS_REQUIRE(frames && (out_f32 || out_u8), CS_ERR_INVALID, "cs_frame: null tensor");
+  CS_REQUIRE((flags & CS_FRAME_MOTION) || (kp_t && kp_can), CS_ERR_INVALID, "cs_frame: null keypoints without CS_FRAME_MOTION");
+  CS_REQUIRE(!(flags & CS_FRAME_MOTION) || ctx->M.loaded, CS_ERR_STATE, "cs_frame: CS_FRAME_MOTION without motion extractor weights");
   CS_REQUIRE(ctx->identity_set || (flags & CS_FRAME_V2I), CS_ERR_STATE, "cs_frame before cs_set_identity");
   Net n = make_net(ctx, stream, false);
   ctx->arena.reset(0);
@@ -450,6 +470,7 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
             const size_t in_off = (flags & CS_FRAME_IN_U8_HWC) ? px0 * 3 : px0 * 3 * sizeof(float);
             Net n0 = n; n0.A = &a0;
             Net n1 = n; n1.A = &a1; n1.L.stream = ctx->cap_stream2; n1.stats = ctx->stats_scratch2;
+            if (ctx->M.sumsq) n1.grn = ctx->M.sumsq + (size_t)B0 * 3072;
             body_frame(n0, ctx->g_frames, ctx->g_kpt, ctx->g_kpc, out_f32 ? ctx->g_out32 : nullptr, out_u8 ? ctx->g_outu8 : nullptr,
                        B0, flags);
             body_frame(n1, static_cast<char*>(ctx->g_frames) + in_off, ctx->g_kpt + (size_t)B0 * NUM_KP * 3,
@@ -474,14 +495,36 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
         ctx->launches = l0;
       }
       CS_CUDA(cudaMemcpyAsync(ctx->g_frames, frames, in_bytes, cudaMemcpyDeviceToDevice, st));
-      CS_CUDA(cudaMemcpyAsync(ctx->g_kpt, kp_t, kp_bytes, cudaMemcpyDeviceToDevice, st));
-      CS_CUDA(cudaMemcpyAsync(ctx->g_kpc, kp_can, kp_bytes, cudaMemcpyDeviceToDevice, st));
+      if (!(flags & CS_FRAME_MOTION)) {
+        CS_CUDA(cudaMemcpyAsync(ctx->g_kpt, kp_t, kp_bytes, cudaMemcpyDeviceToDevice, st));
+        CS_CUDA(cudaMemcpyAsync(ctx->g_kpc, kp_can, kp_bytes, cudaMemcpyDeviceToDevice, st));
+      }
       CS_CUDA(cudaGraphLaunch(fg->exec, st));
       if (out_f32) CS_CUDA(cudaMemcpyAsync(out_f32, ctx->g_out32, o32_bytes, cudaMemcpyDeviceToDevice, st));
       if (out_u8) CS_CUDA(cudaMemcpyAsync(out_u8, ctx->g_outu8, ou8_bytes, cudaMemcpyDeviceToDevice, st));
       ctx->launches += fg->launches;
     }
   }
+  CS_API_END(ctx)
+}
+
+int cs_motion(cs_ctx* ctx, const float* img, float* heads, int B, void* stream) {
+  CS_API_BEGIN(ctx)
+  check_batch(ctx, B);
+  CS_REQUIRE(img && heads, CS_ERR_INVALID, "cs_motion: null tensor");
+  CS_REQUIRE(ctx->M.loaded, CS_ERR_STATE, "cs_motion: motion extractor weights not loaded");
+  Net n = make_net(ctx, stream, false);
+  ctx->arena.reset(0);
+  body_motion(n, img, heads, B);
+  CS_API_END(ctx)
+}
+
+int cs_keypoints(cs_ctx* ctx, const float* heads, float* x_s, float* x_can, float* R, float* deg, int B, void* stream) {
+  CS_API_BEGIN(ctx)
+  CS_REQUIRE(B >= 1 && B <= 65535, CS_ERR_INVALID, "cs_keypoints: bad batch");
+  CS_REQUIRE(heads && x_s, CS_ERR_INVALID, "cs_keypoints: null tensor");
+  Net n = make_net(ctx, stream, false);
+  run_keypoints(n, heads, B, x_s, x_can, R, deg);
   CS_API_END(ctx)
 }
 

@@ -109,13 +109,14 @@ __device__ __forceinline__ void split_operand2(float a, float b, uint32_t& hv, u
 }
 #endif
 
-enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_SIGMOID = 3 };
+enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_SIGMOID = 3, ACT_GELU = 4 };
 
 __host__ __device__ inline float apply_act(float v, int kind, float slope) {
   switch (kind) {
     case ACT_RELU: return v > 0.f ? v : 0.f;
     case ACT_LRELU: return v > 0.f ? v : v * slope;
     case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));   // nn.GELU() (exact, erf form)
     default: return v;
   }
 }

@@ -57,6 +57,25 @@ struct SpadeBlockW {         // reference util.py:305-344
   ConvW conv_0, conv_1, conv_s;    // spectral-norm sigma folded
 };
 
+struct MotionBlockW {        // ConvNeXtV2 Block, reference convnextv2.py:23-47
+  float* dw_w = nullptr;     // depthwise 7x7 [49][C]
+  float* dw_b = nullptr;
+  float* ln_w = nullptr; float* ln_b = nullptr;
+  ConvW pw1, pw2;            // Linear C -> 4C (+GELU), Linear 4C -> C, as 1x1 convs
+  float* grn_g = nullptr; float* grn_b = nullptr;
+};
+
+struct MotionW {             // MotionExtractor.detector, reference convnextv2.py:62-103
+  bool loaded = false;
+  float* stem_w = nullptr; float* stem_b = nullptr; float* stem_ln_w = nullptr; float* stem_ln_b = nullptr;
+  float* ds_ln_w[3] = {}; float* ds_ln_b[3] = {};
+  ConvW ds[3];               // 2x2 stride-2 convs as 1x1 convs over space-to-depth channels (kh, kw, ci)
+  MotionBlockW blk[18];
+  float* norm_w = nullptr; float* norm_b = nullptr;
+  float* head_w = nullptr; float* head_b = nullptr;   // [328][768]: kp | scale | pitch | yaw | roll | t | exp
+  double* sumsq = nullptr;   // GRN scratch [max_batch][3072], kept zero between uses
+};
+
 struct Weights {
   // F
   ConvW f_first, f_down[2], f_second;
@@ -89,6 +108,7 @@ struct cs_ctx {
   size_t owned_bytes = 0;
   cs::Arena arena;
   cs::Weights W;
+  cs::MotionW M;
   double* stats_scratch = nullptr; // [max_batch*512*2] double
   double* stats_scratch2 = nullptr; // the second lane's (CS_OPT_LANES)
   int lanes = 2;                   // CS_OPT_LANES: a graph-captured cs_frame runs as this many concurrent sub-batches
@@ -121,6 +141,7 @@ struct Net {                 // per-call view
   Launcher L;
   Arena* A;
   double* stats = nullptr;   // instance-statistics scratch of this lane
+  double* grn = nullptr;     // GRN sum-of-squares scratch of this lane (motion.cu)
   const Weights& W() const { return ctx->W; }
 };
 
@@ -142,5 +163,10 @@ void run_warp_out(Net& n, const float* vol_in, const float* occ, int B, float* o
 void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks);
 void run_refine(Net& n, const float* vol_in, int B, float* vol_out);
 void run_spade(Net& n, const float* feat256, int B, float* img_nchw, uint8_t* img_u8);
+// motion.cu : motion extractor M + keypoint transform
+bool motion_weights_present(const cs_tensor_desc* table, int n);
+void load_motion_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n);
+void run_motion(Net& n, const float* img_cl, int B, float* heads /*[B,CS_MOTION_HEADS]*/);
+void run_keypoints(Net& n, const float* heads, int B, float* x_s, float* x_can, float* R, float* deg);
 
 }  // namespace cs

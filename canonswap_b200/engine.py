@@ -21,8 +21,10 @@ class CanonSwapError(RuntimeError):
 def _flat_table(weights: Mapping[str, Mapping[str, torch.Tensor]]):
     """`combined_weights.pth`-layout dict -> (cs_tensor_desc array, keep-alive list)."""
     names, tensors = [], []
-    for net in spec.NETS:
+    for net in spec.NETS + (spec.MOTION_NET,):
         if net not in weights:
+            if net == spec.MOTION_NET:        # optional: the path takes the keypoints as inputs without it
+                continue
             raise KeyError(f"weights dict lacks the '{net}' state_dict (reference can_swap_e2e.py:93-98)")
         for key, t in weights[net].items():
             t = t.detach()
@@ -201,12 +203,14 @@ class Engine:
         return (img, u8) if want_u8 else img
 
     # ---- the fused loop body --------------------------------------------------------------------
-    def frame(self, frames: torch.Tensor, kp_t: torch.Tensor, kp_can: torch.Tensor, out_u8: Optional[torch.Tensor] = None,
-              out_f32: Optional[torch.Tensor] = None, debug_decodes: bool = False, v2i: bool = False):
+    def frame(self, frames: torch.Tensor, kp_t: Optional[torch.Tensor] = None, kp_can: Optional[torch.Tensor] = None,
+              out_u8: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, debug_decodes: bool = False,
+              v2i: bool = False, motion: bool = False):
         """One batch of the per-frame loop body (reference can_swap_pipeline_e2e.py:242-267).
 
         frames: [B,net_h,net_w,3] uint8 (HWC, as cropped) or [B,3,net_h,net_w] fp32 in [0,1];
-        kp_t = x_t_info['x_s'], kp_can = scale * kp  (both [B,21,3]).
+        kp_t = x_t_info['x_s'], kp_can = scale * kp  (both [B,21,3]); with motion=True they are derived on the device
+        from the frames by the motion extractor (reference can_swap_pipeline_e2e.py:112-125,231-243) and may be None.
         Returns (out_u8 [B,2H,2W,3] uint8, out_f32 [B,3,2H,2W] or None).
         """
         if self._identity is None and not v2i:
@@ -220,17 +224,48 @@ class Engine:
             flags |= _lib.CS_FRAME_IN_U8_HWC
         else:
             fr = self._in(frames, (B, 3, self.net_h, self.net_w), name="frames")
-        kt, kc = self._kp(kp_t, B, "kp_t"), self._kp(kp_can, B, "kp_can")
+        if motion:
+            flags |= _lib.CS_FRAME_MOTION
+            kt = kc = None
+        else:
+            kt, kc = self._kp(kp_t, B, "kp_t"), self._kp(kp_can, B, "kp_can")
         if out_u8 is None and out_f32 is None:
             out_u8 = self._new(B, 2 * self.net_h, 2 * self.net_w, 3, dtype=torch.uint8)
         if out_u8 is not None:
             out_u8 = self._in(out_u8, (B, 2 * self.net_h, 2 * self.net_w, 3), dtype=torch.uint8, name="out_u8")
         if out_f32 is not None:
             out_f32 = self._in(out_f32, (B, 3, 2 * self.net_h, 2 * self.net_w), name="out_f32")
-        self._check(self._lib.cs_frame(self._ctx, fr.data_ptr(), kt.data_ptr(), kc.data_ptr(),
+        self._check(self._lib.cs_frame(self._ctx, fr.data_ptr(), kt.data_ptr() if kt is not None else None,
+                                       kc.data_ptr() if kc is not None else None,
                                        out_f32.data_ptr() if out_f32 is not None else None,
                                        out_u8.data_ptr() if out_u8 is not None else None, B, flags, self._stream()))
         return out_u8, out_f32
+
+    # ---- motion extractor M + keypoint transform ------------------------
+    HEAD_SLICES = (("kp", 0, 63), ("scale", 63, 64), ("pitch", 64, 130), ("yaw", 130, 196), ("roll", 196, 262), ("t", 262, 265),
+                   ("exp", 265, 328))
+
+    def motion(self, img: torch.Tensor) -> torch.Tensor:
+        """MotionExtractor.forward (reference motion_extractor.py:33-35): [B,3,net_h,net_w] in [0,1] -> raw heads [B,328]."""
+        B = self._batch(img)
+        x = self._in(img, (B, 3, self.net_h, self.net_w), name="img")
+        heads = self._new(B, _lib.MOTION_HEADS)
+        self._check(self._lib.cs_motion(self._ctx, x.data_ptr(), heads.data_ptr(), B, self._stream()))
+        return heads
+
+    def motion_dict(self, heads: torch.Tensor):
+        """The reference's ret_dct (convnextv2.py:130-141) as views of the heads buffer."""
+        return {k: heads[:, a:b] for k, a, b in self.HEAD_SLICES}
+
+    def keypoints(self, heads: torch.Tensor):
+        """transform_keypoint (reference can_swap_e2e.py:226-254) -> dict(x_s, x_can = scale * kp, R, deg)."""
+        B = int(heads.shape[0])
+        h = self._in(heads, (B, _lib.MOTION_HEADS), name="heads")
+        x_s, x_can = self._new(B, spec.NUM_KP, 3), self._new(B, spec.NUM_KP, 3)
+        R, deg = self._new(B, 3, 3), self._new(B, 3)
+        self._check(self._lib.cs_keypoints(self._ctx, h.data_ptr(), x_s.data_ptr(), x_can.data_ptr(), R.data_ptr(), deg.data_ptr(), B,
+                                           self._stream()))
+        return {"x_s": x_s, "x_can": x_can, "R": R, "deg": deg}
 
     # ---- measurement -------------------------------------------------------------------------------
     PROFILE_FAMILIES = ("conv_tcgen05", "conv_simt", "prep", "stats", "sampling", "other")

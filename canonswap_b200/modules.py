@@ -27,6 +27,14 @@ from torch import nn
 from . import spec
 from .engine import CanonSwapError, Engine
 
+def _headpose_pred_to_degree(pred):
+    """reference src/utils/camera.py:14-29 (only for a caller-supplied torch motion extractor)"""
+    if pred.ndim > 1 and pred.shape[1] == 66:
+        idx = torch.arange(66, dtype=torch.float32, device=pred.device)
+        return torch.sum(torch.softmax(pred, dim=1) * idx, dim=1) * 3 - 97.5
+    return pred
+
+
 _BUFFER_LEAVES = ("running_mean", "running_var", "num_batches_tracked", "weight_u", "weight_v")
 
 
@@ -51,7 +59,7 @@ class _EngineHub:
         self.version += 1
 
     def engine(self, net_hw: Tuple[int, int], batch: int = 1) -> Engine:
-        missing = [n for n in spec.NETS if n not in self.modules]
+        missing = [n for n in spec.NETS if n not in self.modules]   # the motion extractor is optional
         if missing:
             raise CanonSwapError(f"engine needs all five hot-path networks; not bound: {missing}")
         if batch > self.max_batch:
@@ -206,6 +214,24 @@ class G3d(_SpecModule):
         return self._engine(x, (4 * int(x.shape[3]), 4 * int(x.shape[4]))).refine(x.float())
 
 
+class MotionExtractor(_SpecModule):
+    """reference src/modules/motion_extractor.py:18-35 (ConvNeXtV2-tiny detector, convnextv2.py:48-144)."""
+    NET = spec.MOTION_NET
+
+    def __init__(self, num_kp=21, backbone="convnextv2_tiny", hub=None, **kwargs):
+        if num_kp != 21 or backbone != "convnextv2_tiny":
+            raise CanonSwapError("unsupported MotionExtractor config (reference models.yaml:10-12)")
+        super().__init__(hub)
+
+    def forward(self, x: torch.Tensor):
+        """[B,3,H,W] in [0,1] -> {'pitch','yaw','roll' [B,66], 't' [B,3], 'exp' [B,63], 'scale' [B,1], 'kp' [B,63]}"""
+        eng = self._engine(x, (int(x.shape[2]), int(x.shape[3])))
+        heads = eng.motion(x.float())
+        d = eng.motion_dict(heads)
+        d["_heads"] = heads                 # the packed buffer (not in the reference dict): lets transform_keypoint run on device
+        return d
+
+
 class can_swapper(object):
     """Hot-path members of the reference wrapper (src/can_swap_e2e.py:39-348).
 
@@ -233,7 +259,10 @@ class can_swapper(object):
         self.spade_generator = SPADEDecoder(upscale=2, hub=self._hub)
         self.swap_module = transfer_model_big(hub=self._hub)
         self.refine_module = G3d(hub=self._hub)
+        # the motion extractor is the B200 module unless the caller passes a torch one (it joins the engine only when its
+        # weights are loaded: combined_weights['motion_extractor'])
         self.motion_extractor = motion_extractor
+        self._own_motion = motion_extractor is None
         self.netArc = netArc
         if weights is not None:
             self.load_cpk(weights)
@@ -247,8 +276,38 @@ class can_swapper(object):
         self.spade_generator.load_state_dict(combined_weights["spade_generator"])
         self.swap_module.load_state_dict(combined_weights["transfer"])
         self.refine_module.load_state_dict(combined_weights["refine"])
-        if self.motion_extractor is not None and "motion_extractor" in combined_weights:
+        if "motion_extractor" in combined_weights:
+            if self.motion_extractor is None:
+                self.motion_extractor = MotionExtractor(hub=self._hub)
             self.motion_extractor.load_state_dict(combined_weights["motion_extractor"])
+
+    # reference can_swap_e2e.py:174-199
+    def get_kp_info(self, x: torch.Tensor, **kwargs) -> dict:
+        if self.motion_extractor is None:
+            raise CanonSwapError("get_kp_info needs the motion extractor weights (combined_weights['motion_extractor'])")
+        with torch.no_grad():
+            kp_info = dict(self.motion_extractor(x))
+        heads = kp_info.pop("_heads", None)
+        if kwargs.get("flag_refine_info", True):
+            bs = kp_info["kp"].shape[0]
+            if heads is not None:
+                deg = self._hub.engine(self.input_shape, bs).keypoints(heads)["deg"]
+                kp_info["pitch"], kp_info["yaw"], kp_info["roll"] = deg[:, 0:1], deg[:, 1:2], deg[:, 2:3]
+            else:
+                for k in ("pitch", "yaw", "roll"):
+                    kp_info[k] = _headpose_pred_to_degree(kp_info[k])[:, None]
+            kp_info["kp"] = kp_info["kp"].reshape(bs, -1, 3)
+            kp_info["exp"] = kp_info["exp"].reshape(bs, -1, 3)
+        if heads is not None:
+            kp_info["_heads"] = heads
+        return kp_info
+
+    # reference can_swap_e2e.py:226-254
+    def transform_keypoint(self, kp_info: dict) -> torch.Tensor:
+        heads = kp_info.get("_heads")
+        if heads is None:
+            raise CanonSwapError("transform_keypoint: kp_info must come from this can_swapper's get_kp_info / motion_extractor")
+        return self._hub.engine(self.input_shape, int(heads.shape[0])).keypoints(heads)["x_s"]
 
     def getid(self, img):
         if self.netArc is None:
@@ -307,9 +366,10 @@ class can_swapper(object):
     def set_source_identity(self, source_id: torch.Tensor):
         self._hub.set_identity(source_id.to(self.device).float())
 
-    def swap_frames(self, frames: torch.Tensor, x_t: torch.Tensor, x_can: torch.Tensor, out_u8=None, out_f32=None,
-                    debug_decodes: bool = False):
-        """frames [B,H,W,3] u8 or [B,3,H,W] fp32 on device; x_t = x_t_info['x_s'], x_can = scale*kp.
+    def swap_frames(self, frames: torch.Tensor, x_t: Optional[torch.Tensor] = None, x_can: Optional[torch.Tensor] = None,
+                    out_u8=None, out_f32=None, debug_decodes: bool = False):
+        """frames [B,H,W,3] u8 or [B,3,H,W] fp32 on device; x_t = x_t_info['x_s'], x_can = scale*kp, or both None to
+        derive them from the frames with the motion extractor (make_motion_template, pipeline_e2e.py:112-125).
         Returns (u8 [B,2H,2W,3], fp32 [B,3,2H,2W] or None)."""
         if frames.dtype == torch.uint8:
             hw = (int(frames.shape[1]), int(frames.shape[2]))
@@ -318,7 +378,8 @@ class can_swapper(object):
         if not frames.is_cuda:
             raise CanonSwapError("swap_frames: frames must be on the CUDA device")
         eng = self._hub.engine(hw, int(frames.shape[0]))
-        return eng.frame(frames, x_t, x_can, out_u8=out_u8, out_f32=out_f32, debug_decodes=debug_decodes)
+        return eng.frame(frames, x_t, x_can, out_u8=out_u8, out_f32=out_f32, debug_decodes=debug_decodes,
+                         motion=x_t is None and x_can is None)
 
     def animate_frames(self, frames: torch.Tensor, kp_source: torch.Tensor, kp_driving: torch.Tensor, out_u8=None, out_f32=None):
         """The per-frame body of the video-to-image pipeline (reference can_swap_pipeline_v2i.py:308-309) in one call:

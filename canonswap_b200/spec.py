@@ -171,8 +171,51 @@ def refine_spec():
     return sd
 
 
+# motion extractor M: ConvNeXtV2-tiny, reference src/modules/convnextv2.py:48-144 wrapped as
+# MotionExtractor.detector (src/modules/motion_extractor.py:18-24); checkpoint key 'motion_extractor' (can_swap_e2e.py:94)
+MOTION_NET = "motion_extractor"
+MOTION_DEPTHS = (3, 3, 9, 3)
+MOTION_DIMS = (96, 192, 384, 768)
+NUM_BINS = 66
+# heads in registration order (convnextv2.py:95-103) -> output width
+MOTION_HEADS = (("fc_kp", 3 * NUM_KP), ("fc_scale", 1), ("fc_pitch", NUM_BINS), ("fc_yaw", NUM_BINS), ("fc_roll", NUM_BINS),
+                ("fc_t", 3), ("fc_exp", 3 * NUM_KP))
+
+
+def motion_extractor_spec():
+    sd = OrderedDict()
+    p = "detector"
+    d = MOTION_DIMS
+    _conv(sd, f"{p}.downsample_layers.0.0", d[0], 3, 4, 4)
+    sd[f"{p}.downsample_layers.0.1.weight"] = (d[0],)
+    sd[f"{p}.downsample_layers.0.1.bias"] = (d[0],)
+    for i in range(3):
+        sd[f"{p}.downsample_layers.{i + 1}.0.weight"] = (d[i],)
+        sd[f"{p}.downsample_layers.{i + 1}.0.bias"] = (d[i],)
+        _conv(sd, f"{p}.downsample_layers.{i + 1}.1", d[i + 1], d[i], 2, 2)
+    for i in range(4):
+        for j in range(MOTION_DEPTHS[i]):
+            q = f"{p}.stages.{i}.{j}"
+            _conv(sd, q + ".dwconv", d[i], 1, 7, 7)
+            sd[q + ".norm.weight"] = (d[i],)
+            sd[q + ".norm.bias"] = (d[i],)
+            sd[q + ".pwconv1.weight"] = (4 * d[i], d[i])
+            sd[q + ".pwconv1.bias"] = (4 * d[i],)
+            sd[q + ".grn.gamma"] = (1, 1, 1, 4 * d[i])
+            sd[q + ".grn.beta"] = (1, 1, 1, 4 * d[i])
+            sd[q + ".pwconv2.weight"] = (d[i], 4 * d[i])
+            sd[q + ".pwconv2.bias"] = (d[i],)
+    sd[f"{p}.norm.weight"] = (d[3],)
+    sd[f"{p}.norm.bias"] = (d[3],)
+    for name, n in MOTION_HEADS:
+        sd[f"{p}.{name}.weight"] = (n, d[3])
+        sd[f"{p}.{name}.bias"] = (n,)
+    return sd
+
+
 def net_spec(net: str):
     return {
+        "motion_extractor": motion_extractor_spec,
         "appearance_feature_extractor": appearance_feature_extractor_spec,
         "warping_module": warping_module_spec,
         "spade_generator": spade_generator_spec,

@@ -123,9 +123,58 @@ def synth_state_dict(net: str, seed: int = WEIGHT_SEED) -> "OrderedDict[str, tor
     return sd
 
 
-def synth_weights(seed: int = WEIGHT_SEED):
-    """The full `combined_weights.pth`-layout dict for the five hot-path networks."""
-    return OrderedDict((n, synth_state_dict(n, seed)) for n in spec.NETS)
+def synth_motion_state_dict(seed: int = WEIGHT_SEED) -> "OrderedDict[str, torch.Tensor]":
+    """Calibrated synthetic state_dict of the motion extractor (`combined_weights['motion_extractor']`, reference
+    can_swap_e2e.py:94): LayerNorm / GRN parameters away from their identity init, residual branches damped so the 18
+    blocks keep O(1) activations, heads scaled so that the keypoints land in (-1, 1), scale near 1 and the head-pose
+    bins give non-trivial angles."""
+    g = torch.Generator().manual_seed(seed + 17 * 7)
+    sd = OrderedDict()
+    for key, shape in spec.motion_extractor_spec().items():
+        leaf = key.rsplit(".", 1)[-1]
+        if re.search(r"(\.norm|downsample_layers\.0\.1|downsample_layers\.[123]\.0)\.weight$", key):
+            t = _uniform(shape, 0.8, 1.2, g)
+        elif re.search(r"(\.norm|downsample_layers\.0\.1|downsample_layers\.[123]\.0)\.bias$", key):
+            t = _normal(shape, 0.1, g)
+        elif leaf == "gamma":
+            t = _normal(shape, 0.3, g)
+        elif leaf == "beta":
+            t = _normal(shape, 0.1, g)
+        elif leaf == "weight":
+            fan_in = math.prod(shape[1:])
+            gain = 1.0
+            if "pwconv2" in key:
+                gain = 0.5
+            elif "dwconv" in key:
+                gain = 1.2
+            elif "fc_kp" in key:
+                gain = 0.25
+            elif "fc_exp" in key:
+                gain = 0.03
+            elif "fc_t" in key:
+                gain = 0.1
+            elif "fc_scale" in key:
+                gain = 0.1
+            elif re.search(r"fc_(pitch|yaw|roll)", key):
+                gain = 1.5
+            t = _normal(shape, gain / math.sqrt(fan_in), g)
+        elif leaf == "bias":
+            if "fc_scale" in key:
+                t = 1.2 + _normal(shape, 0.02, g)
+            else:
+                t = _normal(shape, 0.05, g)
+        else:
+            raise KeyError(f"no synthetic rule for motion_extractor.{key}")
+        sd[key] = t
+    return sd
+
+
+def synth_weights(seed: int = WEIGHT_SEED, with_motion: bool = False):
+    """The full `combined_weights.pth`-layout dict for the five hot-path networks (+ the motion extractor on request)."""
+    w = OrderedDict((n, synth_state_dict(n, seed)) for n in spec.NETS)
+    if with_motion:
+        w[spec.MOTION_NET] = synth_motion_state_dict(seed)
+    return w
 
 
 def synth_inputs(T: int, net_hw: int, seed: int = INPUT_SEED, u8: bool = False):

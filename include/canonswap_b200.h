@@ -58,6 +58,9 @@ typedef struct cs_tensor_desc {
 /* flags of cs_frame */
 #define CS_FRAME_IN_U8_HWC   1   /* frames are [B,net_h,net_w,3] u8 (else [B,3,net_h,net_w] fp32)   */
 #define CS_FRAME_DEBUG_DECODES 2 /* also run the two debug decodes of pipeline_e2e.py:248,257 (results discarded) */
+#define CS_FRAME_MOTION      8   /* derive kp_t / kp_can from the frames themselves with the motion extractor (needs the
+                                    'motion_extractor' tensors): x_t = transform_keypoint(M(I)), x_can = scale * kp
+                                    (can_swap_pipeline_e2e.py:112-125,231-243); the kp_t / kp_can arguments may be null */
 #define CS_FRAME_V2I         4   /* video-to-image per-frame body (can_swap_pipeline_v2i.py:308-309) instead of the e2e one:
                                     out = warp_decode(extract_feature_3d(frames), kp_source = kp_t, kp_driving = kp_can);
                                     no identity needed (the swap ran once per source, outside the loop) */
@@ -134,6 +137,16 @@ CS_API int cs_spade(cs_ctx* ctx, const float* feat, float* img, uint8_t* img_u8,
  * out_f32 [B,3,2*net_h,2*net_w] and/or out_u8 [B,2*net_h,2*net_w,3] (either may be NULL). */
 CS_API int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp_can,
              float* out_f32, uint8_t* out_u8, int B, int flags, void* stream);
+
+/* ---- motion extractor M + keypoint transform ------------------- */
+#define CS_MOTION_HEADS 328      /* kp 63 | scale 1 | pitch 66 | yaw 66 | roll 66 | t 3 | exp 63 (registration order of the heads) */
+/* can_swapper.motion_extractor(x) (src/can_swap_e2e.py:64, src/modules/motion_extractor.py:33-35 -> convnextv2.py:110-144):
+ * img [B,3,net_h,net_w] fp32 in [0,1] -> heads [B,CS_MOTION_HEADS], the seven raw Linear outputs concatenated. */
+CS_API int cs_motion(cs_ctx* ctx, const float* img, float* heads, int B, void* stream);
+/* can_swapper.transform_keypoint (src/can_swap_e2e.py:226-254) with headpose_pred_to_degree / get_rotation_matrix
+ * (src/utils/camera.py:14-73): heads -> x_s [B,21,3]; optional x_can = scale * kp [B,21,3] (can_swap_pipeline_e2e.py:242),
+ * R [B,3,3], deg [B,3] = pitch, yaw, roll in degrees (get_kp_info, src/can_swap_e2e.py:191-197). */
+CS_API int cs_keypoints(cs_ctx* ctx, const float* heads, float* x_s, float* x_can, float* R, float* deg, int B, void* stream);
 
 /* ---- per-kernel-family timing (measurement only) -------------------------------------------- */
 /* enable != 0: bracket every kernel launch of this ctx with CUDA events on the launching stream. */

@@ -328,3 +328,95 @@ def frame_v2i(weights, I, kp_source, kp_driving):
         f = appearance_feature_extractor(sdF, I)
         wf = warping_forward(sdW, f, kp_driving=kp_driving, kp_source=kp_source)
         return spade_decoder(sdG, wf["out"])
+
+
+# ------------------------------------------------------------------------------------------
+# motion extractor M + keypoint transform
+# ------------------------------------------------------------------------------------------
+LN_EPS = 1e-6     # reference convnextv2.py:27,76,79,93 / util.py:378
+MOTION_DEPTHS = (3, 3, 9, 3)
+
+
+def _ln_cf(x, w, b):
+    """LayerNorm over the channel axis of an NCHW tensor, reference util.py:391-396 (channels_first branch)."""
+    u = x.mean(1, keepdim=True)
+    s = (x - u).pow(2).mean(1, keepdim=True)
+    x = (x - u) / torch.sqrt(s + LN_EPS)
+    return w[:, None, None] * x + b[:, None, None]
+
+
+def convnext_block(sd, p, x):
+    """reference convnextv2.py:34-47: dwconv7 -> LN -> Linear -> GELU -> GRN (util.py:365-368) -> Linear -> + input."""
+    dim = x.shape[1]
+    y = F.conv2d(x, sd[p + ".dwconv.weight"], sd[p + ".dwconv.bias"], padding=3, groups=dim)
+    y = y.permute(0, 2, 3, 1)
+    y = F.layer_norm(y, (dim,), sd[p + ".norm.weight"], sd[p + ".norm.bias"], LN_EPS)
+    y = F.linear(y, sd[p + ".pwconv1.weight"], sd[p + ".pwconv1.bias"])
+    y = F.gelu(y)
+    gx = torch.norm(y, p=2, dim=(1, 2), keepdim=True)
+    nx = gx / (gx.mean(dim=-1, keepdim=True) + 1e-6)
+    y = sd[p + ".grn.gamma"] * (y * nx) + sd[p + ".grn.beta"] + y
+    y = F.linear(y, sd[p + ".pwconv2.weight"], sd[p + ".pwconv2.bias"])
+    return x + y.permute(0, 3, 1, 2)
+
+
+def motion_extractor(sd, x):
+    """MotionExtractor.forward -> ConvNeXtV2.forward, reference motion_extractor.py:33-35, convnextv2.py:110-144.
+    x [B,3,H,W] in [0,1] -> dict(pitch, yaw, roll [B,66], t [B,3], exp [B,63], scale [B,1], kp [B,63])."""
+    p = "detector"
+    x = F.conv2d(x, sd[f"{p}.downsample_layers.0.0.weight"], sd[f"{p}.downsample_layers.0.0.bias"], stride=4)
+    x = _ln_cf(x, sd[f"{p}.downsample_layers.0.1.weight"], sd[f"{p}.downsample_layers.0.1.bias"])
+    for i in range(4):
+        if i > 0:
+            x = _ln_cf(x, sd[f"{p}.downsample_layers.{i}.0.weight"], sd[f"{p}.downsample_layers.{i}.0.bias"])
+            x = F.conv2d(x, sd[f"{p}.downsample_layers.{i}.1.weight"], sd[f"{p}.downsample_layers.{i}.1.bias"], stride=2)
+        for j in range(MOTION_DEPTHS[i]):
+            x = convnext_block(sd, f"{p}.stages.{i}.{j}", x)
+    f = F.layer_norm(x.mean([-2, -1]), (x.shape[1],), sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], LN_EPS)
+    return {k: F.linear(f, sd[f"{p}.fc_{k}.weight"], sd[f"{p}.fc_{k}.bias"])
+            for k in ("pitch", "yaw", "roll", "t", "exp", "scale", "kp")}
+
+
+def headpose_pred_to_degree(pred):
+    """reference src/utils/camera.py:14-29."""
+    if pred.ndim > 1 and pred.shape[1] == 66:
+        idx = torch.arange(66, dtype=torch.float32)
+        return torch.sum(F.softmax(pred, dim=1) * idx, dim=1) * 3 - 97.5
+    return pred
+
+
+def get_rotation_matrix(pitch_, yaw_, roll_):
+    """reference src/utils/camera.py:32-73 (degrees in, R = (Rz Ry Rx)^T out)."""
+    import math
+    x, y, z = (a.reshape(-1, 1) / 180 * math.pi for a in (pitch_, yaw_, roll_))
+    bs = x.shape[0]
+    one, zero = torch.ones(bs, 1), torch.zeros(bs, 1)
+    rx = torch.cat([one, zero, zero, zero, torch.cos(x), -torch.sin(x), zero, torch.sin(x), torch.cos(x)], 1).reshape(bs, 3, 3)
+    ry = torch.cat([torch.cos(y), zero, torch.sin(y), zero, one, zero, -torch.sin(y), zero, torch.cos(y)], 1).reshape(bs, 3, 3)
+    rz = torch.cat([torch.cos(z), -torch.sin(z), zero, torch.sin(z), torch.cos(z), zero, zero, zero, one], 1).reshape(bs, 3, 3)
+    return (rz @ ry @ rx).permute(0, 2, 1)
+
+
+def transform_keypoint(kp_info):
+    """can_swapper.transform_keypoint, reference src/can_swap_e2e.py:226-254: s * (kp @ R + exp) + t_xy."""
+    kp = kp_info["kp"]
+    bs = kp.shape[0]
+    pitch = headpose_pred_to_degree(kp_info["pitch"])
+    yaw = headpose_pred_to_degree(kp_info["yaw"])
+    roll = headpose_pred_to_degree(kp_info["roll"])
+    rot = get_rotation_matrix(pitch, yaw, roll)
+    out = kp.reshape(bs, -1, 3) @ rot + kp_info["exp"].reshape(bs, -1, 3)
+    out = out * kp_info["scale"][..., None]
+    out[:, :, 0:2] = out[:, :, 0:2] + kp_info["t"][:, None, 0:2]
+    return out
+
+
+def motion_keypoints(sd, I):
+    """What LOOP C consumes from M per frame (make_motion_template, reference src/can_swap_pipeline_e2e.py:112-125, and
+    :231-243): x_t = transform_keypoint(get_kp_info(I)) and x_can = scale * kp."""
+    info = motion_extractor(sd, I)
+    x_t = transform_keypoint(info)
+    bs = I.shape[0]
+    x_can = info["scale"][..., None] * info["kp"].reshape(bs, -1, 3)
+    deg = torch.stack([headpose_pred_to_degree(info[k]) for k in ("pitch", "yaw", "roll")], 1)
+    return {"info": info, "x_t": x_t, "x_can": x_can, "R": get_rotation_matrix(deg[:, 0], deg[:, 1], deg[:, 2]), "deg": deg}

@@ -63,10 +63,48 @@ def reference_frame(mods, I_s, x_t, x_can, source_id):
     return r
 
 
+def build_reference_motion():
+    """The reference MotionExtractor (src/modules/motion_extractor.py) with models.yaml's parameters."""
+    sys.path.insert(0, REF)
+    from src.modules.motion_extractor import MotionExtractor
+    cfg = yaml.safe_load(open(os.path.join(REF, "src/config/models.yaml")))["model_params"]
+    return MotionExtractor(**cfg["motion_extractor_params"]).eval()
+
+
+def reference_motion(m, I):
+    """get_kp_info + transform_keypoint + x_can with the reference's own functions (can_swap_e2e.py:174-254,
+    camera.py:14-73, pipeline_e2e.py:112-125,242)."""
+    sys.path.insert(0, REF)
+    from src.utils.camera import get_rotation_matrix, headpose_pred_to_degree
+    with torch.no_grad():
+        info = m(I)
+    bs = I.shape[0]
+    pitch, yaw, roll = (headpose_pred_to_degree(info[k]) for k in ("pitch", "yaw", "roll"))
+    rot = get_rotation_matrix(pitch, yaw, roll)
+    x_s = info["kp"].view(bs, 21, 3) @ rot + info["exp"].view(bs, 21, 3)
+    x_s = x_s * info["scale"][..., None]
+    x_s[:, :, 0:2] += info["t"][:, None, 0:2]
+    x_can = info["scale"][..., None] * info["kp"].view(bs, 21, 3)
+    r = dict(info)
+    r.update(x_s=x_s, x_can=x_can, R=rot, deg=torch.stack([pitch, yaw, roll], 1))
+    return r
+
+
 def sample(t, n=4096):
     flat = t.reshape(-1)
     step = max(1, flat.numel() // n)
     return flat[::step][:n].contiguous()
+
+
+def main_motion():
+    """motion extractor: full outputs of the reference module + keypoint transform"""
+    mm = build_reference_motion()
+    mm.load_state_dict(synth.synth_motion_state_dict(), strict=True)
+    for tag, T, hw in (("b2_256", 2, 256), ("b1_128", 1, 128)):
+        inp = synth.synth_inputs(T, hw)
+        r = reference_motion(mm, inp["frames"])
+        np.savez_compressed(os.path.join(HERE, f"motion_{tag}.npz"), **{k: v.numpy().astype(np.float32) for k, v in r.items()})
+        print("motion", tag, {k: float(v.abs().mean()) for k, v in r.items()})
 
 
 def main():
@@ -90,4 +128,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "motion" in sys.argv[1:]:
+        main_motion()
+    else:
+        main()
+        main_motion()
