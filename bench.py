@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--conv-impl", type=int, default=0, help="0 auto (tcgen05 where eligible), 1 force fp32 SIMT convs")
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the CPU baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-motion", action="store_true", help="skip the extra leg that derives the keypoints with the motion extractor")
     ap.add_argument("--lanes", type=int, default=None, help="CS_OPT_LANES: concurrent sub-batches of a graph-replayed step (1 | 2)")
     ap.add_argument("--opt", action="append", default=[], help="experiment: library option id=value (cs_set_option), repeatable")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of a step individually (default: CUDA-graph replay)")
@@ -165,7 +166,7 @@ def main():
     B = args.batch
 
     # ---- synthetic clip, weights, identity --------------------------------------------------------
-    W = synth.synth_weights()
+    W = synth.synth_weights(with_motion=not args.no_motion)
     clip = synth.synth_inputs(CLIP, NET, u8=True)          # frames [T,256,256,3] u8 (as cropped)
     sid = broadcast_identity(clip["source_id"] if rank == 0 else None, device=dev)     # the one collective
     sw = can_swapper(weights=W, device_id=local, max_batch=B, conv_impl=args.conv_impl)
@@ -245,6 +246,26 @@ def main():
         e2e = {"value": world * T / (ems.item() / 1000.0), "unit": "frames/s",
                "h2d_bytes_per_step": pipe.h2d_bytes // args.steps, "d2h_bytes_per_step": pipe.d2h_bytes // args.steps}
 
+    # ---- extra leg: keypoints derived on the device by the motion extractor -------------
+    with_motion = None
+    if not args.no_motion:
+        for i in range(3):
+            eng.frame(frames_d[i % n_batches], out_u8=out_d, motion=True)
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for i in range(args.steps):
+            eng.frame(frames_d[(3 + i) % n_batches], out_u8=out_d, motion=True)
+        m1.record()
+        barrier()
+        mms = torch.tensor([m0.elapsed_time(m1)], device=dev)
+        if world > 1:
+            dist.all_reduce(mms, op=dist.ReduceOp.MAX)
+        with_motion = {"value": world * B * args.steps / (mms.item() / 1000.0), "unit": "frames/s",
+                       "ms_per_step": mms.item() / args.steps,
+                       "note": "same step with x_t / x_can computed from the frames by the motion extractor + "
+                               "transform_keypoint inside cs_frame (CS_FRAME_MOTION) instead of read as inputs"}
+
     # ---- roofline of the dominant kernel family (rank 0, separate profiled pass: events per launch) ------
     roofline = None
     families = None
@@ -297,10 +318,11 @@ def main():
                                    "core path pipeline_e2e.py:242-267 (configs[2])",
                        "frames_per_step_per_gpu": B, "sharding": "frame i -> rank i % N, identity NCCL broadcast",
                        "l2": "per-step working set (activations > 1 GB, weights 0.6 GB) exceeds the 126 MB L2; "
-                             "32 distinct input batches rotate", "conv_impl": args.conv_impl, "cuda_graph": not args.no_graph, "lanes": args.lanes,
+                             "32 distinct input batches rotate", "conv_impl": args.conv_impl, "cuda_graph": not args.no_graph, "lanes": args.lanes or 2,
                        "gflop_per_frame": GFLOP_PER_FRAME},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "families": families, "achieved_tflops_whole_step": value * GFLOP_PER_FRAME / 1000.0,
+            "with_motion_extractor": with_motion,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -84,11 +84,14 @@ class FramePipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def run(self, frames_u8: torch.Tensor, x_t: torch.Tensor, x_can: torch.Tensor, out_u8: torch.Tensor,
+    def run(self, frames_u8: torch.Tensor, x_t: Optional[torch.Tensor], x_can: Optional[torch.Tensor], out_u8: torch.Tensor,
             rank: int = 0, world: int = 1) -> int:
         """frames_u8 [T,H,W,3] u8, x_t/x_can [T,21,3] fp32, out_u8 [T,2H,2W,3] u8 -- all PINNED host tensors.
+        x_t = x_can = None: the keypoints are derived on the device by the motion extractor (no motion template on the
+        host, reference can_swap_pipeline_e2e.py:101-135,225-243).
         Processes frames i % world == rank; returns how many. Synchronises before returning."""
         T = frames_u8.shape[0]
+        motion = x_t is None and x_can is None
         mine = shard_indices(T, rank, world)
         contiguous = world == 1
         k = 0
@@ -101,18 +104,23 @@ class FramePipeline:
                 if contiguous:
                     lo, hi = ids[0], ids[-1] + 1
                     s["frames"][:b].copy_(frames_u8[lo:hi], non_blocking=True)
-                    s["x_t"][:b].copy_(x_t[lo:hi], non_blocking=True)
-                    s["x_can"][:b].copy_(x_can[lo:hi], non_blocking=True)
+                    if not motion:
+                        s["x_t"][:b].copy_(x_t[lo:hi], non_blocking=True)
+                        s["x_can"][:b].copy_(x_can[lo:hi], non_blocking=True)
                 else:
                     for j, i in enumerate(ids):
                         s["frames"][j].copy_(frames_u8[i], non_blocking=True)
-                        s["x_t"][j].copy_(x_t[i], non_blocking=True)
-                        s["x_can"][j].copy_(x_can[i], non_blocking=True)
+                        if not motion:
+                            s["x_t"][j].copy_(x_t[i], non_blocking=True)
+                            s["x_can"][j].copy_(x_can[i], non_blocking=True)
                 s["in_ready"].record(self.copy_in)
-            self.h2d_bytes += b * (frames_u8[0].numel() + 2 * 21 * 3 * 4)
+            self.h2d_bytes += b * (frames_u8[0].numel() + (0 if motion else 2 * 21 * 3 * 4))
             self.compute.wait_event(s["in_ready"])
             self.compute.wait_event(s["drained"])             # previous D2H of this slot's output finished
-            self.sw.swap_frames(s["frames"][:b], s["x_t"][:b], s["x_can"][:b], out_u8=s["out"][:b])
+            if motion:
+                self.sw.swap_frames(s["frames"][:b], out_u8=s["out"][:b])
+            else:
+                self.sw.swap_frames(s["frames"][:b], s["x_t"][:b], s["x_can"][:b], out_u8=s["out"][:b])
             s["done"].record(self.compute)
             with torch.cuda.stream(self.copy_out):
                 self.copy_out.wait_event(s["done"])
