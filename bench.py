@@ -269,6 +269,27 @@ def main():
                        "note": "same step with x_t / x_can computed from the frames by the motion extractor + "
                                "transform_keypoint inside cs_frame (CS_FRAME_MOTION) instead of read as inputs"}
 
+    # ---- extra leg: the loop body AS WRITTEN in the reference, i.e. with its two debug decodes (pipeline_e2e.py:248,257) -------
+    as_written = None
+    if rank == 0 or world > 1:
+        for i in range(2):
+            eng.frame(frames_d[i % n_batches], xt_d[i % n_batches], xc_d[i % n_batches], out_u8=out_d, debug_decodes=True)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        nsteps = max(2, args.steps // 2)
+        for i in range(nsteps):
+            j = (2 + i) % n_batches
+            eng.frame(frames_d[j], xt_d[j], xc_d[j], out_u8=out_d, debug_decodes=True)
+        a1.record()
+        barrier()
+        ams = torch.tensor([a0.elapsed_time(a1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ams, op=dist.ReduceOp.MAX)
+        as_written = {"value": world * B * nsteps / (ams.item() / 1000.0), "unit": "frames/s", "ms_per_step": ams.item() / nsteps,
+                      "gflop_per_frame": 4177.8,
+                      "note": "CS_FRAME_DEBUG_DECODES: the two conv_decode calls of the reference loop run too (results discarded)"}
+
     # ---- roofline of the dominant kernel family (rank 0, separate profiled pass: events per launch) ------
     roofline = None
     families = None
@@ -325,7 +346,7 @@ def main():
                        "gflop_per_frame": GFLOP_PER_FRAME},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "families": families, "achieved_tflops_whole_step": value * GFLOP_PER_FRAME / 1000.0,
-            "with_motion_extractor": with_motion,
+            "with_motion_extractor": with_motion, "as_written": as_written,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -5,9 +5,11 @@ the golden fixtures written by the UNMODIFIED reference module (tests/golden/mak
 /root/reference is present, against the live reference module and its state_dict layout.
 GPU: the CUDA path (cs_motion / cs_keypoints / cs_frame with CS_FRAME_MOTION) against the oracle and the goldens.
 
-Tolerance: the heads feed keypoints in [-1, 1] normalised coordinates and angles in degrees; the bar is the hot path's
-1e-3 max-abs (BASELINE.json), applied to every head relative to max(1, its range), and 1e-3 on the final image when the
-keypoints come from M instead of the caller.
+Tolerance: the heads feed keypoints in [-1, 1] normalised coordinates; measured on B200 they are within 2e-6 (kp) /
+1e-5 (angle logits) of the oracle, the tests ask for 1e-4 * max(1, range) -- ten times tighter than the hot path's 1e-3.
+The generator itself is very sensitive to its keypoints on this fixture (a 1e-5 shift of x_t moves the image by ~1e-2 at
+the mask boundaries, tools/motion_err.py), so the fused call is checked in two parts: keypoints against the oracle, and
+the image against the oracle generator fed the SAME (device-derived) keypoints at the hot path's 1e-3.
 """
 import os
 import sys
@@ -22,6 +24,7 @@ from oracle import canonswap_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-3
+HEAD_TOL = 1e-4
 KEYS = ("pitch", "yaw", "roll", "t", "exp", "scale", "kp")
 
 
@@ -93,7 +96,7 @@ def test_motion_heads_match_oracle_and_golden(eng256, motion_w):
         got = d[k].cpu()
         for name, want in (("oracle", ref[k]), ("golden", g[k])):
             err = (got - want).abs().max().item()
-            assert err <= TOL * max(1.0, want.abs().max().item()), (k, name, err)
+            assert err <= HEAD_TOL * max(1.0, want.abs().max().item()), (k, name, err)
 
 
 @pytest.mark.gpu
@@ -125,26 +128,33 @@ def test_motion_extractor_mirror_module_and_kp_info(synth_w, motion_w):
     assert info["kp"].shape == (2, 21, 3) and info["exp"].shape == (2, 21, 3) and info["pitch"].shape == (2, 1)
     assert (info["pitch"].cpu()[:, 0] - want["deg"][:, 0]).abs().max().item() <= 5e-2      # degrees
     x_s = sw.transform_keypoint(info)
-    assert (x_s.cpu() - want["x_t"]).abs().max().item() <= TOL
+    assert (x_s.cpu() - want["x_t"]).abs().max().item() <= HEAD_TOL
 
 
 @pytest.mark.gpu
 def test_frame_with_motion_matches_oracle(synth_w, motion_w):
-    """cs_frame with CS_FRAME_MOTION: keypoints derived on the device from the frames; image within 1e-3 of the oracle
-    composition motion_keypoints -> frame."""
+    """cs_frame with CS_FRAME_MOTION: keypoints derived on the device from the frames.  Keypoints within 1e-4 of the
+    oracle's; image within 1e-3 of the oracle generator fed the same keypoints; and the fused call gives the same result as
+    cs_motion -> cs_keypoints -> cs_frame (up to the order of the GRN atomics)."""
     from canonswap_b200.engine import Engine
     w = dict(synth_w)
     w[spec.MOTION_NET] = motion_w
     inp = synth.synth_inputs(2, 128)
     mk = O.motion_keypoints(motion_w, inp["frames"])
-    ref = O.frame(synth_w, inp["frames"], mk["x_t"], mk["x_can"], inp["source_id"])["out"]
     eng = Engine(w, net_hw=(128, 128), max_batch=2, device=0)
     try:
         eng.set_identity(inp["source_id"].cuda())
+        kp = eng.keypoints(eng.motion(inp["frames"].cuda()))
+        assert (kp["x_s"].cpu() - mk["x_t"]).abs().max().item() <= HEAD_TOL
+        assert (kp["x_can"].cpu() - mk["x_can"]).abs().max().item() <= HEAD_TOL
+        ref = O.frame(synth_w, inp["frames"], kp["x_s"].cpu(), kp["x_can"].cpu(), inp["source_id"])["out"]
         out = torch.empty(2, 3, 256, 256, device="cuda")
         eng.frame(inp["frames"].cuda(), out_f32=out, motion=True)
         d = (out.cpu() - ref).abs().max().item()
         assert d <= TOL, d
+        o1 = torch.empty_like(out)
+        eng.frame(inp["frames"].cuda(), kp["x_s"], kp["x_can"], out_f32=o1)
+        assert (o1 - out).abs().max().item() <= TOL      # same kernels; GRN sums use fp64 atomics (order may vary)
         # graph replay (two lanes) gives the same bytes as the eager call
         from canonswap_b200 import _lib
         eng.set_option(_lib.CS_OPT_USE_GRAPH, 1)
