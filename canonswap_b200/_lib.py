@@ -24,6 +24,7 @@ CS_OPT_TC_STACKED3 = 7
 CS_OPT_TC_DOUBLE_BUFFER = 8
 CS_OPT_TC_BN_MAX = 9
 CS_OPT_LANES = 10
+CS_OPT_WINOGRAD = 13
 CS_FRAME_MOTION = 8
 MOTION_HEADS = 328
 CS_OPT_TC_CHAIN_MAX = 12

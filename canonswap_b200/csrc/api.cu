@@ -47,6 +47,7 @@ Net make_net(cs_ctx* ctx, void* stream, bool dry) {
   n.L.pair_min_iter = ctx->tc_pair > 1 ? ctx->tc_pair : 16;
   n.L.stacked3 = ctx->tc_stacked3 != 0;
   n.L.double_buffer = ctx->tc_dbuf != 0;
+  n.L.winograd = ctx->winograd != 0;
   n.L.single_chain = ctx->tc_single_chain;
   n.L.prof = dry ? nullptr : &ctx->prof;
   return n;
@@ -185,8 +186,9 @@ void size_workspace(cs_ctx* ctx) {
   {
     Net n = make_net(ctx, nullptr, true);
     // both conv implementations must fit (CS_OPT_CONV_IMPL may be flipped after loading)
-    for (int impl = 0; impl < 2; ++impl) {
-      n.L.conv_impl = impl;
+    for (int impl = 0; impl < 3; ++impl) {                 // SIMT, tcgen05 direct, tcgen05 + Winograd adaptive convs
+      n.L.conv_impl = impl == 0 ? 1 : 0;
+      n.L.winograd = impl == 2;
       A.reset(0); body_appearance(n, fake, fake, B);
       A.reset(0); body_warp(n, fake, fake, fake, fake, fake, fake, B);
       A.reset(0); body_warp_out(n, fake, fake, fake, B);
@@ -204,8 +206,9 @@ void size_workspace(cs_ctx* ctx) {
   {
     Net n = make_net(ctx, nullptr, true);
     A.high = 0;
-    for (int impl = 0; impl < 2; ++impl) {
-      n.L.conv_impl = impl;
+    for (int impl = 0; impl < 3; ++impl) {
+      n.L.conv_impl = impl == 0 ? 1 : 0;
+      n.L.winograd = impl == 2;
       A.reset(0); body_frame(n, fake, fake, fake, fake, reinterpret_cast<uint8_t*>(fake), (B + 1) / 2,
                              CS_FRAME_IN_U8_HWC | CS_FRAME_DEBUG_DECODES | (ctx->M.loaded ? CS_FRAME_MOTION : 0));
     }
@@ -300,6 +303,8 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
     case CS_OPT_TC_CHAIN_MAX:
       if (value < 0 || value > 100000) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_CHAIN_MAX: value must be in [0, 100000]");
       ctx->tc_chain_max = value; return CS_OK;
+    case CS_OPT_WINOGRAD:
+      ctx->winograd = value ? 1 : 0; return CS_OK;
     case CS_OPT_TC_DOUBLE_BUFFER:
       ctx->tc_dbuf = value ? 1 : 0; return CS_OK;
     case CS_OPT_TC_STACKED3:

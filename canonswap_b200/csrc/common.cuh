@@ -234,6 +234,7 @@ struct Launcher {            // everything a kernel launch helper needs
   bool pair = true;          // tcgen05 pair mode (cta_group::2, 2-CTA clusters) for wide N tiles
   int pair_min_iter = 16;    // ... with at least this many K iterations
   int single_chain = 256;    // convs whose whole MMA chain (hi*hi + corrections) is at most this long use ONE accumulator
+  bool winograd = true;      // adaptive convs in Winograd F(2x2,3x3) form (wino.cu)
   bool double_buffer = true; // two TMEM accumulator buffers where they fit (epilogue overlaps the next tile's MMAs)
   float acc_comp = 170.f;     // accumulate-truncation compensation per chained MMA, in units of 1e-10 (0 = off)
   Profiler* prof = nullptr;

@@ -644,7 +644,9 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   // tcgen05 pair mode (cta_group::2): wide N tiles, an even number of M tiles, weights shared by the pair.  The kernel is
   // persistent, so the cluster set-up is paid once per launch and short-K convs profit too (halved B traffic per CTA).
   const int niter = w.taps() * w.nblk;
-  const bool pair = L.pair && k.BN >= 128 && (m_tiles % 2 == 0) && w.zrows == 0 && k.npass == 3 && niter >= L.pair_min_iter && ps == 0;
+  // (depth-dependent weights: the two M tiles of a pair must lie in the same depth slice, i.e. an even number of tiles per slice)
+  const bool pair = L.pair && k.BN >= 128 && (m_tiles % 2 == 0) && (w.zrows == 0 || (k.ntw * k.nth) % 2 == 0) && k.npass == 3 &&
+                    niter >= L.pair_min_iter && ps == 0;
   const int stage_bytes = A_TILE_BYTES + (pair ? k.BN / 2 : k.BN) * 128;
   // thin N tiles (short MMAs: the per-stage issue overhead dominates) run as TWO co-resident CTAs per SM, each with half of the
   // shared memory and of the TMEM columns

@@ -38,6 +38,7 @@ struct AdaptiveConvW {       // reference adaptive_modulate.py:73-193
   float* fc2_w = nullptr; float* fc2_b = nullptr;
   ConvW mask_conv;           // 512 -> 1, sigmoid
   ConvW combined;            // per identity: Cout = 1024 = [W | W * s * demod], bias = [0 | bias_param]
+  ConvW wino;                // per identity: Winograd F(2x2,3x3) transform of `combined` (wino.cu), 16 x 1024 rows, K = 512
   float* style = nullptr;    // [512] per identity
   float* demod = nullptr;    // [512] per identity
 };
@@ -102,7 +103,7 @@ struct cs_ctx {
   int device = 0, max_batch = 1, net_h = 0, net_w = 0, h = 0, w = 0;
   std::string err;
   bool weights_loaded = false, identity_set = false;
-  int conv_impl = 0, use_graph = 0, tc_passes = 3, tc_sets = 0, tc_comp = 170, tc_pair = 1, tc_stacked3 = 1, tc_dbuf = 1, tc_chain_max = 0, tc_single_chain = 256, tc_bn_max = 0;
+  int conv_impl = 0, use_graph = 0, tc_passes = 3, tc_sets = 0, tc_comp = 170, tc_pair = 1, tc_stacked3 = 1, tc_dbuf = 1, winograd = 1, tc_chain_max = 0, tc_single_chain = 256, tc_bn_max = 0;
   int64_t launches = 0;
   std::vector<void*> owned;        // device allocations owned by the ctx
   size_t owned_bytes = 0;
@@ -154,6 +155,12 @@ float weight_prescale(const float* w, size_t n);             // weights.cu
 void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream);
 void pack_conv3s(cs_ctx* ctx, ConvW& w);                     // conv3s_tc.cu
 void pack_conv7(cs_ctx* ctx, ConvW& w);                      // conv7_tc.cu   // derive the split-bf16 B operand from w32 (conv_tc.cu)
+
+// wino.cu : Winograd F(2x2,3x3) form of the adaptive convs
+void pack_wino(cs_ctx* ctx, AdaptiveConvW& a, cudaStream_t stream);
+void wino_in(const Launcher& L, const Act& x, Opd V);
+void wino_out_blend(const Launcher& L, const float* Mt, const float* mask, const float* bias_mod, const float* residual, int relu,
+                    float* y, int B, int H, int W);
 
 // net.cu : stages on the internal (channels-last) layout
 void run_F(Net& n, const float* img_cl, int B, float* vol_out);

@@ -390,7 +390,28 @@ void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks) 
   float* m2 = n.A->f32((size_t)P);
   Act x = vol_as_2d(vol_out, B, h, w);
   Act mk = make_act(m1, B, 1, h, w, 1);
-  if (use_tc(n, W.ad[0].combined, make_act(nullptr, B, 1, h, w, 1024)) && use_tc(n, W.ad[0].mask_conv, mk)) {
+  if (n.L.winograd && n.L.conv_impl != 1 && (W.ad[0].wino.wtc || n.L.dry) && h % 2 == 0 && w % 2 == 0 && (long)(h / 2) * (w / 2) >= 128) {
+    // Winograd F(2x2,3x3) form (wino.cu): input transform -> 16 GEMMs over the channels (depth-dependent weights) ->
+    // output transform fused with the mask blend; the 512 -> 1 mask conv reads the fp32 activation directly
+    float* y1 = n.A->f32((size_t)P * 512);
+    Opd V; V.B = B; V.D = 16; V.H = h / 2; V.W = w / 2; V.nblk = 16;
+    V.p = n.A->bf16((size_t)B * 16 * V.H * V.W * 16 * 64);
+    Act Mt = make_act(n.A->f32((size_t)B * 16 * V.H * V.W * 1024), B, 16, V.H, V.W, 1024);
+    ConvGeom gm; gm.PD = 0; gm.PH = 1; gm.PW = 1; gm.Do = 1; gm.Ho = h; gm.Wo = w;
+    ConvGeom gg; gg.Do = 16; gg.Ho = V.H; gg.Wo = V.W;
+    auto wino_adaptive = [&](const AdaptiveConvW& a, float* in, const float* residual, int relu, float* out, float* mask) {
+      Act xin = vol_as_2d(in, B, h, w);
+      wino_in(n.L, xin, V);
+      conv_tc(n.L, V, a.wino, gg, Epilogue(), Mt);
+      conv_cout1(n.L, xin, a.mask_conv, gm, ACT_SIGMOID, mask);
+      wino_out_blend(n.L, Mt.p, mask, a.bias_param, residual, relu, out, B, h, w);
+    };
+    for (int i = 0; i < 7; ++i) {                                             // ResnetBlock_Adaptive2D :337-349
+      wino_adaptive(W.ad[2 * i], vol_out, nullptr, 1, y1, m1);                // y = relu(conv1(x))
+      wino_adaptive(W.ad[2 * i + 1], y1, vol_out, 0, vol_out, m2);            // x + conv2(y), in place
+      if (masks) avg2(n.L, m1, m2, masks + (long)i * P, P);
+    }
+  } else if (use_tc(n, W.ad[0].combined, make_act(nullptr, B, 1, h, w, 1024)) && use_tc(n, W.ad[0].mask_conv, mk)) {
     Opd oa = conv_tc_alloc_operand(*n.A, W.ad[0].combined, x);
     Opd ob = conv_tc_alloc_operand(*n.A, W.ad[0].combined, x);
     prep_planes(n.L, prep_of(x), oa, nullptr);

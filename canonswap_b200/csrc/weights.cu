@@ -529,6 +529,7 @@ void set_identity(cs_ctx* ctx, const float* id_dev, cudaStream_t stream) {
     check_launch("combine");
     ctx->launches += 4;
     pack_tc(ctx, a.combined, stream);
+    pack_wino(ctx, a, stream);
   }
   ctx->identity_set = true;
 }

@@ -1,0 +1,213 @@
+// Winograd F(2x2, 3x3) form of the adaptive convs of transfer_model2 (reference adaptive_modulate.py:128-193), the largest
+// MMA consumer of the path (28 convs 512 -> 512 per frame, both branches: 24.6 % of the FLOPs).
+//
+//   Y = A^T [ (G g G^T) .* (B^T d B) ] A          (Lavin & Gray; cross-correlation, 2x2 outputs from a 4x4 input patch)
+//
+// The 16 element-wise products are 16 independent GEMMs over the input channels:
+//   M_k[tile, co] = sum_ci V_k[tile, ci] * U_k[ci, co],   k = 0..15,  tile = 2x2 output block
+// i.e. a 1x1x1 "conv" over a tensor whose depth axis is the component k, with depth-dependent weights -- the zrows mode of
+// conv_tc_kernel (one depth per M tile, B rows k * Cout .. of the packed weights).  K = 512 channels = 16 pipeline
+// iterations: one accumulator, double-buffered TMEM, pair mode.  4 MACs per output instead of 9 (2.25x fewer MMAs); the
+// price is the 4x larger fp32 intermediate M (written by the GEMM epilogue, read once by the output transform).
+//
+//   wino_weights   U = G g G^T of the per-identity combined weights [W | W*s*demod], fp32 [ci][k*1024 + co]
+//   wino_in        V = B^T d B of the fp32 activation (zero padding), written as the split-fp16 operand [B,16,H/2,W/2,C]
+//   wino_out_blend Y = A^T M A of both branches + bias, mask blend, ReLU / residual (adaptive_modulate.py:186, :337-349)
+//
+// Numerics (CPU experiment, 512 -> 512 at 64^2, fp32): transforms alone (exact accumulation) 4.8e-7 max / 6e-8 rms, against
+// 1.1e-6 / 1.3e-7 of a direct fp32 conv -- the transforms add and subtract fp32 values, the weights are transformed
+// from the fp32 master before the fp16 split, and the MMA chain per accumulator shrinks from 288 to 96.
+#include "tc_ptx.cuh"
+
+namespace cs {
+
+namespace {
+
+// G (4x3) rows: [1,0,0], [.5,.5,.5], [.5,-.5,.5], [0,0,1]
+__device__ __forceinline__ void g_rows(float a, float b, float c, float* o) {
+  o[0] = a; o[1] = 0.5f * ((a + b) + c); o[2] = 0.5f * ((a - b) + c); o[3] = c;
+}
+
+// w32 [9][Cin][Cout] (tap = kh*3 + kw) -> U [Cin][16 * Cout], column k * Cout + co, k = i*4 + l, scaled by `mul`
+__global__ void __launch_bounds__(256) wino_weights_kernel(const float* __restrict__ w, float* __restrict__ U, int Cin, int Cout,
+                                                           float mul) {
+  const long total = (long)Cin * Cout;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % Cout); const int ci = (int)(idx / Cout);
+    float g[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) g[a][b] = w[((long)(a * 3 + b) * Cin + ci) * Cout + co] * mul;
+    float t[4][3];                       // G g
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      float col[4];
+      g_rows(g[0][b], g[1][b], g[2][b], col);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) t[i][b] = col[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {        // (G g) G^T
+      float row[4];
+      g_rows(t[i][0], t[i][1], t[i][2], row);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) U[(long)ci * (16L * Cout) + (long)(i * 4 + l) * Cout + co] = row[l];
+    }
+  }
+}
+
+// B^T rows: [1,0,-1,0], [0,1,1,0], [0,-1,1,0], [0,1,0,-1]
+__device__ __forceinline__ void bt4(const float4& a, const float4& b, const float4& c, const float4& d, float4* o) {
+  o[0] = make_float4(a.x - c.x, a.y - c.y, a.z - c.z, a.w - c.w);
+  o[1] = make_float4(b.x + c.x, b.y + c.y, b.z + c.z, b.w + c.w);
+  o[2] = make_float4(c.x - b.x, c.y - b.y, c.z - b.z, c.w - b.w);
+  o[3] = make_float4(b.x - d.x, b.y - d.y, b.z - d.z, b.w - d.w);
+}
+
+// x [B,H,W,C] fp32 dense -> V operand [B,16,H/2,W/2,C/32,64]
+__global__ void __launch_bounds__(256) wino_in_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ V, int B, int H, int W,
+                                                      int C) {
+  const int Ht = H >> 1, Wt = W >> 1, C4 = C >> 2;
+  const long total = (long)B * Ht * Wt * C4;
+  const long plane = (long)Ht * Wt * (C >> 5) * 64;               // elements per (b, component)
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C4) * 4; long t = idx / C4;
+    const int tx = (int)(t % Wt); t /= Wt;
+    const int ty = (int)(t % Ht); const int b = (int)(t / Ht);
+    float4 d[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ih = 2 * ty - 1 + r;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int iw = 2 * tx - 1 + q;
+        d[r][q] = (ih >= 0 && ih < H && iw >= 0 && iw < W)
+                      ? *reinterpret_cast<const float4*>(x + (((long)b * H + ih) * W + iw) * C + c)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float4 tm[4][4];                     // B^T d : transform along rows, per column
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 o[4];
+      bt4(d[0][q], d[1][q], d[2][q], d[3][q], o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tm[i][q] = o[i];
+    }
+    __nv_bfloat16* base = V + (long)b * 16 * plane + ((long)ty * Wt + tx) * ((C >> 5) * 64) + (c >> 5) * 64 + (c & 31);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {        // (B^T d) B
+      float4 o[4];
+      bt4(tm[i][0], tm[i][1], tm[i][2], tm[i][3], o);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        uint2 hv, lv;
+        split_operand4(o[l].x, o[l].y, o[l].z, o[l].w, hv, lv);
+        __nv_bfloat16* p = base + (long)(i * 4 + l) * plane;
+        *reinterpret_cast<uint2*>(p) = hv;
+        *reinterpret_cast<uint2*>(p + 32) = lv;
+      }
+    }
+  }
+}
+
+// A^T rows: [1,1,1,0], [0,1,-1,-1]
+__device__ __forceinline__ void at4(const float4& a, const float4& b, const float4& c, const float4& d, float4& o0, float4& o1) {
+  o0 = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
+  o1 = make_float4((b.x - c.x) - d.x, (b.y - c.y) - d.y, (b.z - c.z) - d.z, (b.w - c.w) - d.w);
+}
+
+__device__ __forceinline__ void wino_out4(const float* __restrict__ Mt, long plane, float4 (&y)[2][2]) {
+  float4 s0[4], s1[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const float4 m0 = *reinterpret_cast<const float4*>(Mt + (long)(0 * 4 + l) * plane);
+    const float4 m1 = *reinterpret_cast<const float4*>(Mt + (long)(1 * 4 + l) * plane);
+    const float4 m2 = *reinterpret_cast<const float4*>(Mt + (long)(2 * 4 + l) * plane);
+    const float4 m3 = *reinterpret_cast<const float4*>(Mt + (long)(3 * 4 + l) * plane);
+    at4(m0, m1, m2, m3, s0[l], s1[l]);
+  }
+  at4(s0[0], s0[1], s0[2], s0[3], y[0][0], y[0][1]);
+  at4(s1[0], s1[1], s1[2], s1[3], y[1][0], y[1][1]);
+}
+
+// Mt [B,16,H/2,W/2,1024] = [std 512 | mod 512] -> y [B,H,W,512] = mask * (mod + bias) + (1 - mask) * std (+ReLU / +residual)
+__global__ void __launch_bounds__(256) wino_out_blend_kernel(const float* __restrict__ Mt, const float* __restrict__ mask,
+                                                             const float* __restrict__ bias_mod, const float* residual, int relu,
+                                                             float* y, int B, int H, int W) {
+  const int Ht = H >> 1, Wt = W >> 1;
+  const long total = (long)B * Ht * Wt * 128;
+  const long plane = (long)Ht * Wt * 1024;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx & 127) * 4; long t = idx >> 7;
+    const int tx = (int)(t % Wt); t /= Wt;
+    const int ty = (int)(t % Ht); const int b = (int)(t / Ht);
+    const float* mp = Mt + (long)b * 16 * plane + ((long)ty * Wt + tx) * 1024 + c;
+    float4 ys[2][2], ym[2][2];
+    wino_out4(mp, plane, ys);
+    wino_out4(mp + 512, plane, ym);
+    const float4 bm = __ldg(reinterpret_cast<const float4*>(bias_mod + c));
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const long pix = ((long)b * H + 2 * ty + i) * W + 2 * tx + j;
+        const float m = mask[pix];
+        const float4 s = ys[i][j];
+        const float4 mo = make_float4(ym[i][j].x + bm.x, ym[i][j].y + bm.y, ym[i][j].z + bm.z, ym[i][j].w + bm.w);
+        float4 v;
+        v.x = m * mo.x + (1.f - m) * s.x; v.y = m * mo.y + (1.f - m) * s.y;
+        v.z = m * mo.z + (1.f - m) * s.z; v.w = m * mo.w + (1.f - m) * s.w;
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (residual) {
+          const float4 r = *reinterpret_cast<const float4*>(residual + pix * 512 + c);
+          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        *reinterpret_cast<float4*>(y + pix * 512 + c) = v;
+      }
+  }
+}
+
+}  // namespace
+
+// per identity: U = G g G^T of combined.w32 -> a.wino (a 1x1x1 conv with depth-dependent weights, zrows = 1024)
+void pack_wino(cs_ctx* ctx, AdaptiveConvW& a, cudaStream_t stream) {
+  ConvW& w = a.wino;
+  const int Cin = 512, Cout = 1024;
+  if (!w.w32) w.w32 = static_cast<float*>(ctx->dmalloc((size_t)Cin * 16 * Cout * sizeof(float)));
+  wino_weights_kernel<<<148 * 8, 256, 0, stream>>>(a.combined.w32, w.w32, Cin, Cout, 1.0f);
+  check_launch("wino_weights");
+  w.Cin = Cin; w.Cout = 16 * Cout; w.KD = w.KH = w.KW = 1;
+  w.zrows = 0;
+  w.wmul = a.combined.wmul * 0.25f;                       // |U| <= 2.25 max|g|: a quarter of the direct conv's pre-scale stays inside fp16
+  pack_tc(ctx, w, stream);                               // rows k * 1024 + co, K = 512
+  CS_REQUIRE(w.BN == 256 && w.Cout_p == 16 * Cout, CS_ERR_WEIGHTS, "pack_wino: unexpected N tile");
+  w.Cout = Cout; w.zrows = Cout;
+}
+
+void wino_in(const Launcher& L, const Act& x, Opd V) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(x.D == 1 && x.C % 32 == 0 && x.H % 2 == 0 && x.W % 2 == 0 && x.sw == x.C && x.sh == (long)x.W * x.C &&
+                 x.sb == (long)x.H * x.W * x.C && V.D == 16 && V.H == x.H / 2 && V.W == x.W / 2 && V.nblk == x.C / 32 && V.B == x.B,
+             CS_ERR_INVALID, "wino_in: unsupported geometry");
+  const long total = (long)x.B * (x.H / 2) * (x.W / 2) * (x.C / 4);
+  long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+  ProfScope ps(L, PK_PREP, 0.0, (double)x.pixels() * x.C * 4.0 + (double)x.pixels() * x.C * 4.0 * 4.0, "wino_in");
+  wino_in_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C);
+  check_launch("wino_in");
+}
+
+void wino_out_blend(const Launcher& L, const float* Mt, const float* mask, const float* bias_mod, const float* residual, int relu,
+                    float* y, int B, int H, int W) {
+  L.count();
+  if (L.dry) return;
+  const long total = (long)B * (H / 2) * (W / 2) * 128;
+  long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+  ProfScope ps(L, PK_OTHER, 0.0, (double)B * H * W * (4.0 * 1024 + 512 + (residual ? 512 : 0)) * 4.0, "wino_out_blend");
+  wino_out_blend_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(Mt, mask, bias_mod, residual, relu, y, B, H, W);
+  check_launch("wino_out_blend");
+}
+
+}  // namespace cs

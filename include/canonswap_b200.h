@@ -78,6 +78,7 @@ typedef struct cs_tensor_desc {
 #define CS_OPT_TC_SINGLE_CHAIN 11 /* convs whose whole MMA chain is at most this long accumulate in ONE TMEM set (0 = never) */
 #define CS_OPT_TC_CHAIN_MAX 12   /* longest hi*hi MMA chain per TMEM accumulator set for convs packed AFTER the call: the N tile is halved
                                     until it holds (0 = default 256) */
+#define CS_OPT_WINOGRAD 13       /* 1 (default) = adaptive convs of the swap module in Winograd F(2x2,3x3) form, 0 = direct implicit GEMM */
 #define CS_OPT_LANES 10         /* 1 | 2 (default): a graph-captured cs_frame runs as this many concurrent sub-batches (forked streams) */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */
 
