@@ -122,6 +122,7 @@ __host__ __device__ inline float apply_act(float v, int kind, float slope) {
 }
 
 // packed convolution weights (device)
+struct ConvW;
 struct ConvW {
   int Cin = 0, Cout = 0, KD = 1, KH = 1, KW = 1;
   float* w32 = nullptr;    // [taps][Cin][Cout]   (SIMT path)
@@ -133,6 +134,7 @@ struct ConvW {
   int nblk = 0, Cout_p = 0, BN = 0;
   float wmul = 1.f;                // power of two applied to the packed tcgen05 weights (epilogues multiply by 1 / wmul)
   int zrows = 0;                   // > 0: depth-dependent weights (rows d*zrows .. of wtc belong to depth slice d)
+  ConvW* wn = nullptr;             // Winograd F(2x2,3x3) form of a 3x3 conv (wino.cu): 16 x Cout rows, K = Cin, zrows = Cout
   int taps() const { return KD * KH * KW; }
 };
 

@@ -367,11 +367,15 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
           float v3 = xv[i].w * (1.f + (g.w + bg.w)) + (bt.w + bb.w);
           v0 = apply_act(v0, k.eact, k.eslope); v1 = apply_act(v1, k.eact, k.eslope);
           v2 = apply_act(v2, k.eact, k.eslope); v3 = apply_act(v3, k.eact, k.eslope);
-          uint2 hv, lv;
-          split_operand4(v0, v1, v2, v3, hv, lv);
-          __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (ch >> 5) * 64 + (ch & 31);
-          *reinterpret_cast<uint2*>(ep) = hv;
-          *reinterpret_cast<uint2*>(ep + 32) = lv;
+          if (k.emit) {
+            uint2 hv, lv;
+            split_operand4(v0, v1, v2, v3, hv, lv);
+            __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (ch >> 5) * 64 + (ch & 31);
+            *reinterpret_cast<uint2*>(ep) = hv;
+            *reinterpret_cast<uint2*>(ep + 32) = lv;
+          } else {                                           // fp32 modulated activation [.., sp_C] (input of a Winograd conv)
+            *reinterpret_cast<float4*>(k.y + yoff[i] + ch) = make_float4(v0, v1, v2, v3);
+          }
         }
         __syncwarp();
         continue;
@@ -588,7 +592,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     CS_REQUIRE(ps <= 2 && w.KD == 1 && w.KH == 3 && w.KW == 3 && w.Cout == (w.BN << (2 * ps)) && y.C == w.BN && w.zrows == 0 &&
                    !e.residual && !e.mult && !e.sp_x, CS_ERR_INVALID, "conv_tc: bad phase-mode conv");
   } else {
-    CS_REQUIRE(y.C == w.Cout, CS_ERR_INVALID, "conv_tc: channel mismatch");
+    CS_REQUIRE(y.C == w.Cout || (e.sp_x && !e.emit && y.C == e.sp_C), CS_ERR_INVALID, "conv_tc: channel mismatch");
   }
   CS_REQUIRE(x.nblk == w.nblk, CS_ERR_INVALID, "conv_tc: channel mismatch");
 
@@ -626,8 +630,10 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   k.mult = e.mult;
   k.y = y.p; k.yb = y.sb; k.yd = y.sd; k.yh = y.sh; k.yw = y.sw;
   if (e.sp_x) {
-    CS_REQUIRE(e.emit && !e.residual && !e.mult && y.p == nullptr && w.Cout == 2 * e.sp_C && e.sp_C % 16 == 0 &&
-                   e.emit_nblk * 32 >= e.sp_C && e.sp_C % 32 == 0 && g.Do == 1, CS_ERR_INVALID, "conv_tc: bad SPADE epilogue");
+    // output: the split operand of the consumer conv (e.emit, y.p null) or the fp32 activation itself (y = [.., sp_C])
+    CS_REQUIRE(!e.residual && !e.mult && w.Cout == 2 * e.sp_C && e.sp_C % 32 == 0 && g.Do == 1 &&
+                   ((e.emit && y.p == nullptr && e.emit_nblk * 32 >= e.sp_C) || (!e.emit && y.p != nullptr && y.C == e.sp_C)),
+               CS_ERR_INVALID, "conv_tc: bad SPADE epilogue");
     k.emit = e.emit; k.erow = e.emit_nblk * 64; k.eact = e.emit_act; k.eslope = e.emit_slope;
     k.sp_x = e.sp_x; k.sp_mean = e.sp_mean; k.sp_rstd = e.sp_rstd; k.sp_C = e.sp_C; k.sp_xs = e.sp_xshift;
     k.sp_Hx = e.sp_Hx; k.sp_Wx = e.sp_Wx;
@@ -744,7 +750,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   snprintf(desc, sizeof(desc), "tc M=%ld Cin=%d Cout=%d k=%dx%dx%d BN=%d st=%d sets=%d acc=%d %s%s%s%s%s tiles=%dx%d", M, w.Cin, y.C, w.KD,
            w.KH, w.KW, k.BN, stages, k.nsets, k.nacc, pair ? "pair " : "", k.res ? "res " : "", k.emit ? "emit " : "", k.sp_x ? "spade " : "",
            ps ? "phase " : "", (int)m_tiles, k.n_tiles);
-  ProfScope pscope(L, PK_CONV_TC, 2.0 * (double)M * y.C * w.Cin * w.taps(), 0.0, desc);
+  ProfScope pscope(L, PK_CONV_TC, 2.0 * (double)M * (e.sp_x ? w.Cout : y.C) * w.Cin * w.taps(), 0.0, desc);
   const bool has_res = k.res != nullptr, has_emit = k.emit != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(64 + 128 * egroups); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;

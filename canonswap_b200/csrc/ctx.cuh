@@ -1,6 +1,7 @@
 // Context, packed-weight inventory and per-call helpers of the canonswap_b200 library.
 #pragma once
 #include "common.cuh"
+#include <memory>
 #include "../../include/canonswap_b200.h"
 
 namespace cs {
@@ -110,6 +111,7 @@ struct cs_ctx {
   cs::Arena arena;
   cs::Weights W;
   cs::MotionW M;
+  std::vector<std::unique_ptr<cs::ConvW>> wino_convs;   // Winograd forms of static convs (ConvW::wn)
   double* stats_scratch = nullptr; // [max_batch*512*2] double
   double* stats_scratch2 = nullptr; // the second lane's (CS_OPT_LANES)
   int lanes = 2;                   // CS_OPT_LANES: a graph-captured cs_frame runs as this many concurrent sub-batches
@@ -158,7 +160,12 @@ void pack_conv7(cs_ctx* ctx, ConvW& w);                      // conv7_tc.cu   //
 
 // wino.cu : Winograd F(2x2,3x3) form of the adaptive convs
 void pack_wino(cs_ctx* ctx, AdaptiveConvW& a, cudaStream_t stream);
-void wino_in(const Launcher& L, const Act& x, Opd V);
+void wino_in(const Launcher& L, const Act& x, Opd V, const ConvW* mask_conv, float* mask, const float* pscale = nullptr,
+             const float* pshift = nullptr, int pact = ACT_NONE, float pslope = 0.f);
+void pack_wino_static(cs_ctx* ctx, ConvW& w);
+bool wino_ok(const Launcher& L, const ConvW& w, int H, int W);
+void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const float* pscale, const float* pshift, int pact,
+               float pslope, int act, float slope, const float* residual, Act y);
 void wino_out_blend(const Launcher& L, const float* Mt, const float* mask, const float* bias_mod, const float* residual, int relu,
                     float* y, int B, int H, int W);
 

@@ -102,6 +102,7 @@ static void conv_from_operand(Net& n, const Opd& opd, const ConvW& w, const Conv
   if (o.sp_x) {
     e.sp_x = o.sp_x->p; e.sp_mean = o.sp_mean; e.sp_rstd = o.sp_rstd; e.sp_C = o.sp_x->C; e.sp_xshift = o.sp_xshift;
     e.sp_Hx = o.sp_x->H; e.sp_Wx = o.sp_x->W;
+    e.emit_act = o.emit_act; e.emit_slope = o.emit_slope;      // the activation after the modulation, operand or fp32 output alike
   }
   if (n.L.stacked3 && !o.mult && out.D == 16 && opd.D == 16 && conv3s_supported(w, opd.H, opd.W)) {
     conv3s_tc(n.L, opd, w, e, out);                      // 32 -> 32 3x3x3 volume conv: depth-stacked kernel
@@ -392,18 +393,16 @@ void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks) 
   Act mk = make_act(m1, B, 1, h, w, 1);
   if (n.L.winograd && n.L.conv_impl != 1 && (W.ad[0].wino.wtc || n.L.dry) && h % 2 == 0 && w % 2 == 0 && (long)(h / 2) * (w / 2) >= 128) {
     // Winograd F(2x2,3x3) form (wino.cu): input transform -> 16 GEMMs over the channels (depth-dependent weights) ->
-    // output transform fused with the mask blend; the 512 -> 1 mask conv reads the fp32 activation directly
+    // output transform fused with the mask blend; the 512 -> 1 mask conv is computed by the input transform
     float* y1 = n.A->f32((size_t)P * 512);
     Opd V; V.B = B; V.D = 16; V.H = h / 2; V.W = w / 2; V.nblk = 16;
     V.p = n.A->bf16((size_t)B * 16 * V.H * V.W * 16 * 64);
     Act Mt = make_act(n.A->f32((size_t)B * 16 * V.H * V.W * 1024), B, 16, V.H, V.W, 1024);
-    ConvGeom gm; gm.PD = 0; gm.PH = 1; gm.PW = 1; gm.Do = 1; gm.Ho = h; gm.Wo = w;
     ConvGeom gg; gg.Do = 16; gg.Ho = V.H; gg.Wo = V.W;
     auto wino_adaptive = [&](const AdaptiveConvW& a, float* in, const float* residual, int relu, float* out, float* mask) {
       Act xin = vol_as_2d(in, B, h, w);
-      wino_in(n.L, xin, V);
+      wino_in(n.L, xin, V, &a.mask_conv, mask);              // + the 512 -> 1 mask conv on the same patches
       conv_tc(n.L, V, a.wino, gg, Epilogue(), Mt);
-      conv_cout1(n.L, xin, a.mask_conv, gm, ACT_SIGMOID, mask);
       wino_out_blend(n.L, Mt.p, mask, a.bias_param, residual, relu, out, B, h, w);
     };
     for (int i = 0; i < 7; ++i) {                                             // ResnetBlock_Adaptive2D :337-349
@@ -445,7 +444,17 @@ void run_refine(Net& n, const float* vol_in, int B, float* vol_out) {
   for (int i = 0; i < 3; ++i) gn_resblock3d(n, W.r_gn1[i], vol_out, B, h, w);
   {
     Act x2 = vol_as_2d(vol_out, B, h, w);
-    if (use_tc(n, W.r_res2[0].conv1, x2)) {
+    if (wino_ok(n.L, W.r_res2[0].conv1, h, w) && wino_ok(n.L, W.r_res2[0].conv2, h, w)) {
+      // ResBlock2d (util.py:120-128) in Winograd form: bn1 + lrelu in the input transform, norm2 folded into conv1
+      size_t m = n.A->mark();
+      Act t = new_act(n, B, 1, h, w, 512);
+      for (int i = 0; i < 3; ++i) {
+        const ResBlock2dW& r = W.r_res2[i];
+        wino_conv(n.L, *n.A, x2, r.conv1, r.bn1.scale, r.bn1.shift, ACT_LRELU, 0.01f, ACT_LRELU, 0.01f, nullptr, t);
+        wino_conv(n.L, *n.A, t, r.conv2, nullptr, nullptr, ACT_NONE, 0.f, ACT_NONE, 0.f, x2.p, x2);   // x = conv2(.) + x, in place
+      }
+      n.A->reset(m);
+    } else if (use_tc(n, W.r_res2[0].conv1, x2)) {
       PreActBlock blk[3];
       for (int i = 0; i < 3; ++i) blk[i] = PreActBlock{&W.r_res2[i].bn1, &W.r_res2[i].conv1, &W.r_res2[i].conv2};
       preact_chain_tc(n, blk, 3, x2, ACT_LRELU, 0.01f, false);
@@ -483,11 +492,14 @@ static float* spade_gamma_beta(Net& n, const SpadeNormW& s, const Act& seg, int 
 // intermediates.  mlp_shared runs on the (shared) seg operand and emits relu(.) as the operand of the gamma|beta conv,
 // whose SPADE epilogue reads x and its instance statistics and emits act(x_hat * (1 + gamma) + beta) directly as the
 // consumer conv's operand.
+// out32 != null: the modulated activation is written as fp32 [B,H,W,C] instead (input of a Winograd conv)
 static Opd spade_norm_tc(Net& n, const SpadeNormW& s, const Opd& seg_op, int seg_phase, const Act& x, int xup, const float* mean,
-                         const float* rstd, int act, float slope, const ConvW& consumer, int B, int H, int W) {
+                         const float* rstd, int act, float slope, const ConvW& consumer, int B, int H, int W,
+                         const Act* out32 = nullptr) {
   Act geom128 = make_act(nullptr, B, 1, H, W, 128);
   Act geom2c = make_act(nullptr, B, 1, H, W, 2 * s.C);
-  Opd mod = conv_tc_alloc_operand(*n.A, consumer, geom2c);            // survives this call (caller resets the arena)
+  Opd mod;
+  if (!out32) mod = conv_tc_alloc_operand(*n.A, consumer, geom2c);    // survives this call (caller resets the arena)
   size_t m = n.A->mark();
   Opd actv = conv_tc_alloc_operand(*n.A, s.gamma_beta, geom128);
   ConvOpts o1; o1.act = ACT_RELU; o1.emit = &actv;
@@ -497,9 +509,9 @@ static Opd spade_norm_tc(Net& n, const SpadeNormW& s, const Opd& seg_op, int seg
   } else {
     conv_from_operand(n, seg_op, s.shared, o1, geom128);
   }
-  ConvOpts o2; o2.emit = &mod; o2.emit_act = act; o2.emit_slope = slope;
+  ConvOpts o2; o2.emit = out32 ? nullptr : &mod; o2.emit_act = act; o2.emit_slope = slope;
   o2.sp_x = &x; o2.sp_xshift = xup; o2.sp_mean = mean; o2.sp_rstd = rstd;
-  conv_from_operand(n, actv, s.gamma_beta, o2, geom2c);
+  conv_from_operand(n, actv, s.gamma_beta, o2, out32 ? *out32 : geom2c);
   n.A->reset(m);
   return mod;
 }
@@ -534,17 +546,30 @@ static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, c
   Act dx = new_act(n, B, 1, H, W, b.fmid);
   {
     size_t m2 = n.A->mark();
-    Opd m0 = spade_norm_tc(n, b.norm_0, seg_op, seg_phase, x, xup, mean, rstd, ACT_LRELU, 0.2f, b.conv_0, B, H, W);
-    conv_from_operand(n, m0, b.conv_0, ConvOpts(), dx);
+    if (wino_ok(n.L, b.conv_0, H, W)) {                    // Winograd F(2x2,3x3): the SPADE epilogue writes fp32
+      Act mod = new_act(n, B, 1, H, W, b.fin);
+      spade_norm_tc(n, b.norm_0, seg_op, seg_phase, x, xup, mean, rstd, ACT_LRELU, 0.2f, b.conv_0, B, H, W, &mod);
+      wino_conv(n.L, *n.A, mod, b.conv_0, nullptr, nullptr, ACT_NONE, 0.f, ACT_NONE, 0.f, nullptr, dx);
+    } else {
+      Opd m0 = spade_norm_tc(n, b.norm_0, seg_op, seg_phase, x, xup, mean, rstd, ACT_LRELU, 0.2f, b.conv_0, B, H, W);
+      conv_from_operand(n, m0, b.conv_0, ConvOpts(), dx);
+    }
     n.A->reset(m2);
   }
   {
     float* mean1 = n.A->f32((size_t)B * b.fmid);
     float* rstd1 = n.A->f32((size_t)B * b.fmid);
     instance_stats(n.L, dx, mean1, rstd1, 1e-5f, n.stats);
-    Opd m1 = spade_norm_tc(n, b.norm_1, seg_op, seg_phase, dx, 0, mean1, rstd1, ACT_LRELU, 0.2f, b.conv_1, B, H, W);
-    ConvOpts o; o.residual = &xs;
-    conv_from_operand(n, m1, b.conv_1, o, out);
+    const bool xs_dense = xs.sw == xs.C && xs.sh == (long)xs.W * xs.C && xs.sb == (long)xs.H * xs.W * xs.C && xs.H == H && xs.W == W;
+    if (wino_ok(n.L, b.conv_1, H, W) && xs_dense) {
+      Act mod = new_act(n, B, 1, H, W, b.fmid);
+      spade_norm_tc(n, b.norm_1, seg_op, seg_phase, dx, 0, mean1, rstd1, ACT_LRELU, 0.2f, b.conv_1, B, H, W, &mod);
+      wino_conv(n.L, *n.A, mod, b.conv_1, nullptr, nullptr, ACT_NONE, 0.f, ACT_NONE, 0.f, xs.p, out);
+    } else {
+      Opd m1 = spade_norm_tc(n, b.norm_1, seg_op, seg_phase, dx, 0, mean1, rstd1, ACT_LRELU, 0.2f, b.conv_1, B, H, W);
+      ConvOpts o; o.residual = &xs;
+      conv_from_operand(n, m1, b.conv_1, o, out);
+    }
   }
   n.A->reset(m);
   return out;

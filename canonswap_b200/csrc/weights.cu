@@ -426,6 +426,8 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
     HostConv c2 = read_conv(t, p + ".conv2", 512, 512, 1, 3, 3);
     permute_in_vol(c2); permute_out_vol(c2);
     r.conv2 = pack(ctx, c2);
+    pack_wino_static(ctx, r.conv1);
+    pack_wino_static(ctx, r.conv2);
   }
 
   // ---- G: SPADE decoder (spade_generator.py:13-39) ----
@@ -442,6 +444,8 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
       b.learned_shortcut = b.fin != b.fout;
       b.conv_0 = pack(ctx, read_sn_conv(t, p + ".conv_0", b.fmid, b.fin, 3, true));
       b.conv_1 = pack(ctx, read_sn_conv(t, p + ".conv_1", b.fout, b.fmid, 3, true));
+      pack_wino_static(ctx, b.conv_0);                       // 512 -> 512 / 256, 256 -> 256 (Cout % 256 == 0)
+      pack_wino_static(ctx, b.conv_1);
       const int pshift = i == 6 ? 1 : (i == 7 ? 2 : 0);          // up_0 / up_1 read seg nearest-upsampled x2 / x4 (util.py:297)
       b.norm_0 = read_spade(ctx, t, p + ".norm_0", b.fin, pshift);
       b.norm_1 = read_spade(ctx, t, p + ".norm_1", b.fmid, pshift);

@@ -18,6 +18,7 @@
 // 1.1e-6 / 1.3e-7 of a direct fp32 conv -- the transforms add and subtract fp32 values, the weights are transformed
 // from the fp32 master before the fp16 split, and the MMA chain per accumulator shrinks from 288 to 96.
 #include "tc_ptx.cuh"
+#include <memory>
 
 namespace cs {
 
@@ -65,14 +66,27 @@ __device__ __forceinline__ void bt4(const float4& a, const float4& b, const floa
   o[3] = make_float4(b.x - d.x, b.y - d.y, b.z - d.z, b.w - d.w);
 }
 
-// x [B,H,W,C] fp32 dense -> V operand [B,16,H/2,W/2,C/32,64]
+// x [B,H,W,C] fp32 dense -> V operand [B,16,H/2,W/2,C/32,64].  One block of C/4 threads per 2x2 output tile (thread = 4
+// channels).  MASK: the 3x3 neighbourhoods of the tile's four pixels are exactly the 4x4 patch held in registers, so the
+// 512 -> 1 mask conv of AdaptiveSharedWeightConv2d (adaptive_modulate.py:173-180) is computed here as well: per-thread
+// partial dot products, shuffle + shared-memory reduction over the block (fixed order: deterministic), sigmoid.
+template <bool MASK>
 __global__ void __launch_bounds__(256) wino_in_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ V, int B, int H, int W,
-                                                      int C) {
-  const int Ht = H >> 1, Wt = W >> 1, C4 = C >> 2;
-  const long total = (long)B * Ht * Wt * C4;
+                                                      int C, const float* __restrict__ mw /*[9][C]*/, const float* __restrict__ mb,
+                                                      float* __restrict__ mask /*[B,H,W]*/, const float* __restrict__ pscale,
+                                                      const float* __restrict__ pshift, int pact, float pslope) {
+  __shared__ float red[8][4];
+  const int Ht = H >> 1, Wt = W >> 1;
+  const long tiles = (long)B * Ht * Wt;
   const long plane = (long)Ht * Wt * (C >> 5) * 64;               // elements per (b, component)
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C4) * 4; long t = idx / C4;
+  const int c = threadIdx.x * 4;
+  // optional input transform act(x * scale[c] + shift[c]) (pre-activation BatchNorm of a ResBlock2d): the conv's zero padding
+  // pads the TRANSFORMED tensor, so out-of-bounds elements stay zero
+  float4 psc = make_float4(1.f, 1.f, 1.f, 1.f), psh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pscale) { psc = __ldg(reinterpret_cast<const float4*>(pscale + c)); psh = __ldg(reinterpret_cast<const float4*>(pshift + c)); }
+  const bool pre = pscale != nullptr || pact != ACT_NONE;
+  for (long t0 = blockIdx.x; t0 < tiles; t0 += gridDim.x) {
+    long t = t0;
     const int tx = (int)(t % Wt); t /= Wt;
     const int ty = (int)(t % Ht); const int b = (int)(t / Ht);
     float4 d[4][4];
@@ -82,9 +96,45 @@ __global__ void __launch_bounds__(256) wino_in_kernel(const float* __restrict__ 
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int iw = 2 * tx - 1 + q;
-        d[r][q] = (ih >= 0 && ih < H && iw >= 0 && iw < W)
-                      ? *reinterpret_cast<const float4*>(x + (((long)b * H + ih) * W + iw) * C + c)
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool in = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        d[r][q] = in ? *reinterpret_cast<const float4*>(x + (((long)b * H + ih) * W + iw) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pre && in) {
+          d[r][q].x = apply_act(fmaf(d[r][q].x, psc.x, psh.x), pact, pslope); d[r][q].y = apply_act(fmaf(d[r][q].y, psc.y, psh.y), pact, pslope);
+          d[r][q].z = apply_act(fmaf(d[r][q].z, psc.z, psh.z), pact, pslope); d[r][q].w = apply_act(fmaf(d[r][q].w, psc.w, psh.w), pact, pslope);
+        }
+      }
+    }
+    if constexpr (MASK) {
+      float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(mw + (a * 3 + e) * C + c));
+#pragma unroll
+          for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+            for (int ox = 0; ox < 2; ++ox) {
+              const float4 v = d[oy + a][ox + e];
+              acc[oy][ox] = fmaf(v.x, wv.x, fmaf(v.y, wv.y, fmaf(v.z, wv.z, fmaf(v.w, wv.w, acc[oy][ox]))));
+            }
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        acc[0][0] += __shfl_xor_sync(0xffffffffu, acc[0][0], o); acc[0][1] += __shfl_xor_sync(0xffffffffu, acc[0][1], o);
+        acc[1][0] += __shfl_xor_sync(0xffffffffu, acc[1][0], o); acc[1][1] += __shfl_xor_sync(0xffffffffu, acc[1][1], o);
+      }
+      __syncthreads();                     // the previous tile's readers are done with `red`
+      if ((threadIdx.x & 31) == 0) {
+        float* rr = red[threadIdx.x >> 5];
+        rr[0] = acc[0][0]; rr[1] = acc[0][1]; rr[2] = acc[1][0]; rr[3] = acc[1][1];
+      }
+      __syncthreads();
+      if (threadIdx.x < 4) {
+        float sum = 0.f;
+        for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) sum += red[wq][threadIdx.x];
+        const int oy = threadIdx.x >> 1, ox = threadIdx.x & 1;
+        mask[((long)b * H + 2 * ty + oy) * W + 2 * tx + ox] = 1.f / (1.f + expf(-(sum + mb[0])));
       }
     }
     float4 tm[4][4];                     // B^T d : transform along rows, per column
@@ -169,7 +219,81 @@ __global__ void __launch_bounds__(256) wino_out_blend_kernel(const float* __rest
   }
 }
 
+// generic output transform: Mt [B,16,H/2,W/2,C] -> y [B,H,W,C] = act(Y + bias) (+ residual); y may alias residual
+__global__ void __launch_bounds__(256) wino_out_kernel(const float* __restrict__ Mt, const float* __restrict__ bias, int act, float slope,
+                                                       const float* residual, float* y, int B, int H, int W, int C) {
+  const int Ht = H >> 1, Wt = W >> 1, C4 = C >> 2;
+  const long total = (long)B * Ht * Wt * C4;
+  const long plane = (long)Ht * Wt * C;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C4) * 4; long t = idx / C4;
+    const int tx = (int)(t % Wt); t /= Wt;
+    const int ty = (int)(t % Ht); const int b = (int)(t / Ht);
+    float4 yy[2][2];
+    wino_out4(Mt + (long)b * 16 * plane + ((long)ty * Wt + tx) * C + c, plane, yy);
+    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bz = __ldg(reinterpret_cast<const float4*>(bias + c));
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const long off = (((long)b * H + 2 * ty + i) * W + 2 * tx + j) * C + c;
+        float4 v = make_float4(apply_act(yy[i][j].x + bz.x, act, slope), apply_act(yy[i][j].y + bz.y, act, slope),
+                               apply_act(yy[i][j].z + bz.z, act, slope), apply_act(yy[i][j].w + bz.w, act, slope));
+        if (residual) {
+          const float4 r = *reinterpret_cast<const float4*>(residual + off);
+          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        *reinterpret_cast<float4*>(y + off) = v;
+      }
+  }
+}
+
 }  // namespace
+
+// Winograd form of a static 3x3 conv (weights packed once at load): w.wn, or nothing when the shape does not qualify
+void pack_wino_static(cs_ctx* ctx, ConvW& w) {
+  if (!(w.KD == 1 && w.KH == 3 && w.KW == 3 && w.w32 && w.Cin % 32 == 0 && w.Cin >= 128 && w.Cin <= 1024 && w.Cout % 256 == 0)) return;
+  ConvW* u = new ConvW();
+  ctx->wino_convs.emplace_back(u);
+  u->w32 = static_cast<float*>(ctx->dmalloc((size_t)w.Cin * 16 * w.Cout * sizeof(float)));
+  wino_weights_kernel<<<148 * 8, 256>>>(w.w32, u->w32, w.Cin, w.Cout, 1.0f);
+  check_launch("wino_weights");
+  u->Cin = w.Cin; u->Cout = 16 * w.Cout; u->KD = u->KH = u->KW = 1;
+  u->wmul = w.wmul * 0.25f;
+  pack_tc(ctx, *u, nullptr);
+  CS_REQUIRE(u->BN > 0 && w.Cout % u->BN == 0 && u->Cout_p == 16 * w.Cout, CS_ERR_WEIGHTS, "pack_wino_static: unexpected N tile");
+  u->Cout = w.Cout; u->zrows = w.Cout;
+  u->bias = nullptr;                                     // the bias is added by the output transform
+  w.wn = u;
+}
+
+// y = act(conv3x3(pre(x)) + bias) (+ residual) in Winograd form; x, y, residual dense fp32 [B,1,H,W,C]; V / Mt scratch from `A`
+void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const float* pscale, const float* pshift, int pact,
+               float pslope, int act, float slope, const float* residual, Act y) {
+  CS_REQUIRE(w.wn != nullptr && x.C == w.Cin && y.C == w.Cout && y.H == x.H && y.W == x.W && y.B == x.B && y.sw == y.C &&
+                 y.sh == (long)y.W * y.C && y.sb == (long)y.H * y.W * y.C, CS_ERR_INVALID, "wino_conv: unsupported geometry");
+  const size_t m = A.mark();
+  Opd V; V.B = x.B; V.D = 16; V.H = x.H / 2; V.W = x.W / 2; V.nblk = x.C / 32;
+  V.p = A.bf16((size_t)x.B * 16 * V.H * V.W * V.nblk * 64);
+  Act Mt = make_act(A.f32((size_t)x.B * 16 * V.H * V.W * w.Cout), x.B, 16, V.H, V.W, w.Cout);
+  wino_in(L, x, V, nullptr, nullptr, pscale, pshift, pact, pslope);
+  ConvGeom g; g.Do = 16; g.Ho = V.H; g.Wo = V.W;
+  conv_tc(L, V, *w.wn, g, Epilogue(), Mt);
+  L.count();
+  if (!L.dry) {
+    const long total = (long)x.B * V.H * V.W * (w.Cout / 4);
+    long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+    ProfScope ps(L, PK_OTHER, 0.0, (double)x.pixels() * w.Cout * (4.0 + 1.0 + (residual ? 1.0 : 0.0)) * 4.0, "wino_out");
+    wino_out_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(Mt.p, w.bias, act, slope, residual, y.p, x.B, x.H, x.W, w.Cout);
+    check_launch("wino_out");
+  }
+  A.reset(m);
+}
+
+bool wino_ok(const Launcher& L, const ConvW& w, int H, int W) {
+  return L.winograd && L.conv_impl != 1 && w.wn != nullptr && H % 2 == 0 && W % 2 == 0 && (long)(H / 2) * (W / 2) >= 128;
+}
 
 // per identity: U = G g G^T of combined.w32 -> a.wino (a 1x1x1 conv with depth-dependent weights, zrows = 1024)
 void pack_wino(cs_ctx* ctx, AdaptiveConvW& a, cudaStream_t stream) {
@@ -186,16 +310,27 @@ void pack_wino(cs_ctx* ctx, AdaptiveConvW& a, cudaStream_t stream) {
   w.Cout = Cout; w.zrows = Cout;
 }
 
-void wino_in(const Launcher& L, const Act& x, Opd V) {
+// mask_conv != null: also writes mask[B,H,W] = sigmoid(conv3x3(x; mask_conv) + bias) (w32 layout [9][C][1]);
+// pscale / pshift / pact: optional per-channel affine + activation applied to x before the transform
+void wino_in(const Launcher& L, const Act& x, Opd V, const ConvW* mask_conv, float* mask, const float* pscale, const float* pshift,
+             int pact, float pslope) {
   L.count();
   if (L.dry) return;
-  CS_REQUIRE(x.D == 1 && x.C % 32 == 0 && x.H % 2 == 0 && x.W % 2 == 0 && x.sw == x.C && x.sh == (long)x.W * x.C &&
+  CS_REQUIRE(x.D == 1 && x.C % 32 == 0 && x.C <= 1024 && x.H % 2 == 0 && x.W % 2 == 0 && x.sw == x.C && x.sh == (long)x.W * x.C &&
                  x.sb == (long)x.H * x.W * x.C && V.D == 16 && V.H == x.H / 2 && V.W == x.W / 2 && V.nblk == x.C / 32 && V.B == x.B,
              CS_ERR_INVALID, "wino_in: unsupported geometry");
-  const long total = (long)x.B * (x.H / 2) * (x.W / 2) * (x.C / 4);
-  long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+  const long tiles = (long)x.B * (x.H / 2) * (x.W / 2);
+  long blocks = tiles; if (blocks > 148L * 16) blocks = 148L * 16;
   ProfScope ps(L, PK_PREP, 0.0, (double)x.pixels() * x.C * 4.0 + (double)x.pixels() * x.C * 4.0 * 4.0, "wino_in");
-  wino_in_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C);
+  if (mask_conv) {
+    CS_REQUIRE(mask && mask_conv->w32 && mask_conv->Cin == x.C && mask_conv->Cout == 1 && mask_conv->KD == 1 && mask_conv->KH == 3 &&
+                   mask_conv->KW == 3 && mask_conv->bias, CS_ERR_INVALID, "wino_in: bad mask conv");
+    wino_in_kernel<true><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, mask_conv->w32, mask_conv->bias, mask,
+                                                                     pscale, pshift, pact, pslope);
+  } else {
+    wino_in_kernel<false><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, nullptr, nullptr, nullptr, pscale,
+                                                                      pshift, pact, pslope);
+  }
   check_launch("wino_in");
 }
 
