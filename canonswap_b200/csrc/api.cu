@@ -581,7 +581,7 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
                  int Cout, int KD, int KH, int KW, int PD, int PH, int PW, int act, float slope, int impl, void* stream) {
   CS_API_BEGIN(ctx)
   CS_REQUIRE(x && w && y && B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, CS_ERR_INVALID, "cs_test_conv: bad argument");
-  CS_REQUIRE(KD > 0 && KH > 0 && KW > 0 && impl >= 0 && impl <= 4, CS_ERR_INVALID, "cs_test_conv: bad argument");
+  CS_REQUIRE(KD > 0 && KH > 0 && KW > 0 && impl >= 0 && impl <= 5, CS_ERR_INVALID, "cs_test_conv: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CS_CUDA(cudaStreamSynchronize(st));
   const size_t nw = (size_t)Cout * Cin * KD * KH * KW;
@@ -610,7 +610,18 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
     bool tc = same && conv_tc_supported(cw, ya);
     if (impl == 2) CS_REQUIRE(tc, CS_ERR_INVALID, "cs_test_conv: shape not supported by the tcgen05 conv");
     if (impl == 1) tc = false;
-    if (impl == 4) {
+    if (impl == 5) {
+      // Winograd F(2x2,3x3) form (wino.cu): input transform -> 16 GEMMs on the tcgen05 kernel -> output transform
+      pack_wino_static(ctx, cw);
+      CS_CUDA(cudaDeviceSynchronize());
+      L.winograd = true;
+      CS_REQUIRE(same && D == 1 && wino_ok(L, cw, H, W), CS_ERR_INVALID, "cs_test_conv: shape not supported by the Winograd conv");
+      Arena tmp; tmp.measuring = true;
+      { Launcher dry = L; dry.dry = true; dry.counter = nullptr; dry.prof = nullptr;
+        wino_conv(dry, tmp, xa, cw, nullptr, nullptr, ACT_NONE, 0.f, act, slope, nullptr, ya); }
+      Arena real; real.cap = tmp.high + 4096; real.base = static_cast<char*>(ctx->dmalloc(real.cap));
+      wino_conv(L, real, xa, cw, nullptr, nullptr, ACT_NONE, 0.f, act, slope, nullptr, ya);
+    } else if (impl == 4) {
       // the depth-stacked 32 -> 32 3x3x3 kernel
       pack_conv3s(ctx, cw);
       CS_CUDA(cudaDeviceSynchronize());

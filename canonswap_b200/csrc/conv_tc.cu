@@ -601,7 +601,8 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   int cap = 128;
   int bw = pick_box(x.W, cap, &k.lbw); cap /= bw;
   int bh = pick_box(x.H, cap, &k.lbh); cap /= bh;
-  int bd = pick_box(g.Do, cap, &k.lbd); cap /= bd;
+  int bd = 1; k.lbd = 0;                                   // depth-dependent weights: one depth slice per tile
+  if (w.zrows == 0) { bd = pick_box(g.Do, cap, &k.lbd); cap /= bd; }
   int bb = cap; k.lbb = 0; while ((1 << k.lbb) < bb) ++k.lbb;
   k.ntw = (x.W + bw - 1) / bw; k.nth = (x.H + bh - 1) / bh; k.ntd = (g.Do + bd - 1) / bd;
   const int ntb = (x.B + bb - 1) / bb;

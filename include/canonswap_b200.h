@@ -78,7 +78,8 @@ typedef struct cs_tensor_desc {
 #define CS_OPT_TC_SINGLE_CHAIN 11 /* convs whose whole MMA chain is at most this long accumulate in ONE TMEM set (0 = never) */
 #define CS_OPT_TC_CHAIN_MAX 12   /* longest hi*hi MMA chain per TMEM accumulator set for convs packed AFTER the call: the N tile is halved
                                     until it holds (0 = default 256) */
-#define CS_OPT_WINOGRAD 13       /* 1 (default) = adaptive convs of the swap module in Winograd F(2x2,3x3) form, 0 = direct implicit GEMM */
+#define CS_OPT_WINOGRAD 13       /* 1 (default) = the wide 3x3 2-D convs (adaptive convs of the swap module, SPADE conv_0 / conv_1, refine ResBlock2d) in
+                                    Winograd F(2x2,3x3) form, 0 = direct implicit GEMM */
 #define CS_OPT_LANES 10         /* 1 | 2 (default): a graph-captured cs_frame runs as this many concurrent sub-batches (forked streams) */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */
 
@@ -163,7 +164,7 @@ CS_API int cs_profile_dump(cs_ctx* ctx, char* buf, int cap);
 /* Generic "same"-style convolution on channels-last fp32 through the library's conv kernels.
  * x [B,D,H,W,Cin] -> y [B,Do,Ho,Wo,Cout]; w in PyTorch layout [Cout,Cin,KD,KH,KW] (device), bias
  * [Cout] or NULL. impl: 0 auto, 1 SIMT fp32, 2 tcgen05 split-bf16, 3 tcgen05 depth-stacked 7x7x7 kernel,
- * 4 tcgen05 depth-stacked 32->32 3x3x3 kernel. act: 0 none 1 relu 2 lrelu 3 sigmoid */
+ * 4 tcgen05 depth-stacked 32->32 3x3x3 kernel, 5 Winograd F(2x2,3x3) form of a 3x3 2-D conv (Cin % 32 == 0, Cout % 256 == 0). act: 0 none 1 relu 2 lrelu 3 sigmoid */
 CS_API int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
                  int B, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW,
                  int PD, int PH, int PW, int act, float slope, int impl, void* stream);

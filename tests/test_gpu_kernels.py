@@ -96,6 +96,24 @@ def test_conv7_depth_stacked_matches_torch(eng, case):
     assert (y - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("case", [(1, 32, 32, 128, 256), (2, 64, 64, 512, 512), (1, 16, 32, 256, 256), (1, 24, 40, 128, 256)])
+@pytest.mark.parametrize("act", [0, 2])
+def test_conv_winograd_matches_torch(eng, case, act):
+    """Winograd F(2x2,3x3) form of a 3x3 2-D conv (input transform -> 16 GEMMs with depth-dependent weights on the persistent
+    tcgen05 kernel -> output transform) against fp64 torch, same bar as the direct tcgen05 conv."""
+    B, H, W, Cin, Cout = case
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(B, 1, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 1, 3, 3, device="cuda", generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    y = eng.test_conv(x, w, b, (0, 1, 1), act=act, slope=0.2, impl=5)
+    ref = _ref_conv(x, w, b, (0, 1, 1))
+    if act == 2:
+        ref = F.leaky_relu(ref, 0.2)
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("case", [(1, 16, 8), (2, 24, 40), (2, 32, 32)])
 @pytest.mark.parametrize("act", [0, 2])
 def test_conv3_depth_stacked_matches_torch(eng, case, act):
