@@ -318,7 +318,8 @@ def main():
                         "avg_launch_ms": d["ms"] / max(1, d["launches"]),
                         "algorithmic_flops_per_launch": d["flops"] / max(1, d["launches"]),
                         "note": "achieved = algorithmic fp32-equivalent FLOPs (2*MAC) of all launches of the family / "
-                                "summed CUDA-event durations (conv_tc / conv7_tc / conv3s_tc kernels); the tcgen05 path spends "
+                                "summed CUDA-event durations (conv_tc / conv7_tc / conv3s_tc kernels + the Winograd transform kernels of the convs "
+                                "that run in Winograd form, whose GEMMs are credited with the 3x3 conv's FLOPs); the tcgen05 path spends "
                                 "3 fp16 MMAs per algorithmic MAC (split-fp16 operands for the 1e-3 fp32 parity bar), so its "
                                 "ceiling is 1/3 of the 16-bit peak; traffic = dram bytes per launch from the committed ncu "
                                 "pass (profiles/conv_family_traffic.json)"}

@@ -165,6 +165,8 @@ struct Epilogue {
   // the same source pixel pre-summed (ConvW packed by pack_phase_conv: Cout = 4^phase_shift * BN rows): 2.25 (x2) or
   // 4 (x4) times fewer MACs and no upsampled operand.
   int phase_shift = 0;
+  // measurement only: algorithmic FLOPs of this launch when they differ from the GEMM's (a Winograd GEMM stands for a 3x3 conv)
+  double alg_flops = 0.0;
 };
 
 // conv geometry

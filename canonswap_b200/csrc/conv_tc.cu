@@ -751,7 +751,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   snprintf(desc, sizeof(desc), "tc M=%ld Cin=%d Cout=%d k=%dx%dx%d BN=%d st=%d sets=%d acc=%d %s%s%s%s%s tiles=%dx%d", M, w.Cin, y.C, w.KD,
            w.KH, w.KW, k.BN, stages, k.nsets, k.nacc, pair ? "pair " : "", k.res ? "res " : "", k.emit ? "emit " : "", k.sp_x ? "spade " : "",
            ps ? "phase " : "", (int)m_tiles, k.n_tiles);
-  ProfScope pscope(L, PK_CONV_TC, 2.0 * (double)M * (e.sp_x ? w.Cout : y.C) * w.Cin * w.taps(), 0.0, desc);
+  ProfScope pscope(L, PK_CONV_TC, e.alg_flops > 0.0 ? e.alg_flops : 2.0 * (double)M * (e.sp_x ? w.Cout : y.C) * w.Cin * w.taps(), 0.0, desc);
   const bool has_res = k.res != nullptr, has_emit = k.emit != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(64 + 128 * egroups); cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;

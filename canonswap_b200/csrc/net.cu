@@ -402,7 +402,9 @@ void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks) 
     auto wino_adaptive = [&](const AdaptiveConvW& a, float* in, const float* residual, int relu, float* out, float* mask) {
       Act xin = vol_as_2d(in, B, h, w);
       wino_in(n.L, xin, V, &a.mask_conv, mask);              // + the 512 -> 1 mask conv on the same patches
-      conv_tc(n.L, V, a.wino, gg, Epilogue(), Mt);
+      Epilogue eg;
+      eg.alg_flops = 2.0 * (double)P * 1024 * 512 * 9.0;       // the two 3x3 branches this GEMM stands for
+      conv_tc(n.L, V, a.wino, gg, eg, Mt);
       wino_out_blend(n.L, Mt.p, mask, a.bias_param, residual, relu, out, B, h, w);
     };
     for (int i = 0; i < 7; ++i) {                                             // ResnetBlock_Adaptive2D :337-349

@@ -279,12 +279,14 @@ void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const 
   Act Mt = make_act(A.f32((size_t)x.B * 16 * V.H * V.W * w.Cout), x.B, 16, V.H, V.W, w.Cout);
   wino_in(L, x, V, nullptr, nullptr, pscale, pshift, pact, pslope);
   ConvGeom g; g.Do = 16; g.Ho = V.H; g.Wo = V.W;
-  conv_tc(L, V, *w.wn, g, Epilogue(), Mt);
+  Epilogue eg;
+  eg.alg_flops = 2.0 * (double)x.pixels() * w.Cout * w.Cin * 9.0;   // the 3x3 conv this GEMM stands for
+  conv_tc(L, V, *w.wn, g, eg, Mt);
   L.count();
   if (!L.dry) {
     const long total = (long)x.B * V.H * V.W * (w.Cout / 4);
     long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
-    ProfScope ps(L, PK_OTHER, 0.0, (double)x.pixels() * w.Cout * (4.0 + 1.0 + (residual ? 1.0 : 0.0)) * 4.0, "wino_out");
+    ProfScope ps(L, PK_CONV_TC, 0.0, (double)x.pixels() * w.Cout * (4.0 + 1.0 + (residual ? 1.0 : 0.0)) * 4.0, "wino_out");
     wino_out_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(Mt.p, w.bias, act, slope, residual, y.p, x.B, x.H, x.W, w.Cout);
     check_launch("wino_out");
   }
@@ -321,7 +323,7 @@ void wino_in(const Launcher& L, const Act& x, Opd V, const ConvW* mask_conv, flo
              CS_ERR_INVALID, "wino_in: unsupported geometry");
   const long tiles = (long)x.B * (x.H / 2) * (x.W / 2);
   long blocks = tiles; if (blocks > 148L * 16) blocks = 148L * 16;
-  ProfScope ps(L, PK_PREP, 0.0, (double)x.pixels() * x.C * 4.0 + (double)x.pixels() * x.C * 4.0 * 4.0, "wino_in");
+  ProfScope ps(L, PK_CONV_TC, 0.0, (double)x.pixels() * x.C * 4.0 + (double)x.pixels() * x.C * 4.0 * 4.0, "wino_in");   // part of the conv
   if (mask_conv) {
     CS_REQUIRE(mask && mask_conv->w32 && mask_conv->Cin == x.C && mask_conv->Cout == 1 && mask_conv->KD == 1 && mask_conv->KH == 3 &&
                    mask_conv->KW == 3 && mask_conv->bias, CS_ERR_INVALID, "wino_in: bad mask conv");
@@ -340,7 +342,7 @@ void wino_out_blend(const Launcher& L, const float* Mt, const float* mask, const
   if (L.dry) return;
   const long total = (long)B * (H / 2) * (W / 2) * 128;
   long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
-  ProfScope ps(L, PK_OTHER, 0.0, (double)B * H * W * (4.0 * 1024 + 512 + (residual ? 512 : 0)) * 4.0, "wino_out_blend");
+  ProfScope ps(L, PK_CONV_TC, 0.0, (double)B * H * W * (4.0 * 1024 + 512 + (residual ? 512 : 0)) * 4.0, "wino_out_blend");
   wino_out_blend_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(Mt, mask, bias_mod, residual, relu, y, B, H, W);
   check_launch("wino_out_blend");
 }

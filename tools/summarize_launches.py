@@ -35,9 +35,9 @@ print(f"{len(per)} launches, {tot:.1f} ms summed (cold-cache, serialised)\n")
 print("| kernel | launches | ms | share | dram GB |\n|---|---|---|---|---|")
 for name, (n, ms, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"| {name} | {n} | {ms:.3f} | {100 * ms / tot:.1f}% | {by / 1e9:.2f} |")
-fam = [(n, ms, by) for name, (n, ms, by) in agg.items() if name.startswith(("conv_tc", "conv7_tc", "conv3s_tc"))]
+fam = [(n, ms, by) for name, (n, ms, by) in agg.items() if name.startswith(("conv_tc", "conv7_tc", "conv3s_tc", "wino_"))]
 fn, fms, fby = sum(f[0] for f in fam), sum(f[1] for f in fam), sum(f[2] for f in fam)
-print(f"\nconv family (conv_tc + conv7_tc + conv3s_tc): {fn} launches, {fms:.1f} ms, {fby / 1e9:.1f} GB DRAM traffic = "
+print(f"\nconv family (conv_tc + conv7_tc + conv3s_tc + Winograd transforms): {fn} launches, {fms:.1f} ms, {fby / 1e9:.1f} GB DRAM traffic = "
       f"{fby / fn / 1e6:.1f} MB per launch.")
 if len(sys.argv) > 2:
     json.dump({"dram_bytes_per_launch": fby / fn, "launches": fn, "family_ms": fms, "source": path}, open(sys.argv[2], "w"), indent=1)
