@@ -142,6 +142,33 @@ def test_frame_vs_golden_reference_fixtures(synth_w, tag, T, hw):
         eng.close()
 
 
+@pytest.mark.parametrize("opts", [{13: 0}, {13: 0, 8: 0}, {13: 1, 10: 1}, {1: 1}])
+def test_frame_kernel_variants_vs_oracle(synth_w, opts):
+    """The same frame through the kernel variants that the defaults no longer exercise: direct (non-Winograd) implicit-GEMM
+    convs (CS_OPT_WINOGRAD 13 = 0), without TMEM double buffering (8 = 0), single-lane graph replay (10 = 1), fp32 SIMT convs
+    (CS_OPT_CONV_IMPL 1 = 1) -- each within the 1e-3 bar of the oracle, the swap / refine stages within their stage bars."""
+    from canonswap_b200.engine import Engine
+    from canonswap_b200 import _lib
+    inp = synth.synth_inputs(2, 128)
+    ref = O.frame(synth_w, inp["frames"], inp["x_t"], inp["x_can"], inp["source_id"])
+    eng = Engine(synth_w, net_hw=(128, 128), max_batch=2, device=0, options=opts)
+    try:
+        eng.set_identity(inp["source_id"].cuda())
+        _close(eng.swap(ref["f_can"].cuda()), ref["f_swap"], "f_swap")
+        _close(eng.refine(ref["f_swap"].cuda()), ref["f_refine"], "f_refine")
+        _close(eng.spade(ref["warp_out"].cuda()), ref["out"], "spade")
+        out = torch.empty(2, 3, 256, 256, device="cuda")
+        eng.frame(inp["frames"].cuda(), inp["x_t"].cuda(), inp["x_can"].cuda(), out_f32=out)
+        assert (out.cpu() - ref["out"]).abs().max().item() <= TOL
+        eng.set_option(_lib.CS_OPT_USE_GRAPH, 1)
+        o2 = torch.empty_like(out)
+        for _ in range(3):
+            eng.frame(inp["frames"].cuda(), inp["x_t"].cuda(), inp["x_can"].cuda(), out_f32=o2)
+        assert torch.equal(o2, out)
+    finally:
+        eng.close()
+
+
 def test_cuda_graph_replay_is_bit_identical(case128):
     """CS_OPT_USE_GRAPH: cs_frame replayed from a captured CUDA graph (fixed staging buffers) must reproduce the
     eager result bit for bit, call after call, for changing inputs."""
