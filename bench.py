@@ -118,7 +118,7 @@ def run_reference(args):
     fps = args.steps / dt
     cores = torch.get_num_threads()
     sample = f"{args.steps} steps x 1 frame (B=1, the reference's native loop) of the 512px workload, torch CPU fp32"
-    print(json.dumps({
+    _emit(({
         "impl": "reference", "metric": "face-swap frames/sec @512px", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -129,7 +129,29 @@ def run_reference(args):
     }))
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Library chatter (NCCL's version banner, ...) goes to fd 1: point fd 1 at stderr for the run and keep the real stdout
+    for the ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -162,9 +184,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's version banner goes to stdout at NCCL_DEBUG=VERSION/INFO: keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
 
@@ -334,7 +353,7 @@ def main():
                "sample": f"{args.cpu_frames} frames, B=1 (the reference's native loop), same workload, torch CPU fp32 oracle"}
 
     if rank == 0:
-        print(json.dumps({
+        _emit(({
             "metric": "face-swap frames/sec @512px", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (split-fp16 x3 tcgen05 MMA, fp32 accumulate)" if args.conv_impl == 0 else "f32",
