@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcanonswap_b200.so")
-SOURCES = ["api.cu", "net.cu", "weights.cu", "conv_tc.cu", "conv7_tc.cu", "conv3s_tc.cu", "kernels_conv_simt.cu", "kernels_elem.cu", "kernels_motion.cu", "motion.cu", "wino.cu"]
+SOURCES = ["api.cu", "net.cu", "weights.cu", "conv_tc.cu", "conv7_tc.cu", "conv3s_tc.cu", "kernels_conv_simt.cu", "kernels_elem.cu", "kernels_motion.cu", "motion.cu", "wino.cu", "pasteback.cu"]
 HEADERS = ["common.cuh", "ctx.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "canonswap_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

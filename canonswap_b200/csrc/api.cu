@@ -533,6 +533,17 @@ int cs_keypoints(cs_ctx* ctx, const float* heads, float* x_s, float* x_can, floa
   CS_API_END(ctx)
 }
 
+int cs_paste_back(cs_ctx* ctx, const uint8_t* img_crop, const float* mask_crop, const double* M_c2o, const uint8_t* img_ori,
+                  uint8_t* out, int B, int hc, int wc, int H, int W, void* stream) {
+  CS_API_BEGIN(ctx)
+  CS_REQUIRE(img_crop && mask_crop && M_c2o && img_ori && out, CS_ERR_INVALID, "cs_paste_back: null argument");
+  CS_REQUIRE(hc >= 1 && wc >= 1 && H >= 1 && W >= 1 && hc <= 16384 && wc <= 16384 && H <= 16384 && W <= 16384, CS_ERR_INVALID,
+             "cs_paste_back: image size outside [1, 16384]");
+  Net n = make_net(ctx, stream, false);
+  paste_back(n.L, img_crop, mask_crop, M_c2o, img_ori, out, B, hc, wc, H, W);
+  CS_API_END(ctx)
+}
+
 // ---- per-kernel-family timing (bench.py roofline leg) ---------------------------------------------
 int cs_profile(cs_ctx* ctx, int enable) {
   CS_API_BEGIN(ctx)

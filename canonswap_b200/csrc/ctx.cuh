@@ -169,6 +169,10 @@ void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const 
 void wino_out_blend(const Launcher& L, const float* Mt, const float* mask, const float* bias_mod, const float* residual, int relu,
                     float* y, int B, int H, int W);
 
+// pasteback.cu
+void paste_back(const Launcher& L, const uint8_t* crop, const float* mask, const double* M_c2o, const uint8_t* ori, uint8_t* out, int B,
+                int hc, int wc, int H, int W);
+
 // net.cu : stages on the internal (channels-last) layout
 void run_F(Net& n, const float* img_cl, int B, float* vol_out);
 void run_warp(Net& n, const float* vol_in, const float* kp_source, const float* kp_driving, int B,

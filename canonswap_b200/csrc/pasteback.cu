@@ -1,0 +1,113 @@
+// Paste-back of the swapped crop into the full frame, the step that follows the generator:
+//   prepare_paste_back(mask_crop, M_c2o, dsize, if_float=True)    reference src/utils/crop.py:515-521
+//   paste_back(img_crop, M_c2o, img_ori, mask_ori)                reference src/utils/crop.py:523-529
+//   both through cv2.warpAffine(.., flags=cv2.INTER_LINEAR)       reference src/utils/crop.py:49-63
+// The reference runs two full-frame cv2.warpAffine calls and a float blend on the CPU per frame; here it is ONE kernel, one
+// thread per destination pixel, no full-frame intermediates: the 10-bit fixed-point source coordinate of OpenCV
+// (AB_BITS = 10, INTER_BITS = 5, round_delta = 16, doubles rounded half-to-even), the uint8 bilinear sample with the integer
+// weights 32 * p * q and (sum + 2^14) >> 15, the float32 bilinear sample of the mask ((S00*w0 + S01*w1) + S10*w2) + S11*w3,
+// and clip(mask*result + (1-mask)*img_ori, 0, 255) truncated to uint8 -- every operation written with explicit
+// round-to-nearest intrinsics so that no FMA contraction can change a bit.  Bit-exact against the numpy oracle, which is
+// pinned bit for bit against cv2 / the reference functions (oracle/pasteback_oracle.py, tests/test_pasteback.py).
+#include "ctx.cuh"
+
+namespace cs {
+
+namespace {
+
+struct PasteK {
+  const uint8_t* crop;     // [B,hc,wc,3]
+  const float* mask;       // [B,hc,wc]   (the reference stacks it to 3 equal channels)
+  const uint8_t* ori;      // [B,H,W,3]
+  uint8_t* out;            // [B,H,W,3]
+  int B, hc, wc, H, W;
+  double iM[CS_PASTE_MAX_BATCH][6];   // inverted 2x3 matrices (host, double, cv::warpAffine's formulas)
+};
+
+__device__ __forceinline__ long long cv_round(double v) { return __double2ll_rn(v); }
+
+__global__ void __launch_bounds__(256) paste_back_kernel(const __grid_constant__ PasteK k) {
+  const long total = (long)k.B * k.H * k.W;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % k.W); long t = idx / k.W;
+    const int y = (int)(t % k.H); const int b = (int)(t / k.H);
+    const double* m = k.iM[b];
+    // adelta[x] = round(M00 * x * 1024), X0 = round((M01 * y + M02) * 1024) + 16   (no contraction: __dmul_rn / __dadd_rn)
+    const long long ad = cv_round(__dmul_rn(__dmul_rn(m[0], (double)x), 1024.0));
+    const long long bd = cv_round(__dmul_rn(__dmul_rn(m[3], (double)x), 1024.0));
+    const long long X0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(m[1], (double)y), m[2]), 1024.0)) + 16;
+    const long long Y0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(m[4], (double)y), m[5]), 1024.0)) + 16;
+    const long long X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
+    const long long sx = X >> 5, sy = Y >> 5;
+    const int fx = (int)(X & 31), fy = (int)(Y & 31);
+    const uint8_t* o = k.ori + idx * 3;
+    uint8_t* dst = k.out + idx * 3;
+    if (sx < -1 || sx >= k.wc || sy < -1 || sy >= k.hc) {      // all four taps outside: result = 0, mask = 0 -> the frame itself
+      dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];              // (1 - 0) * img_ori is exact
+      continue;
+    }
+    bool ok[4];
+    long off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long yy = sy + (j >> 1), xx = sx + (j & 1);
+      ok[j] = yy >= 0 && yy < k.hc && xx >= 0 && xx < k.wc;
+      off[j] = ok[j] ? ((long)b * k.hc + yy) * k.wc + xx : 0;
+    }
+    // float32 mask sample
+    const float a = __fmul_rn((float)fx, 1.0f / 32.0f), bb = __fmul_rn((float)fy, 1.0f / 32.0f);
+    const float ia = __fsub_rn(1.f, a), ib = __fsub_rn(1.f, bb);
+    const float w0 = __fmul_rn(ib, ia), w1 = __fmul_rn(ib, a), w2 = __fmul_rn(bb, ia), w3 = __fmul_rn(bb, a);
+    const float s0 = ok[0] ? k.mask[off[0]] : 0.f, s1 = ok[1] ? k.mask[off[1]] : 0.f;
+    const float s2 = ok[2] ? k.mask[off[2]] : 0.f, s3 = ok[3] ? k.mask[off[3]] : 0.f;
+    float mk = __fmul_rn(s0, w0);
+    mk = __fadd_rn(mk, __fmul_rn(s1, w1));
+    mk = __fadd_rn(mk, __fmul_rn(s2, w2));
+    mk = __fadd_rn(mk, __fmul_rn(s3, w3));
+    const float im = __fsub_rn(1.f, mk);
+    // uint8 image sample: integer weights 32 * p * q, (sum + 2^14) >> 15
+    const int iw0 = 32 * (32 - fy) * (32 - fx), iw1 = 32 * (32 - fy) * fx, iw2 = 32 * fy * (32 - fx), iw3 = 32 * fy * fx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int acc = 1 << 14;
+      if (ok[0]) acc += iw0 * k.crop[off[0] * 3 + c];
+      if (ok[1]) acc += iw1 * k.crop[off[1] * 3 + c];
+      if (ok[2]) acc += iw2 * k.crop[off[2] * 3 + c];
+      if (ok[3]) acc += iw3 * k.crop[off[3] * 3 + c];
+      int res = acc >> 15;
+      res = res > 255 ? 255 : res;
+      float v = __fadd_rn(__fmul_rn(mk, (float)res), __fmul_rn(im, (float)o[c]));
+      v = fminf(fmaxf(v, 0.f), 255.f);
+      dst[c] = (uint8_t)v;                                  // astype(uint8): truncation
+    }
+  }
+}
+
+}  // namespace
+
+// M_c2o: [B][6] doubles, row-major 2x3 (the reference's float32 3x3 M_c2o[:2, :] widened to double, as cv2 does)
+void paste_back(const Launcher& L, const uint8_t* crop, const float* mask, const double* M_c2o, const uint8_t* ori, uint8_t* out, int B,
+                int hc, int wc, int H, int W) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(B >= 1 && B <= CS_PASTE_MAX_BATCH, CS_ERR_INVALID, "paste_back: batch outside [1, CS_PASTE_MAX_BATCH]");
+  PasteK k{};
+  k.crop = crop; k.mask = mask; k.ori = ori; k.out = out; k.B = B; k.hc = hc; k.wc = wc; k.H = H; k.W = W;
+  for (int b = 0; b < B; ++b) {
+    const double* M = M_c2o + 6 * b;                        // cv::warpAffine: invert unless WARP_INVERSE_MAP
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = M[4] * D, A22 = M[0] * D;
+    double* q = k.iM[b];
+    q[0] = A11; q[1] = M[1] * (-D); q[3] = M[3] * (-D); q[4] = A22;
+    q[2] = -q[0] * M[2] - q[1] * M[5];
+    q[5] = -q[3] * M[2] - q[4] * M[5];
+  }
+  const long total = (long)B * H * W;
+  long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
+  ProfScope ps(L, PK_OTHER, 0.0, (double)total * 6.0 + (double)B * hc * wc * 7.0, "paste_back");
+  paste_back_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+  check_launch("paste_back");
+}
+
+}  // namespace cs

@@ -267,6 +267,27 @@ class Engine:
                                            self._stream()))
         return {"x_s": x_s, "x_can": x_can, "R": R, "deg": deg}
 
+    # ---- paste-back ---------------------------------------------------
+    def paste_back(self, img_crop: torch.Tensor, mask_crop: torch.Tensor, M_c2o, img_ori: torch.Tensor, out: Optional[torch.Tensor] = None):
+        """prepare_paste_back(if_float=True) + paste_back (reference src/utils/crop.py:515-529), fused and bit-exact with the
+        reference's cv2.warpAffine arithmetic.  img_crop [B,hc,wc,3] u8, mask_crop [B,hc,wc] f32, img_ori [B,H,W,3] u8 on the
+        device; M_c2o: [B,2..3,3] array-like on the HOST (the reference's float32 crop->original matrices)."""
+        import numpy as np
+        B, hc, wc = int(img_crop.shape[0]), int(img_crop.shape[1]), int(img_crop.shape[2])
+        H, W = int(img_ori.shape[1]), int(img_ori.shape[2])
+        if B > _lib.PASTE_MAX_BATCH:
+            raise ValueError(f"paste_back: at most {_lib.PASTE_MAX_BATCH} frames per call")
+        crop = self._in(img_crop, (B, hc, wc, 3), dtype=torch.uint8, name="img_crop")
+        mask = self._in(mask_crop, (B, hc, wc), name="mask_crop")
+        ori = self._in(img_ori, (B, H, W, 3), dtype=torch.uint8, name="img_ori")
+        M = np.ascontiguousarray(np.asarray(M_c2o, dtype=np.float64).reshape(B, -1, 3)[:, :2, :]).reshape(B, 6)
+        if out is None:
+            out = self._new(B, H, W, 3, dtype=torch.uint8)
+        out = self._in(out, (B, H, W, 3), dtype=torch.uint8, name="out")
+        self._check(self._lib.cs_paste_back(self._ctx, crop.data_ptr(), mask.data_ptr(), M.ctypes.data_as(C.POINTER(C.c_double)),
+                                            ori.data_ptr(), out.data_ptr(), B, hc, wc, H, W, self._stream()))
+        return out
+
     # ---- measurement -------------------------------------------------------------------------------
     PROFILE_FAMILIES = ("conv_tcgen05", "conv_simt", "prep", "stats", "sampling", "other")
 

@@ -150,6 +150,16 @@ CS_API int cs_motion(cs_ctx* ctx, const float* img, float* heads, int B, void* s
  * R [B,3,3], deg [B,3] = pitch, yaw, roll in degrees (get_kp_info, src/can_swap_e2e.py:191-197). */
 CS_API int cs_keypoints(cs_ctx* ctx, const float* heads, float* x_s, float* x_can, float* R, float* deg, int B, void* stream);
 
+/* ---- paste-back of the swapped crop into the full frame ------- */
+#define CS_PASTE_MAX_BATCH 16
+/* prepare_paste_back(mask, M_c2o, dsize, if_float=True) + paste_back(img_crop, M_c2o, img_ori, mask_ori), reference
+ * src/utils/crop.py:515-529 (two cv2.warpAffine INTER_LINEAR + float blend per frame, src/can_swap_pipeline_e2e.py:277-282),
+ * fused, bit-exact with OpenCV's fixed-point arithmetic.  img_crop [B,hc,wc,3] u8, mask_crop [B,hc,wc] f32 (the soft mask; the
+ * reference stacks it to 3 equal channels), M_c2o HOST pointer [B][6] doubles (rows 0..1 of the crop->original matrix),
+ * img_ori / out [B,H,W,3] u8 (out may alias img_ori).  Needs no weights. */
+CS_API int cs_paste_back(cs_ctx* ctx, const uint8_t* img_crop, const float* mask_crop, const double* M_c2o, const uint8_t* img_ori,
+                         uint8_t* out, int B, int hc, int wc, int H, int W, void* stream);
+
 /* ---- per-kernel-family timing (measurement only) -------------------------------------------- */
 /* enable != 0: bracket every kernel launch of this ctx with CUDA events on the launching stream. */
 CS_API int cs_profile(cs_ctx* ctx, int enable);

@@ -107,6 +107,32 @@ def main_motion():
         print("motion", tag, {k: float(v.abs().mean()) for k, v in r.items()})
 
 
+def pasteback_case(seed, hc=96, wc=96, H=160, W=200):
+    """Seeded inputs of one paste-back frame: crop image, soft mask, crop->original matrix (float32 3x3), full frame."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (hc, wc, 3), dtype=np.uint8)
+    ori = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:hc, 0:wc].astype(np.float32)
+    mask = np.clip(1.4 - np.sqrt(((yy - hc / 2) / (0.4 * hc)) ** 2 + ((xx - wc / 2) / (0.35 * wc)) ** 2), 0, 1).astype(np.float32)
+    ang, sc = rng.uniform(-0.6, 0.6), rng.uniform(0.5, 1.8)
+    M = np.array([[sc * np.cos(ang), -sc * np.sin(ang), rng.uniform(-30, 90)],
+                  [sc * np.sin(ang), sc * np.cos(ang), rng.uniform(-30, 60)], [0, 0, 1]], dtype=np.float32)
+    return img, mask, M, ori
+
+
+def main_pasteback():
+    """paste-back: the reference's own prepare_paste_back / paste_back (src/utils/crop.py:515-529)"""
+    sys.path.insert(0, REF)
+    from src.utils.crop import prepare_paste_back, paste_back
+    for seed in (0, 1, 2):
+        img, mask, M, ori = pasteback_case(seed)
+        m3 = np.stack([mask] * 3, axis=-1)
+        mask_ori = prepare_paste_back(m3, M, dsize=(ori.shape[1], ori.shape[0]), if_float=True)
+        out = paste_back(img, M, ori, mask_ori)
+        np.savez_compressed(os.path.join(HERE, f"pasteback_{seed}.npz"), out=out, mask_ori=mask_ori[..., 0].astype(np.float32))
+        print("pasteback", seed, out.shape, float(mask_ori.mean()))
+
+
 def main():
     mods = build_reference_modules()
     W = synth.synth_weights()
@@ -128,8 +154,11 @@ def main():
 
 
 if __name__ == "__main__":
-    if "motion" in sys.argv[1:]:
+    if "pasteback" in sys.argv[1:]:
+        main_pasteback()
+    elif "motion" in sys.argv[1:]:
         main_motion()
     else:
         main()
         main_motion()
+        main_pasteback()

@@ -1,0 +1,133 @@
+"""Paste-back of the swapped crop into the full frame: reference src/utils/crop.py:515-529,
+cv2.warpAffine INTER_LINEAR (src/utils/crop.py:49-63), called per frame at src/can_swap_pipeline_e2e.py:277-282.
+
+Byte work: the bar is BIT-EXACT.
+CPU: the numpy oracle (oracle/pasteback_oracle.py) against cv2 itself (present in this image), against the golden outputs of
+the reference's own functions (tests/golden/pasteback_*.npz, make_golden.py pasteback) and, when /root/reference is
+present, against those functions live.  GPU: the fused CUDA kernel (cs_paste_back) against the oracle, bit for bit, over
+random similarity transforms, crops hanging over the frame edge, identity / degenerate matrices and a 1080p frame.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import has_reference
+from oracle import pasteback_oracle as P
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+sys.path.insert(0, GOLDEN)
+from make_golden import pasteback_case  # noqa: E402
+
+
+def _rand_case(seed, hc, wc, H, W, kind="similarity"):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (hc, wc, 3), dtype=np.uint8)
+    ori = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    mask = rng.random((hc, wc), dtype=np.float32)
+    mask[mask > 0.7] = 1.0
+    mask[mask < 0.1] = 0.0
+    if kind == "identity":
+        M = np.eye(3, dtype=np.float32)
+    elif kind == "offscreen":
+        M = np.array([[1.0, 0, W + 50], [0, 1.0, 10], [0, 0, 1]], dtype=np.float32)
+    elif kind == "singular":
+        M = np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 1.0], [0, 0, 1]], dtype=np.float32)
+    elif kind == "edge":
+        M = np.array([[1.3, 0.2, -0.4 * wc], [-0.15, 1.25, H - 0.5 * hc], [0, 0, 1]], dtype=np.float32)
+    else:
+        ang, sc = rng.uniform(-3.1, 3.1), rng.uniform(0.3, 2.5)
+        M = np.array([[sc * np.cos(ang), -sc * np.sin(ang), rng.uniform(-0.3 * W, 0.9 * W)],
+                      [sc * np.sin(ang), sc * np.cos(ang), rng.uniform(-0.3 * H, 0.9 * H)], [0, 0, 1]], dtype=np.float32)
+    return img, mask, M, ori
+
+
+def test_oracle_warp_is_bit_exact_with_cv2():
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(0)
+    for seed in range(6):
+        img, mask, M, ori = _rand_case(seed, 64, 80, 120, 150)
+        dsize = (ori.shape[1], ori.shape[0])
+        assert np.array_equal(P.warp_affine_u8(img, M, dsize), cv2.warpAffine(img, M[:2, :], dsize, flags=cv2.INTER_LINEAR))
+        m3 = np.stack([mask] * 3, -1)
+        assert np.array_equal(P.warp_affine_f32(m3, M, dsize), cv2.warpAffine(m3, M[:2, :], dsize, flags=cv2.INTER_LINEAR))
+    for kind in ("identity", "offscreen", "edge"):
+        img, mask, M, ori = _rand_case(9, 48, 40, 90, 70, kind)
+        dsize = (70, 90)
+        assert np.array_equal(P.warp_affine_u8(img, M, dsize), cv2.warpAffine(img, M[:2, :], dsize, flags=cv2.INTER_LINEAR)), kind
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_matches_reference_golden(seed):
+    g = np.load(os.path.join(GOLDEN, f"pasteback_{seed}.npz"))
+    img, mask, M, ori = pasteback_case(seed)
+    m3 = np.stack([mask] * 3, -1)
+    mask_ori = P.prepare_paste_back(m3, M, (ori.shape[1], ori.shape[0]), if_float=True)
+    assert np.array_equal(mask_ori[..., 0], g["mask_ori"])
+    assert np.array_equal(P.paste_back(img, M, ori, mask_ori), g["out"])
+    assert np.array_equal(P.paste_back_frame(img, mask, M, ori), g["out"])
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not has_reference(), reason="/root/reference not present")
+def test_oracle_matches_live_reference_functions():
+    sys.path.insert(0, "/root/reference")
+    from src.utils.crop import prepare_paste_back, paste_back
+    for seed in range(4):
+        img, mask, M, ori = _rand_case(100 + seed, 96, 96, 180, 240)
+        m3 = np.stack([mask] * 3, -1)
+        mo = prepare_paste_back(m3, M, dsize=(ori.shape[1], ori.shape[0]), if_float=True)
+        assert np.array_equal(P.paste_back_frame(img, mask, M, ori), paste_back(img, M, ori, mo))
+
+
+# ---- GPU -----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def eng():
+    from canonswap_b200.engine import Engine
+    e = Engine(None, net_hw=(128, 128), max_batch=1, device=0)
+    yield e
+    e.close()
+
+
+def _gpu(eng, cases):
+    crop = torch.from_numpy(np.stack([c[0] for c in cases])).cuda()
+    mask = torch.from_numpy(np.stack([c[1] for c in cases])).cuda()
+    ori = torch.from_numpy(np.stack([c[3] for c in cases])).cuda()
+    M = np.stack([c[2] for c in cases])
+    return eng.paste_back(crop, mask, M, ori).cpu().numpy()
+
+
+@pytest.mark.gpu
+def test_paste_back_kernel_is_bit_exact_with_oracle(eng):
+    cases = [_rand_case(s, 96, 112, 200, 260) for s in range(8)]
+    out = _gpu(eng, cases)
+    for i, c in enumerate(cases):
+        assert np.array_equal(out[i], P.paste_back_frame(*c)), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["identity", "offscreen", "edge", "singular"])
+def test_paste_back_kernel_edge_cases(eng, kind):
+    c = _rand_case(5, 64, 48, 100, 140, kind)
+    assert np.array_equal(_gpu(eng, [c])[0], P.paste_back_frame(*c))
+
+
+@pytest.mark.gpu
+def test_paste_back_kernel_matches_reference_golden(eng):
+    for seed in (0, 1, 2):
+        g = np.load(os.path.join(GOLDEN, f"pasteback_{seed}.npz"))
+        assert np.array_equal(_gpu(eng, [pasteback_case(seed)])[0], g["out"])
+
+
+@pytest.mark.gpu
+def test_paste_back_1080p_frame_and_in_place(eng):
+    """The reference's operating point: a 512x512 crop pasted into a 1920x1080 frame; `out` may alias `img_ori`."""
+    c = _rand_case(42, 512, 512, 1080, 1920)
+    want = P.paste_back_frame(*c)
+    assert np.array_equal(_gpu(eng, [c])[0], want)
+    crop, mask = torch.from_numpy(c[0][None]).cuda(), torch.from_numpy(c[1][None]).cuda()
+    ori = torch.from_numpy(c[3][None]).cuda()
+    eng.paste_back(crop, mask, c[2][None], ori, out=ori)
+    assert np.array_equal(ori.cpu().numpy()[0], want)
