@@ -544,6 +544,21 @@ int cs_paste_back(cs_ctx* ctx, const uint8_t* img_crop, const float* mask_crop, 
   CS_API_END(ctx)
 }
 
+int cs_soft_erosion(cs_ctx* ctx, const float* mask, const float* kernel, float* out, uint8_t* hard, int B, int H, int W, int kernel_size,
+                    float threshold, int iterations, void* stream) {
+  CS_API_BEGIN(ctx)
+  CS_REQUIRE(mask && kernel && out && B >= 1 && H >= 1 && W >= 1 && B <= 65535, CS_ERR_INVALID, "cs_soft_erosion: bad argument");
+  const size_t need = ((size_t)2 * B * H * W + B + 64) * sizeof(float);
+  if (need > ctx->se_cap) {                                  // not on the per-frame path of the generator: grown on demand
+    CS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    ctx->se_scratch = static_cast<float*>(ctx->dmalloc(need));
+    ctx->se_cap = need;
+  }
+  Net n = make_net(ctx, stream, false);
+  soft_erosion(n.L, mask, out, hard, ctx->se_scratch, kernel, B, H, W, kernel_size, threshold, iterations);
+  CS_API_END(ctx)
+}
+
 // ---- per-kernel-family timing (bench.py roofline leg) ---------------------------------------------
 int cs_profile(cs_ctx* ctx, int enable) {
   CS_API_BEGIN(ctx)

@@ -111,6 +111,7 @@ struct cs_ctx {
   cs::Arena arena;
   cs::Weights W;
   cs::MotionW M;
+  float* se_scratch = nullptr; size_t se_cap = 0;   // SoftErosion scratch (grown on demand, outside the hot path's arena)
   std::vector<std::unique_ptr<cs::ConvW>> wino_convs;   // Winograd forms of static convs (ConvW::wn)
   double* stats_scratch = nullptr; // [max_batch*512*2] double
   double* stats_scratch2 = nullptr; // the second lane's (CS_OPT_LANES)
@@ -170,6 +171,8 @@ void wino_out_blend(const Launcher& L, const float* Mt, const float* mask, const
                     float* y, int B, int H, int W);
 
 // pasteback.cu
+void soft_erosion(const Launcher& L, const float* x, float* out, uint8_t* hard, float* tmp, const float* kw, int B, int H, int W, int K,
+                  float thr, int iterations);
 void paste_back(const Launcher& L, const uint8_t* crop, const float* mask, const double* M_c2o, const uint8_t* ori, uint8_t* out, int B,
                 int hc, int wc, int H, int W);
 

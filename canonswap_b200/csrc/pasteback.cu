@@ -111,3 +111,88 @@ void paste_back(const Launcher& L, const uint8_t* crop, const float* mask, const
 }
 
 }  // namespace cs
+
+// ------------------------------------------------------------------------------------------
+// SoftErosion (reference src/utils/crop.py:21-47; pipeline_e2e.py:42,275: kernel_size 21, threshold 0.9, iterations 3):
+//   for i in range(iterations - 1): x = min(x, conv2d(x, k, padding=r));  x = conv2d(x, k, padding=r)
+//   mask = x >= threshold;  x[mask] = 1;  x[~mask] /= x[~mask].max()
+// k = (dist.max() - dist) / sum, dist = distance to the kernel centre.  Float work: one block per 32x8 output tile with the
+// haloed input tile in shared memory, the kernel weights in constant-like global memory (L1-resident); the maximum of the
+// sub-threshold values through an integer atomicMax on the (non-negative) float bit patterns.
+// ------------------------------------------------------------------------------------------
+namespace cs {
+
+namespace {
+
+constexpr int SE_TW = 32, SE_TH = 8, SE_MAXK = 31;
+
+__global__ void __launch_bounds__(256) soft_erosion_conv_kernel(const float* __restrict__ x, const float* __restrict__ kw, float* __restrict__ y,
+                                                                int H, int W, int K, int take_min) {
+  extern __shared__ float tile[];                           // (SE_TH + K - 1) x (SE_TW + K - 1)
+  const int r = K / 2, tw = SE_TW + K - 1, th = SE_TH + K - 1;
+  const int b = blockIdx.z, x0 = blockIdx.x * SE_TW, y0 = blockIdx.y * SE_TH;
+  const float* xb = x + (long)b * H * W;
+  for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
+    const int ty = i / tw, tx = i % tw;
+    const int gy = y0 + ty - r, gx = x0 + tx - r;
+    tile[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? xb[(long)gy * W + gx] : 0.f;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % SE_TW, ly = threadIdx.x / SE_TW;
+  const int gx = x0 + lx, gy = y0 + ly;
+  if (gx >= W || gy >= H) return;
+  float acc = 0.f;
+  for (int ky = 0; ky < K; ++ky) {
+    const float* trow = tile + (ly + ky) * tw + lx;
+    const float* wrow = kw + ky * K;
+    for (int kx = 0; kx < K; ++kx) acc = fmaf(trow[kx], __ldg(wrow + kx), acc);
+  }
+  const float c = tile[(ly + r) * tw + lx + r];
+  y[(long)b * H * W + (long)gy * W + gx] = take_min ? fminf(c, acc) : acc;
+}
+
+__global__ void __launch_bounds__(256) soft_erosion_max_kernel(const float* __restrict__ x, long n, long per, float thr, int* __restrict__ mx) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    if (!(v >= thr)) atomicMax(mx + i / per, __float_as_int(fmaxf(v, 0.f)));   // conv of a non-negative mask: v >= 0
+  }
+}
+
+__global__ void __launch_bounds__(256) soft_erosion_apply_kernel(float* __restrict__ x, long n, long per, float thr, const int* __restrict__ mx,
+                                                                 uint8_t* __restrict__ hard) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    x[i] = (v >= thr) ? 1.f : v / __int_as_float(mx[i / per]);
+    if (hard) hard[i] = v >= thr ? 1 : 0;
+  }
+}
+
+}  // namespace
+
+// x [B,H,W] -> out [B,H,W]; tmp: 2 * B*H*W floats + B ints of scratch; kw: [K*K] normalised kernel on the device
+void soft_erosion(const Launcher& L, const float* x, float* out, uint8_t* hard, float* tmp, const float* kw, int B, int H, int W, int K,
+                  float thr, int iterations) {
+  for (int i = 0; i < iterations + 2; ++i) L.count();
+  if (L.dry) return;
+  CS_REQUIRE(K >= 1 && K <= SE_MAXK && (K & 1) && iterations >= 1, CS_ERR_INVALID, "soft_erosion: kernel_size must be odd and <= 31");
+  const long n = (long)B * H * W;
+  float* a = tmp; float* bbuf = tmp + n;
+  int* mx = reinterpret_cast<int*>(tmp + 2 * n);
+  const dim3 grid((W + SE_TW - 1) / SE_TW, (H + SE_TH - 1) / SE_TH, B);
+  const size_t smem = (size_t)(SE_TH + K - 1) * (SE_TW + K - 1) * sizeof(float);
+  ProfScope ps(L, PK_OTHER, 0.0, (double)n * 8.0 * iterations, "soft_erosion");
+  const float* src = x;
+  for (int i = 0; i < iterations; ++i) {
+    float* dst = (i == iterations - 1) ? out : ((i & 1) ? bbuf : a);
+    soft_erosion_conv_kernel<<<grid, 256, smem, L.stream>>>(src, kw, dst, H, W, K, i < iterations - 1 ? 1 : 0);
+    check_launch("soft_erosion_conv");
+    src = dst;
+  }
+  CS_CUDA(cudaMemsetAsync(mx, 0, sizeof(int) * B, L.stream));
+  long blocks = (n + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+  soft_erosion_max_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(out, n, (long)H * W, thr, mx);
+  soft_erosion_apply_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(out, n, (long)H * W, thr, mx, hard);
+  check_launch("soft_erosion_apply");
+}
+
+}  // namespace cs

@@ -288,6 +288,19 @@ class Engine:
                                             ori.data_ptr(), out.data_ptr(), B, hc, wc, H, W, self._stream()))
         return out
 
+    def soft_erosion(self, mask: torch.Tensor, kernel: torch.Tensor, threshold: float = 0.9, iterations: int = 3):
+        """SoftErosion.forward (reference src/utils/crop.py:37-47): mask [B,H,W] f32 -> (soft mask [B,H,W] f32, x >= threshold [B,H,W]
+        bool); kernel [K,K] f32 = the module's `weight` buffer."""
+        B, H, W = (int(v) for v in mask.shape)
+        K = int(kernel.shape[-1])
+        m = self._in(mask, (B, H, W), name="mask")
+        kw = self._in(kernel.reshape(K, K), (K, K), name="kernel")
+        out = self._new(B, H, W)
+        hard = self._new(B, H, W, dtype=torch.uint8)
+        self._check(self._lib.cs_soft_erosion(self._ctx, m.data_ptr(), kw.data_ptr(), out.data_ptr(), hard.data_ptr(), B, H, W, K,
+                                              float(threshold), int(iterations), self._stream()))
+        return out, hard.bool()
+
     # ---- measurement -------------------------------------------------------------------------------
     PROFILE_FAMILIES = ("conv_tcgen05", "conv_simt", "prep", "stats", "sampling", "other")
 

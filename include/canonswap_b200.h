@@ -160,6 +160,12 @@ CS_API int cs_keypoints(cs_ctx* ctx, const float* heads, float* x_s, float* x_ca
 CS_API int cs_paste_back(cs_ctx* ctx, const uint8_t* img_crop, const float* mask_crop, const double* M_c2o, const uint8_t* img_ori,
                          uint8_t* out, int B, int hc, int wc, int H, int W, void* stream);
 
+/* SoftErosion.forward (reference src/utils/crop.py:21-47; pipeline_e2e.py:42,275 uses kernel_size 21, threshold 0.9, iterations 3):
+ * mask [B,H,W] f32 -> out [B,H,W] f32 soft mask, hard [B,H,W] u8 = (x >= threshold) or NULL.  kernel: DEVICE pointer to the module's
+ * normalised [kernel_size^2] weight buffer (the binding builds it exactly as the reference's __init__ does). */
+CS_API int cs_soft_erosion(cs_ctx* ctx, const float* mask, const float* kernel, float* out, uint8_t* hard, int B, int H, int W,
+                           int kernel_size, float threshold, int iterations, void* stream);
+
 /* ---- per-kernel-family timing (measurement only) -------------------------------------------- */
 /* enable != 0: bracket every kernel launch of this ctx with CUDA events on the launching stream. */
 CS_API int cs_profile(cs_ctx* ctx, int enable);

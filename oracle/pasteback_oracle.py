@@ -117,3 +117,25 @@ def paste_back_frame(img_crop: np.ndarray, mask_crop: np.ndarray, M_c2o, img_ori
         mask_crop = np.stack([mask_crop] * 3, axis=-1)
     mask_ori = prepare_paste_back(mask_crop, M_c2o, dsize=(img_ori.shape[1], img_ori.shape[0]), if_float=True)
     return paste_back(img_crop, M_c2o, img_ori, mask_ori)
+
+
+def soft_erosion(x, kernel_size=21, threshold=0.9, iterations=3):
+    """SoftErosion (reference src/utils/crop.py:21-47) in plain torch on the CPU: x [B,1,H,W] -> (soft mask, x >= threshold).
+    Float work: compared with a tolerance, away from the threshold (tests/test_pasteback.py)."""
+    import torch
+    import torch.nn.functional as F
+    r = kernel_size // 2
+    yi, xi = torch.meshgrid(torch.arange(0., kernel_size), torch.arange(0., kernel_size), indexing="ij")
+    dist = torch.sqrt((xi - r) ** 2 + (yi - r) ** 2)
+    kernel = dist.max() - dist
+    kernel /= kernel.sum()
+    weight = kernel.view(1, 1, *kernel.shape)
+    x = x.float().clone()
+    for _ in range(iterations - 1):
+        x = torch.min(x, F.conv2d(x, weight=weight, groups=x.shape[1], padding=r))
+    x = F.conv2d(x, weight=weight, groups=x.shape[1], padding=r)
+    pre = x.clone()
+    mask = x >= threshold
+    x[mask] = 1.0
+    x[~mask] /= x[~mask].max()
+    return x, mask, pre

@@ -131,3 +131,42 @@ def test_paste_back_1080p_frame_and_in_place(eng):
     ori = torch.from_numpy(c[3][None]).cuda()
     eng.paste_back(crop, mask, c[2][None], ori, out=ori)
     assert np.array_equal(ori.cpu().numpy()[0], want)
+
+
+def _face_mask(H=256, W=256, seed=0):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    m = (((yy - H * 0.52) / (0.33 * H)) ** 2 + ((xx - W * 0.48) / (0.27 * W)) ** 2 < 1).astype(np.float32)
+    m[rng.random((H, W)) < 0.002] = 0                      # pin-holes, as a parsing mask has
+    return torch.from_numpy(m)[None, None]
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not has_reference(), reason="/root/reference not present")
+def test_soft_erosion_oracle_matches_reference_module():
+    sys.path.insert(0, "/root/reference")
+    from src.utils.crop import SoftErosion as RefSE
+    from canonswap_b200.pasteback import SoftErosion
+    x = _face_mask()
+    ref = RefSE(kernel_size=21, threshold=0.9, iterations=3)
+    want, wmask = ref(x.clone())
+    got, gmask, _ = P.soft_erosion(x, 21, 0.9, 3)
+    assert torch.equal(got, want) and torch.equal(gmask, wmask)
+    assert torch.equal(SoftErosion(21, 0.9, 3).weight, ref.weight)     # the mirror builds the same buffer
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [(21, 0.9, 3), (21, 0.9, 2), (15, 0.6, 1)])
+def test_soft_erosion_kernel_matches_oracle(eng, cfg):
+    """Float work (a 21x21 convolution in a different summation order): within 1e-5 wherever the pre-threshold value is not
+    within 1e-5 of the threshold, where the hard decision may flip."""
+    from canonswap_b200.pasteback import SoftErosion
+    K, thr, it = cfg
+    x = _face_mask(seed=3)
+    want, wmask, pre = P.soft_erosion(x, K, thr, it)
+    se = SoftErosion(K, thr, it).bind(eng)
+    got, gmask = se(x.cuda())
+    safe = (pre - thr).abs() > 1e-5
+    assert safe.float().mean().item() > 0.99
+    assert ((got.cpu() - want).abs()[safe]).max().item() <= 1e-5
+    assert torch.equal(gmask.cpu()[safe], wmask[safe])
