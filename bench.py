@@ -309,6 +309,46 @@ def main():
                       "gflop_per_frame": 4177.8,
                       "note": "CS_FRAME_DEBUG_DECODES: the two conv_decode calls of the reference loop run too (results discarded)"}
 
+    # ---- extra leg: paste-back of a 512x512 crop into a 1920x1080 frame, next to cv2 on the host ----
+    paste = None
+    if rank == 0:
+        import numpy as np
+        PB, PH, PW = 8, 1080, 1920
+        g = torch.Generator().manual_seed(7)
+        crop_p = torch.randint(0, 256, (PB, 2 * NET, 2 * NET, 3), dtype=torch.uint8, generator=g).to(dev)
+        ori_p = torch.randint(0, 256, (PB, PH, PW, 3), dtype=torch.uint8, generator=g).to(dev)
+        mask_p = torch.rand(PB, 2 * NET, 2 * NET, generator=g).to(dev)
+        Mp = np.tile(np.array([[1.21, -0.13, 640.0], [0.13, 1.21, 230.0], [0, 0, 1]], dtype=np.float32), (PB, 1, 1))
+        outp = torch.empty_like(ori_p)
+        for _ in range(3):
+            eng.paste_back(crop_p, mask_p, Mp, ori_p, out=outp)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(20):
+            eng.paste_back(crop_p, mask_p, Mp, ori_p, out=outp)
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1) / 20
+        alg = PB * (2 * PH * PW * 3 + (2 * NET) ** 2 * 7)            # frame read + written, crop (3 B) + mask (4 B) read
+        paste = {"value": PB / (pms / 1000.0), "unit": "frames/s", "frame": f"{PW}x{PH}", "crop": f"{2 * NET}x{2 * NET}",
+                 "ms_per_batch_of_8": pms, "hbm_gbs": alg / pms / 1e6, "hbm_frac": alg / pms / 1e6 / (_peaks()[1] or 6650.0)}
+        try:                                                          # the reference's host path: two cv2.warpAffine + numpy blend
+            import cv2
+            cv2.setNumThreads(0)
+            c_h, o_h, m_h = crop_p[0].cpu().numpy(), ori_p[0].cpu().numpy(), mask_p[0].cpu().numpy()
+            m3 = np.stack([m_h] * 3, axis=-1)
+            t0 = time.perf_counter()
+            for _ in range(4):
+                mo = cv2.warpAffine(m3, Mp[0][:2, :], (PW, PH), flags=cv2.INTER_LINEAR)
+                res = cv2.warpAffine(c_h, Mp[0][:2, :], (PW, PH), flags=cv2.INTER_LINEAR)
+                ref_out = np.clip(mo * res + (1 - mo) * o_h, 0, 255).astype(np.uint8)
+            paste["cpu_value"] = 4 / (time.perf_counter() - t0)
+            paste["cpu_kind"] = "reference arithmetic (cv2.warpAffine x2 + numpy blend, 1 thread as the reference sets), 4 frames"
+            paste["bit_exact_vs_cv2"] = bool(np.array_equal(outp[0].cpu().numpy(), ref_out))
+        except ImportError:
+            pass
+
     # ---- roofline of the dominant kernel family (rank 0, separate profiled pass: events per launch) ------
     roofline = None
     families = None
@@ -366,7 +406,7 @@ def main():
                        "gflop_per_frame": GFLOP_PER_FRAME},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "families": families, "achieved_tflops_whole_step": value * GFLOP_PER_FRAME / 1000.0,
-            "with_motion_extractor": with_motion, "as_written": as_written,
+            "with_motion_extractor": with_motion, "as_written": as_written, "paste_back": paste,
         }))
     if world > 1:
         dist.destroy_process_group()

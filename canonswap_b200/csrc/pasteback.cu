@@ -26,59 +26,84 @@ struct PasteK {
 
 __device__ __forceinline__ long long cv_round(double v) { return __double2ll_rn(v); }
 
+// one destination pixel: its three output bytes from the frame's bytes o[0..2]
+__device__ __forceinline__ void paste_pixel(const PasteK& k, int b, int x, int y, const uint8_t* o, uint8_t* dst) {
+  const double* m = k.iM[b];
+  // adelta[x] = round(M00 * x * 1024), X0 = round((M01 * y + M02) * 1024) + 16   (no contraction: __dmul_rn / __dadd_rn)
+  const long long ad = cv_round(__dmul_rn(__dmul_rn(m[0], (double)x), 1024.0));
+  const long long bd = cv_round(__dmul_rn(__dmul_rn(m[3], (double)x), 1024.0));
+  const long long X0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(m[1], (double)y), m[2]), 1024.0)) + 16;
+  const long long Y0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(m[4], (double)y), m[5]), 1024.0)) + 16;
+  const long long X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
+  const long long sx = X >> 5, sy = Y >> 5;
+  const int fx = (int)(X & 31), fy = (int)(Y & 31);
+  if (sx < -1 || sx >= k.wc || sy < -1 || sy >= k.hc) {      // all four taps outside: result = 0, mask = 0 -> the frame itself
+    dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];              // (1 - 0) * img_ori is exact
+    return;
+  }
+  bool ok[4];
+  long off[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long yy = sy + (j >> 1), xx = sx + (j & 1);
+    ok[j] = yy >= 0 && yy < k.hc && xx >= 0 && xx < k.wc;
+    off[j] = ok[j] ? ((long)b * k.hc + yy) * k.wc + xx : 0;
+  }
+  // float32 mask sample
+  const float a = __fmul_rn((float)fx, 1.0f / 32.0f), bb = __fmul_rn((float)fy, 1.0f / 32.0f);
+  const float ia = __fsub_rn(1.f, a), ib = __fsub_rn(1.f, bb);
+  const float w0 = __fmul_rn(ib, ia), w1 = __fmul_rn(ib, a), w2 = __fmul_rn(bb, ia), w3 = __fmul_rn(bb, a);
+  const float s0 = ok[0] ? k.mask[off[0]] : 0.f, s1 = ok[1] ? k.mask[off[1]] : 0.f;
+  const float s2 = ok[2] ? k.mask[off[2]] : 0.f, s3 = ok[3] ? k.mask[off[3]] : 0.f;
+  float mk = __fmul_rn(s0, w0);
+  mk = __fadd_rn(mk, __fmul_rn(s1, w1));
+  mk = __fadd_rn(mk, __fmul_rn(s2, w2));
+  mk = __fadd_rn(mk, __fmul_rn(s3, w3));
+  const float im = __fsub_rn(1.f, mk);
+  // uint8 image sample: integer weights 32 * p * q, (sum + 2^14) >> 15
+  const int iw0 = 32 * (32 - fy) * (32 - fx), iw1 = 32 * (32 - fy) * fx, iw2 = 32 * fy * (32 - fx), iw3 = 32 * fy * fx;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    int acc = 1 << 14;
+    if (ok[0]) acc += iw0 * k.crop[off[0] * 3 + c];
+    if (ok[1]) acc += iw1 * k.crop[off[1] * 3 + c];
+    if (ok[2]) acc += iw2 * k.crop[off[2] * 3 + c];
+    if (ok[3]) acc += iw3 * k.crop[off[3] * 3 + c];
+    int res = acc >> 15;
+    res = res > 255 ? 255 : res;
+    float v = __fadd_rn(__fmul_rn(mk, (float)res), __fmul_rn(im, (float)o[c]));
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    dst[c] = (uint8_t)v;                                  // astype(uint8): truncation
+  }
+}
+
+// VEC: one thread = 4 consecutive pixels of a row = 12 bytes = three aligned 32-bit words of the frame (W % 4 == 0, 4-byte
+// aligned bases); else one thread = one pixel with byte accesses
+template <bool VEC>
 __global__ void __launch_bounds__(256) paste_back_kernel(const __grid_constant__ PasteK k) {
-  const long total = (long)k.B * k.H * k.W;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % k.W); long t = idx / k.W;
-    const int y = (int)(t % k.H); const int b = (int)(t / k.H);
-    const double* m = k.iM[b];
-    // adelta[x] = round(M00 * x * 1024), X0 = round((M01 * y + M02) * 1024) + 16   (no contraction: __dmul_rn / __dadd_rn)
-    const long long ad = cv_round(__dmul_rn(__dmul_rn(m[0], (double)x), 1024.0));
-    const long long bd = cv_round(__dmul_rn(__dmul_rn(m[3], (double)x), 1024.0));
-    const long long X0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(m[1], (double)y), m[2]), 1024.0)) + 16;
-    const long long Y0 = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(m[4], (double)y), m[5]), 1024.0)) + 16;
-    const long long X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
-    const long long sx = X >> 5, sy = Y >> 5;
-    const int fx = (int)(X & 31), fy = (int)(Y & 31);
-    const uint8_t* o = k.ori + idx * 3;
-    uint8_t* dst = k.out + idx * 3;
-    if (sx < -1 || sx >= k.wc || sy < -1 || sy >= k.hc) {      // all four taps outside: result = 0, mask = 0 -> the frame itself
-      dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];              // (1 - 0) * img_ori is exact
-      continue;
-    }
-    bool ok[4];
-    long off[4];
+  if constexpr (VEC) {
+    const int W4 = k.W >> 2;
+    const long total = (long)k.B * k.H * W4;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+      const int x4 = (int)(idx % W4); long t = idx / W4;
+      const int y = (int)(t % k.H); const int b = (int)(t / k.H);
+      const long base = (((long)b * k.H + y) * k.W + (long)x4 * 4) * 3;
+      union { uint32_t w[3]; uint8_t c[12]; } in, out;
+      const uint32_t* ip = reinterpret_cast<const uint32_t*>(k.ori + base);
+      in.w[0] = ip[0]; in.w[1] = ip[1]; in.w[2] = ip[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const long long yy = sy + (j >> 1), xx = sx + (j & 1);
-      ok[j] = yy >= 0 && yy < k.hc && xx >= 0 && xx < k.wc;
-      off[j] = ok[j] ? ((long)b * k.hc + yy) * k.wc + xx : 0;
+      for (int p = 0; p < 4; ++p) paste_pixel(k, b, x4 * 4 + p, y, in.c + 3 * p, out.c + 3 * p);
+      uint32_t* op = reinterpret_cast<uint32_t*>(k.out + base);
+      op[0] = out.w[0]; op[1] = out.w[1]; op[2] = out.w[2];
     }
-    // float32 mask sample
-    const float a = __fmul_rn((float)fx, 1.0f / 32.0f), bb = __fmul_rn((float)fy, 1.0f / 32.0f);
-    const float ia = __fsub_rn(1.f, a), ib = __fsub_rn(1.f, bb);
-    const float w0 = __fmul_rn(ib, ia), w1 = __fmul_rn(ib, a), w2 = __fmul_rn(bb, ia), w3 = __fmul_rn(bb, a);
-    const float s0 = ok[0] ? k.mask[off[0]] : 0.f, s1 = ok[1] ? k.mask[off[1]] : 0.f;
-    const float s2 = ok[2] ? k.mask[off[2]] : 0.f, s3 = ok[3] ? k.mask[off[3]] : 0.f;
-    float mk = __fmul_rn(s0, w0);
-    mk = __fadd_rn(mk, __fmul_rn(s1, w1));
-    mk = __fadd_rn(mk, __fmul_rn(s2, w2));
-    mk = __fadd_rn(mk, __fmul_rn(s3, w3));
-    const float im = __fsub_rn(1.f, mk);
-    // uint8 image sample: integer weights 32 * p * q, (sum + 2^14) >> 15
-    const int iw0 = 32 * (32 - fy) * (32 - fx), iw1 = 32 * (32 - fy) * fx, iw2 = 32 * fy * (32 - fx), iw3 = 32 * fy * fx;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      int acc = 1 << 14;
-      if (ok[0]) acc += iw0 * k.crop[off[0] * 3 + c];
-      if (ok[1]) acc += iw1 * k.crop[off[1] * 3 + c];
-      if (ok[2]) acc += iw2 * k.crop[off[2] * 3 + c];
-      if (ok[3]) acc += iw3 * k.crop[off[3] * 3 + c];
-      int res = acc >> 15;
-      res = res > 255 ? 255 : res;
-      float v = __fadd_rn(__fmul_rn(mk, (float)res), __fmul_rn(im, (float)o[c]));
-      v = fminf(fmaxf(v, 0.f), 255.f);
-      dst[c] = (uint8_t)v;                                  // astype(uint8): truncation
+  } else {
+    const long total = (long)k.B * k.H * k.W;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+      const int x = (int)(idx % k.W); long t = idx / k.W;
+      const int y = (int)(t % k.H); const int b = (int)(t / k.H);
+      uint8_t o[3] = {k.ori[idx * 3], k.ori[idx * 3 + 1], k.ori[idx * 3 + 2]}, d[3];
+      paste_pixel(k, b, x, y, o, d);
+      k.out[idx * 3] = d[0]; k.out[idx * 3 + 1] = d[1]; k.out[idx * 3 + 2] = d[2];
     }
   }
 }
@@ -104,9 +129,11 @@ void paste_back(const Launcher& L, const uint8_t* crop, const float* mask, const
     q[5] = -q[3] * M[2] - q[4] * M[5];
   }
   const long total = (long)B * H * W;
-  long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
+  const bool vec = (W % 4 == 0) && ((uintptr_t)ori % 4 == 0) && ((uintptr_t)out % 4 == 0);
+  long blocks = ((vec ? total / 4 : total) + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
   ProfScope ps(L, PK_OTHER, 0.0, (double)total * 6.0 + (double)B * hc * wc * 7.0, "paste_back");
-  paste_back_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+  if (vec) paste_back_kernel<true><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+  else paste_back_kernel<false><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
   check_launch("paste_back");
 }
 
