@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the CPU baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-motion", action="store_true", help="skip the extra leg that derives the keypoints with the motion extractor")
-    ap.add_argument("--lanes", type=int, default=None, help="CS_OPT_LANES: concurrent sub-batches of a graph-replayed step (1 | 2)")
+    ap.add_argument("--lanes", type=int, default=None, help="CS_OPT_LANES: concurrent sub-batches of a graph-replayed step (1 | 2 | 4)")
     ap.add_argument("--opt", action="append", default=[], help="experiment: library option id=value (cs_set_option), repeatable")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of a step individually (default: CUDA-graph replay)")
     args = ap.parse_args()

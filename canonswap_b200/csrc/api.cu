@@ -201,20 +201,21 @@ void size_workspace(cs_ctx* ctx) {
       if (ctx->M.loaded) { A.reset(0); body_motion(n, fake, fake, B); }
     }
   }
-  // two-lane replay (CS_OPT_LANES): each half of the arena must hold cs_frame at ceil(max_batch / 2)
+  // multi-lane replay (CS_OPT_LANES = 2 | 4): each 1/L of the arena must hold cs_frame at ceil(max_batch / L)
   size_t full_high = A.high;
-  {
+  for (int lanes = 2; lanes <= 4; lanes *= 2) {
     Net n = make_net(ctx, nullptr, true);
     A.high = 0;
     for (int impl = 0; impl < 3; ++impl) {
       n.L.conv_impl = impl == 0 ? 1 : 0;
       n.L.winograd = impl == 2;
-      A.reset(0); body_frame(n, fake, fake, fake, fake, reinterpret_cast<uint8_t*>(fake), (B + 1) / 2,
+      A.reset(0); body_frame(n, fake, fake, fake, fake, reinterpret_cast<uint8_t*>(fake), (B + lanes - 1) / lanes,
                              CS_FRAME_IN_U8_HWC | CS_FRAME_DEBUG_DECODES | (ctx->M.loaded ? CS_FRAME_MOTION : 0));
     }
-    ctx->arena_half_need = A.high + 4096;
-    A.high = full_high > 2 * ctx->arena_half_need ? full_high : 2 * ctx->arena_half_need;
+    const size_t lane_need = (A.high + 4096) * lanes;
+    if (lane_need > full_high) full_high = lane_need;
   }
+  A.high = full_high;
   ctx->identity_set = id;
   size_t need = A.high + (1 << 20);
   A.measuring = false; A.off = 0; A.high = 0;
@@ -252,7 +253,8 @@ int cs_create(cs_ctx** out, int device, int max_batch, int net_h, int net_w) {
     size_t sb = sizeof(double) * 2 * (size_t)max_batch * 512;
     if (sb < 4096) sb = 4096;
     ctx->stats_scratch = static_cast<double*>(ctx->dmalloc(sb));
-    ctx->stats_scratch2 = static_cast<double*>(ctx->dmalloc(sb));
+    ctx->stats_lane[0] = ctx->stats_scratch;
+    for (int l = 1; l < 4; ++l) ctx->stats_lane[l] = static_cast<double*>(ctx->dmalloc(sb));
   } catch (const std::exception& ex) {
     if (ctx) cs_destroy(ctx);
     return fail(nullptr, CS_ERR_CUDA, ex.what());
@@ -267,9 +269,11 @@ void cs_destroy(cs_ctx* ctx) {
   cudaDeviceSynchronize();
   ctx->drop_graphs();
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
-  if (ctx->cap_stream2) cudaStreamDestroy(ctx->cap_stream2);
+  for (int l = 1; l < 4; ++l) {
+    if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
+    if (ctx->ev_lane[l]) cudaEventDestroy(ctx->ev_lane[l]);
+  }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (void* p : ctx->owned) cudaFree(p);
   delete ctx;
 }
@@ -315,7 +319,7 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
     case CS_OPT_USE_GRAPH:
       ctx->use_graph = value ? 1 : 0; return CS_OK;
     case CS_OPT_LANES:
-      if (value < 1 || value > 2) return fail(ctx, CS_ERR_INVALID, "CS_OPT_LANES: value must be 1 or 2");
+      if (value != 1 && value != 2 && value != 4) return fail(ctx, CS_ERR_INVALID, "CS_OPT_LANES: value must be 1, 2 or 4");
       ctx->lanes = value; return CS_OK;
     default: return fail(ctx, CS_ERR_INVALID, "unknown option");
   }
@@ -458,31 +462,40 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
         n.L.stream = cst;
         CS_CUDA(cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal));
         try {
-          if (ctx->lanes == 2 && B >= 2) {
-            // two concurrent sub-batches on forked capture streams: frames are independent, so the tail wave of one lane's
-            // kernel is filled by CTAs of the other lane's (each lane owns half of the arena and its own statistics scratch)
-            const int B0 = (B + 1) / 2, B1 = B - B0;
-            if (!ctx->cap_stream2) CS_CUDA(cudaStreamCreateWithFlags(&ctx->cap_stream2, cudaStreamNonBlocking));
+          const int lanes = ctx->lanes <= B ? ctx->lanes : (B >= 2 ? 2 : 1);
+          if (lanes >= 2) {
+            // concurrent sub-batches on forked capture streams: frames are independent, so the tail wave of one lane's kernel
+            // is filled by CTAs of another lane's, and one lane's bandwidth-bound kernels overlap another's MMA-bound ones
+            // (each lane owns 1/L of the arena and its own statistics scratch)
             if (!ctx->ev_fork) CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-            if (!ctx->ev_join) CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-            Arena a0 = ctx->arena, a1 = ctx->arena;
-            const size_t half = (ctx->arena.cap / 2) & ~size_t(255);
-            a0.cap = half; a0.off = 0; a0.high = 0;
-            a1.base = ctx->arena.base + half; a1.cap = ctx->arena.cap - half; a1.off = 0; a1.high = 0;
             CS_CUDA(cudaEventRecord(ctx->ev_fork, cst));
-            CS_CUDA(cudaStreamWaitEvent(ctx->cap_stream2, ctx->ev_fork, 0));
-            const size_t px0 = (size_t)B0 * ctx->net_h * ctx->net_w;
-            const size_t in_off = (flags & CS_FRAME_IN_U8_HWC) ? px0 * 3 : px0 * 3 * sizeof(float);
-            Net n0 = n; n0.A = &a0;
-            Net n1 = n; n1.A = &a1; n1.L.stream = ctx->cap_stream2; n1.stats = ctx->stats_scratch2;
-            if (ctx->M.sumsq) n1.grn = ctx->M.sumsq + (size_t)B0 * 3072;
-            body_frame(n0, ctx->g_frames, ctx->g_kpt, ctx->g_kpc, out_f32 ? ctx->g_out32 : nullptr, out_u8 ? ctx->g_outu8 : nullptr,
-                       B0, flags);
-            body_frame(n1, static_cast<char*>(ctx->g_frames) + in_off, ctx->g_kpt + (size_t)B0 * NUM_KP * 3,
-                       ctx->g_kpc + (size_t)B0 * NUM_KP * 3, out_f32 ? ctx->g_out32 + px0 * 4 * 3 : nullptr,
-                       out_u8 ? ctx->g_outu8 + px0 * 4 * 3 : nullptr, B1, flags);
-            CS_CUDA(cudaEventRecord(ctx->ev_join, ctx->cap_stream2));
-            CS_CUDA(cudaStreamWaitEvent(cst, ctx->ev_join, 0));
+            const size_t part = (ctx->arena.cap / lanes) & ~size_t(255);
+            Arena arenas[4];
+            int b_lo = 0;
+            for (int l = 0; l < lanes; ++l) {
+              const int Bl = (B - b_lo + (lanes - l) - 1) / (lanes - l);          // even split of what is left
+              cudaStream_t sl = cst;
+              if (l > 0) {
+                if (!ctx->lane_stream[l]) CS_CUDA(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+                if (!ctx->ev_lane[l]) CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_lane[l], cudaEventDisableTiming));
+                sl = ctx->lane_stream[l];
+                CS_CUDA(cudaStreamWaitEvent(sl, ctx->ev_fork, 0));
+              }
+              arenas[l] = ctx->arena;
+              arenas[l].base = ctx->arena.base + part * l; arenas[l].cap = part; arenas[l].off = 0; arenas[l].high = 0;
+              const size_t px0 = (size_t)b_lo * ctx->net_h * ctx->net_w;
+              const size_t in_off = (flags & CS_FRAME_IN_U8_HWC) ? px0 * 3 : px0 * 3 * sizeof(float);
+              Net nl = n; nl.A = &arenas[l]; nl.L.stream = sl; nl.stats = ctx->stats_lane[l];
+              if (ctx->M.sumsq) nl.grn = ctx->M.sumsq + (size_t)b_lo * 3072;
+              body_frame(nl, static_cast<char*>(ctx->g_frames) + in_off, ctx->g_kpt + (size_t)b_lo * NUM_KP * 3,
+                         ctx->g_kpc + (size_t)b_lo * NUM_KP * 3, out_f32 ? ctx->g_out32 + px0 * 4 * 3 : nullptr,
+                         out_u8 ? ctx->g_outu8 + px0 * 4 * 3 : nullptr, Bl, flags);
+              if (l > 0) {
+                CS_CUDA(cudaEventRecord(ctx->ev_lane[l], sl));
+                CS_CUDA(cudaStreamWaitEvent(cst, ctx->ev_lane[l], 0));
+              }
+              b_lo += Bl;
+            }
           } else {
             body_frame(n, ctx->g_frames, ctx->g_kpt, ctx->g_kpc, out_f32 ? ctx->g_out32 : nullptr, out_u8 ? ctx->g_outu8 : nullptr, B,
                        flags);

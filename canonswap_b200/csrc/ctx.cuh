@@ -114,11 +114,11 @@ struct cs_ctx {
   float* se_scratch = nullptr; size_t se_cap = 0;   // SoftErosion scratch (grown on demand, outside the hot path's arena)
   std::vector<std::unique_ptr<cs::ConvW>> wino_convs;   // Winograd forms of static convs (ConvW::wn)
   double* stats_scratch = nullptr; // [max_batch*512*2] double
-  double* stats_scratch2 = nullptr; // the second lane's (CS_OPT_LANES)
+  double* stats_lane[4] = {};      // per-lane statistics scratch (CS_OPT_LANES); [0] == stats_scratch
   int lanes = 2;                   // CS_OPT_LANES: a graph-captured cs_frame runs as this many concurrent sub-batches
-  cudaStream_t cap_stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  size_t arena_half_need = 0;      // high-water mark of cs_frame at ceil(max_batch / 2)
+  cudaStream_t lane_stream[4] = {}; // [0] unused (the capture stream itself)
+  cudaEvent_t ev_lane[4] = {};
+  cudaEvent_t ev_fork = nullptr;
   cs::Profiler prof;
   // CUDA-graph replay of cs_frame (CS_OPT_USE_GRAPH): the whole loop body is captured once per (B, flags, outputs)
   // on fixed staging buffers; a call then is copy-in -> graph launch -> copy-out on the caller's stream.

@@ -80,7 +80,7 @@ typedef struct cs_tensor_desc {
                                     until it holds (0 = default 256) */
 #define CS_OPT_WINOGRAD 13       /* 1 (default) = the wide 3x3 2-D convs (adaptive convs of the swap module, SPADE conv_0 / conv_1, refine ResBlock2d) in
                                     Winograd F(2x2,3x3) form, 0 = direct implicit GEMM */
-#define CS_OPT_LANES 10         /* 1 | 2 (default): a graph-captured cs_frame runs as this many concurrent sub-batches (forked streams) */
+#define CS_OPT_LANES 10         /* 1 | 2 (default) | 4: a graph-captured cs_frame runs as this many concurrent sub-batches (forked streams) */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
