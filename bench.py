@@ -349,6 +349,31 @@ def main():
         except ImportError:
             pass
 
+    # ---- extra leg: the whole LOOP C body with host buffers (motion extractor -> generator -> SoftErosion -> paste-back into
+    #      1920x1080 frames), pinned host memory in and out, H2D / D2H inside the timed region -------------------------------
+    full_loop = None
+    if rank == 0 and not args.no_motion and not args.no_e2e:
+        from canonswap_b200.pipeline import FullLoopPipeline
+        import numpy as np
+        TF, PH, PW = B * max(2, args.steps // 2), 1080, 1920
+        g = torch.Generator().manual_seed(11)
+        h_crops = clip["frames"][:TF].contiguous().pin_memory()
+        h_masks = (torch.rand(TF, 2 * NET, 2 * NET, generator=g) > 0.4).float().pin_memory()
+        h_full = torch.randint(0, 256, (TF, PH, PW, 3), dtype=torch.uint8, generator=g).pin_memory()
+        h_res = torch.empty_like(h_full).pin_memory()
+        Mf = np.tile(np.array([[1.21, -0.13, 640.0], [0.13, 1.21, 230.0], [0, 0, 1]], dtype=np.float32), (TF, 1, 1))
+        fl = FullLoopPipeline(sw, net_hw=(NET, NET), batch=B)
+        fl.run(h_crops[:B], h_masks[:B], Mf[:B], h_full[:B], h_res[:B])          # warm-up
+        fl.h2d_bytes = fl.d2h_bytes = 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fl.run(h_crops, h_masks, Mf, h_full, h_res)
+        dt = time.perf_counter() - t0
+        full_loop = {"value": TF / dt, "unit": "frames/s", "frames": TF, "frame": f"{PW}x{PH}",
+                     "h2d_bytes_per_frame": fl.h2d_bytes // TF, "d2h_bytes_per_frame": fl.d2h_bytes // TF,
+                     "note": "crop + parsing mask + full frame from pinned host memory -> pasted full frame in pinned host memory "
+                             "(reference can_swap_pipeline_e2e.py:223-283 after the cropper / face parser), wall clock"}
+
     # ---- roofline of the dominant kernel family (rank 0, separate profiled pass: events per launch) ------
     roofline = None
     families = None
@@ -406,7 +431,7 @@ def main():
                        "gflop_per_frame": GFLOP_PER_FRAME},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "families": families, "achieved_tflops_whole_step": value * GFLOP_PER_FRAME / 1000.0,
-            "with_motion_extractor": with_motion, "as_written": as_written, "paste_back": paste,
+            "with_motion_extractor": with_motion, "as_written": as_written, "paste_back": paste, "full_loop": full_loop,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -134,3 +134,50 @@ class FramePipeline:
         self.copy_out.synchronize()
         self.compute.synchronize()
         return len(mine)
+
+
+class FullLoopPipeline:
+    """The whole per-frame body of `CanSwapPipeline.execute` LOOP C after the front-end (reference
+    src/can_swap_pipeline_e2e.py:223-283 with flag_pasteback and flag_do_crop, the defaults):
+
+        x_t, x_can  <- motion extractor + transform_keypoint of the cropped frame     (:112-125, :231-243)
+        I_p         <- generator (F, warp, swap, refine, warp_decode) + parse_output  (:242-267)
+        mask        <- SoftErosion(21, 0.9, 3)(parsing mask)                          (:42, :275)
+        frame       <- paste_back(I_p, M_c2o, full frame, prepare_paste_back(mask))   (:277-282)
+
+    Inputs per frame (what the reference's cropper / face parser hand to the loop): the 256x256 crop, the 512x512 parsing
+    mask, the crop->original matrix and the full frame.  Everything stays on the device between the H2D of the inputs and the
+    D2H of the pasted frame; the reference moves the keypoints, the mask and the image through numpy per frame.
+    """
+
+    def __init__(self, swapper, net_hw=(256, 256), batch: int = 8):
+        from .pasteback import SoftErosion
+        self.sw = swapper
+        self.batch = batch
+        self.net_h, self.net_w = net_hw
+        self.dev = torch.device(swapper.device)
+        self.engine = swapper.engine(net_hw, batch)
+        self.soft_mask = SoftErosion(kernel_size=21, threshold=0.9, iterations=3).bind(self.engine)   # pipeline_e2e.py:42
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def run(self, crops_u8: torch.Tensor, parse_masks: torch.Tensor, M_c2o, frames_u8: torch.Tensor, out_u8: torch.Tensor) -> int:
+        """crops_u8 [T,h,w,3] u8, parse_masks [T,2h,2w] f32, frames_u8 / out_u8 [T,H,W,3] u8: PINNED host tensors; M_c2o [T,3,3]
+        (or [T,2,3]) numpy.  Returns the number of frames; synchronises before returning."""
+        import numpy as np
+        T = int(crops_u8.shape[0])
+        M = np.asarray(M_c2o)
+        st = torch.cuda.current_stream(self.dev)
+        for lo in range(0, T, self.batch):
+            hi = min(T, lo + self.batch)
+            crops = crops_u8[lo:hi].to(self.dev, non_blocking=True)
+            masks = parse_masks[lo:hi].to(self.dev, non_blocking=True)
+            full = frames_u8[lo:hi].to(self.dev, non_blocking=True)
+            self.h2d_bytes += crops.numel() + masks.numel() * 4 + full.numel()
+            I_p, _ = self.sw.swap_frames(crops)                                   # keypoints from the motion extractor
+            soft, _ = self.soft_mask(masks[:, None])
+            pasted = self.engine.paste_back(I_p, soft[:, 0], M[lo:hi], full, out=full)
+            out_u8[lo:hi].copy_(pasted, non_blocking=True)
+            self.d2h_bytes += pasted.numel()
+        st.synchronize()
+        return T
