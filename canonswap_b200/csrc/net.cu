@@ -342,7 +342,8 @@ void run_warp_out(Net& n, const float* vol_in, const float* occ, int B, float* o
   Act x = vol_as_2d(const_cast<float*>(vol_in), B, h, w);
   Act t = new_act(n, B, 1, h, w, 256);
   ConvOpts o1; o1.act = ACT_LRELU; o1.slope = 0.01f;                      // SameBlock2d(lrelu=True), BN folded
-  conv_layer(n, nullptr, x, W.w_third, o1, t);
+  if (wino_ok(n.L, W.w_third, h, w)) wino_conv(n.L, *n.A, x, W.w_third, nullptr, nullptr, ACT_NONE, 0.f, ACT_LRELU, 0.01f, nullptr, t);
+  else conv_layer(n, nullptr, x, W.w_third, o1, t);
   ConvOpts o2; o2.mult = occ;                                             // out * occlusion_map
   conv_layer(n, nullptr, t, W.w_fourth, o2, make_act(out256, B, 1, h, w, 256));
   n.A->reset(m);
@@ -644,7 +645,8 @@ void run_spade(Net& n, const float* feat256, int B, float* img_nchw, uint8_t* im
   Act seg = make_act(const_cast<float*>(feat256), B, 1, h, w, 256);
   Act xa = new_act(n, B, 1, h, w, 512);
   Act xb = new_act(n, B, 1, h, w, 512);
-  conv_layer(n, nullptr, seg, W.g_fc, ConvOpts(), xa);
+  if (wino_ok(n.L, W.g_fc, h, w)) wino_conv(n.L, *n.A, seg, W.g_fc, nullptr, nullptr, ACT_NONE, 0.f, ACT_NONE, 0.f, nullptr, xa);
+  else conv_layer(n, nullptr, seg, W.g_fc, ConvOpts(), xa);
   for (int i = 0; i < 6; ++i) {                                           // G_middle_0..5
     spade_block(n, W.g_blocks[i], xa, 0, seg, 0, xb);
     Act t = xa; xa = xb; xb = t;

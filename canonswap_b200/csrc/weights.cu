@@ -365,6 +365,7 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
     fold_bn_post(third, read_bn(t, "third.norm", 256));
     permute_in_vol(third);
     W.w_third = pack(ctx, third);
+    pack_wino_static(ctx, W.w_third);
     W.w_fourth = pack(ctx, read_conv(t, "fourth", 256, 256, 1, 1, 1));
   }
 
@@ -433,6 +434,7 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
   // ---- G: SPADE decoder (spade_generator.py:13-39) ----
   t.net = "spade_generator.";
   W.g_fc = pack(ctx, read_conv(t, "fc", 512, 256, 1, 3, 3));
+  pack_wino_static(ctx, W.g_fc);
   {
     static const char* names[8] = {"G_middle_0", "G_middle_1", "G_middle_2", "G_middle_3", "G_middle_4", "G_middle_5",
                                    "up_0", "up_1"};
