@@ -542,7 +542,8 @@ bool conv_tc_supported(const ConvW& w, const Act& out) {
   return w.wtc != nullptr;
 }
 
-bool conv_tc_shape_ok(int Cin, int Cout) { return Cin >= 16 && Cout >= 1; }
+// (Cin < 16, e.g. the RGB input of the first conv, is zero-padded to one 16-channel K step)
+bool conv_tc_shape_ok(int Cin, int Cout) { return Cin >= 1 && Cout >= 1; }
 
 Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out) {
   Opd o;

@@ -61,6 +61,7 @@ TC_CASES = [c for c in CONV_CASES if c[4] >= 16] + [
     (3, 16, 1, 1, 512, 1024, (3, 3, 3), (1, 1, 1)),   # deepest hourglass level at net 128: 1x1 spatial, batch-tiled box
     (1, 1, 24, 40, 48, 272, (1, 3, 3), (0, 1, 1)),    # non-power-of-two extents, two N tiles of 144
     (2, 1, 64, 64, 512, 512, (1, 3, 3), (0, 1, 1)),   # the most-used shape
+    (2, 1, 64, 48, 3, 64, (1, 3, 3), (0, 1, 1)),      # RGB input of the first conv: 3 channels padded to one K step
 ]
 
 
