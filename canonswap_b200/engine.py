@@ -275,8 +275,14 @@ class Engine:
         import numpy as np
         B, hc, wc = int(img_crop.shape[0]), int(img_crop.shape[1]), int(img_crop.shape[2])
         H, W = int(img_ori.shape[1]), int(img_ori.shape[2])
-        if B > _lib.PASTE_MAX_BATCH:
-            raise ValueError(f"paste_back: at most {_lib.PASTE_MAX_BATCH} frames per call")
+        if B > _lib.PASTE_MAX_BATCH:                  # the C entry point takes <= 16 matrices per launch: chunk
+            if out is None:
+                out = self._new(B, H, W, 3, dtype=torch.uint8)
+            Mh = np.asarray(M_c2o)
+            for lo in range(0, B, _lib.PASTE_MAX_BATCH):
+                hi = min(B, lo + _lib.PASTE_MAX_BATCH)
+                self.paste_back(img_crop[lo:hi], mask_crop[lo:hi], Mh[lo:hi], img_ori[lo:hi], out=out[lo:hi])
+            return out
         crop = self._in(img_crop, (B, hc, wc, 3), dtype=torch.uint8, name="img_crop")
         mask = self._in(mask_crop, (B, hc, wc), name="mask_crop")
         ori = self._in(img_ori, (B, H, W, 3), dtype=torch.uint8, name="img_ori")

@@ -115,6 +115,14 @@ def test_paste_back_kernel_edge_cases(eng, kind):
 
 
 @pytest.mark.gpu
+def test_paste_back_more_frames_than_one_launch_takes(eng):
+    cases = [_rand_case(200 + s, 40, 40, 64, 80) for s in range(19)]          # > CS_PASTE_MAX_BATCH = 16: chunked by the binding
+    out = _gpu(eng, cases)
+    for i, c in enumerate(cases):
+        assert np.array_equal(out[i], P.paste_back_frame(*c)), i
+
+
+@pytest.mark.gpu
 def test_paste_back_kernel_odd_width_scalar_path(eng):
     """W % 4 != 0 takes the one-pixel-per-thread kernel (the 4-pixel kernel needs word-aligned rows)."""
     cases = [_rand_case(s, 50, 70, 97, 141) for s in (11, 12)]
