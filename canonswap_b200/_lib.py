@@ -25,6 +25,7 @@ CS_OPT_TC_DOUBLE_BUFFER = 8
 CS_OPT_TC_BN_MAX = 9
 CS_OPT_LANES = 10
 CS_OPT_WINOGRAD = 13
+CS_OPT_TC_POSCOMP = 14
 CS_FRAME_MOTION = 8
 MOTION_HEADS = 328
 PASTE_MAX_BATCH = 16

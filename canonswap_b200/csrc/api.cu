@@ -250,11 +250,10 @@ int cs_create(cs_ctx** out, int device, int max_batch, int net_h, int net_w) {
     ctx = new cs_ctx();
     ctx->device = device; ctx->max_batch = max_batch; ctx->net_h = net_h; ctx->net_w = net_w;
     ctx->h = net_h / 4; ctx->w = net_w / 4;
-    size_t sb = sizeof(double) * 2 * (size_t)max_batch * 512;
-    if (sb < 4096) sb = 4096;
+    const size_t sb = sizeof(double) * 2 * (size_t)max_batch * 512 * STATS_MAX_BLOCKS;   // per-block partials (deterministic reduction)
     ctx->stats_scratch = static_cast<double*>(ctx->dmalloc(sb));
     ctx->stats_lane[0] = ctx->stats_scratch;
-    for (int l = 1; l < 4; ++l) ctx->stats_lane[l] = static_cast<double*>(ctx->dmalloc(sb));
+    for (int l = 1; l < 4; ++l) ctx->stats_lane[l] = static_cast<double*>(ctx->dmalloc(sb / 2 + 4096));   // a lane runs <= ceil(B / 2) frames
   } catch (const std::exception& ex) {
     if (ctx) cs_destroy(ctx);
     return fail(nullptr, CS_ERR_CUDA, ex.what());
@@ -285,7 +284,16 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   ctx->drop_graphs();                                       // captured graphs bake the kernel selection in
+  // options that shape the packed weights (accumulator plan, truncation pre-compensation) are fixed by cs_load_weights
+  const bool pack_time = option == CS_OPT_TC_PASSES || option == CS_OPT_TC_SETS || option == CS_OPT_TC_SINGLE_CHAIN ||
+                         option == CS_OPT_TC_DOUBLE_BUFFER || option == CS_OPT_TC_POSCOMP || option == CS_OPT_TC_BN_MAX ||
+                         option == CS_OPT_TC_CHAIN_MAX;
+  if (pack_time && ctx->weights_loaded)
+    return fail(ctx, CS_ERR_STATE, "this option shapes the packed weights: set it before cs_load_weights");
   switch (option) {
+    case CS_OPT_TC_POSCOMP:
+      if (value < 0 || value > 2000) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_POSCOMP: value must be in [0, 2000]");
+      ctx->tc_poscomp = value; return CS_OK;
     case CS_OPT_CONV_IMPL:
       if (value < 0 || value > 1) return fail(ctx, CS_ERR_INVALID, "CS_OPT_CONV_IMPL: value must be 0 or 1");
       ctx->conv_impl = value; return CS_OK;

@@ -130,11 +130,19 @@ struct ConvW {
   // tcgen05 path: B operand [Cout_p][tap][nblk][hi 32 | lo 32] bf16 (K-major rows), N tile BN
   __nv_bfloat16* wtc = nullptr;
   __nv_bfloat16* w3s = nullptr;    // 3x3x3 32->32 depth-stacked packing (conv3s_tc.cu)
+  float w3s_kappa = 0.f;           // truncation pre-compensation folded into w3s
   __nv_bfloat16* w7 = nullptr;     // 7x7x7 depth-stacked packing (conv7_tc.cu), mask conv only
+  float w7_kappa = 0.f;            // truncation pre-compensation folded into w7
   int nblk = 0, Cout_p = 0, BN = 0;
   float wmul = 1.f;                // power of two applied to the packed tcgen05 weights (epilogues multiply by 1 / wmul)
   int zrows = 0;                   // > 0: depth-dependent weights (rows d*zrows .. of wtc belong to depth slice d)
   ConvW* wn = nullptr;             // Winograd F(2x2,3x3) form of a 3x3 conv (wino.cu): 16 x Cout rows, K = Cin, zrows = Cout
+  // accumulator plan of the tcgen05 kernel, fixed when the weights are packed (pack_tc): the packed weights carry the
+  // position-dependent truncation pre-compensation of exactly this MMA issue order (see TcPlan in tc_ptx.cuh)
+  int plan_nsets = 0, plan_chunk = 0, plan_nacc = 0, plan_npass = 3;
+  bool plan_thin = false;
+  float plan_kappa = 0.f;          // pre-compensation per truncation event folded into wtc (0 = none: the epilogue compensates)
+  int phase_shift = 0;             // > 0: phase-form conv of an input nearest-upsampled by 2^phase_shift (pack_phase_conv)
   int taps() const { return KD * KH * KW; }
 };
 
@@ -240,7 +248,8 @@ struct Launcher {            // everything a kernel launch helper needs
   int single_chain = 256;    // convs whose whole MMA chain (hi*hi + corrections) is at most this long use ONE accumulator
   bool winograd = true;      // adaptive convs in Winograd F(2x2,3x3) form (wino.cu)
   bool double_buffer = true; // two TMEM accumulator buffers where they fit (epilogue overlaps the next tile's MMAs)
-  float acc_comp = 170.f;     // accumulate-truncation compensation per chained MMA, in units of 1e-10 (0 = off)
+  float acc_comp = 170.f;     // accumulate-truncation compensation per chained MMA, in units of 1e-10 (0 = off): constant epilogue factor,
+                              // used by the kernels whose weights are not position-compensated at pack time (ConvW::plan_kappa == 0)
   Profiler* prof = nullptr;
   const char* tag = nullptr;  // stage label attached to profiler records
   void count() const { if (counter) ++*counter; }
@@ -274,6 +283,7 @@ inline void check_launch(const char* what) {
 void prep_f32(const Launcher& L, const Prep& p, Act out);                    // out: fp32 (strides from Act)
 void prep_planes(const Launcher& L, const Prep& p, Opd out, const Act* out32);   // split-bf16 planes (+ optional fp32 copy)
 void avg2(const Launcher& L, const float* a, const float* b, float* y, long n);   // y = (a + b) / 2
+constexpr int STATS_MAX_BLOCKS = 256;      // per-sample partial blocks of instance_stats: scratch = [B][256][C <= 512][2] doubles
 void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch);
 void adaptive_blend(const Launcher& L, const float* o2 /*[P,1024]*/, const float* mask /*[P]*/,
                     const float* residual /*[P,512] or null*/, int relu, float* y /*[P,512] or null*/,
@@ -301,7 +311,9 @@ Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out);   // split-
 void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y);
 // conv3s_tc.cu : the 32 -> 32 3x3x3 volume convs (depth-stacked, weights resident in shared memory)
 bool conv3s_supported(const ConvW& w, int H, int W);
-void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& e, Act y);
+void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& e, Act y, float* stats_part = nullptr);
+size_t conv3s_stats_floats(int B, int H, int W);            // per-tile partial sums written when stats_part != null
+void conv3s_stats(const Launcher& L, const float* stats_part, int B, int H, int W, float* mean, float* rstd, float eps);
 // conv7_tc.cu : the 7x7x7 mask conv (depth-stacked, kh-split); scratch holds the 7 partial logit tensors
 bool conv7_supported(const ConvW& w, const Act& out);
 size_t conv7_scratch_floats(const Act& out);

@@ -45,8 +45,10 @@ struct Conv7K {
   float* parts;                    // [7][B,16,H,W,ldo]
   long part_stride;                // elements between partial tensors
   int ldo;                         // channel stride of a partial (24)
-  float acc_scale;                 // round-toward-zero compensation of the hi*hi chain (see conv_tc.cu)
+  float acc_scale;                 // constant round-toward-zero compensation of the hi*hi chain (weights without pre-compensation)
   float out_scale;                 // 1 / ConvW::wmul
+  float kappa;                     // > 0: the packed weights carry the position-dependent pre-compensation (tc_ptx.cuh); the epilogue
+  int ev_slice;                    //      takes back what was assumed for taps in the zero padding. ev_slice = hi*hi events per input slice
 };
 
 template <int CTAS>
@@ -187,7 +189,23 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    // pre-compensated weights: output depths 13..15 have no slices z > 15 (a suffix of the chain: exact take-back), columns
+    // within 3 pixels of the left / right edge lose interleaved kw taps (kappa * fraction * real events / 2 on average)
+    float fw = 0.f;
+    if (k.kappa != 0.f) {
+      const int my_ow = w0 + ((q * 32 + lane) & ((1 << k.lbw) - 1));
+      int vw = 0;
+      for (int kw = 0; kw < 7; ++kw) vw += (my_ow + kw - 3 >= 0 && my_ow + kw - 3 < k.W) ? 1 : 0;
+      fw = 0.5f * k.kappa * (1.f - (float)vw * (1.f / 7.f));
+    }
     for (int dl = 0; dl < C7_GROUP; ++dl) {
+      float msc = k.acc_scale;
+      if (k.kappa != 0.f) {
+        const int d = C7_GROUP * g + dl;
+        const int nz = min(15, d + 3) - max(0, d - 3) + 1;
+        const int zmiss = max(0, d + 3 - 15);
+        msc = 1.f - k.kappa * (float)(zmiss * k.ev_slice) - fw * (float)(nz * k.ev_slice);
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[16], u[16];
@@ -198,10 +216,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
         float4* dst = reinterpret_cast<float4*>(tile + lane * STG_LD + 16 * half);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          dst[j] = make_float4(fmaf(__uint_as_float(v[4 * j]), k.acc_scale, __uint_as_float(u[4 * j])) * k.out_scale,
-                               fmaf(__uint_as_float(v[4 * j + 1]), k.acc_scale, __uint_as_float(u[4 * j + 1])) * k.out_scale,
-                               fmaf(__uint_as_float(v[4 * j + 2]), k.acc_scale, __uint_as_float(u[4 * j + 2])) * k.out_scale,
-                               fmaf(__uint_as_float(v[4 * j + 3]), k.acc_scale, __uint_as_float(u[4 * j + 3])) * k.out_scale);
+          dst[j] = make_float4(fmaf(__uint_as_float(v[4 * j]), msc, __uint_as_float(u[4 * j])) * k.out_scale,
+                               fmaf(__uint_as_float(v[4 * j + 1]), msc, __uint_as_float(u[4 * j + 1])) * k.out_scale,
+                               fmaf(__uint_as_float(v[4 * j + 2]), msc, __uint_as_float(u[4 * j + 2])) * k.out_scale,
+                               fmaf(__uint_as_float(v[4 * j + 3]), msc, __uint_as_float(u[4 * j + 3])) * k.out_scale);
       }
       __syncwarp();
       if (c4 < k.ldo) {
@@ -229,8 +247,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
 
 // w32 [tap = (kd*7+kh)*7+kw][Cin][Cout] fp32 -> rows ((kh*7+kw)*7 + j)*32 + co, j <-> kd = 6 - j (ascending output
 // depth d = z - 3 + j), columns [blk][hi 32 | lo 32]
+// kappa: truncation pre-compensation per event.  Issue order of conv7_tc_kernel for one (kh): z ascending, kw, blk, then
+// hh k0, hh k1 into the main accumulator (corrections go to their own): K step (kd, kw, blk, ks) of the chain of an output
+// depth is followed by (6-kd) slices x ev_slice + (6-kw) x ev_kw + the rest of its kw group.
 __global__ void __launch_bounds__(256) pack_conv7_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ out, int Cin,
-                                                         int Cout, int nblk, float wmul) {
+                                                         int Cout, int nblk, float wmul, float kappa) {
+  const int last_ks = ((Cin - (nblk - 1) * 32) + 15) / 16;
+  const int ev_kw = 2 * (nblk - 1) + last_ks, ev_slice = 7 * ev_kw;
   const long total = 49L * 7 * C7_COUT_P * nblk * 32;         // the 8 pad rows per filter position stay zero (memset)
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int e = (int)(i & 31); long r = i >> 5;
@@ -239,7 +262,9 @@ __global__ void __launch_bounds__(256) pack_conv7_kernel(const float* __restrict
     const int j = (int)(r % 7); const int khw = (int)(r / 7);       // khw = kh*7 + kw
     const int kd = 6 - j, ci = blk * 32 + e;
     const int tap = kd * 49 + khw;
-    const float v = (co < Cout && ci < Cin) ? w32[((long)tap * Cin + ci) * Cout + co] * wmul : 0.f;
+    const int kw = khw % 7;
+    const int rem = (6 - kd) * ev_slice + (6 - kw) * ev_kw + (ev_kw - (2 * blk + (e >> 4)));
+    const float v = (co < Cout && ci < Cin) ? w32[((long)tap * Cin + ci) * Cout + co] * wmul * (1.0f + kappa * (float)rem) : 0.f;
     __nv_bfloat16 hi, lo;
     split_operand(v, hi, lo);
     const long row = (long)khw * C7_BROWS + j * C7_COUT_P + co;
@@ -287,7 +312,8 @@ void pack_conv7(cs_ctx* ctx, ConvW& w) {
   const size_t n = (size_t)49 * C7_BROWS * nblk * 64;
   if (!w.w7) w.w7 = static_cast<__nv_bfloat16*>(ctx->dmalloc(n * sizeof(__nv_bfloat16)));
   CS_CUDA(cudaMemset(w.w7, 0, n * sizeof(__nv_bfloat16)));
-  pack_conv7_kernel<<<148 * 8, 256>>>(w.w32, w.w7, w.Cin, w.Cout, nblk, w.wmul);
+  w.w7_kappa = (float)ctx->tc_poscomp * 1e-10f;
+  pack_conv7_kernel<<<148 * 8, 256>>>(w.w32, w.w7, w.Cin, w.Cout, nblk, w.wmul, w.w7_kappa);
   check_launch("pack_conv7");
 }
 
@@ -311,7 +337,9 @@ void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* s
   k.parts = scratch;
   k.part_stride = (long)x.B * 16 * x.H * x.W * k.ldo;
   k.out_scale = 1.0f / w.wmul;
-  k.acc_scale = 1.0f + L.acc_comp * 1e-10f * (float)(7 * 7 * (2 * (x.nblk - 1) + k.last_ksteps));   // chain: 7 z x 7 kw x K steps
+  k.ev_slice = 7 * (2 * (x.nblk - 1) + k.last_ksteps);
+  k.kappa = w.w7_kappa;
+  k.acc_scale = w.w7_kappa != 0.f ? 1.0f : 1.0f + L.acc_comp * 1e-10f * (float)(7 * k.ev_slice);   // chain: 7 z x 7 kw x K steps
 
   const unsigned gx = (unsigned)(k.ntw * k.nth * x.B);
   const bool pair = L.pair && (gx % 2 == 0);

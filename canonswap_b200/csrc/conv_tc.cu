@@ -41,6 +41,8 @@ struct ConvTcK {
   int nacc;                        // accumulator buffers (of nsets * BN columns): 2 = the epilogue of tile i overlaps the MMAs of tile i+1
   int m_units, n_tiles;            // persistent tile loop: units of CTAS consecutive M tiles x N tiles (unit u -> m = u % m_units, n = u / m_units)
   float acc_scale;                 // compensation of the tensor core's round-toward-zero accumulation (see host code)
+  float kappa;                     // > 0: the weights carry the position-dependent pre-compensation; the epilogue takes back what it
+  int Din;                         //      assumed for filter taps that fall into the zero padding (no products, no truncation)
   float out_scale;                 // 1 / ConvW::wmul
   int zrows;                       // > 0: depth-dependent weights, B rows of depth slice d start at d * zrows
   const float* bias; int act; float slope;
@@ -266,6 +268,41 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
       }
       mu[i] = (k.mult && valid) ? k.mult[(((long)ob * k.D + od) * k.H + oh) * k.W + ow] : 1.f;
     }
+    // Border rows: the packed pre-compensation assumes that every K step is followed by the full chain of truncation
+    // events, but taps in the zero padding add exact zeros (no truncation).  Depth padding removes a SUFFIX of the tap
+    // order (kd is the slowest index): a uniform over-compensation of kappa * (zero events of the set), taken back exactly;
+    // h / w padding removes interleaved taps: kappa * fraction * (real events) / 2 on average.
+    int b_it0 = 0x7fffffff, b_lead = 0; float b_frac = 0.f;
+    const bool bcomp = k.kappa != 0.f && taps > 1 && k.ph_s == 0;
+    if (bcomp) {
+      int r = q * 32 + lane;
+      const int ow = w0 + (r & ((1 << k.lbw) - 1)); r >>= k.lbw;
+      const int oh = h0 + (r & ((1 << k.lbh) - 1)); r >>= k.lbh;
+      const int od = d0 + (r & ((1 << k.lbd) - 1));
+      int vh = 0, vw = 0;
+      for (int kh = 0; kh < k.KH; ++kh) vh += (oh + kh - k.PH >= 0 && oh + kh - k.PH < k.H) ? 1 : 0;
+      for (int kw = 0; kw < k.KW; ++kw) vw += (ow + kw - k.PW >= 0 && ow + kw - k.PW < k.W) ? 1 : 0;
+      b_frac = 1.f - (float)(vh * vw) / (float)(k.KH * k.KW);
+      if (k.KD > 1 && k.PD > 0) {
+        const int kd0 = k.Din - od + k.PD;                   // first depth tap beyond the last input slice
+        if (kd0 < k.KD) b_it0 = (kd0 < 0 ? 0 : kd0) * k.KH * k.KW * k.nblk;
+        const int lead = k.PD - od;                          // depth taps before the first input slice
+        if (lead > 0) b_lead = lead * k.KH * k.KW * k.nblk;
+      }
+    }
+    const int niter_all = taps * k.nblk;
+    auto set_factor = [&](int set_idx) -> float {            // set_idx: hi*hi set (0-based); single accumulator: the whole chain
+      if (!bcomp) return 1.f;
+      const int a = k.nsets == 1 ? 0 : set_idx * k.chunk;
+      int e = k.nsets == 1 ? niter_all : a + k.chunk;
+      if (e > niter_all) e = niter_all;
+      const int mul = k.nsets == 1 ? k.npass : 1;
+      const int z0 = b_it0 > a ? (b_it0 < e ? b_it0 : e) : a;         // zero suffix [z0, e)
+      const int r0 = b_lead > a ? (b_lead < e ? b_lead : e) : a;      // real iterations [r0, z0)
+      const int zev = (tc_events_upto(e, k.nblk, k.last_ksteps) - tc_events_upto(z0, k.nblk, k.last_ksteps)) * mul;
+      const int rev = z0 > r0 ? (tc_events_upto(z0, k.nblk, k.last_ksteps) - tc_events_upto(r0, k.nblk, k.last_ksteps)) * mul : 0;
+      return 1.f - k.kappa * ((float)zev + 0.5f * b_frac * (float)rev);
+    };
     if (RES && eg == 0) {                                   // pull the residual tile towards L2 while the MMAs run
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -312,12 +349,18 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
           const uint32_t tcol = trow + (uint32_t)(c0 + 16 * half);
           tc_ld16(tcol + (uint32_t)(corr * k.BN), v);
           tc_ld_wait();
+          if (bcomp) {
+            const float f0 = set_factor(0);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * f0);
+          }
           for (int st = corr + 1; st < k.nsets; ++st) {     // hi*hi sets in K order ...
             uint32_t u[16];
             tc_ld16(tcol + (uint32_t)(st * k.BN), u);
             tc_ld_wait();
+            const float fs = set_factor(st - corr);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(u[j]), fs, __uint_as_float(v[j])));
           }
           if (corr) {                                       // ... then the small correction terms
             uint32_t u[16];
@@ -471,8 +514,15 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------
 // weight packing: w32 [tap][Cin][Cout] fp32 -> [Cout_p][tap][nblk][hi 32 | lo 32] bf16
 // ------------------------------------------------------------------------------------------
+struct PackPlan {                   // issue order of the kernel that will consume the packed rows (see TcPlan, tc_ptx.cuh)
+  int nsets, chunk, npass, last_ksteps;
+  float kappa;                      // pre-compensation per truncation event (0 = none)
+  int ph_s, rows_per_phase;         // phase mode: rows [p * rows_per_phase, ..) belong to phase p, which walks the taps in tapmask[p]
+  unsigned short tapmask[16];
+};
+
 __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ out, int taps,
-                                                      int Cin, int Cout, int Cout_p, int nblk, float wmul) {
+                                                      int Cin, int Cout, int Cout_p, int nblk, float wmul, PackPlan pp) {
   const long rowlen = (long)taps * nblk * 64;
   const long total = (long)Cout_p * taps * nblk * 32;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -481,6 +531,16 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
     int tap = (int)(r % taps); int co = (int)(r / taps);
     int ci = blk * 32 + j;
     float v = (co < Cout && ci < Cin) ? w32[((long)tap * Cin + ci) * Cout + co] * wmul : 0.f;
+    if (pp.kappa != 0.f) {
+      int it = tap * nblk + blk, niter = taps * nblk;
+      if (pp.ph_s) {                                          // ordinal of the tap among the taps this phase walks
+        const unsigned m = pp.tapmask[co / pp.rows_per_phase];
+        it = __popc(m & ((1u << tap) - 1u)) * nblk + blk;
+        niter = __popc(m) * nblk;
+      }
+      const int rem = tc_remaining_events(pp.nsets, pp.chunk, pp.npass, niter, nblk, pp.last_ksteps, it, j >> 4);
+      v *= 1.0f + pp.kappa * (float)rem;
+    }
     __nv_bfloat16 hi, lo;
     split_operand(v, hi, lo);
     long o = (long)co * rowlen + ((long)tap * nblk + blk) * 64 + j;
@@ -505,7 +565,58 @@ int pick_bn(int Cout) {
 bool g_attr_set[64] = {};
 constexpr int MAX_DYN_SMEM = 220 * 1024;
 
+// phase-mode tap masks: output row Y = y*f + a reads input rows floor((Y + dy) / f): a = 0 -> {y-1: dy=-1, y: dy=0,+1};
+// a = f-1 -> {y: dy=-1,0, y+1: dy=+1}; else only row y.  The packed weights hold the per-phase tap sums; taps outside the
+// mask are zero and skipped.
+void phase_tapmasks(int ps, unsigned short* out) {
+  const int f = 1 << ps;
+  for (int a = 0; a < f; ++a)
+    for (int b = 0; b < f; ++b) {
+      unsigned rows = 2u | (a == 0 ? 1u : 0u) | (a == f - 1 ? 4u : 0u), cols = 2u | (b == 0 ? 1u : 0u) | (b == f - 1 ? 4u : 0u);
+      unsigned m = 0;
+      for (int ty = 0; ty < 3; ++ty)
+        for (int tx = 0; tx < 3; ++tx) if (((rows >> ty) & 1u) && ((cols >> tx) & 1u)) m |= 1u << (ty * 3 + tx);
+      out[a * f + b] = (unsigned short)m;
+    }
+}
+
 }  // namespace
+
+namespace tc {
+// Accumulator sets: chains of <= ~256 MMAs per TMEM accumulator.  A short K (whole chain <= single_chain MMAs) runs in ONE
+// accumulator; otherwise one set for the correction products + hi*hi sets of <= ~256 MMAs.  If two such buffers fit into the
+// TMEM columns the accumulators are double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1.  Thin N tiles
+// (BN <= 64) run two CTAs per SM with half of the TMEM each.
+TcPlan tc_make_plan(int BN, int niter, int npass, int single_chain, int max_sets, bool double_buffer, int phase_shift) {
+  TcPlan p;
+  p.npass = npass;
+  const int steps_main = niter * 2;
+  // thin N tiles (short MMAs: the per-stage issue overhead dominates) run as TWO co-resident CTAs per SM with half of the
+  // TMEM each -- unless the chain is so long that it needs the whole TMEM for accumulator sets
+  const bool thin = BN <= 64 && (steps_main + 2) / 3 <= 256;
+  p.thin = thin;
+  int want = (steps_main * npass <= single_chain) ? 1 : 1 + (steps_main + 255) / 256;
+  if (npass == 1 && want > 1) want -= 1;
+  if (max_sets > 0 && want > max_sets) want = max_sets;
+  const int tmem_budget = thin ? 256 : 512;
+  while (want > 1 && BN * want > tmem_budget) --want;
+  p.nacc = (double_buffer && 2 * BN * want <= tmem_budget) ? 2 : 1;
+  const int per_buf = tmem_budget / p.nacc;
+  int nsets = want == 1 ? 1 : per_buf / BN;               // spare columns shorten the chains further
+  if (nsets > 16) nsets = 16;
+  if (max_sets > 0 && nsets > max_sets) nsets = max_sets;
+  if (nsets < 1) nsets = 1;
+  const int corr = (npass > 1 && nsets > 1) ? 1 : 0;
+  int nmain = nsets - corr;
+  if (nmain > niter) nmain = niter;
+  const int chunk = (niter + nmain - 1) / nmain;          // K iterations per hi*hi set
+  nmain = (niter + chunk - 1) / chunk;                    // sets actually written
+  if (phase_shift) nmain = 1;
+  p.nsets = corr + nmain;
+  p.chunk = phase_shift ? (1 << 30) : chunk;
+  return p;
+}
+}  // namespace tc
 
 namespace tc {
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
@@ -559,23 +670,37 @@ void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream) {
   int BN = pick_bn(w.Cout);
   // Accumulator-set policy.  The hi*hi products of a tile accumulate in 512 / BN - 1 TMEM sets (one more holds the small
   // correction products); every MMA added into a set truncates it (round toward zero), so the error grows with the chain
-  // length per set.  Halve the N tile (down to 128) until a chain is at most `chain_max` MMAs: BN = 256 leaves one hi*hi set
-  // (a 3x3 conv over 512 channels would chain 288 MMAs), BN = 128 three (96 each).  Measured end to end (max|d| vs the
-  // oracle, 1e-3 bar; fp32-vs-fp32 reordering noise alone is 1.2e-4 / 4.9e-4 .. 6.9e-4 at 512 / 1024 px): 320 -> 256 takes
-  // 5.0e-4 -> 3.3e-4 at 512 px and 1.0e-3 -> 8.6e-4 at 1024 px at the same step time (BN = 128 pairs tile the SMs better).
+  // length per set (the first-order loss is pre-compensated in the packed weights, what remains grows with the chain too:
+  // tests/test_gpu_configs.py).  Halve the N tile (down to 64) until a chain is at most `chain_max` MMAs: BN = 256 leaves
+  // one hi*hi set (a 3x3 conv over 512 channels would chain 288 MMAs), BN = 128 three (96 each), BN = 64 seven (the deep
+  // hourglass levels, K up to 27 x 1024: 247 each; their M is tiny, so the narrow tile costs nothing and fills more SMs).
   {
     const int chain_max = ctx->tc_chain_max > 0 ? ctx->tc_chain_max : 256;
     const int steps_main = w.taps() * nblk * 2;
-    while (BN > 128 && (steps_main + (512 / BN - 1) - 1) / (512 / BN - 1) > chain_max) BN = round_up(BN / 2, 16);
+    while (BN > 64 && (steps_main + (512 / BN - 1) - 1) / (512 / BN - 1) > chain_max) BN = round_up(BN / 2, 16);
   }
   if (ctx->tc_bn_max > 0 && BN > ctx->tc_bn_max) BN = ctx->tc_bn_max;
+  if (w.phase_shift > 0) {                                  // one N tile per output phase (pack_phase_conv): Cout = 4^ps * BN rows
+    BN = w.Cout >> (2 * w.phase_shift);
+    CS_REQUIRE(BN % 16 == 0 && BN <= 256 && w.taps() == 9, CS_ERR_WEIGHTS, "pack_tc: bad phase-form conv");
+  }
   const int Cout_p = round_up(w.Cout, BN);
   const size_t n = (size_t)Cout_p * w.taps() * nblk * 64;
   if (!w.wtc) w.wtc = static_cast<__nv_bfloat16*>(ctx->dmalloc(n * sizeof(__nv_bfloat16)));
   w.nblk = nblk; w.BN = BN; w.Cout_p = Cout_p;
+  // the accumulator plan is fixed here: the packed rows carry the truncation pre-compensation of this issue order
+  const int npass = ctx->tc_passes >= 1 && ctx->tc_passes <= 3 ? ctx->tc_passes : 3;
+  const TcPlan plan = tc_make_plan(BN, w.taps() * nblk, npass, ctx->tc_single_chain, ctx->tc_sets, ctx->tc_dbuf != 0, w.phase_shift);
+  w.plan_nsets = plan.nsets; w.plan_chunk = plan.chunk; w.plan_nacc = plan.nacc; w.plan_npass = npass; w.plan_thin = plan.thin;
+  w.plan_kappa = (float)ctx->tc_poscomp * 1e-10f;
+  PackPlan pp{};
+  pp.nsets = plan.nsets; pp.chunk = plan.chunk; pp.npass = npass; pp.kappa = w.plan_kappa;
+  pp.last_ksteps = ((w.Cin - (nblk - 1) * 32) + 15) / 16;
+  pp.ph_s = w.phase_shift; pp.rows_per_phase = BN;
+  if (w.phase_shift) phase_tapmasks(w.phase_shift, pp.tapmask);
   long total = (long)Cout_p * w.taps() * nblk * 32;
   long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
-  pack_tc_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w.w32, w.wtc, w.taps(), w.Cin, w.Cout, Cout_p, nblk, w.wmul);
+  pack_tc_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w.w32, w.wtc, w.taps(), w.Cin, w.Cout, Cout_p, nblk, w.wmul, pp);
   check_launch("pack_tc");
 }
 
@@ -613,20 +738,8 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   k.rowA = w.nblk * 64;
   k.BN = w.BN; k.Cout = w.Cout; k.zrows = w.zrows;
   k.ph_s = ps;
-  if (ps) {
-    // output row Y = y*f + a reads input rows floor((Y + dy) / f): a = 0 -> {y-1: dy=-1, y: dy=0,+1}; a = f-1 -> {y: dy=-1,0, y+1: dy=+1};
-    // else only row y.  The packed weights hold the per-phase tap sums; taps outside the mask are zero and skipped.
-    const int f = 1 << ps;
-    for (int a = 0; a < f; ++a)
-      for (int b = 0; b < f; ++b) {
-        unsigned rows = 2u | (a == 0 ? 1u : 0u) | (a == f - 1 ? 4u : 0u), cols = 2u | (b == 0 ? 1u : 0u) | (b == f - 1 ? 4u : 0u);
-        unsigned m = 0;
-        for (int ty = 0; ty < 3; ++ty)
-          for (int tx = 0; tx < 3; ++tx) if (((rows >> ty) & 1u) && ((cols >> tx) & 1u)) m |= 1u << (ty * 3 + tx);
-        k.tapmask[a * f + b] = (unsigned short)m;
-      }
-  }
-  k.npass = L.npass >= 1 && L.npass <= 3 ? L.npass : 3;
+  if (ps) phase_tapmasks(ps, k.tapmask);
+  k.npass = w.plan_nsets > 0 ? w.plan_npass : (L.npass >= 1 && L.npass <= 3 ? L.npass : 3);
   k.bias = w.bias; k.act = e.act; k.slope = e.slope;
   k.res = e.residual; k.rb = e.rs_b; k.rd = e.rs_d; k.rh = e.rs_h; k.rw = e.rs_w;
   k.mult = e.mult;
@@ -658,38 +771,25 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   const int stage_bytes = A_TILE_BYTES + (pair ? k.BN / 2 : k.BN) * 128;
   // thin N tiles (short MMAs: the per-stage issue overhead dominates) run as TWO co-resident CTAs per SM, each with half of the
   // shared memory and of the TMEM columns
-  const bool thin = k.BN <= 64;
-  // accumulator sets: chains of <= ~256 MMAs per TMEM accumulator.  A short K (whole chain <= 256 MMAs) runs in ONE
-  // accumulator; otherwise one set for the correction products + hi*hi sets of <= ~256 MMAs.  If two such buffers fit
-  // into the 512 TMEM columns the accumulators are double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1.
+  const bool thin = w.plan_nsets > 0 ? w.plan_thin : (k.BN <= 64 && (niter * 2 + 2) / 3 <= 256);
+  // accumulator plan: the one the weights were packed for (pack_tc); hand-packed weights (no plan) get the default policy
   {
-    const int steps_main = niter * 2;
-    int want = (steps_main * k.npass <= L.single_chain) ? 1 : 1 + (steps_main + 255) / 256;
-    if (k.npass == 1 && want > 1) want -= 1;
-    if (L.max_sets > 0 && want > L.max_sets) want = L.max_sets;
-    const int tmem_budget = thin ? 256 : 512;
-    while (want > 1 && k.BN * want > tmem_budget) --want;
-    k.nacc = (L.double_buffer && 2 * k.BN * want <= tmem_budget) ? 2 : 1;
-    const int per_buf = tmem_budget / k.nacc;
-    int nsets = want == 1 ? 1 : per_buf / k.BN;               // spare columns shorten the chains further
-    if (nsets > 16) nsets = 16;
-    if (L.max_sets > 0 && nsets > L.max_sets) nsets = L.max_sets;
-    if (nsets < 1) nsets = 1;
-    const int corr = (k.npass > 1 && nsets > 1) ? 1 : 0;
-    int nmain = nsets - corr;
-    if (nmain > niter) nmain = niter;
-    const int chunk = (niter + nmain - 1) / nmain;          // K iterations per hi*hi set
-    nmain = (niter + chunk - 1) / chunk;                    // sets actually written
-    if (ps) { nmain = 1; }
-    k.nsets = corr + nmain; k.chunk = ps ? (1 << 30) : chunk;
+    TcPlan plan;
+    if (w.plan_nsets > 0) { plan.nsets = w.plan_nsets; plan.chunk = w.plan_chunk; plan.nacc = w.plan_nacc; plan.npass = w.plan_npass; plan.thin = w.plan_thin; }
+    else plan = tc_make_plan(k.BN, niter, k.npass, L.single_chain, L.max_sets, L.double_buffer, ps);
+    CS_REQUIRE(!ps || w.phase_shift == ps, CS_ERR_INVALID, "conv_tc: phase-mode launch of a conv not packed in phase form");
+    k.nsets = plan.nsets; k.chunk = plan.chunk; k.nacc = plan.nacc;
+    const int corr = (k.npass > 1 && k.nsets > 1) ? 1 : 0;
     int tcols = 32;
     while (tcols < k.nacc * k.nsets * k.BN) tcols <<= 1;
     k.tcols = tcols;
-    // The tensor core truncates (rounds toward zero) when it adds an MMA into the fp32 accumulator: measured on B200, a
-    // chain of L MMAs loses ~1.2e-8 * L of the accumulated magnitude, systematically (mean signed error, tools/tc_check.py).
-    // Errors of that sign add linearly over the ~75 stacked convs, so the epilogue scales the hi*hi sum back.
-    const int chain = chunk * 2 * (corr ? 1 : k.npass);
-    k.acc_scale = 1.0f + L.acc_comp * 1e-10f * (float)chain;
+    // The tensor core truncates (rounds toward zero) when it adds an MMA into the fp32 accumulator.  Weights packed with the
+    // position-dependent pre-compensation (ConvW::plan_kappa, tc_ptx.cuh) need no epilogue factor; otherwise the epilogue
+    // scales the hi*hi sum by 1 + c * chain (the mean loss of a chain, CS_OPT_TC_COMP).
+    const int per_set = k.chunk < niter ? k.chunk : niter;
+    const int chain = per_set * 2 * (corr ? 1 : k.npass);
+    k.acc_scale = w.plan_kappa != 0.f ? 1.0f : 1.0f + L.acc_comp * 1e-10f * (float)chain;
+    k.kappa = w.plan_kappa; k.Din = x.D;
     k.out_scale = 1.0f / w.wmul;
   }
   const int egroups = k.BN > 64 ? 2 : 1;                   // 8 epilogue warps on wide tiles

@@ -104,7 +104,7 @@ struct cs_ctx {
   int device = 0, max_batch = 1, net_h = 0, net_w = 0, h = 0, w = 0;
   std::string err;
   bool weights_loaded = false, identity_set = false;
-  int conv_impl = 0, use_graph = 0, tc_passes = 3, tc_sets = 0, tc_comp = 170, tc_pair = 1, tc_stacked3 = 1, tc_dbuf = 1, winograd = 1, tc_chain_max = 0, tc_single_chain = 256, tc_bn_max = 0;
+  int conv_impl = 0, use_graph = 0, tc_passes = 3, tc_sets = 0, tc_comp = 170, tc_poscomp = 330, tc_pair = 1, tc_stacked3 = 1, tc_dbuf = 1, winograd = 1, tc_chain_max = 0, tc_single_chain = 256, tc_bn_max = 0;
   int64_t launches = 0;
   std::vector<void*> owned;        // device allocations owned by the ctx
   size_t owned_bytes = 0;
@@ -113,7 +113,7 @@ struct cs_ctx {
   cs::MotionW M;
   float* se_scratch = nullptr; size_t se_cap = 0;   // SoftErosion scratch (grown on demand, outside the hot path's arena)
   std::vector<std::unique_ptr<cs::ConvW>> wino_convs;   // Winograd forms of static convs (ConvW::wn)
-  double* stats_scratch = nullptr; // [max_batch*512*2] double
+  double* stats_scratch = nullptr; // [max_batch][STATS_MAX_BLOCKS][512][2] double: per-block partial sums of instance_stats
   double* stats_lane[4] = {};      // per-lane statistics scratch (CS_OPT_LANES); [0] == stats_scratch
   int lanes = 2;                   // CS_OPT_LANES: a graph-captured cs_frame runs as this many concurrent sub-batches
   cudaStream_t lane_stream[4] = {}; // [0] unused (the capture stream itself)
@@ -153,7 +153,7 @@ struct Net {                 // per-call view
 void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n);
 void set_identity(cs_ctx* ctx, const float* id_dev, cudaStream_t stream);
 ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt /*[Cout][Cin][taps]*/, const std::vector<float>* bias,
-                     int Cout, int Cin, int KD, int KH, int KW);
+                     int Cout, int Cin, int KD, int KH, int KW, int phase_shift = 0);
 float weight_prescale(const float* w, size_t n);             // weights.cu
 void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream);
 void pack_conv3s(cs_ctx* ctx, ConvW& w);                     // conv3s_tc.cu

@@ -246,9 +246,11 @@ __global__ void stats_finalize_kernel(const double* __restrict__ acc, float* __r
 }
 
 // dense [B,S,C] fp32 (C a multiple of 4, C <= 1024): a block takes `rows` consecutive positions, thread = (row group,
-// float4 of channels); fp32 partials over <= rows/groups positions, smem reduce over row groups, fp64 atomics.
+// float4 of channels); fp32 partials over <= rows/groups positions, smem reduce over row groups in a fixed order, one fp64
+// partial per (sample, block, channel) -- summed in block order by stats_finalize_blocks_kernel.  No atomics: the result is
+// bit-reproducible and, because the block size depends on S only, independent of the batch the sample is part of.
 __global__ void __launch_bounds__(256) stats_dense_kernel(const float* __restrict__ x, long S, int C, int rows,
-                                                          double* __restrict__ acc) {
+                                                          double* __restrict__ part /*[B][gridDim.x][C][2]*/) {
   __shared__ float4 red1[256], red2[256];
   const int b = blockIdx.y;
   const int C4 = C >> 2;
@@ -272,10 +274,25 @@ __global__ void __launch_bounds__(256) stats_dense_kernel(const float* __restric
       a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
       q[0] += w.x; q[1] += w.y; q[2] += w.z; q[3] += w.w;
     }
-    double* o = acc + ((long)b * C + c4 * 4) * 2;
+    double* o = part + (((long)b * gridDim.x + blockIdx.x) * C + c4 * 4) * 2;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { atomicAdd(o + 2 * j, a[j]); atomicAdd(o + 2 * j + 1, q[j]); }
+    for (int j = 0; j < 4; ++j) { o[2 * j] = a[j]; o[2 * j + 1] = q[j]; }
   }
+}
+
+__global__ void stats_finalize_blocks_kernel(const double* __restrict__ part, int nblocks, int C, float* __restrict__ mean,
+                                             float* __restrict__ rstd, int n /*B*C*/, double inv_count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = i / C, c = i % C;
+  const double* p = part + ((long)b * nblocks * C + c) * 2;
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = 0; t < nblocks; ++t) { s1 += p[(long)t * C * 2]; s2 += p[(long)t * C * 2 + 1]; }
+  const double m = s1 * inv_count;
+  double var = s2 * inv_count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch) {
@@ -284,19 +301,25 @@ void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, f
   int C = x.C;
   long S = (long)x.D * x.H * x.W;
   ProfScope ps(L, PK_STATS, 0.0, (double)x.B * S * C * 4.0, "stats");
-  CS_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * x.B * C, L.stream));
   const int C4 = C >> 2;
   const bool pow2 = C4 > 0 && (C4 & (C4 - 1)) == 0;
+  const int n = x.B * C;
   if ((C & 3) == 0 && pow2 && C4 <= 256 && x.sb == S * C && ((uintptr_t)x.p & 15) == 0) {
     // the tensor is dense per sample with the channel fastest (2-D activations and the [h,w,16,32] volume alike)
     const int groups = 256 / C4;
-    long rows = (x.B * S + 2047) / 2048;          // ~2048 blocks in flight
+    long rows = (S + STATS_MAX_BLOCKS - 1) / STATS_MAX_BLOCKS;   // <= STATS_MAX_BLOCKS blocks per sample, a function of S only
     if (rows < groups) rows = groups;
-    if (rows > 64L * groups) rows = 64L * groups; // <= 64 fp32 additions per partial
-    dim3 grid((unsigned)((S + rows - 1) / rows), x.B);
+    const long nblocks = (S + rows - 1) / rows;
+    CS_REQUIRE(nblocks <= STATS_MAX_BLOCKS && C <= 512, -1, "instance_stats: scratch too small");
+    dim3 grid((unsigned)nblocks, x.B);
     stats_dense_kernel<<<grid, 256, 0, L.stream>>>(x.p, S, C, (int)rows, scratch);
     check_launch("stats_dense");
-  } else {
+    stats_finalize_blocks_kernel<<<(n + 127) / 128, 128, 0, L.stream>>>(scratch, (int)nblocks, C, mean, rstd, n, 1.0 / (double)S, eps);
+    check_launch("stats_finalize");
+    return;
+  }
+  CS_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * x.B * C, L.stream));
+  {
     int CT = 1;
     while (CT * 2 <= C && CT * 2 <= 256) CT *= 2;
     // when C is not a multiple of CT the strided loop `c = cl; c < C; c += CT` has a non-uniform trip
@@ -308,7 +331,6 @@ void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, f
     stats_partial_kernel<<<grid, 256, 0, L.stream>>>(x.p, x.sb, x.sd, x.sh, x.sw, x.D, x.H, x.W, C, CT, chunk, scratch);
     check_launch("stats_partial");
   }
-  int n = x.B * C;
   stats_finalize_kernel<<<(n + 127) / 128, 128, 0, L.stream>>>(scratch, mean, rstd, n, 1.0 / (double)S, eps);
   check_launch("stats_finalize");
 }

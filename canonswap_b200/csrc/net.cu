@@ -212,6 +212,44 @@ static void gn_resblock3d(Net& n, const GnResBlockW& w, float* vol, int B, int h
   n.A->reset(m);
 }
 
+// A run of ResBlock3D_stage3_leak blocks (util.py:528-544) on the depth-stacked tcgen05 kernel: the conv epilogues write the
+// per-tile partial sums of their output, so the GroupNorm statistics need no extra pass over the tensor (and are
+// deterministic / independent of the batch size); the block's last element-wise pass lrelu(gn2(.) + x) also writes the next
+// block's conv1 operand.
+static void gn_resblock3d_chain_tc(Net& n, const GnResBlockW* w, int nb, float* vol, int B, int h, int wd) {
+  size_t m = n.A->mark();
+  Act x = vol_as_3d(vol, B, h, wd);
+  Act t1 = vol_as_3d(n.A->f32((size_t)B * h * wd * 512), B, h, wd);
+  Act t2 = vol_as_3d(n.A->f32((size_t)B * h * wd * 512), B, h, wd);
+  float* mean = n.A->f32((size_t)B * 32);
+  float* rstd = n.A->f32((size_t)B * 32);
+  float* part = n.A->f32(conv3s_stats_floats(B, h, wd));
+  Opd a = conv_tc_alloc_operand(*n.A, w[0].conv1, x);
+  Opd b = conv_tc_alloc_operand(*n.A, w[0].conv2, x);
+  prep_planes(n.L, prep_of(x), a, nullptr);
+  for (int i = 0; i < nb; ++i) {
+    conv3s_tc(n.L, a, w[i].conv1, Epilogue(), t1, part);
+    conv3s_stats(n.L, part, B, h, wd, mean, rstd, 1e-5f);
+    Prep p = prep_of(t1);
+    p.norm = NORM_STATS_BC; p.mean = mean; p.rstd = rstd; p.scale = w[i].gn1.scale; p.shift = w[i].gn1.shift;
+    p.act = ACT_LRELU; p.slope = 0.01f;
+    prep_planes(n.L, p, b, nullptr);
+    conv3s_tc(n.L, b, w[i].conv2, Epilogue(), t2, part);
+    conv3s_stats(n.L, part, B, h, wd, mean, rstd, 1e-5f);
+    Prep q = prep_of(t2);
+    q.norm = NORM_STATS_BC; q.mean = mean; q.rstd = rstd; q.scale = w[i].gn2.scale; q.shift = w[i].gn2.shift;
+    q.add = x; q.act = ACT_LRELU; q.slope = 0.01f;
+    if (i + 1 < nb) prep_planes(n.L, q, a, &x);          // x = lrelu(gn2(.) + x) (element-wise, safe in place) + next operand
+    else prep_f32(n.L, q, x);
+  }
+  n.A->reset(m);
+}
+
+static void gn_resblock3d_run(Net& n, const GnResBlockW* w, int nb, float* vol, int B, int h, int wd) {
+  if (n.L.conv_impl != 1 && n.L.stacked3 && conv3s_supported(w[0].conv1, h, wd)) gn_resblock3d_chain_tc(n, w, nb, vol, B, h, wd);
+  else for (int i = 0; i < nb; ++i) gn_resblock3d(n, w[i], vol, B, h, wd);
+}
+
 // ------------------------------------------------------------------------------------------
 // F : AppearanceFeatureExtractor.forward, reference appearance_feature_extractor.py:38-48
 // ------------------------------------------------------------------------------------------
@@ -444,7 +482,7 @@ void run_refine(Net& n, const float* vol_in, int B, float* vol_out) {
   const int h = n.ctx->h, w = n.ctx->w;
   if (vol_out != vol_in && !n.L.dry)
     CS_CUDA(cudaMemcpyAsync(vol_out, vol_in, (size_t)B * h * w * 512 * sizeof(float), cudaMemcpyDeviceToDevice, n.L.stream));
-  for (int i = 0; i < 3; ++i) gn_resblock3d(n, W.r_gn1[i], vol_out, B, h, w);
+  gn_resblock3d_run(n, W.r_gn1, 3, vol_out, B, h, w);
   {
     Act x2 = vol_as_2d(vol_out, B, h, w);
     if (wino_ok(n.L, W.r_res2[0].conv1, h, w) && wino_ok(n.L, W.r_res2[0].conv2, h, w)) {
@@ -465,7 +503,7 @@ void run_refine(Net& n, const float* vol_in, int B, float* vol_out) {
       for (int i = 0; i < 3; ++i) resblock2d(n, W.r_res2[i], vol_out, B, h, w);
     }
   }
-  for (int i = 0; i < 3; ++i) gn_resblock3d(n, W.r_gn3[i], vol_out, B, h, w);
+  gn_resblock3d_run(n, W.r_gn3, 3, vol_out, B, h, w);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -200,6 +200,36 @@ constexpr int A_TILE_BYTES = 128 * 128;
 constexpr int STG_LD = 36;                                  // floats per staged row (32 + pad, 16-B aligned)
 constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;              // one 32x32 fp32 staging tile per epilogue warp
 
+// ------------------------------------------------------------------------------------------
+// Accumulator plan + position-dependent truncation pre-compensation
+// ------------------------------------------------------------------------------------------
+// The tensor core adds every MMA into the fp32 TMEM accumulator with truncation toward zero: event t loses ~kappa * acc_t,
+// so an element loses kappa * sum_t acc_t = kappa * sum_s rem(s) * m_s, where m_s is the contribution of K step s and
+// rem(s) the number of truncation events from its entry to the end of the chain.  That is a LINEAR functional of the
+// products whose coefficients depend only on the issue order -- so the weights of K step s are packed pre-multiplied by
+// (1 + kappa * rem(s)) and the loss cancels to first order per element, at no run-time cost (measured on B200,
+// tools/poscomp_probe.py: per-conv rms error 2.5 - 2.8x below the constant epilogue factor it replaces; kappa = 3.3e-8).
+// The plan (sets, chunk) therefore belongs to the packed weights: pack_tc fixes it, conv_tc launches with it.
+struct TcPlan {
+  int nsets = 1;      // TMEM accumulator sets of BN columns per buffer (set 0 = corrections when nsets > 1 and npass > 1)
+  int chunk = 1 << 30;// K iterations (32-channel blocks) per hi*hi set
+  int nacc = 1;       // accumulator buffers (2 = epilogue of tile i overlaps the MMAs of tile i+1)
+  int npass = 3;
+  bool thin = false;   // two co-resident CTAs per SM, half of the TMEM columns each
+};
+// hi*hi events issued in iterations [0, i) of a tap-major / block-minor walk (the last block of a tap may hold one K step)
+__host__ __device__ inline int tc_events_upto(int i, int nblk, int last_ksteps) { return 2 * i - (i / nblk) * (2 - last_ksteps); }
+// truncation events from the entry of (iteration it, K step ks) into its accumulator to the end of that accumulator's chain
+__host__ __device__ inline int tc_remaining_events(int nsets, int chunk, int npass, int niter, int nblk, int last_ksteps, int it, int ks) {
+  const bool corr = npass > 1 && nsets > 1;
+  if (nsets == 1) return npass * (tc_events_upto(niter, nblk, last_ksteps) - tc_events_upto(it, nblk, last_ksteps)) - ks;
+  (void)corr;
+  int end = (it / chunk + 1) * chunk;
+  if (end > niter) end = niter;
+  return tc_events_upto(end, nblk, last_ksteps) - tc_events_upto(it, nblk, last_ksteps) - ks;
+}
+TcPlan tc_make_plan(int BN, int niter, int npass, int single_chain, int max_sets, bool double_buffer, int phase_shift);   // conv_tc.cu
+
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn();             // conv_tc.cu
 int pick_box(int dim, int cap, int* log2out);               // conv_tc.cu
 

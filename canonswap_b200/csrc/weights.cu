@@ -11,7 +11,7 @@
 //     (c*16 + d) to the internal channels-last order (d*32 + c),
 //   - re-lays every conv as [tap][Cin][Cout] fp32 (SIMT path) and derives the split-bf16 tcgen05
 //     operand [tap][Cout_p][Cin_p] from it on the device.
-#include "ctx.cuh"
+#include "tc_ptx.cuh"
 #include <cmath>
 #include <cstring>
 
@@ -140,8 +140,8 @@ Affine upload_affine(cs_ctx* ctx, const HostAffine& a) {
   return r;
 }
 
-ConvW pack(cs_ctx* ctx, const HostConv& c) {
-  return pack_conv_host(ctx, c.w, c.b.empty() ? nullptr : &c.b, c.Cout, c.Cin, c.KD, c.KH, c.KW);
+ConvW pack(cs_ctx* ctx, const HostConv& c, int phase_shift = 0) {
+  return pack_conv_host(ctx, c.w, c.b.empty() ? nullptr : &c.b, c.Cout, c.Cin, c.KD, c.KH, c.KW, phase_shift);
 }
 
 ResBlock3dW read_resblock3d(cs_ctx* ctx, const Table& t, const std::string& p) {
@@ -220,9 +220,7 @@ SpadeNormW read_spade(cs_ctx* ctx, const Table& t, const std::string& p, int C, 
   s.shared = pack(ctx, sh);
   if (phase_shift > 0) {
     s.phase_shift = phase_shift;
-    s.shared_ph = pack(ctx, phase_conv(sh, phase_shift));
-    s.shared_ph.BN = 128;                       // one N tile per phase (the packed rows do not depend on the tile width)
-    s.shared_ph.Cout_p = s.shared_ph.Cout;
+    s.shared_ph = pack(ctx, phase_conv(sh, phase_shift), phase_shift);     // one N tile (BN = 128) per output phase
   }
   HostConv g = read_conv(t, p + ".mlp_gamma", C, 128, 1, 3, 3);
   HostConv b = read_conv(t, p + ".mlp_beta", C, 128, 1, 3, 3);
@@ -262,9 +260,9 @@ float weight_prescale(const float* w, size_t n) {
 // [Cout][Cin][taps] (PyTorch) -> device [taps][Cin][Cout] (+ bias) (+ tcgen05 operand)
 // ------------------------------------------------------------------------------------------
 ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt, const std::vector<float>* bias, int Cout, int Cin,
-                     int KD, int KH, int KW) {
+                     int KD, int KH, int KW, int phase_shift) {
   ConvW c;
-  c.Cin = Cin; c.Cout = Cout; c.KD = KD; c.KH = KH; c.KW = KW;
+  c.Cin = Cin; c.Cout = Cout; c.KD = KD; c.KH = KH; c.KW = KW; c.phase_shift = phase_shift;
   int taps = KD * KH * KW;
   CS_REQUIRE((long)w_pt.size() == (long)Cout * Cin * taps, CS_ERR_WEIGHTS, "pack_conv_host: size mismatch");
   std::vector<float> w((size_t)taps * Cin * Cout);
@@ -348,11 +346,18 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
       y.nblk = (HG_OUT + 31) / 32; y.BN = 64; y.zrows = 64; y.Cout_p = 64 * 16;
       const long rowlen = (long)y.nblk * 64;
       y.wmul = weight_prescale(oc.w.data(), oc.w.size());
+      // same accumulator plan and truncation pre-compensation as pack_tc gives a 1x1x1 conv of this shape (tc_ptx.cuh)
+      const int npass = ctx->tc_passes >= 1 && ctx->tc_passes <= 3 ? ctx->tc_passes : 3;
+      const tc::TcPlan plan = tc::tc_make_plan(y.BN, y.nblk, npass, ctx->tc_single_chain, ctx->tc_sets, ctx->tc_dbuf != 0, 0);
+      y.plan_nsets = plan.nsets; y.plan_chunk = plan.chunk; y.plan_nacc = plan.nacc; y.plan_npass = npass; y.plan_thin = plan.thin;
+      y.plan_kappa = (float)ctx->tc_poscomp * 1e-10f;
+      const int last_ks = ((HG_OUT - (y.nblk - 1) * 32) + 15) / 16;
       std::vector<__nv_bfloat16> hw((size_t)y.Cout_p * rowlen, __float2bfloat16(0.f));
       for (int z = 0; z < 16; ++z)
         for (int tp = 0; tp < 49; ++tp)
           for (int ci = 0; ci < HG_OUT; ++ci) {
-            const float v = oc.w[(long)ci * (16 * 49) + z * 49 + tp] * y.wmul;
+            const int rem = tc::tc_remaining_events(plan.nsets, plan.chunk, npass, y.nblk, y.nblk, last_ks, ci >> 5, (ci >> 4) & 1);
+            const float v = oc.w[(long)ci * (16 * 49) + z * 49 + tp] * y.wmul * (1.0f + y.plan_kappa * (float)rem);
             __nv_bfloat16 hi, lo;
             split_operand(v, hi, lo);
             const long o = ((long)z * 64 + tp) * rowlen + (ci >> 5) * 64 + (ci & 31);

@@ -80,6 +80,10 @@ typedef struct cs_tensor_desc {
                                     until it holds (0 = default 256) */
 #define CS_OPT_WINOGRAD 13       /* 1 (default) = the wide 3x3 2-D convs (adaptive convs of the swap module, SPADE conv_0 / conv_1, refine ResBlock2d) in
                                     Winograd F(2x2,3x3) form, 0 = direct implicit GEMM */
+#define CS_OPT_TC_POSCOMP 14     /* position-dependent pre-compensation of the tensor core's accumulate truncation, folded into the packed
+                                    weights: units of 1e-10 per truncation event (default 330, 0 = off: the epilogue then applies the
+                                    constant CS_OPT_TC_COMP factor).  Options 3, 4, 8, 9, 11, 12 and 14 shape the packed weights and
+                                    must be set before cs_load_weights (CS_ERR_STATE afterwards). */
 #define CS_OPT_LANES 10         /* 1 | 2 (default) | 4: a graph-captured cs_frame runs as this many concurrent sub-batches (forked streams) */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */
 

@@ -2,9 +2,10 @@
 the same seeded synthetic weights / inputs, and the end-to-end frame against the oracle and against
 the golden fixtures produced by the unmodified reference modules.
 
-Tolerance: BASELINE.json north_star -- max-abs 1e-3 fp32 vs the reference forward.  Stage tests feed
-each stage the ORACLE's input for that stage (so errors do not compound) and scale 1e-3 by the stage's
-dynamic range; the end-to-end image test uses the absolute 1e-3 on [0,1] pixels.
+Tolerance: BASELINE.json north_star -- max-abs 1e-3 fp32 vs the reference forward, absolute, on the [0,1] image
+(every image comparison below).  Stage tests feed each stage the ORACLE's input for that stage (so errors do not
+compound); intermediate feature tensors (range 4 .. 20) are held to 1e-4 of their dynamic range, i.e. 4e-4 .. 2e-3
+absolute -- the measured stage errors are 2e-6 .. 4e-5 of the range (tools/stage_err.py).
 """
 import os
 
@@ -17,15 +18,24 @@ from oracle import canonswap_oracle as O
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-TOL = 1e-3
+TOL = 1e-3            # the image bar (absolute)
+FEAT_TOL = 1e-4       # feature tensors: relative to the tensor's dynamic range
 
 
-def _close(a, b, name, tol=TOL):
+def _close(a, b, name, tol=FEAT_TOL):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     assert a.shape == b.shape, (name, a.shape, b.shape)
     scale = max(1.0, b.abs().max().item())
     d = (a - b).abs().max().item()
     assert d <= tol * scale, f"{name}: max|d| = {d:.3e} > {tol * scale:.3e}"
+    return d
+
+
+def _close_img(a, b, name):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    d = (a - b).abs().max().item()
+    assert d <= TOL, f"{name}: max|d| = {d:.3e} > {TOL:.0e}"
     return d
 
 
@@ -81,7 +91,7 @@ def test_stage_warp_out_and_decode(case128):
     eng, inp, ref = case128
     w = eng.warp_out(ref["f_can"].cuda(), ref["occ_can"].cuda())
     img = eng.spade(w)
-    _close(img, ref["rec_can"], "rec_can (conv_decode)")
+    _close_img(img, ref["rec_can"], "rec_can (conv_decode)")
     w2 = eng.warp_out(ref["f_can"].cuda(), None)
     assert torch.isfinite(w2).all() and w2.shape == w.shape
 
@@ -89,7 +99,7 @@ def test_stage_warp_out_and_decode(case128):
 def test_stage_spade_and_u8(case128):
     eng, inp, ref = case128
     img, u8 = eng.spade(ref["warp_out"].cuda(), want_u8=True)
-    _close(img, ref["out"], "out")
+    _close_img(img, ref["out"], "out")
     exp = O.parse_output(ref["out"])
     diff = (u8.cpu().int() - exp.int()).abs()
     assert diff.max().item() <= 1                      # truncation boundary crossings only
@@ -101,7 +111,7 @@ def test_frame_end_to_end_vs_oracle(case128):
     out_f32 = torch.empty(2, 3, 256, 256, device="cuda")
     out_u8 = torch.empty(2, 256, 256, 3, dtype=torch.uint8, device="cuda")
     eng.frame(inp["frames"], inp["x_t"], inp["x_can"], out_u8=out_u8, out_f32=out_f32)
-    d = _close(out_f32, ref["out"], "frame out")
+    d = _close_img(out_f32, ref["out"], "frame out")
     print(f"end-to-end max|d| = {d:.3e}")
     exp = O.parse_output(ref["out"])
     assert (out_u8.cpu().int() - exp.int()).abs().max().item() <= 1
@@ -156,7 +166,7 @@ def test_frame_kernel_variants_vs_oracle(synth_w, opts):
         eng.set_identity(inp["source_id"].cuda())
         _close(eng.swap(ref["f_can"].cuda()), ref["f_swap"], "f_swap")
         _close(eng.refine(ref["f_swap"].cuda()), ref["f_refine"], "f_refine")
-        _close(eng.spade(ref["warp_out"].cuda()), ref["out"], "spade")
+        _close_img(eng.spade(ref["warp_out"].cuda()), ref["out"], "spade")
         out = torch.empty(2, 3, 256, 256, device="cuda")
         eng.frame(inp["frames"].cuda(), inp["x_t"].cuda(), inp["x_can"].cuda(), out_f32=out)
         assert (out.cpu() - ref["out"]).abs().max().item() <= TOL
@@ -236,10 +246,10 @@ def test_v2i_frame_body(case128, synth_w):
     exp = O.frame_v2i(synth_w, inp["frames"].cpu(), inp["x_can"].cpu(), inp["x_t"].cpu())
     out = torch.empty(2, 3, 256, 256, device="cuda")
     eng.frame(inp["frames"], inp["x_can"], inp["x_t"], out_f32=out, v2i=True)
-    _close(out, exp, "v2i frame")
+    _close_img(out, exp, "v2i frame")
     f = eng.appearance(inp["frames"])
     wf = eng.warp_forward(f, kp_driving=inp["x_t"], kp_source=inp["x_can"])
-    _close(eng.spade(wf["out"]), exp, "v2i staged")
+    _close_img(eng.spade(wf["out"]), exp, "v2i staged")
 
 
 def test_batch_independence(case128):
@@ -269,7 +279,7 @@ def test_reference_surface_mirror(synth_w):
     f_swap = sw.refine_module(f_swap)
     out = sw.warp_decode(f_swap, x_can, x_t)
     assert set(out.keys()) == {"occlusion_map", "deformation", "out"}
-    _close(out["out"], ref["out"], "mirror out")
+    _close_img(out["out"], ref["out"], "mirror out")
     img = sw.parse_output(out["out"])
     assert img.dtype == np.uint8 and img.shape == (1, 256, 256, 3)
     assert rec_can.shape == (1, 3, 256, 256)
