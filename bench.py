@@ -15,7 +15,15 @@ Printed JSON (one line, rank 0):
   e2e        same metric through can_swapper/FramePipeline with PINNED HOST buffers (H2D + D2H inside)
   roofline   the dominant kernel family (the conv kernels): algorithmic FLOPs / summed CUDA-event launch
              durations (library-side events on the launching stream) vs MEASURED_PEAKS.json bf16 TF/s
-  cpu_baseline  the oracle port of the reference algorithm on the host cores, bounded sample
+  cpu_baseline  the reference modules themselves (oracle/_ref bundle, kind "reference"; the oracle port when the bundle is
+             absent) on the host cores, bounded sample
+  parity     max|d| of the timed configuration's own output (same graph, same lanes) against the CPU oracle -- asserted
+  torch_gpu  comparator: the oracle (plain torch ops = what the reference dispatches: cuDNN / ATen) on the same GPU,
+             fp32 with TF32 off and on, with its own max|d| against the CPU oracle (the bar to beat)
+  sustained  >= 10 s of back-to-back steps with the clock trace (the step is power-bound)
+  strong     BASELINE configs[3]: a fixed 2048-frame clip through FramePipeline.run(rank, world) from pinned host memory,
+             identity broadcast inside the timed region, per-frame checksums gathered and compared with a single-GPU rerun
+  configs    throughput of configs[1] (256 px, B = 4) and configs[4] (1024 px, B = 2)
 """
 from __future__ import annotations
 
@@ -72,42 +80,58 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "sm_mhz_min": sm[0] if sm else None, "sm_mhz_max": sm[-1] if sm else None}
+
+
+def _cpu_reference():
+    """(kind, frame_fn): the reference's own modules from the oracle/_ref bundle when it travelled with the snapshot
+    (oracle/make_ref.py), else the oracle port.  frame_fn(I, x_t, x_can, id) -> image."""
+    from canonswap_b200 import synth
+    W = synth.synth_weights()
+    try:
+        from oracle import ref_bundle as RB
+        if RB.available():
+            mods = RB.build_modules(W)
+            return "reference", (lambda I, xt, xc, sid: RB.frame(mods, I, xt, xc, sid)), W
+    except Exception as e:                                   # a broken bundle must not take the bench down
+        print(f"bench.py: oracle/_ref unusable ({type(e).__name__}: {e}); falling back to the oracle port", file=sys.stderr)
+    from oracle import canonswap_oracle as O
+    return "port", (lambda I, xt, xc, sid: O.frame(W, I, xt, xc, sid)["out"]), W
 
 
 def oracle_sample(n_frames: int, threads=None):
-    """Time the CPU oracle (port of the reference forward) on `n_frames` frames, B=1 (the reference's
-    native loop), same synthetic weights / inputs. Returns (frames/s, cores)."""
+    """Time the reference's CPU implementation of the path on `n_frames` frames, B=1 (the reference's native loop), same
+    synthetic weights / inputs. Returns (frames/s, cores, kind)."""
     import torch
     from canonswap_b200 import synth
-    from oracle import canonswap_oracle as O
     if threads:
         torch.set_num_threads(threads)
-    W = synth.synth_weights()
-    inp = synth.synth_inputs(max(1, n_frames), NET)
+    kind, fn, _ = _cpu_reference()
+    inp = synth.synth_inputs(max(1, n_frames) + 1, NET)
+    fn(inp["frames"][:1], inp["x_t"][:1], inp["x_can"][:1], inp["source_id"])           # warm-up
     t0 = time.perf_counter()
-    for i in range(n_frames):
-        O.frame(W, inp["frames"][i:i + 1], inp["x_t"][i:i + 1], inp["x_can"][i:i + 1], inp["source_id"])
+    for i in range(1, n_frames + 1):
+        fn(inp["frames"][i:i + 1], inp["x_t"][i:i + 1], inp["x_can"][i:i + 1], inp["source_id"])
     dt = time.perf_counter() - t0
-    return n_frames / dt, torch.get_num_threads()
+    return n_frames / dt, torch.get_num_threads(), kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm on the host cores (oracle port; the reference's
-    Python sources do not travel to the GPU box). Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores -- the unmodified
+    src/modules/* classes from the oracle/_ref bundle (kind "reference"), or the oracle port when the bundle is absent.
+    Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
     from canonswap_b200 import synth
-    from oracle import canonswap_oracle as O
-    W = synth.synth_weights()
+    kind, fn, _ = _cpu_reference()
     inp = synth.synth_inputs(4, NET)
 
     def step(i):
         j = i % 4
-        O.frame(W, inp["frames"][j:j + 1], inp["x_t"][j:j + 1], inp["x_can"][j:j + 1], inp["source_id"])
+        fn(inp["frames"][j:j + 1], inp["x_t"][j:j + 1], inp["x_can"][j:j + 1], inp["source_id"])
 
     for i in range(args.warmup):
         step(i)
@@ -117,14 +141,15 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     fps = args.steps / dt
     cores = torch.get_num_threads()
-    sample = f"{args.steps} steps x 1 frame (B=1, the reference's native loop) of the 512px workload, torch CPU fp32"
+    what = ("the reference's src/modules/* (oracle/_ref bundle)" if kind == "reference" else "oracle port of the reference forward")
+    sample = f"{args.steps} steps x 1 frame (B=1, the reference's native loop) of the 512px workload, torch CPU fp32, {what}"
     _emit(({
         "impl": "reference", "metric": "face-swap frames/sec @512px", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "512x512 frames (net 256x256), synthetic clip, core path pipeline_e2e.py:242-267",
                    "frames_per_step": 1},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -165,6 +190,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=None, help="CS_OPT_LANES: concurrent sub-batches of a graph-replayed step (1 | 2 | 4)")
     ap.add_argument("--opt", action="append", default=[], help="experiment: library option id=value (cs_set_option), repeatable")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of a step individually (default: CUDA-graph replay)")
+    ap.add_argument("--sustained-seconds", type=float, default=10.0, help="length of the sustained leg (0 = skip; N=1 only)")
+    ap.add_argument("--strong-frames", type=int, default=2048, help="clip length of the strong-scaling leg, configs[3] (0 = skip)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the parity / torch_gpu / sustained / strong / configs legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -194,8 +222,8 @@ def main():
     sw = can_swapper(weights=W, device_id=local, max_batch=B, conv_impl=args.conv_impl)
     sw.set_source_identity(sid)
     eng = sw.engine((NET, NET), B)
+    from canonswap_b200 import _lib
     if not args.no_graph:
-        from canonswap_b200 import _lib
         eng.set_option(_lib.CS_OPT_USE_GRAPH, 1)          # cs_frame replays a captured CUDA graph (same kernels, fewer launch gaps)
         if args.lanes:
             eng.set_option(_lib.CS_OPT_LANES, args.lanes)
@@ -235,6 +263,7 @@ def main():
     e1.record()
     barrier()
     launches = eng.launch_count - l0
+    timed_u8 = out_d.clone()                              # the bytes of the last timed step (the parity leg checks them)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -408,14 +437,182 @@ def main():
                                 "ceiling is 1/3 of the 16-bit peak; traffic = dram bytes per launch from the committed ncu "
                                 "pass (profiles/conv_family_traffic.json)"}
 
-    # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only) -----------------
+    # ---- parity of the timed configuration itself (rank 0): same engine, same graph, same lanes ---------------------
+    parity = None
+    ref_frames = {}
+    if rank == 0 and not args.no_extra:
+        from oracle import canonswap_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        jl = (args.warmup + args.steps - 1) % n_batches           # the batch of the last timed step (timed_u8 holds its result)
+        chk32 = torch.empty(B, 3, 2 * NET, 2 * NET, device=dev)
+        chk8 = torch.empty_like(out_d)
+        for _ in range(3):                                        # this output combination captures its own graph: eager, capture, replay
+            eng.frame(frames_d[jl], xt_d[jl], xc_d[jl], out_u8=chk8, out_f32=chk32)
+        torch.cuda.synchronize()
+        same_u8 = bool(torch.equal(chk8, timed_u8))                  # the checked call reproduces the timed call's bytes
+        worst = 0.0
+        for fi in sorted({0, B - 1}):                             # one frame of each lane
+            g_i = mine[jl * B + fi]
+            r = O.frame(W, clip["frames"][g_i:g_i + 1].permute(0, 3, 1, 2).float() / 255.0, clip["x_t"][g_i:g_i + 1],
+                        clip["x_can"][g_i:g_i + 1], clip["source_id"])["out"]
+            ref_frames[fi] = r
+            worst = max(worst, (chk32[fi:fi + 1].cpu() - r).abs().max().item())
+        parity = {"max_abs_err": worst, "bar": 1e-3, "ok": worst <= 1e-3 and same_u8, "frames_checked": sorted({0, B - 1}),
+                  "u8_identical_to_timed_step": same_u8,
+                  "mode": f"B={B}, net {NET}, cuda_graph={not args.no_graph}, lanes={args.lanes or 2}",
+                  "against": "CPU oracle (torch fp32 restatement of the reference forward, pinned to the reference modules)"}
+
+    # ---- comparator: the same forward as plain torch ops on the SAME GPU = what the reference
+    #      dispatches (cuDNN / ATen fp32), TF32 off and on.  Not the product path; the oracle is only executed, not shipped.
+    torch_gpu = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            from oracle import canonswap_oracle as O
+            Wg = {n: {k: v.to(dev) for k, v in sd.items()} for n, sd in W.items() if n != "motion_extractor"}
+            fr32 = frames_d[0].permute(0, 3, 1, 2).float() / 255.0
+            sid_g = clip["source_id"].to(dev)
+            torch_gpu = {}
+            for tf32 in (False, True):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                for _ in range(2):
+                    o = O.frame(Wg, fr32, xt_d[0], xc_d[0], sid_g)["out"]
+                torch.cuda.synchronize()
+                t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                nrep = 3
+                t0e.record()
+                for _ in range(nrep):
+                    o = O.frame(Wg, fr32, xt_d[0], xc_d[0], sid_g)["out"]
+                t1e.record()
+                torch.cuda.synchronize()
+                tms = t0e.elapsed_time(t1e) / nrep
+                g0 = mine[0]
+                r0 = O.frame(W, clip["frames"][g0:g0 + 1].permute(0, 3, 1, 2).float() / 255.0, clip["x_t"][g0:g0 + 1],
+                             clip["x_can"][g0:g0 + 1], clip["source_id"])["out"]
+                torch_gpu["tf32_on" if tf32 else "tf32_off"] = {
+                    "value": B / (tms / 1000.0), "unit": "frames/s", "ms_per_step": tms,
+                    "max_abs_err_vs_cpu_oracle": (o[0:1].cpu() - r0).abs().max().item()}
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch_gpu["note"] = ("torch-eager forward of the same networks (oracle functions on cuda: cuDNN conv2d/conv3d, ATen "
+                                 "grid_sample / norms), B=8 per step, same weights / inputs; comparator only")
+            del Wg
+            torch.cuda.empty_cache()
+        except Exception as e:                                   # a comparator failure must not take the bench down
+            torch_gpu = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- sustained leg: >= 10 s of back-to-back steps with the clock trace (N=1) -------------------------------------
+    sustained = None
+    if rank == 0 and world == 1 and not args.no_extra and args.sustained_seconds > 0:
+        sclk = ClockSampler(local)
+        sclk.start()
+        per = ms / args.steps
+        chunk_steps = max(4, int(1000.0 / per))                   # ~1 s of steps per event pair
+        rates = []
+        t_begin = time.perf_counter()
+        k_step = 0
+        while time.perf_counter() - t_begin < args.sustained_seconds:
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(chunk_steps):
+                step(k_step); k_step += 1
+            c1.record()
+            torch.cuda.synchronize()
+            rates.append(B * chunk_steps / (c0.elapsed_time(c1) / 1000.0))
+        sc = sclk.summary()
+        sustained = {"value": sum(rates) / len(rates), "unit": "frames/s", "seconds": time.perf_counter() - t_begin,
+                     "steps": k_step, "first_second": rates[0], "last_second": rates[-1], "min": min(rates), "max": max(rates),
+                     "clocks": sc}
+
+    # ---- strong scaling, BASELINE configs[3]: a fixed clip through FramePipeline.run(rank, world), broadcast included ----
+    strong = None
+    if not args.no_extra and args.strong_frames > 0:
+        import zlib
+        import numpy as np
+        TS = args.strong_frames
+        rep = (TS + CLIP - 1) // CLIP
+        s_frames = clip["frames"].repeat(rep, 1, 1, 1)[:TS].contiguous().pin_memory()       # frame i = clip frame i % 256
+        s_xt = clip["x_t"].repeat(rep, 1, 1)[:TS].contiguous().pin_memory()
+        s_xc = clip["x_can"].repeat(rep, 1, 1)[:TS].contiguous().pin_memory()
+        my_ids = list(range(rank, TS, world))
+        s_out = torch.empty(len(my_ids), 2 * NET, 2 * NET, 3, dtype=torch.uint8).pin_memory()   # this rank's frames, local order
+        spipe = FramePipeline(sw, net_hw=(NET, NET), batch=B)
+        spipe.run(s_frames[: B * world * 2], s_xt, s_xc, s_out, rank=rank, world=world, out_local=True)    # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        sid_s = broadcast_identity(clip["source_id"] if rank == 0 else None, device=dev)     # the one collective, timed
+        sw.set_source_identity(sid_s)                                                         # 14 style / demod tables per rank
+        n_done = spipe.run(s_frames, s_xt, s_xc, s_out, rank=rank, world=world, out_local=True)
+        barrier()
+        wall = time.perf_counter() - t0
+        wt = torch.tensor([wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        crc = torch.zeros(TS, dtype=torch.int64)
+        o_np = s_out.numpy()
+        for j, gi in enumerate(my_ids):
+            crc[gi] = zlib.crc32(o_np[j])
+        crc_d = crc.to(dev)
+        if world > 1:
+            dist.all_reduce(crc_d)                                                            # every frame is owned by one rank
+        match = None
+        if rank == 0:
+            # single-GPU rerun of the first frames (contiguous batches, as the N = 1 run forms them) -> checksums must agree
+            nv = min(TS, 8 * B)
+            v_out = torch.empty(nv, 2 * NET, 2 * NET, 3, dtype=torch.uint8).pin_memory()
+            FramePipeline(sw, net_hw=(NET, NET), batch=B).run(s_frames[:nv], s_xt[:nv], s_xc[:nv], v_out)
+            v_np = v_out.numpy()
+            match = all(int(crc_d[i].item()) == zlib.crc32(v_np[i]) for i in range(nv))
+            strong = {"value": TS / wt.item(), "unit": "frames/s", "frames": TS, "seconds": wt.item(), "scaling": "strong",
+                      "frames_per_rank": n_done, "includes": "NCCL identity broadcast + per-rank style tables + H2D / D2H of every frame",
+                      "checksum": "crc32 per output frame, all-reduced; first %d frames recomputed on one GPU" % nv,
+                      "checksums_match_single_gpu": bool(match)}
+        del s_frames, s_out
+
+    # ---- BASELINE configs[1] (256 px, 32-frame clip, B = 4) and configs[4] (1024 px, B = 2): throughput lines ----------
+    configs = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        configs = {}
+        for tag, net_c, b_c, t_c, nstep in (("256px_b4", 128, 4, 32, 20), ("1024px_b2", 512, 2, 8, 6)):
+            try:
+                cclip = synth.synth_inputs(t_c, net_c, u8=True)
+                swc = can_swapper(weights=W, device_id=local, max_batch=b_c, conv_impl=args.conv_impl)
+                swc.set_source_identity(clip["source_id"].to(dev))
+                ec = swc.engine((net_c, net_c), b_c)
+                if not args.no_graph:
+                    ec.set_option(_lib.CS_OPT_USE_GRAPH, 1)
+                nb_c = t_c // b_c
+                fr_c = cclip["frames"].to(dev).reshape(nb_c, b_c, net_c, net_c, 3)
+                xt_c = cclip["x_t"].to(dev).reshape(nb_c, b_c, 21, 3)
+                xc_c = cclip["x_can"].to(dev).reshape(nb_c, b_c, 21, 3)
+                o_c = torch.empty(b_c, 2 * net_c, 2 * net_c, 3, dtype=torch.uint8, device=dev)
+                for i in range(3):
+                    ec.frame(fr_c[i % nb_c], xt_c[i % nb_c], xc_c[i % nb_c], out_u8=o_c)
+                torch.cuda.synchronize()
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record()
+                for i in range(nstep):
+                    ec.frame(fr_c[(3 + i) % nb_c], xt_c[(3 + i) % nb_c], xc_c[(3 + i) % nb_c], out_u8=o_c)
+                q1.record()
+                torch.cuda.synchronize()
+                qms = q0.elapsed_time(q1) / nstep
+                gf = GFLOP_PER_FRAME * (net_c / 256.0) ** 2
+                configs[tag] = {"value": b_c / (qms / 1000.0), "unit": "frames/s", "ms_per_step": qms, "batch": b_c,
+                                "frame_px": 2 * net_c, "clip_frames": t_c, "gflop_per_frame": gf,
+                                "achieved_tflops": b_c / (qms / 1000.0) * gf / 1000.0}
+                del swc, ec
+                torch.cuda.empty_cache()
+            except Exception as e:
+                configs[tag] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- CPU baseline: the reference's own CPU implementation on the host cores, bounded sample (rank 0, N=1 only) ------
     cpu = None
     if rank == 0 and world == 1 and args.cpu_frames > 0:
         torch.set_num_threads(os.cpu_count() or 1)
-        oracle_sample(1)                                  # warm-up
-        fps, cores = oracle_sample(args.cpu_frames)
-        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_frames} frames, B=1 (the reference's native loop), same workload, torch CPU fp32 oracle"}
+        fps, cores, kind = oracle_sample(args.cpu_frames)
+        what = "the reference's src/modules/* from the oracle/_ref bundle" if kind == "reference" else "torch CPU fp32 oracle port"
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+               "sample": f"{args.cpu_frames} frames, B=1 (the reference's native loop), same workload, {what}"}
 
     if rank == 0:
         _emit(({
@@ -432,7 +629,10 @@ def main():
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "families": families, "achieved_tflops_whole_step": value * GFLOP_PER_FRAME / 1000.0,
             "with_motion_extractor": with_motion, "as_written": as_written, "paste_back": paste, "full_loop": full_loop,
+            "parity": parity, "torch_gpu": torch_gpu, "sustained": sustained, "strong": strong, "configs": configs,
         }))
+        if parity is not None and not parity["ok"]:
+            raise SystemExit(f"bench.py: PARITY FAILURE at the timed configuration: {parity}")
     if world > 1:
         dist.destroy_process_group()
 

@@ -85,7 +85,9 @@ __device__ __forceinline__ TileOrg tile_origin(const ConvTcK& k, int m_tile, int
 // A tile and HALF of the B tile, the leader issues cta_group::2 MMAs (M = 256) that read A / B from both CTAs' shared
 // memory and accumulate into both CTAs' TMEM.  Halving the B bytes written and read per CTA takes the kernel off the
 // shared-memory bandwidth limit that bounds the 1-CTA form at N = 256 (3 MMAs per operand load).
-template <bool RES, bool EMIT, int CTAS, bool SPADE = false>
+// BCOMP: border take-back of the truncation pre-compensation (multi-tap convs whose weights carry it); a template parameter
+// so that the 1x1 / Winograd GEMM instantiations, whose epilogue paces the kernel, carry none of its code.
+template <bool RES, bool EMIT, int CTAS, bool SPADE = false, bool BCOMP = false>
 __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, ConvTcK k) {
   extern __shared__ uint8_t smem_raw[];
@@ -273,8 +275,8 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
     // order (kd is the slowest index): a uniform over-compensation of kappa * (zero events of the set), taken back exactly;
     // h / w padding removes interleaved taps: kappa * fraction * (real events) / 2 on average.
     int b_it0 = 0x7fffffff, b_lead = 0; float b_frac = 0.f;
-    const bool bcomp = k.kappa != 0.f && taps > 1 && k.ph_s == 0;
-    if (bcomp) {
+    constexpr bool bcomp = BCOMP;
+    if constexpr (BCOMP) {
       int r = q * 32 + lane;
       const int ow = w0 + (r & ((1 << k.lbw) - 1)); r >>= k.lbw;
       const int oh = h0 + (r & ((1 << k.lbh) - 1)); r >>= k.lbh;
@@ -292,7 +294,6 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
     }
     const int niter_all = taps * k.nblk;
     auto set_factor = [&](int set_idx) -> float {            // set_idx: hi*hi set (0-based); single accumulator: the whole chain
-      if (!bcomp) return 1.f;
       const int a = k.nsets == 1 ? 0 : set_idx * k.chunk;
       int e = k.nsets == 1 ? niter_all : a + k.chunk;
       if (e > niter_all) e = niter_all;
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
           const uint32_t tcol = trow + (uint32_t)(c0 + 16 * half);
           tc_ld16(tcol + (uint32_t)(corr * k.BN), v);
           tc_ld_wait();
-          if (bcomp) {
+          if constexpr (BCOMP) {
             const float f0 = set_factor(0);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * f0);
@@ -358,7 +359,8 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
             uint32_t u[16];
             tc_ld16(tcol + (uint32_t)(st * k.BN), u);
             tc_ld_wait();
-            const float fs = set_factor(st - corr);
+            float fs = 1.f;
+            if constexpr (BCOMP) fs = set_factor(st - corr);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(u[j]), fs, __uint_as_float(v[j])));
           }
@@ -670,14 +672,15 @@ void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream) {
   int BN = pick_bn(w.Cout);
   // Accumulator-set policy.  The hi*hi products of a tile accumulate in 512 / BN - 1 TMEM sets (one more holds the small
   // correction products); every MMA added into a set truncates it (round toward zero), so the error grows with the chain
-  // length per set (the first-order loss is pre-compensated in the packed weights, what remains grows with the chain too:
-  // tests/test_gpu_configs.py).  Halve the N tile (down to 64) until a chain is at most `chain_max` MMAs: BN = 256 leaves
-  // one hi*hi set (a 3x3 conv over 512 channels would chain 288 MMAs), BN = 128 three (96 each), BN = 64 seven (the deep
-  // hourglass levels, K up to 27 x 1024: 247 each; their M is tiny, so the narrow tile costs nothing and fills more SMs).
+  // length per set (the first-order loss is pre-compensated in the packed weights; what remains grows with the chain too:
+  // tests/test_gpu_configs.py).  Halve the N tile (down to tc_bn_min = 128) until a chain is at most `chain_max` MMAs:
+  // BN = 256 leaves one hi*hi set (a 3x3 conv over 512 channels would chain 288 MMAs), BN = 128 three (96 each).  (BN = 64
+  // -- seven sets -- was measured for the deep hourglass levels, K up to 27 x 1024: their chains drop from 576 to 247, but
+  // the narrow tile re-reads the A operand twice as often: +1.8 ms per step for no visible end-to-end gain.)
   {
     const int chain_max = ctx->tc_chain_max > 0 ? ctx->tc_chain_max : 256;
     const int steps_main = w.taps() * nblk * 2;
-    while (BN > 64 && (steps_main + (512 / BN - 1) - 1) / (512 / BN - 1) > chain_max) BN = round_up(BN / 2, 16);
+    while (BN > ctx->tc_bn_min && (steps_main + (512 / BN - 1) - 1) / (512 / BN - 1) > chain_max) BN = round_up(BN / 2, 16);
   }
   if (ctx->tc_bn_max > 0 && BN > ctx->tc_bn_max) BN = ctx->tc_bn_max;
   if (w.phase_shift > 0) {                                  // one N tile per output phase (pack_phase_conv): Cout = 4^ps * BN rows
@@ -834,16 +837,27 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, ConvTcK);
-  static const KernelFn fns[2][2][2] = {
-      {{conv_tc_kernel<false, false, 1>, conv_tc_kernel<false, false, 2>}, {conv_tc_kernel<false, true, 1>, conv_tc_kernel<false, true, 2>}},
-      {{conv_tc_kernel<true, false, 1>, conv_tc_kernel<true, false, 2>}, {conv_tc_kernel<true, true, 1>, conv_tc_kernel<true, true, 2>}}};
+  // [residual][emit][pair][border take-back]; the SPADE epilogue has its own four
+  static const KernelFn fns[2][2][2][2] = {
+      {{{conv_tc_kernel<false, false, 1, false, false>, conv_tc_kernel<false, false, 1, false, true>},
+        {conv_tc_kernel<false, false, 2, false, false>, conv_tc_kernel<false, false, 2, false, true>}},
+       {{conv_tc_kernel<false, true, 1, false, false>, conv_tc_kernel<false, true, 1, false, true>},
+        {conv_tc_kernel<false, true, 2, false, false>, conv_tc_kernel<false, true, 2, false, true>}}},
+      {{{conv_tc_kernel<true, false, 1, false, false>, conv_tc_kernel<true, false, 1, false, true>},
+        {conv_tc_kernel<true, false, 2, false, false>, conv_tc_kernel<true, false, 2, false, true>}},
+       {{conv_tc_kernel<true, true, 1, false, false>, conv_tc_kernel<true, true, 1, false, true>},
+        {conv_tc_kernel<true, true, 2, false, false>, conv_tc_kernel<true, true, 2, false, true>}}}};
+  // (no border take-back in the SPADE epilogue: its K is short -- at most kappa * 0.56 * 108 = 2e-6 on corner pixels -- and the
+  //  epilogue, which already holds the normalised activation in registers, paces these kernels: +9 % measured with it)
+  static const KernelFn fns_spade[2] = {conv_tc_kernel<false, true, 1, true, false>, conv_tc_kernel<false, true, 2, true, false>};
   if (!g_attr_set[dev & 63]) {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
         for (int c = 0; c < 2; ++c)
-          CS_CUDA(cudaFuncSetAttribute(fns[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
-    CS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
-    CS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
+          for (int d = 0; d < 2; ++d)
+            CS_CUDA(cudaFuncSetAttribute(fns[a][b][c][d], cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
+    for (int c = 0; c < 2; ++c)
+      CS_CUDA(cudaFuncSetAttribute(fns_spade[c], cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM + 4096));
     g_attr_set[dev & 63] = true;
   }
   if (w.zrows > 0) CS_REQUIRE(bd == 1 && w.zrows % k.BN == 0, CS_ERR_INVALID, "conv_tc: depth-dependent weights need one depth per tile");
@@ -862,8 +876,9 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
   }
-  KernelFn fn = fns[has_res][has_emit][pair ? 1 : 0];
-  if (k.sp_x) fn = pair ? conv_tc_kernel<false, true, 2, true> : conv_tc_kernel<false, true, 1, true>;
+  const int bcomp = (k.kappa != 0.f && w.taps() > 1 && ps == 0) ? 1 : 0;
+  KernelFn fn = fns[has_res][has_emit][pair ? 1 : 0][bcomp];
+  if (k.sp_x) fn = fns_spade[pair ? 1 : 0];
   int clusters = thin ? 2 * n_sm : n_sm;
   if (pair) {
     // co-resident 2-CTA clusters (GPC boundaries can strand an SM): a persistent grid must not exceed one wave

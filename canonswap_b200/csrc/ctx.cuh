@@ -104,7 +104,7 @@ struct cs_ctx {
   int device = 0, max_batch = 1, net_h = 0, net_w = 0, h = 0, w = 0;
   std::string err;
   bool weights_loaded = false, identity_set = false;
-  int conv_impl = 0, use_graph = 0, tc_passes = 3, tc_sets = 0, tc_comp = 170, tc_poscomp = 330, tc_pair = 1, tc_stacked3 = 1, tc_dbuf = 1, winograd = 1, tc_chain_max = 0, tc_single_chain = 256, tc_bn_max = 0;
+  int conv_impl = 0, use_graph = 0, tc_passes = 3, tc_sets = 0, tc_comp = 170, tc_poscomp = 330, tc_pair = 1, tc_stacked3 = 1, tc_dbuf = 1, winograd = 1, tc_chain_max = 0, tc_single_chain = 256, tc_bn_max = 0, tc_bn_min = 128;
   int64_t launches = 0;
   std::vector<void*> owned;        // device allocations owned by the ctx
   size_t owned_bytes = 0;

@@ -280,19 +280,30 @@ __global__ void __launch_bounds__(256) stats_dense_kernel(const float* __restric
   }
 }
 
-__global__ void stats_finalize_blocks_kernel(const double* __restrict__ part, int nblocks, int C, float* __restrict__ mean,
-                                             float* __restrict__ rstd, int n /*B*C*/, double inv_count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int b = i / C, c = i % C;
-  const double* p = part + ((long)b * nblocks * C + c) * 2;
+// block = 32 (b,c) pairs x 8 slices of the block range; every slice and the final combine run in a fixed order
+__global__ void __launch_bounds__(256) stats_finalize_blocks_kernel(const double* __restrict__ part, int nblocks, int C,
+                                                                    float* __restrict__ mean, float* __restrict__ rstd, int n /*B*C*/,
+                                                                    double inv_count, float eps) {
+  __shared__ double r1[8][32], r2[8][32];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   double s1 = 0.0, s2 = 0.0;
-  for (int t = 0; t < nblocks; ++t) { s1 += p[(long)t * C * 2]; s2 += p[(long)t * C * 2 + 1]; }
-  const double m = s1 * inv_count;
-  double var = s2 * inv_count - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[i] = (float)m;
-  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  if (i < n) {
+    const int b = i / C, c = i % C;
+    const double* p = part + ((long)b * nblocks * C + c) * 2;
+    for (int t = sl; t < nblocks; t += 8) { s1 += p[(long)t * C * 2]; s2 += p[(long)t * C * 2 + 1]; }
+  }
+  r1[sl][lane] = s1; r2[sl][lane] = s2;
+  __syncthreads();
+  if (sl == 0 && i < n) {
+    s1 = 0.0; s2 = 0.0;
+    for (int q = 0; q < 8; ++q) { s1 += r1[q][lane]; s2 += r2[q][lane]; }
+    const double m = s1 * inv_count;
+    double var = s2 * inv_count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[i] = (float)m;
+    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch) {
@@ -314,7 +325,7 @@ void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, f
     dim3 grid((unsigned)nblocks, x.B);
     stats_dense_kernel<<<grid, 256, 0, L.stream>>>(x.p, S, C, (int)rows, scratch);
     check_launch("stats_dense");
-    stats_finalize_blocks_kernel<<<(n + 127) / 128, 128, 0, L.stream>>>(scratch, (int)nblocks, C, mean, rstd, n, 1.0 / (double)S, eps);
+    stats_finalize_blocks_kernel<<<(n + 31) / 32, 256, 0, L.stream>>>(scratch, (int)nblocks, C, mean, rstd, n, 1.0 / (double)S, eps);
     check_launch("stats_finalize");
     return;
   }

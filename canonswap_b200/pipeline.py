@@ -85,16 +85,22 @@ class FramePipeline:
         self.d2h_bytes = 0
 
     def run(self, frames_u8: torch.Tensor, x_t: Optional[torch.Tensor], x_can: Optional[torch.Tensor], out_u8: torch.Tensor,
-            rank: int = 0, world: int = 1) -> int:
+            rank: int = 0, world: int = 1, out_local: bool = False) -> int:
         """frames_u8 [T,H,W,3] u8, x_t/x_can [T,21,3] fp32, out_u8 [T,2H,2W,3] u8 -- all PINNED host tensors.
         x_t = x_can = None: the keypoints are derived on the device by the motion extractor (no motion template on the
         host, reference can_swap_pipeline_e2e.py:101-135,225-243).
-        Processes frames i % world == rank; returns how many. Synchronises before returning."""
+        Processes frames i % world == rank; returns how many. Synchronises before returning.
+        out_local: out_u8 holds only this rank's frames, in the order of shard_indices (row j = global frame rank + j * world)
+        instead of being indexed by the global frame id.
+        The kernels run on the stream that is current when run() is called (the ctx is single-stream: do not call run()
+        of two pipelines sharing one can_swapper from different streams at the same time)."""
         T = frames_u8.shape[0]
         motion = x_t is None and x_can is None
         mine = shard_indices(T, rank, world)
         contiguous = world == 1
+        self.compute = torch.cuda.current_stream(self.dev)          # resolved per call, not at construction
         k = 0
+        done = 0
         for ids in batches(mine, self.batch):
             s = self.slots[k % 2]
             k += 1
@@ -124,12 +130,15 @@ class FramePipeline:
             s["done"].record(self.compute)
             with torch.cuda.stream(self.copy_out):
                 self.copy_out.wait_event(s["done"])
-                if contiguous:
+                if out_local:
+                    out_u8[done:done + b].copy_(s["out"][:b], non_blocking=True)
+                elif contiguous:
                     out_u8[ids[0]:ids[-1] + 1].copy_(s["out"][:b], non_blocking=True)
                 else:
                     for j, i in enumerate(ids):
                         out_u8[i].copy_(s["out"][j], non_blocking=True)
                 s["drained"].record(self.copy_out)
+            done += b
             self.d2h_bytes += b * out_u8[0].numel()
         self.copy_out.synchronize()
         self.compute.synchronize()

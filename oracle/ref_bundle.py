@@ -19,57 +19,46 @@ def available() -> bool:
     return os.path.isfile(os.path.join(DST, "src", "modules", "warping_network.py"))
 
 
-def _import(name):
-    """Import `src.modules.X` from the bundle without leaving the bundle on sys.path (and without picking up another `src`)."""
-    saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
-    for k in saved:
-        del sys.modules[k]
+_MODS = {}
+
+
+def _load_bundle():
+    """Import the bundle's `src.modules.*` once, without leaving `oracle/_ref` on sys.path or its `src` package in sys.modules
+    (another `src` -- e.g. /root/reference itself in the authoring container -- must stay importable)."""
+    if _MODS:
+        return _MODS
+    if not available():
+        raise FileNotFoundError("oracle/_ref is missing: run `python oracle/make_ref.py` where /root/reference exists")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "src" or k.startswith("src.")}
     sys.path.insert(0, DST)
     try:
-        return importlib.import_module(name)
+        for name in ("appearance_feature_extractor", "warping_network", "spade_generator", "adaptive_modulate", "motion_extractor"):
+            _MODS[name] = importlib.import_module("src.modules." + name)
     finally:
         sys.path.remove(DST)
-        bundle = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
-        for k in bundle:
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
             del sys.modules[k]
         sys.modules.update(saved)
-        _CACHE.update(bundle)
-
-
-_CACHE = {}
+    return _MODS
 
 
 def build_modules(weights, device="cpu"):
     """The five hot-path networks of can_swapper.__init__ (can_swap_e2e.py:60-68) with `weights` (combined_weights.pth layout)
     loaded strictly, in eval mode."""
     import yaml
-    if not available():
-        raise FileNotFoundError("oracle/_ref is missing: run `python oracle/make_ref.py` where /root/reference exists")
-    sys.modules.update(_CACHE)
-    try:
-        afe = _import("src.modules.appearance_feature_extractor")
-        sys.modules.update(_CACHE)
-        wn = _import("src.modules.warping_network")
-        sys.modules.update(_CACHE)
-        sg = _import("src.modules.spade_generator")
-        sys.modules.update(_CACHE)
-        am = _import("src.modules.adaptive_modulate")
-    finally:
-        for k in list(sys.modules):
-            if (k == "src" or k.startswith("src.")) and k in _CACHE:
-                del sys.modules[k]
+    m = _load_bundle()
     cfg = yaml.safe_load(open(os.path.join(DST, "src", "config", "models.yaml")))["model_params"]
     cfg["spade_generator_params"]["upscale"] = 2                       # can_swap_e2e.py:62
     mods = {
-        "appearance_feature_extractor": afe.AppearanceFeatureExtractor(**cfg["appearance_feature_extractor_params"]),
-        "warping_module": wn.WarpingNetwork(**cfg["warping_module_params"]),
-        "spade_generator": sg.SPADEDecoder(**cfg["spade_generator_params"]),
-        "transfer": am.transfer_model2(),
-        "refine": am.G3d(),
+        "appearance_feature_extractor": m["appearance_feature_extractor"].AppearanceFeatureExtractor(**cfg["appearance_feature_extractor_params"]),
+        "warping_module": m["warping_network"].WarpingNetwork(**cfg["warping_module_params"]),
+        "spade_generator": m["spade_generator"].SPADEDecoder(**cfg["spade_generator_params"]),
+        "transfer": m["adaptive_modulate"].transfer_model2(),
+        "refine": m["adaptive_modulate"].G3d(),
     }
-    for name, m in mods.items():
-        m.load_state_dict(weights[name], strict=True)
-        m.to(device).eval()
+    for name, mod in mods.items():
+        mod.load_state_dict(weights[name], strict=True)
+        mod.to(device).eval()
     return mods
 
 
