@@ -27,6 +27,7 @@ CS_OPT_LANES = 10
 CS_OPT_WINOGRAD = 13
 CS_OPT_TC_POSCOMP = 14
 CS_FRAME_MOTION = 8
+CS_FRAME_V2I_FEATURE = 16
 MOTION_HEADS = 328
 PASTE_MAX_BATCH = 16
 CS_OPT_TC_CHAIN_MAX = 12

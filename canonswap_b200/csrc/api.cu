@@ -135,6 +135,16 @@ void body_frame(Net& n, const void* frames, const float* kp_t, const float* kp_c
   float* vb = n.A->f32(vol_elems(c, B));
   float* occ = n.A->f32((size_t)B * c->h * c->w);
   float* o256 = n.A->f32((size_t)B * c->h * c->w * 256);
+  if ((flags & CS_FRAME_V2I) && (flags & CS_FRAME_V2I_FEATURE)) {  // v2i with the appearance volume resident (one per source)
+    nchw_to_cl(n.L, static_cast<const float*>(frames), va, 1, 512, (long)c->h * c->w, 1);
+    if (!n.L.dry)
+      for (int b = 1; b < B; ++b)
+        CS_CUDA(cudaMemcpyAsync(va + vol_elems(c, b), va, (size_t)vol_elems(c, 1) * sizeof(float), cudaMemcpyDeviceToDevice, n.L.stream));
+    run_warp(n, va, /*kp_source=*/kp_t, /*kp_driving=*/kp_can, B, vb, occ, nullptr);
+    run_warp_out(n, vb, occ, B, o256);
+    run_spade(n, o256, B, out_f32, out_u8);
+    return;
+  }
   if (flags & CS_FRAME_IN_U8_HWC) ingest_u8(n.L, static_cast<const uint8_t*>(frames), img_cl, npix * 3);   // prepare_videos
   else nchw_to_cl(n.L, static_cast<const float*>(frames), img_cl, B, 3, (long)c->net_h * c->net_w, 0);
   if (flags & CS_FRAME_MOTION) {                                  // x_t / x_can of the frames from M (:112-125, :231-243)
@@ -431,6 +441,8 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
   CS_REQUIRE((flags & CS_FRAME_MOTION) || (kp_t && kp_can), CS_ERR_INVALID, "cs_frame: null keypoints without CS_FRAME_MOTION");
   CS_REQUIRE(!(flags & CS_FRAME_MOTION) || ctx->M.loaded, CS_ERR_STATE, "cs_frame: CS_FRAME_MOTION without motion extractor weights");
   CS_REQUIRE(ctx->identity_set || (flags & CS_FRAME_V2I), CS_ERR_STATE, "cs_frame before cs_set_identity");
+  CS_REQUIRE(!(flags & CS_FRAME_V2I_FEATURE) || ((flags & CS_FRAME_V2I) && !(flags & (CS_FRAME_IN_U8_HWC | CS_FRAME_MOTION))),
+             CS_ERR_INVALID, "cs_frame: CS_FRAME_V2I_FEATURE needs CS_FRAME_V2I and fp32 input without CS_FRAME_MOTION");
   Net n = make_net(ctx, stream, false);
   ctx->arena.reset(0);
   if (!ctx->use_graph || ctx->prof.on) {
@@ -438,12 +450,13 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
   } else {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t npix = (size_t)B * ctx->net_h * ctx->net_w;
-    const size_t in_bytes = (flags & CS_FRAME_IN_U8_HWC) ? npix * 3 : npix * 3 * sizeof(float);
+    const size_t vol_bytes = (size_t)ctx->h * ctx->w * 512 * sizeof(float);
+    const size_t in_bytes = (flags & CS_FRAME_V2I_FEATURE) ? vol_bytes : (flags & CS_FRAME_IN_U8_HWC) ? npix * 3 : npix * 3 * sizeof(float);
     const size_t kp_bytes = (size_t)B * NUM_KP * 3 * sizeof(float);
     const size_t o32_bytes = npix * 4 * 3 * sizeof(float), ou8_bytes = npix * 4 * 3;
     if (!ctx->g_frames) {                                   // staging buffers sized for max_batch
       const size_t mp = (size_t)ctx->max_batch * ctx->net_h * ctx->net_w;
-      ctx->g_frames = ctx->dmalloc(mp * 3 * sizeof(float));
+      ctx->g_frames = ctx->dmalloc(mp * 3 * sizeof(float) > vol_bytes ? mp * 3 * sizeof(float) : vol_bytes);
       ctx->g_kpt = static_cast<float*>(ctx->dmalloc((size_t)ctx->max_batch * NUM_KP * 3 * sizeof(float)));
       ctx->g_kpc = static_cast<float*>(ctx->dmalloc((size_t)ctx->max_batch * NUM_KP * 3 * sizeof(float)));
       ctx->g_out32 = static_cast<float*>(ctx->dmalloc(mp * 4 * 3 * sizeof(float)));
@@ -492,7 +505,7 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
               arenas[l] = ctx->arena;
               arenas[l].base = ctx->arena.base + part * l; arenas[l].cap = part; arenas[l].off = 0; arenas[l].high = 0;
               const size_t px0 = (size_t)b_lo * ctx->net_h * ctx->net_w;
-              const size_t in_off = (flags & CS_FRAME_IN_U8_HWC) ? px0 * 3 : px0 * 3 * sizeof(float);
+              const size_t in_off = (flags & CS_FRAME_V2I_FEATURE) ? 0 : (flags & CS_FRAME_IN_U8_HWC) ? px0 * 3 : px0 * 3 * sizeof(float);
               Net nl = n; nl.A = &arenas[l]; nl.L.stream = sl; nl.stats = ctx->stats_lane[l];
               if (ctx->M.sumsq) nl.grn = ctx->M.sumsq + (size_t)b_lo * 3072;
               body_frame(nl, static_cast<char*>(ctx->g_frames) + in_off, ctx->g_kpt + (size_t)b_lo * NUM_KP * 3,

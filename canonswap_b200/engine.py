@@ -85,14 +85,22 @@ class Engine:
         except Exception:
             pass
 
+    def _live(self):
+        if not self._ctx.value:
+            raise CanonSwapError("this Engine was closed (its weights were reloaded or a larger batch was requested): "
+                                 "fetch the current one from can_swapper.engine(...)")
+        return self._ctx
+
     def _check(self, rc: int):
+        if rc != 0 and not self._ctx.value:
+            self._live()
         if rc != 0:
             raise CanonSwapError(f"canonswap_b200 error {rc}: {self._lib.cs_last_error(self._ctx).decode()}")
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _in(self, t: torch.Tensor, shape, dtype=torch.float32, name="tensor") -> torch.Tensor:
+    def _in(self, t: torch.Tensor, shape, dtype=torch.float32, name="tensor", output: bool = False) -> torch.Tensor:
         if not isinstance(t, torch.Tensor):
             raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
         if t.device != self.device:
@@ -101,6 +109,8 @@ class Engine:
             raise ValueError(f"{name}: shape {tuple(t.shape)} != expected {tuple(shape)}")
         if t.dtype != dtype:
             raise TypeError(f"{name}: dtype {t.dtype} != expected {dtype}")
+        if output and not t.is_contiguous():
+            raise ValueError(f"{name}: output buffers must be contiguous (a temporary copy would never reach the caller)")
         return t.detach().contiguous()
 
     def _batch(self, t: torch.Tensor) -> int:
@@ -205,21 +215,26 @@ class Engine:
     # ---- the fused loop body --------------------------------------------------------------------
     def frame(self, frames: torch.Tensor, kp_t: Optional[torch.Tensor] = None, kp_can: Optional[torch.Tensor] = None,
               out_u8: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, debug_decodes: bool = False,
-              v2i: bool = False, motion: bool = False):
+              v2i: bool = False, motion: bool = False, v2i_feature: bool = False, batch: Optional[int] = None):
         """One batch of the per-frame loop body (reference can_swap_pipeline_e2e.py:242-267).
 
-        frames: [B,net_h,net_w,3] uint8 (HWC, as cropped) or [B,3,net_h,net_w] fp32 in [0,1];
+        frames: [B,net_h,net_w,3] uint8 (HWC, as cropped) or [B,3,net_h,net_w] fp32 in [0,1]
+        (v2i_feature=True: ONE appearance volume [1,32,16,h,w] for the whole batch, see CS_FRAME_V2I_FEATURE);
         kp_t = x_t_info['x_s'], kp_can = scale * kp  (both [B,21,3]); with motion=True they are derived on the device
         from the frames by the motion extractor (reference can_swap_pipeline_e2e.py:112-125,231-243) and may be None.
         Returns (out_u8 [B,2H,2W,3] uint8, out_f32 [B,3,2H,2W] or None).
         """
+        v2i = v2i or v2i_feature
         if self._identity is None and not v2i:
             raise CanonSwapError("frame: no identity set (call set_identity first)")
-        B = self._batch(frames)
+        B = self._batch(kp_t) if v2i_feature else self._batch(frames)
         flags = _lib.CS_FRAME_DEBUG_DECODES if debug_decodes else 0
         if v2i:      # reference can_swap_pipeline_v2i.py:308-309: kp_t = kp_source, kp_can = kp_driving, no swap / refine
             flags |= _lib.CS_FRAME_V2I
-        if frames.dtype == torch.uint8:
+        if v2i_feature:   # `frames` = ONE appearance volume [1,32,16,h,w] shared by the B keypoint sets (CS_FRAME_V2I_FEATURE)
+            flags |= _lib.CS_FRAME_V2I_FEATURE
+            fr = self._in(frames, (1, 32, 16, self.h, self.w), name="feature")
+        elif frames.dtype == torch.uint8:
             fr = self._in(frames, (B, self.net_h, self.net_w, 3), dtype=torch.uint8, name="frames")
             flags |= _lib.CS_FRAME_IN_U8_HWC
         else:
@@ -232,9 +247,9 @@ class Engine:
         if out_u8 is None and out_f32 is None:
             out_u8 = self._new(B, 2 * self.net_h, 2 * self.net_w, 3, dtype=torch.uint8)
         if out_u8 is not None:
-            out_u8 = self._in(out_u8, (B, 2 * self.net_h, 2 * self.net_w, 3), dtype=torch.uint8, name="out_u8")
+            out_u8 = self._in(out_u8, (B, 2 * self.net_h, 2 * self.net_w, 3), dtype=torch.uint8, name="out_u8", output=True)
         if out_f32 is not None:
-            out_f32 = self._in(out_f32, (B, 3, 2 * self.net_h, 2 * self.net_w), name="out_f32")
+            out_f32 = self._in(out_f32, (B, 3, 2 * self.net_h, 2 * self.net_w), name="out_f32", output=True)
         self._check(self._lib.cs_frame(self._ctx, fr.data_ptr(), kt.data_ptr() if kt is not None else None,
                                        kc.data_ptr() if kc is not None else None,
                                        out_f32.data_ptr() if out_f32 is not None else None,
@@ -289,7 +304,7 @@ class Engine:
         M = np.ascontiguousarray(np.asarray(M_c2o, dtype=np.float64).reshape(B, -1, 3)[:, :2, :]).reshape(B, 6)
         if out is None:
             out = self._new(B, H, W, 3, dtype=torch.uint8)
-        out = self._in(out, (B, H, W, 3), dtype=torch.uint8, name="out")
+        out = self._in(out, (B, H, W, 3), dtype=torch.uint8, name="out", output=True)
         self._check(self._lib.cs_paste_back(self._ctx, crop.data_ptr(), mask.data_ptr(), M.ctypes.data_as(C.POINTER(C.c_double)),
                                             ori.data_ptr(), out.data_ptr(), B, hc, wc, H, W, self._stream()))
         return out

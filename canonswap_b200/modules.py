@@ -39,14 +39,21 @@ _BUFFER_LEAVES = ("running_mean", "running_var", "num_batches_tracked", "weight_
 
 
 class _EngineHub:
-    """Shares one Engine per (net_h, net_w) among the five mirror modules."""
+    """Shares one Engine per (net_h, net_w) among the mirror modules.
+
+    Options set through `set_option` are kept at hub level and re-applied to every engine the hub (re)builds.  An engine is
+    rebuilt only when the weights change (load_state_dict / .to()) or when a call needs a larger batch than THAT engine was
+    built for; handles held by callers keep working until then and raise a clear CanonSwapError afterwards (Engine.close)."""
 
     def __init__(self, device_id: int = 0, max_batch: int = 8, conv_impl: int = 0):
         self.device_id, self.max_batch, self.conv_impl = device_id, max_batch, conv_impl
         self.modules: Dict[str, "_SpecModule"] = {}
         self.engines: Dict[Tuple[int, int], Engine] = {}
         self.identity: Optional[torch.Tensor] = None
+        self._identity_key = None        # (data_ptr, _version, shape) of the dlatents tensor the identity was taken from
+        self.options: Dict[int, int] = {}
         self.version = 0
+        self.last_hw: Optional[Tuple[int, int]] = None   # resolution of the engine used last (cs_keypoints runs on any engine)
 
     def register(self, mod: "_SpecModule"):
         self.modules[mod.NET] = mod
@@ -58,17 +65,28 @@ class _EngineHub:
         self.engines.clear()
         self.version += 1
 
+    def set_option(self, option: int, value: int):
+        """Library option (cs_set_option) for every current and future engine of this hub."""
+        self.options[int(option)] = int(value)
+        for e in self.engines.values():
+            try:
+                e.set_option(option, value)
+            except CanonSwapError:
+                pass                       # a pack-time option: takes effect when the engine is rebuilt
+
     def engine(self, net_hw: Tuple[int, int], batch: int = 1) -> Engine:
         missing = [n for n in spec.NETS if n not in self.modules]   # the motion extractor is optional
         if missing:
             raise CanonSwapError(f"engine needs all five hot-path networks; not bound: {missing}")
-        if batch > self.max_batch:
-            self.max_batch = batch
-            self.invalidate()
+        self.last_hw = net_hw
         e = self.engines.get(net_hw)
+        if e is not None and batch > e.max_batch:                   # grow only the engine that needs it
+            e.close()
+            e = None
         if e is None:
             weights = {n: m.state_dict() for n, m in self.modules.items()}
-            e = Engine(weights, net_hw=net_hw, max_batch=self.max_batch, device=self.device_id, conv_impl=self.conv_impl)
+            e = Engine(weights, net_hw=net_hw, max_batch=max(self.max_batch, batch), device=self.device_id, conv_impl=self.conv_impl,
+                       options=self.options)
             if self.identity is not None:
                 e.set_identity(self.identity)
             self.engines[net_hw] = e
@@ -193,15 +211,45 @@ class transfer_model2(_SpecModule):
     NET = "transfer"
 
     def forward(self, x: torch.Tensor, dlatents: torch.Tensor, return_mask: bool = False):
-        """reference adaptive_modulate.py:522-554. dlatents [1 or B,512]: one identity per call."""
-        d = dlatents.reshape(-1, spec.LATENT).float()
-        if d.shape[0] > 1 and not bool((d == d[:1]).all()):
-            raise CanonSwapError("transfer_model2: one source identity per call (the pipeline broadcasts a single source_id)")
+        """reference adaptive_modulate.py:522-554.  dlatents [1 or B,512].
+
+        The engine keeps the modulated weight sets of ONE identity resident (adaptive_modulate.py:148-170 hoisted out of the
+        frame loop); per-sample identities (the reference's groups=N path, :150-167) are served by grouping the batch rows per
+        distinct identity -- one cs_set_identity + cs_swap per group.  The pipeline's case (the same `source_id` tensor every
+        frame, can_swap_pipeline_e2e.py:253) costs no device synchronisation after the first call."""
+        d = dlatents.reshape(-1, spec.LATENT)
+        B = int(x.shape[0])
+        if d.shape[0] not in (1, B):
+            raise CanonSwapError(f"transfer_model2: dlatents batch {d.shape[0]} does not match x batch {B}")
         hub = self._hub
-        if hub.identity is None or hub.identity.device != d.device or not torch.equal(hub.identity, d[0]):
-            hub.set_identity(d[0])
         eng = self._engine(x, (4 * int(x.shape[3]), 4 * int(x.shape[4])))
-        return eng.swap(x.float(), return_mask=return_mask)
+        key = (dlatents.data_ptr(), dlatents._version, tuple(dlatents.shape), str(dlatents.device))
+        if hub._identity_key == key and hub.identity is not None:
+            return eng.swap(x.float(), return_mask=return_mask)                 # same tensor as last call: nothing to compare
+        dh = d.detach().float().cpu()                                            # ONE device->host read of the latents
+        groups = {}
+        for i in range(dh.shape[0]):
+            groups.setdefault(dh[i].numpy().tobytes(), []).append(i)
+        if len(groups) == 1:
+            if hub.identity is None or hub.identity.device != x.device or not torch.equal(hub.identity.cpu(), dh[0]):
+                hub.set_identity(dh[0].to(x.device))
+            hub._identity_key = key
+            return eng.swap(x.float(), return_mask=return_mask)
+        # several identities in one batch
+        hub._identity_key = None
+        out = torch.empty(B, 32, 16, x.shape[3], x.shape[4], device=x.device)
+        masks = [torch.empty(B, 1, x.shape[3], x.shape[4], device=x.device) for _ in range(7)] if return_mask else None
+        for rows in groups.values():
+            idx = torch.tensor(rows, device=x.device)
+            hub.set_identity(dh[rows[0]].to(x.device))
+            r = eng.swap(x.float().index_select(0, idx).contiguous(), return_mask=return_mask)
+            if return_mask:
+                out.index_copy_(0, idx, r[0])
+                for m_all, m in zip(masks, r[1]):
+                    m_all.index_copy_(0, idx, m)
+            else:
+                out.index_copy_(0, idx, r)
+        return (out, masks) if return_mask else out
 
 
 transfer_model_big = transfer_model2        # reference adaptive_modulate.py alias used by can_swap_e2e.py:24
@@ -240,8 +288,16 @@ class can_swapper(object):
     path; pass the reference's torch modules to keep `get_kp_info` / `getid`.
     """
 
+    COMBINED_WEIGHTS = "pretrained_weights/combined_weights.pth"      # reference can_swap_e2e.py:88
+    ARCFACE_CHECKPOINT = "pretrained_weights/arcface_checkpoint.tar"  # reference can_swap_e2e.py:82
+
     def __init__(self, inference_cfg=None, *, weights=None, device_id: Optional[int] = None, max_batch: int = 8,
                  motion_extractor=None, netArc=None, conv_impl: int = 0):
+        """`can_swapper(inference_cfg)` alone behaves like the reference constructor (can_swap_e2e.py:44-85): it checks
+        `inference_cfg.models_config` against the one architecture this library implements, loads
+        `pretrained_weights/combined_weights.pth` when that file exists (load_cpk, :87-100) and the ArcFace encoder from
+        `pretrained_weights/arcface_checkpoint.tar` when that file exists (:82-85; it needs the reference's `models` package on
+        sys.path to unpickle, as in the reference).  The keyword arguments are extras for callers without those files."""
         self.inference_cfg = inference_cfg
         if device_id is None:
             device_id = getattr(inference_cfg, "device_id", 0) if inference_cfg is not None else 0
@@ -252,7 +308,9 @@ class can_swapper(object):
                                  "(reference inference_canswap.py:58 forces it off)")
         self.device_id = device_id
         self.device = f"cuda:{device_id}"
+        self.compile = False              # flag_do_torch_compile has nothing to compile here
         self.input_shape = tuple(getattr(inference_cfg, "input_shape", (256, 256)))
+        self._check_models_config(getattr(inference_cfg, "models_config", None))
         self._hub = _EngineHub(device_id=device_id, max_batch=max_batch, conv_impl=conv_impl)
         self.appearance_feature_extractor = AppearanceFeatureExtractor(hub=self._hub)
         self.warping_module = WarpingNetwork(hub=self._hub)
@@ -266,9 +324,48 @@ class can_swapper(object):
         self.netArc = netArc
         if weights is not None:
             self.load_cpk(weights)
+        else:
+            self.load_cpk()               # the reference's default path, when it exists (can_swap_e2e.py:87-100)
+        if self.netArc is None:
+            self._load_arcface()
 
-    # reference can_swap_e2e.py:87-100 (path or the already-loaded dict)
-    def load_cpk(self, combined_weights="pretrained_weights/combined_weights.pth"):
+    @staticmethod
+    def _check_models_config(path):
+        """reference can_swap_e2e.py:60-62: the hyper-parameters of models.yaml must be the ones this library is built for."""
+        import os
+        if not path or not os.path.exists(path):
+            return
+        import yaml
+        cfg = yaml.safe_load(open(path))["model_params"]
+        want = {"appearance_feature_extractor_params": {"image_channel": 3, "block_expansion": 64, "num_down_blocks": 2,
+                                                        "max_features": 512, "reshape_channel": 32, "reshape_depth": 16,
+                                                        "num_resblocks": 6},
+                "motion_extractor_params": {"num_kp": 21, "backbone": "convnextv2_tiny"}}
+        for sec, kv in want.items():
+            for k, v in kv.items():
+                if cfg.get(sec, {}).get(k, v) != v:
+                    raise CanonSwapError(f"models_config {path}: {sec}.{k} = {cfg[sec][k]!r}, this library implements {v!r}")
+        wp = cfg.get("warping_module_params", {})
+        dm = wp.get("dense_motion_params", {})
+        if (wp.get("num_kp", 21), wp.get("reshape_channel", 32), dm.get("num_blocks", 5), dm.get("reshape_depth", 16),
+                dm.get("compress", 4), dm.get("max_features", 1024), dm.get("block_expansion", 32)) != (21, 32, 5, 16, 4, 1024, 32):
+            raise CanonSwapError(f"models_config {path}: unsupported warping_module_params")
+
+    def _load_arcface(self):
+        """reference can_swap_e2e.py:81-85 -- only when the checkpoint is there (the encoder runs once per source, outside the
+        hot path, as the reference's own torch module)."""
+        import os
+        if os.path.exists(self.ARCFACE_CHECKPOINT):
+            net = torch.load(self.ARCFACE_CHECKPOINT, map_location=torch.device("cpu"), weights_only=False)
+            self.netArc = net.to(self.device).eval()
+
+    # reference can_swap_e2e.py:87-100 (the default path, a path, or the already-loaded dict)
+    def load_cpk(self, combined_weights=None):
+        import os
+        if combined_weights is None:
+            if not os.path.exists(self.COMBINED_WEIGHTS):
+                return                     # as the reference: silently keeps the initial (here: zero) weights
+            combined_weights = self.COMBINED_WEIGHTS
         if isinstance(combined_weights, (str, bytes)):
             combined_weights = torch.load(combined_weights, map_location=torch.device("cpu"))
         self.appearance_feature_extractor.load_state_dict(combined_weights["appearance_feature_extractor"])
@@ -281,6 +378,10 @@ class can_swapper(object):
                 self.motion_extractor = MotionExtractor(hub=self._hub)
             self.motion_extractor.load_state_dict(combined_weights["motion_extractor"])
 
+    def set_option(self, option: int, value: int):
+        """Library option for every engine of this wrapper (kept across engine rebuilds)."""
+        self._hub.set_option(option, value)
+
     # reference can_swap_e2e.py:174-199
     def get_kp_info(self, x: torch.Tensor, **kwargs) -> dict:
         if self.motion_extractor is None:
@@ -291,7 +392,7 @@ class can_swapper(object):
         if kwargs.get("flag_refine_info", True):
             bs = kp_info["kp"].shape[0]
             if heads is not None:
-                deg = self._hub.engine(self.input_shape, bs).keypoints(heads)["deg"]
+                deg = self._hub.engine(self._hub.last_hw or self.input_shape, bs).keypoints(heads)["deg"]
                 kp_info["pitch"], kp_info["yaw"], kp_info["roll"] = deg[:, 0:1], deg[:, 1:2], deg[:, 2:3]
             else:
                 for k in ("pitch", "yaw", "roll"):
@@ -307,7 +408,7 @@ class can_swapper(object):
         heads = kp_info.get("_heads")
         if heads is None:
             raise CanonSwapError("transform_keypoint: kp_info must come from this can_swapper's get_kp_info / motion_extractor")
-        return self._hub.engine(self.input_shape, int(heads.shape[0])).keypoints(heads)["x_s"]
+        return self._hub.engine(self._hub.last_hw or self.input_shape, int(heads.shape[0])).keypoints(heads)["x_s"]
 
     def getid(self, img):
         if self.netArc is None:

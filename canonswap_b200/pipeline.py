@@ -190,3 +190,103 @@ class FullLoopPipeline:
             self.d2h_bytes += pasted.numel()
         st.synchronize()
         return T
+
+
+class V2IPipeline:
+    """The video-to-image variant (reference src/can_swap_pipeline_v2i.py:254-321) on the B200 path: the identity of the
+    driving video is swapped onto ONE source image, which is then animated by the driving expressions.
+
+      prepare()    once per source (:86-98 execute_face_canonical + the `i == 0` block :285-304): source -> canonical volume ->
+                   swap -> decode -> re-extract motion + appearance of the swapped canonical image.  The loop extracts the
+                   appearance volume of that SAME image every frame (:308); it is computed once here and kept resident.
+      broadcast()  the one collective: the state (the 32x16xhxw appearance volume, 8.4 MB at 512 px, + ~0.6 KB of keypoints /
+                   pose) from rank 0 over NCCL -- no other rank needs the source image, the identity or the swap module.
+      run()        frames i % world == rank: x_t_2 = scale * (kp_swap @ R + exp_i) + t (:305) and
+                   out = warp_decode(feature, x_swap, x_t_2) (:309) in ONE cs_frame call per batch (CS_FRAME_V2I_FEATURE),
+                   driving expressions from pinned host memory in, u8 frames to pinned host memory out.
+    """
+    STATE_KEYS = ("feature", "x_swap", "kp_swap", "R_swap", "t_swap", "scale_swap")
+
+    def __init__(self, swapper, net_hw=(256, 256), batch: int = 8):
+        """net_hw: the size the swapped canonical image is resized to before it is animated -- (256, 256) in the reference
+        (can_swap_pipeline_v2i.py:294), whatever the size of the source crop; output frames are twice that."""
+        self.sw, self.batch = swapper, batch
+        self.net_h, self.net_w = net_hw
+        self.dev = torch.device(swapper.device)
+        self.state = None
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def prepare(self, source_crop: torch.Tensor, driving_id: torch.Tensor):
+        """source_crop [1,3,H,W] fp32 in [0,1] on the device (prepare_source), driving_id [1,512]."""
+        sw = self.sw
+        x_s_info = sw.get_kp_info(source_crop)                                        # :87
+        f_s = sw.extract_feature_3d(source_crop)                                      # :89
+        x_s = sw.transform_keypoint(x_s_info)                                         # :90
+        x_d = x_s_info["scale"] * x_s_info["kp"]                                      # :94
+        f_s_can, occ = sw.warping_module.warp(f_s, x_s, x_d)                          # :97
+        f_can_swap = sw.swap_module(f_s_can, driving_id)                              # :286
+        swap_can = sw.conv_decode(f_can_swap, occ)                                    # :289
+        lr = torch.nn.functional.interpolate(swap_can, size=(self.net_h, self.net_w), mode="bilinear", align_corners=False)   # :294
+        x_swap_info = sw.get_kp_info(lr)                                              # :297
+        x_swap = sw.transform_keypoint(x_swap_info)                                   # :298
+        eng = sw.engine((self.net_h, self.net_w), self.batch)
+        R_swap = eng.keypoints(x_s_info["_heads"])["R"]                               # :301 get_rotation_matrix of the SOURCE pose
+        t_swap = x_s_info["t"].clone()
+        t_swap[..., 2] = 0                                                            # :303
+        self.state = {"feature": sw.extract_feature_3d(lr).contiguous(), "x_swap": x_swap.contiguous(),
+                      "kp_swap": x_swap_info["kp"].contiguous(), "R_swap": R_swap.contiguous(), "t_swap": t_swap.contiguous(),
+                      "scale_swap": x_s_info["scale"].clone().contiguous(), "swap_can": swap_can}
+        return self.state
+
+    def _shapes(self):
+        h, w = self.net_h // 4, self.net_w // 4
+        return {"feature": (1, 32, 16, h, w), "x_swap": (1, 21, 3), "kp_swap": (1, 21, 3), "R_swap": (1, 3, 3), "t_swap": (1, 3),
+                "scale_swap": (1, 1)}
+
+    def broadcast(self, src: int = 0):
+        """One NCCL broadcast of the per-source state from `src` (a no-op without a process group)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return self.state
+        shapes = self._shapes()
+        n = sum(int(torch.tensor(s).prod()) for s in shapes.values())
+        buf = torch.empty(n, dtype=torch.float32, device=self.dev)
+        if dist.get_rank() == src:
+            torch.cat([self.state[k].reshape(-1).float() for k in self.STATE_KEYS], out=buf)
+        dist.broadcast(buf, src=src)
+        st, o = {}, 0
+        for k in self.STATE_KEYS:
+            m = int(torch.tensor(shapes[k]).prod())
+            st[k] = buf[o:o + m].reshape(shapes[k]).clone()
+            o += m
+        self.state = st
+        return st
+
+    def run(self, exp_driving: torch.Tensor, out_u8: torch.Tensor, rank: int = 0, world: int = 1, out_local: bool = False) -> int:
+        """exp_driving [T,21,3] fp32 (x_t_info['exp'] of every driving frame) and out_u8 [T or local,2H,2W,3]: PINNED host
+        tensors.  Processes frames i % world == rank; returns how many.  Synchronises before returning."""
+        st = self.state
+        if st is None:
+            raise RuntimeError("V2IPipeline.run before prepare() / broadcast()")
+        eng = self.sw.engine((self.net_h, self.net_w), self.batch)
+        mine = shard_indices(int(exp_driving.shape[0]), rank, world)
+        done = 0
+        for ids in batches(mine, self.batch):
+            b = len(ids)
+            if world == 1:
+                delta = exp_driving[ids[0]:ids[-1] + 1].to(self.dev, non_blocking=True)
+            else:
+                delta = exp_driving[torch.tensor(ids)].to(self.dev, non_blocking=True)
+            self.h2d_bytes += delta.numel() * 4
+            x_t_2 = st["scale_swap"] * (st["kp_swap"] @ st["R_swap"] + delta) + st["t_swap"]          # :305
+            u8, _ = eng.frame(st["feature"], st["x_swap"].expand(b, -1, -1).contiguous(), x_t_2.contiguous(), v2i_feature=True)
+            if out_local:
+                out_u8[done:done + b].copy_(u8, non_blocking=True)
+            elif world == 1:
+                out_u8[ids[0]:ids[-1] + 1].copy_(u8, non_blocking=True)
+            else:
+                for j, i in enumerate(ids):
+                    out_u8[i].copy_(u8[j], non_blocking=True)
+            self.d2h_bytes += u8.numel()
+            done += b
+        torch.cuda.current_stream(self.dev).synchronize()
+        return len(mine)

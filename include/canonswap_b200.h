@@ -64,6 +64,10 @@ typedef struct cs_tensor_desc {
 #define CS_FRAME_V2I         4   /* video-to-image per-frame body (can_swap_pipeline_v2i.py:308-309) instead of the e2e one:
                                     out = warp_decode(extract_feature_3d(frames), kp_source = kp_t, kp_driving = kp_can);
                                     no identity needed (the swap ran once per source, outside the loop) */
+#define CS_FRAME_V2I_FEATURE 16  /* with CS_FRAME_V2I: `frames` is not images but ONE appearance volume [1,32,16,h,w] fp32 (NCDHW),
+                                    shared by the B samples -- the v2i loop extracts the features of the SAME swapped canonical image
+                                    every frame (can_swap_pipeline_v2i.py:308), so they are computed once per source and stay
+                                    resident: out = G(W.forward(feature, kp_driving = kp_can, kp_source = kp_t)) */
 
 /* options of cs_set_option */
 #define CS_OPT_CONV_IMPL 1       /* 0 = auto (tcgen05 where eligible), 1 = force SIMT fp32 convs (debug) */

@@ -330,6 +330,46 @@ def frame_v2i(weights, I, kp_source, kp_driving):
         return spade_decoder(sdG, wf["out"])
 
 
+V2I_ANIMATE_HW = (256, 256)      # the size the reference resizes the swapped canonical image to (can_swap_pipeline_v2i.py:294)
+
+
+def v2i_source_state(weights, I_s, driving_id):
+    """The once-per-source part of the video-to-image pipeline: execute_face_canonical (reference
+    src/can_swap_pipeline_v2i.py:86-98) and the `i == 0` block of its frame loop (:285-304).
+    I_s [1,3,H,W] in [0,1], driving_id [1,512].  Returns the frame-invariant state the loop body reads."""
+    sdW, sdG, sdM = weights["warping_module"], weights["spade_generator"], weights["motion_extractor"]
+    with torch.no_grad():
+        info = motion_extractor(sdM, I_s)                                          # :87 get_kp_info(I_s)
+        kp_s = info["kp"].reshape(1, -1, 3)                                        # :88
+        f_s = appearance_feature_extractor(weights["appearance_feature_extractor"], I_s)   # :89
+        x_s = transform_keypoint(info)                                             # :90
+        x_d = info["scale"] * kp_s                                                 # :94 scale_new * x_c_s
+        f_s_can, occ = warp(sdW, f_s, x_s, x_d)                                    # :97
+        f_can_swap = swap_module(weights["transfer"], f_s_can, driving_id)         # :286
+        swap_can = spade_decoder(sdG, warp_out(sdW, f_can_swap, occ))              # :289 conv_decode
+        swap_can_lr = F.interpolate(swap_can, size=V2I_ANIMATE_HW, mode="bilinear", align_corners=False)   # :294
+        info2 = motion_extractor(sdM, swap_can_lr)                                 # :297
+        x_swap = transform_keypoint(info2)                                         # :298
+        deg = [headpose_pred_to_degree(info[k]) for k in ("pitch", "yaw", "roll")]
+        R_swap = get_rotation_matrix(deg[0], deg[1], deg[2])                       # :301 (the SOURCE's rotation)
+        t_swap = info["t"].clone()
+        t_swap[..., 2] = 0                                                         # :303
+        f2 = appearance_feature_extractor(weights["appearance_feature_extractor"], swap_can_lr)   # :308 (frame-invariant)
+    return {"swap_can": swap_can, "swap_can_lr": swap_can_lr, "feature": f2, "x_swap": x_swap, "kp_swap": info2["kp"].reshape(1, -1, 3),
+            "R_swap": R_swap, "t_swap": t_swap, "scale_swap": info["scale"], "f_s_can": f_s_can, "occ": occ}
+
+
+def v2i_frames(weights, st, delta_t):
+    """The per-frame body of the v2i loop (reference can_swap_pipeline_v2i.py:305-312) for a batch of driving expressions
+    delta_t [B,21,3]: x_t_2 = scale_swap * (kp_swap @ R_swap + delta_t) + t_swap; out = warp_decode(F(swap_can_256), x_swap, x_t_2)."""
+    B = delta_t.shape[0]
+    with torch.no_grad():
+        x_t_2 = st["scale_swap"] * (st["kp_swap"] @ st["R_swap"] + delta_t) + st["t_swap"]        # :305
+        wf = warping_forward(weights["warping_module"], st["feature"].expand(B, -1, -1, -1, -1),
+                             kp_driving=x_t_2, kp_source=st["x_swap"].expand(B, -1, -1))        # :309 -> can_swap_e2e.py:298
+        return spade_decoder(weights["spade_generator"], wf["out"]), x_t_2
+
+
 # ------------------------------------------------------------------------------------------
 # motion extractor M + keypoint transform (SURVEY.md section 8f rank 1)
 # ------------------------------------------------------------------------------------------

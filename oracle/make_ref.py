@@ -1,7 +1,8 @@
 """Recipe for oracle/_ref: the reference's OWN implementation of the hot path, made runnable on the GPU box's host cores.
 
 TEST / MEASUREMENT INFRASTRUCTURE ONLY.  The reference is pure Python: its hot-path arithmetic lives in nine files under
-`/root/reference/src/modules` plus `src/config/models.yaml`.  `/root/reference` does not exist on the GPU box, so this
+`/root/reference/src/modules` plus `src/config/models.yaml`; the per-frame loop that calls them is
+`src/can_swap_pipeline_e2e.py` (+ the helpers it imports from `src/utils`, `src/config`).  `/root/reference` does not exist on the GPU box, so this
 script copies exactly those files, unmodified, from where they lie into `oracle/_ref/` (git-ignored -- reference sources
 never enter the repository history -- but shipped to the box with the snapshot, like the built .so files).  It is run by
 `__graft_entry__.build()` whenever `/root/reference` is present.
@@ -33,8 +34,21 @@ FILES = [
     "src/modules/adaptive_modulate.py",
     "src/modules/convnextv2.py",
     "src/modules/motion_extractor.py",
+    "src/modules/stitching_retargeting_network.py",     # imported by src/utils/helper.py
     "src/config/models.yaml",
+    "src/config/__init__.py",
+    "src/config/base_config.py",
+    "src/config/argument_config.py",
+    "src/config/inference_config.py",
+    "src/config/crop_config.py",
     "src/utils/camera.py",
+    "src/utils/helper.py",
+    "src/utils/crop.py",
+    "src/utils/rprint.py",
+    # the caller of the path: tests/ref_pipeline_harness.py executes its LOOP C text (:223-283) and make_motion_template
+    # (:101-135) against the drop-in can_swapper, with the I/O imports stubbed
+    "src/can_swap_pipeline_e2e.py",
+    "src/can_swap_pipeline_v2i.py",
 ]
 
 

@@ -148,3 +148,43 @@ def test_world_size_2_gloo_sharding_reassembles_exactly(tmp_path):
     assert torch.equal(sid, sid0)                                  # broadcast id equals the root's bit-for-bit
     exp = torch.stack([frames[i].long() * 3 + int(sid0[0, i % 512].item() * 1e6) % 7 for i in range(37)])
     assert np.array_equal(got, exp.numpy())
+
+
+def test_can_swapper_constructor_behaves_like_the_reference(tmp_path, monkeypatch, synth_w):
+    """`can_swapper(inference_cfg)` alone (reference can_swap_e2e.py:44-100): reads models_config, loads
+    pretrained_weights/combined_weights.pth when it exists, keeps going without it (as the reference's load_cpk does)."""
+    import types
+    from canonswap_b200 import modules
+    from canonswap_b200.engine import CanonSwapError
+    monkeypatch.chdir(tmp_path)
+    yaml_path = None
+    for root in ("/root/reference", os.path.join(ROOT, "oracle", "_ref")):
+        p = os.path.join(root, "src", "config", "models.yaml")
+        if os.path.exists(p):
+            yaml_path = p
+    cfg = types.SimpleNamespace(device_id=0, flag_force_cpu=False, flag_use_half_precision=False, flag_do_torch_compile=False,
+                                models_config=yaml_path, input_shape=(256, 256))
+    sw = modules.can_swapper(cfg)                                      # no checkpoint in the cwd: zero weights, no error
+    assert sw.netArc is None and float(sw.refine_module.state_dict()["resblocks1.0.conv1.weight"].abs().sum()) == 0.0
+    os.makedirs("pretrained_weights")
+    small = {k: synth_w[k] for k in ("appearance_feature_extractor", "refine")}
+    full = dict(synth_w)
+    torch.save({**full, **small}, "pretrained_weights/combined_weights.pth")
+    sw = modules.can_swapper(cfg)                                      # the reference's two-argument-free construction
+    for name, m in (("appearance_feature_extractor", sw.appearance_feature_extractor), ("refine", sw.refine_module),
+                    ("transfer", sw.swap_module)):
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, synth_w[name][k]), (name, k)
+    assert sw.device == "cuda:0" and sw.input_shape == (256, 256)
+    if yaml_path:                                                      # a config this library does not implement is refused
+        import yaml
+        bad = yaml.safe_load(open(yaml_path))
+        bad["model_params"]["appearance_feature_extractor_params"]["num_resblocks"] = 4
+        yaml.safe_dump(bad, open("bad.yaml", "w"))
+        cfg.models_config = "bad.yaml"
+        with pytest.raises(CanonSwapError):
+            modules.can_swapper(cfg)
+    cfg.models_config = yaml_path
+    cfg.flag_force_cpu = True
+    with pytest.raises(CanonSwapError):
+        modules.can_swapper(cfg)

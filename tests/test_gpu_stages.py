@@ -285,3 +285,24 @@ def test_reference_surface_mirror(synth_w):
     assert rec_can.shape == (1, 3, 256, 256)
     u8, _ = sw.swap_frames(I_s, x_t, x_can)
     assert np.abs(u8.cpu().numpy().astype(int) - img.astype(int)).max() <= 1
+
+
+def test_swap_per_sample_identities(case128, synth_w):
+    """dlatents [B,512] with DIFFERENT identities per sample (the reference's groups=N path, adaptive_modulate.py:150-167):
+    served per distinct identity; the pipeline's case (one identity, the same tensor every frame) is one call without
+    host synchronisation after the first."""
+    from canonswap_b200.modules import can_swapper
+    eng, inp, ref = case128
+    g = torch.Generator().manual_seed(77)
+    ids = torch.nn.functional.normalize(torch.randn(2, 512, generator=g))
+    exp = O.swap_module(synth_w["transfer"], ref["f_can"], ids)
+    sw = can_swapper(weights=synth_w, device_id=0, max_batch=2)
+    out = sw.swap_module(ref["f_can"].cuda(), ids.cuda())
+    _close(out, exp, "per-sample identities")
+    one = ids[:1].cuda()
+    a = sw.swap_module(ref["f_can"].cuda(), one)
+    b = sw.swap_module(ref["f_can"].cuda(), one)              # same tensor again: the cached-identity fast path
+    assert torch.equal(a, b)
+    _close(a, O.swap_module(synth_w["transfer"], ref["f_can"], ids[:1].expand(2, -1)), "one identity")
+    with pytest.raises(Exception):
+        sw.swap_module(ref["f_can"].cuda(), torch.zeros(3, 512, device="cuda"))
