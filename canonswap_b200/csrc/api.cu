@@ -593,6 +593,16 @@ int cs_soft_erosion(cs_ctx* ctx, const float* mask, const float* kernel, float* 
   CS_API_END(ctx)
 }
 
+int cs_parse_mask(cs_ctx* ctx, const float* logits, int B, int C, int h, int w, int H, int W, uint64_t valid_classes, float* mask,
+                  int32_t* labels, void* stream) {
+  CS_API_BEGIN(ctx)
+  CS_REQUIRE(logits && mask && B >= 1 && B <= 65535 && C >= 1 && C <= 64 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && h <= 16384 &&
+                 w <= 16384 && H <= 16384 && W <= 16384, CS_ERR_INVALID, "cs_parse_mask: bad argument (1 <= C <= 64 classes)");
+  Net n = make_net(ctx, stream, false);
+  parse_mask(n.L, logits, B, C, h, w, H, W, (unsigned long long)valid_classes, mask, labels);
+  CS_API_END(ctx)
+}
+
 // ---- per-kernel-family timing (bench.py roofline leg) ---------------------------------------------
 int cs_profile(cs_ctx* ctx, int enable) {
   CS_API_BEGIN(ctx)

@@ -176,6 +176,9 @@ void soft_erosion(const Launcher& L, const float* x, float* out, uint8_t* hard, 
 void paste_back(const Launcher& L, const uint8_t* crop, const float* mask, const double* M_c2o, const uint8_t* ori, uint8_t* out, int B,
                 int hc, int wc, int H, int W);
 
+void parse_mask(const Launcher& L, const float* logits, int B, int C, int h, int w, int H, int W, unsigned long long valid, float* mask,
+                int* labels);
+
 // net.cu : stages on the internal (channels-last) layout
 void run_F(Net& n, const float* img_cl, int B, float* vol_out);
 void run_warp(Net& n, const float* vol_in, const float* kp_source, const float* kp_driving, int B,

@@ -222,4 +222,54 @@ void soft_erosion(const Launcher& L, const float* x, float* out, uint8_t* hard, 
   check_launch("soft_erosion_apply");
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Face-parsing post-processing (the step BEFORE the path, reference src/can_swap_pipeline_e2e.py:183-190):
+//   upsampled = F.interpolate(logits, size=(H, W), mode='bilinear', align_corners=False)
+//   labels    = upsampled.argmax(dim=1);   mask = isin(labels, valid_list)
+// fused into one kernel: no [B,19,512,512] upsampled tensor (20 MB per frame), no label tensor unless asked for.  The
+// interpolation follows ATen's upsample_bilinear2d arithmetic (source index scale * (dst + 0.5) - 0.5 clamped at 0, weights
+// 1 - lambda / lambda, rows combined after columns), with explicit round-to-nearest products and sums so that no FMA
+// contraction can move a near-tie; argmax keeps the FIRST maximal class, as torch does.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) parse_mask_kernel(const float* __restrict__ logits, int B, int C, int h, int w, int H, int W,
+                                                         unsigned long long valid, float* __restrict__ mask, int* __restrict__ labels) {
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  const long total = (long)B * H * W;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % W); long t = i / W;
+    const int oy = (int)(t % H); const int b = (int)(t / H);
+    float fy = __fsub_rn(__fmul_rn(sh, (float)oy + 0.5f), 0.5f); if (fy < 0.f) fy = 0.f;
+    float fx = __fsub_rn(__fmul_rn(sw, (float)ox + 0.5f), 0.5f); if (fx < 0.f) fx = 0.f;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly1 = __fsub_rn(fy, (float)y0), lx1 = __fsub_rn(fx, (float)x0);
+    const float ly0 = __fsub_rn(1.f, ly1), lx0 = __fsub_rn(1.f, lx1);
+    const float* base = logits + (long)b * C * h * w;
+    float best = 0.f; int arg = 0;
+    for (int c = 0; c < C; ++c) {
+      const float* pc = base + (long)c * h * w;
+      const float v00 = __ldg(pc + (long)y0 * w + x0), v01 = __ldg(pc + (long)y0 * w + x1);
+      const float v10 = __ldg(pc + (long)y1 * w + x0), v11 = __ldg(pc + (long)y1 * w + x1);
+      const float r0 = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
+      const float r1 = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
+      const float v = __fadd_rn(__fmul_rn(ly0, r0), __fmul_rn(ly1, r1));
+      if (c == 0 || v > best || (v != v && best == best)) { best = v; arg = c; }    // first maximum; a NaN wins, as in torch
+    }
+    mask[i] = ((valid >> arg) & 1ull) ? 1.f : 0.f;
+    if (labels) labels[i] = arg;
+  }
+}
+
+void parse_mask(const Launcher& L, const float* logits, int B, int C, int h, int w, int H, int W, unsigned long long valid, float* mask,
+                int* labels) {
+  L.count();
+  if (L.dry) return;
+  const long total = (long)B * H * W;
+  long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
+  ProfScope ps(L, PK_OTHER, 0.0, (double)B * C * h * w * 4.0 + (double)total * 4.0, "parse_mask");
+  parse_mask_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(logits, B, C, h, w, H, W, valid, mask, labels);
+  check_launch("parse_mask");
+}
+
 }  // namespace cs

@@ -322,6 +322,25 @@ class Engine:
                                               float(threshold), int(iterations), self._stream()))
         return out, hard.bool()
 
+    VALID_PARSE_LABELS = (1, 2, 4, 5, 6, 7, 10, 11, 12)      # reference can_swap_pipeline_e2e.py:48
+
+    def parse_mask(self, logits: torch.Tensor, out_hw=(512, 512), valid_list=VALID_PARSE_LABELS, want_labels: bool = False):
+        """The post-processing of the face parser's logits (reference can_swap_pipeline_e2e.py:183-190): bilinear upsample to
+        out_hw (align_corners=False) -> argmax over the classes -> isin(valid_list).  logits [B,C,h,w] fp32 on the device ->
+        mask [B,H,W] fp32 of 1.0 / 0.0 (what SoftErosion consumes) and, on request, the int32 label map."""
+        B, Cc, h, w = (int(v) for v in logits.shape)
+        H, W = int(out_hw[0]), int(out_hw[1])
+        lg = self._in(logits, (B, Cc, h, w), name="logits")
+        valid = 0
+        for c in valid_list:
+            if 0 <= int(c) < Cc:
+                valid |= 1 << int(c)
+        mask = self._new(B, H, W)
+        labels = self._new(B, H, W, dtype=torch.int32) if want_labels else None
+        self._check(self._lib.cs_parse_mask(self._ctx, lg.data_ptr(), B, Cc, h, w, H, W, valid, mask.data_ptr(),
+                                            labels.data_ptr() if labels is not None else None, self._stream()))
+        return (mask, labels) if want_labels else mask
+
     # ---- measurement -------------------------------------------------------------------------------
     PROFILE_FAMILIES = ("conv_tcgen05", "conv_simt", "prep", "stats", "sampling", "other")
 

@@ -171,8 +171,10 @@ class FullLoopPipeline:
         self.d2h_bytes = 0
 
     def run(self, crops_u8: torch.Tensor, parse_masks: torch.Tensor, M_c2o, frames_u8: torch.Tensor, out_u8: torch.Tensor) -> int:
-        """crops_u8 [T,h,w,3] u8, parse_masks [T,2h,2w] f32, frames_u8 / out_u8 [T,H,W,3] u8: PINNED host tensors; M_c2o [T,3,3]
-        (or [T,2,3]) numpy.  Returns the number of frames; synchronises before returning."""
+        """crops_u8 [T,h,w,3] u8, parse_masks [T,2h,2w] f32 -- or the face parser's raw logits [T,C,hl,wl] f32, whose
+        post-processing (upsample -> argmax -> isin, can_swap_pipeline_e2e.py:183-190) then runs on the device too --,
+        frames_u8 / out_u8 [T,H,W,3] u8: PINNED host tensors; M_c2o [T,3,3] (or [T,2,3]) numpy.  Returns the number of frames;
+        synchronises before returning."""
         import numpy as np
         T = int(crops_u8.shape[0])
         M = np.asarray(M_c2o)
@@ -183,6 +185,8 @@ class FullLoopPipeline:
             masks = parse_masks[lo:hi].to(self.dev, non_blocking=True)
             full = frames_u8[lo:hi].to(self.dev, non_blocking=True)
             self.h2d_bytes += crops.numel() + masks.numel() * 4 + full.numel()
+            if masks.dim() == 4:                                                  # logits -> parsing mask on the device
+                masks = self.engine.parse_mask(masks, (2 * self.net_h, 2 * self.net_w))
             I_p, _ = self.sw.swap_frames(crops)                                   # keypoints from the motion extractor
             soft, _ = self.soft_mask(masks[:, None])
             pasted = self.engine.paste_back(I_p, soft[:, 0], M[lo:hi], full, out=full)

@@ -174,6 +174,13 @@ CS_API int cs_paste_back(cs_ctx* ctx, const uint8_t* img_crop, const float* mask
 CS_API int cs_soft_erosion(cs_ctx* ctx, const float* mask, const float* kernel, float* out, uint8_t* hard, int B, int H, int W,
                            int kernel_size, float threshold, int iterations, void* stream);
 
+/* Face-parsing post-processing, the step before the path (reference src/can_swap_pipeline_e2e.py:183-190; the Segformer itself is an
+ * external HF model and stays outside): logits [B,C,h,w] fp32 -> F.interpolate(size=(H,W), bilinear, align_corners=False) -> argmax over C
+ * -> isin(valid) fused in one kernel.  valid_classes: bit c set = class c belongs to valid_list (:48: {1,2,4,5,6,7,10,11,12}).
+ * mask [B,H,W] f32 (1.0 / 0.0: the input of cs_soft_erosion, no host round trip), labels [B,H,W] i32 or NULL. */
+CS_API int cs_parse_mask(cs_ctx* ctx, const float* logits, int B, int C, int h, int w, int H, int W, uint64_t valid_classes, float* mask,
+                         int32_t* labels, void* stream);
+
 /* ---- per-kernel-family timing (measurement only) -------------------------------------------- */
 /* enable != 0: bracket every kernel launch of this ctx with CUDA events on the launching stream. */
 CS_API int cs_profile(cs_ctx* ctx, int enable);

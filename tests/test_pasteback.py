@@ -222,3 +222,33 @@ def test_full_loop_pipeline_against_oracle_chain(synth_w):
     ref = O.frame(synth_w, inp["frames"].permute(0, 3, 1, 2).float() / 255.0, kp["x_s"].cpu(), kp["x_can"].cpu(), inp["source_id"])["out"]
     ref_u8 = O.parse_output(ref)
     assert (ref_u8.int() - I_p.cpu().int()).abs().max().item() <= 1
+
+
+@pytest.mark.gpu
+def test_parse_mask_matches_torch_bit_for_bit():
+    """LOOP A post-processing (reference can_swap_pipeline_e2e.py:183-190) fused on the device: labels and mask equal torch's
+    interpolate -> argmax -> isin exactly, on random logits, on integer logits (exact arithmetic: real ties, first index wins),
+    for the Segformer geometry (19 x 128 x 128 -> 512 x 512) and a ragged one; the mask feeds SoftErosion directly."""
+    from canonswap_b200.engine import Engine
+    eng = Engine(None, net_hw=(128, 128), max_batch=1, device=0)
+    try:
+        valid = torch.tensor(Engine.VALID_PARSE_LABELS, device="cuda")
+        g = torch.Generator(device="cuda").manual_seed(3)
+        cases = [(2, 19, 128, 128, 512, 512, "randn"), (1, 19, 128, 128, 512, 512, "int"), (2, 7, 33, 21, 100, 77, "randn"),
+                 (1, 19, 64, 64, 512, 512, "int")]
+        for (B, C, h, w, H, W, kind) in cases:
+            if kind == "randn":
+                lg = torch.randn(B, C, h, w, device="cuda", generator=g) * 4
+            else:
+                lg = torch.randint(-3, 4, (B, C, h, w), device="cuda", generator=g).float()
+            up = torch.nn.functional.interpolate(lg, size=(H, W), mode="bilinear", align_corners=False)
+            lab = up.argmax(dim=1)
+            ref = torch.isin(lab, valid).to(torch.int)
+            mask, labels = eng.parse_mask(lg, (H, W), want_labels=True)
+            assert torch.equal(labels.long(), lab), (kind, (labels.long() != lab).sum().item())
+            assert torch.equal(mask, ref.float())
+        from canonswap_b200.pasteback import SoftErosion
+        soft, hard = SoftErosion(21, 0.9, 3).bind(eng)(mask[:, None])
+        assert soft.shape == (1, 1, 512, 512) and torch.isfinite(soft).all()
+    finally:
+        eng.close()
