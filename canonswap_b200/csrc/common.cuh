@@ -68,6 +68,8 @@ inline Act slice_c(Act a, int c0, int C) { a.p += c0; a.C = C; return a; }
 struct Opd {
   __nv_bfloat16* p = nullptr;
   int B = 0, D = 1, H = 0, W = 0, nblk = 0;
+  int pstride = 0;      // 16-bit elements per pixel when the operand is a block range of a wider one (0 = dense: nblk * 64)
+  long row() const { return pstride ? pstride : (long)nblk * 64; }
 };
 
 // The split itself: hi = fp16(v), lo = fp16(v - hi): v ~= hi + lo to ~2^-23 relative while |v| is in fp16's normal range
@@ -285,6 +287,9 @@ void prep_planes(const Launcher& L, const Prep& p, Opd out, const Act* out32);  
 void avg2(const Launcher& L, const float* a, const float* b, float* y, long n);   // y = (a + b) / 2
 constexpr int STATS_MAX_BLOCKS = 256;      // per-sample partial blocks of instance_stats: scratch = [B][256][C <= 512][2] doubles
 void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch);
+void stats_finalize_blocks(const Launcher& L, const double* part, int nblocks, int B, int C, long S, float* mean, float* rstd, float eps);
+// request for the instance statistics of a conv's OUTPUT, computed by the kernel that writes it (no extra pass over the tensor)
+struct StatsOut { double* scratch = nullptr; float* mean = nullptr; float* rstd = nullptr; float eps = 1e-5f; };
 void adaptive_blend(const Launcher& L, const float* o2 /*[P,1024]*/, const float* mask /*[P]*/,
                     const float* residual /*[P,512] or null*/, int relu, float* y /*[P,512] or null*/,
                     __nv_bfloat16* opl /*next conv operand [P,16,64] or null*/, long P);
@@ -300,6 +305,8 @@ void conv_cout1(const Launcher& L, const Act& x, const ConvW& w, const ConvGeom&
 // kernels_motion.cu
 void dm_input(const Launcher& L, const Act& c4, const float* kp_driving, const float* kp_source, int K,
               Act out /*[B,D,H,W,(K+1)*5 (+pad)]*/);
+// the same tensor written directly as the split operand of the convs that read it (4 blocks, pad channels zero)
+void dm_input_operand(const Launcher& L, const Act& c4, const float* kp_driving, const float* kp_source, int K, Opd out);
 void softmax_flow_warp(const Launcher& L, const Act& logits /*[B,D,H,W,K+1]*/, const float* kp_driving,
                        const float* kp_source, int K, const float* vol /*[B,H,W,16,32]*/,
                        float* out /*[B,H,W,16,32]*/, float* deformation /*[B,D,H,W,3] or null*/);

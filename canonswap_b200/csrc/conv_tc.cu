@@ -756,7 +756,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     k.sp_x = e.sp_x; k.sp_mean = e.sp_mean; k.sp_rstd = e.sp_rstd; k.sp_C = e.sp_C; k.sp_xs = e.sp_xshift;
     k.sp_Hx = e.sp_Hx; k.sp_Wx = e.sp_Wx;
   } else if (e.emit) {
-    CS_REQUIRE(y.C % 32 == 0 && e.emit_nblk * 32 == y.C, CS_ERR_INVALID, "conv_tc: operand emission needs Cout % 32 == 0");
+    CS_REQUIRE(y.C % 32 == 0 && e.emit_nblk * 32 >= y.C, CS_ERR_INVALID, "conv_tc: operand emission needs Cout % 32 == 0");
     k.emit = e.emit; k.erow = e.emit_nblk * 64; k.escale = e.emit_scale; k.eshift = e.emit_shift; k.eact = e.emit_act;
     k.eslope = e.emit_slope;
   }
@@ -815,7 +815,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   auto enc = encode_fn();
   CUtensorMap tmA, tmB;
   {
-    const cuuint64_t pix = (cuuint64_t)k.rowA * 2;
+    const cuuint64_t pix = (cuuint64_t)x.row() * 2;          // a block range of a wider operand keeps the wider pixel stride
     cuuint64_t dims[5] = {(cuuint64_t)k.rowA, (cuuint64_t)x.W, (cuuint64_t)x.H, (cuuint64_t)x.D, (cuuint64_t)x.B};
     cuuint64_t strides[4] = {pix, pix * x.W, pix * x.W * x.H, pix * x.W * x.H * x.D};
     cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, (cuuint32_t)bb};

@@ -166,7 +166,7 @@ void wino_in(const Launcher& L, const Act& x, Opd V, const ConvW* mask_conv, flo
 void pack_wino_static(cs_ctx* ctx, ConvW& w);
 bool wino_ok(const Launcher& L, const ConvW& w, int H, int W);
 void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const float* pscale, const float* pshift, int pact,
-               float pslope, int act, float slope, const float* residual, Act y);
+               float pslope, int act, float slope, const float* residual, Act y, const StatsOut* st = nullptr);
 void wino_out_blend(const Launcher& L, const float* Mt, const float* mask, const float* bias_mod, const float* residual, int relu,
                     float* y, int B, int H, int W);
 

@@ -306,6 +306,16 @@ __global__ void __launch_bounds__(256) stats_finalize_blocks_kernel(const double
   }
 }
 
+// mean / rstd from per-block partial sums [B][nblocks][C][2] (doubles) written by a producer kernel (instance_stats' own
+// stats_dense_kernel, or the Winograd output transform of the conv that produced the tensor)
+void stats_finalize_blocks(const Launcher& L, const double* part, int nblocks, int B, int C, long S, float* mean, float* rstd, float eps) {
+  L.count();
+  if (L.dry) return;
+  const int n = B * C;
+  stats_finalize_blocks_kernel<<<(n + 31) / 32, 256, 0, L.stream>>>(part, nblocks, C, mean, rstd, n, 1.0 / (double)S, eps);
+  check_launch("stats_finalize");
+}
+
 void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch) {
   L.count(); L.count();
   if (L.dry) return;

@@ -99,6 +99,77 @@ void dm_input(const Launcher& L, const Act& c4, const float* kp_driving, const f
   check_launch("dm_input");
 }
 
+// The same tensor written directly as the split-fp16 operand [pixel][4 blocks][hi 32 | lo 32] (channels 110..127 zero) of the
+// two convs that consume it (hourglass conv0 and, as blocks 1..4 of its 142-channel input, the hourglass' last conv): no fp32
+// copy of the 110-channel tensor, no prep passes.  One warp per voxel: lanes 0..K compute keypoint k's 5 channels into shared
+// memory, then every lane splits 4 channels and the warp writes 4 full 128-byte rows.
+__global__ void __launch_bounds__(256) dm_input_operand_kernel(const float4* __restrict__ c4, const float* __restrict__ kpd,
+                                                               const float* __restrict__ kps, int K, int B, int D, int H, int W,
+                                                               __nv_bfloat16* __restrict__ out, long prow) {
+  __shared__ float vals[8][128];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long nvox = (long)B * D * H * W;
+  for (long pix = (long)blockIdx.x * 8 + wid; pix < nvox; pix += (long)gridDim.x * 8) {
+    int w = (int)(pix % W); long t = pix / W; int h = (int)(t % H); t /= H; int d = (int)(t % D); int b = (int)(t / D);
+    float gx, gy, gz;
+    grid_xyz(d, h, w, D, H, W, gx, gy, gz);
+    float* vv = vals[wid];
+    for (int i = lane; i < 128; i += 32) vv[i] = 0.f;
+    __syncwarp();
+    if (lane <= K) {
+      const int k = lane;
+      float mx = gx, my = gy, mz = gz, heat = 0.f;
+      if (k > 0) {
+        const float* pd = kpd + ((long)b * K + (k - 1)) * 3;
+        const float* ps = kps + ((long)b * K + (k - 1)) * 3;
+        float dx = gx - pd[0], dy = gy - pd[1], dz = gz - pd[2];          // identity_grid - kp_driving
+        mx = dx + ps[0]; my = dy + ps[1]; mz = dz + ps[2];                 // + kp_source
+        float sx = gx - ps[0], sy = gy - ps[1], sz = gz - ps[2];
+        float qd = (dx * dx + dy * dy) + dz * dz, qs = (sx * sx + sy * sy) + sz * sz;
+        heat = expf(-0.5f * qd / 0.01f) - expf(-0.5f * qs / 0.01f);
+      }
+      Tri tr = make_tri(mx, my, mz, D, H, W);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int cz = 0; cz < 2; ++cz)
+#pragma unroll
+        for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+          for (int cx = 0; cx < 2; ++cx) {
+            int x = tr.x0 + cx, y = tr.y0 + cy, z = tr.z0 + cz;
+            if (x >= 0 && x < W && y >= 0 && y < H && z >= 0 && z < D) {
+              float wt = tr.w[cz * 4 + cy * 2 + cx];
+              float4 v = c4[(((long)b * D + z) * H + y) * W + x];
+              acc.x += v.x * wt; acc.y += v.y * wt; acc.z += v.z * wt; acc.w += v.w * wt;
+            }
+          }
+      float* o = vv + k * 5;
+      o[0] = heat; o[1] = acc.x; o[2] = acc.y; o[3] = acc.z; o[4] = acc.w;
+    }
+    __syncwarp();
+    const int c = lane * 4;
+    uint2 hv, lv;
+    split_operand4(vv[c], vv[c + 1], vv[c + 2], vv[c + 3], hv, lv);
+    __nv_bfloat16* o = out + pix * prow + (c >> 5) * 64 + (c & 31);
+    *reinterpret_cast<uint2*>(o) = hv;
+    *reinterpret_cast<uint2*>(o + 32) = lv;
+    __syncwarp();
+  }
+}
+
+void dm_input_operand(const Launcher& L, const Act& c4, const float* kp_driving, const float* kp_source, int K, Opd out) {
+  L.count();
+  if (L.dry) return;
+  CS_REQUIRE(c4.C == 4 && c4.sw == 4 && (K + 1) * 5 <= 128 && K < 32 && out.nblk == 4 && out.B == c4.B && out.D == c4.D && out.H == c4.H &&
+                 out.W == c4.W, -1, "dm_input_operand: bad geometry");
+  const long nvox = c4.pixels();
+  long blocks = (nvox + 7) / 8; if (blocks > 148L * 32) blocks = 148L * 32;
+  ProfScope ps(L, PK_SAMPLE, 0.0, (double)nvox * (4 + 128) * 4.0, "dm_input");
+  dm_input_operand_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(c4.p), kp_driving, kp_source, K, c4.B,
+                                                                 c4.D, c4.H, c4.W, out.p, out.row());
+  check_launch("dm_input_operand");
+}
+
 // ------------------------------------------------------------------------------------------
 // sample the [B,H,W,16,32] volume: 8 threads per voxel, 4 channels (one float4) each
 // ------------------------------------------------------------------------------------------
@@ -120,42 +191,72 @@ __device__ __forceinline__ float4 sample_vol(const float* __restrict__ vol, int 
   return acc;
 }
 
+// 8 lanes per voxel: the lanes SHARE one softmax (lane j takes classes j, j+8, j+16; max / sums by xor-shuffles over the
+// 8-lane group) instead of each recomputing all 22 exponentials, the keypoint translations ks_k - kd_k of the block's
+// sample sit in shared memory, and every lane then gathers its float4 (4 of the 32 channels) of the 8 corners: a corner is
+// one 128-byte line for the group.  Voxel order (b, h, w, d): the 16 depths of a pixel are adjacent in the output volume, so
+// a warp (4 voxels) writes 512 contiguous bytes.  A block = 32 voxels = 2 pixels x 16 depths of one sample.
+constexpr int SFW_MAXK = 32;
+
 __global__ void __launch_bounds__(256) softmax_flow_warp_kernel(const float* __restrict__ logits, long lb, long ld, long lh, long lw,
                                                                const float* __restrict__ kpd, const float* __restrict__ kps,
                                                                int K, int B, int D, int H, int W,
                                                                const float* __restrict__ vol, float* __restrict__ out,
                                                                float* __restrict__ deformation) {
-  long total = (long)B * D * H * W * 8;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    int c4 = (int)(idx & 7); long pix = idx >> 3;
-    // voxel order (b, h, w, d): the 16 depths of a pixel are adjacent in the output volume
-    int d = (int)(pix % D); long t = pix / D; int w = (int)(t % W); t /= W; int h = (int)(t % H); int b = (int)(t / H);
+  __shared__ float s_kd[SFW_MAXK * 3], s_ks[SFW_MAXK * 3];
+  const long nvox = (long)B * D * H * W;
+  const long per_b = (long)D * H * W;
+  const int j = threadIdx.x & 7;                              // lane within the voxel group = channel quad
+  for (long v0 = (long)blockIdx.x * 32; v0 < nvox; v0 += (long)gridDim.x * 32) {
+    const int b = (int)(v0 / per_b);                          // per_b is a multiple of 32: the block's voxels share b
+    __syncthreads();
+    if (threadIdx.x < K * 3) {
+      s_kd[threadIdx.x] = kpd[(long)b * K * 3 + threadIdx.x];
+      s_ks[threadIdx.x] = kps[(long)b * K * 3 + threadIdx.x];
+    }
+    __syncthreads();
+    const long pix = v0 + (threadIdx.x >> 3);
+    const int d = (int)(pix % D); long t = pix / D; const int w = (int)(t % W); t /= W; const int h = (int)(t % H);
     const float* lg = logits + b * lb + d * ld + h * lh + w * lw;
-    float mxl = lg[0];
-    for (int k = 1; k <= K; ++k) mxl = fmaxf(mxl, lg[k]);
     float gx, gy, gz;
     grid_xyz(d, h, w, D, H, W, gx, gy, gz);
+    // this lane's classes
+    float l0 = lg[j], l1 = (j + 8 <= K) ? lg[j + 8] : -INFINITY, l2 = (j + 16 <= K) ? lg[j + 16] : -INFINITY;
+    float mxl = fmaxf(l0, fmaxf(l1, l2));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) mxl = fmaxf(mxl, __shfl_xor_sync(0xffffffffu, mxl, o));
     float den = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
-    for (int k = 0; k <= K; ++k) {
-      float e = expf(lg[k] - mxl);
-      den += e;
-      float mx = gx, my = gy, mz = gz;
-      if (k > 0) {
-        const float* pd = kpd + ((long)b * K + (k - 1)) * 3;
-        const float* ps = kps + ((long)b * K + (k - 1)) * 3;
-        mx = (gx - pd[0]) + ps[0]; my = (gy - pd[1]) + ps[1]; mz = (gz - pd[2]) + ps[2];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int k = j + 8 * q;
+      if (k <= K) {
+        const float e = expf((q == 0 ? l0 : (q == 1 ? l1 : l2)) - mxl);
+        den += e;
+        float mx = gx, my = gy, mz = gz;
+        if (k > 0) {                                          // identity_grid - kp_driving + kp_source (dense_motion.py:38-40)
+          mx = (gx - s_kd[(k - 1) * 3 + 0]) + s_ks[(k - 1) * 3 + 0];
+          my = (gy - s_kd[(k - 1) * 3 + 1]) + s_ks[(k - 1) * 3 + 1];
+          mz = (gz - s_kd[(k - 1) * 3 + 2]) + s_ks[(k - 1) * 3 + 2];
+        }
+        fx = fmaf(mx, e, fx); fy = fmaf(my, e, fy); fz = fmaf(mz, e, fz);
       }
-      fx += mx * e; fy += my * e; fz += mz * e;
     }
-    float inv = 1.f / den;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {                         // xor butterflies: every lane of the group ends with the same sums
+      den += __shfl_xor_sync(0xffffffffu, den, o);
+      fx += __shfl_xor_sync(0xffffffffu, fx, o);
+      fy += __shfl_xor_sync(0xffffffffu, fy, o);
+      fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+    const float inv = 1.f / den;
     fx *= inv; fy *= inv; fz *= inv;
-    if (deformation && c4 == 0) {
+    if (deformation && j == 0) {
       float* df = deformation + ((((long)b * D + d) * H + h) * W + w) * 3;
       df[0] = fx; df[1] = fy; df[2] = fz;
     }
-    Tri tr = make_tri(fx, fy, fz, D, H, W);
-    float4 v = sample_vol(vol, b, tr, D, H, W, c4);
-    *reinterpret_cast<float4*>(out + (((long)b * H + h) * W + w) * 512 + d * 32 + c4 * 4) = v;
+    const Tri tr = make_tri(fx, fy, fz, D, H, W);
+    const float4 v = sample_vol(vol, b, tr, D, H, W, j);
+    *reinterpret_cast<float4*>(out + (((long)b * H + h) * W + w) * 512 + d * 32 + j * 4) = v;
   }
 }
 
@@ -163,9 +264,10 @@ void softmax_flow_warp(const Launcher& L, const Act& logits, const float* kp_dri
                        const float* vol, float* out, float* deformation) {
   L.count();
   if (L.dry) return;
-  CS_REQUIRE(logits.D == 16 && logits.C >= K + 1, -1, "softmax_flow_warp: bad logits tensor");
-  long total = logits.pixels() * 8;
-  long blocks = (total + 255) / 256; if (blocks > 148L * 32) blocks = 148L * 32;
+  CS_REQUIRE(logits.D == 16 && logits.C >= K + 1 && K + 1 <= 24 && K <= SFW_MAXK && (logits.H * logits.W) % 2 == 0, -1,
+             "softmax_flow_warp: bad logits tensor");
+  const long nvox = logits.pixels();
+  long blocks = nvox / 32; if (blocks > 148L * 32) blocks = 148L * 32;
   // algorithmic bytes / voxel: 32 ch in + 32 ch out + 22 logits (22.5 MB / sample)
   ProfScope ps(L, PK_SAMPLE, 0.0, (double)logits.pixels() * (32 + 32 + (K + 1)) * 4.0, "flow_warp");
   softmax_flow_warp_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(logits.p, logits.sb, logits.sd, logits.sh, logits.sw,

@@ -291,22 +291,36 @@ static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, c
   const int hs[6] = {h, h / 2, h / 4, h / 8, h / 16, h / 32};
   const int ws[6] = {w, w / 2, w / 4, w / 8, w / 16, w / 32};
   CS_REQUIRE(hs[5] >= 1 && ws[5] >= 1, CS_ERR_INVALID, "feature resolution too small for the 5-level hourglass");
-  Act cat5 = new_act(n, B, D, hs[0], ws[0], HG_OUT, 144); // [up4 32 | x 110] (+2 pad floats: 16-byte rows)
+  // tcgen05 path: the 142-channel input of the hourglass' last conv [up4 32 | x 110] exists ONLY as its split operand
+  // (5 blocks): block 0 is emitted by the last decoder conv's epilogue, blocks 1..4 are written by dm_input_operand and are,
+  // as a block range, also the operand of the first encoder conv.  No fp32 copy of either tensor, no prep pass over them.
+  const bool opd_path = n.L.conv_impl != 1 && conv_tc_supported(W.hg_enc[0], make_act(nullptr, B, D, h, w, 64)) &&
+                        conv_tc_supported(W.hg_dec[4], make_act(nullptr, B, D, h, w, 32)) && conv_tc_supported(W.hg_final, make_act(nullptr, B, D, h, w, HG_OUT));
+  Opd cat5_op, x_op;
+  Act cat5, x;
+  if (opd_path) {
+    cat5_op = conv_tc_alloc_operand(*n.A, W.hg_final, make_act(nullptr, B, D, h, w, HG_OUT));     // 5 blocks
+    x_op = cat5_op; x_op.p = cat5_op.p + 64; x_op.nblk = 4; x_op.pstride = cat5_op.nblk * 64;
+  } else {
+    cat5 = new_act(n, B, D, hs[0], ws[0], HG_OUT, 144);  // [up4 32 | x 110] (+2 pad floats: 16-byte rows)
+    x = slice_c(cat5, 32, HG_IN);
+  }
   Act cat4 = new_act(n, B, D, hs[1], ws[1], 128);        // [up3 64 | p0 64]
   Act cat3 = new_act(n, B, D, hs[2], ws[2], 256);        // [up2 128 | p1 128]
   Act cat2 = new_act(n, B, D, hs[3], ws[3], 512);        // [up1 256 | p2 256]
   Act cat1 = new_act(n, B, D, hs[4], ws[4], 1024);       // [up0 512 | p3 512]
   Act p4 = new_act(n, B, D, hs[5], ws[5], 1024);
   // hourglass input: [heat_k, deformed_k(4)] per keypoint (:29-65, :83-84)
-  Act x = slice_c(cat5, 32, HG_IN);
-  dm_input(n.L, c4, kp_driving, kp_source, NUM_KP, x);
+  if (opd_path) dm_input_operand(n.L, c4, kp_driving, kp_source, NUM_KP, x_op);
+  else dm_input(n.L, c4, kp_driving, kp_source, NUM_KP, x);
   // encoder: conv-BN-ReLU at full res, then avg-pool (1,2,2) into the skip slice (util.py:185-190)
   Act skips[5] = {slice_c(cat4, 64, 64), slice_c(cat3, 128, 128), slice_c(cat2, 256, 256), slice_c(cat1, 512, 512), p4};
   Act cur = x;
   for (int i = 0; i < 5; ++i) {
     size_t m = n.A->mark();
     Act e = new_act(n, B, D, hs[i], ws[i], W.hg_enc[i].Cout);
-    conv_layer(n, nullptr, cur, W.hg_enc[i], relu, e);
+    if (i == 0 && opd_path) conv_from_operand(n, x_op, W.hg_enc[0], relu, e);
+    else conv_layer(n, nullptr, cur, W.hg_enc[i], relu, e);
     Prep pp = prep_of(e); pp.pool2 = 1;
     prep_f32(n.L, pp, skips[i]);
     n.A->reset(m);
@@ -316,6 +330,17 @@ static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, c
   Act cats[5] = {cat1, cat2, cat3, cat4, cat5};
   Act dcur = p4;
   for (int i = 0; i < 5; ++i) {
+    if (i == 4 && opd_path) {                              // the last decoder conv: operand block 0 of cat5 only
+      size_t m = n.A->mark();
+      Act geom = make_act(nullptr, B, D, h, w, W.hg_dec[4].Cout);
+      Opd up_op = conv_tc_alloc_operand(*n.A, W.hg_dec[4], geom);
+      Prep up = prep_of(dcur); up.upshift = 1;
+      prep_planes(n.L, up, up_op, nullptr);
+      ConvOpts o = relu; o.emit = &cat5_op;
+      conv_from_operand(n, up_op, W.hg_dec[4], o, geom);
+      n.A->reset(m);
+      break;
+    }
     Act dst = slice_c(cats[i], 0, W.hg_dec[i].Cout);
     if (n.L.conv_impl == 1 || !conv_tc_supported(W.hg_dec[i], dst)) {
       ConvOpts o = relu; o.xshift = 1;
@@ -327,7 +352,8 @@ static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, c
     dcur = cats[i];
   }
   Act pred = new_act(n, B, D, h, w, HG_OUT, 144);
-  conv_layer(n, nullptr, cat5, W.hg_final, relu, pred);
+  if (opd_path) conv_from_operand(n, cat5_op, W.hg_final, relu, pred);
+  else conv_layer(n, nullptr, cat5, W.hg_final, relu, pred);
   // mask logits 7x7x7 (:88); softmax is fused into the flow/warp kernel
   // occlusion 7x7 over (c*16+d) channels == conv3d kernel (16,7,7), pad (0,3,3), then sigmoid (:98-102)
   Act logits = new_act(n, B, D, h, w, NUM_KP + 1, 24);
@@ -567,12 +593,19 @@ static bool spade_block_tc_ok(const Net& n, const SpadeBlockW& b) {
 
 // SPADEResnetBlock (util.py:329-344) on the tcgen05 path. seg_op: split operand of the (upsampled) seg map at this
 // block's resolution, shared by the block's mlp_shared convs.
-static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, const Opd& seg_op, int seg_phase, Act out) {
+// xstat: statistics of x when its producer already computed them (else they are computed here); ostat: request for the
+// statistics of the block's output (filled by the Winograd output transform of conv_1 when it runs in that form)
+struct StatPair { float* mean = nullptr; float* rstd = nullptr; bool valid = false; };
+
+static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, const Opd& seg_op, int seg_phase, Act out,
+                          const StatPair* xstat, StatPair* ostat) {
   const int B = x.B, H = x.H << xup, W = x.W << xup;
   size_t m = n.A->mark();
   float* mean = n.A->f32((size_t)B * b.fin);
   float* rstd = n.A->f32((size_t)B * b.fin);
-  instance_stats(n.L, x, mean, rstd, 1e-5f, n.stats);
+  if (xstat && xstat->valid) { mean = xstat->mean; rstd = xstat->rstd; }
+  else instance_stats(n.L, x, mean, rstd, 1e-5f, n.stats);
+  if (ostat) ostat->valid = false;
   Act xs;
   if (b.learned_shortcut) {
     xs = new_act(n, B, 1, H, W, b.fout);
@@ -585,12 +618,17 @@ static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, c
     xs = x;
   }
   Act dx = new_act(n, B, 1, H, W, b.fmid);
+  float* mean1 = n.A->f32((size_t)B * b.fmid);
+  float* rstd1 = n.A->f32((size_t)B * b.fmid);
+  bool have1 = false;
   {
     size_t m2 = n.A->mark();
     if (wino_ok(n.L, b.conv_0, H, W)) {                    // Winograd F(2x2,3x3): the SPADE epilogue writes fp32
       Act mod = new_act(n, B, 1, H, W, b.fin);
       spade_norm_tc(n, b.norm_0, seg_op, seg_phase, x, xup, mean, rstd, ACT_LRELU, 0.2f, b.conv_0, B, H, W, &mod);
-      wino_conv(n.L, *n.A, mod, b.conv_0, nullptr, nullptr, ACT_NONE, 0.f, ACT_NONE, 0.f, nullptr, dx);
+      StatsOut so; so.scratch = n.stats; so.mean = mean1; so.rstd = rstd1;       // statistics of dx from the output transform
+      wino_conv(n.L, *n.A, mod, b.conv_0, nullptr, nullptr, ACT_NONE, 0.f, ACT_NONE, 0.f, nullptr, dx, &so);
+      have1 = true;
     } else {
       Opd m0 = spade_norm_tc(n, b.norm_0, seg_op, seg_phase, x, xup, mean, rstd, ACT_LRELU, 0.2f, b.conv_0, B, H, W);
       conv_from_operand(n, m0, b.conv_0, ConvOpts(), dx);
@@ -598,14 +636,14 @@ static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, c
     n.A->reset(m2);
   }
   {
-    float* mean1 = n.A->f32((size_t)B * b.fmid);
-    float* rstd1 = n.A->f32((size_t)B * b.fmid);
-    instance_stats(n.L, dx, mean1, rstd1, 1e-5f, n.stats);
+    if (!have1) instance_stats(n.L, dx, mean1, rstd1, 1e-5f, n.stats);
     const bool xs_dense = xs.sw == xs.C && xs.sh == (long)xs.W * xs.C && xs.sb == (long)xs.H * xs.W * xs.C && xs.H == H && xs.W == W;
     if (wino_ok(n.L, b.conv_1, H, W) && xs_dense) {
       Act mod = new_act(n, B, 1, H, W, b.fmid);
       spade_norm_tc(n, b.norm_1, seg_op, seg_phase, dx, 0, mean1, rstd1, ACT_LRELU, 0.2f, b.conv_1, B, H, W, &mod);
-      wino_conv(n.L, *n.A, mod, b.conv_1, nullptr, nullptr, ACT_NONE, 0.f, ACT_NONE, 0.f, xs.p, out);
+      StatsOut so; so.scratch = n.stats;
+      if (ostat && ostat->mean) { so.mean = ostat->mean; so.rstd = ostat->rstd; ostat->valid = true; }
+      wino_conv(n.L, *n.A, mod, b.conv_1, nullptr, nullptr, ACT_NONE, 0.f, ACT_NONE, 0.f, xs.p, out, ostat && ostat->mean ? &so : nullptr);
     } else {
       Opd m1 = spade_norm_tc(n, b.norm_1, seg_op, seg_phase, dx, 0, mean1, rstd1, ACT_LRELU, 0.2f, b.conv_1, B, H, W);
       ConvOpts o; o.residual = &xs;
@@ -617,8 +655,10 @@ static Act spade_block_tc(Net& n, const SpadeBlockW& b, const Act& x, int xup, c
 }
 
 // SPADEResnetBlock (util.py:329-344). x is read nearest-upsampled by 2^xup; returns [B,H,W,fout].
-static Act spade_block(Net& n, const SpadeBlockW& b, const Act& x, int xup, const Act& seg, int segshift, Act out) {
+static Act spade_block(Net& n, const SpadeBlockW& b, const Act& x, int xup, const Act& seg, int segshift, Act out,
+                       const StatPair* xstat = nullptr, StatPair* ostat = nullptr) {
   const int B = x.B, H = x.H << xup, W = x.W << xup;
+  if (ostat) ostat->valid = false;
   if (spade_block_tc_ok(n, b)) {
     size_t m0 = n.A->mark();
     // the seg map's operand at its own resolution; up blocks convolve it in phase form instead of upsampling it
@@ -628,7 +668,7 @@ static Act spade_block(Net& n, const SpadeBlockW& b, const Act& x, int xup, cons
     Opd seg_op = conv_tc_alloc_operand(*n.A, b.norm_0.shared, make_act(nullptr, B, 1, seg.H << sh, seg.W << sh, 128));
     Prep up = prep_of(seg); up.upshift = sh;
     prep_planes(n.L, up, seg_op, nullptr);
-    spade_block_tc(n, b, x, xup, seg_op, phase ? segshift : 0, out);
+    spade_block_tc(n, b, x, xup, seg_op, phase ? segshift : 0, out, xstat, ostat);
     n.A->reset(m0);
     return out;
   }
@@ -683,16 +723,27 @@ void run_spade(Net& n, const float* feat256, int B, float* img_nchw, uint8_t* im
   Act seg = make_act(const_cast<float*>(feat256), B, 1, h, w, 256);
   Act xa = new_act(n, B, 1, h, w, 512);
   Act xb = new_act(n, B, 1, h, w, 512);
-  if (wino_ok(n.L, W.g_fc, h, w)) wino_conv(n.L, *n.A, seg, W.g_fc, nullptr, nullptr, ACT_NONE, 0.f, ACT_NONE, 0.f, nullptr, xa);
-  else conv_layer(n, nullptr, seg, W.g_fc, ConvOpts(), xa);
+  // the InstanceNorm statistics of every block input travel with the tensor: they are produced by the Winograd output
+  // transform of the conv that wrote it (no separate pass; nearest upsampling leaves mean / biased variance unchanged)
+  StatPair sa, sb;
+  sa.mean = n.A->f32((size_t)B * 512); sa.rstd = n.A->f32((size_t)B * 512);
+  sb.mean = n.A->f32((size_t)B * 512); sb.rstd = n.A->f32((size_t)B * 512);
+  if (wino_ok(n.L, W.g_fc, h, w)) {
+    StatsOut so; so.scratch = n.stats; so.mean = sa.mean; so.rstd = sa.rstd;
+    wino_conv(n.L, *n.A, seg, W.g_fc, nullptr, nullptr, ACT_NONE, 0.f, ACT_NONE, 0.f, nullptr, xa, &so);
+    sa.valid = true;
+  } else {
+    conv_layer(n, nullptr, seg, W.g_fc, ConvOpts(), xa);
+  }
   for (int i = 0; i < 6; ++i) {                                           // G_middle_0..5
-    spade_block(n, W.g_blocks[i], xa, 0, seg, 0, xb);
+    spade_block(n, W.g_blocks[i], xa, 0, seg, 0, xb, &sa, &sb);
     Act t = xa; xa = xb; xb = t;
+    StatPair ts = sa; sa = sb; sb = ts;
   }
   Act u0 = new_act(n, B, 1, 2 * h, 2 * w, 256);
-  spade_block(n, W.g_blocks[6], xa, 1, seg, 1, u0);                       // up -> up_0
+  spade_block(n, W.g_blocks[6], xa, 1, seg, 1, u0, &sa, &sb);             // up -> up_0
   Act u1 = new_act(n, B, 1, 4 * h, 4 * w, 64);
-  spade_block(n, W.g_blocks[7], u0, 1, seg, 2, u1);                       // up -> up_1
+  spade_block(n, W.g_blocks[7], u0, 1, seg, 2, u1, &sb, nullptr);         // up -> up_1
   Act y = new_act(n, B, 1, 4 * h, 4 * w, 12);
   Prep pl = prep_of(u1); pl.act = ACT_LRELU; pl.slope = 0.2f;             // conv_img(leaky_relu(x, 0.2))
   conv_layer(n, &pl, u1, W.g_img, ConvOpts(), y);

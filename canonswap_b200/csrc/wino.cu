@@ -219,16 +219,22 @@ __global__ void __launch_bounds__(256) wino_out_blend_kernel(const float* __rest
   }
 }
 
-// generic output transform: Mt [B,16,H/2,W/2,C] -> y [B,H,W,C] = act(Y + bias) (+ residual); y may alias residual
+// generic output transform: Mt [B,16,H/2,W/2,C] -> y [B,H,W,C] = act(Y + bias) (+ residual); y may alias residual.
+// grid = (blocks per sample, B).  STATS: also the per-(sample, block, channel) partial sums (sum y, sum y^2) of the OUTPUT for
+// the InstanceNorm that follows (reference util.py:286,296): fp32 over a thread's <= ~16 values, fixed-order shared-memory
+// combine of the threads that share a channel quad, one fp64 partial per block -- finalised by stats_finalize_blocks.
+template <bool STATS>
 __global__ void __launch_bounds__(256) wino_out_kernel(const float* __restrict__ Mt, const float* __restrict__ bias, int act, float slope,
-                                                       const float* residual, float* y, int B, int H, int W, int C) {
+                                                       const float* residual, float* y, int H, int W, int C, double* __restrict__ part) {
+  __shared__ float4 r1[STATS ? 256 : 1], r2[STATS ? 256 : 1];
   const int Ht = H >> 1, Wt = W >> 1, C4 = C >> 2;
-  const long total = (long)B * Ht * Wt * C4;
+  const int b = blockIdx.y;
+  const long per = (long)Ht * Wt * C4;
   const long plane = (long)Ht * Wt * C;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < per; idx += (long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C4) * 4; long t = idx / C4;
-    const int tx = (int)(t % Wt); t /= Wt;
-    const int ty = (int)(t % Ht); const int b = (int)(t / Ht);
+    const int tx = (int)(t % Wt); const int ty = (int)(t / Wt);
     float4 yy[2][2];
     wino_out4(Mt + (long)b * 16 * plane + ((long)ty * Wt + tx) * C + c, plane, yy);
     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -244,8 +250,28 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float* __restrict__
           const float4 r = *reinterpret_cast<const float4*>(residual + off);
           v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
         }
+        if constexpr (STATS) {
+          s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+          s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+        }
         *reinterpret_cast<float4*>(y + off) = v;
       }
+  }
+  if constexpr (STATS) {
+    // (gridDim.x * 256) % C4 == 0 (host): a thread keeps its channel quad over the loop; threads t, t + C4, ... share it
+    r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
+    __syncthreads();
+    if ((int)threadIdx.x < C4) {
+      double a[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+      for (int i = threadIdx.x; i < 256; i += C4) {
+        const float4 u = r1[i], w = r2[i];
+        a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+        q[0] += w.x; q[1] += w.y; q[2] += w.z; q[3] += w.w;
+      }
+      double* o = part + (((long)b * gridDim.x + blockIdx.x) * C + threadIdx.x * 4) * 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { o[2 * j] = a[j]; o[2 * j + 1] = q[j]; }
+    }
   }
 }
 
@@ -270,7 +296,7 @@ void pack_wino_static(cs_ctx* ctx, ConvW& w) {
 
 // y = act(conv3x3(pre(x)) + bias) (+ residual) in Winograd form; x, y, residual dense fp32 [B,1,H,W,C]; V / Mt scratch from `A`
 void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const float* pscale, const float* pshift, int pact,
-               float pslope, int act, float slope, const float* residual, Act y) {
+               float pslope, int act, float slope, const float* residual, Act y, const StatsOut* st) {
   CS_REQUIRE(w.wn != nullptr && x.C == w.Cin && y.C == w.Cout && y.H == x.H && y.W == x.W && y.B == x.B && y.sw == y.C &&
                  y.sh == (long)y.W * y.C && y.sb == (long)y.H * y.W * y.C, CS_ERR_INVALID, "wino_conv: unsupported geometry");
   const size_t m = A.mark();
@@ -283,12 +309,20 @@ void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const 
   eg.alg_flops = 2.0 * (double)x.pixels() * w.Cout * w.Cin * 9.0;   // the 3x3 conv this GEMM stands for
   conv_tc(L, V, *w.wn, g, eg, Mt);
   L.count();
+  const int C4 = w.Cout / 4;
+  const bool stats = st && st->scratch && C4 <= 256 && 256 % C4 == 0 && w.Cout <= 512;
+  const long per = (long)V.H * V.W * C4;
+  long blocks = (per + 255) / 256; if (blocks > STATS_MAX_BLOCKS) blocks = STATS_MAX_BLOCKS;
   if (!L.dry) {
-    const long total = (long)x.B * V.H * V.W * (w.Cout / 4);
-    long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
     ProfScope ps(L, PK_CONV_TC, 0.0, (double)x.pixels() * w.Cout * (4.0 + 1.0 + (residual ? 1.0 : 0.0)) * 4.0, "wino_out");
-    wino_out_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(Mt.p, w.bias, act, slope, residual, y.p, x.B, x.H, x.W, w.Cout);
+    dim3 grid((unsigned)blocks, x.B);
+    if (stats) wino_out_kernel<true><<<grid, 256, 0, L.stream>>>(Mt.p, w.bias, act, slope, residual, y.p, x.H, x.W, w.Cout, st->scratch);
+    else wino_out_kernel<false><<<grid, 256, 0, L.stream>>>(Mt.p, w.bias, act, slope, residual, y.p, x.H, x.W, w.Cout, nullptr);
     check_launch("wino_out");
+  }
+  if (st && st->mean) {
+    if (stats) stats_finalize_blocks(L, st->scratch, (int)blocks, x.B, w.Cout, (long)x.H * x.W, st->mean, st->rstd, st->eps);
+    else instance_stats(L, y, st->mean, st->rstd, st->eps, st->scratch);
   }
   A.reset(m);
 }
