@@ -26,6 +26,7 @@ CS_OPT_TC_BN_MAX = 9
 CS_OPT_LANES = 10
 CS_OPT_WINOGRAD = 13
 CS_OPT_TC_POSCOMP = 14
+CS_OPT_TEST_AMUL = 15
 CS_FRAME_MOTION = 8
 CS_FRAME_V2I_FEATURE = 16
 MOTION_HEADS = 328
@@ -37,7 +38,7 @@ CS_OPT_TC_SINGLE_CHAIN = 11
 SYMBOLS = [
     "cs_create", "cs_destroy", "cs_last_error", "cs_set_option", "cs_launch_count", "cs_workspace_bytes",
     "cs_load_weights", "cs_set_identity", "cs_appearance", "cs_warp", "cs_warp_out", "cs_warp_forward",
-    "cs_swap", "cs_refine", "cs_spade", "cs_frame", "cs_profile", "cs_profile_read", "cs_profile_dump", "cs_motion", "cs_keypoints", "cs_paste_back", "cs_soft_erosion", "cs_parse_mask", "cs_test_conv", "cs_test_grid_sample3d",
+    "cs_swap", "cs_refine", "cs_spade", "cs_frame", "cs_profile", "cs_profile_read", "cs_profile_dump", "cs_motion", "cs_keypoints", "cs_paste_back", "cs_soft_erosion", "cs_parse_mask", "cs_calibrate", "cs_test_conv", "cs_test_grid_sample3d",
     "cs_test_instance_stats",
 ]
 
@@ -85,6 +86,7 @@ def load() -> C.CDLL:
     lib.cs_paste_back.argtypes = [vp, p, p, C.POINTER(C.c_double), p, p, i, i, i, i, i, vp]
     lib.cs_soft_erosion.argtypes = [vp, p, p, p, p, i, i, i, i, f, i, vp]
     lib.cs_parse_mask.argtypes = [vp, p, i, i, i, i, i, i, C.c_uint64, p, p, vp]
+    lib.cs_calibrate.argtypes = [vp, i, p, i]
     lib.cs_profile.argtypes = [vp, i]
     lib.cs_profile_read.argtypes = [vp, C.POINTER(C.c_double)]
     lib.cs_profile_dump.argtypes = [vp, C.c_char_p, i]

@@ -4,6 +4,7 @@
 // device, unsupported shape or CUDA error is reported, not worked around.
 #include "ctx.cuh"
 #include <cstring>
+#include <cmath>
 
 using namespace cs;
 
@@ -50,6 +51,7 @@ Net make_net(cs_ctx* ctx, void* stream, bool dry) {
   n.L.winograd = ctx->winograd != 0;
   n.L.single_chain = ctx->tc_single_chain;
   n.L.prof = dry ? nullptr : &ctx->prof;
+  n.L.calib = (!dry && ctx->calib_on) ? ctx->calib_tab : nullptr;
   return n;
 }
 
@@ -325,6 +327,9 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
     case CS_OPT_TC_CHAIN_MAX:
       if (value < 0 || value > 100000) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TC_CHAIN_MAX: value must be in [0, 100000]");
       ctx->tc_chain_max = value; return CS_OK;
+    case CS_OPT_TEST_AMUL:
+      if (value < -14 || value > 14) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TEST_AMUL: log2 of the scale, in [-14, 14]");
+      ctx->test_amul_log2 = value; return CS_OK;
     case CS_OPT_WINOGRAD:
       ctx->winograd = value ? 1 : 0; return CS_OK;
     case CS_OPT_TC_DOUBLE_BUFFER:
@@ -348,9 +353,27 @@ size_t cs_workspace_bytes(const cs_ctx* ctx) { return ctx ? ctx->owned_bytes : 0
 
 int cs_load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
   CS_API_BEGIN(ctx)
-  load_weights(ctx, table, n);
-  if (motion_weights_present(table, n)) load_motion_weights(ctx, table, n);   // optional: combined_weights['motion_extractor']
-  size_workspace(ctx);
+  // a failure anywhere below (malformed optional tensors, arena allocation) must leave the ctx UNLOADED and free what this call
+  // allocated, so that the caller can retry
+  const size_t owned0 = ctx->owned.size();
+  const size_t bytes0 = ctx->owned_bytes;
+  try {
+    load_weights(ctx, table, n);
+    ctx->weights_loaded = false;                             // not usable before the workspace exists
+    if (motion_weights_present(table, n)) load_motion_weights(ctx, table, n);   // optional: combined_weights['motion_extractor']
+    size_workspace(ctx);
+    ctx->weights_loaded = true;
+  } catch (...) {
+    cudaDeviceSynchronize();
+    while (ctx->owned.size() > owned0) { cudaFree(ctx->owned.back()); ctx->owned.pop_back(); }
+    ctx->owned_bytes = bytes0;
+    ctx->W = cs::Weights();
+    ctx->M = cs::MotionW();
+    ctx->wino_convs.clear();
+    ctx->arena = cs::Arena();
+    ctx->weights_loaded = false; ctx->identity_set = false; ctx->calib_tab = nullptr;
+    throw;
+  }
   CS_API_END(ctx)
 }
 
@@ -445,7 +468,7 @@ int cs_frame(cs_ctx* ctx, const void* frames, const float* kp_t, const float* kp
              CS_ERR_INVALID, "cs_frame: CS_FRAME_V2I_FEATURE needs CS_FRAME_V2I and fp32 input without CS_FRAME_MOTION");
   Net n = make_net(ctx, stream, false);
   ctx->arena.reset(0);
-  if (!ctx->use_graph || ctx->prof.on) {
+  if (!ctx->use_graph || ctx->prof.on || ctx->calib_on) {
     body_frame(n, frames, kp_t, kp_can, out_f32, out_u8, B, flags);
   } else {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -571,6 +594,7 @@ int cs_paste_back(cs_ctx* ctx, const uint8_t* img_crop, const float* mask_crop, 
                   uint8_t* out, int B, int hc, int wc, int H, int W, void* stream) {
   CS_API_BEGIN(ctx)
   CS_REQUIRE(img_crop && mask_crop && M_c2o && img_ori && out, CS_ERR_INVALID, "cs_paste_back: null argument");
+  CS_REQUIRE(B >= 1 && B <= CS_PASTE_MAX_BATCH, CS_ERR_INVALID, "cs_paste_back: batch outside [1, CS_PASTE_MAX_BATCH]");
   CS_REQUIRE(hc >= 1 && wc >= 1 && H >= 1 && W >= 1 && hc <= 16384 && wc <= 16384 && H <= 16384 && W <= 16384, CS_ERR_INVALID,
              "cs_paste_back: image size outside [1, 16384]");
   Net n = make_net(ctx, stream, false);
@@ -585,11 +609,35 @@ int cs_soft_erosion(cs_ctx* ctx, const float* mask, const float* kernel, float* 
   const size_t need = ((size_t)2 * B * H * W + B + 64) * sizeof(float);
   if (need > ctx->se_cap) {                                  // not on the per-frame path of the generator: grown on demand
     CS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    if (ctx->se_scratch) {                                    // the smaller buffer is not kept
+      for (size_t i = 0; i < ctx->owned.size(); ++i)
+        if (ctx->owned[i] == ctx->se_scratch) { ctx->owned.erase(ctx->owned.begin() + (long)i); break; }
+      cudaFree(ctx->se_scratch);
+      ctx->owned_bytes -= ctx->se_cap;
+      ctx->se_scratch = nullptr; ctx->se_cap = 0;
+    }
     ctx->se_scratch = static_cast<float*>(ctx->dmalloc(need));
     ctx->se_cap = need;
   }
   Net n = make_net(ctx, stream, false);
   soft_erosion(n.L, mask, out, hard, ctx->se_scratch, kernel, B, H, W, kernel_size, threshold, iterations);
+  CS_API_END(ctx)
+}
+
+int cs_calibrate(cs_ctx* ctx, int phase, float* maxima, int cap) {
+  CS_API_BEGIN(ctx)
+  CS_CUDA(cudaDeviceSynchronize());
+  ctx->drop_graphs();                                        // captured graphs bake the operand scales in
+  if (phase == 1) {
+    calibrate_begin(ctx);
+  } else if (phase == 0) {
+    calibrate_end(ctx, maxima, cap);
+  } else if (phase == 2) {                                   // back to the unscaled operands
+    ctx->calib_on = false;
+    reset_activation_scales(ctx);
+  } else {
+    throw cs::Error(CS_ERR_INVALID, "cs_calibrate: phase must be 1 (begin), 0 (end) or 2 (reset)");
+  }
   CS_API_END(ctx)
 }
 
@@ -667,6 +715,7 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
   };
   try {
     ConvW cw = pack_conv_host(ctx, hw, bias ? &hb : nullptr, Cout, Cin, KD, KH, KW);
+    cw.amul = std::ldexp(1.f, ctx->test_amul_log2);          // CS_OPT_TEST_AMUL: exercise the activation pre-scale
     CS_CUDA(cudaDeviceSynchronize());          // the packing kernels ran on the null stream
     const int Do = D + 2 * PD - KD + 1, Ho = H + 2 * PH - KH + 1, Wo = W + 2 * PW - KW + 1;
     CS_REQUIRE(Do > 0 && Ho > 0 && Wo > 0, CS_ERR_INVALID, "cs_test_conv: empty output");
@@ -683,6 +732,7 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
     if (impl == 5) {
       // Winograd F(2x2,3x3) form (wino.cu): input transform -> 16 GEMMs on the tcgen05 kernel -> output transform
       pack_wino_static(ctx, cw);
+      if (cw.wn) cw.wn->amul = cw.amul;                     // the pre-scale applies to the transformed operand V
       CS_CUDA(cudaDeviceSynchronize());
       L.winograd = true;
       CS_REQUIRE(same && D == 1 && wino_ok(L, cw, H, W), CS_ERR_INVALID, "cs_test_conv: shape not supported by the Winograd conv");

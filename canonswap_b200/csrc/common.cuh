@@ -69,6 +69,8 @@ struct Opd {
   __nv_bfloat16* p = nullptr;
   int B = 0, D = 1, H = 0, W = 0, nblk = 0;
   int pstride = 0;      // 16-bit elements per pixel when the operand is a block range of a wider one (0 = dense: nblk * 64)
+  float amul = 1.f;     // power of two the values were multiplied by before the fp16 split (ConvW::amul of the conv the operand
+                        // was allocated for): keeps small activations out of fp16's subnormal range; the reader divides it out
   long row() const { return pstride ? pstride : (long)nblk * 64; }
 };
 
@@ -137,6 +139,10 @@ struct ConvW {
   float w7_kappa = 0.f;            // truncation pre-compensation folded into w7
   int nblk = 0, Cout_p = 0, BN = 0;
   float wmul = 1.f;                // power of two applied to the packed tcgen05 weights (epilogues multiply by 1 / wmul)
+  float amul = 1.f;                // power of two applied to this conv's INPUT operand by whoever writes it (Opd::amul), chosen by
+                                   // cs_calibrate from the measured max |activation| so that the split halves stay in fp16's normal range
+  int id = -1;                     // index of this conv in the ctx's calibration table
+  bool amul_fixed = false;         // operand writers that do not take a scale (motion extractor): amul stays 1
   int zrows = 0;                   // > 0: depth-dependent weights (rows d*zrows .. of wtc belong to depth slice d)
   ConvW* wn = nullptr;             // Winograd F(2x2,3x3) form of a 3x3 conv (wino.cu): 16 x Cout rows, K = Cin, zrows = Cout
   // accumulator plan of the tcgen05 kernel, fixed when the weights are packed (pack_tc): the packed weights carry the
@@ -159,6 +165,7 @@ struct Epilogue {
   // [pixels, emit_nblk, 64] of the next conv (scale/shift null = identity); the fp32 output pointer may then be null
   __nv_bfloat16* emit = nullptr;
   int emit_nblk = 0;
+  float emit_mul = 1.f;              // Opd::amul of the emitted operand
   const float* emit_scale = nullptr;
   const float* emit_shift = nullptr;
   int emit_act = ACT_NONE;
@@ -254,6 +261,7 @@ struct Launcher {            // everything a kernel launch helper needs
                               // used by the kernels whose weights are not position-compensated at pack time (ConvW::plan_kappa == 0)
   Profiler* prof = nullptr;
   const char* tag = nullptr;  // stage label attached to profiler records
+  unsigned* calib = nullptr;  // calibration pass (cs_calibrate): per-conv max |input activation| as float bits, indexed by ConvW::id
   void count() const { if (counter) ++*counter; }
 };
 
@@ -292,7 +300,9 @@ void stats_finalize_blocks(const Launcher& L, const double* part, int nblocks, i
 struct StatsOut { double* scratch = nullptr; float* mean = nullptr; float* rstd = nullptr; float eps = 1e-5f; };
 void adaptive_blend(const Launcher& L, const float* o2 /*[P,1024]*/, const float* mask /*[P]*/,
                     const float* residual /*[P,512] or null*/, int relu, float* y /*[P,512] or null*/,
-                    __nv_bfloat16* opl /*next conv operand [P,16,64] or null*/, long P);
+                    __nv_bfloat16* opl /*next conv operand [P,16,64] or null*/, long P, float opl_mul = 1.f);
+// calibration: max |value| of a split operand (hi halves, scale divided out) into slot `id` of the table
+void operand_absmax(const Launcher& L, const Opd& x, int id);
 void nchw_to_cl(const Launcher& L, const float* src, float* dst, int B, int C, long S, int vol_perm);
 void cl_to_nchw(const Launcher& L, const float* src, float* dst, int B, int C, long S, int vol_perm, int Cstride);
 void ingest_u8(const Launcher& L, const uint8_t* src, float* dst, long n);

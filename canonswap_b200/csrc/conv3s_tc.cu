@@ -50,7 +50,7 @@ struct Conv3sK {
   const float* bias; int act; float slope;
   const float* res; long rb, rd, rh, rw;
   float* y; long yb, yd, yh, yw;
-  __nv_bfloat16* emit; const float* escale; const float* eshift; int eact; float eslope;
+  __nv_bfloat16* emit; const float* escale; const float* eshift; int eact; float eslope; float emul;
   float out_scale;                 // 1 / ConvW::wmul (x the constant truncation compensation when the weights carry none)
   float kappa;                     // > 0: pre-compensated weights; the epilogue takes back what was assumed for taps in the zero padding:
                                    // depth 15 ends 54 events early (exact), h / w border rows lose interleaved taps (kappa * fraction * events / 2)
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3s_tc_kernel(const __grid_cons
           if constexpr (EMIT) {
             float e[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope);
+            for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope) * k.emul;
             uint2 hv, lv;
             split_operand4(e[0], e[1], e[2], e[3], hv, lv);
             __nv_bfloat16* ep = k.emit + (epix[i] + d * dstride_e) * 64 + c4;
@@ -393,7 +393,9 @@ void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& 
   // weights packed with the position-dependent pre-compensation need no epilogue factor except at depth 15 (54 events early);
   // otherwise the constant factor of the mean loss of a 162-MMA chain (CS_OPT_TC_COMP)
   k.kappa = w.w3s_kappa;
-  k.out_scale = (w.w3s_kappa != 0.f ? 1.0f : 1.0f + L.acc_comp * 1e-10f * 162.f) / w.wmul;
+  k.out_scale = (w.w3s_kappa != 0.f ? 1.0f : 1.0f + L.acc_comp * 1e-10f * 162.f) / (w.wmul * x.amul);
+  k.emul = e.emit_mul;
+  operand_absmax(L, x, w.id);
   k.stats = stats_part;
 
   auto enc = encode_fn();

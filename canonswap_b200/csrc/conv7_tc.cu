@@ -336,7 +336,8 @@ void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* s
   k.ldo = (int)out.sw;
   k.parts = scratch;
   k.part_stride = (long)x.B * 16 * x.H * x.W * k.ldo;
-  k.out_scale = 1.0f / w.wmul;
+  k.out_scale = 1.0f / (w.wmul * x.amul);
+  operand_absmax(L, x, w.id);
   k.ev_slice = 7 * (2 * (x.nblk - 1) + k.last_ksteps);
   k.kappa = w.w7_kappa;
   k.acc_scale = w.w7_kappa != 0.f ? 1.0f : 1.0f + L.acc_comp * 1e-10f * (float)(7 * k.ev_slice);   // chain: 7 z x 7 kw x K steps

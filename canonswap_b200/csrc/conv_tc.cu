@@ -51,7 +51,7 @@ struct ConvTcK {
   float* y; long yb, yd, yh, yw;               // may be null when only the operand is emitted
   int vec4;
   // optional: also write act(v * escale[n] + eshift[n]) as the split-bf16 operand of the next conv (dense, output geometry)
-  __nv_bfloat16* emit; int erow; const float* escale; const float* eshift; int eact; float eslope;
+  __nv_bfloat16* emit; int erow; const float* escale; const float* eshift; int eact; float eslope; float emul;
   // SPADE epilogue (see Epilogue::sp_x)
   const float* sp_x; const float* sp_mean; const float* sp_rstd; int sp_C, sp_xs, sp_Hx, sp_Wx;
   // phase mode (conv of a nearest-upsampled input computed on the low-resolution operand, see Epilogue::phase_shift):
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
           v2 = apply_act(v2, k.eact, k.eslope); v3 = apply_act(v3, k.eact, k.eslope);
           if (k.emit) {
             uint2 hv, lv;
-            split_operand4(v0, v1, v2, v3, hv, lv);
+            split_operand4(v0 * k.emul, v1 * k.emul, v2 * k.emul, v3 * k.emul, hv, lv);
             __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (ch >> 5) * 64 + (ch & 31);
             *reinterpret_cast<uint2*>(ep) = hv;
             *reinterpret_cast<uint2*>(ep + 32) = lv;
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
           if constexpr (EMIT) {                             // the next conv's split-bf16 operand, transform fused
             float e[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope);
+            for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope) * k.emul;
             uint2 hv, lv;
             split_operand4(e[0], e[1], e[2], e[3], hv, lv);
             __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (nc >> 5) * 64 + (nc & 31);
@@ -662,6 +662,7 @@ Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out) {
   Opd o;
   o.B = out.B; o.D = out.D; o.H = out.H; o.W = out.W;
   o.nblk = (w.Cin + 31) / 32;
+  o.amul = w.amul;
   o.p = A.bf16((size_t)out.B * out.D * out.H * out.W * o.nblk * 64);
   return o;
 }
@@ -725,7 +726,9 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   }
   CS_REQUIRE(x.nblk == w.nblk, CS_ERR_INVALID, "conv_tc: channel mismatch");
 
+  operand_absmax(L, x, w.id);
   ConvTcK k{};
+  k.emul = e.emit_mul;
   k.B = x.B; k.D = g.Do; k.H = x.H; k.W = x.W;
   int cap = 128;
   int bw = pick_box(x.W, cap, &k.lbw); cap /= bw;
@@ -793,7 +796,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     const int chain = per_set * 2 * (corr ? 1 : k.npass);
     k.acc_scale = w.plan_kappa != 0.f ? 1.0f : 1.0f + L.acc_comp * 1e-10f * (float)chain;
     k.kappa = w.plan_kappa; k.Din = x.D;
-    k.out_scale = 1.0f / w.wmul;
+    k.out_scale = 1.0f / (w.wmul * x.amul);
   }
   const int egroups = k.BN > 64 ? 2 : 1;                   // 8 epilogue warps on wide tiles
   CS_REQUIRE(!k.sp_x || (k.BN + 32 * egroups - 1) / (32 * egroups) <= 4, CS_ERR_INVALID, "conv_tc: SPADE epilogue holds <= 4 chunks per warp");

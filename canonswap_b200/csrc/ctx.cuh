@@ -120,6 +120,8 @@ struct cs_ctx {
   cudaEvent_t ev_lane[4] = {};
   cudaEvent_t ev_fork = nullptr;
   cs::Profiler prof;
+  // activation-scale calibration (cs_calibrate): per-conv max |input activation| as float bits, indexed by ConvW::id
+  unsigned* calib_tab = nullptr; int n_conv_ids = 0; bool calib_on = false; int test_amul_log2 = 0;
   // CUDA-graph replay of cs_frame (CS_OPT_USE_GRAPH): the whole loop body is captured once per (B, flags, outputs)
   // on fixed staging buffers; a call then is copy-in -> graph launch -> copy-out on the caller's stream.
   struct FrameGraph { cudaGraphExec_t exec = nullptr; int B = 0, flags = 0; bool f32 = false, u8 = false; int seen = 0; int64_t launches = 0; };
@@ -152,6 +154,9 @@ struct Net {                 // per-call view
 // weights.cu
 void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n);
 void set_identity(cs_ctx* ctx, const float* id_dev, cudaStream_t stream);
+void calibrate_begin(cs_ctx* ctx);                     // weights.cu
+int calibrate_end(cs_ctx* ctx, float* maxima, int cap);
+void reset_activation_scales(cs_ctx* ctx);
 ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt /*[Cout][Cin][taps]*/, const std::vector<float>* bias,
                      int Cout, int Cin, int KD, int KH, int KW, int phase_shift = 0);
 float weight_prescale(const float* w, size_t n);             // weights.cu

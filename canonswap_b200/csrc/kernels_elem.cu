@@ -23,6 +23,7 @@ struct PrepK {
   // outputs
   float* o32; long ob, od, oh, ow;
   __nv_bfloat16* opl; long prow;   // split-bf16 operand: dense pixels, prow = nblk*64 elements per pixel
+  float amul;                      // Opd::amul
 };
 
 __global__ void __launch_bounds__(256) prep_kernel(PrepK k) {
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepK k) {
     if (k.o32 && c < k.Cl) k.o32[b * k.ob + d * k.od + h * k.oh + w * k.ow + c] = v;
     if (k.opl) {
       long o = pix * k.prow + (c >> 5) * 64 + (c & 31);
-      split_operand(v, k.opl[o], k.opl[o + 32]);
+      split_operand(v * k.amul, k.opl[o], k.opl[o + 32]);
     }
   }
 }
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) prep_kernel_v4(PrepK k) {
     if (k.opl) {
       const long o = pix * k.prow + (c >> 5) * 64 + (c & 31);
       uint2 hv, lv;
-      split_operand4(v.x, v.y, v.z, v.w, hv, lv);
+      split_operand4(v.x * k.amul, v.y * k.amul, v.z * k.amul, v.w * k.amul, hv, lv);
       *reinterpret_cast<uint2*>(k.opl + o) = hv;
       *reinterpret_cast<uint2*>(k.opl + o + 32) = lv;
     }
@@ -194,7 +195,7 @@ void prep_planes(const Launcher& L, const Prep& p, Opd out, const Act* out32) {
   PrepK k = make_prepk(p);
   CS_REQUIRE(out.nblk * 32 >= k.Cl, -1, "prep_planes: padded channels too small");
   k.B = out.B; k.D = out.D; k.H = out.H; k.W = out.W; k.Cout = out.nblk * 32;
-  k.opl = out.p; k.prow = (long)out.nblk * 64;
+  k.opl = out.p; k.prow = out.row(); k.amul = out.amul;
   if (out32) {
     CS_REQUIRE(out32->C == k.Cl, -1, "prep_planes: fp32 copy channel mismatch");
     k.o32 = out32->p; k.ob = out32->sb; k.od = out32->sd; k.oh = out32->sh; k.ow = out32->sw;
@@ -361,7 +362,7 @@ void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, f
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adaptive_blend_kernel(const float4* __restrict__ o2, const float* __restrict__ mask,
                                                             const float4* residual, int relu, float4* y,
-                                                            __nv_bfloat16* __restrict__ opl, long P) {
+                                                            __nv_bfloat16* __restrict__ opl, long P, float opl_mul) {
   long total = P * 128;     // 512 channels / 4
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long pix = i >> 7; int q = (int)(i & 127);
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(256) adaptive_blend_kernel(const float4* __res
     if (opl) {                // split-bf16 operand of the next conv: [pix][16 blocks][hi 32 | lo 32]
       const int c = q * 4;
       uint2 hv, lv;
-      split_operand4(v.x, v.y, v.z, v.w, hv, lv);
+      split_operand4(v.x * opl_mul, v.y * opl_mul, v.z * opl_mul, v.w * opl_mul, hv, lv);
       __nv_bfloat16* o = opl + pix * 1024 + (c >> 5) * 64 + (c & 31);
       *reinterpret_cast<uint2*>(o) = hv;
       *reinterpret_cast<uint2*>(o + 32) = lv;
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(256) adaptive_blend_kernel(const float4* __res
 }
 
 void adaptive_blend(const Launcher& L, const float* o2, const float* mask, const float* residual, int relu, float* y,
-                    __nv_bfloat16* opl, long P) {
+                    __nv_bfloat16* opl, long P, float opl_mul) {
   L.count();
   if (L.dry) return;
   long blocks = (P * 128 + 255) / 256;
@@ -393,8 +394,35 @@ void adaptive_blend(const Launcher& L, const float* o2, const float* mask, const
   ProfScope ps(L, PK_OTHER, 0.0, (double)P * (1024 + 512 + 512) * 4.0, "blend");
   adaptive_blend_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(o2), mask,
                                                                reinterpret_cast<const float4*>(residual), relu,
-                                                               reinterpret_cast<float4*>(y), opl, P);
+                                                               reinterpret_cast<float4*>(y), opl, P, opl_mul);
   check_launch("adaptive_blend");
+}
+
+// ------------------------------------------------------------------------------------------
+// calibration (cs_calibrate): max |v| over a split operand, from the hi halves (|lo| <= 2^-11 |hi|), scale divided out
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) operand_absmax_kernel(const __half* __restrict__ p, long nrows /*64-element rows*/, long rstride,
+                                                             int nblk, float inv_amul, unsigned* __restrict__ slot) {
+  float mx = 0.f;
+  const long total = nrows * 32;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i >> 5; const int j = (int)(i & 31);
+    const long pix = r / nblk; const int blk = (int)(r % nblk);
+    const float v = fabsf(__half2float(p[pix * rstride + blk * 64 + j]));
+    if (v > mx && v <= 65504.f) mx = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(slot, __float_as_uint(mx * inv_amul));
+}
+
+void operand_absmax(const Launcher& L, const Opd& x, int id) {
+  if (L.dry || !L.calib || id < 0) return;
+  const long pixels = (long)x.B * x.D * x.H * x.W;
+  long blocks = (pixels * x.nblk * 32 + 255) / 256; if (blocks > 148L * 8) blocks = 148L * 8;
+  operand_absmax_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const __half*>(x.p), pixels * x.nblk, x.row(), x.nblk,
+                                                               1.0f / x.amul, L.calib + id);
+  check_launch("operand_absmax");
 }
 
 __global__ void avg2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, long n) {

@@ -105,7 +105,7 @@ void dm_input(const Launcher& L, const Act& c4, const float* kp_driving, const f
 // memory, then every lane splits 4 channels and the warp writes 4 full 128-byte rows.
 __global__ void __launch_bounds__(256) dm_input_operand_kernel(const float4* __restrict__ c4, const float* __restrict__ kpd,
                                                                const float* __restrict__ kps, int K, int B, int D, int H, int W,
-                                                               __nv_bfloat16* __restrict__ out, long prow) {
+                                                               __nv_bfloat16* __restrict__ out, long prow, float amul) {
   __shared__ float vals[8][128];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long nvox = (long)B * D * H * W;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) dm_input_operand_kernel(const float4* __r
     __syncwarp();
     const int c = lane * 4;
     uint2 hv, lv;
-    split_operand4(vv[c], vv[c + 1], vv[c + 2], vv[c + 3], hv, lv);
+    split_operand4(vv[c] * amul, vv[c + 1] * amul, vv[c + 2] * amul, vv[c + 3] * amul, hv, lv);
     __nv_bfloat16* o = out + pix * prow + (c >> 5) * 64 + (c & 31);
     *reinterpret_cast<uint2*>(o) = hv;
     *reinterpret_cast<uint2*>(o + 32) = lv;
@@ -166,7 +166,7 @@ void dm_input_operand(const Launcher& L, const Act& c4, const float* kp_driving,
   long blocks = (nvox + 7) / 8; if (blocks > 148L * 32) blocks = 148L * 32;
   ProfScope ps(L, PK_SAMPLE, 0.0, (double)nvox * (4 + 128) * 4.0, "dm_input");
   dm_input_operand_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(c4.p), kp_driving, kp_source, K, c4.B,
-                                                                 c4.D, c4.H, c4.W, out.p, out.row());
+                                                                 c4.D, c4.H, c4.W, out.p, out.row(), out.amul);
   check_launch("dm_input_operand");
 }
 

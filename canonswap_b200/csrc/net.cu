@@ -95,7 +95,7 @@ static void conv_from_operand(Net& n, const Opd& opd, const ConvW& w, const Conv
     e.rs_b = o.residual->sb; e.rs_d = o.residual->sd; e.rs_h = o.residual->sh; e.rs_w = o.residual->sw;
   }
   if (o.emit) {
-    e.emit = o.emit->p; e.emit_nblk = o.emit->nblk;
+    e.emit = o.emit->p; e.emit_nblk = o.emit->nblk; e.emit_mul = o.emit->amul;
     if (o.emit_affine) { e.emit_scale = o.emit_affine->scale; e.emit_shift = o.emit_affine->shift; }
     e.emit_act = o.emit_act; e.emit_slope = o.emit_slope;
   }
@@ -439,7 +439,7 @@ static void adaptive_conv_tc(Net& n, const AdaptiveConvW& a, const Act& geom, co
   conv_from_operand(n, in, a.combined, ConvOpts(), o2);
   ConvOpts sg; sg.act = ACT_SIGMOID;
   conv_from_operand(n, in, a.mask_conv, sg, make_act(mask, geom.B, 1, geom.H, geom.W, 1));
-  adaptive_blend(n.L, o2.p, mask, residual, relu, y, out ? out->p : nullptr, geom.pixels());
+  adaptive_blend(n.L, o2.p, mask, residual, relu, y, out ? out->p : nullptr, geom.pixels(), out ? out->amul : 1.f);
   n.A->reset(m);
 }
 
@@ -466,6 +466,7 @@ void run_swap(Net& n, const float* vol_in, int B, float* vol_out, float* masks) 
     ConvGeom gg; gg.Do = 16; gg.Ho = V.H; gg.Wo = V.W;
     auto wino_adaptive = [&](const AdaptiveConvW& a, float* in, const float* residual, int relu, float* out, float* mask) {
       Act xin = vol_as_2d(in, B, h, w);
+      V.amul = a.wino.amul;
       wino_in(n.L, xin, V, &a.mask_conv, mask);              // + the 512 -> 1 mask conv on the same patches
       Epilogue eg;
       eg.alg_flops = 2.0 * (double)P * 1024 * 512 * 9.0;       // the two 3x3 branches this GEMM stands for

@@ -278,6 +278,77 @@ ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt, const std::vec
   return c;
 }
 
+// every tcgen05 conv of the five networks (and its Winograd form), in a fixed order
+template <class F>
+static void for_each_conv(Weights& W, F f) {
+  auto one = [&](ConvW& w) { if (w.wtc || w.w32) f(w); if (w.wn) f(*w.wn); };
+  one(W.f_first); one(W.f_down[0]); one(W.f_down[1]); one(W.f_second);
+  for (auto& r : W.f_res) { one(r.conv1); one(r.conv2); }
+  one(W.dm_compress);
+  for (auto& c : W.hg_enc) one(c);
+  for (auto& c : W.hg_dec) one(c);
+  one(W.hg_final); one(W.dm_mask); one(W.dm_occlusion); one(W.dm_occ_y); one(W.w_third); one(W.w_fourth);
+  for (auto& a : W.ad) { one(a.mask_conv); one(a.combined); one(a.wino); }
+  for (auto& r : W.t_res) { one(r.conv1); one(r.conv2); }
+  for (auto& r : W.r_gn1) { one(r.conv1); one(r.conv2); }
+  for (auto& r : W.r_gn3) { one(r.conv1); one(r.conv2); }
+  for (auto& r : W.r_res2) { one(r.conv1); one(r.conv2); }
+  one(W.g_fc); one(W.g_img);
+  for (auto& b : W.g_blocks) {
+    for (SpadeNormW* s : {&b.norm_0, &b.norm_1, &b.norm_s}) { one(s->shared); one(s->shared_ph); one(s->gamma_beta); }
+    one(b.conv_0); one(b.conv_1); one(b.conv_s);
+  }
+}
+
+static void assign_conv_ids(cs_ctx* ctx) {
+  int id = 0;
+  for_each_conv(ctx->W, [&](ConvW& w) { w.id = id++; });
+  // the per-identity convs are filled by set_identity: give them ids now (their ConvW objects are stable members)
+  for (auto& a : ctx->W.ad) { if (a.combined.id < 0) a.combined.id = id++; if (a.wino.id < 0) a.wino.id = id++; }
+  ctx->n_conv_ids = id;
+}
+
+// Activation-scale calibration.  The split-fp16 operand format has fp16's exponent range: values beyond 65504 saturate and
+// the lo half of values below ~0.06 is subnormal (the conv's relative error grows from 4e-7 to 2e-5 at |x| ~ 1e-3,
+// tools/scale_probe.py).  Weights get a power-of-two pre-scale at pack time (ConvW::wmul); activations get one per conv
+// (ConvW::amul, applied by whoever writes the operand, divided out by the conv's epilogue) chosen from the largest |input|
+// seen while a representative batch runs between calibrate_begin and calibrate_end: max * amul ~ 2^10, i.e. a factor 64 of
+// head-room to saturation and full precision down to 1e-4 of the maximum.
+void calibrate_begin(cs_ctx* ctx) {
+  CS_REQUIRE(ctx->weights_loaded, CS_ERR_STATE, "cs_calibrate before cs_load_weights");
+  if (!ctx->calib_tab) ctx->calib_tab = static_cast<unsigned*>(ctx->dmalloc(sizeof(unsigned) * (size_t)(ctx->n_conv_ids + 1)));
+  CS_CUDA(cudaMemset(ctx->calib_tab, 0, sizeof(unsigned) * (size_t)(ctx->n_conv_ids + 1)));
+  ctx->calib_on = true;
+}
+
+int calibrate_end(cs_ctx* ctx, float* maxima, int cap) {
+  CS_REQUIRE(ctx->calib_on && ctx->calib_tab, CS_ERR_STATE, "cs_calibrate(end) without cs_calibrate(begin)");
+  CS_CUDA(cudaDeviceSynchronize());
+  std::vector<float> mx((size_t)ctx->n_conv_ids + 1, 0.f);
+  CS_CUDA(cudaMemcpy(mx.data(), ctx->calib_tab, sizeof(float) * mx.size(), cudaMemcpyDeviceToHost));
+  ctx->calib_on = false;
+  int changed = 0;
+  auto apply = [&](ConvW& w) {
+    if (w.id < 0 || w.id >= ctx->n_conv_ids || w.amul_fixed) return;
+    const float m = mx[w.id];
+    if (!(m > 0.f) || !std::isfinite(m)) return;                 // conv not reached by the calibration batch: keep its scale
+    int k = (int)std::floor(std::log2(1024.0 / (double)m));
+    if (k < -14) k = -14;
+    if (k > 14) k = 14;
+    const float a = std::ldexp(1.f, k);
+    if (a != w.amul) { w.amul = a; ++changed; }
+  };
+  for_each_conv(ctx->W, apply);
+  for (auto& a : ctx->W.ad) { apply(a.combined); apply(a.wino); }
+  if (maxima) for (int i = 0; i < cap && i < ctx->n_conv_ids; ++i) maxima[i] = mx[i];
+  return changed;
+}
+
+void reset_activation_scales(cs_ctx* ctx) {
+  for_each_conv(ctx->W, [](ConvW& w) { w.amul = 1.f; });
+  for (auto& a : ctx->W.ad) { a.combined.amul = 1.f; a.wino.amul = 1.f; }
+}
+
 // ------------------------------------------------------------------------------------------
 // load_weights
 // ------------------------------------------------------------------------------------------
@@ -465,6 +536,7 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
   W.g_img = pack(ctx, read_conv(t, "conv_img.0", 12, 64, 1, 3, 3));
 
   CS_CUDA(cudaDeviceSynchronize());
+  assign_conv_ids(ctx);
   ctx->weights_loaded = true;
 }
 

@@ -74,7 +74,7 @@ template <bool MASK>
 __global__ void __launch_bounds__(256) wino_in_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ V, int B, int H, int W,
                                                       int C, const float* __restrict__ mw /*[9][C]*/, const float* __restrict__ mb,
                                                       float* __restrict__ mask /*[B,H,W]*/, const float* __restrict__ pscale,
-                                                      const float* __restrict__ pshift, int pact, float pslope) {
+                                                      const float* __restrict__ pshift, int pact, float pslope, float amul) {
   __shared__ float red[8][4];
   const int Ht = H >> 1, Wt = W >> 1;
   const long tiles = (long)B * Ht * Wt;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) wino_in_kernel(const float* __restrict__ 
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         uint2 hv, lv;
-        split_operand4(o[l].x, o[l].y, o[l].z, o[l].w, hv, lv);
+        split_operand4(o[l].x * amul, o[l].y * amul, o[l].z * amul, o[l].w * amul, hv, lv);
         __nv_bfloat16* p = base + (long)(i * 4 + l) * plane;
         *reinterpret_cast<uint2*>(p) = hv;
         *reinterpret_cast<uint2*>(p + 32) = lv;
@@ -301,6 +301,7 @@ void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const 
                  y.sh == (long)y.W * y.C && y.sb == (long)y.H * y.W * y.C, CS_ERR_INVALID, "wino_conv: unsupported geometry");
   const size_t m = A.mark();
   Opd V; V.B = x.B; V.D = 16; V.H = x.H / 2; V.W = x.W / 2; V.nblk = x.C / 32;
+  V.amul = w.wn->amul;
   V.p = A.bf16((size_t)x.B * 16 * V.H * V.W * V.nblk * 64);
   Act Mt = make_act(A.f32((size_t)x.B * 16 * V.H * V.W * w.Cout), x.B, 16, V.H, V.W, w.Cout);
   wino_in(L, x, V, nullptr, nullptr, pscale, pshift, pact, pslope);
@@ -362,10 +363,10 @@ void wino_in(const Launcher& L, const Act& x, Opd V, const ConvW* mask_conv, flo
     CS_REQUIRE(mask && mask_conv->w32 && mask_conv->Cin == x.C && mask_conv->Cout == 1 && mask_conv->KD == 1 && mask_conv->KH == 3 &&
                    mask_conv->KW == 3 && mask_conv->bias, CS_ERR_INVALID, "wino_in: bad mask conv");
     wino_in_kernel<true><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, mask_conv->w32, mask_conv->bias, mask,
-                                                                     pscale, pshift, pact, pslope);
+                                                                     pscale, pshift, pact, pslope, V.amul);
   } else {
     wino_in_kernel<false><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, nullptr, nullptr, nullptr, pscale,
-                                                                      pshift, pact, pslope);
+                                                                      pshift, pact, pslope, V.amul);
   }
   check_launch("wino_in");
 }

@@ -341,6 +341,20 @@ class Engine:
                                             labels.data_ptr() if labels is not None else None, self._stream()))
         return (mask, labels) if want_labels else mask
 
+    def calibrate(self, run_batch):
+        """Choose the per-conv activation pre-scales from a representative batch: `run_batch()` must call this engine
+        (frame / stage calls) at least once.  Returns the measured max |input| per conv (library order)."""
+        self._check(self._lib.cs_calibrate(self._ctx, 1, None, 0))
+        try:
+            run_batch()
+        finally:
+            buf = (C.c_float * 1024)()
+            self._check(self._lib.cs_calibrate(self._ctx, 0, buf, 1024))
+        return [float(v) for v in buf]
+
+    def reset_calibration(self):
+        self._check(self._lib.cs_calibrate(self._ctx, 2, None, 0))
+
     # ---- measurement -------------------------------------------------------------------------------
     PROFILE_FAMILIES = ("conv_tcgen05", "conv_simt", "prep", "stats", "sampling", "other")
 

@@ -491,5 +491,14 @@ class can_swapper(object):
         eng = self._hub.engine(hw, int(frames.shape[0]))
         return eng.frame(frames, kp_source, kp_driving, out_u8=out_u8, out_f32=out_f32, v2i=True)
 
+    def calibrate(self, frames: torch.Tensor, x_t: Optional[torch.Tensor] = None, x_can: Optional[torch.Tensor] = None):
+        """Choose the per-conv activation pre-scales of the tcgen05 convs from one representative batch of frames (the split-fp16
+        operands keep fp32-grade precision for |activation| in about [0.06, 65504]; a power-of-two scale per conv centres each
+        layer's range, include/canonswap_b200.h: cs_calibrate).  Worth one call after loading a real checkpoint; the synthetic
+        fixture's activations already sit inside the range.  Returns the measured max |input| per conv."""
+        hw = (int(frames.shape[1]), int(frames.shape[2])) if frames.dtype == torch.uint8 else (int(frames.shape[2]), int(frames.shape[3]))
+        eng = self._hub.engine(hw, int(frames.shape[0]))
+        return eng.calibrate(lambda: eng.frame(frames, x_t, x_can, motion=x_t is None and x_can is None))
+
     def engine(self, net_hw=(256, 256), batch: int = 1) -> Engine:
         return self._hub.engine(tuple(net_hw), batch)

@@ -88,6 +88,7 @@ typedef struct cs_tensor_desc {
                                     weights: units of 1e-10 per truncation event (default 330, 0 = off: the epilogue then applies the
                                     constant CS_OPT_TC_COMP factor).  Options 3, 4, 8, 9, 11, 12 and 14 shape the packed weights and
                                     must be set before cs_load_weights (CS_ERR_STATE afterwards). */
+#define CS_OPT_TEST_AMUL 15      /* cs_test_conv only: log2 of the activation pre-scale applied to the test conv's operand (default 0) */
 #define CS_OPT_LANES 10         /* 1 | 2 (default) | 4: a graph-captured cs_frame runs as this many concurrent sub-batches (forked streams) */
 #define CS_OPT_USE_GRAPH 2       /* 1 = capture cs_frame into a CUDA graph per batch size (default 0)  */
 
@@ -170,9 +171,20 @@ CS_API int cs_paste_back(cs_ctx* ctx, const uint8_t* img_crop, const float* mask
 
 /* SoftErosion.forward (reference src/utils/crop.py:21-47; pipeline_e2e.py:42,275 uses kernel_size 21, threshold 0.9, iterations 3):
  * mask [B,H,W] f32 -> out [B,H,W] f32 soft mask, hard [B,H,W] u8 = (x >= threshold) or NULL.  kernel: DEVICE pointer to the module's
- * normalised [kernel_size^2] weight buffer (the binding builds it exactly as the reference's __init__ does). */
+ * normalised [kernel_size^2] weight buffer (the binding builds it exactly as the reference's __init__ does).
+ * Normalisation: the reference divides the below-threshold values by their maximum over the WHOLE tensor (crop.py:44); it only ever
+ * passes one image (pipeline_e2e.py:275).  Here every image of the batch is normalised by ITS OWN maximum, i.e. a batch of B equals
+ * B reference calls of one image each -- not one reference call on a [B,1,H,W] tensor. */
 CS_API int cs_soft_erosion(cs_ctx* ctx, const float* mask, const float* kernel, float* out, uint8_t* hard, int B, int H, int W,
                            int kernel_size, float threshold, int iterations, void* stream);
+
+/* Activation-scale calibration.  The tcgen05 convs compute on split-fp16 operands (value = hi + lo, both fp16): full fp32-grade precision
+ * needs |activation| within about [0.06, 65504] per tensor.  Weights are pre-scaled at load; activations get one power-of-two scale per
+ * conv, chosen from the largest |input| seen while a representative batch runs:
+ *     cs_calibrate(ctx, 1, NULL, 0);  cs_frame(...) [one or more batches];  cs_calibrate(ctx, 0, maxima, cap);
+ * phase 2 resets every scale to 1.  Scaling by a power of two is exact, so results change only where operands were leaving fp16's
+ * normal range.  maxima (may be NULL): the measured max |input| per conv, in the library's internal conv order. */
+CS_API int cs_calibrate(cs_ctx* ctx, int phase, float* maxima, int cap);
 
 /* Face-parsing post-processing, the step before the path (reference src/can_swap_pipeline_e2e.py:183-190; the Segformer itself is an
  * external HF model and stays outside): logits [B,C,h,w] fp32 -> F.interpolate(size=(H,W), bilinear, align_corners=False) -> argmax over C

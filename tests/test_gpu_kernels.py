@@ -214,3 +214,29 @@ def _tc_any(eng):
         return True
     except Exception:
         return False
+
+
+def test_activation_prescale_restores_precision_of_small_activations():
+    """The split-fp16 operand has fp16's exponent range: with activations of magnitude 1e-3 the lo halves are subnormal and the
+    conv's relative error grows 50x; the per-conv power-of-two activation pre-scale (ConvW::amul, chosen by cs_calibrate) brings it
+    back.  CS_OPT_TEST_AMUL applies a given scale to the test conv's operand."""
+    from canonswap_b200 import _lib
+    from canonswap_b200.engine import Engine
+    e = Engine(None, net_hw=(128, 128), max_batch=1, device=0)
+    try:
+        g = torch.Generator(device="cuda").manual_seed(7)
+        x = torch.randn(2, 1, 32, 32, 256, device="cuda", generator=g) * 1e-3
+        w = torch.randn(256, 256, 1, 3, 3, device="cuda", generator=g) / (256 * 9) ** 0.5
+        ref = _ref_conv(x, w, None, (0, 1, 1)).double()
+        rms = {}
+        for lg in (0, 10):
+            e.set_option(_lib.CS_OPT_TEST_AMUL, lg)
+            for impl in (2, 5):
+                y = e.test_conv(x, w, None, (0, 1, 1), impl=impl)
+                rms[(lg, impl)] = ((y.double() - ref).pow(2).mean().sqrt() / ref.abs().mean()).item()
+        print("relative rms error, activations ~1e-3:", {k: f"{v:.1e}" for k, v in rms.items()})
+        for impl in (2, 5):
+            assert rms[(0, impl)] > 5e-6                      # the unscaled operand really loses precision ...
+            assert rms[(10, impl)] < 1.5e-6                   # ... and the pre-scale restores it
+    finally:
+        e.close()

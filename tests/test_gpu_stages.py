@@ -306,3 +306,28 @@ def test_swap_per_sample_identities(case128, synth_w):
     _close(a, O.swap_module(synth_w["transfer"], ref["f_can"], ids[:1].expand(2, -1)), "one identity")
     with pytest.raises(Exception):
         sw.swap_module(ref["f_can"].cuda(), torch.zeros(3, 512, device="cuda"))
+
+
+def test_activation_scale_calibration(case128, synth_w):
+    """cs_calibrate: per-conv power-of-two activation scales from a representative batch.  Scaling by a power of two is exact, so
+    the calibrated engine reproduces the uncalibrated frame (to the rounding of values that were leaving fp16's normal range) and
+    keeps the parity bar; the measured maxima show the fixture's operands far from saturation."""
+    eng, inp, ref = case128
+    base = torch.empty(2, 3, 256, 256, device="cuda")
+    eng.frame(inp["frames"], inp["x_t"], inp["x_can"], out_f32=base)
+    maxima = eng.calibrate(lambda: eng.frame(inp["frames"], inp["x_t"], inp["x_can"]))
+    seen = [m for m in maxima if m > 0]
+    assert len(seen) > 100 and max(seen) < 65504 / 8, (len(seen), max(seen))
+    try:
+        cal = torch.empty_like(base)
+        eng.frame(inp["frames"], inp["x_t"], inp["x_can"], out_f32=cal)
+        d_cal = (cal.cpu() - ref["out"]).abs().max().item()
+        print(f"calibrated: {len(seen)} convs, max |activation| {max(seen):.1f} / min {min(seen):.2e}; max|d| vs oracle {d_cal:.2e}, "
+              f"vs uncalibrated {(cal - base).abs().max().item():.2e}")
+        assert d_cal <= TOL
+        assert (cal - base).abs().max().item() <= 2e-4
+    finally:
+        eng.reset_calibration()
+    again = torch.empty_like(base)
+    eng.frame(inp["frames"], inp["x_t"], inp["x_can"], out_f32=again)
+    assert torch.equal(again, base)
