@@ -147,6 +147,82 @@ __global__ void __launch_bounds__(256) prep_kernel_v4(PrepK k) {
   }
 }
 
+// The common shapes of the input transform -- one source, no pooling / upsampling / SPADE modulation: plain split, pre-activation
+// BatchNorm, instance / group normalisation (+ residual, + fp32 copy) -- with four independent float4 groups per thread per
+// iteration: all loads are issued before the first use, which is what an HBM-bound kernel needs (the generic kernel keeps one
+// load in flight per thread and runs at a third of the copy bandwidth).
+template <int NORM, bool ADD>
+__global__ void __launch_bounds__(256) prep_kernel_fast(PrepK k) {
+  constexpr int U = 4;
+  // 32-bit index arithmetic (the host checks total < 2^31): the 64-bit divisions of the generic kernel cost more issue slots
+  // than the memory system needs to be kept busy
+  const unsigned C4 = (unsigned)k.Cout >> 2;
+  const unsigned total = (unsigned)k.B * k.D * k.H * k.W * C4;
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned uW = k.W, uH = k.H, uD = k.D;
+  for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x; base < total; base += stride * U) {
+    float4 v[U], a[ADD ? U : 1];
+    int cc[U], bb[U]; unsigned pp[U]; long ooff[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned idx = base + u * stride;
+      live[u] = idx < total && idx >= base;               // (>= base: no wrap-around)
+      const unsigned id2 = live[u] ? idx : 0u;
+      const unsigned pix = id2 / C4;
+      cc[u] = (int)(id2 - pix * C4) * 4;
+      pp[u] = pix;
+      unsigned t = pix / uW; const unsigned w = pix - t * uW;
+      unsigned t2 = t / uH; const unsigned h = t - t2 * uH;
+      const unsigned b = t2 / uD; const unsigned d = t2 - b * uD;
+      bb[u] = (int)b;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live[u] && cc[u] < k.Cl) v[u] = *reinterpret_cast<const float4*>(k.s0 + b * k.s0b + d * k.s0d + h * k.s0h + w * k.s0w + cc[u]);
+      if constexpr (ADD) {
+        a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live[u] && cc[u] < k.Cl) a[u] = *reinterpret_cast<const float4*>(k.add + b * k.ab + d * k.ad + h * k.ah + w * k.aw + cc[u]);
+      }
+      ooff[u] = b * k.ob + d * k.od + h * k.oh + w * k.ow + cc[u];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) continue;
+      float4 x = v[u];
+      const int c = cc[u];
+      if (c < k.Cl) {
+        if constexpr (NORM == NORM_AFFINE_C) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(k.scale + c)), sh = __ldg(reinterpret_cast<const float4*>(k.shift + c));
+          x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
+        } else if constexpr (NORM == NORM_STATS_BC) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(k.mean + bb[u] * k.C0 + c));
+          const float4 r = __ldg(reinterpret_cast<const float4*>(k.rstd + bb[u] * k.C0 + c));
+          x.x = (x.x - m.x) * r.x; x.y = (x.y - m.y) * r.y; x.z = (x.z - m.z) * r.z; x.w = (x.w - m.w) * r.w;
+          if (k.scale) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(k.scale + c)), sh = __ldg(reinterpret_cast<const float4*>(k.shift + c));
+            x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
+          }
+        }
+        if constexpr (ADD) { x.x += a[u].x; x.y += a[u].y; x.z += a[u].z; x.w += a[u].w; }
+        x.x = apply_act(x.x, k.act, k.slope); x.y = apply_act(x.y, k.act, k.slope);
+        x.z = apply_act(x.z, k.act, k.slope); x.w = apply_act(x.w, k.act, k.slope);
+        if (c + 3 >= k.Cl) {                       // ragged tail (plain conversions only): the over-read lanes are pad
+          if (c + 1 >= k.Cl) x.y = 0.f;
+          if (c + 2 >= k.Cl) x.z = 0.f;
+          x.w = 0.f;
+        }
+        if (k.o32) *reinterpret_cast<float4*>(k.o32 + ooff[u]) = x;
+      }
+      if (k.opl) {
+        const long o = (long)pp[u] * k.prow + (c >> 5) * 64 + (c & 31);
+        uint2 hv, lv;
+        split_operand4(x.x * k.amul, x.y * k.amul, x.z * k.amul, x.w * k.amul, hv, lv);
+        *reinterpret_cast<uint2*>(k.opl + o) = hv;
+        *reinterpret_cast<uint2*>(k.opl + o + 32) = lv;
+      }
+    }
+  }
+}
+
 static bool prep_vec_ok(const PrepK& k) {
   auto a4 = [](long v) { return (v & 3) == 0; };
   auto p16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
@@ -171,7 +247,21 @@ static void launch_prep(const Launcher& L, PrepK& k) {
   const long total = (long)k.B * k.D * k.H * k.W * k.Cout;
   // algorithmic bytes: every logical element read once (fp32) and written once (fp32 or hi+lo bf16)
   ProfScope ps(L, PK_PREP, 0.0, (double)k.B * k.D * k.H * k.W * k.Cl * 4.0 * 2.0, "prep");
-  if (prep_vec_ok(k)) {
+  const bool fast = prep_vec_ok(k) && !k.s1 && !k.pool2 && !k.upshift && !k.gb && total / 4 < (1L << 30);
+  if (fast) {
+    long blocks = (total / 16 + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    if (blocks < 1) blocks = 1;
+    if (k.add) {
+      if (k.norm == NORM_STATS_BC) prep_kernel_fast<NORM_STATS_BC, true><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+      else if (k.norm == NORM_AFFINE_C) prep_kernel_fast<NORM_AFFINE_C, true><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+      else prep_kernel_fast<NORM_NONE, true><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+    } else {
+      if (k.norm == NORM_STATS_BC) prep_kernel_fast<NORM_STATS_BC, false><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+      else if (k.norm == NORM_AFFINE_C) prep_kernel_fast<NORM_AFFINE_C, false><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+      else prep_kernel_fast<NORM_NONE, false><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+    }
+  } else if (prep_vec_ok(k)) {
     long blocks = (total / 4 + 255) / 256;
     if (blocks > 148L * 16) blocks = 148L * 16;
     prep_kernel_v4<<<(unsigned)blocks, 256, 0, L.stream>>>(k);
