@@ -569,6 +569,42 @@ def main():
                       "checksums_match_single_gpu": bool(match)}
         del s_frames, s_out
 
+    # ---- video-to-image variant (reference can_swap_pipeline_v2i.py:254-321): the source is swapped
+    #      once (rank 0), the per-source state (the 8.4 MB appearance volume + keypoints / pose) is broadcast over NCCL, and every
+    #      rank animates its share of the driving expressions: one cs_frame (CS_FRAME_V2I_FEATURE) per batch, host buffers in / out
+    v2i = None
+    if not args.no_extra and not args.no_motion and args.strong_frames > 0:
+        from canonswap_b200.pipeline import V2IPipeline
+        TV = max(B * world * 4, args.strong_frames // 4)
+        vp = V2IPipeline(sw, net_hw=(NET, NET), batch=B)
+        g = torch.Generator().manual_seed(21)
+        v_exp = (0.02 * torch.randn(TV, 21, 3, generator=g)).pin_memory()
+        v_ids = list(range(rank, TV, world))
+        v_out = torch.empty(len(v_ids), 2 * NET, 2 * NET, 3, dtype=torch.uint8).pin_memory()
+        src_img = (clip["frames"][:1].permute(0, 3, 1, 2).float() / 255.0).to(dev)
+        if rank == 0:
+            vp.prepare(src_img, clip["source_id"].to(dev))           # warm-up of the once-per-source stage
+        vp.broadcast()
+        vp.run(v_exp[: B * world * 2], v_out, rank=rank, world=world, out_local=True)
+        barrier()
+        t0 = time.perf_counter()
+        if rank == 0:
+            vp.prepare(src_img, clip["source_id"].to(dev))           # source -> canonical -> swap -> decode -> re-extract
+        vp.broadcast()                                                # the one collective (8.4 MB)
+        vp.run(v_exp, v_out, rank=rank, world=world, out_local=True)
+        barrier()
+        vw = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(vw, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            v2i = {"value": TV / vw.item(), "unit": "frames/s", "frames": TV, "seconds": vw.item(), "scaling": "strong",
+                   "gflop_per_frame": 1233.6,
+                   "includes": "once-per-source stage on rank 0 + NCCL broadcast of the state (8.4 MB) + H2D of the driving expressions "
+                               "+ D2H of every frame",
+                   "note": "per frame W.forward + G only: the appearance volume of the swapped canonical image is frame-invariant "
+                           "(the reference recomputes it every frame, can_swap_pipeline_v2i.py:308)"}
+        del v_out
+
     # ---- BASELINE configs[1] (256 px, 32-frame clip, B = 4) and configs[4] (1024 px, B = 2): throughput lines ----------
     configs = None
     if rank == 0 and world == 1 and not args.no_extra:
@@ -629,7 +665,7 @@ def main():
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "families": families, "achieved_tflops_whole_step": value * GFLOP_PER_FRAME / 1000.0,
             "with_motion_extractor": with_motion, "as_written": as_written, "paste_back": paste, "full_loop": full_loop,
-            "parity": parity, "torch_gpu": torch_gpu, "sustained": sustained, "strong": strong, "configs": configs,
+            "parity": parity, "torch_gpu": torch_gpu, "sustained": sustained, "strong": strong, "v2i": v2i, "configs": configs,
         }))
         if parity is not None and not parity["ok"]:
             raise SystemExit(f"bench.py: PARITY FAILURE at the timed configuration: {parity}")

@@ -293,7 +293,7 @@ inline void check_launch(const char* what) {
 void prep_f32(const Launcher& L, const Prep& p, Act out);                    // out: fp32 (strides from Act)
 void prep_planes(const Launcher& L, const Prep& p, Opd out, const Act* out32);   // split-bf16 planes (+ optional fp32 copy)
 void avg2(const Launcher& L, const float* a, const float* b, float* y, long n);   // y = (a + b) / 2
-constexpr int STATS_MAX_BLOCKS = 256;      // per-sample partial blocks of instance_stats: scratch = [B][256][C <= 512][2] doubles
+constexpr int STATS_MAX_BLOCKS = 128;      // per-sample partial blocks of instance_stats: scratch = [B][128][C <= 512][2] doubles
 void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch);
 void stats_finalize_blocks(const Launcher& L, const double* part, int nblocks, int B, int C, long S, float* mean, float* rstd, float eps);
 // request for the instance statistics of a conv's OUTPUT, computed by the kernel that writes it (no extra pass over the tensor)

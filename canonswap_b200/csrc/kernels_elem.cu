@@ -148,79 +148,85 @@ __global__ void __launch_bounds__(256) prep_kernel_v4(PrepK k) {
 }
 
 // The common shapes of the input transform -- one source, no pooling / upsampling / SPADE modulation: plain split, pre-activation
-// BatchNorm, instance / group normalisation (+ residual, + fp32 copy) -- with four independent float4 groups per thread per
-// iteration: all loads are issued before the first use, which is what an HBM-bound kernel needs (the generic kernel keeps one
-// load in flight per thread and runs at a third of the copy bandwidth).
-template <int NORM, bool ADD>
+// BatchNorm, instance / group normalisation (+ residual, + fp32 copy).  The generic kernel is ISSUE-bound (ncu: 66 % issue
+// slots, 2.4 TB/s): a thread there decomposes a 64-bit index, walks a run-time activation switch and splits ONE float4.  Here a
+// thread owns 16 consecutive channels of a pixel (4 float4 loads in flight, one 32-bit index decomposition per 64 bytes, hi / lo
+// halves written as 32-byte runs) and norm / activation / residual are compile-time.
+template <int NORM, bool ADD, int ACT>
 __global__ void __launch_bounds__(256) prep_kernel_fast(PrepK k) {
-  constexpr int U = 4;
-  // 32-bit index arithmetic (the host checks total < 2^31): the 64-bit divisions of the generic kernel cost more issue slots
-  // than the memory system needs to be kept busy
-  const unsigned C4 = (unsigned)k.Cout >> 2;
-  const unsigned total = (unsigned)k.B * k.D * k.H * k.W * C4;
-  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned G = (unsigned)(k.Cout + 15) >> 4;                         // 16-channel groups per pixel
+  const unsigned total = (unsigned)k.B * k.D * k.H * k.W * G;
   const unsigned uW = k.W, uH = k.H, uD = k.D;
-  for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x; base < total; base += stride * U) {
-    float4 v[U], a[ADD ? U : 1];
-    int cc[U], bb[U]; unsigned pp[U]; long ooff[U];
-    bool live[U];
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned pix = idx / G;
+    const int c0 = (int)(idx - pix * G) * 16;
+    unsigned t = pix / uW; const unsigned w = pix - t * uW;
+    unsigned t2 = t / uH; const unsigned h = t - t2 * uH;
+    const unsigned b = t2 / uD; const unsigned d = t2 - b * uD;
+    const float* sp = k.s0 + b * k.s0b + d * k.s0d + h * k.s0h + w * k.s0w + c0;
+    float4 v[4], a[ADD ? 4 : 1];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned idx = base + u * stride;
-      live[u] = idx < total && idx >= base;               // (>= base: no wrap-around)
-      const unsigned id2 = live[u] ? idx : 0u;
-      const unsigned pix = id2 / C4;
-      cc[u] = (int)(id2 - pix * C4) * 4;
-      pp[u] = pix;
-      unsigned t = pix / uW; const unsigned w = pix - t * uW;
-      unsigned t2 = t / uH; const unsigned h = t - t2 * uH;
-      const unsigned b = t2 / uD; const unsigned d = t2 - b * uD;
-      bb[u] = (int)b;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live[u] && cc[u] < k.Cl) v[u] = *reinterpret_cast<const float4*>(k.s0 + b * k.s0b + d * k.s0d + h * k.s0h + w * k.s0w + cc[u]);
-      if constexpr (ADD) {
-        a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live[u] && cc[u] < k.Cl) a[u] = *reinterpret_cast<const float4*>(k.add + b * k.ab + d * k.ad + h * k.ah + w * k.aw + cc[u]);
-      }
-      ooff[u] = b * k.ob + d * k.od + h * k.oh + w * k.ow + cc[u];
+    for (int q = 0; q < 4; ++q) {
+      v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + 4 * q < k.Cl) v[q] = *reinterpret_cast<const float4*>(sp + 4 * q);
     }
+    if constexpr (ADD) {
+      const float* ap = k.add + b * k.ab + d * k.ad + h * k.ah + w * k.aw + c0;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!live[u]) continue;
-      float4 x = v[u];
-      const int c = cc[u];
+      for (int q = 0; q < 4; ++q) {
+        a[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + 4 * q < k.Cl) a[q] = *reinterpret_cast<const float4*>(ap + 4 * q);
+      }
+    }
+    uint2 hv[4], lv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = c0 + 4 * q;
+      float4 x = v[q];
       if (c < k.Cl) {
         if constexpr (NORM == NORM_AFFINE_C) {
           const float4 sc = __ldg(reinterpret_cast<const float4*>(k.scale + c)), sh = __ldg(reinterpret_cast<const float4*>(k.shift + c));
           x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
         } else if constexpr (NORM == NORM_STATS_BC) {
-          const float4 m = __ldg(reinterpret_cast<const float4*>(k.mean + bb[u] * k.C0 + c));
-          const float4 r = __ldg(reinterpret_cast<const float4*>(k.rstd + bb[u] * k.C0 + c));
+          const float4 m = __ldg(reinterpret_cast<const float4*>(k.mean + b * k.C0 + c));
+          const float4 r = __ldg(reinterpret_cast<const float4*>(k.rstd + b * k.C0 + c));
           x.x = (x.x - m.x) * r.x; x.y = (x.y - m.y) * r.y; x.z = (x.z - m.z) * r.z; x.w = (x.w - m.w) * r.w;
           if (k.scale) {
             const float4 sc = __ldg(reinterpret_cast<const float4*>(k.scale + c)), sh = __ldg(reinterpret_cast<const float4*>(k.shift + c));
             x.x = x.x * sc.x + sh.x; x.y = x.y * sc.y + sh.y; x.z = x.z * sc.z + sh.z; x.w = x.w * sc.w + sh.w;
           }
         }
-        if constexpr (ADD) { x.x += a[u].x; x.y += a[u].y; x.z += a[u].z; x.w += a[u].w; }
-        x.x = apply_act(x.x, k.act, k.slope); x.y = apply_act(x.y, k.act, k.slope);
-        x.z = apply_act(x.z, k.act, k.slope); x.w = apply_act(x.w, k.act, k.slope);
+        if constexpr (ADD) { x.x += a[q].x; x.y += a[q].y; x.z += a[q].z; x.w += a[q].w; }
+        if constexpr (ACT == ACT_RELU) {
+          x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+        } else if constexpr (ACT == ACT_LRELU) {
+          x.x = x.x > 0.f ? x.x : x.x * k.slope; x.y = x.y > 0.f ? x.y : x.y * k.slope;
+          x.z = x.z > 0.f ? x.z : x.z * k.slope; x.w = x.w > 0.f ? x.w : x.w * k.slope;
+        }
         if (c + 3 >= k.Cl) {                       // ragged tail (plain conversions only): the over-read lanes are pad
           if (c + 1 >= k.Cl) x.y = 0.f;
           if (c + 2 >= k.Cl) x.z = 0.f;
           x.w = 0.f;
         }
-        if (k.o32) *reinterpret_cast<float4*>(k.o32 + ooff[u]) = x;
+        if (k.o32) *reinterpret_cast<float4*>(k.o32 + b * k.ob + d * k.od + h * k.oh + w * k.ow + c) = x;
       }
-      if (k.opl) {
-        const long o = (long)pp[u] * k.prow + (c >> 5) * 64 + (c & 31);
-        uint2 hv, lv;
-        split_operand4(x.x * k.amul, x.y * k.amul, x.z * k.amul, x.w * k.amul, hv, lv);
-        *reinterpret_cast<uint2*>(k.opl + o) = hv;
-        *reinterpret_cast<uint2*>(k.opl + o + 32) = lv;
-      }
+      split_operand4(x.x * k.amul, x.y * k.amul, x.z * k.amul, x.w * k.amul, hv[q], lv[q]);
+    }
+    if (k.opl) {                                   // 16 channels: hi 32 bytes, lo 32 bytes (64 bytes further)
+      __nv_bfloat16* o = k.opl + (long)pix * k.prow + (c0 >> 5) * 64 + (c0 & 31);
+      *reinterpret_cast<uint4*>(o) = make_uint4(hv[0].x, hv[0].y, hv[1].x, hv[1].y);
+      *reinterpret_cast<uint4*>(o + 8) = make_uint4(hv[2].x, hv[2].y, hv[3].x, hv[3].y);
+      *reinterpret_cast<uint4*>(o + 32) = make_uint4(lv[0].x, lv[0].y, lv[1].x, lv[1].y);
+      *reinterpret_cast<uint4*>(o + 40) = make_uint4(lv[2].x, lv[2].y, lv[3].x, lv[3].y);
     }
   }
+}
+
+template <int NORM, bool ADD>
+static void launch_prep_fast(const PrepK& k, unsigned blocks, cudaStream_t st) {
+  if (k.act == ACT_RELU) prep_kernel_fast<NORM, ADD, ACT_RELU><<<blocks, 256, 0, st>>>(k);
+  else if (k.act == ACT_LRELU) prep_kernel_fast<NORM, ADD, ACT_LRELU><<<blocks, 256, 0, st>>>(k);
+  else prep_kernel_fast<NORM, ADD, ACT_NONE><<<blocks, 256, 0, st>>>(k);
 }
 
 static bool prep_vec_ok(const PrepK& k) {
@@ -247,19 +253,22 @@ static void launch_prep(const Launcher& L, PrepK& k) {
   const long total = (long)k.B * k.D * k.H * k.W * k.Cout;
   // algorithmic bytes: every logical element read once (fp32) and written once (fp32 or hi+lo bf16)
   ProfScope ps(L, PK_PREP, 0.0, (double)k.B * k.D * k.H * k.W * k.Cl * 4.0 * 2.0, "prep");
-  const bool fast = prep_vec_ok(k) && !k.s1 && !k.pool2 && !k.upshift && !k.gb && total / 4 < (1L << 30);
+  // (operand outputs have Cout % 32 == 0; fp32-only outputs need whole 16-channel groups to keep the stores inside the row)
+  const bool fast = prep_vec_ok(k) && !k.s1 && !k.pool2 && !k.upshift && !k.gb && total / 4 < (1L << 30) &&
+                    (k.act == ACT_NONE || k.act == ACT_RELU || k.act == ACT_LRELU) && (k.opl ? (k.Cout & 31) == 0 : (k.Cout & 15) == 0) &&
+                    (k.opl == nullptr || ((uintptr_t)k.opl & 15) == 0);
   if (fast) {
     long blocks = (total / 16 + 255) / 256;
     if (blocks > 148L * 16) blocks = 148L * 16;
     if (blocks < 1) blocks = 1;
     if (k.add) {
-      if (k.norm == NORM_STATS_BC) prep_kernel_fast<NORM_STATS_BC, true><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
-      else if (k.norm == NORM_AFFINE_C) prep_kernel_fast<NORM_AFFINE_C, true><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
-      else prep_kernel_fast<NORM_NONE, true><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+      if (k.norm == NORM_STATS_BC) launch_prep_fast<NORM_STATS_BC, true>(k, (unsigned)blocks, L.stream);
+      else if (k.norm == NORM_AFFINE_C) launch_prep_fast<NORM_AFFINE_C, true>(k, (unsigned)blocks, L.stream);
+      else launch_prep_fast<NORM_NONE, true>(k, (unsigned)blocks, L.stream);
     } else {
-      if (k.norm == NORM_STATS_BC) prep_kernel_fast<NORM_STATS_BC, false><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
-      else if (k.norm == NORM_AFFINE_C) prep_kernel_fast<NORM_AFFINE_C, false><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
-      else prep_kernel_fast<NORM_NONE, false><<<(unsigned)blocks, 256, 0, L.stream>>>(k);
+      if (k.norm == NORM_STATS_BC) launch_prep_fast<NORM_STATS_BC, false>(k, (unsigned)blocks, L.stream);
+      else if (k.norm == NORM_AFFINE_C) launch_prep_fast<NORM_AFFINE_C, false>(k, (unsigned)blocks, L.stream);
+      else launch_prep_fast<NORM_NONE, false>(k, (unsigned)blocks, L.stream);
     }
   } else if (prep_vec_ok(k)) {
     long blocks = (total / 4 + 255) / 256;

@@ -313,7 +313,8 @@ void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const 
   const int C4 = w.Cout / 4;
   const bool stats = st && st->scratch && C4 <= 256 && 256 % C4 == 0 && w.Cout <= 512;
   const long per = (long)V.H * V.W * C4;
-  long blocks = (per + 255) / 256; if (blocks > STATS_MAX_BLOCKS) blocks = STATS_MAX_BLOCKS;
+  const long cap = stats ? STATS_MAX_BLOCKS : 512;          // the statistics scratch holds STATS_MAX_BLOCKS partials per sample
+  long blocks = (per + 255) / 256; if (blocks > cap) blocks = cap;
   if (!L.dry) {
     ProfScope ps(L, PK_CONV_TC, 0.0, (double)x.pixels() * w.Cout * (4.0 + 1.0 + (residual ? 1.0 : 0.0)) * 4.0, "wino_out");
     dim3 grid((unsigned)blocks, x.B);
