@@ -70,8 +70,8 @@ __device__ __forceinline__ void bt4(const float4& a, const float4& b, const floa
 // channels).  MASK: the 3x3 neighbourhoods of the tile's four pixels are exactly the 4x4 patch held in registers, so the
 // 512 -> 1 mask conv of AdaptiveSharedWeightConv2d (adaptive_modulate.py:173-180) is computed here as well: per-thread
 // partial dot products, shuffle + shared-memory reduction over the block (fixed order: deterministic), sigmoid.
-template <bool MASK>
-__global__ void __launch_bounds__(256) wino_in_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ V, int B, int H, int W,
+template <bool MASK, int MINB>
+__global__ void __launch_bounds__(128, MINB) wino_in_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ V, int B, int H, int W,
                                                       int C, const float* __restrict__ mw /*[9][C]*/, const float* __restrict__ mb,
                                                       float* __restrict__ mask /*[B,H,W]*/, const float* __restrict__ pscale,
                                                       const float* __restrict__ pshift, int pact, float pslope, float amul) {
@@ -137,19 +137,19 @@ __global__ void __launch_bounds__(256) wino_in_kernel(const float* __restrict__ 
         mask[((long)b * H + 2 * ty + oy) * W + 2 * tx + ox] = 1.f / (1.f + expf(-(sum + mb[0])));
       }
     }
-    float4 tm[4][4];                     // B^T d : transform along rows, per column
+    // B^T d : transform along rows, per column, IN PLACE (d is dead after the mask conv): halves the live registers
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float4 o[4];
       bt4(d[0][q], d[1][q], d[2][q], d[3][q], o);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) tm[i][q] = o[i];
+      for (int i = 0; i < 4; ++i) d[i][q] = o[i];
     }
     __nv_bfloat16* base = V + (long)b * 16 * plane + ((long)ty * Wt + tx) * ((C >> 5) * 64) + (c >> 5) * 64 + (c & 31);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {        // (B^T d) B
+    for (int i = 0; i < 4; ++i) {        // (B^T d) B, row by row, stored as soon as it is formed
       float4 o[4];
-      bt4(tm[i][0], tm[i][1], tm[i][2], tm[i][3], o);
+      bt4(d[i][0], d[i][1], d[i][2], d[i][3], o);
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         uint2 hv, lv;
@@ -360,14 +360,16 @@ void wino_in(const Launcher& L, const Act& x, Opd V, const ConvW* mask_conv, flo
   const long tiles = (long)x.B * (x.H / 2) * (x.W / 2);
   long blocks = tiles; if (blocks > 148L * 16) blocks = 148L * 16;
   ProfScope ps(L, PK_CONV_TC, 0.0, (double)x.pixels() * x.C * 4.0 + (double)x.pixels() * x.C * 4.0 * 4.0, "wino_in");   // part of the conv
+  CS_REQUIRE(x.C / 4 <= 128, CS_ERR_INVALID, "wino_in: at most 512 channels");
+  // 6 resident blocks of 128 threads per SM (80 registers, a few spilled words): measured 3.95 -> 3.59 ms per step against 4 blocks
   if (mask_conv) {
     CS_REQUIRE(mask && mask_conv->w32 && mask_conv->Cin == x.C && mask_conv->Cout == 1 && mask_conv->KD == 1 && mask_conv->KH == 3 &&
                    mask_conv->KW == 3 && mask_conv->bias, CS_ERR_INVALID, "wino_in: bad mask conv");
-    wino_in_kernel<true><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, mask_conv->w32, mask_conv->bias, mask,
-                                                                     pscale, pshift, pact, pslope, V.amul);
+    wino_in_kernel<true, 6><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, mask_conv->w32, mask_conv->bias, mask,
+                                                                        pscale, pshift, pact, pslope, V.amul);
   } else {
-    wino_in_kernel<false><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, nullptr, nullptr, nullptr, pscale,
-                                                                      pshift, pact, pslope, V.amul);
+    wino_in_kernel<false, 6><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, nullptr, nullptr, nullptr, pscale,
+                                                                         pshift, pact, pslope, V.amul);
   }
   check_launch("wino_in");
 }
