@@ -253,14 +253,15 @@ class V2IPipeline:
             return self.state
         shapes = self._shapes()
         n = sum(int(torch.tensor(s).prod()) for s in shapes.values())
-        buf = torch.empty(n, dtype=torch.float32, device=self.dev)
+        dev = self.dev if dist.get_backend() == "nccl" else torch.device("cpu")     # gloo (CPU tests of the host logic): host buffer
+        buf = torch.empty(n, dtype=torch.float32, device=dev)
         if dist.get_rank() == src:
-            torch.cat([self.state[k].reshape(-1).float() for k in self.STATE_KEYS], out=buf)
+            buf.copy_(torch.cat([self.state[k].reshape(-1).float() for k in self.STATE_KEYS]))
         dist.broadcast(buf, src=src)
         st, o = {}, 0
         for k in self.STATE_KEYS:
             m = int(torch.tensor(shapes[k]).prod())
-            st[k] = buf[o:o + m].reshape(shapes[k]).clone()
+            st[k] = buf[o:o + m].reshape(shapes[k]).clone().to(self.dev if dist.get_backend() == "nccl" else dev)
             o += m
         self.state = st
         return st

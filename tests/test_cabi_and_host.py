@@ -188,3 +188,50 @@ def test_can_swapper_constructor_behaves_like_the_reference(tmp_path, monkeypatc
     cfg.flag_force_cpu = True
     with pytest.raises(CanonSwapError):
         modules.can_swapper(cfg)
+
+
+_GLOO_V2I_WORKER = r'''
+import os, sys, types, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["CS_ROOT"])
+from canonswap_b200.pipeline import V2IPipeline, FramePipeline, shard_indices
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["CS_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+sw = types.SimpleNamespace(device="cpu")
+vp = V2IPipeline.__new__(V2IPipeline)                     # host logic only: no engine, no CUDA
+vp.sw, vp.batch, vp.net_h, vp.net_w, vp.dev, vp.state = sw, 4, 128, 128, torch.device("cpu"), None
+g = torch.Generator().manual_seed(5)
+if rank == 0:
+    vp.state = {k: torch.randn(*s, generator=g) for k, s in vp._shapes().items()}
+    vp.state["swap_can"] = torch.zeros(1)                 # rank-0-only extras are not broadcast
+st = vp.broadcast(src=0)
+np.save(os.environ["CS_OUT"] + ".%d.npy" % rank, torch.cat([st[k].reshape(-1) for k in V2IPipeline.STATE_KEYS]).numpy())
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_gloo_v2i_state_broadcast(tmp_path):
+    """The v2i pipeline's one collective (the per-source state: appearance volume + keypoints / pose, packed into ONE buffer)
+    on a world of 2 over gloo: every rank ends with rank 0's state bit for bit, in the declared shapes."""
+    import socket
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_V2I_WORKER)
+    out = str(tmp_path / "state")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", CS_PORT=str(port), CS_OUT=out, CS_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        o, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, o.decode()
+    a, b = np.load(out + ".0.npy"), np.load(out + ".1.npy")
+    assert a.shape == b.shape and a.size == 32 * 16 * 32 * 32 + 63 + 63 + 9 + 3 + 1
+    assert np.array_equal(a, b)
+    g = torch.Generator().manual_seed(5)
+    from canonswap_b200.pipeline import V2IPipeline
+    vp = V2IPipeline.__new__(V2IPipeline)
+    vp.net_h = vp.net_w = 128
+    exp = torch.cat([torch.randn(*s, generator=g).reshape(-1) for s in vp._shapes().values()]).numpy()
+    assert np.array_equal(a, exp)
