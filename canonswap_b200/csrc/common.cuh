@@ -161,7 +161,7 @@ struct Epilogue {
   const float* residual = nullptr;   // same geometry/strides as the output
   long rs_b = 0, rs_d = 0, rs_h = 0, rs_w = 0;
   const float* mult = nullptr;       // [B, Do*Ho*Wo] per-pixel multiplier
-  // tcgen05 path only: additionally emit act2(v * emit_scale[c] + emit_shift[c]) as the split-bf16 operand
+  // tcgen05 path only: additionally emit act2(v * emit_scale[c] + emit_shift[c]) as the split-fp16 operand
   // [pixels, emit_nblk, 64] of the next conv (scale/shift null = identity); the fp32 output pointer may then be null
   __nv_bfloat16* emit = nullptr;
   int emit_nblk = 0;
@@ -247,7 +247,7 @@ struct Launcher {            // everything a kernel launch helper needs
   bool dry = false;          // measuring pass: skip launches
   int64_t* counter = nullptr;
   int conv_impl = 0;         // 0 auto, 1 SIMT, 2 TC
-  int npass = 3;             // split-bf16 MMA passes of the tcgen05 conv (3 = hi*hi + lo*hi + hi*lo)
+  int npass = 3;             // split-fp16 MMA passes of the tcgen05 conv (3 = hi*hi + lo*hi + hi*lo)
   int max_sets = 0;          // cap on the accumulator sets (0 = automatic)
   bool phase_conv = true;    // convs of a nearest-upsampled seg map in phase form on the low-resolution operand
   bool spade_fused = true;   // SPADE normalise + modulate + activate inside the gamma|beta conv's epilogue
@@ -291,7 +291,7 @@ inline void check_launch(const char* what) {
 // ------------------------------------------------------------------------------------------
 // kernels_elem.cu
 void prep_f32(const Launcher& L, const Prep& p, Act out);                    // out: fp32 (strides from Act)
-void prep_planes(const Launcher& L, const Prep& p, Opd out, const Act* out32);   // split-bf16 planes (+ optional fp32 copy)
+void prep_planes(const Launcher& L, const Prep& p, Opd out, const Act* out32);   // split-fp16 planes (+ optional fp32 copy)
 void avg2(const Launcher& L, const float* a, const float* b, float* y, long n);   // y = (a + b) / 2
 constexpr int STATS_MAX_BLOCKS = 128;      // per-sample partial blocks of instance_stats: scratch = [B][128][C <= 512][2] doubles
 void instance_stats(const Launcher& L, const Act& x, float* mean, float* rstd, float eps, double* scratch);
@@ -324,7 +324,7 @@ void grid_sample3d_cl(const Launcher& L, const float* vol, const float* grid, fl
 // conv_tc.cu
 // "same" convolution (stride 1, pad = k/2) of a dense channels-last tensor with the geometry of `out`
 bool conv_tc_supported(const ConvW& w, const Act& out);
-Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out);   // split-bf16 operand with the geometry of `out`
+Opd conv_tc_alloc_operand(Arena& A, const ConvW& w, const Act& out);   // split-fp16 operand with the geometry of `out`
 void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g, const Epilogue& e, Act y);
 // conv3s_tc.cu : the 32 -> 32 3x3x3 volume convs (depth-stacked, weights resident in shared memory)
 bool conv3s_supported(const ConvW& w, int H, int W);

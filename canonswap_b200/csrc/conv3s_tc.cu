@@ -362,7 +362,7 @@ void pack_conv3s(cs_ctx* ctx, ConvW& w) {
   check_launch("pack_conv3s");
 }
 
-// x: split-bf16 operand [B,16,H,W,64] of a 32-channel volume; y (fp32, may have a null pointer when only the operand is
+// x: split-fp16 operand [B,16,H,W,64] of a 32-channel volume; y (fp32, may have a null pointer when only the operand is
 // emitted) / residual: channels-last with generic strides and channel stride 1 (the [B,h,w,16,32] volume view).
 // stats_part != null: also writes conv3s_stats_floats() per-tile partial sums of the fp32 output (see conv3s_stats).
 size_t conv3s_stats_floats(int B, int H, int W) { return (size_t)B * ((H + 15) / 16) * ((W + 7) / 8) * 2 * 64; }

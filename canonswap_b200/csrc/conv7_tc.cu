@@ -317,7 +317,7 @@ void pack_conv7(cs_ctx* ctx, ConvW& w) {
   check_launch("pack_conv7");
 }
 
-// x: split-bf16 operand [B,16,H,W,nblk*64]; out: logits [B,16,H,W,ldo] (dense, ldo = out.sw >= Cout);
+// x: split-fp16 operand [B,16,H,W,nblk*64]; out: logits [B,16,H,W,ldo] (dense, ldo = out.sw >= Cout);
 // scratch: conv7_scratch_floats(out) floats
 void conv7_tc(const Launcher& L, const Opd& x, const ConvW& w, Act out, float* scratch) {
   L.count(); L.count();

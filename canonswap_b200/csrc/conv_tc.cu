@@ -7,15 +7,17 @@
 //             so the A tile of filter tap (kd,kh,kw) is the SAME box shifted by the tap: one TMA tiled
 //             load per stage, the zero padding of the convolution is TMA out-of-bounds zero fill.
 //   N tile  = BN <= 256 output channels, K = taps x Cin walked in 32-channel blocks.
-//   operand = split bf16: every fp32 value v is stored as hi = bf16(v), lo = bf16(v - hi); a 32-channel
+//   operand = split fp16: every fp32 value v is stored as hi = fp16(v), lo = fp16(v - hi); a 32-channel
 //             block is the 128-byte row [hi x32 | lo x32], which is exactly one SWIZZLE_128B row, so a
 //             stage is ONE A box (128 rows) and ONE B box (BN rows) and the MMA descriptors of the
 //             hi / lo halves are 64-byte K-advances inside the swizzle atom.
-//   math    = 3 x tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32 in TMEM) per 16-channel K step:
-//             hi*hi + hi*lo + lo*hi  (~2^-16 relative, the 1e-3 fp32 parity bar of BASELINE.json);
+//   math    = 3 x tcgen05.mma.kind::f16 (fp16 x fp16 -> fp32 in TMEM) per 16-channel K step:
+//             hi*hi + hi*lo + lo*hi  (~2^-22 relative, for the 1e-3 fp32 parity bar of BASELINE.json);
 //             `npass` 2 / 1 drop the correction terms (measurement only).
-//   roles   = warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
-//             (tcgen05.ld -> bias / activation / residual / per-pixel multiplier -> fp32 channels-last).
+//   roles   = warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5 (2-9 on wide tiles): epilogue
+//             (tcgen05.ld -> bias / activation / residual / per-pixel multiplier -> fp32 channels-last and / or the next
+//             conv's operand); persistent tile loop, double-buffered TMEM, tcgen05 pair mode: DESIGN.md section 4.2.
+//   the 16-bit storage type of the operands is spelled __nv_bfloat16 in the code (a 16-bit slot); the bits are fp16.
 #include "tc_ptx.cuh"
 #include <mutex>
 
@@ -50,7 +52,7 @@ struct ConvTcK {
   const float* mult;
   float* y; long yb, yd, yh, yw;               // may be null when only the operand is emitted
   int vec4;
-  // optional: also write act(v * escale[n] + eshift[n]) as the split-bf16 operand of the next conv (dense, output geometry)
+  // optional: also write act(v * escale[n] + eshift[n]) as the split-fp16 operand of the next conv (dense, output geometry)
   __nv_bfloat16* emit; int erow; const float* escale; const float* eshift; int eact; float eslope; float emul;
   // SPADE epilogue (see Epilogue::sp_x)
   const float* sp_x; const float* sp_mean; const float* sp_rstd; int sp_C, sp_xs, sp_Hx, sp_Wx;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
     }
   } else if (warp == 1 && (CTAS == 1 || cta_rank == 0)) {
     // ===== MMA issuer: the whole warp walks the loop converged, one elected lane issues =====
-    // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128 per CTA
+    // instruction descriptor: D fp32, A/B fp16 (IDESC_AB_FMT), both K-major, N = BN, M = 128 per CTA
     const uint32_t idesc = (1u << 4) | IDESC_AB_FMT | ((uint32_t)(k.BN >> 3) << 17) | (((128u * CTAS) >> 4) << 24);
     int s = 0; uint32_t ph = 0;
     int it = 0;
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
               for (int j = 0; j < 4; ++j) if (n + j < k.Cout) yp[j] = o[j];
             }
           }
-          if constexpr (EMIT) {                             // the next conv's split-bf16 operand, transform fused
+          if constexpr (EMIT) {                             // the next conv's split-fp16 operand, transform fused
             float e[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope) * k.emul;

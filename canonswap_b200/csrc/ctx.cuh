@@ -162,7 +162,7 @@ ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt /*[Cout][Cin][t
 float weight_prescale(const float* w, size_t n);             // weights.cu
 void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream);
 void pack_conv3s(cs_ctx* ctx, ConvW& w);                     // conv3s_tc.cu
-void pack_conv7(cs_ctx* ctx, ConvW& w);                      // conv7_tc.cu   // derive the split-bf16 B operand from w32 (conv_tc.cu)
+void pack_conv7(cs_ctx* ctx, ConvW& w);                      // conv7_tc.cu   // derive the split-fp16 B operand from w32 (conv_tc.cu)
 
 // wino.cu : Winograd F(2x2,3x3) form of the adaptive convs
 void pack_wino(cs_ctx* ctx, AdaptiveConvW& a, cudaStream_t stream);

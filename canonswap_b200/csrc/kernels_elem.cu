@@ -1,6 +1,6 @@
 // Element-wise / reduction / layout kernels of the generator hot path (HBM-bound, sm_100a).
 //   prep            gather (+nearest-up / 2x2 avg-pool / concat) -> normalise -> SPADE modulate -> (+add) -> act
-//                   -> fp32 channels-last and/or split-bf16 operand planes for the tcgen05 conv
+//                   -> fp32 channels-last and/or split-fp16 operand planes for the tcgen05 conv
 //   instance_stats  per-(b,c) mean / rstd (InstanceNorm2d, GroupNorm(32,32)), reference util.py:286,521
 //   adaptive_blend  mask*out_mod + (1-mask)*out_std, reference adaptive_modulate.py:186
 //   nchw<->cl       layout shims at the per-stage C-ABI boundary
@@ -22,7 +22,7 @@ struct PrepK {
   int Cout;                 // channels written (>= Cl, pad written as zero)
   // outputs
   float* o32; long ob, od, oh, ow;
-  __nv_bfloat16* opl; long prow;   // split-bf16 operand: dense pixels, prow = nblk*64 elements per pixel
+  __nv_bfloat16* opl; long prow;   // split-fp16 operand: dense pixels, prow = nblk*64 elements per pixel
   float amul;                      // Opd::amul
 };
 
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256) adaptive_blend_kernel(const float4* __res
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     if (residual) { float4 r = residual[i]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
     if (y) y[i] = v;
-    if (opl) {                // split-bf16 operand of the next conv: [pix][16 blocks][hi 32 | lo 32]
+    if (opl) {                // split-fp16 operand of the next conv: [pix][16 blocks][hi 32 | lo 32]
       const int c = q * 4;
       uint2 hv, lv;
       split_operand4(v.x * opl_mul, v.y * opl_mul, v.z * opl_mul, v.w * opl_mul, hv, lv);

@@ -60,7 +60,7 @@ void conv_layer(Net& n, const Prep* prep, const Act& x, const ConvW& w, const Co
     e.rs_b = o.residual->sb; e.rs_d = o.residual->sd; e.rs_h = o.residual->sh; e.rs_w = o.residual->sw;
   }
   size_t m = n.A->mark();
-  // ---- tcgen05 path: split-bf16 operand planes produced by the prep kernel ----
+  // ---- tcgen05 path: split-fp16 operand planes produced by the prep kernel ----
   if (n.L.conv_impl != 1 && !o.xshift && conv_tc_supported(w, out)) {
     Opd opd = conv_tc_alloc_operand(*n.A, w, out);
     Prep ident;
@@ -83,7 +83,7 @@ void conv_layer(Net& n, const Prep* prep, const Act& x, const ConvW& w, const Co
   n.A->reset(m);
 }
 
-// tcgen05 conv on an operand that is already in split-bf16 form (several convs can share one operand)
+// tcgen05 conv on an operand that is already in split-fp16 form (several convs can share one operand)
 static void conv_from_operand(Net& n, const Opd& opd, const ConvW& w, const ConvOpts& o, Act out) {
   ConvGeom g;
   g.PD = (out.D == opd.D) ? w.KD / 2 : 0; g.PH = w.KH / 2; g.PW = w.KW / 2;
@@ -132,7 +132,7 @@ static void resblock3d(Net& n, const ResBlock3dW& w, float* vol, int B, int h, i
 
 // A run of pre-activation residual blocks (ResBlock3d util.py:94-102 on the 3-D view, ResBlock2d util.py:120-128 on the
 // 2-D view) on the tcgen05 path: only the first block's input goes through a prep kernel; every conv epilogue emits
-// the next conv's split-bf16 operand (conv1: act(.) as is, conv2: act(bn1_next(x + conv2(.)))), so the intermediate
+// the next conv's split-fp16 operand (conv1: act(.) as is, conv2: act(bn1_next(x + conv2(.)))), so the intermediate
 // `t` never exists in fp32 and the volume is read once per block (as the residual).
 struct PreActBlock { const Affine* bn1; const ConvW* conv1; const ConvW* conv2; };
 

@@ -9,7 +9,7 @@
 //   - stacks mlp_gamma | mlp_beta of every SPADE into one Cout = 2C conv,
 //   - permutes every 512-channel axis that is a view of the 32x16 volume from the reference order
 //     (c*16 + d) to the internal channels-last order (d*32 + c),
-//   - re-lays every conv as [tap][Cin][Cout] fp32 (SIMT path) and derives the split-bf16 tcgen05
+//   - re-lays every conv as [tap][Cin][Cout] fp32 (SIMT path) and derives the split-fp16 tcgen05
 //     operand [tap][Cout_p][Cin_p] from it on the device.
 #include "tc_ptx.cuh"
 #include <cmath>

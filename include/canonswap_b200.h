@@ -71,7 +71,7 @@ typedef struct cs_tensor_desc {
 
 /* options of cs_set_option */
 #define CS_OPT_CONV_IMPL 1       /* 0 = auto (tcgen05 where eligible), 1 = force SIMT fp32 convs (debug) */
-#define CS_OPT_TC_PASSES 3       /* split-bf16 MMA passes of the tcgen05 conv: 3 (default, fp32-grade) | 2 | 1 (measurement only) */
+#define CS_OPT_TC_PASSES 3       /* split-fp16 MMA passes of the tcgen05 conv: 3 (default, fp32-grade) | 2 | 1 (measurement only) */
 #define CS_OPT_TC_SETS 4         /* cap on TMEM accumulator sets per tile (0 = automatic; 1 = single accumulator, measurement only) */
 #define CS_OPT_TC_COMP 5         /* tensor-core accumulate-truncation compensation per chained MMA, units of 1e-10 (default 170, 0 = off) */
 #define CS_OPT_TC_PAIR 6         /* tcgen05 pair mode (cta_group::2 over 2-CTA clusters) for wide N tiles: 0 = off, 1 = on (default),
@@ -206,7 +206,7 @@ CS_API int cs_profile_dump(cs_ctx* ctx, char* buf, int cap);
 /* ---- kernel-level entry points (unit tests / profiling) ------------------------------------- */
 /* Generic "same"-style convolution on channels-last fp32 through the library's conv kernels.
  * x [B,D,H,W,Cin] -> y [B,Do,Ho,Wo,Cout]; w in PyTorch layout [Cout,Cin,KD,KH,KW] (device), bias
- * [Cout] or NULL. impl: 0 auto, 1 SIMT fp32, 2 tcgen05 split-bf16, 3 tcgen05 depth-stacked 7x7x7 kernel,
+ * [Cout] or NULL. impl: 0 auto, 1 SIMT fp32, 2 tcgen05 split-fp16, 3 tcgen05 depth-stacked 7x7x7 kernel,
  * 4 tcgen05 depth-stacked 32->32 3x3x3 kernel, 5 Winograd F(2x2,3x3) form of a 3x3 2-D conv (Cin % 32 == 0, Cout % 256 == 0). act: 0 none 1 relu 2 lrelu 3 sigmoid */
 CS_API int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
                  int B, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW,
