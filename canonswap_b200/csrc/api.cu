@@ -699,7 +699,7 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
                  int Cout, int KD, int KH, int KW, int PD, int PH, int PW, int act, float slope, int impl, void* stream) {
   CS_API_BEGIN(ctx)
   CS_REQUIRE(x && w && y && B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, CS_ERR_INVALID, "cs_test_conv: bad argument");
-  CS_REQUIRE(KD > 0 && KH > 0 && KW > 0 && impl >= 0 && impl <= 5, CS_ERR_INVALID, "cs_test_conv: bad argument");
+  CS_REQUIRE(KD > 0 && KH > 0 && KW > 0 && impl >= 0 && impl <= 6, CS_ERR_INVALID, "cs_test_conv: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CS_CUDA(cudaStreamSynchronize(st));
   const size_t nw = (size_t)Cout * Cin * KD * KH * KW;
@@ -729,7 +729,23 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
     bool tc = same && conv_tc_supported(cw, ya);
     if (impl == 2) CS_REQUIRE(tc, CS_ERR_INVALID, "cs_test_conv: shape not supported by the tcgen05 conv");
     if (impl == 1) tc = false;
-    if (impl == 5) {
+    if (impl == 6) {
+      // phase form: x is the LOW-resolution input of a conv applied to nearest-upsample(x, (1,2,2)); y [B,D,2H,2W,Cout]
+      CS_REQUIRE(KH == 3 && KW == 3 && (KD == 1 || KD == 3) && PH == 1 && PW == 1 && PD == KD / 2 && Cout % 16 == 0 && Cout <= 256,
+                 CS_ERR_INVALID, "cs_test_conv: shape not supported by the phase-form conv");
+      ConvW pw = pack_phase_conv_host(ctx, hw, bias ? &hb : nullptr, Cout, Cin, KD, 1);
+      CS_CUDA(cudaDeviceSynchronize());
+      Act yup = make_act(y, B, D, 2 * H, 2 * W, Cout);
+      Arena tmp; tmp.measuring = true;
+      conv_tc_alloc_operand(tmp, pw, xa);
+      Arena real; real.cap = tmp.high + 4096; real.base = static_cast<char*>(ctx->dmalloc(real.cap));
+      Opd opd = conv_tc_alloc_operand(real, pw, xa);
+      Prep p; p.src0 = xa;
+      prep_planes(L, p, opd, nullptr);
+      ConvGeom gp; gp.PD = PD; gp.PH = 1; gp.PW = 1; gp.Do = D; gp.Ho = 2 * H; gp.Wo = 2 * W;
+      Epilogue ep; ep.act = act; ep.slope = slope; ep.phase_shift = 1;
+      conv_tc(L, opd, pw, gp, ep, yup);
+    } else if (impl == 5) {
       // Winograd F(2x2,3x3) form (wino.cu): input transform -> 16 GEMMs on the tcgen05 kernel -> output transform
       pack_wino_static(ctx, cw);
       if (cw.wn) cw.wn->amul = cw.amul;                     // the pre-scale applies to the transformed operand V

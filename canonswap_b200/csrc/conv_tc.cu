@@ -59,7 +59,7 @@ struct ConvTcK {
   // phase mode (conv of a nearest-upsampled input computed on the low-resolution operand, see Epilogue::phase_shift):
   // N tile p = output phase (a, b) = (p >> ph_s, p & (2^ph_s - 1)); only the taps in tapmask[p] are walked; the tile's
   // pixels land at (oh * 2^ph_s + a, ow * 2^ph_s + b) of the output.
-  int ph_s; unsigned short tapmask[16];
+  int ph_s; unsigned tapmask[16];                 // bit t = filter tap t (kd-major, up to 27 taps) is walked by this phase
 };
 
 
@@ -522,7 +522,7 @@ struct PackPlan {                   // issue order of the kernel that will consu
   int nsets, chunk, npass, last_ksteps;
   float kappa;                      // pre-compensation per truncation event (0 = none)
   int ph_s, rows_per_phase;         // phase mode: rows [p * rows_per_phase, ..) belong to phase p, which walks the taps in tapmask[p]
-  unsigned short tapmask[16];
+  unsigned tapmask[16];
 };
 
 __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ out, int taps,
@@ -572,7 +572,9 @@ constexpr int MAX_DYN_SMEM = 220 * 1024;
 // phase-mode tap masks: output row Y = y*f + a reads input rows floor((Y + dy) / f): a = 0 -> {y-1: dy=-1, y: dy=0,+1};
 // a = f-1 -> {y: dy=-1,0, y+1: dy=+1}; else only row y.  The packed weights hold the per-phase tap sums; taps outside the
 // mask are zero and skipped.
-void phase_tapmasks(int ps, unsigned short* out) {
+// (a kernel with KD = 3 -- the hourglass decoder convs, whose input is upsampled in (h, w) only -- walks the same in-plane
+//  taps at every depth tap: the 9-bit mask is replicated per kd)
+void phase_tapmasks(int ps, int KD, unsigned* out) {
   const int f = 1 << ps;
   for (int a = 0; a < f; ++a)
     for (int b = 0; b < f; ++b) {
@@ -580,7 +582,9 @@ void phase_tapmasks(int ps, unsigned short* out) {
       unsigned m = 0;
       for (int ty = 0; ty < 3; ++ty)
         for (int tx = 0; tx < 3; ++tx) if (((rows >> ty) & 1u) && ((cols >> tx) & 1u)) m |= 1u << (ty * 3 + tx);
-      out[a * f + b] = (unsigned short)m;
+      unsigned all = 0;
+      for (int kd = 0; kd < KD; ++kd) all |= m << (9 * kd);
+      out[a * f + b] = all;
     }
 }
 
@@ -591,7 +595,9 @@ namespace tc {
 // accumulator; otherwise one set for the correction products + hi*hi sets of <= ~256 MMAs.  If two such buffers fit into the
 // TMEM columns the accumulators are double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1.  Thin N tiles
 // (BN <= 64) run two CTAs per SM with half of the TMEM each.
-TcPlan tc_make_plan(int BN, int niter, int npass, int single_chain, int max_sets, bool double_buffer, int phase_shift) {
+// niter: K iterations a tile walks (phase form: the ACTIVE taps only); single_main: one hi*hi set whatever the chain length
+// (phase form with a non-uniform number of taps per phase)
+TcPlan tc_make_plan(int BN, int niter, int npass, int single_chain, int max_sets, bool double_buffer, int single_main) {
   TcPlan p;
   p.npass = npass;
   const int steps_main = niter * 2;
@@ -615,9 +621,9 @@ TcPlan tc_make_plan(int BN, int niter, int npass, int single_chain, int max_sets
   if (nmain > niter) nmain = niter;
   const int chunk = (niter + nmain - 1) / nmain;          // K iterations per hi*hi set
   nmain = (niter + chunk - 1) / chunk;                    // sets actually written
-  if (phase_shift) nmain = 1;
+  if (single_main) nmain = 1;
   p.nsets = corr + nmain;
-  p.chunk = phase_shift ? (1 << 30) : chunk;
+  p.chunk = single_main ? (1 << 30) : chunk;
   return p;
 }
 }  // namespace tc
@@ -688,7 +694,8 @@ void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream) {
   if (ctx->tc_bn_max > 0 && BN > ctx->tc_bn_max) BN = ctx->tc_bn_max;
   if (w.phase_shift > 0) {                                  // one N tile per output phase (pack_phase_conv): Cout = 4^ps * BN rows
     BN = w.Cout >> (2 * w.phase_shift);
-    CS_REQUIRE(BN % 16 == 0 && BN <= 256 && w.taps() == 9, CS_ERR_WEIGHTS, "pack_tc: bad phase-form conv");
+    CS_REQUIRE(BN % 16 == 0 && BN <= 256 && w.KH == 3 && w.KW == 3 && (w.KD == 1 || (w.KD == 3 && w.phase_shift == 1)), CS_ERR_WEIGHTS,
+               "pack_tc: bad phase-form conv");
   }
   const int Cout_p = round_up(w.Cout, BN);
   const size_t n = (size_t)Cout_p * w.taps() * nblk * 64;
@@ -696,14 +703,17 @@ void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream) {
   w.nblk = nblk; w.BN = BN; w.Cout_p = Cout_p;
   // the accumulator plan is fixed here: the packed rows carry the truncation pre-compensation of this issue order
   const int npass = ctx->tc_passes >= 1 && ctx->tc_passes <= 3 ? ctx->tc_passes : 3;
-  const TcPlan plan = tc_make_plan(BN, w.taps() * nblk, npass, ctx->tc_single_chain, ctx->tc_sets, ctx->tc_dbuf != 0, w.phase_shift);
+  // phase form, x2: every phase walks 2 x 2 of the 3 x 3 in-plane taps (uniform: ordinary accumulator sets over the active
+  // iterations); x4: 4, 6 or 9 taps depending on the phase -> one hi*hi set
+  const int niter_plan = w.phase_shift == 1 ? w.KD * 4 * nblk : w.taps() * nblk;
+  const TcPlan plan = tc_make_plan(BN, niter_plan, npass, ctx->tc_single_chain, ctx->tc_sets, ctx->tc_dbuf != 0, w.phase_shift >= 2 ? 1 : 0);
   w.plan_nsets = plan.nsets; w.plan_chunk = plan.chunk; w.plan_nacc = plan.nacc; w.plan_npass = npass; w.plan_thin = plan.thin;
   w.plan_kappa = (float)ctx->tc_poscomp * 1e-10f;
   PackPlan pp{};
   pp.nsets = plan.nsets; pp.chunk = plan.chunk; pp.npass = npass; pp.kappa = w.plan_kappa;
   pp.last_ksteps = ((w.Cin - (nblk - 1) * 32) + 15) / 16;
   pp.ph_s = w.phase_shift; pp.rows_per_phase = BN;
-  if (w.phase_shift) phase_tapmasks(w.phase_shift, pp.tapmask);
+  if (w.phase_shift) phase_tapmasks(w.phase_shift, w.KD, pp.tapmask);
   long total = (long)Cout_p * w.taps() * nblk * 32;
   long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
   pack_tc_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w.w32, w.wtc, w.taps(), w.Cin, w.Cout, Cout_p, nblk, w.wmul, pp);
@@ -721,8 +731,8 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   CS_REQUIRE((same_d || full_d) && g.Ho == (x.H << ps) && g.Wo == (x.W << ps) && g.PH == w.KH / 2 && g.PW == w.KW / 2,
              CS_ERR_INVALID, "conv_tc: unsupported geometry");
   if (ps) {
-    CS_REQUIRE(ps <= 2 && w.KD == 1 && w.KH == 3 && w.KW == 3 && w.Cout == (w.BN << (2 * ps)) && y.C == w.BN && w.zrows == 0 &&
-                   !e.residual && !e.mult && !e.sp_x, CS_ERR_INVALID, "conv_tc: bad phase-mode conv");
+    CS_REQUIRE(ps <= 2 && (w.KD == 1 || (w.KD == 3 && ps == 1)) && w.KH == 3 && w.KW == 3 && w.Cout == (w.BN << (2 * ps)) && y.C == w.BN &&
+                   w.zrows == 0 && !e.residual && !e.mult && !e.sp_x, CS_ERR_INVALID, "conv_tc: bad phase-mode conv");
   } else {
     CS_REQUIRE(y.C == w.Cout || (e.sp_x && !e.emit && y.C == e.sp_C), CS_ERR_INVALID, "conv_tc: channel mismatch");
   }
@@ -746,7 +756,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   k.rowA = w.nblk * 64;
   k.BN = w.BN; k.Cout = w.Cout; k.zrows = w.zrows;
   k.ph_s = ps;
-  if (ps) phase_tapmasks(ps, k.tapmask);
+  if (ps) phase_tapmasks(ps, w.KD, k.tapmask);
   k.npass = w.plan_nsets > 0 ? w.plan_npass : (L.npass >= 1 && L.npass <= 3 ? L.npass : 3);
   k.bias = w.bias; k.act = e.act; k.slope = e.slope;
   k.res = e.residual; k.rb = e.rs_b; k.rd = e.rs_d; k.rh = e.rs_h; k.rw = e.rs_w;
@@ -784,7 +794,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   {
     TcPlan plan;
     if (w.plan_nsets > 0) { plan.nsets = w.plan_nsets; plan.chunk = w.plan_chunk; plan.nacc = w.plan_nacc; plan.npass = w.plan_npass; plan.thin = w.plan_thin; }
-    else plan = tc_make_plan(k.BN, niter, k.npass, L.single_chain, L.max_sets, L.double_buffer, ps);
+    else plan = tc_make_plan(k.BN, niter, k.npass, L.single_chain, L.max_sets, L.double_buffer, ps ? 1 : 0);
     CS_REQUIRE(!ps || w.phase_shift == ps, CS_ERR_INVALID, "conv_tc: phase-mode launch of a conv not packed in phase form");
     k.nsets = plan.nsets; k.chunk = plan.chunk; k.nacc = plan.nacc;
     const int corr = (k.npass > 1 && k.nsets > 1) ? 1 : 0;

@@ -85,6 +85,7 @@ struct Weights {
   // W
   ConvW dm_compress;
   ConvW hg_enc[5], hg_dec[5], hg_final, dm_mask, dm_occlusion;
+  ConvW hg_dec_ph[5];        // decoder convs in phase form on the low-resolution operand (Cout <= 256 only)
   ConvW dm_occ_y;            // occlusion conv as per-tap projections (1x1x1, depth-dependent weights; tcgen05 only)
   ConvW w_third, w_fourth;
   // swap
@@ -159,6 +160,7 @@ int calibrate_end(cs_ctx* ctx, float* maxima, int cap);
 void reset_activation_scales(cs_ctx* ctx);
 ConvW pack_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt /*[Cout][Cin][taps]*/, const std::vector<float>* bias,
                      int Cout, int Cin, int KD, int KH, int KW, int phase_shift = 0);
+ConvW pack_phase_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt, const std::vector<float>* bias, int Cout, int Cin, int KD, int shift);
 float weight_prescale(const float* w, size_t n);             // weights.cu
 void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream);
 void pack_conv3s(cs_ctx* ctx, ConvW& w);                     // conv3s_tc.cu

@@ -330,16 +330,25 @@ static void dense_motion(Net& n, const float* vol_in, const float* kp_driving, c
   Act cats[5] = {cat1, cat2, cat3, cat4, cat5};
   Act dcur = p4;
   for (int i = 0; i < 5; ++i) {
-    if (i == 4 && opd_path) {                              // the last decoder conv: operand block 0 of cat5 only
+    const bool phase = n.L.conv_impl != 1 && n.L.phase_conv && W.hg_dec_ph[i].wtc != nullptr;
+    if (phase || (i == 4 && opd_path)) {
+      // phase form: the conv of the (1,2,2)-upsampled tensor runs on the low-resolution operand, one N tile per output phase;
+      // the last decoder conv writes operand block 0 of cat5 only (no fp32 output)
       size_t m = n.A->mark();
-      Act geom = make_act(nullptr, B, D, h, w, W.hg_dec[4].Cout);
-      Opd up_op = conv_tc_alloc_operand(*n.A, W.hg_dec[4], geom);
-      Prep up = prep_of(dcur); up.upshift = 1;
-      prep_planes(n.L, up, up_op, nullptr);
-      ConvOpts o = relu; o.emit = &cat5_op;
-      conv_from_operand(n, up_op, W.hg_dec[4], o, geom);
+      const ConvW& wc = phase ? W.hg_dec_ph[i] : W.hg_dec[i];
+      const bool last = i == 4 && opd_path;
+      Act dst = last ? make_act(nullptr, B, D, h, w, W.hg_dec[4].Cout) : slice_c(cats[i], 0, W.hg_dec[i].Cout);
+      Act ingeom = phase ? make_act(nullptr, dcur.B, dcur.D, dcur.H, dcur.W, wc.Cin) : make_act(nullptr, B, D, dst.H, dst.W, wc.Cin);
+      Opd in_op = conv_tc_alloc_operand(*n.A, wc, ingeom);
+      Prep up = prep_of(dcur); up.upshift = phase ? 0 : 1;
+      prep_planes(n.L, up, in_op, nullptr);
+      ConvOpts o = relu;
+      if (phase) o.phase_shift = 1;
+      if (last) o.emit = &cat5_op;
+      conv_from_operand(n, in_op, wc, o, dst);
       n.A->reset(m);
-      break;
+      dcur = cats[i];
+      continue;
     }
     Act dst = slice_c(cats[i], 0, W.hg_dec[i].Cout);
     if (n.L.conv_impl == 1 || !conv_tc_supported(W.hg_dec[i], dst)) {

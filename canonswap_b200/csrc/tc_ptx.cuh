@@ -228,7 +228,7 @@ __host__ __device__ inline int tc_remaining_events(int nsets, int chunk, int npa
   if (end > niter) end = niter;
   return tc_events_upto(end, nblk, last_ksteps) - tc_events_upto(it, nblk, last_ksteps) - ks;
 }
-TcPlan tc_make_plan(int BN, int niter, int npass, int single_chain, int max_sets, bool double_buffer, int phase_shift);   // conv_tc.cu
+TcPlan tc_make_plan(int BN, int niter, int npass, int single_chain, int max_sets, bool double_buffer, int single_main);   // conv_tc.cu
 
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn();             // conv_tc.cu
 int pick_box(int dim, int cap, int* log2out);               // conv_tc.cu

@@ -191,20 +191,23 @@ HostConv read_sn_conv(const Table& t, const std::string& p, int Cout, int Cin, i
 // 3x3 conv applied to an input nearest-upsampled by f = 2^shift, rewritten on the low-resolution input: output phase
 // (a, b) sees the source rows {y-1, y} (a = 0), {y} (0 < a < f-1) or {y, y+1} (a = f-1), so the taps that hit the same
 // source pixel are summed.  Result: a 3x3 conv with f*f*Cout output rows (phase-major), zero where a phase has no tap.
+// (KD = 3: the hourglass decoder convs, whose input is upsampled in (h, w) only -- the same in-plane sums at every depth tap)
 HostConv phase_conv(const HostConv& c, int shift) {
   const int f = 1 << shift;
+  const int KD = c.KD, T = KD * 9;
   HostConv r;
-  r.Cout = c.Cout * f * f; r.Cin = c.Cin; r.KD = 1; r.KH = 3; r.KW = 3;
-  r.w.assign((size_t)r.Cout * c.Cin * 9, 0.f);
+  r.Cout = c.Cout * f * f; r.Cin = c.Cin; r.KD = KD; r.KH = 3; r.KW = 3;
+  r.w.assign((size_t)r.Cout * c.Cin * T, 0.f);
   auto src_tap = [&](int a, int d) { return a == 0 ? (d == 0 ? 0 : 1) : (a == f - 1 ? (d == 2 ? 2 : 1) : 1); };
   for (int a = 0; a < f; ++a)
     for (int b = 0; b < f; ++b)
       for (int co = 0; co < c.Cout; ++co)
         for (int ci = 0; ci < c.Cin; ++ci) {
-          const float* w = c.w.data() + ((long)co * c.Cin + ci) * 9;
-          float* o = r.w.data() + (((long)(a * f + b) * c.Cout + co) * c.Cin + ci) * 9;
-          for (int dy = 0; dy < 3; ++dy)
-            for (int dx = 0; dx < 3; ++dx) o[src_tap(a, dy) * 3 + src_tap(b, dx)] += w[dy * 3 + dx];
+          const float* w = c.w.data() + ((long)co * c.Cin + ci) * T;
+          float* o = r.w.data() + (((long)(a * f + b) * c.Cout + co) * c.Cin + ci) * T;
+          for (int kd = 0; kd < KD; ++kd)
+            for (int dy = 0; dy < 3; ++dy)
+              for (int dx = 0; dx < 3; ++dx) o[kd * 9 + src_tap(a, dy) * 3 + src_tap(b, dx)] += w[kd * 9 + dy * 3 + dx];
         }
   if (!c.b.empty()) {
     r.b.resize(r.Cout);
@@ -256,6 +259,15 @@ float weight_prescale(const float* w, size_t n) {
   return std::ldexp(1.f, k);
 }
 
+// test entry: a 3x3 / 3x3x3 conv in phase form (input nearest-upsampled by 2^shift in (h, w))
+ConvW pack_phase_conv_host(cs_ctx* ctx, const std::vector<float>& w_pt, const std::vector<float>* bias, int Cout, int Cin, int KD, int shift) {
+  HostConv c;
+  c.Cout = Cout; c.Cin = Cin; c.KD = KD; c.KH = 3; c.KW = 3;
+  c.w = w_pt;
+  if (bias) c.b = *bias;
+  return pack(ctx, phase_conv(c, shift), shift);
+}
+
 // ------------------------------------------------------------------------------------------
 // [Cout][Cin][taps] (PyTorch) -> device [taps][Cin][Cout] (+ bias) (+ tcgen05 operand)
 // ------------------------------------------------------------------------------------------
@@ -287,6 +299,7 @@ static void for_each_conv(Weights& W, F f) {
   one(W.dm_compress);
   for (auto& c : W.hg_enc) one(c);
   for (auto& c : W.hg_dec) one(c);
+  for (auto& c : W.hg_dec_ph) one(c);
   one(W.hg_final); one(W.dm_mask); one(W.dm_occlusion); one(W.dm_occ_y); one(W.w_third); one(W.w_fourth);
   for (auto& a : W.ad) { one(a.mask_conv); one(a.combined); one(a.wino); }
   for (auto& r : W.t_res) { one(r.conv1); one(r.conv2); }
@@ -398,6 +411,9 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
       HostConv c = read_conv(t, q + ".conv", dec[i][1], dec[i][0], 3, 3, 3);
       fold_bn_post(c, read_bn(t, q + ".norm", dec[i][1]));
       W.hg_dec[i] = pack(ctx, c);
+      // the conv reads its input nearest-upsampled (1,2,2) (util.py:142-143): phase form on the LOW-resolution operand --
+      // 2 x 2 instead of 3 x 3 in-plane taps (2.25x fewer MMAs) and no upsampled operand (one N tile per phase: Cout <= 256)
+      if (dec[i][1] <= 256) W.hg_dec_ph[i] = pack(ctx, phase_conv(c, 1), 1);
     }
     HostConv fin = read_conv(t, p + ".hourglass.decoder.conv", HG_OUT, HG_OUT, 3, 3, 3);
     fold_bn_post(fin, read_bn(t, p + ".hourglass.decoder.norm", HG_OUT));

@@ -394,6 +394,19 @@ class Engine:
                                            impl, self._stream()))
         return y
 
+    def test_conv_up2(self, x_cl, w, bias, act=0, slope=0.0):
+        """The conv of nearest-upsample(x, (1,2,2)) in phase form on x itself: x_cl [B,D,H,W,Cin], w [Cout,Cin,KD,3,3] ->
+        y [B,D,2H,2W,Cout]."""
+        B, D, H, W, Cin = x_cl.shape
+        Cout, _, KD, KH, KW = w.shape
+        y = self._new(B, D, 2 * H, 2 * W, Cout)
+        x_cl, w = x_cl.contiguous(), w.contiguous()
+        b = bias.contiguous() if bias is not None else None
+        self._check(self._lib.cs_test_conv(self._ctx, x_cl.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None,
+                                           y.data_ptr(), B, D, H, W, Cin, Cout, KD, KH, KW, KD // 2, 1, 1, act, float(slope), 6,
+                                           self._stream()))
+        return y
+
     def test_grid_sample3d(self, inp, grid):
         B, Cc, D, H, W = inp.shape
         out = torch.empty_like(inp)

@@ -207,7 +207,9 @@ CS_API int cs_profile_dump(cs_ctx* ctx, char* buf, int cap);
 /* Generic "same"-style convolution on channels-last fp32 through the library's conv kernels.
  * x [B,D,H,W,Cin] -> y [B,Do,Ho,Wo,Cout]; w in PyTorch layout [Cout,Cin,KD,KH,KW] (device), bias
  * [Cout] or NULL. impl: 0 auto, 1 SIMT fp32, 2 tcgen05 split-fp16, 3 tcgen05 depth-stacked 7x7x7 kernel,
- * 4 tcgen05 depth-stacked 32->32 3x3x3 kernel, 5 Winograd F(2x2,3x3) form of a 3x3 2-D conv (Cin % 32 == 0, Cout % 256 == 0). act: 0 none 1 relu 2 lrelu 3 sigmoid */
+ * 4 tcgen05 depth-stacked 32->32 3x3x3 kernel, 5 Winograd F(2x2,3x3) form of a 3x3 2-D conv (Cin % 32 == 0, Cout % 256 == 0),
+ * 6 phase form: the 3x3 / 3x3x3 conv of nearest-upsample(x, (1,2,2)) computed on x itself, y [B,D,2H,2W,Cout] (Cout % 16 == 0, <= 256).
+ * act: 0 none 1 relu 2 lrelu 3 sigmoid */
 CS_API int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
                  int B, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW,
                  int PD, int PH, int PW, int act, float slope, int impl, void* stream);

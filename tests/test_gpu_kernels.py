@@ -240,3 +240,24 @@ def test_activation_prescale_restores_precision_of_small_activations():
             assert rms[(10, impl)] < 1.5e-6                   # ... and the pre-scale restores it
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("case", [(1, 16, 8, 8, 128, 32, 3), (2, 16, 4, 4, 256, 64, 3), (1, 16, 2, 2, 512, 128, 3), (2, 1, 16, 16, 256, 128, 1),
+                                  (1, 16, 6, 10, 96, 48, 3)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_conv_phase_form_matches_upsample_then_conv(eng, case, act):
+    """The hourglass decoder convs read their input nearest-upsampled (1,2,2) (reference util.py:142-143).  Phase form: the conv
+    runs on the LOW-resolution operand, one N tile per output phase (a, b) with the taps that fall on the same source pixel
+    pre-summed -- 2 x 2 instead of 3 x 3 in-plane taps, no upsampled operand.  Against fp64 torch interpolate + conv3d."""
+    B, D, H, W, Cin, Cout, KD = case
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.randn(B, D, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, KD, 3, 3, device="cuda", generator=g) / (Cin * KD * 9) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    y = eng.test_conv_up2(x, w, b, act=act)
+    xu = F.interpolate(x.permute(0, 4, 1, 2, 3).double(), scale_factor=(1, 2, 2), mode="nearest")
+    ref = F.conv3d(xu, w.double(), b.double(), padding=(KD // 2, 1, 1)).permute(0, 2, 3, 4, 1).float()
+    if act == 1:
+        ref = F.relu(ref)
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
