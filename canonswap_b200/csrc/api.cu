@@ -731,7 +731,7 @@ int cs_test_conv(cs_ctx* ctx, const float* x, const float* w, const float* bias,
     if (impl == 1) tc = false;
     if (impl == 6) {
       // phase form: x is the LOW-resolution input of a conv applied to nearest-upsample(x, (1,2,2)); y [B,D,2H,2W,Cout]
-      CS_REQUIRE(KH == 3 && KW == 3 && (KD == 1 || KD == 3) && PH == 1 && PW == 1 && PD == KD / 2 && Cout % 16 == 0 && Cout <= 256,
+      CS_REQUIRE(KH == 3 && KW == 3 && (KD == 1 || KD == 3) && PH == 1 && PW == 1 && PD == KD / 2 && Cout % 16 == 0 && (Cout <= 256 || Cout % 256 == 0),
                  CS_ERR_INVALID, "cs_test_conv: shape not supported by the phase-form conv");
       ConvW pw = pack_phase_conv_host(ctx, hw, bias ? &hb : nullptr, Cout, Cin, KD, 1);
       CS_CUDA(cudaDeviceSynchronize());

@@ -60,6 +60,7 @@ struct ConvTcK {
   // N tile p = output phase (a, b) = (p >> ph_s, p & (2^ph_s - 1)); only the taps in tapmask[p] are walked; the tile's
   // pixels land at (oh * 2^ph_s + a, ow * 2^ph_s + b) of the output.
   int ph_s; unsigned tapmask[16];                 // bit t = filter tap t (kd-major, up to 27 taps) is walked by this phase
+  int ph_tpp;                                     // N tiles per phase (a phase produces ph_tpp * BN output channels)
 };
 
 
@@ -74,10 +75,11 @@ __device__ __forceinline__ TileOrg tile_origin(const ConvTcK& k, int m_tile, int
   o.w0 = tw << k.lbw; o.h0 = th << k.lbh; o.d0 = td << k.lbd; o.b0 = tb << k.lbb;
   o.n0 = n_idx * k.BN;
   o.nrow0 = o.n0 + o.d0 * k.zrows;               // first B row of this tile
-  o.tmask = k.ph_s ? k.tapmask[n_idx] : 0xFFFFFFFFu;
-  o.ph_a = k.ph_s ? (n_idx >> k.ph_s) : 0;
-  o.ph_b = k.ph_s ? (n_idx & ((1 << k.ph_s) - 1)) : 0;
-  o.chan0 = k.ph_s ? o.n0 : 0;                   // phase tiles all produce output channels 0 .. BN-1
+  const int phase = k.ph_s ? n_idx / k.ph_tpp : 0;
+  o.tmask = k.ph_s ? k.tapmask[phase] : 0xFFFFFFFFu;
+  o.ph_a = k.ph_s ? (phase >> k.ph_s) : 0;
+  o.ph_b = k.ph_s ? (phase & ((1 << k.ph_s) - 1)) : 0;
+  o.chan0 = k.ph_s ? phase * k.ph_tpp * k.BN : 0;  // every phase produces output channels 0 .. ph_tpp * BN - 1
   return o;
 }
 
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
     int s = 0; uint32_t ph = 0;
     int it = 0;
     for (int u = unit0; u < units; u += unit_step, ++it) {
-      const uint32_t tmask = k.ph_s ? k.tapmask[u / k.m_units] : 0xFFFFFFFFu;
+      const uint32_t tmask = k.ph_s ? k.tapmask[(u / k.m_units) / k.ph_tpp] : 0xFFFFFFFFu;
       const int buf = k.nacc == 2 ? (it & 1) : 0, use = k.nacc == 2 ? (it >> 1) : it;
       if (use > 0) {                                       // the epilogue warps (of both CTAs) have drained this buffer
         mbar_wait(tmem_empty + 8u * buf, (uint32_t)((use - 1) & 1));
@@ -692,9 +694,12 @@ void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream) {
     while (BN > ctx->tc_bn_min && (steps_main + (512 / BN - 1) - 1) / (512 / BN - 1) > chain_max) BN = round_up(BN / 2, 16);
   }
   if (ctx->tc_bn_max > 0 && BN > ctx->tc_bn_max) BN = ctx->tc_bn_max;
-  if (w.phase_shift > 0) {                                  // one N tile per output phase (pack_phase_conv): Cout = 4^ps * BN rows
-    BN = w.Cout >> (2 * w.phase_shift);
-    CS_REQUIRE(BN % 16 == 0 && BN <= 256 && w.KH == 3 && w.KW == 3 && (w.KD == 1 || (w.KD == 3 && w.phase_shift == 1)), CS_ERR_WEIGHTS,
+  int rows_per_phase = 0;
+  if (w.phase_shift > 0) {                                  // N tiles never straddle output phases: Cout = 4^ps * (tiles per phase) * BN rows
+    rows_per_phase = w.Cout >> (2 * w.phase_shift);
+    BN = rows_per_phase;
+    while (BN > 256) BN /= 2;
+    CS_REQUIRE(BN % 16 == 0 && rows_per_phase % BN == 0 && w.KH == 3 && w.KW == 3 && (w.KD == 1 || (w.KD == 3 && w.phase_shift == 1)), CS_ERR_WEIGHTS,
                "pack_tc: bad phase-form conv");
   }
   const int Cout_p = round_up(w.Cout, BN);
@@ -712,7 +717,7 @@ void pack_tc(cs_ctx* ctx, ConvW& w, cudaStream_t stream) {
   PackPlan pp{};
   pp.nsets = plan.nsets; pp.chunk = plan.chunk; pp.npass = npass; pp.kappa = w.plan_kappa;
   pp.last_ksteps = ((w.Cin - (nblk - 1) * 32) + 15) / 16;
-  pp.ph_s = w.phase_shift; pp.rows_per_phase = BN;
+  pp.ph_s = w.phase_shift; pp.rows_per_phase = rows_per_phase;
   if (w.phase_shift) phase_tapmasks(w.phase_shift, w.KD, pp.tapmask);
   long total = (long)Cout_p * w.taps() * nblk * 32;
   long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
@@ -731,7 +736,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   CS_REQUIRE((same_d || full_d) && g.Ho == (x.H << ps) && g.Wo == (x.W << ps) && g.PH == w.KH / 2 && g.PW == w.KW / 2,
              CS_ERR_INVALID, "conv_tc: unsupported geometry");
   if (ps) {
-    CS_REQUIRE(ps <= 2 && (w.KD == 1 || (w.KD == 3 && ps == 1)) && w.KH == 3 && w.KW == 3 && w.Cout == (w.BN << (2 * ps)) && y.C == w.BN &&
+    CS_REQUIRE(ps <= 2 && (w.KD == 1 || (w.KD == 3 && ps == 1)) && w.KH == 3 && w.KW == 3 && y.C == (w.Cout >> (2 * ps)) && y.C % w.BN == 0 &&
                    w.zrows == 0 && !e.residual && !e.mult && !e.sp_x, CS_ERR_INVALID, "conv_tc: bad phase-mode conv");
   } else {
     CS_REQUIRE(y.C == w.Cout || (e.sp_x && !e.emit && y.C == e.sp_C), CS_ERR_INVALID, "conv_tc: channel mismatch");
@@ -756,6 +761,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   k.rowA = w.nblk * 64;
   k.BN = w.BN; k.Cout = w.Cout; k.zrows = w.zrows;
   k.ph_s = ps;
+  k.ph_tpp = ps ? y.C / w.BN : 1;
   if (ps) phase_tapmasks(ps, w.KD, k.tapmask);
   k.npass = w.plan_nsets > 0 ? w.plan_npass : (L.npass >= 1 && L.npass <= 3 ? L.npass : 3);
   k.bias = w.bias; k.act = e.act; k.slope = e.slope;

@@ -85,7 +85,7 @@ struct Weights {
   // W
   ConvW dm_compress;
   ConvW hg_enc[5], hg_dec[5], hg_final, dm_mask, dm_occlusion;
-  ConvW hg_dec_ph[5];        // decoder convs in phase form on the low-resolution operand (Cout <= 256 only)
+  ConvW hg_dec_ph[5];        // decoder convs in phase form on the low-resolution operand
   ConvW dm_occ_y;            // occlusion conv as per-tap projections (1x1x1, depth-dependent weights; tcgen05 only)
   ConvW w_third, w_fourth;
   // swap

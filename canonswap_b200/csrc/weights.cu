@@ -412,8 +412,8 @@ void load_weights(cs_ctx* ctx, const cs_tensor_desc* table, int n) {
       fold_bn_post(c, read_bn(t, q + ".norm", dec[i][1]));
       W.hg_dec[i] = pack(ctx, c);
       // the conv reads its input nearest-upsampled (1,2,2) (util.py:142-143): phase form on the LOW-resolution operand --
-      // 2 x 2 instead of 3 x 3 in-plane taps (2.25x fewer MMAs) and no upsampled operand (one N tile per phase: Cout <= 256)
-      if (dec[i][1] <= 256) W.hg_dec_ph[i] = pack(ctx, phase_conv(c, 1), 1);
+      // 2 x 2 instead of 3 x 3 in-plane taps (2.25x fewer MMAs) and no upsampled operand
+      W.hg_dec_ph[i] = pack(ctx, phase_conv(c, 1), 1);
     }
     HostConv fin = read_conv(t, p + ".hourglass.decoder.conv", HG_OUT, HG_OUT, 3, 3, 3);
     fold_bn_post(fin, read_bn(t, p + ".hourglass.decoder.norm", HG_OUT));

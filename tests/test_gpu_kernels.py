@@ -243,7 +243,7 @@ def test_activation_prescale_restores_precision_of_small_activations():
 
 
 @pytest.mark.parametrize("case", [(1, 16, 8, 8, 128, 32, 3), (2, 16, 4, 4, 256, 64, 3), (1, 16, 2, 2, 512, 128, 3), (2, 1, 16, 16, 256, 128, 1),
-                                  (1, 16, 6, 10, 96, 48, 3)])
+                                  (1, 16, 6, 10, 96, 48, 3), (1, 16, 4, 4, 128, 512, 3)])
 @pytest.mark.parametrize("act", [0, 1])
 def test_conv_phase_form_matches_upsample_then_conv(eng, case, act):
     """The hourglass decoder convs read their input nearest-upsampled (1,2,2) (reference util.py:142-143).  Phase form: the conv
