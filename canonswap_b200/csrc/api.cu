@@ -49,6 +49,7 @@ Net make_net(cs_ctx* ctx, void* stream, bool dry) {
   n.L.stacked3 = ctx->tc_stacked3 != 0;
   n.L.double_buffer = ctx->tc_dbuf != 0;
   n.L.winograd = ctx->winograd != 0;
+  n.L.winograd_static = ctx->winograd == 1;
   n.L.single_chain = ctx->tc_single_chain;
   n.L.prof = dry ? nullptr : &ctx->prof;
   n.L.calib = (!dry && ctx->calib_on) ? ctx->calib_tab : nullptr;
@@ -331,7 +332,8 @@ int cs_set_option(cs_ctx* ctx, int option, int value) {
       if (value < -14 || value > 14) return fail(ctx, CS_ERR_INVALID, "CS_OPT_TEST_AMUL: log2 of the scale, in [-14, 14]");
       ctx->test_amul_log2 = value; return CS_OK;
     case CS_OPT_WINOGRAD:
-      ctx->winograd = value ? 1 : 0; return CS_OK;
+      if (value < 0 || value > 2) return fail(ctx, CS_ERR_INVALID, "CS_OPT_WINOGRAD: 0 off, 1 on (default), 2 adaptive convs only");
+      ctx->winograd = value; return CS_OK;
     case CS_OPT_TC_DOUBLE_BUFFER:
       ctx->tc_dbuf = value ? 1 : 0; return CS_OK;
     case CS_OPT_TC_STACKED3:

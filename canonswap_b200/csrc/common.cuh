@@ -256,6 +256,7 @@ struct Launcher {            // everything a kernel launch helper needs
   int pair_min_iter = 16;    // ... with at least this many K iterations
   int single_chain = 256;    // convs whose whole MMA chain (hi*hi + corrections) is at most this long use ONE accumulator
   bool winograd = true;      // adaptive convs in Winograd F(2x2,3x3) form (wino.cu)
+  bool winograd_static = true;   // ... and the static 3x3 convs with Cout % 256 == 0 (CS_OPT_WINOGRAD = 2: adaptive convs only)
   bool double_buffer = true; // two TMEM accumulator buffers where they fit (epilogue overlaps the next tile's MMAs)
   float acc_comp = 170.f;     // accumulate-truncation compensation per chained MMA, in units of 1e-10 (0 = off): constant epilogue factor,
                               // used by the kernels whose weights are not position-compensated at pack time (ConvW::plan_kappa == 0)

@@ -330,7 +330,7 @@ void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const 
 }
 
 bool wino_ok(const Launcher& L, const ConvW& w, int H, int W) {
-  return L.winograd && L.conv_impl != 1 && w.wn != nullptr && H % 2 == 0 && W % 2 == 0 && (long)(H / 2) * (W / 2) >= 128;
+  return L.winograd && L.winograd_static && L.conv_impl != 1 && w.wn != nullptr && H % 2 == 0 && W % 2 == 0 && (long)(H / 2) * (W / 2) >= 128;
 }
 
 // per identity: U = G g G^T of combined.w32 -> a.wino (a 1x1x1 conv with depth-dependent weights, zrows = 1024)

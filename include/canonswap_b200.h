@@ -82,7 +82,7 @@ typedef struct cs_tensor_desc {
 #define CS_OPT_TC_SINGLE_CHAIN 11 /* convs whose whole MMA chain is at most this long accumulate in ONE TMEM set (0 = never) */
 #define CS_OPT_TC_CHAIN_MAX 12   /* longest hi*hi MMA chain per TMEM accumulator set for convs packed AFTER the call: the N tile is halved
                                     until it holds (0 = default 256) */
-#define CS_OPT_WINOGRAD 13       /* 1 (default) = the wide 3x3 2-D convs (adaptive convs of the swap module, SPADE conv_0 / conv_1, refine ResBlock2d) in
+#define CS_OPT_WINOGRAD 13       /* (2 = only the adaptive convs in Winograd form: measured 152.7 against 155.7 frames/s with everything) 1 (default) = the wide 3x3 2-D convs (adaptive convs of the swap module, SPADE conv_0 / conv_1, refine ResBlock2d) in
                                     Winograd F(2x2,3x3) form, 0 = direct implicit GEMM */
 #define CS_OPT_TC_POSCOMP 14     /* position-dependent pre-compensation of the tensor core's accumulate truncation, folded into the packed
                                     weights: units of 1e-10 per truncation event (default 330, 0 = off: the epilogue then applies the
