@@ -125,6 +125,13 @@ __host__ __device__ inline float apply_act(float v, int kind, float slope) {
   }
 }
 
+// NONE / RELU / LRELU as one branch-free select (slope 1 / 0 / slope): the hot epilogues hoist the slope once instead of
+// running apply_act's switch (with expf / erff inlined at every call site) per element.  Same values as apply_act
+// (a negative input under RELU gives -0 instead of +0, which no consumer can tell apart).
+__host__ __device__ inline bool act_is_leaky(int kind) { return kind <= ACT_LRELU; }
+__host__ __device__ inline float leaky_slope(int kind, float slope) { return kind == ACT_NONE ? 1.f : (kind == ACT_RELU ? 0.f : slope); }
+__host__ __device__ inline float apply_leaky(float v, float s) { return v > 0.f ? v : v * s; }
+
 // packed convolution weights (device)
 struct ConvW;
 struct ConvW {

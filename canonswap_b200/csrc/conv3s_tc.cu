@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3s_tc_kernel(const __grid_cons
       eb[0] = b4.x; eb[1] = b4.y; eb[2] = b4.z; eb[3] = b4.w;
     }
     const long dstride_e = (long)k.H * k.W;
+    const float aslope = leaky_slope(k.act, k.slope), easlope = leaky_slope(k.eact, k.eslope);
     const uint32_t trow0 = tmem_base + ((uint32_t)(q * 32) << 16);
     int it = 0;
     for (int t = blockIdx.x; t < k.tiles; t += gridDim.x, ++it) {
@@ -222,14 +223,14 @@ __global__ void __launch_bounds__(C3_THREADS) conv3s_tc_kernel(const __grid_cons
         const int d = d0 + dl;
         const float ev_real = (d == 0 || d == 15) ? 108.f : 162.f;     // events of the slices that exist
         const float zsc = d == 15 ? 1.f - 54.f * k.kappa : 1.f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[16];
-          tc_ld16(trow + (uint32_t)(dl * 32 + 16 * half), v);
+        {
+          uint32_t v[32];
+          tc_ld16(trow + (uint32_t)(dl * 32), v);
+          tc_ld16(trow + (uint32_t)(dl * 32 + 16), v + 16);
           tc_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(tile + lane * STG_LD + 16 * half);
+          float4* dst = reinterpret_cast<float4*>(tile + lane * STG_LD);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < 8; ++j)
             dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                  __uint_as_float(v[4 * j + 3]));
         }
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3s_tc_kernel(const __grid_cons
           const float osc = k.out_scale * (zsc - bfr[i] * ev_real);
           float o[4] = {fmaf(a.x, osc, bz[0]), fmaf(a.y, osc, bz[1]), fmaf(a.z, osc, bz[2]), fmaf(a.w, osc, bz[3])};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], k.act, k.slope);
+          for (int j = 0; j < 4; ++j) o[j] = apply_leaky(o[j], aslope);
           if constexpr (RES) { o[0] += rr4[i].x; o[1] += rr4[i].y; o[2] += rr4[i].z; o[3] += rr4[i].w; }
           if constexpr (STATS) {
 #pragma unroll
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3s_tc_kernel(const __grid_cons
           if constexpr (EMIT) {
             float e[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope) * k.emul;
+            for (int j = 0; j < 4; ++j) e[j] = apply_leaky(fmaf(o[j], es[j], eb[j]), easlope) * k.emul;
             uint2 hv, lv;
             split_operand4(e[0], e[1], e[2], e[3], hv, lv);
             __nv_bfloat16* ep = k.emit + (epix[i] + d * dstride_e) * 64 + c4;
@@ -376,6 +377,7 @@ void conv3s_tc(const Launcher& L, const Opd& x, const ConvW& w, const Epilogue& 
   CS_REQUIRE(al4(y.sb) && al4(y.sd) && al4(y.sh) && al4(y.sw) && ((uintptr_t)y.p % 16 == 0), CS_ERR_INVALID,
              "conv3s_tc: output must be 16-byte aligned");
   CS_REQUIRE(!e.mult, CS_ERR_INVALID, "conv3s_tc: per-pixel multiplier not supported");
+  CS_REQUIRE(act_is_leaky(e.act) && act_is_leaky(e.emit_act), CS_ERR_INVALID, "conv3s_tc: activation must be none / relu / leaky relu");
   Conv3sK k{};
   k.B = x.B; k.H = x.H; k.W = x.W;
   k.ntw = (x.W + 7) / 8; k.nth = (x.H + 15) / 16;

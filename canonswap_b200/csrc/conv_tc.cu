@@ -91,6 +91,11 @@ __device__ __forceinline__ TileOrg tile_origin(const ConvTcK& k, int m_tile, int
 // shared-memory bandwidth limit that bounds the 1-CTA form at N = 256 (3 MMAs per operand load).
 // BCOMP: border take-back of the truncation pre-compensation (multi-tap convs whose weights carry it); a template parameter
 // so that the 1x1 / Winograd GEMM instantiations, whose epilogue paces the kernel, carry none of its code.
+// sigmoid / GELU out of line: one copy of the expf / erff code per kernel instead of one per unrolled call site
+__device__ __noinline__ float4 act_rare4(float4 v, int kind) {
+  return make_float4(apply_act(v.x, kind, 0.f), apply_act(v.y, kind, 0.f), apply_act(v.z, kind, 0.f), apply_act(v.w, kind, 0.f));
+}
+
 template <bool RES, bool EMIT, int CTAS, bool SPADE = false, bool BCOMP = false>
 __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, ConvTcK k) {
@@ -247,6 +252,8 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
     // row mapping of the coalesced phase: 4 rows x 8 lanes (x 8 passes); SPADE: 8 rows x 4 lanes (x 4 passes)
     constexpr int RSTEP = SPADE ? 8 : 4;
     const int sub = SPADE ? (lane >> 2) : (lane >> 3), c4 = (lane & 7) * 4;
+    const bool act_rare = !act_is_leaky(k.act);              // sigmoid / GELU: two layers of the whole path
+    const float aslope = leaky_slope(k.act, k.slope), easlope = leaky_slope(k.eact, k.eslope);
     int it = 0;
     for (int u = unit0; u < units; u += unit_step, ++it) {
     const TileOrg o = tile_origin(k, (u % k.m_units) * CTAS + (int)cta_rank, u / k.m_units);
@@ -414,8 +421,8 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
           float v1 = xv[i].y * (1.f + (g.y + bg.y)) + (bt.y + bb.y);
           float v2 = xv[i].z * (1.f + (g.z + bg.z)) + (bt.z + bb.z);
           float v3 = xv[i].w * (1.f + (g.w + bg.w)) + (bt.w + bb.w);
-          v0 = apply_act(v0, k.eact, k.eslope); v1 = apply_act(v1, k.eact, k.eslope);
-          v2 = apply_act(v2, k.eact, k.eslope); v3 = apply_act(v3, k.eact, k.eslope);
+          v0 = apply_leaky(v0, easlope); v1 = apply_leaky(v1, easlope);
+          v2 = apply_leaky(v2, easlope); v3 = apply_leaky(v3, easlope);
           if (k.emit) {
             uint2 hv, lv;
             split_operand4(v0 * k.emul, v1 * k.emul, v2 * k.emul, v3 * k.emul, hv, lv);
@@ -459,7 +466,11 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
           const float4 a = *reinterpret_cast<const float4*>(tile + (sub + 4 * i) * STG_LD + c4);
           float o[4] = {a.x + bz[0], a.y + bz[1], a.z + bz[2], a.w + bz[3]};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], k.act, k.slope);
+          for (int j = 0; j < 4; ++j) o[j] = apply_leaky(o[j], aslope);
+          if (act_rare) {                                    // warp-uniform; one out-of-line copy of the expf / erff code
+            const float4 r = act_rare4(make_float4(a.x + bz[0], a.y + bz[1], a.z + bz[2], a.w + bz[3]), k.act);
+            o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+          }
           if constexpr (RES) {
             if (full4) {
               o[0] += rr4[i].x; o[1] += rr4[i].y; o[2] += rr4[i].z; o[3] += rr4[i].w;
@@ -482,7 +493,7 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
           if constexpr (EMIT) {                             // the next conv's split-fp16 operand, transform fused
             float e[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) e[j] = apply_act(fmaf(o[j], es[j], eb[j]), k.eact, k.eslope) * k.emul;
+            for (int j = 0; j < 4; ++j) e[j] = apply_leaky(fmaf(o[j], es[j], eb[j]), easlope) * k.emul;
             uint2 hv, lv;
             split_operand4(e[0], e[1], e[2], e[3], hv, lv);
             __nv_bfloat16* ep = k.emit + epix[i] * k.erow + (nc >> 5) * 64 + (nc & 31);
@@ -781,6 +792,7 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
     k.emit = e.emit; k.erow = e.emit_nblk * 64; k.escale = e.emit_scale; k.eshift = e.emit_shift; k.eact = e.emit_act;
     k.eslope = e.emit_slope;
   }
+  CS_REQUIRE(act_is_leaky(e.emit_act), CS_ERR_INVALID, "conv_tc: the fused operand activation must be none / relu / leaky relu");
   auto al4 = [](long v) { return (v & 3) == 0; };
   k.vec4 = al4(y.sb) && al4(y.sd) && al4(y.sh) && al4(y.sw) && ((uintptr_t)y.p % 16 == 0) &&
            (!e.residual || (al4(e.rs_b) && al4(e.rs_d) && al4(e.rs_h) && al4(e.rs_w) && ((uintptr_t)e.residual % 16 == 0)));

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(128, MINB) wino_in_kernel(const float* __restr
   float4 psc = make_float4(1.f, 1.f, 1.f, 1.f), psh = make_float4(0.f, 0.f, 0.f, 0.f);
   if (pscale) { psc = __ldg(reinterpret_cast<const float4*>(pscale + c)); psh = __ldg(reinterpret_cast<const float4*>(pshift + c)); }
   const bool pre = pscale != nullptr || pact != ACT_NONE;
+  const float ps = leaky_slope(pact, pslope);
   for (long t0 = blockIdx.x; t0 < tiles; t0 += gridDim.x) {
     long t = t0;
     const int tx = (int)(t % Wt); t /= Wt;
@@ -99,8 +100,8 @@ __global__ void __launch_bounds__(128, MINB) wino_in_kernel(const float* __restr
         const bool in = ih >= 0 && ih < H && iw >= 0 && iw < W;
         d[r][q] = in ? *reinterpret_cast<const float4*>(x + (((long)b * H + ih) * W + iw) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (pre && in) {
-          d[r][q].x = apply_act(fmaf(d[r][q].x, psc.x, psh.x), pact, pslope); d[r][q].y = apply_act(fmaf(d[r][q].y, psc.y, psh.y), pact, pslope);
-          d[r][q].z = apply_act(fmaf(d[r][q].z, psc.z, psh.z), pact, pslope); d[r][q].w = apply_act(fmaf(d[r][q].w, psc.w, psh.w), pact, pslope);
+          d[r][q].x = apply_leaky(fmaf(d[r][q].x, psc.x, psh.x), ps); d[r][q].y = apply_leaky(fmaf(d[r][q].y, psc.y, psh.y), ps);
+          d[r][q].z = apply_leaky(fmaf(d[r][q].z, psc.z, psh.z), ps); d[r][q].w = apply_leaky(fmaf(d[r][q].w, psc.w, psh.w), ps);
         }
       }
     }
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float* __restrict__
   const long per = (long)Ht * Wt * C4;
   const long plane = (long)Ht * Wt * C;
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const float as = leaky_slope(act, slope);
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < per; idx += (long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C4) * 4; long t = idx / C4;
     const int tx = (int)(t % Wt); const int ty = (int)(t / Wt);
@@ -244,8 +246,8 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float* __restrict__
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const long off = (((long)b * H + 2 * ty + i) * W + 2 * tx + j) * C + c;
-        float4 v = make_float4(apply_act(yy[i][j].x + bz.x, act, slope), apply_act(yy[i][j].y + bz.y, act, slope),
-                               apply_act(yy[i][j].z + bz.z, act, slope), apply_act(yy[i][j].w + bz.w, act, slope));
+        float4 v = make_float4(apply_leaky(yy[i][j].x + bz.x, as), apply_leaky(yy[i][j].y + bz.y, as),
+                               apply_leaky(yy[i][j].z + bz.z, as), apply_leaky(yy[i][j].w + bz.w, as));
         if (residual) {
           const float4 r = *reinterpret_cast<const float4*>(residual + off);
           v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
@@ -299,6 +301,7 @@ void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const 
                float pslope, int act, float slope, const float* residual, Act y, const StatsOut* st) {
   CS_REQUIRE(w.wn != nullptr && x.C == w.Cin && y.C == w.Cout && y.H == x.H && y.W == x.W && y.B == x.B && y.sw == y.C &&
                  y.sh == (long)y.W * y.C && y.sb == (long)y.H * y.W * y.C, CS_ERR_INVALID, "wino_conv: unsupported geometry");
+  CS_REQUIRE(act_is_leaky(act) && act_is_leaky(pact), CS_ERR_INVALID, "wino_conv: activation must be none / relu / leaky relu");
   const size_t m = A.mark();
   Opd V; V.B = x.B; V.D = 16; V.H = x.H / 2; V.W = x.W / 2; V.nblk = x.C / 32;
   V.amul = w.wn->amul;
@@ -357,6 +360,7 @@ void wino_in(const Launcher& L, const Act& x, Opd V, const ConvW* mask_conv, flo
   CS_REQUIRE(x.D == 1 && x.C % 32 == 0 && x.C <= 1024 && x.H % 2 == 0 && x.W % 2 == 0 && x.sw == x.C && x.sh == (long)x.W * x.C &&
                  x.sb == (long)x.H * x.W * x.C && V.D == 16 && V.H == x.H / 2 && V.W == x.W / 2 && V.nblk == x.C / 32 && V.B == x.B,
              CS_ERR_INVALID, "wino_in: unsupported geometry");
+  CS_REQUIRE(act_is_leaky(pact), CS_ERR_INVALID, "wino_in: activation must be none / relu / leaky relu");
   const long tiles = (long)x.B * (x.H / 2) * (x.W / 2);
   long blocks = tiles; if (blocks > 148L * 16) blocks = 148L * 16;
   ProfScope ps(L, PK_CONV_TC, 0.0, (double)x.pixels() * x.C * 4.0 + (double)x.pixels() * x.C * 4.0 * 4.0, "wino_in");   // part of the conv
