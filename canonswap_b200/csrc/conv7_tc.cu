@@ -82,10 +82,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // pair mode: the two-CTA allocation protocol writes to the peer's shared memory -- the peer must be running (conv_tc.cu)
+  if constexpr (CTAS == 2) cluster_sync_all();
   if (warp == 1) {
     if constexpr (CTAS == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -105,6 +106,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
   tc_fence_before();
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();    // barriers + zeroed accumulators of BOTH CTAs
   tc_fence_after();
+  if constexpr (CTAS == 2) {
+    if (warp == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ===== TMA producer =====

@@ -70,7 +70,7 @@ __device__ __forceinline__ void bt4(const float4& a, const float4& b, const floa
 // channels).  MASK: the 3x3 neighbourhoods of the tile's four pixels are exactly the 4x4 patch held in registers, so the
 // 512 -> 1 mask conv of AdaptiveSharedWeightConv2d (adaptive_modulate.py:173-180) is computed here as well: per-thread
 // partial dot products, shuffle + shared-memory reduction over the block (fixed order: deterministic), sigmoid.
-template <bool MASK, int MINB>
+template <bool MASK, int MINB, bool PRE>
 __global__ void __launch_bounds__(128, MINB) wino_in_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ V, int B, int H, int W,
                                                       int C, const float* __restrict__ mw /*[9][C]*/, const float* __restrict__ mb,
                                                       float* __restrict__ mask /*[B,H,W]*/, const float* __restrict__ pscale,
@@ -84,7 +84,6 @@ __global__ void __launch_bounds__(128, MINB) wino_in_kernel(const float* __restr
   // pads the TRANSFORMED tensor, so out-of-bounds elements stay zero
   float4 psc = make_float4(1.f, 1.f, 1.f, 1.f), psh = make_float4(0.f, 0.f, 0.f, 0.f);
   if (pscale) { psc = __ldg(reinterpret_cast<const float4*>(pscale + c)); psh = __ldg(reinterpret_cast<const float4*>(pshift + c)); }
-  const bool pre = pscale != nullptr || pact != ACT_NONE;
   const float ps = leaky_slope(pact, pslope);
   for (long t0 = blockIdx.x; t0 < tiles; t0 += gridDim.x) {
     long t = t0;
@@ -99,7 +98,7 @@ __global__ void __launch_bounds__(128, MINB) wino_in_kernel(const float* __restr
         const int iw = 2 * tx - 1 + q;
         const bool in = ih >= 0 && ih < H && iw >= 0 && iw < W;
         d[r][q] = in ? *reinterpret_cast<const float4*>(x + (((long)b * H + ih) * W + iw) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pre && in) {
+        if (PRE && in) {
           d[r][q].x = apply_leaky(fmaf(d[r][q].x, psc.x, psh.x), ps); d[r][q].y = apply_leaky(fmaf(d[r][q].y, psc.y, psh.y), ps);
           d[r][q].z = apply_leaky(fmaf(d[r][q].z, psc.z, psh.z), ps); d[r][q].w = apply_leaky(fmaf(d[r][q].w, psc.w, psh.w), ps);
         }
@@ -366,14 +365,19 @@ void wino_in(const Launcher& L, const Act& x, Opd V, const ConvW* mask_conv, flo
   ProfScope ps(L, PK_CONV_TC, 0.0, (double)x.pixels() * x.C * 4.0 + (double)x.pixels() * x.C * 4.0 * 4.0, "wino_in");   // part of the conv
   CS_REQUIRE(x.C / 4 <= 128, CS_ERR_INVALID, "wino_in: at most 512 channels");
   // 6 resident blocks of 128 threads per SM (80 registers, a few spilled words): measured 3.95 -> 3.59 ms per step against 4 blocks
+  const bool pre = pscale != nullptr || pact != ACT_NONE;     // compile-time in the kernel: the plain form carries none of its code
   if (mask_conv) {
     CS_REQUIRE(mask && mask_conv->w32 && mask_conv->Cin == x.C && mask_conv->Cout == 1 && mask_conv->KD == 1 && mask_conv->KH == 3 &&
-                   mask_conv->KW == 3 && mask_conv->bias, CS_ERR_INVALID, "wino_in: bad mask conv");
-    wino_in_kernel<true, 6><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, mask_conv->w32, mask_conv->bias, mask,
-                                                                        pscale, pshift, pact, pslope, V.amul);
+                   mask_conv->KW == 3 && mask_conv->bias && !pre, CS_ERR_INVALID, "wino_in: bad mask conv");
+    // 5 resident blocks (96 registers, no spills): 6 blocks (80 registers) spill 150 B per thread here -- measured 1.41 -> 1.14 ms per step
+    wino_in_kernel<true, 5, false><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, mask_conv->w32, mask_conv->bias,
+                                                                               mask, nullptr, nullptr, ACT_NONE, 0.f, V.amul);
+  } else if (pre) {
+    wino_in_kernel<false, 6, true><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, nullptr, nullptr, nullptr, pscale,
+                                                                               pshift, pact, pslope, V.amul);
   } else {
-    wino_in_kernel<false, 6><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, nullptr, nullptr, nullptr, pscale,
-                                                                         pshift, pact, pslope, V.amul);
+    wino_in_kernel<false, 6, false><<<(unsigned)blocks, x.C / 4, 0, L.stream>>>(x.p, V.p, x.B, x.H, x.W, x.C, nullptr, nullptr, nullptr, nullptr,
+                                                                                nullptr, ACT_NONE, 0.f, V.amul);
   }
   check_launch("wino_in");
 }

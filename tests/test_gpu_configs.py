@@ -8,6 +8,10 @@
 Every comparison is the CUDA path through the C ABI against the CPU oracle on the same seeded inputs; the bar is the
 absolute 1e-3 max-abs on the [0,1] image (BASELINE.json north_star).
 """
+import os
+import sys
+import time
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -207,3 +211,41 @@ def test_conv7_signed_error():
         assert abs(bias) <= 2.5e-7 and rms <= 2.0e-6, (bias, rms)      # measured +3.6e-8 / 1.2e-6
     finally:
         eng.close()
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes", [2, 4])
+def test_lane_replay_stress_no_deadlock(synth_w, lanes):
+    """Back-to-back replays of the multi-lane graph (what bench.py's timed loop does).  Regression test of a deadlock of the
+    pair-mode kernels: tcgen05.alloc.cta_group::2 talks to the peer CTA's shared memory and used to be issued before the peer
+    was known to be running -- with two lanes competing for registers the peer could start late, miss the message and spin
+    forever (one replay in ~10 hung).  The watchdog turns a hang into a failure: a replay takes ~50 ms."""
+    import threading
+    from canonswap_b200.engine import Engine
+    B, hw = 8, 256
+    inp = synth.synth_inputs(B, hw)
+    eng = Engine(synth_w, net_hw=(hw, hw), max_batch=B, device=0)
+    try:
+        eng.set_identity(inp["source_id"].cuda())
+        fr, xt, xc = inp["frames"].cuda(), inp["x_t"].cuda(), inp["x_can"].cuda()
+        eng.set_option(_lib.CS_OPT_USE_GRAPH, 1)
+        eng.set_option(_lib.CS_OPT_LANES, lanes)
+        u8 = torch.empty(B, 2 * hw, 2 * hw, 3, dtype=torch.uint8, device="cuda")
+        first = None
+        done = torch.cuda.Event()
+        for _ in range(40):
+            eng.frame(fr, xt, xc, out_u8=u8)
+            if first is None:
+                first = u8.clone()
+        done.record()
+        t0 = time.time()
+        while not done.query():
+            if time.time() - t0 > 60.0:
+                # a hung GPU cannot be torn down from this process: leave at once instead of blocking in cudaFree
+                sys.stderr.write("FAILED: multi-lane graph replay did not finish within 60 s (deadlock)\n")
+                sys.stderr.flush()
+                os._exit(70)
+            time.sleep(0.05)
+        assert torch.equal(u8, first)
+    finally:
+        eng.close()
+
