@@ -85,11 +85,11 @@ __global__ void __launch_bounds__(256) prep_kernel_v4(PrepK k) {
   const int C4 = k.Cout >> 2;
   const long total = (long)k.B * k.D * k.H * k.W * C4;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C4) * 4;
-    const long pix = idx / C4;
-    const int w = (int)(pix % k.W); long t = pix / k.W;
-    const int h = (int)(t % k.H); t /= k.H;
-    const int d = (int)(t % k.D); const int b = (int)(t / k.D);
+    const unsigned ui = (unsigned)idx, pix = ui / (unsigned)C4;      // 32-bit divisions (total < 2^32: host check)
+    const int c = (int)(ui - pix * (unsigned)C4) * 4;
+    const unsigned t1 = pix / (unsigned)k.W, t2 = t1 / (unsigned)k.H;
+    const int w = (int)(pix - t1 * (unsigned)k.W), h = (int)(t1 - t2 * (unsigned)k.H);
+    const int b = (int)(t2 / (unsigned)k.D), d = (int)(t2 - (unsigned)b * (unsigned)k.D);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < k.Cl) {
       if (c < k.C0) {
@@ -273,6 +273,7 @@ static void launch_prep(const Launcher& L, PrepK& k) {
   } else if (prep_vec_ok(k)) {
     long blocks = (total / 4 + 255) / 256;
     if (blocks > 148L * 16) blocks = 148L * 16;
+    CS_REQUIRE(total / 4 < (1L << 31), -1, "prep: tensor too large for the 32-bit index math of prep_kernel_v4");
     prep_kernel_v4<<<(unsigned)blocks, 256, 0, L.stream>>>(k);
   } else {
     long blocks = (total + 255) / 256;

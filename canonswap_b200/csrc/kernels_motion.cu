@@ -101,23 +101,33 @@ void dm_input(const Launcher& L, const Act& c4, const float* kp_driving, const f
 
 // The same tensor written directly as the split-fp16 operand [pixel][4 blocks][hi 32 | lo 32] (channels 110..127 zero) of the
 // two convs that consume it (hourglass conv0 and, as blocks 1..4 of its 142-channel input, the hourglass' last conv): no fp32
-// copy of the 110-channel tensor, no prep passes.  One warp per voxel: lanes 0..K compute keypoint k's 5 channels into shared
-// memory, then every lane splits 4 channels and the warp writes 4 full 128-byte rows.
+// copy of the 110-channel tensor, no prep passes.
+// A block takes 32 consecutive voxels (adjacent in w).  Phase 1: a warp = one keypoint x the 32 voxels -- the motion of a
+// keypoint is a pure translation, so the 32 lanes gather 32 ADJACENT float4 of the compressed feature per corner (4..5 lines
+// instead of the 32 lines of the one-warp-per-voxel form) and leave their 5 channels in a shared tile [32][128 + 4].
+// Phase 2: a warp per voxel splits 4 channels per lane and writes 4 full 128-byte rows.
+constexpr int DMI_VOX = 32, DMI_LD = 132;
+
 __global__ void __launch_bounds__(256) dm_input_operand_kernel(const float4* __restrict__ c4, const float* __restrict__ kpd,
                                                                const float* __restrict__ kps, int K, int B, int D, int H, int W,
                                                                __nv_bfloat16* __restrict__ out, long prow, float amul) {
-  __shared__ float vals[8][128];
+  __shared__ __align__(16) float vals[DMI_VOX * DMI_LD];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long nvox = (long)B * D * H * W;
-  for (long pix = (long)blockIdx.x * 8 + wid; pix < nvox; pix += (long)gridDim.x * 8) {
-    int w = (int)(pix % W); long t = pix / W; int h = (int)(t % H); t /= H; int d = (int)(t % D); int b = (int)(t / D);
+  for (int i = threadIdx.x; i < DMI_VOX * DMI_LD; i += 256) vals[i] = 0.f;        // channels 110..127 stay zero
+  const int items = (K + 1) * DMI_VOX;
+  for (long v0 = (long)blockIdx.x * DMI_VOX; v0 < nvox; v0 += (long)gridDim.x * DMI_VOX) {
+    __syncthreads();                                       // the previous tile has been written out (and the zero fill)
+    // a thread keeps the same voxel (lane) for all its keypoints: decode it once, with 32-bit divisions
+    const unsigned upix = (unsigned)v0 + (unsigned)lane;
+    const unsigned t1 = upix / (unsigned)W, t2 = t1 / (unsigned)H;
+    const int w = (int)(upix - t1 * (unsigned)W), h = (int)(t1 - t2 * (unsigned)H);
+    const int b = (int)(t2 / (unsigned)D), d = (int)(t2 - (unsigned)b * (unsigned)D);
     float gx, gy, gz;
     grid_xyz(d, h, w, D, H, W, gx, gy, gz);
-    float* vv = vals[wid];
-    for (int i = lane; i < 128; i += 32) vv[i] = 0.f;
-    __syncwarp();
-    if (lane <= K) {
-      const int k = lane;
+    for (int it = threadIdx.x; it < items; it += 256) {
+      const int k = it >> 5;
+      if (v0 + lane >= nvox) break;
       float mx = gx, my = gy, mz = gz, heat = 0.f;
       if (k > 0) {
         const float* pd = kpd + ((long)b * K + (k - 1)) * 3;
@@ -143,17 +153,23 @@ __global__ void __launch_bounds__(256) dm_input_operand_kernel(const float4* __r
               acc.x += v.x * wt; acc.y += v.y * wt; acc.z += v.z * wt; acc.w += v.w * wt;
             }
           }
-      float* o = vv + k * 5;
+      float* o = vals + (it & 31) * DMI_LD + k * 5;
       o[0] = heat; o[1] = acc.x; o[2] = acc.y; o[3] = acc.z; o[4] = acc.w;
     }
-    __syncwarp();
+    __syncthreads();
     const int c = lane * 4;
-    uint2 hv, lv;
-    split_operand4(vv[c] * amul, vv[c + 1] * amul, vv[c + 2] * amul, vv[c + 3] * amul, hv, lv);
-    __nv_bfloat16* o = out + pix * prow + (c >> 5) * 64 + (c & 31);
-    *reinterpret_cast<uint2*>(o) = hv;
-    *reinterpret_cast<uint2*>(o + 32) = lv;
-    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < DMI_VOX / 8; ++q) {
+      const int v = wid + 8 * q;
+      const long pix = v0 + v;
+      if (pix >= nvox) continue;
+      const float4 f = *reinterpret_cast<const float4*>(vals + v * DMI_LD + c);
+      uint2 hv, lv;
+      split_operand4(f.x * amul, f.y * amul, f.z * amul, f.w * amul, hv, lv);
+      __nv_bfloat16* o = out + pix * prow + (c >> 5) * 64 + (c & 31);
+      *reinterpret_cast<uint2*>(o) = hv;
+      *reinterpret_cast<uint2*>(o + 32) = lv;
+    }
   }
 }
 
@@ -163,7 +179,8 @@ void dm_input_operand(const Launcher& L, const Act& c4, const float* kp_driving,
   CS_REQUIRE(c4.C == 4 && c4.sw == 4 && (K + 1) * 5 <= 128 && K < 32 && out.nblk == 4 && out.B == c4.B && out.D == c4.D && out.H == c4.H &&
                  out.W == c4.W, -1, "dm_input_operand: bad geometry");
   const long nvox = c4.pixels();
-  long blocks = (nvox + 7) / 8; if (blocks > 148L * 32) blocks = 148L * 32;
+  CS_REQUIRE(nvox < (1L << 31), -1, "dm_input_operand: volume too large for 32-bit index math");
+  long blocks = (nvox + DMI_VOX - 1) / DMI_VOX; if (blocks > 148L * 8) blocks = 148L * 8;
   ProfScope ps(L, PK_SAMPLE, 0.0, (double)nvox * (4 + 128) * 4.0, "dm_input");
   dm_input_operand_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(reinterpret_cast<const float4*>(c4.p), kp_driving, kp_source, K, c4.B,
                                                                  c4.D, c4.H, c4.W, out.p, out.row(), out.amul);
@@ -216,7 +233,8 @@ __global__ void __launch_bounds__(256) softmax_flow_warp_kernel(const float* __r
     }
     __syncthreads();
     const long pix = v0 + (threadIdx.x >> 3);
-    const int d = (int)(pix % D); long t = pix / D; const int w = (int)(t % W); t /= W; const int h = (int)(t % H);
+    const unsigned up = (unsigned)pix, u1 = up / (unsigned)D, u2 = u1 / (unsigned)W;       // 32-bit divisions
+    const int d = (int)(up - u1 * (unsigned)D), w = (int)(u1 - u2 * (unsigned)W), h = (int)(u2 % (unsigned)H);
     const float* lg = logits + b * lb + d * ld + h * lh + w * lw;
     float gx, gy, gz;
     grid_xyz(d, h, w, D, H, W, gx, gy, gz);
@@ -267,6 +285,7 @@ void softmax_flow_warp(const Launcher& L, const Act& logits, const float* kp_dri
   CS_REQUIRE(logits.D == 16 && logits.C >= K + 1 && K + 1 <= 24 && K <= SFW_MAXK && (logits.H * logits.W) % 2 == 0, -1,
              "softmax_flow_warp: bad logits tensor");
   const long nvox = logits.pixels();
+  CS_REQUIRE(nvox < (1L << 31), -1, "softmax_flow_warp: volume too large for 32-bit index math");
   long blocks = nvox / 32; if (blocks > 148L * 32) blocks = 148L * 32;
   // algorithmic bytes / voxel: 32 ch in + 32 ch out + 22 logits (22.5 MB / sample)
   ProfScope ps(L, PK_SAMPLE, 0.0, (double)logits.pixels() * (32 + 32 + (K + 1)) * 4.0, "flow_warp");
@@ -297,20 +316,24 @@ __global__ void __launch_bounds__(256) grid_sample3d_cl_kernel(const float* __re
 // (b,h); per (z,kh) lane l loads the 7 kw-columns of row w0+l-3 (28 contiguous bytes), lanes 0..5 also rows
 // w0+29..w0+34, and the diagonal sum is formed with shuffles: every Y element is read once.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) occlusion_gather_kernel(const float* __restrict__ Y, const float* __restrict__ bias,
-                                                               float* __restrict__ occ, int B, int D, int H, int W, int ldy) {
-  const int lane = threadIdx.x & 31;
+// One block = 32 consecutive w of one (b,h); warp j takes the depth slices j, j+16, .. and the partial sums of the warps are
+// added in warp order (fixed: deterministic and independent of the batch).
+constexpr int OCC_WARPS = 16;
+
+__global__ void __launch_bounds__(32 * OCC_WARPS) occlusion_gather_kernel(const float* __restrict__ Y, const float* __restrict__ bias,
+                                                                          float* __restrict__ occ, int B, int D, int H, int W, int ldy) {
+  __shared__ float part[OCC_WARPS][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wtiles = (W + 31) / 32;
-  const long warp_id = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (warp_id >= (long)B * H * wtiles) return;
-  const int wt = (int)(warp_id % wtiles); const long r = warp_id / wtiles;
+  const long tile = blockIdx.x;
+  const int wt = (int)(tile % wtiles); const long r = tile / wtiles;
   const int h = (int)(r % H); const int b = (int)(r / H);
   const int w0 = wt * 32;
   const int xa = w0 + lane - 3;                 // row held in v[]
   const int xb = w0 + 32 + lane - 3;            // row held in e[] (lanes 0..5)
   const bool va = xa >= 0 && xa < W, vb = lane < 6 && xb < W;
   float acc = 0.f;
-  for (int z = 0; z < D; ++z) {
+  for (int z = wid; z < D; z += OCC_WARPS) {
     for (int kh = 0; kh < 7; ++kh) {
       const int y = h + kh - 3;
       if (y < 0 || y >= H) continue;            // warp-uniform
@@ -331,8 +354,15 @@ __global__ void __launch_bounds__(256) occlusion_gather_kernel(const float* __re
       }
     }
   }
-  const int w = w0 + lane;
-  if (w < W) occ[((long)b * H + h) * W + w] = 1.f / (1.f + expf(-(acc + (bias ? bias[0] : 0.f))));
+  part[wid][lane] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < OCC_WARPS; ++j) sum += part[j][lane];
+    const int w = w0 + lane;
+    if (w < W) occ[((long)b * H + h) * W + w] = 1.f / (1.f + expf(-(sum + (bias ? bias[0] : 0.f))));
+  }
 }
 
 void occlusion_gather(const Launcher& L, const Act& Y, const float* bias, float* occ) {
@@ -340,9 +370,9 @@ void occlusion_gather(const Launcher& L, const Act& Y, const float* bias, float*
   if (L.dry) return;
   CS_REQUIRE(Y.C >= 49 && Y.sh == (long)Y.W * Y.sw && Y.sd == (long)Y.H * Y.sh && Y.sb == (long)Y.D * Y.sd, -1,
              "occlusion_gather: Y must be dense [B,D,H,W,>=49]");
-  const long warps = (long)Y.B * Y.H * ((Y.W + 31) / 32);
+  const long tiles = (long)Y.B * Y.H * ((Y.W + 31) / 32);
   ProfScope ps(L, PK_SAMPLE, 0.0, (double)Y.pixels() * 49 * 4.0, "occ_gather");
-  occlusion_gather_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, L.stream>>>(Y.p, bias, occ, Y.B, Y.D, Y.H, Y.W, (int)Y.sw);
+  occlusion_gather_kernel<<<(unsigned)tiles, 32 * OCC_WARPS, 0, L.stream>>>(Y.p, bias, occ, Y.B, Y.D, Y.H, Y.W, (int)Y.sw);
   check_launch("occlusion_gather");
 }
 

@@ -86,9 +86,9 @@ __global__ void __launch_bounds__(128, MINB) wino_in_kernel(const float* __restr
   if (pscale) { psc = __ldg(reinterpret_cast<const float4*>(pscale + c)); psh = __ldg(reinterpret_cast<const float4*>(pshift + c)); }
   const float ps = leaky_slope(pact, pslope);
   for (long t0 = blockIdx.x; t0 < tiles; t0 += gridDim.x) {
-    long t = t0;
-    const int tx = (int)(t % Wt); t /= Wt;
-    const int ty = (int)(t % Ht); const int b = (int)(t / Ht);
+    const unsigned t = (unsigned)t0, tq = t / (unsigned)Wt;          // 32-bit divisions (tile counts are checked on the host)
+    const int tx = (int)(t - tq * (unsigned)Wt);
+    const int b = (int)(tq / (unsigned)Ht), ty = (int)(tq - (unsigned)b * (unsigned)Ht);
     float4 d[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -190,9 +190,10 @@ __global__ void __launch_bounds__(256) wino_out_blend_kernel(const float* __rest
   const long total = (long)B * Ht * Wt * 128;
   const long plane = (long)Ht * Wt * 1024;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx & 127) * 4; long t = idx >> 7;
-    const int tx = (int)(t % Wt); t /= Wt;
-    const int ty = (int)(t % Ht); const int b = (int)(t / Ht);
+    const int c = (int)(idx & 127) * 4;
+    const unsigned t = (unsigned)(idx >> 7), tq = t / (unsigned)Wt;
+    const int tx = (int)(t - tq * (unsigned)Wt);
+    const int b = (int)(tq / (unsigned)Ht), ty = (int)(tq - (unsigned)b * (unsigned)Ht);
     const float* mp = Mt + (long)b * 16 * plane + ((long)ty * Wt + tx) * 1024 + c;
     float4 ys[2][2], ym[2][2];
     wino_out4(mp, plane, ys);
@@ -234,8 +235,9 @@ __global__ void __launch_bounds__(256) wino_out_kernel(const float* __restrict__
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
   const float as = leaky_slope(act, slope);
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < per; idx += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C4) * 4; long t = idx / C4;
-    const int tx = (int)(t % Wt); const int ty = (int)(t / Wt);
+    const unsigned ui = (unsigned)idx, t = ui / (unsigned)C4;
+    const int c = (int)(ui - t * (unsigned)C4) * 4;
+    const int ty = (int)(t / (unsigned)Wt), tx = (int)(t - (unsigned)ty * (unsigned)Wt);
     float4 yy[2][2];
     wino_out4(Mt + (long)b * 16 * plane + ((long)ty * Wt + tx) * C + c, plane, yy);
     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -315,6 +317,7 @@ void wino_conv(const Launcher& L, Arena& A, const Act& x, const ConvW& w, const 
   const int C4 = w.Cout / 4;
   const bool stats = st && st->scratch && C4 <= 256 && 256 % C4 == 0 && w.Cout <= 512;
   const long per = (long)V.H * V.W * C4;
+  CS_REQUIRE(per < (1L << 31), CS_ERR_INVALID, "wino_conv: tensor too large for 32-bit index math");
   const long cap = stats ? STATS_MAX_BLOCKS : 512;          // the statistics scratch holds STATS_MAX_BLOCKS partials per sample
   long blocks = (per + 255) / 256; if (blocks > cap) blocks = cap;
   if (!L.dry) {
@@ -361,6 +364,7 @@ void wino_in(const Launcher& L, const Act& x, Opd V, const ConvW* mask_conv, flo
              CS_ERR_INVALID, "wino_in: unsupported geometry");
   CS_REQUIRE(act_is_leaky(pact), CS_ERR_INVALID, "wino_in: activation must be none / relu / leaky relu");
   const long tiles = (long)x.B * (x.H / 2) * (x.W / 2);
+  CS_REQUIRE(tiles < (1L << 31), CS_ERR_INVALID, "wino_in: tensor too large for 32-bit index math");
   long blocks = tiles; if (blocks > 148L * 16) blocks = 148L * 16;
   ProfScope ps(L, PK_CONV_TC, 0.0, (double)x.pixels() * x.C * 4.0 + (double)x.pixels() * x.C * 4.0 * 4.0, "wino_in");   // part of the conv
   CS_REQUIRE(x.C / 4 <= 128, CS_ERR_INVALID, "wino_in: at most 512 channels");
@@ -387,6 +391,7 @@ void wino_out_blend(const Launcher& L, const float* Mt, const float* mask, const
   L.count();
   if (L.dry) return;
   const long total = (long)B * (H / 2) * (W / 2) * 128;
+  CS_REQUIRE(total < (1L << 31), CS_ERR_INVALID, "wino_out_blend: tensor too large for 32-bit index math");
   long blocks = (total + 255) / 256; if (blocks > 148L * 16) blocks = 148L * 16;
   ProfScope ps(L, PK_CONV_TC, 0.0, (double)B * H * W * (4.0 * 1024 + 512 + (residual ? 512 : 0)) * 4.0, "wino_out_blend");
   wino_out_blend_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(Mt, mask, bias_mod, residual, relu, y, B, H, W);
