@@ -29,11 +29,13 @@ struct PrepK {
 __global__ void __launch_bounds__(256) prep_kernel(PrepK k) {
   long total = (long)k.B * k.D * k.H * k.W * k.Cout;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    int c = (int)(idx % k.Cout);
-    long pix = idx / k.Cout;
-    int w = (int)(pix % k.W); long t = pix / k.W;
-    int h = (int)(t % k.H); t /= k.H;
-    int d = (int)(t % k.D); int b = (int)(t / k.D);
+    // 32-bit divisions (total < 2^32: host check); a 64-bit division costs ~100 instructions
+    const unsigned ui = (unsigned)idx, upix = ui / (unsigned)k.Cout;
+    const int c = (int)(ui - upix * (unsigned)k.Cout);
+    const long pix = upix;
+    const unsigned t1 = upix / (unsigned)k.W, t2 = t1 / (unsigned)k.H;
+    const int w = (int)(upix - t1 * (unsigned)k.W), h = (int)(t1 - t2 * (unsigned)k.H);
+    const int b = (int)(t2 / (unsigned)k.D), d = (int)(t2 - (unsigned)b * (unsigned)k.D);
     float v = 0.f;
     if (c < k.Cl) {
       if (c < k.C0) {
@@ -278,6 +280,7 @@ static void launch_prep(const Launcher& L, PrepK& k) {
   } else {
     long blocks = (total + 255) / 256;
     if (blocks > 148L * 32) blocks = 148L * 32;
+    CS_REQUIRE(total < (1L << 31), -1, "prep: tensor too large for the 32-bit index math of prep_kernel");
     prep_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(k);
   }
   check_launch("prep");

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) dm_input_operand_kernel(const float4* __r
             int x = tr.x0 + cx, y = tr.y0 + cy, z = tr.z0 + cz;
             if (x >= 0 && x < W && y >= 0 && y < H && z >= 0 && z < D) {
               float wt = tr.w[cz * 4 + cy * 2 + cx];
-              float4 v = c4[(((long)b * D + z) * H + y) * W + x];
+              float4 v = c4[((b * D + z) * H + y) * W + x];                 // < 2^31 voxels (host check)
               acc.x += v.x * wt; acc.y += v.y * wt; acc.z += v.z * wt; acc.w += v.w * wt;
             }
           }
