@@ -52,6 +52,7 @@ struct ConvTcK {
   const float* mult;
   float* y; long yb, yd, yh, yw;               // may be null when only the operand is emitted
   int vec4;
+  int plain;                       // no bias / activation / residual / multiplier / emission: the rows are copied out as they are
   // optional: also write act(v * escale[n] + eshift[n]) as the split-fp16 operand of the next conv (dense, output geometry)
   __nv_bfloat16* emit; int erow; const float* escale; const float* eshift; int eact; float eslope; float emul;
   // SPADE epilogue (see Epilogue::sp_x)
@@ -361,13 +362,16 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
     for (int c0 = eg * 32; c0 < k.BN; c0 += 32 * egroups) {
       ++cidx;
       if (n0 + c0 >= k.Cout) break;                         // warp-uniform
+      uint32_t vv[2][16];                                   // both halves of the chunk in flight before one wait
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+        if (c0 + 16 * half < k.BN) tc_ld16(trow + (uint32_t)(c0 + 16 * half) + (uint32_t)(corr * k.BN), vv[half]);
+      tc_ld_wait();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         if (c0 + 16 * half < k.BN) {                        // warp-uniform (BN is a multiple of 16)
-          uint32_t v[16];
+          uint32_t* v = vv[half];
           const uint32_t tcol = trow + (uint32_t)(c0 + 16 * half);
-          tc_ld16(tcol + (uint32_t)(corr * k.BN), v);
-          tc_ld_wait();
           if constexpr (BCOMP) {
             const float f0 = set_factor(0);
 #pragma unroll
@@ -442,6 +446,20 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
         }
         __syncwarp();
         continue;
+      }
+      if constexpr (!RES && !EMIT) {
+        // plain GEMM output (the Winograd GEMMs, whose tile period is set by these warps: ncu showed them 91 % busy with ~70
+        // instructions per row quad in the generic path below): 32 full columns -> one LDS.128 + one STG.128 per row
+        if (k.plain && c0 + 32 <= k.BN && n0 + c0 + 32 <= k.Cout) {     // warp-uniform
+          const int ncp = n0 + c0 + c4 - chan0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!((vmask >> i) & 1u)) continue;
+            *reinterpret_cast<float4*>(k.y + yoff[i] + ncp) = *reinterpret_cast<const float4*>(tile + (sub + 4 * i) * STG_LD + c4);
+          }
+          __syncwarp();
+          continue;
+        }
       }
       const int n = n0 + c0 + c4;
       if (c0 + c4 < k.BN && n < k.Cout) {
@@ -803,6 +821,8 @@ void conv_tc(const Launcher& L, const Opd& x, const ConvW& w, const ConvGeom& g,
   auto al4 = [](long v) { return (v & 3) == 0; };
   k.vec4 = al4(y.sb) && al4(y.sd) && al4(y.sh) && al4(y.sw) && ((uintptr_t)y.p % 16 == 0) &&
            (!e.residual || (al4(e.rs_b) && al4(e.rs_d) && al4(e.rs_h) && al4(e.rs_w) && ((uintptr_t)e.residual % 16 == 0)));
+
+  k.plain = k.vec4 && y.p && !w.bias && e.act == ACT_NONE && !e.residual && !e.mult && !e.emit && !e.sp_x;
 
   const unsigned m_tiles = (unsigned)(k.ntw * k.nth * k.ntd * ntb);
   // tcgen05 pair mode (cta_group::2): wide N tiles, an even number of M tiles, weights shared by the pair.  The kernel is
