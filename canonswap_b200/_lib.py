@@ -55,11 +55,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB):
+    # CANONSWAP_B200_LIB: another build of the SAME library (same-box A/B measurements); never a different implementation
+    path = os.environ.get("CANONSWAP_B200_LIB", LIB)
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB} is missing. canonswap_b200 has no CPU / PyTorch fallback: build the CUDA library first "
+            f"{path} is missing. canonswap_b200 has no CPU / PyTorch fallback: build the CUDA library first "
             "(python -m canonswap_b200._build, or __graft_entry__.build()).")
-    lib = C.CDLL(LIB)
+    lib = C.CDLL(path)
     p, i, f, vp = C.c_void_p, C.c_int, C.c_float, C.c_void_p
     lib.cs_create.argtypes = [C.POINTER(vp), i, i, i, i]
     lib.cs_destroy.argtypes = [vp]

@@ -331,9 +331,11 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
           asm volatile("prefetch.global.L2 [%0];" ::"l"(k.res + roff[i] + n0 + c));
       }
     }
-    // SPADE: the normalised input x_hat = (x - mean) * rstd of every chunk this warp will emit does not depend on the
-    // accumulators: it is gathered into registers here, i.e. while the MMAs of the tile are still running
-    // (<= 4 chunks per warp: 2 epilogue groups for BN > 64, checked by the host)
+    // SPADE: the input x of every chunk this warp will emit does not depend on the accumulators: it is gathered into
+    // registers here, i.e. while the MMAs of the tile are still running (<= 4 chunks per warp: 2 epilogue groups for
+    // BN > 64, checked by the host).  Only the x loads are issued here -- 16 independent 16-byte loads in flight; the
+    // (L1-resident) statistics are read and x_hat = (x - mean) * rstd is formed per row after the accumulator wait
+    // (ncu: with the three dependent loads per row in this place the epilogue warps spent half their time stalled on them).
     float4 xh[SPADE ? 4 : 1][SPADE ? 4 : 1];
     if constexpr (SPADE) {
       const int cc = (lane & 3) * 4;
@@ -345,12 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           xh[ci][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live && ((vmask >> i) & 1u)) {
-            const float4 xv = *reinterpret_cast<const float4*>(k.sp_x + xoff[i] + ch);
-            const float4 mn = __ldg(reinterpret_cast<const float4*>(k.sp_mean + sbase[i] + ch));
-            const float4 rs = __ldg(reinterpret_cast<const float4*>(k.sp_rstd + sbase[i] + ch));
-            xh[ci][i] = make_float4((xv.x - mn.x) * rs.x, (xv.y - mn.y) * rs.y, (xv.z - mn.z) * rs.z, (xv.w - mn.w) * rs.w);
-          }
+          if (live && ((vmask >> i) & 1u)) xh[ci][i] = *reinterpret_cast<const float4*>(k.sp_x + xoff[i] + ch);
         }
       }
     }
@@ -426,12 +423,15 @@ __global__ void __launch_bounds__(TC_THREADS_MAX) conv_tc_kernel(const __grid_co
         for (int i = 0; i < 4; ++i) {
           if (!((vmask >> i) & 1u)) continue;
           const float* trp = tile + (sub + 8 * i) * STG_LD;
+          const float4 mn = __ldg(reinterpret_cast<const float4*>(k.sp_mean + sbase[i] + ch));
+          const float4 rs = __ldg(reinterpret_cast<const float4*>(k.sp_rstd + sbase[i] + ch));
           const float4 g = *reinterpret_cast<const float4*>(trp + cc);
           const float4 bt = *reinterpret_cast<const float4*>(trp + 16 + cc);
-          float v0 = xv[i].x * (1.f + (g.x + bg.x)) + (bt.x + bb.x);
-          float v1 = xv[i].y * (1.f + (g.y + bg.y)) + (bt.y + bb.y);
-          float v2 = xv[i].z * (1.f + (g.z + bg.z)) + (bt.z + bb.z);
-          float v3 = xv[i].w * (1.f + (g.w + bg.w)) + (bt.w + bb.w);
+          const float4 xn = make_float4((xv[i].x - mn.x) * rs.x, (xv[i].y - mn.y) * rs.y, (xv[i].z - mn.z) * rs.z, (xv[i].w - mn.w) * rs.w);
+          float v0 = xn.x * (1.f + (g.x + bg.x)) + (bt.x + bb.x);
+          float v1 = xn.y * (1.f + (g.y + bg.y)) + (bt.y + bb.y);
+          float v2 = xn.z * (1.f + (g.z + bg.z)) + (bt.z + bb.z);
+          float v3 = xn.w * (1.f + (g.w + bg.w)) + (bt.w + bb.w);
           v0 = apply_leaky(v0, easlope); v1 = apply_leaky(v1, easlope);
           v2 = apply_leaky(v2, easlope); v3 = apply_leaky(v3, easlope);
           if (k.emit) {
