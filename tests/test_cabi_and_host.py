@@ -41,6 +41,17 @@ def test_no_gpu_means_loud_failure_not_fallback(lib):
         Engine({}, net_hw=(256, 256))
 
 
+def test_missing_library_fails_loudly(tmp_path):
+    """The product path has no fallback: a missing libcanonswap_b200.so (here: CANONSWAP_B200_LIB pointing at a path that does
+    not exist, in a fresh interpreter) must raise, naming the file and the build command."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CANONSWAP_B200_LIB=str(tmp_path / "absent.so"))
+    code = "from canonswap_b200 import _lib\ntry:\n    _lib.load()\nexcept RuntimeError as e:\n    print('RAISED', e)\n"
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert "RAISED" in out.stdout and "absent.so" in out.stdout and "no CPU / PyTorch fallback" in out.stdout, out.stdout + out.stderr
+
+
 def test_create_rejects_bad_arguments(lib):
     import ctypes as C
     ctx = C.c_void_p()
