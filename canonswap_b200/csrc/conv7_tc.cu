@@ -30,12 +30,16 @@ constexpr int C7_COUT_P = 24;                    // 22 -> 24 columns per output 
 constexpr int C7_GROUP = 8;                      // output depths per CTA
 constexpr int C7_BROWS = 7 * C7_COUT_P + 8;      // 176 B rows per filter position (kh,kw): 7 depth slots + 8 zero rows
 // CTAS = 1: 5 stages of A (16 KB) + B (22 KB).  CTAS = 2 (tcgen05 pair, two pixel tiles share the weights): each CTA holds
-// half of the B rows, 7 stages of 16 + 11 KB.
+// half of the B rows, 8 stages of 16 + 11 KB.  The kernel is paced by the bytes it keeps in flight (a slot is refilled only
+// after its MMAs have completed), so in pair mode the epilogue's staging tile does not get its own
+// shared memory: it reuses stage 0, which is idle once the last MMA has completed (tmem_full), and the 18 KB buy an 8th stage.
 template <int CTAS> struct C7Cfg {
   static constexpr int BROWS = C7_BROWS / CTAS;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + BROWS * 128;
-  static constexpr int STAGES = CTAS == 2 ? 7 : 5;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 16 * STAGES + 32;
+  static constexpr int STAGES = CTAS == 2 ? 8 : 5;
+  static constexpr bool STG_IN_STAGE0 = CTAS == 2;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + (STG_IN_STAGE0 ? 0 : STG_BYTES) + 1024 + 16 * STAGES + 32;
+  static_assert(STG_BYTES <= STAGE_BYTES, "the staging tile must fit into one stage");
 };
 
 struct Conv7K {
@@ -61,8 +65,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv7_tc_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t stg = base + (uint32_t)C7_STAGES * C7_STAGE_BYTES;
-  const uint32_t bars = stg + STG_BYTES;
+  const uint32_t stg = C7Cfg<CTAS>::STG_IN_STAGE0 ? base : base + (uint32_t)C7_STAGES * C7_STAGE_BYTES;
+  const uint32_t bars = base + (uint32_t)C7_STAGES * C7_STAGE_BYTES + (C7Cfg<CTAS>::STG_IN_STAGE0 ? 0u : (uint32_t)STG_BYTES);
   const uint32_t tmem_full = bars + 16u * C7_STAGES;
   const uint32_t tmem_slot = tmem_full + 8u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
